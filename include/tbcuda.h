@@ -1,0 +1,208 @@
+/*
+ * tbcuda.h -- C ABI of libtbcuda.so, the B200 (sm_100a) engine behind the tropical-contraction hot
+ * path of TensorBranching.jl.
+ *
+ * The library stands where the reference's
+ *     solve_slice(branch, element_type, usecuda)        /root/reference/src/dynamic_ob.jl:30-34
+ *     contract_slices(branches, element_type, usecuda)  /root/reference/src/dynamic_ob.jl:36-48
+ * stand today (callers: dynamic_ob_mis src/dynamic_ob.jl:24, slice_dfs_lp src/slice.jl:39, user code
+ * after load_all_finished src/io.jl:113-121).  The reference has no FFI of its own for this path (it
+ * calls GenericTensorNetworks.solve in-process); INTEGRATION.md shows the Julia `ccall` stubs a
+ * maintainer would add.  Every entry point below names the reference behaviour it replaces.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the ABI; every function returning int returns a tb_status
+ *     (0 = ok, negative = error); the message is available from tb_last_error().
+ *   - all ids are 0-based.  Inputs are caller-owned and only read during the call (they are copied
+ *     by tb_plan_create).  Handles are library-owned and freed only by the matching destroy call.
+ *     Outputs go to caller-allocated buffers.  Device memory never crosses the ABI.
+ *   - one tb_ctx is used from one host thread at a time; calls block until results are on the host.
+ *     Distinct contexts are independent.  The library installs no signal handlers and owns no thread
+ *     that outlives the call that spawned it.
+ *   - a tensor "layout" is a list of labels in address-bit order, bit 0 (fastest) first -- i.e.
+ *     Julia's column-major dimension order.  Every label has size 2 (uniformsize(code, 2),
+ *     /root/reference/src/types.jl:118).
+ */
+#ifndef TBCUDA_H
+#define TBCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb_ctx tb_ctx;
+typedef struct tb_plan tb_plan;
+
+typedef enum tb_status {
+    TB_OK = 0,
+    TB_ERR_BAD_ARGUMENT = -1,
+    TB_ERR_NOT_BINARY_TREE = -2,   /* tree arrays do not describe a binary tree over the leaves */
+    TB_ERR_UNSUPPORTED = -3,       /* leaf rank > 2, tensor rank > 31, value range too large ... */
+    TB_ERR_OUT_OF_MEMORY = -4,
+    TB_ERR_CUDA = -5,              /* no usable device / a CUDA call failed; there is NO CPU fallback */
+    TB_ERR_NCCL = -6,
+    TB_ERR_INTERNAL = -7
+} tb_status;
+
+/* value types of the tropical numbers (element_type of the reference, src/dynamic_ob.jl:6) */
+typedef enum tb_value_type {
+    TB_VALUE_AUTO = 0,   /* i32 for unit / integer weights, f32 otherwise */
+    TB_VALUE_I32 = 1,    /* exact; -inf is the sentinel -2^30 */
+    TB_VALUE_F32 = 2,    /* Tropical{Float32}; -inf is IEEE -inf */
+    TB_VALUE_I16X2 = 3   /* packed pairs; requires sum of weights < 2^13 (reserved) */
+} tb_value_type;
+
+typedef enum tb_weight_dtype {
+    TB_WEIGHT_UNIT = 0,  /* UnitWeight: weights pointer ignored, every vertex weighs 1 */
+    TB_WEIGHT_I32 = 1,
+    TB_WEIGHT_I64 = 2,
+    TB_WEIGHT_F32 = 3,
+    TB_WEIGHT_F64 = 4
+} tb_weight_dtype;
+
+/* plan flags */
+#define TB_PLAN_KEEP_INTERMEDIATES 1u /* every node gets its own arena region (no reuse) so that
+                                         tb_plan_read_tensor can return it after tb_contract */
+#define TB_PLAN_NO_FUSED_SUBTREES 2u  /* testing: run every node as its own step */
+#define TB_PLAN_NO_GEMM 4u            /* testing: never choose the tiled max-plus GEMM kernel */
+#define TB_PLAN_SCRAMBLE_LAYOUT 8u    /* testing: pseudo-random (valid) operand layouts */
+
+typedef struct tb_options {
+    int32_t device;          /* CUDA device ordinal */
+    int32_t reserved0;
+    int64_t arena_bytes;     /* HBM arena for intermediates; 0 = 60 % of free memory at first use */
+    int32_t max_wave;        /* max branches contracted concurrently (0 = default 256) */
+    int32_t host_threads;    /* plan-compiler threads for the *_networks calls (0 = all cores) */
+    uint32_t plan_flags;     /* default flags OR-ed into every plan */
+    int32_t reserved1;
+} tb_options;
+
+/*
+ * One branch network = what a SlicedBranch carries (src/types.jl:85-103): the leaf label lists
+ * `ixs` and the binary ContractionTree of its CompressedEinsum (src/types.jl:51-58), plus weights.
+ *   leaf i has labels leaf_labels[leaf_off[i] .. leaf_off[i+1]); 1 label = vertex tensor [0, w_v],
+ *   2 labels = edge tensor [[0,0],[0,-inf]] (generate_tensors of IndependentSet [upstream]).
+ *   internal node j (tensor id n_leaves + j) contracts tensor ids node_left[j], node_right[j];
+ *   children always have smaller ids (post-order); the last node is the root.  n_leaves - 1 nodes.
+ *   open_labels (iy) is empty on the solve_slice path; if given, the root keeps those labels.
+ *   weights[v] is the weight of label/vertex v (n_labels entries) unless weight_dtype == UNIT.
+ */
+typedef struct tb_network {
+    int32_t n_labels;
+    int32_t n_leaves;
+    const int32_t* leaf_off;
+    const int32_t* leaf_labels;
+    int32_t n_open;
+    const int32_t* open_labels;
+    const int32_t* node_left;
+    const int32_t* node_right;
+    const void* weights;
+    int32_t weight_dtype;    /* tb_weight_dtype */
+    int32_t value_type;      /* tb_value_type */
+    uint32_t flags;          /* TB_PLAN_* */
+    int32_t reserved;
+} tb_network;
+
+/* what complexity(branch) reports in the reference (src/types.jl:115-121) + engine facts */
+typedef struct tb_plan_stats {
+    double sc;               /* max tensor rank */
+    double tc;               /* log2(sum over nodes of 2^(labels involved)) */
+    double ops;              /* tropical ops = sum over nodes 2^(m+n+k+b) */
+    double algo_bytes;       /* sum over nodes elem_size*(2^rank A + 2^rank B + 2^rank C) */
+    int64_t arena_elems;     /* peak arena footprint in elements */
+    int32_t n_nodes;
+    int32_t n_levels;        /* dependency levels of the non-fused nodes */
+    int32_t n_fused_subtrees;
+    int32_t n_fused_steps;
+    int32_t n_gemm_steps;
+    int32_t n_generic_steps;
+    int32_t value_type;      /* resolved tb_value_type */
+    int32_t root_rank;
+    double gemm_ops;         /* ops carried by the tiled GEMM kernel */
+    double fused_ops;
+    double generic_ops;
+} tb_plan_stats;
+
+/* one exported step (for inspection / the oracle-side plan checker / estimators) */
+typedef struct tb_step_info {
+    int32_t node;            /* tensor id produced */
+    int32_t left, right;     /* operand tensor ids */
+    int32_t kind;            /* 0 fused-subtree step, 1 generic, 2 gemm */
+    int32_t level;
+    int32_t rank_a, rank_b, rank_c;
+    int32_t n_m, n_n, n_b, n_k, n_ka, n_kb;
+    int32_t tile_m, tile_n;
+    int64_t c_offset;        /* arena / smem element offset */
+    int32_t labels_a[32];    /* layouts, bit 0 first */
+    int32_t labels_b[32];
+    int32_t labels_c[32];
+} tb_step_info;
+
+const char* tb_version(void);
+
+/* lifetime of the engine on one device.  Fails with TB_ERR_CUDA when no device is usable. */
+int tb_init(const tb_options* opts, tb_ctx** out_ctx);
+int tb_shutdown(tb_ctx* ctx);
+const char* tb_last_error(const tb_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+
+/* replaces uncompress(branch.code) + GenericTensorNetwork(...) (src/dynamic_ob.jl:31, src/types.jl:75-79):
+ * compiles the tree into a device-resident step list.  ctx may be NULL (host-only compile; the plan is
+ * uploaded on first use). */
+int tb_plan_create(tb_ctx* ctx, const tb_network* net, tb_plan** out_plan);
+int tb_plan_destroy(tb_plan* plan);
+int tb_plan_info(const tb_plan* plan, tb_plan_stats* out);
+/* exports up to `cap` steps in execution order; returns the number of steps (or a negative status) */
+int tb_plan_export(const tb_plan* plan, tb_step_info* out, int32_t cap);
+
+/* raw descriptor sections of a compiled plan, for the test-side descriptor interpreter and for
+ * debugging: which = 0 leaf pool (u32 words), 1 fused steps (48-byte records), 2 fused subtrees
+ * (24-byte records), 3 level steps (144-byte records), 4 level index (i32), 5 header (i64 words:
+ * arena_elems, root_off, n_levels, value_type).  Copies min(cap, size) bytes, returns the size. */
+int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_t cap);
+
+/* replaces solve(net, SizeMax(), T, usecuda)[].n (src/dynamic_ob.jl:32): the root scalar of one plan */
+int tb_contract(tb_ctx* ctx, tb_plan* plan, double* out_value);
+
+/* replaces the loop of contract_slices (src/dynamic_ob.jl:38-46) and maximum(res) (:27).
+ * plans[i] == NULL means "empty graph": the value is r[i] (src/dynamic_ob.jl:39-40).
+ * r may be NULL (all zero).  out_values[i] = value_i + r[i] in double; out_status may be NULL;
+ * out_max may be NULL.  A failed branch gets a negative status and NaN, never a silent wrong max. */
+int tb_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n,
+                      double* out_values, int32_t* out_status, double* out_max);
+
+/* the whole of contract_slices in one call: compile (multi-threaded), upload, contract, discard.
+ * nets[i].n_leaves == 0 means "empty graph". */
+int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n,
+                         double* out_values, int32_t* out_status, double* out_max);
+
+/* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
+ * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */
+int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap,
+                        int32_t* out_labels, int32_t* out_rank);
+
+/* timing of the last tb_contract / tb_contract_batch on this ctx, measured with CUDA events on the
+ * engine's stream: total device ms and number of kernel launches. */
+int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches);
+
+/* run the engine on a caller-owned CUDA stream (cudaStream_t), e.g. the harness's current stream, so
+ * that the caller's events bracket the engine's work.  The stream is not destroyed by tb_shutdown. */
+int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
+
+/* opt-in per-launch CUDA-event timing, accumulated by kernel kind
+ * (0 fused subtrees, 1 generic, 2 tiled max-plus GEMM, 3 finalize) over the last contract call. */
+int tb_profile(tb_ctx* ctx, int enable);
+int tb_last_profile(const tb_ctx* ctx, double* ms_by_kind /*[4]*/, int64_t* launches_by_kind /*[4]*/);
+
+/* host<->device bytes moved by the last contract call (descriptors + work lists up, results down) */
+int tb_last_transfers(const tb_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes);
+
+/* K5: out[dst] = in[src] where bit i of dst is bit perm[i] of src (2^rank elements of 4 bytes),
+ * host buffers; exercises the bit-permutation transpose kernel (OMEinsum permutedims [upstream]). */
+int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const int32_t* perm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBCUDA_H */

@@ -1,0 +1,87 @@
+"""ctypes wrapper of oracle/c/libtropical_ref.so (plain-C + OpenMP restatement; test infrastructure and
+the CPU baseline of bench.py).  Built by __graft_entry__.build()."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "c", "libtropical_ref.so")
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} missing: run __graft_entry__.build()")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.tref_contract_batch.restype = C.c_int
+    return _lib
+
+
+def flatten(branch):
+    """Branch (workloads.standin_host) or tbcuda.SlicedBranch -> (n_labels, leaf_off, leaf_labels, left, right, weights)."""
+    if hasattr(branch, "code"):  # SlicedBranch
+        code = branch.code
+        w = branch.p.weights
+        w = None if not isinstance(w, np.ndarray) else np.ascontiguousarray(w, dtype=np.float64)
+        return (branch.p.nv, code.leaf_off, code.leaf_labels, code.node_left, code.node_right, w)
+    from .tropical_oracle import nested_to_postorder
+    off = np.zeros(len(branch.ixs) + 1, dtype=np.int32)
+    np.cumsum([len(ix) for ix in branch.ixs], out=off[1:])
+    labs = np.asarray([l for ix in branch.ixs for l in ix], dtype=np.int32)
+    left, right = nested_to_postorder(branch.tree, len(branch.ixs)) if len(branch.ixs) > 1 else ([], [])
+    w = None if branch.weights is None else np.ascontiguousarray(branch.weights, dtype=np.float64)
+    return (branch.nv, off, labs, np.asarray(left, dtype=np.int32), np.asarray(right, dtype=np.int32), w)
+
+
+def contract_batch(flat_list):
+    """flat_list: list of flatten() tuples (None for an empty graph).  -> (values float64, ops float64, threads)."""
+    lib = load()
+    n = len(flat_list)
+    ip = C.POINTER(C.c_int32)
+    dp = C.POINTER(C.c_double)
+    nl = (C.c_int32 * max(n, 1))()
+    nv = (C.c_int32 * max(n, 1))()
+    a_off = (ip * max(n, 1))()
+    a_lab = (ip * max(n, 1))()
+    a_l = (ip * max(n, 1))()
+    a_r = (ip * max(n, 1))()
+    a_w = (dp * max(n, 1))()
+    any_w = False
+    keep = []
+    for i, f in enumerate(flat_list):
+        if f is None:
+            nl[i] = 0
+            continue
+        nlab, off, labs, left, right, w = f
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        labs = np.ascontiguousarray(labs, dtype=np.int32)
+        left = np.ascontiguousarray(left, dtype=np.int32)
+        right = np.ascontiguousarray(right, dtype=np.int32)
+        keep += [off, labs, left, right, w]
+        nv[i] = nlab
+        nl[i] = len(off) - 1
+        a_off[i] = off.ctypes.data_as(ip)
+        a_lab[i] = labs.ctypes.data_as(ip)
+        a_l[i] = left.ctypes.data_as(ip)
+        a_r[i] = right.ctypes.data_as(ip)
+        if w is not None:
+            any_w = True
+            a_w[i] = w.ctypes.data_as(dp)
+    vals = np.zeros(n, dtype=np.float64)
+    ops = np.zeros(n, dtype=np.float64)
+    th = lib.tref_contract_batch(n, nv, nl, a_off, a_lab, a_l, a_r, a_w if any_w else None,
+                                 vals.ctypes.data_as(dp), ops.ctypes.data_as(dp))
+    return vals, ops, th
+
+
+def contract_slices(branches, element_type=np.float32):
+    """contract_slices (/root/reference/src/dynamic_ob.jl:36-48) on the C oracle."""
+    flats = [None if b.nv == 0 else flatten(b) for b in branches]
+    vals, _, _ = contract_batch(flats)
+    et = np.dtype(element_type).type
+    return np.asarray([et(b.r) if b.nv == 0 else et(et(v) + et(b.r)) for b, v in zip(branches, vals)], dtype=element_type)

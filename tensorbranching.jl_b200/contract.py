@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's hot-path entry points, backed by libtbcuda.so.
+
+    solve_slice(branch, element_type, usecuda)        /root/reference/src/dynamic_ob.jl:30-34
+    contract_slices(branches, element_type, usecuda)  /root/reference/src/dynamic_ob.jl:36-48
+    complexity / sc / tc                              /root/reference/src/types.jl:115-121
+
+Same names, argument meaning and error behaviour.  `usecuda` is the switch position this library
+occupies: usecuda=False raises (the CPU path is the reference's own TropicalGEMM route, which this
+package deliberately does not contain -- there is no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .types import CompressedEinsum, MISProblem, SlicedBranch, UnitWeight
+
+
+def _weight_desc(weights, n_labels):
+    """-> (keepalive array or None, dtype code)."""
+    if weights is None or isinstance(weights, UnitWeight):
+        return None, L.TB_WEIGHT_UNIT
+    w = np.asarray(weights)
+    if w.shape != (n_labels,):
+        raise ValueError(f"weights has shape {w.shape}, expected ({n_labels},)")
+    if w.dtype == np.float32:
+        return np.ascontiguousarray(w), L.TB_WEIGHT_F32
+    if w.dtype == np.float64:
+        return np.ascontiguousarray(w), L.TB_WEIGHT_F64
+    if w.dtype == np.int32:
+        return np.ascontiguousarray(w), L.TB_WEIGHT_I32
+    if np.issubdtype(w.dtype, np.integer):
+        return np.ascontiguousarray(w, dtype=np.int64), L.TB_WEIGHT_I64
+    return np.ascontiguousarray(w, dtype=np.float64), L.TB_WEIGHT_F64
+
+
+def _value_type_for(element_type, weight_code):
+    """element_type of the reference -> tb_value_type.  Integer-valued problems (UnitWeight / integer
+    weights) are computed exactly in int32 whatever float container is asked for; real weights need
+    Float32 (the only float width the device kernels implement)."""
+    et = np.dtype(element_type) if element_type is not None else None
+    if weight_code in (L.TB_WEIGHT_UNIT, L.TB_WEIGHT_I32, L.TB_WEIGHT_I64):
+        return L.TB_VALUE_I32
+    if et is not None and et == np.float64:
+        raise L.TBError(L.TB_ERR_UNSUPPORTED, "element_type Float64 with real weights is not implemented on the device (use Float32)")
+    return L.TB_VALUE_F32
+
+
+def _network_of(branch: SlicedBranch, element_type, flags=0, keep: Optional[list] = None):
+    code = branch.code
+    net = L.tb_network()
+    net.n_labels = branch.p.nv
+    net.n_leaves = len(code.ixs)
+    net.leaf_off = code.leaf_off.ctypes.data_as(C.POINTER(C.c_int32))
+    net.leaf_labels = code.leaf_labels.ctypes.data_as(C.POINTER(C.c_int32))
+    net.n_open = len(code.open_labels)
+    net.open_labels = code.open_labels.ctypes.data_as(C.POINTER(C.c_int32))
+    net.node_left = code.node_left.ctypes.data_as(C.POINTER(C.c_int32))
+    net.node_right = code.node_right.ctypes.data_as(C.POINTER(C.c_int32))
+    w, wcode = _weight_desc(branch.p.weights, branch.p.nv)
+    if keep is not None and w is not None:
+        keep.append(w)
+    net.weights = w.ctypes.data if w is not None else None
+    net.weight_dtype = wcode
+    net.value_type = _value_type_for(element_type, wcode)
+    net.flags = flags
+    return net, w
+
+
+class Plan:
+    """Compiled, device-resident form of one branch's contraction (tb_plan)."""
+
+    def __init__(self, branch: SlicedBranch, element_type=np.float32, flags=0, engine: "Engine" = None):
+        lib = L.load()
+        self._lib = lib
+        self.handle = C.c_void_p()
+        net, w = _network_of(branch, element_type, flags)
+        self._keep = (branch, w)
+        L.check(lib.tb_plan_create(engine.handle if engine else None, C.byref(net), C.byref(self.handle)),
+                engine.handle if engine else None)
+
+    def info(self) -> L.tb_plan_stats:
+        st = L.tb_plan_stats()
+        L.check(self._lib.tb_plan_info(self.handle, C.byref(st)))
+        return st
+
+    def steps(self) -> List[L.tb_step_info]:
+        n = L.check(self._lib.tb_plan_export(self.handle, None, 0))
+        arr = (L.tb_step_info * max(n, 1))()
+        L.check(self._lib.tb_plan_export(self.handle, arr, n))
+        return list(arr[:n])
+
+    def raw(self, which: int) -> bytes:
+        n = self._lib.tb_plan_export_raw(self.handle, which, None, 0)
+        L.check(int(n))
+        buf = C.create_string_buffer(max(int(n), 1))
+        self._lib.tb_plan_export_raw(self.handle, which, buf, n)
+        return buf.raw[:n]
+
+    def close(self):
+        if self.handle:
+            self._lib.tb_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """tb_ctx: one engine per CUDA device."""
+
+    def __init__(self, device: int = 0, arena_bytes: int = 0, max_wave: int = 0, host_threads: int = 0,
+                 plan_flags: int = 0):
+        lib = L.load()
+        self._lib = lib
+        opts = L.tb_options(device=device, arena_bytes=arena_bytes, max_wave=max_wave,
+                            host_threads=host_threads, plan_flags=plan_flags)
+        self.handle = C.c_void_p()
+        L.check(lib.tb_init(C.byref(opts), C.byref(self.handle)))
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            self._lib.tb_shutdown(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- single plan -------------------------------------------------------------------------
+    def contract(self, plan: Plan) -> float:
+        out = C.c_double()
+        L.check(self._lib.tb_contract(self.handle, plan.handle, C.byref(out)), self.handle)
+        return out.value
+
+    def read_tensor(self, plan: Plan, node: int):
+        """-> (labels in bit order, flat float64 array of 2^rank values)."""
+        rank = C.c_int32()
+        labels = (C.c_int32 * 32)()
+        L.check(self._lib.tb_plan_read_tensor(self.handle, plan.handle, node, None, 0, labels, C.byref(rank)), self.handle)
+        n = 1 << rank.value
+        data = np.empty(n, dtype=np.float64)
+        L.check(self._lib.tb_plan_read_tensor(self.handle, plan.handle, node, data.ctypes.data_as(C.POINTER(C.c_double)), n,
+                                              labels, C.byref(rank)), self.handle)
+        return list(labels[:rank.value]), data
+
+    # -- batches -----------------------------------------------------------------------------
+    def contract_plans(self, plans: Sequence[Optional[Plan]], r: Optional[np.ndarray] = None):
+        n = len(plans)
+        arr = (C.c_void_p * max(n, 1))(*[p.handle if p is not None else None for p in plans])
+        out = np.empty(n, dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32)
+        mx = C.c_double()
+        rp = None
+        if r is not None:
+            r = np.ascontiguousarray(r, dtype=np.float64)
+            rp = r.ctypes.data_as(C.POINTER(C.c_double))
+        L.check(self._lib.tb_contract_batch(self.handle, arr, rp, n, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                            status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mx)), self.handle)
+        return out, status, mx.value
+
+    def contract_branches(self, branches: Sequence[SlicedBranch], element_type=np.float32, flags=0):
+        """The whole of contract_slices through ONE C call (compile + upload + contract):
+        returns the contracted values WITHOUT r (float64)."""
+        n = len(branches)
+        nets = (L.tb_network * max(n, 1))()
+        keep: list = []
+        for i, br in enumerate(branches):
+            if br.p.nv == 0 or br.code is None:
+                nets[i].n_leaves = 0
+            else:
+                nets[i], _ = _network_of(br, element_type, flags, keep)
+        out = np.empty(n, dtype=np.float64)
+        status = np.zeros(n, dtype=np.int32)
+        mx = C.c_double()
+        L.check(self._lib.tb_contract_networks(self.handle, nets, None, n, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                               status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mx)), self.handle)
+        return out, status
+
+    def last_timing(self):
+        ms = C.c_double()
+        nl = C.c_int64()
+        L.check(self._lib.tb_last_timing(self.handle, C.byref(ms), C.byref(nl)))
+        return ms.value, nl.value
+
+    def set_stream(self, cuda_stream_handle: int):
+        L.check(self._lib.tb_set_stream(self.handle, C.c_void_p(cuda_stream_handle)), self.handle)
+
+    def profile(self, enable: bool = True):
+        L.check(self._lib.tb_profile(self.handle, int(enable)), self.handle)
+
+    def last_profile(self):
+        ms = (C.c_double * 4)()
+        nl = (C.c_int64 * 4)()
+        L.check(self._lib.tb_last_profile(self.handle, ms, nl))
+        names = ("fused", "generic", "gemm", "finalize")
+        return {k: (ms[i], nl[i]) for i, k in enumerate(names)}
+
+    def last_transfers(self):
+        a = C.c_int64()
+        b = C.c_int64()
+        L.check(self._lib.tb_last_transfers(self.handle, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def permute_bits(self, x: np.ndarray, perm: Sequence[int]) -> np.ndarray:
+        x = np.ascontiguousarray(x)
+        assert x.dtype.itemsize == 4
+        rank = len(perm)
+        assert x.size == 1 << rank
+        out = np.empty_like(x)
+        p = (C.c_int32 * max(rank, 1))(*perm)
+        L.check(self._lib.tb_permute_bits(self.handle, x.ctypes.data, out.ctypes.data, rank, p), self.handle)
+        return out
+
+
+_default_engine: Optional[Engine] = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+def _require_cuda(usecuda):
+    if not usecuda:
+        raise L.TBError(L.TB_ERR_UNSUPPORTED,
+                        "usecuda=False selects the reference's own CPU route (TropicalGEMM.jl); "
+                        "tensorbranching.jl_b200 implements only the usecuda=True position and has no CPU fallback")
+
+
+def solve_slice(branch: SlicedBranch, element_type=np.float32, usecuda: bool = True, engine: Engine = None):
+    """solve_slice (src/dynamic_ob.jl:30-34): the contracted value of one branch, as element_type."""
+    _require_cuda(usecuda)
+    eng = engine or default_engine()
+    vals, status = eng.contract_branches([branch], element_type)
+    return np.dtype(element_type).type(vals[0])
+
+
+def contract_slices(branches: Sequence[SlicedBranch], element_type=np.float32, usecuda: bool = True,
+                    engine: Engine = None) -> np.ndarray:
+    """contract_slices (src/dynamic_ob.jl:36-48): one value per branch, in input order:
+    element_type(r) for an empty graph, else solve_slice + element_type(r) in element_type arithmetic."""
+    _require_cuda(usecuda)
+    et = np.dtype(element_type).type
+    eng = engine or default_engine()
+    vals, status = eng.contract_branches(branches, element_type)
+    res = np.empty(len(branches), dtype=element_type)
+    for i, br in enumerate(branches):
+        if br.p.nv == 0 or br.code is None:
+            res[i] = et(br.r)
+        else:
+            res[i] = et(vals[i]) + et(br.r)
+    return res
+
+
+def complexity(branch: SlicedBranch):
+    """complexity(branch) (src/types.jl:115-119): (tc, sc) of the branch's tree; zeros for code=None."""
+    if branch.code is None:
+        return dict(tc=0.0, sc=0.0, rwc=0.0)
+    p = Plan(branch)
+    st = p.info()
+    p.close()
+    return dict(tc=st.tc, sc=st.sc)
+
+
+def tc(branch):  # src/types.jl:120
+    return complexity(branch)["tc"]
+
+
+def sc(branch):  # src/types.jl:121
+    return complexity(branch)["sc"]

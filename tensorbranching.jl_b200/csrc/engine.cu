@@ -1,0 +1,814 @@
+// engine.cu -- tb_ctx, plan residency, the wave executor and the C ABI of libtbcuda.so.
+//
+// Execution model (replaces the serial `for branch in branches` loop of contract_slices,
+// /root/reference/src/dynamic_ob.jl:38-46, and OMEinsum's recursive, allocating executor):
+//   * branches are grouped into WAVES that fit the HBM arena together;
+//   * inside a wave, steps of ALL branches that sit on the same dependency level run in ONE launch
+//     (work lists of (branch, step) instances; a CTA finds its instance by binary search);
+//     level 0 = all fused small subtrees, levels >= 1 = generic + tiled-GEMM steps;
+//   * root scalars are gathered by k_finalize into one result vector, copied back once.
+// There is no CPU fallback: without a CUDA device tb_init fails with TB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace tb;
+
+namespace {
+thread_local std::string g_tls_error;
+
+struct BlobChunk {
+    void* d = nullptr;
+    size_t cap = 0, used = 0;
+    int live = 0;
+};
+}  // namespace
+
+struct tb_ctx {
+    tb_options opts{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<BlobChunk> chunks;
+    // staging for work lists
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    void* d_stage = nullptr;
+    size_t d_stage_cap = 0;
+    double* d_results = nullptr;
+    double* h_results = nullptr;
+    size_t results_cap = 0;
+    std::string last_error;
+    double last_ms = 0;
+    int64_t last_launches = 0;
+    int64_t last_plan_arena_base_elems = 0;  // where tb_contract placed the single plan
+    int sm_count = 148;
+    bool own_stream = true;
+    bool profile = false;          // per-launch CUDA events, accumulated by kernel kind
+    double prof_ms[4] = {0, 0, 0, 0};
+    int64_t prof_launches[4] = {0, 0, 0, 0};
+    int64_t h2d_bytes = 0, d2h_bytes = 0;  // of the last contract call
+    std::vector<cudaEvent_t> prof_events;
+};
+
+namespace {
+
+int set_err(tb_ctx* ctx, int code, const std::string& msg) {
+    g_tls_error = msg;
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define TB_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t e__ = (call);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            return set_err(ctx, e__ == cudaErrorMemoryAllocation ? TB_ERR_OUT_OF_MEMORY : TB_ERR_CUDA,       \
+                           std::string(#call) + ": " + cudaGetErrorString(e__));                             \
+    } while (0)
+
+int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
+    if (ctx->arena && ctx->arena_bytes >= need_bytes) return TB_OK;
+    size_t want = (size_t)ctx->opts.arena_bytes;
+    if (want == 0) {
+        size_t fr = 0, tot = 0;
+        TB_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+        want = (size_t)((double)fr * 0.6);
+        want = std::min(want, (size_t)96 << 30);
+    }
+    if (ctx->arena && ctx->arena_bytes >= want && need_bytes > want)
+        return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "a single branch needs " + std::to_string(need_bytes) + " bytes of arena, more than configured");
+    if (need_bytes > want) return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "a single branch needs " + std::to_string(need_bytes) + " bytes of arena; arena limit is " + std::to_string(want));
+    if (ctx->arena) {
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->arena);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+    }
+    // grow lazily: start small, double up to `want`
+    size_t sz = std::max<size_t>(need_bytes, std::min<size_t>(want, (size_t)1 << 30));
+    sz = std::min(std::max(sz, need_bytes), want);
+    TB_CUDA(ctx, cudaMalloc(&ctx->arena, sz));
+    ctx->arena_bytes = sz;
+    return TB_OK;
+}
+
+int ensure_stage(tb_ctx* ctx, size_t bytes) {
+    if (ctx->h_stage_cap < bytes) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        size_t cap = std::max(bytes * 3 / 2, (size_t)1 << 20);
+        TB_CUDA(ctx, cudaMallocHost(&ctx->h_stage, cap));
+        ctx->h_stage_cap = cap;
+    }
+    if (ctx->d_stage_cap < bytes) {
+        if (ctx->d_stage) cudaFree(ctx->d_stage);
+        ctx->d_stage = nullptr;
+        size_t cap = std::max(bytes * 3 / 2, (size_t)1 << 20);
+        TB_CUDA(ctx, cudaMalloc(&ctx->d_stage, cap));
+        ctx->d_stage_cap = cap;
+    }
+    return TB_OK;
+}
+
+int ensure_results(tb_ctx* ctx, size_t n) {
+    if (ctx->results_cap >= n) return TB_OK;
+    if (ctx->d_results) cudaFree(ctx->d_results);
+    if (ctx->h_results) cudaFreeHost(ctx->h_results);
+    ctx->d_results = nullptr;
+    ctx->h_results = nullptr;
+    size_t cap = std::max<size_t>(n * 2, 1024);
+    TB_CUDA(ctx, cudaMalloc(&ctx->d_results, cap * sizeof(double)));
+    TB_CUDA(ctx, cudaMallocHost(&ctx->h_results, cap * sizeof(double)));
+    ctx->results_cap = cap;
+    return TB_OK;
+}
+
+// upload the descriptor blobs of all plans that are not resident yet (one staging copy per chunk)
+int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
+    std::vector<tb_plan*> todo;
+    size_t total = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        tb_plan* p = plans[i];
+        if (!p) continue;
+        if (p->p.d_blob) {
+            if (p->p.owner != ctx) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan is resident on a different context");
+            continue;
+        }
+        if (std::find(todo.begin(), todo.end(), p) != todo.end()) continue;
+        todo.push_back(p);
+    }
+    if (todo.empty()) return TB_OK;
+    std::vector<std::vector<uint8_t>> blobs(todo.size());
+    for (size_t i = 0; i < todo.size(); ++i) {
+        build_blob(todo[i]->p, blobs[i]);
+        total += (blobs[i].size() + 255) / 256 * 256;
+    }
+    // one new chunk sized for everything that does not fit the current one
+    size_t pos = 0;
+    while (pos < todo.size()) {
+        BlobChunk* ck = ctx->chunks.empty() ? nullptr : &ctx->chunks.back();
+        size_t need = (blobs[pos].size() + 255) / 256 * 256;
+        if (!ck || ck->used + need > ck->cap) {
+            size_t rest = 0;
+            for (size_t j = pos; j < todo.size(); ++j) rest += (blobs[j].size() + 255) / 256 * 256;
+            BlobChunk nc;
+            nc.cap = std::max<size_t>(rest, (size_t)8 << 20);
+            TB_CUDA(ctx, cudaMalloc(&nc.d, nc.cap));
+            ctx->chunks.push_back(nc);
+            ck = &ctx->chunks.back();
+        }
+        // pack as many as fit, stage, copy
+        size_t first = pos, bytes = 0;
+        while (pos < todo.size()) {
+            size_t nb = (blobs[pos].size() + 255) / 256 * 256;
+            if (ck->used + bytes + nb > ck->cap) break;
+            bytes += nb;
+            ++pos;
+        }
+        int rc = ensure_stage(ctx, bytes);
+        if (rc) return rc;
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer may be in flight
+        size_t o = 0;
+        for (size_t j = first; j < pos; ++j) {
+            std::memcpy((uint8_t*)ctx->h_stage + o, blobs[j].data(), blobs[j].size());
+            todo[j]->p.d_blob = (uint8_t*)ck->d + ck->used + o;
+            todo[j]->p.owner = ctx;
+            ck->live++;
+            o += (blobs[j].size() + 255) / 256 * 256;
+        }
+        TB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ck->d + ck->used, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d_bytes += (int64_t)bytes;
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ck->used += bytes;
+    }
+    (void)total;
+    return TB_OK;
+}
+
+struct Launch {
+    int kind;        // 0 fused, 1 generic, 2 gemm, 3 finalize
+    int vt;
+    size_t inst_off; // byte offset of the instance array in the staging buffer
+    size_t starts_off;
+    int n_insts;
+    uint32_t grid;
+    uint32_t smem;
+};
+
+template <typename T>
+void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
+    switch (L.kind) {
+        case 0:
+            k_fused_subtrees<T><<<L.grid, FUSED_THREADS, L.smem, ctx->stream>>>((const SubInst*)(dbase + L.inst_off), L.n_insts);
+            break;
+        case 1:
+            k_generic<T><<<L.grid, BIG_THREADS, 0, ctx->stream>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
+            break;
+        case 2:
+            k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
+            break;
+        case 3:
+            k_finalize<T><<<(L.n_insts + 127) / 128, 128, 0, ctx->stream>>>((const FinalInst*)(dbase + L.inst_off), L.n_insts, ctx->d_results);
+            break;
+    }
+}
+
+// contract plans[idx[0..m)] (all of one value type); results land in ctx->d_results[idx[i]]
+int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& idx, int vt, std::vector<int32_t>& status,
+              bool single_plan_mode) {
+    if (idx.empty()) return TB_OK;
+    const size_t elem = 4;
+    // ---- waves
+    size_t max_need = 0;
+    for (int64_t i : idx) max_need = std::max(max_need, (size_t)plans[i]->p.arena_elems * elem + 256);
+    int rc = ensure_arena(ctx, std::max<size_t>(max_need, 1 << 20));
+    if (rc == TB_ERR_OUT_OF_MEMORY) {
+        // keep going with what we have: oversize branches get a per-branch status below
+        if (!ctx->arena) {
+            rc = ensure_arena(ctx, 1 << 20);
+            if (rc) return rc;
+        }
+    } else if (rc) {
+        return rc;
+    }
+    // try to grow the arena so that a full wave fits (bounded by the configured limit)
+    {
+        size_t total = 0;
+        int cnt = 0;
+        const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 256;
+        std::vector<size_t> needs;
+        for (int64_t i : idx) needs.push_back(((size_t)plans[i]->p.arena_elems * elem + 255) / 256 * 256);
+        std::sort(needs.begin(), needs.end(), std::greater<size_t>());
+        for (size_t v : needs) {
+            if (cnt++ >= max_wave) break;
+            total += v;
+        }
+        if (total > ctx->arena_bytes) {
+            size_t want = (size_t)ctx->opts.arena_bytes;
+            if (want == 0) {
+                size_t fr = 0, tot = 0;
+                cudaMemGetInfo(&fr, &tot);
+                want = std::min((size_t)((double)(fr + ctx->arena_bytes) * 0.6), (size_t)96 << 30);
+            }
+            size_t target = std::min(total, want);
+            if (target > ctx->arena_bytes) {
+                cudaStreamSynchronize(ctx->stream);
+                void* na = nullptr;
+                cudaFree(ctx->arena);
+                ctx->arena = nullptr;
+                if (cudaMalloc(&na, target) == cudaSuccess) {
+                    ctx->arena = na;
+                    ctx->arena_bytes = target;
+                } else {
+                    cudaGetLastError();
+                    size_t back = std::max<size_t>(max_need, 1 << 20);
+                    TB_CUDA(ctx, cudaMalloc(&ctx->arena, back));
+                    ctx->arena_bytes = back;
+                }
+            }
+        }
+    }
+
+    struct Wave {
+        std::vector<int64_t> members;
+        std::vector<size_t> base;  // arena byte offsets
+        int levels = 0;
+    };
+    std::vector<Wave> waves;
+    {
+        const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 256;
+        Wave cur;
+        size_t used = 0;
+        for (int64_t i : idx) {
+            const Plan& P = plans[i]->p;
+            size_t need = ((size_t)P.arena_elems * elem + 255) / 256 * 256;
+            if (need > ctx->arena_bytes) {
+                status[i] = TB_ERR_OUT_OF_MEMORY;
+                continue;
+            }
+            if (!cur.members.empty() && (used + need > ctx->arena_bytes || (int)cur.members.size() >= max_wave)) {
+                waves.push_back(std::move(cur));
+                cur = Wave();
+                used = 0;
+            }
+            cur.members.push_back(i);
+            cur.base.push_back(used);
+            cur.levels = std::max(cur.levels, P.n_levels);
+            used += need;
+        }
+        if (!cur.members.empty()) waves.push_back(std::move(cur));
+    }
+    if (single_plan_mode && !waves.empty()) ctx->last_plan_arena_base_elems = 0;
+
+    // ---- build work lists for every wave into one host buffer
+    std::vector<uint8_t> host;
+    std::vector<Launch> launches;
+    auto align16 = [&]() { host.resize((host.size() + 15) / 16 * 16); };
+    for (const Wave& w : waves) {
+        // level 0: fused subtrees
+        {
+            align16();
+            Launch L{};
+            L.kind = 0;
+            L.vt = vt;
+            L.inst_off = host.size();
+            uint32_t smem_elems = 0;
+            std::vector<SubInst> insts;
+            for (size_t m = 0; m < w.members.size(); ++m) {
+                const Plan& P = plans[w.members[m]]->p;
+                uint8_t* blob = (uint8_t*)P.d_blob;
+                uint8_t* ab = (uint8_t*)ctx->arena + w.base[m];
+                for (const SubTree& st : P.subtrees) {
+                    SubInst si{};
+                    si.steps = (const SubStep*)(blob + P.sub_blob_off) + st.first_step;
+                    si.pool = blob;
+                    si.out = ab + st.out_off * elem;
+                    si.n_steps = st.n_steps;
+                    insts.push_back(si);
+                    smem_elems = std::max(smem_elems, st.smem_elems);
+                }
+            }
+            if (!insts.empty()) {
+                L.n_insts = (int)insts.size();
+                L.grid = (uint32_t)insts.size();
+                L.smem = std::max<uint32_t>(smem_elems * (uint32_t)elem, 16);
+                size_t o = host.size();
+                host.resize(o + insts.size() * sizeof(SubInst));
+                std::memcpy(host.data() + o, insts.data(), insts.size() * sizeof(SubInst));
+                launches.push_back(L);
+            }
+        }
+        for (int lv = 1; lv <= w.levels; ++lv) {
+            for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
+                std::vector<BigInst> insts;
+                std::vector<uint32_t> starts;
+                uint64_t tiles = 0;
+                for (size_t m = 0; m < w.members.size(); ++m) {
+                    const Plan& P = plans[w.members[m]]->p;
+                    if (lv > P.n_levels) continue;
+                    uint8_t* blob = (uint8_t*)P.d_blob;
+                    const BigStep* dsteps = (const BigStep*)(blob + P.big_blob_off);
+                    for (int s = P.big_level_begin[lv]; s < P.big_level_begin[lv + 1]; ++s) {
+                        if (P.big_steps[s].kind != kind) continue;
+                        BigInst bi{};
+                        bi.step = dsteps + s;
+                        bi.pool = blob;
+                        bi.arena = (uint8_t*)ctx->arena + w.base[m];
+                        bi.tile_start = (uint32_t)tiles;
+                        insts.push_back(bi);
+                        starts.push_back((uint32_t)tiles);
+                        tiles += P.big_steps[s].n_tiles;
+                    }
+                }
+                if (insts.empty()) continue;
+                if (tiles > 0x7fffffffull) return set_err(ctx, TB_ERR_UNSUPPORTED, "a level needs more than 2^31 CTAs");
+                align16();
+                Launch L{};
+                L.kind = kind;
+                L.vt = vt;
+                L.inst_off = host.size();
+                host.resize(host.size() + insts.size() * sizeof(BigInst));
+                std::memcpy(host.data() + L.inst_off, insts.data(), insts.size() * sizeof(BigInst));
+                align16();
+                L.starts_off = host.size();
+                host.resize(host.size() + starts.size() * 4);
+                std::memcpy(host.data() + L.starts_off, starts.data(), starts.size() * 4);
+                L.n_insts = (int)insts.size();
+                L.grid = (uint32_t)tiles;
+                launches.push_back(L);
+            }
+        }
+        // finalize
+        {
+            align16();
+            Launch L{};
+            L.kind = 3;
+            L.vt = vt;
+            L.inst_off = host.size();
+            std::vector<FinalInst> fin;
+            for (size_t m = 0; m < w.members.size(); ++m) {
+                const Plan& P = plans[w.members[m]]->p;
+                FinalInst f{};
+                f.src = (uint8_t*)ctx->arena + w.base[m] + P.root_off * elem;
+                f.out_index = w.members[m];
+                fin.push_back(f);
+            }
+            L.n_insts = (int)fin.size();
+            host.resize(host.size() + fin.size() * sizeof(FinalInst));
+            std::memcpy(host.data() + L.inst_off, fin.data(), fin.size() * sizeof(FinalInst));
+            launches.push_back(L);
+        }
+    }
+    if (launches.empty()) return TB_OK;
+    rc = ensure_stage(ctx, host.size());
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::memcpy(ctx->h_stage, host.data(), host.size());
+    TB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, host.size(), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (ctx->profile) {
+        while (ctx->prof_events.size() < launches.size() + 1) {
+            cudaEvent_t e;
+            TB_CUDA(ctx, cudaEventCreate(&e));
+            ctx->prof_events.push_back(e);
+        }
+        TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[0], ctx->stream));
+    }
+    for (size_t li = 0; li < launches.size(); ++li) {
+        const Launch& L = launches[li];
+        if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)ctx->d_stage);
+        else launch_one<float>(ctx, L, (uint8_t*)ctx->d_stage);
+        if (ctx->profile) TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[li + 1], ctx->stream));
+    }
+    TB_CUDA(ctx, cudaGetLastError());
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms += ms;
+    ctx->last_launches += (int64_t)launches.size();
+    ctx->h2d_bytes += (int64_t)host.size();
+    if (ctx->profile) {
+        for (size_t li = 0; li < launches.size(); ++li) {
+            float pm = 0;
+            TB_CUDA(ctx, cudaEventElapsedTime(&pm, ctx->prof_events[li], ctx->prof_events[li + 1]));
+            ctx->prof_ms[launches[li].kind] += pm;
+            ctx->prof_launches[launches[li].kind] += 1;
+        }
+    }
+    return TB_OK;
+}
+
+int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
+                  double* out_max, bool single) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!plans || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->last_ms = 0;
+    ctx->last_launches = 0;
+    ctx->h2d_bytes = 0;
+    ctx->d2h_bytes = 0;
+    for (int q = 0; q < 4; ++q) {
+        ctx->prof_ms[q] = 0;
+        ctx->prof_launches[q] = 0;
+    }
+    int rc = ensure_uploaded(ctx, plans, n);
+    if (rc) return rc;
+    rc = ensure_results(ctx, (size_t)std::max<int64_t>(n, 1));
+    if (rc) return rc;
+    std::vector<int32_t> status((size_t)n, TB_OK);
+    std::vector<int64_t> gi, gf;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!plans[i]) continue;
+        (plans[i]->p.value_type == TB_VALUE_I32 ? gi : gf).push_back(i);
+    }
+    rc = run_group(ctx, plans, gi, TB_VALUE_I32, status, single);
+    if (rc) return rc;
+    rc = run_group(ctx, plans, gf, TB_VALUE_F32, status, single);
+    if (rc) return rc;
+    if (!gi.empty() || !gf.empty()) {
+        TB_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->d2h_bytes += (int64_t)n * 8;
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    double mx = -std::numeric_limits<double>::infinity();
+    int worst = TB_OK;
+    for (int64_t i = 0; i < n; ++i) {
+        double ri = r ? r[i] : 0.0;
+        double v;
+        if (!plans[i]) v = ri;  // empty graph: value is r (src/dynamic_ob.jl:39-40)
+        else if (status[i] != TB_OK) {
+            v = std::numeric_limits<double>::quiet_NaN();
+            worst = status[i];
+        } else v = ctx->h_results[i] + ri;
+        out_values[i] = v;
+        if (out_status) out_status[i] = status[i];
+        if (status[i] == TB_OK && v > mx) mx = v;
+    }
+    if (out_max) *out_max = mx;
+    if (worst != TB_OK) return set_err(ctx, worst, "one or more branches failed (see per-branch status): arena too small");
+    return TB_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char* tb_version(void) { return "tbcuda 0.1.0 (sm_100a)"; }
+
+const char* tb_last_error(const tb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_tls_error.c_str(); }
+
+int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
+    if (!out_ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_err(nullptr, TB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libtbcuda has no CPU fallback");
+    std::unique_ptr<tb_ctx> ctx(new tb_ctx());
+    if (opts) ctx->opts = *opts;
+    ctx->device = ctx->opts.device;
+    if (ctx->device < 0 || ctx->device >= ndev) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    tb_ctx* c = ctx.get();
+    TB_CUDA(nullptr, cudaSetDevice(c->device));
+    cudaDeviceProp prop{};
+    TB_CUDA(nullptr, cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10)
+        return set_err(nullptr, TB_ERR_CUDA, "device compute capability " + std::to_string(prop.major) + "." + std::to_string(prop.minor) + " < 10.0: libtbcuda is built for sm_100a only");
+    c->sm_count = prop.multiProcessorCount;
+    TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TB_CUDA(nullptr, cudaEventCreate(&c->ev0));
+    TB_CUDA(nullptr, cudaEventCreate(&c->ev1));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    *out_ctx = ctx.release();
+    return TB_OK;
+}
+
+int tb_shutdown(tb_ctx* ctx) {
+    if (!ctx) return TB_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->arena) cudaFree(ctx->arena);
+    for (auto& c : ctx->chunks)
+        if (c.d) cudaFree(c.d);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->d_results) cudaFree(ctx->d_results);
+    if (ctx->h_results) cudaFreeHost(ctx->h_results);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TB_OK;
+}
+
+int tb_plan_create(tb_ctx* ctx, const tb_network* net, tb_plan** out_plan) {
+    if (!net || !out_plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net / out_plan is NULL");
+    *out_plan = nullptr;
+    std::unique_ptr<tb_plan> p(new tb_plan());
+    std::string err;
+    int rc = compile_plan(*net, ctx ? ctx->opts.plan_flags : 0u, p->p, err);
+    if (rc) return set_err(ctx, rc, err);
+    *out_plan = p.release();
+    return TB_OK;
+}
+
+int tb_plan_destroy(tb_plan* plan) {
+    if (!plan) return TB_OK;
+    if (plan->p.owner && plan->p.d_blob) {
+        tb_ctx* ctx = plan->p.owner;
+        for (auto& c : ctx->chunks) {
+            if ((uint8_t*)plan->p.d_blob >= (uint8_t*)c.d && (uint8_t*)plan->p.d_blob < (uint8_t*)c.d + c.cap) {
+                if (--c.live == 0 && &c != &ctx->chunks.back()) {
+                    cudaSetDevice(ctx->device);
+                    cudaStreamSynchronize(ctx->stream);
+                    cudaFree(c.d);
+                    c.d = nullptr;
+                    c.cap = c.used = 0;
+                } else if (c.live == 0) {
+                    c.used = 0;  // recycle the open chunk
+                }
+                break;
+            }
+        }
+    }
+    delete plan;
+    return TB_OK;
+}
+
+int tb_plan_info(const tb_plan* plan, tb_plan_stats* out) {
+    if (!plan || !out) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "plan / out is NULL");
+    *out = plan->p.stats;
+    return TB_OK;
+}
+
+int tb_plan_export(const tb_plan* plan, tb_step_info* out, int32_t cap) {
+    if (!plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "plan is NULL");
+    int n = (int)plan->p.info.size();
+    if (out)
+        for (int i = 0; i < n && i < cap; ++i) out[i] = plan->p.info[i];
+    return n;
+}
+
+int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_t cap) {
+    if (!plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "plan is NULL");
+    const Plan& P = plan->p;
+    const void* src = nullptr;
+    int64_t bytes = 0;
+    int64_t header[4] = {P.arena_elems, P.root_off, P.n_levels, P.value_type};
+    switch (which) {
+        case 0: src = P.pool.data(); bytes = (int64_t)P.pool.size() * 4; break;
+        case 1: src = P.sub_steps.data(); bytes = (int64_t)(P.sub_steps.size() * sizeof(SubStep)); break;
+        case 2: src = P.subtrees.data(); bytes = (int64_t)(P.subtrees.size() * sizeof(SubTree)); break;
+        case 3: src = P.big_steps.data(); bytes = (int64_t)(P.big_steps.size() * sizeof(BigStep)); break;
+        case 4: src = P.big_level_begin.data(); bytes = (int64_t)P.big_level_begin.size() * 4; break;
+        case 5: src = header; bytes = sizeof header; break;
+        default: return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "unknown section");
+    }
+    if (out && cap > 0 && bytes > 0) std::memcpy(out, src, (size_t)std::min(cap, bytes));
+    return bytes;
+}
+
+int tb_contract(tb_ctx* ctx, tb_plan* plan, double* out_value) {
+    if (!plan || !out_value) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan / out_value is NULL");
+    tb_plan* arr[1] = {plan};
+    return contract_impl(ctx, arr, nullptr, 1, out_value, nullptr, nullptr, true);
+}
+
+int tb_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
+                      double* out_max) {
+    return contract_impl(ctx, plans, r, n, out_values, out_status, out_max, false);
+}
+
+int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n, double* out_values,
+                         int32_t* out_status, double* out_max) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!nets || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    std::vector<tb_plan*> plans((size_t)n, nullptr);
+    std::vector<int> codes((size_t)n, TB_OK);
+    std::vector<std::string> errs((size_t)n);
+    int nthreads = ctx->opts.host_threads > 0 ? ctx->opts.host_threads : (int)std::thread::hardware_concurrency();
+    nthreads = std::max(1, std::min<int>(nthreads, (int)std::max<int64_t>(1, n / 8)));
+    std::atomic<int64_t> next{0};
+    const uint32_t flags = ctx->opts.plan_flags;
+    auto worker = [&]() {
+        for (;;) {
+            int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            if (nets[i].n_leaves == 0) continue;  // empty graph
+            tb_plan* p = new tb_plan();
+            codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
+            if (codes[i]) delete p;
+            else plans[i] = p;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+    }
+    int rc = TB_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (codes[i]) {
+            rc = set_err(ctx, codes[i], "branch " + std::to_string(i) + ": " + errs[i]);
+            break;
+        }
+    if (rc == TB_OK) rc = contract_impl(ctx, plans.data(), r, n, out_values, out_status, out_max, false);
+    for (tb_plan* p : plans) tb_plan_destroy(p);
+    return rc;
+}
+
+int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap, int32_t* out_labels,
+                        int32_t* out_rank) {
+    if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
+    const Plan& P = plan->p;
+    if (!(P.flags & TB_PLAN_KEEP_INTERMEDIATES)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan was not created with TB_PLAN_KEEP_INTERMEDIATES");
+    int nT = P.n_leaves + P.n_nodes;
+    if (node < P.n_leaves || node >= nT) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "node id is not an internal node");
+    int rank = (int)P.layout[node].size();
+    if (out_rank) *out_rank = rank;
+    if (out_labels)
+        for (int i = 0; i < rank; ++i) out_labels[i] = P.layout[node][i];
+    int64_t n = (int64_t)1 << rank;
+    if (!out_data) return TB_OK;
+    if (cap < n) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "output buffer too small");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d_tmp = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&d_tmp, (size_t)n * sizeof(double)));
+    const uint8_t* src = (const uint8_t*)ctx->arena + (size_t)(ctx->last_plan_arena_base_elems + P.off[node]) * 4;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (P.value_type == TB_VALUE_I32) k_to_double<int32_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t*)src, d_tmp, n);
+    else k_to_double<float><<<blocks, 256, 0, ctx->stream>>>((const float*)src, d_tmp, n);
+    cudaError_t e = cudaMemcpyAsync(out_data, d_tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
+    return TB_OK;
+}
+
+int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (out_device_ms) *out_device_ms = ctx->last_ms;
+    if (out_launches) *out_launches = ctx->last_launches;
+    return TB_OK;
+}
+
+int tb_set_stream(tb_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return TB_OK;
+}
+
+int tb_profile(tb_ctx* ctx, int enable) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    ctx->profile = enable != 0;
+    return TB_OK;
+}
+
+int tb_last_profile(const tb_ctx* ctx, double* ms_by_kind, int64_t* launches_by_kind) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    for (int q = 0; q < 4; ++q) {
+        if (ms_by_kind) ms_by_kind[q] = ctx->prof_ms[q];
+        if (launches_by_kind) launches_by_kind[q] = ctx->prof_launches[q];
+    }
+    return TB_OK;
+}
+
+int tb_last_transfers(const tb_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    return TB_OK;
+}
+
+int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const int32_t* perm) {
+    if (!ctx || !in || !out || !perm) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "NULL argument");
+    if (rank < 0 || rank > 31) return set_err(ctx, TB_ERR_UNSUPPORTED, "rank must be in [0, 31]");
+    std::vector<int> dst_of_src(rank, -1);
+    for (int i = 0; i < rank; ++i) {
+        if (perm[i] < 0 || perm[i] >= rank || dst_of_src[perm[i]] != -1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "perm is not a permutation");
+        dst_of_src[perm[i]] = i;
+    }
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    PermuteDesc d{};
+    d.rank = (uint8_t)rank;
+    const int Lb = std::min(rank, 5);
+    std::vector<int> in_tile(rank, 0);
+    for (int i = 0; i < Lb; ++i) {
+        in_tile[i] = 1;        // low source bits
+        in_tile[perm[i]] = 1;  // source bits feeding the low destination bits
+    }
+    std::vector<int> tsrc, gsrc;
+    for (int b = 0; b < rank; ++b) (in_tile[b] ? tsrc : gsrc).push_back(b);
+    d.u = (uint8_t)tsrc.size();
+    d.ng = (uint8_t)gsrc.size();
+    std::vector<int> tdst;  // destination bits of the tile, ascending
+    for (int b : tsrc) tdst.push_back(dst_of_src[b]);
+    std::sort(tdst.begin(), tdst.end());
+    for (size_t j = 0; j < tsrc.size(); ++j) d.tile_src_bit[j] = (uint8_t)tsrc[j];
+    for (size_t j = 0; j < tdst.size(); ++j) {
+        d.tile_dst_bit[j] = (uint8_t)tdst[j];
+        int sb = perm[tdst[j]];
+        d.dst_to_src_tile[j] = (uint8_t)(std::find(tsrc.begin(), tsrc.end(), sb) - tsrc.begin());
+    }
+    for (size_t j = 0; j < gsrc.size(); ++j) {
+        d.grid_src_bit[j] = (uint8_t)gsrc[j];
+        d.grid_dst_bit[j] = (uint8_t)dst_of_src[gsrc[j]];
+    }
+    size_t bytes = ((size_t)1 << rank) * 4;
+    void *din = nullptr, *dout = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&din, bytes));
+    cudaError_t e = cudaMalloc(&dout, bytes);
+    if (e != cudaSuccess) {
+        cudaFree(din);
+        return set_err(ctx, TB_ERR_OUT_OF_MEMORY, cudaGetErrorString(e));
+    }
+    e = cudaMemcpyAsync(din, in, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        k_permute_bits<<<(unsigned)(1u << d.ng), 256, 0, ctx->stream>>>((const uint32_t*)din, (uint32_t*)dout, d);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->last_ms = ms;
+        ctx->last_launches = 1;
+    }
+    cudaFree(din);
+    cudaFree(dout);
+    if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
+    return TB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,426 @@
+// kernels.cuh -- sm_100a device code of libtbcuda: the max-plus contraction kernels.
+//
+//   k_fused_subtrees  K4/K6: one CTA walks a whole small subtree of the contraction tree with every
+//                     intermediate in shared memory (leaf tensors come from the plan's pool).
+//   k_generic         any single contraction, one thread per output element (block-level split-k for
+//                     tiny outputs); memory-bound nodes, skinny nodes, nodes touching leaves.
+//   k_gemm            K1/K3: tiled batched max-plus GEMM, 8x8 register microtile, cp.async double
+//                     buffered contiguous operand panels, DPX VIADDMNMX (int32) / FADD+FMNMX (f32).
+//   k_permute_bits    K5: bit-permutation transpose through shared memory, 128-bit global accesses.
+//   k_finalize        root scalars -> per-branch result vector (the input of maximum(res),
+//                     /root/reference/src/dynamic_ob.jl:27).
+//
+// Semantics of one step (OMEinsum binary rule + TropicalGEMM mul! [upstream]):
+//   C[M,N,Bt] = max_{K,KA,KB} A[M,K,KA,Bt] + B[N,K,KB,Bt]      with (+) = max, (x) = +.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "desc.h"
+
+namespace tb {
+
+template <typename T> struct Ops;
+template <> struct Ops<int32_t> {
+    typedef int4 vec4;
+    static __device__ __forceinline__ int32_t neg_inf() { return -(1 << 30); }
+    // DPX: one VIADDMNMX = max(a + b, c)
+    static __device__ __forceinline__ int32_t addmax(int32_t a, int32_t b, int32_t c) { return __viaddmax_s32(a, b, c); }
+    static __device__ __forceinline__ int32_t vmax(int32_t a, int32_t b) { return max(a, b); }
+    static __device__ __forceinline__ double to_double(int32_t v) { return v <= -(1 << 29) ? -INFINITY : (double)v; }
+};
+template <> struct Ops<float> {
+    typedef float4 vec4;
+    static __device__ __forceinline__ float neg_inf() { return -INFINITY; }
+    static __device__ __forceinline__ float addmax(float a, float b, float c) { return fmaxf(__fadd_rn(a, b), c); }
+    static __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ double to_double(float v) { return (double)v; }
+};
+
+__device__ __forceinline__ uint32_t scatter_bits(uint32_t x, const uint8_t* sh, int n) {
+    uint32_t off = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t s = sh[i];
+        if (s != NO_BIT) off |= ((x >> i) & 1u) << s;
+    }
+    return off;
+}
+
+// largest idx with starts[idx] <= b
+__device__ __forceinline__ int find_inst(const uint32_t* __restrict__ starts, int n, uint32_t b) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (__ldg(starts + mid) <= b) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: fused small subtrees.  grid = one CTA per (branch, subtree), 128 threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int FUSED_THREADS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst* __restrict__ insts, int n_insts) {
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    T* smem = reinterpret_cast<T*>(dyn_smem);
+    __shared__ uint32_t s_desc[2][12];
+    if ((int)blockIdx.x >= n_insts) return;
+    const SubInst inst = insts[blockIdx.x];
+    const int tid = threadIdx.x;
+    const T* pool = reinterpret_cast<const T*>(inst.pool);
+    T* out = reinterpret_cast<T*>(inst.out);
+    const uint32_t* gdesc = reinterpret_cast<const uint32_t*>(inst.steps);
+    if (tid < 12) s_desc[0][tid] = __ldg(gdesc + tid);
+    __syncthreads();
+    for (uint32_t st = 0; st < inst.n_steps; ++st) {
+        const SubStep& d = *reinterpret_cast<const SubStep*>(s_desc[st & 1]);
+        if (st + 1 < inst.n_steps && tid < 12) s_desc[(st + 1) & 1][tid] = __ldg(gdesc + (st + 1) * 12 + tid);
+        const T* A = (d.a_loc == LOC_SMEM ? smem : pool) + d.a_off;
+        const T* B = (d.b_loc == LOC_SMEM ? smem : pool) + d.b_off;
+        T* C = (d.c_loc == LOC_SMEM) ? smem + d.c_off : out;
+        const int rc = d.rc, nk = d.nk, nka = d.nka;
+        const int nkt = nk + nka + d.nkb;
+        int ks = 7 - rc;  // lanes cooperating on one output: 2^ks consecutive lanes (within a warp)
+        ks = ks < 0 ? 0 : ks;
+        ks = ks > 5 ? 5 : ks;
+        ks = ks > nkt ? nkt : ks;
+        const uint32_t W = 1u << (rc + ks);
+        const uint32_t kmask = (1u << nk) - 1u, amask = (1u << (nk + nka)) - 1u;
+        const uint32_t n_red = 1u << nkt;
+        for (uint32_t w0 = 0; w0 < W; w0 += FUSED_THREADS) {
+            const uint32_t w = w0 + tid;
+            const bool active = w < W;
+            const uint32_t c = w >> ks, kp = w & ((1u << ks) - 1u);
+            T acc = Ops<T>::neg_inf();
+            if (active) {
+                const uint32_t offA = scatter_bits(c, d.a_shift, rc);
+                const uint32_t offB = scatter_bits(c, d.b_shift, rc);
+                for (uint32_t r = kp; r < n_red; r += (1u << ks)) {
+                    const uint32_t ra = (r & amask) << d.sa;
+                    const uint32_t rb = ((r & kmask) | ((r >> (nk + nka)) << nk)) << d.sb;
+                    acc = Ops<T>::addmax(A[offA + ra], B[offB + rb], acc);
+                }
+            }
+            for (int s = 1; s < (1 << ks); s <<= 1) acc = Ops<T>::vmax(acc, __shfl_xor_sync(0xffffffffu, acc, s));
+            if (active && kp == 0) C[c] = acc;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic single contraction.  grid = sum of n_tiles over the launch, 256 threads.
+// ------------------------------------------------------------------------------------------------
+constexpr int BIG_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restrict__ insts,
+                                                         const uint32_t* __restrict__ tile_starts, int n_insts) {
+    __shared__ BigStep sd;
+    __shared__ T s_red[BIG_THREADS];
+    const int tid = threadIdx.x;
+    const int idx = find_inst(tile_starts, n_insts, blockIdx.x);
+    const BigInst inst = insts[idx];
+    const uint32_t tile = blockIdx.x - __ldg(tile_starts + idx);
+    if (tid < (int)(sizeof(BigStep) / 4)) reinterpret_cast<uint32_t*>(&sd)[tid] = __ldg(reinterpret_cast<const uint32_t*>(inst.step) + tid);
+    __syncthreads();
+    const T* pool = reinterpret_cast<const T*>(inst.pool);
+    T* arena = reinterpret_cast<T*>(inst.arena);
+    const T* __restrict__ A = (sd.a_loc == LOC_POOL ? pool : arena) + sd.a_off;
+    const T* __restrict__ B = (sd.b_loc == LOC_POOL ? pool : arena) + sd.b_off;
+    T* __restrict__ C = arena + sd.c_off;
+    const int rc = sd.rc, nk = sd.nk, nka = sd.nka, ks = sd.ks;
+    const int nkt = nk + nka + sd.nkb;
+    uint32_t c, kp;
+    bool active = true;
+    if (rc >= 8) {
+        c = tile * BIG_THREADS + tid;
+        kp = 0;
+    } else {
+        c = tid & ((1u << rc) - 1u);
+        kp = tid >> rc;
+        active = kp < (1u << ks);
+    }
+    T acc = Ops<T>::neg_inf();
+    if (active) {
+        const uint32_t offA = scatter_bits(c, sd.a_shift, rc);
+        const uint32_t offB = scatter_bits(c, sd.b_shift, rc);
+        const uint32_t kmask = (1u << nk) - 1u, amask = (1u << (nk + nka)) - 1u;
+        const uint32_t n_red = 1u << nkt;
+        const int sa = sd.sa, sb = sd.sb;
+        if (nka == 0 && sd.nkb == 0) {
+#pragma unroll 4
+            for (uint32_t r = kp; r < n_red; r += (1u << ks))
+                acc = Ops<T>::addmax(A[offA + (r << sa)], B[offB + (r << sb)], acc);
+        } else {
+            for (uint32_t r = kp; r < n_red; r += (1u << ks)) {
+                const uint32_t ra = (r & amask) << sa;
+                const uint32_t rb = ((r & kmask) | ((r >> (nk + nka)) << nk)) << sb;
+                acc = Ops<T>::addmax(A[offA + ra], B[offB + rb], acc);
+            }
+        }
+    }
+    if (ks == 0) {
+        if (active) C[c] = acc;
+    } else {
+        s_red[tid] = acc;
+        __syncthreads();
+        if (active && kp == 0) {
+            for (uint32_t j = 1; j < (1u << ks); ++j) acc = Ops<T>::vmax(acc, s_red[tid + (j << rc)]);
+            C[c] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1/K3: tiled batched max-plus GEMM.  256 threads, each an 8x8 microtile; a CTA holds S = 2^s_log
+// independent (2^tm x 2^tn) sub-tiles (consecutive grid indices) so that small tiles still fill it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+constexpr int GEMM_SMEM_BYTES = 2 * GEMM_STAGE_ELEMS * 4;
+
+template <typename T>
+__global__ void __launch_bounds__(BIG_THREADS, 2) k_gemm(const BigInst* __restrict__ insts,
+                                                         const uint32_t* __restrict__ tile_starts, int n_insts) {
+    typedef typename Ops<T>::vec4 vec4;
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    T* stage_mem = reinterpret_cast<T*>(dyn_smem);
+    __shared__ BigStep sd;
+    __shared__ long long s_abase[32], s_bbase[32], s_cbase[32];
+    const int tid = threadIdx.x;
+    const int idx = find_inst(tile_starts, n_insts, blockIdx.x);
+    const BigInst inst = insts[idx];
+    const uint32_t tile = blockIdx.x - __ldg(tile_starts + idx);
+    if (tid < (int)(sizeof(BigStep) / 4)) reinterpret_cast<uint32_t*>(&sd)[tid] = __ldg(reinterpret_cast<const uint32_t*>(inst.step) + tid);
+    __syncthreads();
+    const int tm = sd.tm, tn = sd.tn, nk = sd.nk, kc = sd.kc, ng = sd.ng;
+    const int tps_log = tm + tn - 6, s_log = 8 - tps_log, S = 1 << s_log;
+    T* arena = reinterpret_cast<T*>(inst.arena);
+    const T* __restrict__ Ag = arena + sd.a_off;
+    const T* __restrict__ Bg = arena + sd.b_off;
+    T* __restrict__ Cg = arena + sd.c_off;
+    if (tid < S) {
+        const unsigned long long g = (unsigned long long)tile * S + tid;
+        long long ab = -1, bb = -1, cb = -1;
+        if (g < (1ull << ng)) {
+            const int n_mhi = sd.n_mhi, n_nhi = sd.n_nhi;
+            const unsigned long long gm = g & ((1ull << n_mhi) - 1ull);
+            const unsigned long long gn = (g >> n_mhi) & ((1ull << n_nhi) - 1ull);
+            const unsigned long long gb = g >> (n_mhi + n_nhi);
+            ab = (long long)((gm | (gb << n_mhi)) << (tm + nk));
+            bb = (long long)((gn | (gb << n_nhi)) << (tn + nk));
+            cb = (long long)scatter_bits((uint32_t)g, sd.c_shift + tm + tn, ng);
+        }
+        s_abase[tid] = ab;
+        s_bbase[tid] = bb;
+        s_cbase[tid] = cb;
+    }
+    __syncthreads();
+
+    const int la = kc + tm, lb = kc + tn;  // log2 elements of one sub-tile's A / B chunk
+    T* stageB_off = nullptr;
+    (void)stageB_off;
+    auto load_stage = [&](int stage, int chunk) {
+        T* sA = stage_mem + stage * GEMM_STAGE_ELEMS;
+        T* sB = sA + ((size_t)S << la);
+        const int nvA = 1 << (s_log + la - 2), nvB = 1 << (s_log + lb - 2);
+        for (int v = tid; v < nvA; v += BIG_THREADS) {
+            const int s = v >> (la - 2), w = v & ((1 << (la - 2)) - 1);
+            const long long base = s_abase[s];
+            if (base >= 0) cp_async16(sA + ((size_t)s << la) + w * 4, Ag + base + ((long long)chunk << la) + w * 4);
+        }
+        for (int v = tid; v < nvB; v += BIG_THREADS) {
+            const int s = v >> (lb - 2), w = v & ((1 << (lb - 2)) - 1);
+            const long long base = s_bbase[s];
+            if (base >= 0) cp_async16(sB + ((size_t)s << lb) + w * 4, Bg + base + ((long long)chunk << lb) + w * 4);
+        }
+    };
+
+    const int sub = tid >> tps_log, lt = tid & ((1 << tps_log) - 1);
+    const int tmh = lt & ((1 << (tm - 3)) - 1), tnh = lt >> (tm - 3);
+    const int m_lo = tmh * 4, m_hi = (1 << (tm - 1)) + tmh * 4;
+    const int n_lo = tnh * 4, n_hi = (1 << (tn - 1)) + tnh * 4;
+
+    T acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = Ops<T>::neg_inf();
+
+    const int nchunks = 1 << (nk - kc);
+    load_stage(0, 0);
+    cp_async_commit();
+    for (int ch = 0; ch < nchunks; ++ch) {
+        if (ch + 1 < nchunks) load_stage((ch + 1) & 1, ch + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const T* sA = stage_mem + (ch & 1) * GEMM_STAGE_ELEMS + ((size_t)sub << la);
+        const T* sB = stage_mem + (ch & 1) * GEMM_STAGE_ELEMS + ((size_t)S << la) + ((size_t)sub << lb);
+        const int KC = 1 << kc;
+#pragma unroll 2
+        for (int kk = 0; kk < KC; ++kk) {
+            const T* ar = sA + (kk << tm);
+            const T* br = sB + (kk << tn);
+            const vec4 a0 = *reinterpret_cast<const vec4*>(ar + m_lo);
+            const vec4 a1 = *reinterpret_cast<const vec4*>(ar + m_hi);
+            const vec4 b0 = *reinterpret_cast<const vec4*>(br + n_lo);
+            const vec4 b1 = *reinterpret_cast<const vec4*>(br + n_hi);
+            const T a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const T b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = Ops<T>::addmax(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    const long long cbase = s_cbase[sub];
+    if (cbase < 0) return;
+    T* __restrict__ Ct = Cg + cbase;
+    uint32_t moff[8], noff[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const uint32_t mi = (i < 4) ? (uint32_t)(m_lo + i) : (uint32_t)(m_hi + i - 4);
+        const uint32_t ni = (i < 4) ? (uint32_t)(n_lo + i) : (uint32_t)(n_hi + i - 4);
+        moff[i] = scatter_bits(mi, sd.c_shift, tm);
+        noff[i] = scatter_bits(ni, sd.c_shift + tm, tn);
+    }
+    if (sd.store_mode == STORE_VEC_M) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int ih = 0; ih < 2; ++ih) {
+                vec4 v;
+                v.x = acc[ih * 4 + 0][j];
+                v.y = acc[ih * 4 + 1][j];
+                v.z = acc[ih * 4 + 2][j];
+                v.w = acc[ih * 4 + 3][j];
+                *reinterpret_cast<vec4*>(Ct + moff[ih * 4] + noff[j]) = v;
+            }
+    } else if (sd.store_mode == STORE_VEC_N) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+                vec4 v;
+                v.x = acc[i][jh * 4 + 0];
+                v.y = acc[i][jh * 4 + 1];
+                v.z = acc[i][jh * 4 + 2];
+                v.w = acc[i][jh * 4 + 3];
+                *reinterpret_cast<vec4*>(Ct + moff[i] + noff[jh * 4]) = v;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) Ct[moff[i] + noff[j]] = acc[i][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// root scalars -> result vector
+// ------------------------------------------------------------------------------------------------
+struct FinalInst {
+    const void* src;
+    int64_t out_index;
+};
+
+template <typename T>
+__global__ void k_finalize(const FinalInst* __restrict__ f, int n, double* __restrict__ results) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) results[f[i].out_index] = Ops<T>::to_double(*reinterpret_cast<const T*>(f[i].src));
+}
+
+template <typename T>
+__global__ void k_to_double(const T* __restrict__ src, double* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = Ops<T>::to_double(src[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: bit-permutation transpose of a 2^rank array of 4-byte elements: bit i of the destination
+// address is bit perm[i] of the source address.  A CTA moves the tile spanned by the union of the low
+// L source bits and the source bits feeding the low L destination bits (<= 2^10 elements) through
+// shared memory: 128-bit coalesced global reads along the source order, 128-bit coalesced global
+// writes along the destination order.
+// ------------------------------------------------------------------------------------------------
+struct PermuteDesc {
+    uint8_t rank, u, ng, pad;
+    uint8_t tile_src_bit[12];   // tile element bit j (source order)  -> source address bit
+    uint8_t tile_dst_bit[12];   // tile element bit j (dest order)    -> destination address bit
+    uint8_t dst_to_src_tile[12];// tile element bit j (dest order)    -> tile element bit (source order)
+    uint8_t grid_src_bit[32];   // grid bit j -> source address bit
+    uint8_t grid_dst_bit[32];   // grid bit j -> destination address bit
+};
+
+__global__ void __launch_bounds__(256) k_permute_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, PermuteDesc d) {
+    __shared__ uint32_t tile[1024 + 32];
+    const int tid = threadIdx.x;
+    const uint64_t g = blockIdx.x;
+    uint64_t sbase = 0, dbase = 0;
+    for (int j = 0; j < d.ng; ++j) {
+        const uint64_t bit = (g >> j) & 1ull;
+        sbase |= bit << d.grid_src_bit[j];
+        dbase |= bit << d.grid_dst_bit[j];
+    }
+    const int n = 1 << d.u;
+    if (d.u >= 2 && d.tile_src_bit[0] == 0 && d.tile_src_bit[1] == 1 && d.tile_dst_bit[0] == 0 && d.tile_dst_bit[1] == 1) {
+        // 128-bit path: 4 consecutive tile elements are 4 consecutive addresses on both sides
+        for (int e = tid * 4; e < n; e += 256 * 4) {
+            uint64_t so = 0;
+            for (int j = 2; j < d.u; ++j) so |= (uint64_t)((e >> j) & 1) << d.tile_src_bit[j];
+            const uint4 v = *reinterpret_cast<const uint4*>(in + sbase + so);
+            tile[(e + 0) + ((e + 0) >> 5)] = v.x;
+            tile[(e + 1) + ((e + 1) >> 5)] = v.y;
+            tile[(e + 2) + ((e + 2) >> 5)] = v.z;
+            tile[(e + 3) + ((e + 3) >> 5)] = v.w;
+        }
+        __syncthreads();
+        for (int f = tid * 4; f < n; f += 256 * 4) {
+            uint64_t dof = 0;
+            uint32_t e0 = 0;
+            for (int j = 2; j < d.u; ++j) {
+                const uint32_t bit = (f >> j) & 1;
+                dof |= (uint64_t)bit << d.tile_dst_bit[j];
+                e0 |= bit << d.dst_to_src_tile[j];
+            }
+            uint32_t r[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t e = e0 | ((q & 1) << d.dst_to_src_tile[0]) | (((q >> 1) & 1) << d.dst_to_src_tile[1]);
+                r[q] = tile[e + (e >> 5)];
+            }
+            *reinterpret_cast<uint4*>(out + dbase + dof) = make_uint4(r[0], r[1], r[2], r[3]);
+        }
+    } else {
+        for (int e = tid; e < n; e += 256) {
+            uint64_t so = 0;
+            for (int j = 0; j < d.u; ++j) so |= (uint64_t)((e >> j) & 1) << d.tile_src_bit[j];
+            tile[e + (e >> 5)] = in[sbase + so];
+        }
+        __syncthreads();
+        for (int f = tid; f < n; f += 256) {
+            uint64_t dof = 0;
+            uint32_t e = 0;
+            for (int j = 0; j < d.u; ++j) {
+                const uint32_t bit = (f >> j) & 1;
+                dof |= (uint64_t)bit << d.tile_dst_bit[j];
+                e |= bit << d.dst_to_src_tile[j];
+            }
+            out[dbase + dof] = tile[e + (e >> 5)];
+        }
+    }
+}
+
+}  // namespace tb

@@ -1,0 +1,60 @@
+// plan.hpp -- host-side plan compiler: contraction tree -> flat, layout-resolved step list.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/tbcuda.h"
+#include "desc.h"
+
+struct tb_ctx;
+
+namespace tb {
+
+struct Plan {
+    // resolved inputs
+    int n_labels = 0;
+    int n_leaves = 0;  // including the synthetic unit leaf of a single-leaf network
+    int n_nodes = 0;
+    uint32_t flags = 0;
+    int value_type = TB_VALUE_I32;
+
+    // per tensor id (leaves, then nodes)
+    std::vector<std::vector<int32_t>> layout;  // labels in address-bit order
+    std::vector<int8_t> loc;                   // LOC_*
+    std::vector<int64_t> off;                  // element offset within loc
+    std::vector<int32_t> level;                // -1 for leaves / interior of fused subtrees
+
+    // descriptors
+    std::vector<uint32_t> pool;  // raw 32-bit values (int32 or float bits)
+    std::vector<SubStep> sub_steps;
+    std::vector<SubTree> subtrees;
+    std::vector<BigStep> big_steps;        // sorted by level (levels start at 1)
+    std::vector<int32_t> big_level_begin;  // big_steps index where level L starts, size n_levels + 2
+    int n_levels = 0;                      // number of levels with big steps (levels 1..n_levels)
+    int64_t arena_elems = 0;
+    int64_t root_off = 0;
+    int32_t root_id = 0;
+
+    tb_plan_stats stats{};
+    std::vector<tb_step_info> info;  // execution order: fused steps first, then big steps by level
+
+    // device residency (managed by the engine)
+    tb_ctx* owner = nullptr;
+    void* d_blob = nullptr;
+    size_t blob_bytes = 0;
+    size_t sub_blob_off = 0, big_blob_off = 0;
+};
+
+// returns a tb_status; on failure `err` holds the message
+int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& plan, std::string& err);
+
+// serialise pool | SubStep[] | BigStep[] (16-byte aligned sections) for upload
+void build_blob(Plan& plan, std::vector<uint8_t>& blob);
+
+}  // namespace tb
+
+// the opaque C handle
+struct tb_plan {
+    tb::Plan p;
+};

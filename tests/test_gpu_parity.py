@@ -1,0 +1,150 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI of
+libtbcuda.so and is compared bit-exactly with the oracle / golden fixtures."""
+import numpy as np
+import pytest
+
+from helpers import align_to, device_tensor_as_ndarray, golden_branches, load_golden, regular_root, to_sliced
+from oracle import tropical_oracle as O
+from workloads import standin_host as H
+
+pytestmark = pytest.mark.gpu
+
+FLAGS = [0, 2, 4, 8, 2 | 8, 2 | 4]
+
+
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
+def test_contract_slices_on_golden(tb, engine, name):
+    rec = load_golden(name + ".json")
+    et = np.dtype(rec["element_type"]).type
+    brs = golden_branches(rec)
+    got = tb.contract_slices([to_sliced(b) for b in brs], et, True, engine=engine)
+    assert got.dtype == np.dtype(et)
+    assert np.array_equal(got.astype(np.float64), np.asarray(rec["values"]))  # bit-exact, per branch
+    assert float(got.max()) == pytest.approx(rec["exact"], rel=1e-6)
+
+
+@pytest.mark.parametrize("n,seed", [(12, 1), (30, 3), (60, 5), (100, 7), (120, 9)])
+@pytest.mark.parametrize("flags", FLAGS)
+def test_single_plan_all_kernel_paths(tb, engine, n, seed, flags):
+    root = regular_root(n, seed)
+    p = tb.Plan(to_sliced(root), flags=flags, engine=engine)
+    assert engine.contract(p) == O.solve_slice(root, np.float64)
+    p.close()
+
+
+@pytest.mark.parametrize("flags", [0, 2, 8])
+def test_weighted_f32_bit_exact(tb, engine, flags):
+    rng = np.random.default_rng(3)
+    nv, edges = H.random_regular_graph(80, 3, 21)
+    w = (1 + rng.random(nv)).astype(np.float32)
+    root = H.make_root(nv, edges, weights=w, seed=3)
+    p = tb.Plan(to_sliced(root), flags=flags, engine=engine)
+    assert np.float32(engine.contract(p)) == O.solve_slice(root, np.float32)
+
+
+def test_float64_weights_with_float32_element_type(tb, engine):
+    # /root/reference/test/slice.jl:41-47: ws = ones(n) (Float64), element_type Float32
+    nv, edges = H.random_regular_graph(40, 3, 2)
+    root = H.make_root(nv, edges, weights=np.ones(nv), seed=2)
+    got = tb.solve_slice(to_sliced(root), np.float32, True, engine=engine)
+    assert got == O.solve_slice(root, np.float32) == O.exact_mis_milp(nv, edges)
+
+
+@pytest.mark.parametrize("flags", [1, 1 | 8, 1 | 4])
+def test_every_node_bit_exact(tb, engine, flags):
+    """node-by-node: every intermediate tensor equals the oracle's (SURVEY 8c oracle plan (1))."""
+    root = regular_root(70, 8)
+    left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+    _, _, inter = O.contract_tree(root.ixs, left, right, None, np.float64, keep_intermediates=True)
+    p = tb.Plan(to_sliced(root), flags=flags, engine=engine)
+    engine.contract(p)
+    kinds = set()
+    for s in p.steps():
+        labels, data = engine.read_tensor(p, s.node)
+        dl, darr = device_tensor_as_ndarray(labels, data)
+        ol, oarr = inter[s.node]
+        assert np.array_equal(align_to(dl, darr, ol), oarr), f"node {s.node} kind {s.kind}"
+        kinds.add(s.kind)
+    if not flags & 4:
+        assert 2 in kinds  # the tiled GEMM kernel was exercised
+
+
+def test_every_node_bit_exact_f32(tb, engine):
+    rng = np.random.default_rng(5)
+    nv, edges = H.random_regular_graph(60, 3, 31)
+    w = (1 + rng.random(nv)).astype(np.float32)
+    root = H.make_root(nv, edges, weights=w, seed=4)
+    left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+    _, _, inter = O.contract_tree(root.ixs, left, right, w, np.float32, keep_intermediates=True)
+    p = tb.Plan(to_sliced(root), flags=1, engine=engine)
+    engine.contract(p)
+    for s in p.steps():
+        labels, data = engine.read_tensor(p, s.node)
+        dl, darr = device_tensor_as_ndarray(labels, data)
+        ol, oarr = inter[s.node]
+        assert np.array_equal(align_to(dl, darr, ol).astype(np.float32), oarr), f"node {s.node}"
+
+
+def test_branching_property_config2_shape(tb, engine):
+    """3-regular n=120 sliced to sc 12: every branch equals the oracle, the max equals the exact MIS
+    (the property of /root/reference/test/slice.jl:32-33 and test/dynamic_ob.jl:20)."""
+    nv, edges = H.random_regular_graph(120, 3, 2)
+    root = H.make_root(nv, edges, seed=2)
+    brs = H.slice_bfs(root, 12)
+    got = tb.contract_slices([to_sliced(b) for b in brs], np.float32, True, engine=engine)
+    want = O.contract_slices(brs, np.float32)
+    assert np.array_equal(got, want)
+    assert float(got.max()) == O.exact_mis_milp(nv, edges)
+
+
+def test_large_tensors_sc20(tb, engine):
+    """one n=150 branch at sc ~20: big GEMM / generic nodes, checked against the oracle root value."""
+    root = regular_root(150, 1000)
+    p = tb.Plan(to_sliced(root), engine=engine)
+    st = p.info()
+    assert st.sc >= 16 and st.n_gemm_steps > 0
+    assert engine.contract(p) == O.solve_slice(root, np.float64)
+    # and with the GEMM kernel disabled: identical
+    q = tb.Plan(to_sliced(root), flags=4, engine=engine)
+    assert engine.contract(q) == engine.contract(p)
+
+
+def test_corner_cases(tb, engine):
+    b1 = tb.SlicedBranch(tb.MISProblem(1, [], None), tb.CompressedEinsum([(0,)], (), None), 3)
+    b2 = tb.SlicedBranch(tb.MISProblem(2, [], None), tb.CompressedEinsum([(0,), (1,)], (), (0, 1)), 0)
+    w = np.array([2.5, 1.0, 4.0], dtype=np.float32)
+    b3 = tb.SlicedBranch(tb.MISProblem(3, [(0, 1)], w), tb.CompressedEinsum([(0,), (1,), (2,), (0, 1)], (), ((0, (1, 3)), 2)), 0.5)
+    b4 = tb.SlicedBranch(tb.MISProblem(0, [], None), None, 9)  # empty graph => r (src/dynamic_ob.jl:39-40)
+    got = tb.contract_slices([b1, b2, b3, b4], np.float32, True, engine=engine)
+    assert list(got) == [4.0, 2.0, 7.0, 9.0]
+    assert tb.contract_slices([], np.float32, True, engine=engine).shape == (0,)
+
+
+def test_batch_api_and_max(tb, engine):
+    rec = load_golden("rr100_sc10_unit.json")
+    brs = golden_branches(rec)
+    plans = [tb.Plan(to_sliced(b), engine=engine) if b.nv else None for b in brs]
+    r = np.array([b.r for b in brs], dtype=np.float64)
+    vals, status, mx = engine.contract_plans(plans, r)
+    assert np.array_equal(vals, np.asarray(rec["values"])) and not status.any()
+    assert mx == rec["exact"]
+    # idempotence: a second run over resident plans gives the same vector
+    vals2, _, _ = engine.contract_plans(plans, r)
+    assert np.array_equal(vals, vals2)
+    ms, launches = engine.last_timing()
+    assert launches > 0 and ms > 0
+
+
+@pytest.mark.parametrize("rank", [0, 1, 3, 7, 12, 20])
+def test_permute_bits(tb, engine, rank):
+    rng = np.random.default_rng(rank)
+    x = rng.integers(-1000, 1000, size=1 << rank, dtype=np.int32)
+    for trial in range(3):
+        perm = list(rng.permutation(rank)) if trial else list(range(rank))[::-1]
+        perm = [int(v) for v in perm]
+        got = engine.permute_bits(x, perm)
+        dst = np.arange(1 << rank, dtype=np.int64)
+        src = np.zeros_like(dst)
+        for i, pbit in enumerate(perm):
+            src |= ((dst >> i) & 1) << pbit
+        assert np.array_equal(got, x[src])

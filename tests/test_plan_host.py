@@ -1,0 +1,142 @@
+"""CPU tests of the host side: C-ABI surface, plan compiler (via the numpy descriptor interpreter),
+error behaviour.  No compute call touches a GPU here."""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+import desc_interp as DI
+from helpers import align_to, device_tensor_as_ndarray, golden_branches, load_golden, regular_root, to_sliced
+from oracle import tropical_oracle as O
+from workloads import standin_host as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(tb):
+    lib = tb.load()
+    hdr = open(os.path.join(ROOT, "include", "tbcuda.h")).read()
+    declared = set(re.findall(r"\b(tb_[a-z_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/tbcuda.h but not exported"
+    assert b"sm_100a" in lib.tb_version()
+
+
+def test_init_without_gpu_fails_loudly(tb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(tb.TBError) as e:
+        tb.Engine(0)
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+
+
+def test_usecuda_false_is_refused(tb):
+    root = regular_root(12, 1)
+    with pytest.raises(tb.TBError):
+        tb.contract_slices([to_sliced(root)], np.float32, False)
+
+
+FLAGS = [0, 2, 4, 8, 2 | 8, 4 | 8]
+
+
+@pytest.mark.parametrize("n,seed", [(12, 1), (30, 3), (60, 5), (100, 7)])
+@pytest.mark.parametrize("flags", FLAGS)
+def test_plan_interpreted_equals_oracle(tb, n, seed, flags):
+    root = regular_root(n, seed)
+    p = tb.Plan(to_sliced(root), flags=flags)
+    val, _ = DI.run_plan(p)
+    assert val == O.solve_slice(root, np.float64)
+    st = p.info()
+    sc, tc = H.tree_complexity(root.ixs, root.tree)
+    assert st.sc == sc and st.tc == pytest.approx(tc)
+    if flags & 2:
+        assert st.n_fused_steps == 0
+    if flags & 4:
+        assert st.n_gemm_steps == 0
+
+
+def test_plan_weighted_f32_bit_exact(tb):
+    rng = np.random.default_rng(3)
+    nv, edges = H.random_regular_graph(60, 3, 21)
+    w = (1 + rng.random(nv)).astype(np.float32)
+    root = H.make_root(nv, edges, weights=w, seed=3)
+    for flags in (0, 2, 8):
+        p = tb.Plan(to_sliced(root), flags=flags)
+        assert p.info().value_type == 2
+        val, _ = DI.run_plan(p)
+        assert np.float32(val) == O.solve_slice(root, np.float32)  # bit-exact: same tree, one rounding per add
+
+
+def test_plan_every_node_matches_oracle(tb):
+    """KEEP_INTERMEDIATES: every node's tensor, in the plan's layout, equals the oracle's."""
+    root = regular_root(40, 8)
+    left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+    _, _, inter = O.contract_tree(root.ixs, left, right, None, np.float64, keep_intermediates=True)
+    for flags in (1, 1 | 8):
+        p = tb.Plan(to_sliced(root), flags=flags)
+        _, arena = DI.run_plan(p)
+        for s in p.steps():
+            labels = [s.labels_c[i] for i in range(s.rank_c)]
+            data = DI.to_float(arena[s.c_offset:s.c_offset + (1 << s.rank_c)], 1)
+            dl, darr = device_tensor_as_ndarray(labels, data)
+            ol, oarr = inter[s.node]
+            assert sorted(dl) == sorted(ol)
+            assert np.array_equal(align_to(dl, darr, ol), oarr), f"node {s.node}"
+
+
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
+def test_plan_on_golden(tb, name):
+    rec = load_golden(name + ".json")
+    et = np.dtype(rec["element_type"]).type
+    for b, want in list(zip(golden_branches(rec), rec["values"]))[:12]:
+        if b.nv == 0:
+            continue
+        p = tb.Plan(to_sliced(b))
+        val, _ = DI.run_plan(p)
+        assert et(et(val) + et(b.r)) == et(want)
+
+
+def test_corner_cases(tb):
+    # single isolated vertex: one leaf, no tree
+    b = tb.SlicedBranch(tb.MISProblem(1, [], None), tb.CompressedEinsum([(0,)], (), None), 0)
+    assert DI.run_plan(tb.Plan(b))[0] == 1.0
+    # two isolated vertices -> outer product of two scalars
+    b = tb.SlicedBranch(tb.MISProblem(2, [], None), tb.CompressedEinsum([(0,), (1,)], (), (0, 1)), 0)
+    assert DI.run_plan(tb.Plan(b))[0] == 2.0
+    # one edge (2-vertex component) + isolated vertex with weights
+    w = np.array([2.5, 1.0, 4.0], dtype=np.float32)
+    b = tb.SlicedBranch(tb.MISProblem(3, [(0, 1)], w), tb.CompressedEinsum([(0,), (1,), (2,), (0, 1)], (), ((0, (1, 3)), 2)), 0)
+    assert DI.run_plan(tb.Plan(b))[0] == 6.5
+
+
+def test_error_codes(tb):
+    lib = tb.load()
+    # non-binary / malformed trees
+    with pytest.raises(ValueError):
+        tb.CompressedEinsum([(0,), (1,), (0, 1)], (), (0, 1, 2))
+    ce = tb.CompressedEinsum([(0,), (1,), (0, 1)], (), None, flat=(np.array([0, 0]), np.array([1, 3])))
+    with pytest.raises(tb.TBError) as e:
+        tb.Plan(tb.SlicedBranch(tb.MISProblem(2, [(0, 1)], None), ce, 0))
+    assert e.value.code == -2
+    # leaf of rank 3 is not an IndependentSet tensor
+    ce = tb.CompressedEinsum([(0, 1, 2), (1,)], (), (0, 1))
+    with pytest.raises(tb.TBError) as e:
+        tb.Plan(tb.SlicedBranch(tb.MISProblem(3, [], None), ce, 0))
+    assert e.value.code == -3
+    # label out of range
+    ce = tb.CompressedEinsum([(0,), (5,)], (), (0, 1))
+    with pytest.raises(tb.TBError) as e:
+        tb.Plan(tb.SlicedBranch(tb.MISProblem(2, [], None), ce, 0))
+    assert e.value.code == -1
+    assert lib.tb_last_error(None)
+
+
+def test_arena_reuse_is_smaller_than_keep(tb):
+    root = regular_root(100, 7)
+    a = tb.Plan(to_sliced(root)).info().arena_elems
+    b = tb.Plan(to_sliced(root), flags=1).info().arena_elems
+    assert a < b
