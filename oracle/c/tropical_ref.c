@@ -48,10 +48,21 @@ static float* permute(const tens* src, const int* order, int n_order) {
         memcpy(out, src->data, n * sizeof(float));
         return out;
     }
-    for (size_t d = 0; d < n; ++d) {
-        size_t s = 0;
-        for (int i = 0; i < n_order; ++i) s |= ((d >> i) & 1u) << sh[i];
-        out[d] = src->data[s];
+    /* byte-wise lookup tables of the bit scatter */
+    size_t lut[5][256];
+    int nbytes = (n_order + 7) / 8;
+    for (int by = 0; by < nbytes; ++by)
+        for (int v = 0; v < 256; ++v) {
+            size_t s = 0;
+            for (int i = 0; i < 8 && by * 8 + i < n_order; ++i) s |= ((size_t)((v >> i) & 1)) << sh[by * 8 + i];
+            lut[by][v] = s;
+        }
+    const float* sd = src->data;
+    for (size_t hi = 0; hi < n; hi += 256) {
+        size_t sb = 0;
+        for (int by = 1; by < nbytes; ++by) sb |= lut[by][(hi >> (8 * by)) & 255];
+        size_t lim = n - hi < 256 ? n - hi : 256;
+        for (size_t lo = 0; lo < lim; ++lo) out[hi + lo] = sd[sb | lut[0][lo]];
     }
     return out;
 }
@@ -84,7 +95,8 @@ static void tropical_gemm(const float* A, const float* B, float* C, int lm, int 
             for (size_t n = 0; n < N; ++n) c[n] = -INFINITY;
             for (size_t k = 0; k < K; ++k) {
                 const float a = Ab[m * K + k];
-                const float* brow = Bb + k * N;
+                const float* __restrict brow = Bb + k * N;
+#pragma omp simd
                 for (size_t n = 0; n < N; ++n) {
                     float v = a + brow[n];
                     c[n] = v > c[n] ? v : c[n];
@@ -173,6 +185,13 @@ int tref_contract(int n_labels, int n_leaves, const int* leaf_off, const int* le
         for (int i = 0; i < B->rank; ++i) {
             int l = B->labels[i];
             if (find_label(A, l) < 0) { cN[nn] = cb[i]; N[nn++] = l; }
+        }
+        if (nn < nm) { /* tropical GEMM is symmetric: make the vectorised inner dimension the larger one */
+            tens* tt = A; A = B; B = tt;
+            int tmp[40];
+            memcpy(tmp, M, sizeof tmp); memcpy(M, N, sizeof tmp); memcpy(N, tmp, sizeof tmp);
+            memcpy(tmp, cM, sizeof tmp); memcpy(cM, cN, sizeof tmp); memcpy(cN, tmp, sizeof tmp);
+            int t2 = nm; nm = nn; nn = t2;
         }
         /* matrix forms: A -> [k | m | b], B -> [n | k | b] */
         int ordA[40], ordB[40], na = 0, nbb = 0;
