@@ -68,6 +68,7 @@ typedef enum tb_weight_dtype {
 #define TB_PLAN_NO_FUSED_SUBTREES 2u  /* testing: run every node as its own step */
 #define TB_PLAN_NO_GEMM 4u            /* testing: never choose the tiled max-plus GEMM kernel */
 #define TB_PLAN_SCRAMBLE_LAYOUT 8u    /* testing: pseudo-random (valid) operand layouts */
+#define TB_PLAN_NO_SPLIT_K 16u        /* testing: never split a long reduction into partial + reduce steps */
 
 typedef struct tb_options {
     int32_t device;          /* CUDA device ordinal */

@@ -22,6 +22,7 @@ TB_PLAN_KEEP_INTERMEDIATES = 1
 TB_PLAN_NO_FUSED_SUBTREES = 2
 TB_PLAN_NO_GEMM = 4
 TB_PLAN_SCRAMBLE_LAYOUT = 8
+TB_PLAN_NO_SPLIT_K = 16
 
 
 class tb_options(C.Structure):

@@ -50,6 +50,13 @@ def _value_type_for(element_type, weight_code):
 
 
 def _network_of(branch: SlicedBranch, element_type, flags=0, keep: Optional[list] = None):
+    """tb_network view of a branch.  The struct only holds pointers into the branch's flat arrays
+    (built once by CompressedEinsum, the analogue of `compress`), so it is cached on the branch."""
+    key = (np.dtype(element_type).name if element_type is not None else None, flags)
+    cache = branch.__dict__.setdefault("_net_cache", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
     code = branch.code
     net = L.tb_network()
     net.n_labels = branch.p.nv
@@ -67,6 +74,7 @@ def _network_of(branch: SlicedBranch, element_type, flags=0, keep: Optional[list
     net.weight_dtype = wcode
     net.value_type = _value_type_for(element_type, wcode)
     net.flags = flags
+    cache[key] = (net, w)  # w is kept alive by the cache entry
     return net, w
 
 
@@ -173,12 +181,11 @@ class Engine:
         returns the contracted values WITHOUT r (float64)."""
         n = len(branches)
         nets = (L.tb_network * max(n, 1))()
-        keep: list = []
         for i, br in enumerate(branches):
             if br.p.nv == 0 or br.code is None:
                 nets[i].n_leaves = 0
             else:
-                nets[i], _ = _network_of(br, element_type, flags, keep)
+                nets[i] = _network_of(br, element_type, flags)[0]
         out = np.empty(n, dtype=np.float64)
         status = np.zeros(n, dtype=np.int32)
         mx = C.c_double()

@@ -72,8 +72,9 @@ struct BigStep {
     uint8_t a_shift[32];
     uint8_t b_shift[32];
     uint8_t c_shift[32];
-    uint8_t ks;  // generic: log2 threads cooperating on one output (block-level split-k), 0 if rc >= 8
-    uint8_t pad[3];
+    uint8_t ks;  // generic: log2 threads of a CTA cooperating on one output (block-level split-k)
+    uint8_t po;  // generic: log2 outputs per CTA (po + ks <= 8); n_tiles = 2^(rc - po)
+    uint8_t pad[2];
 };
 static_assert(sizeof(BigStep) == 144, "BigStep layout");
 

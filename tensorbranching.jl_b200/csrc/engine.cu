@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <memory>
@@ -58,6 +59,11 @@ struct tb_ctx {
     int64_t last_plan_arena_base_elems = 0;  // where tb_contract placed the single plan
     int sm_count = 148;
     bool own_stream = true;
+    static constexpr int kMaxLanes = 8;
+    bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
+    int n_lanes = 4;                       // waves in flight: lane 0 = main stream, others = side streams
+    cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
     bool profile = false;          // per-launch CUDA events, accumulated by kernel kind
     double prof_ms[4] = {0, 0, 0, 0};
     int64_t prof_launches[4] = {0, 0, 0, 0};
@@ -153,43 +159,49 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
         todo.push_back(p);
     }
     if (todo.empty()) return TB_OK;
-    std::vector<std::vector<uint8_t>> blobs(todo.size());
+    // section sizes are known from the plan; blobs are serialised straight into the pinned staging buffer
+    auto a16 = [](size_t x) { return (x + 15) / 16 * 16; };
+    auto blob_size = [&](const Plan& P) {
+        return a16(P.pool.size() * 4) + a16(P.sub_steps.size() * sizeof(SubStep)) + a16(P.big_steps.size() * sizeof(BigStep));
+    };
+    auto write_blob = [&](Plan& P, uint8_t* dst) {
+        size_t pool_b = a16(P.pool.size() * 4), sub_b = a16(P.sub_steps.size() * sizeof(SubStep));
+        P.sub_blob_off = pool_b;
+        P.big_blob_off = pool_b + sub_b;
+        P.blob_bytes = blob_size(P);
+        if (!P.pool.empty()) std::memcpy(dst, P.pool.data(), P.pool.size() * 4);
+        if (!P.sub_steps.empty()) std::memcpy(dst + P.sub_blob_off, P.sub_steps.data(), P.sub_steps.size() * sizeof(SubStep));
+        if (!P.big_steps.empty()) std::memcpy(dst + P.big_blob_off, P.big_steps.data(), P.big_steps.size() * sizeof(BigStep));
+    };
+    std::vector<size_t> bsz(todo.size());
     for (size_t i = 0; i < todo.size(); ++i) {
-        build_blob(todo[i]->p, blobs[i]);
-        total += (blobs[i].size() + 255) / 256 * 256;
+        bsz[i] = (blob_size(todo[i]->p) + 255) / 256 * 256;
+        total += bsz[i];
     }
-    // one new chunk sized for everything that does not fit the current one
     size_t pos = 0;
     while (pos < todo.size()) {
         BlobChunk* ck = ctx->chunks.empty() ? nullptr : &ctx->chunks.back();
-        size_t need = (blobs[pos].size() + 255) / 256 * 256;
-        if (!ck || ck->used + need > ck->cap) {
+        if (!ck || ck->used + bsz[pos] > ck->cap) {
             size_t rest = 0;
-            for (size_t j = pos; j < todo.size(); ++j) rest += (blobs[j].size() + 255) / 256 * 256;
+            for (size_t j = pos; j < todo.size(); ++j) rest += bsz[j];
             BlobChunk nc;
             nc.cap = std::max<size_t>(rest, (size_t)8 << 20);
             TB_CUDA(ctx, cudaMalloc(&nc.d, nc.cap));
             ctx->chunks.push_back(nc);
             ck = &ctx->chunks.back();
         }
-        // pack as many as fit, stage, copy
         size_t first = pos, bytes = 0;
-        while (pos < todo.size()) {
-            size_t nb = (blobs[pos].size() + 255) / 256 * 256;
-            if (ck->used + bytes + nb > ck->cap) break;
-            bytes += nb;
-            ++pos;
-        }
+        while (pos < todo.size() && ck->used + bytes + bsz[pos] <= ck->cap) bytes += bsz[pos++];
         int rc = ensure_stage(ctx, bytes);
         if (rc) return rc;
         TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer may be in flight
         size_t o = 0;
         for (size_t j = first; j < pos; ++j) {
-            std::memcpy((uint8_t*)ctx->h_stage + o, blobs[j].data(), blobs[j].size());
+            write_blob(todo[j]->p, (uint8_t*)ctx->h_stage + o);
             todo[j]->p.d_blob = (uint8_t*)ck->d + ck->used + o;
             todo[j]->p.owner = ctx;
             ck->live++;
-            o += (blobs[j].size() + 255) / 256 * 256;
+            o += bsz[j];
         }
         TB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ck->d + ck->used, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d_bytes += (int64_t)bytes;
@@ -201,10 +213,12 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
 }
 
 struct Launch {
+    int lane;        // stream lane the launch goes to
     int kind;        // 0 fused, 1 generic, 2 gemm, 3 finalize
     int vt;
     size_t inst_off; // byte offset of the instance array in the staging buffer
     size_t starts_off;
+    size_t counter_off;  // gemm v2: a zeroed u32 tile counter inside the staging buffer
     int n_insts;
     uint32_t grid;
     uint32_t smem;
@@ -212,18 +226,25 @@ struct Launch {
 
 template <typename T>
 void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
+    cudaStream_t st = L.lane == 0 ? ctx->stream : ctx->side[L.lane];
     switch (L.kind) {
         case 0:
-            k_fused_subtrees<T><<<L.grid, FUSED_THREADS, L.smem, ctx->stream>>>((const SubInst*)(dbase + L.inst_off), L.n_insts);
+            k_fused_subtrees<T><<<L.grid, FUSED_THREADS, L.smem, st>>>((const SubInst*)(dbase + L.inst_off), L.n_insts);
             break;
         case 1:
-            k_generic<T><<<L.grid, BIG_THREADS, 0, ctx->stream>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
+            k_generic<T><<<L.grid, BIG_THREADS, 0, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             break;
         case 2:
-            k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, ctx->stream>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
+            if (ctx->gemm_v1) {
+                k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
+            } else {
+                const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(2 * ctx->sm_count));
+                k_gemm2<T><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
+                                                                   L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off));
+            }
             break;
         case 3:
-            k_finalize<T><<<(L.n_insts + 127) / 128, 128, 0, ctx->stream>>>((const FinalInst*)(dbase + L.inst_off), L.n_insts, ctx->d_results);
+            k_finalize<T><<<(L.n_insts + 127) / 128, 128, 0, st>>>((const FinalInst*)(dbase + L.inst_off), L.n_insts, ctx->d_results);
             break;
     }
 }
@@ -246,26 +267,28 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     } else if (rc) {
         return rc;
     }
-    // try to grow the arena so that a full wave fits (bounded by the configured limit)
+    const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 64;
+    const int NL = (ctx->profile || single_plan_mode) ? 1 : std::max(1, std::min(ctx->n_lanes, (int)((idx.size() + max_wave - 1) / max_wave)));
+    // try to grow the arena so that NL full waves fit (bounded by the configured limit)
     {
-        size_t total = 0;
-        int cnt = 0;
-        const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 256;
         std::vector<size_t> needs;
-        for (int64_t i : idx) needs.push_back(((size_t)plans[i]->p.arena_elems * elem + 255) / 256 * 256);
-        std::sort(needs.begin(), needs.end(), std::greater<size_t>());
-        for (size_t v : needs) {
-            if (cnt++ >= max_wave) break;
-            total += v;
+        size_t total_all = 0;
+        for (int64_t i : idx) {
+            needs.push_back(((size_t)plans[i]->p.arena_elems * elem + 255) / 256 * 256);
+            total_all += needs.back();
         }
-        if (total > ctx->arena_bytes) {
+        std::sort(needs.begin(), needs.end(), std::greater<size_t>());
+        size_t top = 0;
+        for (size_t q = 0; q < needs.size() && q < (size_t)max_wave; ++q) top += needs[q];
+        size_t target = std::max((size_t)NL * needs[0], std::min(total_all, (size_t)NL * top)) + 4096;
+        if (target > ctx->arena_bytes) {
             size_t want = (size_t)ctx->opts.arena_bytes;
             if (want == 0) {
                 size_t fr = 0, tot = 0;
                 cudaMemGetInfo(&fr, &tot);
                 want = std::min((size_t)((double)(fr + ctx->arena_bytes) * 0.6), (size_t)96 << 30);
             }
-            size_t target = std::min(total, want);
+            target = std::min(target, want);
             if (target > ctx->arena_bytes) {
                 cudaStreamSynchronize(ctx->stream);
                 void* na = nullptr;
@@ -288,12 +311,25 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         std::vector<int64_t> members;
         std::vector<size_t> base;  // arena byte offsets
         int levels = 0;
+        int lane = 0;
     };
-    std::vector<Wave> waves;
+    // lanes own equal arena partitions; a plan too big for a partition runs alone on the whole arena
+    // after everything else ("solo" waves, lane 0)
+    std::vector<Wave> waves, solo;
     {
-        const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 256;
+        const size_t cap = (ctx->arena_bytes / (size_t)NL) / 256 * 256;
         Wave cur;
         size_t used = 0;
+        int lane = 0;
+        auto flush = [&]() {
+            if (cur.members.empty()) return;
+            cur.lane = lane;
+            for (auto& b : cur.base) b += (size_t)lane * cap;
+            waves.push_back(std::move(cur));
+            cur = Wave();
+            used = 0;
+            lane = (lane + 1) % NL;
+        };
         for (int64_t i : idx) {
             const Plan& P = plans[i]->p;
             size_t need = ((size_t)P.arena_elems * elem + 255) / 256 * 256;
@@ -301,29 +337,39 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 status[i] = TB_ERR_OUT_OF_MEMORY;
                 continue;
             }
-            if (!cur.members.empty() && (used + need > ctx->arena_bytes || (int)cur.members.size() >= max_wave)) {
-                waves.push_back(std::move(cur));
-                cur = Wave();
-                used = 0;
+            if (need > cap) {
+                Wave w;
+                w.members.push_back(i);
+                w.base.push_back(0);
+                w.levels = P.n_levels;
+                solo.push_back(std::move(w));
+                continue;
             }
+            if (used + need > cap || (int)cur.members.size() >= max_wave) flush();
             cur.members.push_back(i);
             cur.base.push_back(used);
             cur.levels = std::max(cur.levels, P.n_levels);
             used += need;
         }
-        if (!cur.members.empty()) waves.push_back(std::move(cur));
+        flush();
     }
+    const size_t n_lane_waves = waves.size();
+    for (auto& w : solo) waves.push_back(std::move(w));
     if (single_plan_mode && !waves.empty()) ctx->last_plan_arena_base_elems = 0;
 
     // ---- build work lists for every wave into one host buffer
     std::vector<uint8_t> host;
     std::vector<Launch> launches;
     auto align16 = [&]() { host.resize((host.size() + 15) / 16 * 16); };
-    for (const Wave& w : waves) {
+    size_t first_solo_launch = (size_t)-1;
+    for (size_t wi = 0; wi < waves.size(); ++wi) {
+        const Wave& w = waves[wi];
+        if (wi == n_lane_waves) first_solo_launch = launches.size();
         // level 0: fused subtrees
         {
             align16();
             Launch L{};
+            L.lane = w.lane;
             L.kind = 0;
             L.vt = vt;
             L.inst_off = host.size();
@@ -356,7 +402,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         for (int lv = 1; lv <= w.levels; ++lv) {
             for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
                 std::vector<BigInst> insts;
-                std::vector<uint32_t> starts;
+                std::vector<uint32_t> starts, inst_nk, inst_tiles;
                 uint64_t tiles = 0;
                 for (size_t m = 0; m < w.members.size(); ++m) {
                     const Plan& P = plans[w.members[m]]->p;
@@ -372,13 +418,31 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                         bi.tile_start = (uint32_t)tiles;
                         insts.push_back(bi);
                         starts.push_back((uint32_t)tiles);
+                        inst_nk.push_back(P.big_steps[s].nk);
+                        inst_tiles.push_back(P.big_steps[s].n_tiles);
                         tiles += P.big_steps[s].n_tiles;
                     }
                 }
                 if (insts.empty()) continue;
                 if (tiles > 0x7fffffffull) return set_err(ctx, TB_ERR_UNSUPPORTED, "a level needs more than 2^31 CTAs");
+                if (kind == KIND_GEMM) {
+                    // longest reductions first: the dynamic tile scheduler then fills the tail with short tiles
+                    std::vector<uint32_t> ord(insts.size());
+                    for (size_t q = 0; q < ord.size(); ++q) ord[q] = (uint32_t)q;
+                    std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return inst_nk[x] > inst_nk[y]; });
+                    std::vector<BigInst> si(insts.size());
+                    uint64_t acc_t = 0;
+                    for (size_t q = 0; q < ord.size(); ++q) {
+                        si[q] = insts[ord[q]];
+                        si[q].tile_start = (uint32_t)acc_t;
+                        starts[q] = (uint32_t)acc_t;
+                        acc_t += inst_tiles[ord[q]];
+                    }
+                    insts.swap(si);
+                }
                 align16();
                 Launch L{};
+                L.lane = w.lane;
                 L.kind = kind;
                 L.vt = vt;
                 L.inst_off = host.size();
@@ -388,6 +452,9 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 L.starts_off = host.size();
                 host.resize(host.size() + starts.size() * 4);
                 std::memcpy(host.data() + L.starts_off, starts.data(), starts.size() * 4);
+                align16();
+                L.counter_off = host.size();
+                host.resize(host.size() + 16, 0);
                 L.n_insts = (int)insts.size();
                 L.grid = (uint32_t)tiles;
                 launches.push_back(L);
@@ -397,6 +464,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         {
             align16();
             Launch L{};
+            L.lane = w.lane;
             L.kind = 3;
             L.vt = vt;
             L.inst_off = host.size();
@@ -429,11 +497,32 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         }
         TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[0], ctx->stream));
     }
+    if (NL > 1) {
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        for (int l = 1; l < NL; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+    }
+    auto join_lanes = [&]() -> int {
+        for (int l = 1; l < NL; ++l) {
+            TB_CUDA(ctx, cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
+            TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
+        }
+        return TB_OK;
+    };
+    bool joined = (NL == 1);
     for (size_t li = 0; li < launches.size(); ++li) {
+        if (li == first_solo_launch && !joined) {
+            rc = join_lanes();
+            if (rc) return rc;
+            joined = true;
+        }
         const Launch& L = launches[li];
         if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)ctx->d_stage);
         else launch_one<float>(ctx, L, (uint8_t*)ctx->d_stage);
         if (ctx->profile) TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[li + 1], ctx->stream));
+    }
+    if (!joined) {
+        rc = join_lanes();
+        if (rc) return rc;
     }
     TB_CUDA(ctx, cudaGetLastError());
     TB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -537,10 +626,23 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
     TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     TB_CUDA(nullptr, cudaEventCreate(&c->ev0));
     TB_CUDA(nullptr, cudaEventCreate(&c->ev1));
+    {
+        const char* e1 = getenv("TB_GEMM_V1");
+        c->gemm_v1 = e1 && e1[0] == '1';
+        const char* e2 = getenv("TB_LANES");
+        if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
+    }
+    TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    for (int l = 1; l < c->n_lanes; ++l) {
+        TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking));
+        TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
+    }
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
     *out_ctx = ctx.release();
     return TB_OK;
 }
@@ -559,6 +661,11 @@ int tb_shutdown(tb_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    for (int l = 1; l < tb_ctx::kMaxLanes; ++l) {
+        if (ctx->side[l]) cudaStreamDestroy(ctx->side[l]);
+        if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
+    }
     if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TB_OK;
@@ -606,9 +713,9 @@ int tb_plan_info(const tb_plan* plan, tb_plan_stats* out) {
 
 int tb_plan_export(const tb_plan* plan, tb_step_info* out, int32_t cap) {
     if (!plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "plan is NULL");
-    int n = (int)plan->p.info.size();
+    int n = (int)plan->p.recs.size();
     if (out)
-        for (int i = 0; i < n && i < cap; ++i) out[i] = plan->p.info[i];
+        for (int i = 0; i < n && i < cap; ++i) out[i] = plan->p.step_info((size_t)i);
     return n;
 }
 
@@ -677,7 +784,31 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
             break;
         }
     if (rc == TB_OK) rc = contract_impl(ctx, plans.data(), r, n, out_values, out_status, out_max, false);
-    for (tb_plan* p : plans) tb_plan_destroy(p);
+    // the temporary plans all live in chunks of this call: release the device side once, free hosts in parallel
+    for (tb_plan* p : plans)
+        if (p && p->p.d_blob) {
+            for (auto& c : ctx->chunks)
+                if ((uint8_t*)p->p.d_blob >= (uint8_t*)c.d && (uint8_t*)p->p.d_blob < (uint8_t*)c.d + c.cap) {
+                    if (--c.live == 0) c.used = 0;
+                    break;
+                }
+            p->p.d_blob = nullptr;
+            p->p.owner = nullptr;
+        }
+    {
+        std::atomic<int64_t> nx{0};
+        auto killer = [&]() {
+            for (;;) {
+                int64_t i = nx.fetch_add(64);
+                if (i >= n) break;
+                for (int64_t j = i; j < std::min<int64_t>(n, i + 64); ++j) delete plans[j];
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; ++t) th.emplace_back(killer);
+        killer();
+        for (auto& t : th) t.join();
+    }
     return rc;
 }
 
@@ -686,12 +817,12 @@ int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_da
     if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
     const Plan& P = plan->p;
     if (!(P.flags & TB_PLAN_KEEP_INTERMEDIATES)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan was not created with TB_PLAN_KEEP_INTERMEDIATES");
-    int nT = P.n_leaves + P.n_nodes;
-    if (node < P.n_leaves || node >= nT) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "node id is not an internal node");
-    int rank = (int)P.layout[node].size();
+    if (node < 0 || node >= P.n_tensors || P.loc[node] != LOC_ARENA)
+        return set_err(ctx, TB_ERR_BAD_ARGUMENT, "node id is not an internal node");
+    int rank = P.rank(node);
     if (out_rank) *out_rank = rank;
     if (out_labels)
-        for (int i = 0; i < rank; ++i) out_labels[i] = P.layout[node][i];
+        for (int i = 0; i < rank; ++i) out_labels[i] = P.layout(node)[i];
     int64_t n = (int64_t)1 << rank;
     if (!out_data) return TB_OK;
     if (cap < n) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "output buffer too small");

@@ -64,7 +64,7 @@ constexpr int FUSED_THREADS = 128;
 
 template <typename T>
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst* __restrict__ insts, int n_insts) {
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* smem = reinterpret_cast<T*>(dyn_smem);
     __shared__ uint32_t s_desc[2][12];
     if ((int)blockIdx.x >= n_insts) return;
@@ -132,18 +132,12 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
     const T* __restrict__ A = (sd.a_loc == LOC_POOL ? pool : arena) + sd.a_off;
     const T* __restrict__ B = (sd.b_loc == LOC_POOL ? pool : arena) + sd.b_off;
     T* __restrict__ C = arena + sd.c_off;
-    const int rc = sd.rc, nk = sd.nk, nka = sd.nka, ks = sd.ks;
+    const int rc = sd.rc, nk = sd.nk, nka = sd.nka, ks = sd.ks, po = sd.po;
     const int nkt = nk + nka + sd.nkb;
-    uint32_t c, kp;
-    bool active = true;
-    if (rc >= 8) {
-        c = tile * BIG_THREADS + tid;
-        kp = 0;
-    } else {
-        c = tid & ((1u << rc) - 1u);
-        kp = tid >> rc;
-        active = kp < (1u << ks);
-    }
+    // thread -> (output, k-part): 2^po outputs per CTA, 2^ks threads share one output
+    const uint32_t c = (tile << po) | (tid & ((1u << po) - 1u));
+    const uint32_t kp = (uint32_t)tid >> po;
+    const bool active = kp < (1u << ks);
     T acc = Ops<T>::neg_inf();
     if (active) {
         const uint32_t offA = scatter_bits(c, sd.a_shift, rc);
@@ -166,12 +160,17 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
     if (ks == 0) {
         if (active) C[c] = acc;
     } else {
+        // tree reduction over the k-parts (uniform trip count: ks is per-CTA)
         s_red[tid] = acc;
         __syncthreads();
-        if (active && kp == 0) {
-            for (uint32_t j = 1; j < (1u << ks); ++j) acc = Ops<T>::vmax(acc, s_red[tid + (j << rc)]);
-            C[c] = acc;
+        for (int s = ks - 1; s >= 0; --s) {
+            if (kp < (1u << s)) {
+                acc = Ops<T>::vmax(acc, s_red[tid + ((1u << s) << po)]);
+                s_red[tid] = acc;
+            }
+            __syncthreads();
         }
+        if (kp == 0) C[c] = acc;
     }
 }
 
@@ -192,7 +191,7 @@ template <typename T>
 __global__ void __launch_bounds__(BIG_THREADS, 2) k_gemm(const BigInst* __restrict__ insts,
                                                          const uint32_t* __restrict__ tile_starts, int n_insts) {
     typedef typename Ops<T>::vec4 vec4;
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);
     __shared__ BigStep sd;
     __shared__ long long s_abase[32], s_bbase[32], s_cbase[32];
@@ -325,6 +324,247 @@ __global__ void __launch_bounds__(BIG_THREADS, 2) k_gemm(const BigInst* __restri
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) Ct[moff[i] + noff[j]] = acc[i][j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1/K3 v2: persistent, warp-specialised tiled max-plus GEMM.
+//   warp 8 (producer): fetches tiles from a global counter, decodes the step descriptor, publishes a
+//     TileInfo record and streams the contiguous A / B panels into a 4-stage shared-memory ring with
+//     TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx), running ahead across tile boundaries.
+//   warps 0-7 (consumers): wait on the stage's "full" mbarrier, run the 8x8 DPX microtile loop, release
+//     the stage, and scatter-store the tile when its k loop ends.
+// No __syncthreads in steady state; prologue / epilogue of one tile overlap the k loop of the next.
+// ------------------------------------------------------------------------------------------------
+constexpr int G2_STAGES = 4;
+constexpr int G2_CONSUMERS = 256;
+constexpr int G2_THREADS = G2_CONSUMERS + 32;
+constexpr int G2_SMEM_BYTES = G2_STAGES * GEMM_STAGE_ELEMS * 4;
+
+struct TileInfo {
+    long long cbase[32];  // per sub-tile element offset into C, -1 = inactive
+    void* C;
+    int tm, tn, kc, nchunks, store_mode, valid;
+    unsigned char c_shift[16];
+};
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    unsigned long long spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > (1ull << 26)) __trap();  // a lost arrival must fail loudly, never hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <typename T>
+__global__ void __maxnreg__(112) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
+                                                         int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter) {
+    typedef typename Ops<T>::vec4 vec4;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    T* stage_mem = reinterpret_cast<T*>(dyn_smem);
+    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ TileInfo tinfo[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < G2_STAGES; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], G2_CONSUMERS / 32);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], G2_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= G2_CONSUMERS) {
+        // ------------------------------------------------------------------ producer warp
+        const int lane = tid - G2_CONSUMERS;
+        unsigned it = 0;  // global chunk counter (ring position)
+        for (unsigned tcount = 0;; ++tcount) {
+            unsigned tile_g = 0;
+            if (lane == 0) tile_g = atomicAdd(counter, 1u);
+            tile_g = __shfl_sync(0xffffffffu, tile_g, 0);
+            const int slot = tcount & 1;
+            mbar_wait(&bar_tempty[slot], ((tcount >> 1) & 1) ^ 1);
+            if (tile_g >= total_tiles) {
+                if (lane == 0) {
+                    tinfo[slot].valid = 0;
+                    mbar_arrive(&bar_tfull[slot]);
+                }
+                break;
+            }
+            const int idx = find_inst(tile_starts, n_insts, tile_g);
+            const BigInst inst = insts[idx];
+            const uint32_t tile = tile_g - __ldg(tile_starts + idx);
+            const BigStep* __restrict__ d = inst.step;
+            const int tm = d->tm, tn = d->tn, nk = d->nk, kc = d->kc, ng = d->ng;
+            const int s_log = 8 - (tm + tn - 6), S = 1 << s_log;
+            const T* Ag = reinterpret_cast<const T*>(inst.arena) + d->a_off;
+            const T* Bg = reinterpret_cast<const T*>(inst.arena) + d->b_off;
+            long long ab = -1, bb = -1, cb = -1;
+            if (lane < S) {
+                const unsigned long long g = (unsigned long long)tile * S + lane;
+                if (g < (1ull << ng)) {
+                    const int n_mhi = d->n_mhi, n_nhi = d->n_nhi;
+                    const unsigned long long gm = g & ((1ull << n_mhi) - 1ull);
+                    const unsigned long long gn = (g >> n_mhi) & ((1ull << n_nhi) - 1ull);
+                    const unsigned long long gb = g >> (n_mhi + n_nhi);
+                    ab = (long long)((gm | (gb << n_mhi)) << (tm + nk));
+                    bb = (long long)((gn | (gb << n_nhi)) << (tn + nk));
+                    cb = (long long)scatter_bits((uint32_t)g, d->c_shift + tm + tn, ng);
+                }
+            }
+            TileInfo& ti = tinfo[slot];
+            ti.cbase[lane] = cb;
+            if (lane < 16) ti.c_shift[lane] = (lane < tm + tn) ? d->c_shift[lane] : NO_BIT;
+            if (lane == 0) {
+                ti.C = reinterpret_cast<T*>(inst.arena) + d->c_off;
+                ti.tm = tm;
+                ti.tn = tn;
+                ti.kc = kc;
+                ti.nchunks = 1 << (nk - kc);
+                ti.store_mode = d->store_mode;
+                ti.valid = 1;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tfull[slot]);
+            const int la = kc + tm, lb = kc + tn;
+            const unsigned n_active = __popc(__ballot_sync(0xffffffffu, ab >= 0));
+            const unsigned stage_bytes = n_active * ((1u << la) + (1u << lb)) * 4u;
+            const int nchunks = 1 << (nk - kc);
+            for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                const int stage = it % G2_STAGES;
+                mbar_wait(&bar_empty[stage], ((it / G2_STAGES) & 1) ^ 1);
+                if (lane == 0) mbar_arrive_expect_tx(&bar_full[stage], stage_bytes);
+                __syncwarp();
+                if (ab >= 0) {
+                    T* sA = stage_mem + stage * GEMM_STAGE_ELEMS + ((size_t)lane << la);
+                    T* sB = stage_mem + stage * GEMM_STAGE_ELEMS + ((size_t)S << la) + ((size_t)lane << lb);
+                    bulk_g2s(sA, Ag + ab + ((long long)ch << la), (1u << la) * 4u, &bar_full[stage]);
+                    bulk_g2s(sB, Bg + bb + ((long long)ch << lb), (1u << lb) * 4u, &bar_full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int lane = tid & 31;
+    unsigned it = 0;
+    for (unsigned tcount = 0;; ++tcount) {
+        const int slot = tcount & 1;
+        mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
+        const TileInfo& ti = tinfo[slot];
+        if (!ti.valid) break;
+        const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
+        const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
+        const int sub = tid >> tps_log, lt = tid & ((1 << tps_log) - 1);
+        const int tmh = lt & ((1 << (tm - 3)) - 1), tnh = lt >> (tm - 3);
+        const int m_lo = tmh * 4, m_hi = (1 << (tm - 1)) + tmh * 4;
+        const int n_lo = tnh * 4, n_hi = (1 << (tn - 1)) + tnh * 4;
+        const int la = kc + tm, lb = kc + tn;
+        T acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = Ops<T>::neg_inf();
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int stage = it % G2_STAGES;
+            mbar_wait(&bar_full[stage], (it / G2_STAGES) & 1);
+            const T* sA = stage_mem + stage * GEMM_STAGE_ELEMS + ((size_t)sub << la);
+            const T* sB = stage_mem + stage * GEMM_STAGE_ELEMS + ((size_t)S << la) + ((size_t)sub << lb);
+            const int KC = 1 << kc;
+#pragma unroll 2
+            for (int kk = 0; kk < KC; ++kk) {
+                const T* ar = sA + (kk << tm);
+                const T* br = sB + (kk << tn);
+                const vec4 a0 = *reinterpret_cast<const vec4*>(ar + m_lo);
+                const vec4 a1 = *reinterpret_cast<const vec4*>(ar + m_hi);
+                const vec4 b0 = *reinterpret_cast<const vec4*>(br + n_lo);
+                const vec4 b1 = *reinterpret_cast<const vec4*>(br + n_hi);
+                const T a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const T b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = Ops<T>::addmax(a[i], b[j], acc[i][j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[stage]);
+        }
+        const long long cbase = ti.cbase[sub];
+        if (cbase >= 0) {
+            T* __restrict__ Ct = reinterpret_cast<T*>(ti.C) + cbase;
+            uint32_t moff[8], noff[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const uint32_t mi = (i < 4) ? (uint32_t)(m_lo + i) : (uint32_t)(m_hi + i - 4);
+                const uint32_t ni = (i < 4) ? (uint32_t)(n_lo + i) : (uint32_t)(n_hi + i - 4);
+                moff[i] = scatter_bits(mi, ti.c_shift, tm);
+                noff[i] = scatter_bits(ni, ti.c_shift + tm, tn);
+            }
+            const int store_mode = ti.store_mode;
+            if (store_mode == STORE_VEC_M) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                    for (int ih = 0; ih < 2; ++ih) {
+                        vec4 v;
+                        v.x = acc[ih * 4 + 0][j];
+                        v.y = acc[ih * 4 + 1][j];
+                        v.z = acc[ih * 4 + 2][j];
+                        v.w = acc[ih * 4 + 3][j];
+                        *reinterpret_cast<vec4*>(Ct + moff[ih * 4] + noff[j]) = v;
+                    }
+            } else if (store_mode == STORE_VEC_N) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int jh = 0; jh < 2; ++jh) {
+                        vec4 v;
+                        v.x = acc[i][jh * 4 + 0];
+                        v.y = acc[i][jh * 4 + 1];
+                        v.z = acc[i][jh * 4 + 2];
+                        v.w = acc[i][jh * 4 + 3];
+                        *reinterpret_cast<vec4*>(Ct + moff[i] + noff[jh * 4]) = v;
+                    }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) Ct[moff[i] + noff[j]] = acc[i][j];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[slot]);
     }
 }
 

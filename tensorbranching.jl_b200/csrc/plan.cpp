@@ -2,29 +2,40 @@
 // layout-resolved step list.  Replaces, for the hot path, what the reference does on every
 // solve_slice call: uncompress -> parse_eincode -> decorate (/root/reference/src/types.jl:75-79) and
 // OMEinsum's per-node label analysis + permutedims decisions [upstream].  Pure host C++.
+//
+// Passes: validate -> label sets (bottom-up) -> split-K rewrite (long reductions become a partial step
+// that keeps some reduced labels + a unary max step) -> layouts (top-down, consumer dictates operand
+// layout) -> kinds (fused subtree / generic / tiled GEMM) -> levels -> arena lifetimes -> descriptors.
+//
+// contract_slices compiles thousands of these per call, so everything is flat arrays + O(1) stamp
+// tests; no per-node heap allocation.
 #include "plan.hpp"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <functional>
 #include <limits>
+#ifdef TB_PLAN_PROFILE
+#include <chrono>
+#include <cstdio>
+static double g_pt[16];
+static const char* g_pn[16];
+#define PT(i, name) { auto now_ = std::chrono::steady_clock::now(); g_pt[i] += std::chrono::duration<double, std::micro>(now_ - last_).count(); g_pn[i] = name; last_ = now_; }
+void tb_plan_profile_dump(int reps) { for (int i = 0; i < 16; ++i) if (g_pn[i]) printf("%-12s %8.2f us\n", g_pn[i], g_pt[i] / reps); }
+#else
+#define PT(i, name)
+#endif
 
 namespace tb {
 namespace {
 
-struct Classes {
-    std::vector<int32_t> M, N, Bt, K, KA, KB;
-    int tm = 0, tn = 0;
+struct NodeCls {  // label classes of one contraction, labels stored in cls_data at off in this order
+    int32_t off = 0;
+    uint8_t nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0, tm = 0, tn = 0;
 };
 
-inline bool contains_sorted(const std::vector<int32_t>& v, int32_t x) {
-    return std::binary_search(v.begin(), v.end(), x);
-}
-
 struct FreeList {
-    // sorted, non-adjacent free blocks (offset, size) below `top`
-    std::vector<std::pair<int64_t, int64_t>> blocks;
+    std::vector<std::pair<int64_t, int64_t>> blocks;  // sorted, non-adjacent free blocks below `top`
     int64_t top = 0;
     int64_t alloc(int64_t size) {
         for (size_t i = 0; i < blocks.size(); ++i) {
@@ -36,7 +47,6 @@ struct FreeList {
                 return o;
             }
         }
-        // extend: if the last free block touches top, grow from it
         if (!blocks.empty() && blocks.back().first + blocks.back().second == top) {
             int64_t o = blocks.back().first;
             top = o + size;
@@ -50,7 +60,6 @@ struct FreeList {
     void release(int64_t o, int64_t size) {
         auto it = std::lower_bound(blocks.begin(), blocks.end(), std::make_pair(o, (int64_t)0));
         it = blocks.insert(it, {o, size});
-        // merge with next
         auto nx = it + 1;
         if (nx != blocks.end() && it->first + it->second == nx->first) {
             it->second += nx->second;
@@ -75,10 +84,31 @@ struct Lcg {
         s = s * 6364136223846793005ull + 1442695040888963407ull;
         return (uint32_t)(s >> 33);
     }
-    template <typename V> void shuffle(V& v) {
-        for (size_t i = v.size(); i > 1; --i) std::swap(v[i - 1], v[next() % i]);
+    void shuffle(int32_t* v, int n) {
+        for (int i = n; i > 1; --i) std::swap(v[i - 1], v[next() % i]);
     }
 };
+
+// block-level split-k of the generic kernel: ks thread-bits per output, po output-bits per CTA
+inline void generic_split(int rc, int nkt, int& ks, int& po) {
+    int ks0 = std::min(std::max(nkt - 6, 0), 8);
+    ks = (rc < 8 - ks0) ? std::min(nkt, 8 - rc) : ks0;
+    po = std::min(rc, 8 - ks);
+}
+
+// sort labels v[0..n) by key (small n): insertion sort on (key, label)
+inline void sort_by_key(int32_t* v, const int32_t* key, int n) {
+    for (int i = 1; i < n; ++i) {
+        int32_t x = v[i];
+        int32_t kx = key[x];
+        int j = i - 1;
+        while (j >= 0 && (key[v[j]] > kx || (key[v[j]] == kx && v[j] > x))) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = x;
+    }
+}
 
 }  // namespace
 
@@ -95,18 +125,32 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         return fail(TB_ERR_BAD_ARGUMENT, "node_left / node_right is NULL");
     if (net.n_open < 0 || (net.n_open > 0 && !net.open_labels)) return fail(TB_ERR_BAD_ARGUMENT, "bad open labels");
 
+#ifdef TB_PLAN_PROFILE
+    auto last_ = std::chrono::steady_clock::now();
+#endif
     P.flags = net.flags | extra_flags;
     if (P.flags & TB_PLAN_KEEP_INTERMEDIATES) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;
     P.n_labels = net.n_labels;
     const bool synth = (net.n_leaves == 1);
     const int nL = net.n_leaves + (synth ? 1 : 0);
     const int nN = nL - 1;
-    const int nT = nL + nN;
+    const int nT0 = nL + nN;      // tensors of the given tree
+    const int nTmax = nT0 + 2 * nN;  // + (partial node, unit leaf) per split
     P.n_leaves = nL;
     P.n_nodes = nN;
+    const int NLAB = std::max(net.n_labels, 1);
+
+    // ---- flat per-tensor storage
+    std::vector<int32_t> lch(nTmax, -1), rch(nTmax, -1), parent(nTmax, -1);
+    std::vector<uint8_t> leaf(nTmax, 0), unary(nTmax, 0);
+    std::vector<int32_t> lab_off(nTmax, 0);
+    std::vector<uint8_t> lab_n(nTmax, 0);
+    std::vector<int32_t> lab_data;
+    lab_data.reserve((size_t)nT0 * 8);
+    auto labp = [&](int t) { return lab_data.data() + lab_off[t]; };
 
     // ---- leaves
-    std::vector<std::vector<int32_t>> lab(nT);  // sorted label sets
+    for (int i = 0; i < nL; ++i) leaf[i] = 1;
     for (int i = 0; i < net.n_leaves; ++i) {
         int b = net.leaf_off[i], e = net.leaf_off[i + 1];
         if (e < b) return fail(TB_ERR_BAD_ARGUMENT, "leaf_off not monotone");
@@ -114,46 +158,50 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         if (r < 1 || r > 2)
             return fail(TB_ERR_UNSUPPORTED, "leaf " + std::to_string(i) + " has " + std::to_string(r) +
                                                 " labels; IndependentSet leaves have 1 (vertex) or 2 (edge)");
+        lab_off[i] = (int32_t)lab_data.size();
+        lab_n[i] = (uint8_t)r;
         for (int q = b; q < e; ++q) {
             int32_t l = net.leaf_labels[q];
             if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "leaf label out of range");
-            lab[i].push_back(l);
+            lab_data.push_back(l);
         }
-        if (r == 2 && lab[i][0] == lab[i][1]) return fail(TB_ERR_UNSUPPORTED, "edge tensor with a repeated label (self loop)");
-        std::sort(lab[i].begin(), lab[i].end());
+        if (r == 2) {
+            int32_t* v = lab_data.data() + lab_off[i];
+            if (v[0] == v[1]) return fail(TB_ERR_UNSUPPORTED, "edge tensor with a repeated label (self loop)");
+            if (v[0] > v[1]) std::swap(v[0], v[1]);
+        }
     }
+    if (synth) lab_off[1] = (int32_t)lab_data.size();
 
     // ---- tree
-    std::vector<int32_t> left(nN), right(nN), parent(nT, -1);
     if (synth) {
-        left[0] = 0;
-        right[0] = 1;
+        lch[nL] = 0;
+        rch[nL] = 1;
     } else {
         for (int j = 0; j < nN; ++j) {
-            left[j] = net.node_left[j];
-            right[j] = net.node_right[j];
+            lch[nL + j] = net.node_left[j];
+            rch[nL + j] = net.node_right[j];
         }
     }
     for (int j = 0; j < nN; ++j) {
         int id = nL + j;
-        for (int c : {left[j], right[j]}) {
+        for (int c : {lch[id], rch[id]}) {
             if (c < 0 || c >= id) return fail(TB_ERR_NOT_BINARY_TREE, "node " + std::to_string(j) + ": child id must be in [0, own id)");
             if (parent[c] != -1) return fail(TB_ERR_NOT_BINARY_TREE, "tensor " + std::to_string(c) + " is used twice");
             parent[c] = id;
         }
-        if (left[j] == right[j]) return fail(TB_ERR_NOT_BINARY_TREE, "node contracts a tensor with itself");
+        if (lch[id] == rch[id]) return fail(TB_ERR_NOT_BINARY_TREE, "node contracts a tensor with itself");
     }
-    for (int t = 0; t < nT - 1; ++t)
+    for (int t = 0; t < nT0 - 1; ++t)
         if (parent[t] == -1) return fail(TB_ERR_NOT_BINARY_TREE, "tensor " + std::to_string(t) + " is never contracted (forest, not a tree)");
-    const int root = nT - 1;
+    const int root = nT0 - 1;
     P.root_id = root;
-    auto is_leaf = [&](int t) { return t < nL; };
-    auto L = [&](int t) { return left[t - nL]; };
-    auto R = [&](int t) { return right[t - nL]; };
 
+    PT(0, "validate")
     // ---- weights / value type
     int vt = net.value_type;
     const int wd = net.weight_dtype;
+    if (wd < TB_WEIGHT_UNIT || wd > TB_WEIGHT_F64) return fail(TB_ERR_BAD_ARGUMENT, "unknown weight_dtype");
     if (wd != TB_WEIGHT_UNIT && !net.weights) return fail(TB_ERR_BAD_ARGUMENT, "weights is NULL but weight_dtype is not UNIT");
     auto weight_of = [&](int v) -> double {
         switch (wd) {
@@ -161,43 +209,41 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             case TB_WEIGHT_I32: return (double)((const int32_t*)net.weights)[v];
             case TB_WEIGHT_I64: return (double)((const int64_t*)net.weights)[v];
             case TB_WEIGHT_F32: return (double)((const float*)net.weights)[v];
-            case TB_WEIGHT_F64: return ((const double*)net.weights)[v];
-            default: return std::numeric_limits<double>::quiet_NaN();
+            default: return ((const double*)net.weights)[v];
         }
     };
-    if (wd < TB_WEIGHT_UNIT || wd > TB_WEIGHT_F64) return fail(TB_ERR_BAD_ARGUMENT, "unknown weight_dtype");
     if (vt == TB_VALUE_AUTO) vt = (wd == TB_WEIGHT_F32 || wd == TB_WEIGHT_F64) ? TB_VALUE_F32 : TB_VALUE_I32;
     if (vt == TB_VALUE_I16X2) return fail(TB_ERR_UNSUPPORTED, "value type i16x2 is reserved (not implemented)");
     if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32) return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
     P.value_type = vt;
 
     // ---- leaf positions (DFS order) and subtree ranges
-    std::vector<int32_t> lo(nT, 0), hi(nT, 0);
+    std::vector<int32_t> lo(nT0, 0), hi(nT0, 0);
     {
-        std::vector<int32_t> stack{root};
+        std::vector<int32_t> stack;
+        stack.reserve(64);
+        stack.push_back(root);
         int pos = 0;
-        std::vector<int32_t> leafpos(nL, -1);
         while (!stack.empty()) {
             int t = stack.back();
             stack.pop_back();
-            if (is_leaf(t)) {
-                leafpos[t] = pos++;
+            if (leaf[t]) {
+                lo[t] = hi[t] = pos++;
             } else {
-                stack.push_back(R(t));
-                stack.push_back(L(t));
+                stack.push_back(rch[t]);
+                stack.push_back(lch[t]);
             }
         }
-        for (int t = 0; t < nL; ++t) lo[t] = hi[t] = leafpos[t];
-        for (int t = nL; t < nT; ++t) {
-            lo[t] = std::min(lo[L(t)], lo[R(t)]);
-            hi[t] = std::max(hi[L(t)], hi[R(t)]);
+        for (int t = nL; t < nT0; ++t) {
+            lo[t] = std::min(lo[lch[t]], lo[rch[t]]);
+            hi[t] = std::max(hi[lch[t]], hi[rch[t]]);
         }
     }
-    std::vector<int32_t> minpos(std::max(net.n_labels, 1), std::numeric_limits<int32_t>::max());
-    std::vector<int32_t> maxpos(std::max(net.n_labels, 1), -1);
-    std::vector<uint8_t> is_open(std::max(net.n_labels, 1), 0);
+    std::vector<int32_t> minpos(NLAB, std::numeric_limits<int32_t>::max()), maxpos(NLAB, -1);
+    std::vector<uint8_t> is_open(NLAB, 0);
     for (int i = 0; i < nL; ++i)
-        for (int32_t l : lab[i]) {
+        for (int q = 0; q < lab_n[i]; ++q) {
+            int32_t l = labp(i)[q];
             minpos[l] = std::min(minpos[l], lo[i]);
             maxpos[l] = std::max(maxpos[l], lo[i]);
         }
@@ -208,98 +254,267 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         is_open[l] = 1;
     }
 
-    // ---- label sets bottom-up
-    for (int t = nL; t < nT; ++t) {
-        const auto &a = lab[L(t)], &b = lab[R(t)];
-        std::vector<int32_t> u;
-        u.reserve(a.size() + b.size());
-        std::set_union(a.begin(), a.end(), b.begin(), b.end(), std::back_inserter(u));
-        if ((int)u.size() > 40) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 40 labels");
-        auto& o = lab[t];
-        for (int32_t l : u) {
-            bool closed = !is_open[l] && minpos[l] >= lo[t] && maxpos[l] <= hi[t];
-            if (!closed) o.push_back(l);
+    PT(1, "positions")
+    // ---- label sets bottom-up (ids of the given tree are already topological); sets are sorted
+    for (int t = nL; t < nT0; ++t) {
+        const int A = lch[t], B = rch[t];
+        const int na = lab_n[A], nb = lab_n[B];
+        int32_t u[80];
+        int nu = 0;
+        {
+            const int32_t *a = labp(A), *b = labp(B);
+            int i = 0, j = 0;
+            while (i < na || j < nb) {
+                if (j >= nb || (i < na && a[i] < b[j])) u[nu++] = a[i++];
+                else if (i >= na || b[j] < a[i]) u[nu++] = b[j++];
+                else {
+                    u[nu++] = a[i];
+                    ++i;
+                    ++j;
+                }
+            }
         }
-        if ((int)o.size() > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(o.size()) + " > 31");
-        if ((int)(u.size() - o.size()) > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
+        if (nu > 40) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 40 labels");
+        lab_off[t] = (int32_t)lab_data.size();
+        int no = 0;
+        for (int q = 0; q < nu; ++q) {
+            int32_t l = u[q];
+            bool closed = !is_open[l] && minpos[l] >= lo[t] && maxpos[l] <= hi[t];
+            if (!closed) {
+                lab_data.push_back(l);
+                ++no;
+            }
+        }
+        if (no > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(no) + " > 31");
+        if (nu - no > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
+        lab_n[t] = (uint8_t)no;
     }
 
-    // ---- layouts top-down
-    P.layout.assign(nT, {});
-    std::vector<Classes> cls(nT);
+    PT(2, "labelsets")
+    // stamp arrays for O(1) membership
+    std::vector<int32_t> stA(NLAB, -1), stB(NLAB, -1), stC(NLAB, -1);
+    int stamp = 0;
+
+    // ---- split-K rewrite: node t = contract(A, B) with a long reduction becomes
+    //      u = contract(A, B) keeping `sk` of the shared reduced labels, t = max over those labels of u
+    //      (t = contract(u, unit scalar)).  Balances CTA run times inside a level launch.
+    int nT = nT0;
+    if (!(P.flags & TB_PLAN_NO_SPLIT_K)) {
+        for (int t = nL; t < nT0; ++t) {
+            const int A = lch[t], B = rch[t];
+            if ((int)lab_n[A] + (int)lab_n[B] < 16) continue;  // cannot have a long reduction
+            ++stamp;
+            for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = stamp;
+            for (int q = 0; q < lab_n[t]; ++q) stC[labp(t)[q]] = stamp;
+            int nm = 0, nn = 0, nk = 0, nka = 0, nkb = 0;
+            int32_t Ksh[40];
+            for (int q = 0; q < lab_n[A]; ++q) {
+                int32_t l = labp(A)[q];
+                stA[l] = stamp;
+                bool inB = stB[l] == stamp, inC = stC[l] == stamp;
+                if (inB && !inC) Ksh[nk++] = l;
+                else if (!inB && inC) ++nm;
+                else if (!inB && !inC) ++nka;
+            }
+            for (int q = 0; q < lab_n[B]; ++q) {
+                int32_t l = labp(B)[q];
+                if (stA[l] != stamp) (stC[l] == stamp ? nn : nkb)++;
+            }
+            const int rc = lab_n[t];
+            const bool gemm_like = !(P.flags & TB_PLAN_NO_GEMM) && nm >= 3 && nn >= 3 &&
+                                   std::min(nm, GEMM_TILE_MAX) + std::min(nn, GEMM_TILE_MAX) >= 9 && nk >= 1 && nka == 0 &&
+                                   nkb == 0 && !leaf[A] && !leaf[B];
+            int serial_log, limit;
+            if (gemm_like) {
+                serial_log = nk;
+                limit = 8;
+            } else {
+                int ks, po;
+                generic_split(rc, nk + nka + nkb, ks, po);
+                serial_log = nk + nka + nkb - ks;
+                limit = 7;
+            }
+            if (serial_log <= limit || nk == 0) continue;
+            int sk = std::min(serial_log - limit, gemm_like ? nk - 1 : nk);
+            sk = std::min(sk, MAX_RANK - rc);
+            if (sk <= 0) continue;
+            const int u = nT++, ul = nT++;
+            lch[u] = A;
+            rch[u] = B;
+            parent[u] = t;
+            // lab[u] = lab[t] + the last sk shared reduced labels, sorted
+            {
+                int32_t tmp[48];
+                int n = 0;
+                for (int q = 0; q < rc; ++q) tmp[n++] = labp(t)[q];
+                for (int q = nk - sk; q < nk; ++q) tmp[n++] = Ksh[q];
+                std::sort(tmp, tmp + n);
+                lab_off[u] = (int32_t)lab_data.size();
+                lab_n[u] = (uint8_t)n;
+                lab_data.insert(lab_data.end(), tmp, tmp + n);
+            }
+            leaf[ul] = 1;
+            parent[ul] = t;
+            lab_off[ul] = (int32_t)lab_data.size();
+            lab_n[ul] = 0;
+            parent[A] = parent[B] = u;
+            lch[t] = u;
+            rch[t] = ul;
+            unary[t] = 1;
+        }
+    }
+    P.n_tensors = nT;
+
+    PT(3, "splitk")
+    // ---- topological order of internal nodes (children before parents)
+    std::vector<int32_t> topo;
+    topo.reserve(nT);
+    {
+        std::vector<int32_t> stack;
+        stack.reserve(128);
+        stack.push_back(root);
+        // iterative post-order: negative id = "emit"
+        while (!stack.empty()) {
+            int t = stack.back();
+            stack.pop_back();
+            if (t < 0) {
+                topo.push_back(~t);
+                continue;
+            }
+            if (leaf[t]) continue;
+            stack.push_back(~t);
+            stack.push_back(rch[t]);
+            stack.push_back(lch[t]);
+        }
+    }
+
+    PT(4, "topo")
+    // ---- layouts top-down (the consumer dictates the layout of both of its operands)
+    P.lay_off.assign(nT, 0);
+    P.lay_n.assign(nT, 0);
+    P.lay_data.clear();
+    P.lay_data.reserve(lab_data.size() + 64);
+    std::vector<NodeCls> cls(nT);
+    std::vector<int32_t> cls_data;
+    cls_data.reserve(lab_data.size() * 2);
     {
         if (net.n_open) {
-            std::vector<int32_t> o(net.open_labels, net.open_labels + net.n_open);
-            std::vector<int32_t> s = o;
-            std::sort(s.begin(), s.end());
-            if (s != lab[root]) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
-            P.layout[root] = o;
+            ++stamp;
+            for (int q = 0; q < lab_n[root]; ++q) stC[labp(root)[q]] = stamp;
+            if (net.n_open != lab_n[root]) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
+            for (int i = 0; i < net.n_open; ++i)
+                if (stC[net.open_labels[i]] != stamp) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
+            P.lay_off[root] = 0;
+            P.lay_n[root] = (uint8_t)net.n_open;
+            P.lay_data.insert(P.lay_data.end(), net.open_labels, net.open_labels + net.n_open);
         }
-        std::vector<int32_t> posC(std::max(net.n_labels, 1), -1);
-        auto batch_in = [&](int child, int32_t l) -> int {
-            if (is_leaf(child)) return 0;
-            return contains_sorted(lab[L(child)], l) && contains_sorted(lab[R(child)], l);
-        };
-        for (int t = nT - 1; t >= nL; --t) {
-            const int A = L(t), B = R(t);
-            const auto& lc = P.layout[t];
-            for (size_t i = 0; i < lc.size(); ++i) posC[lc[i]] = (int)i;
-            Classes& c = cls[t];
-            for (int32_t l : lab[A]) {
-                bool inB = contains_sorted(lab[B], l), inC = posC[l] >= 0;
-                if (inB) (inC ? c.Bt : c.K).push_back(l);
-                else (inC ? c.M : c.KA).push_back(l);
+        std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
+        std::vector<int32_t> posC(NLAB, -1);
+        std::vector<int32_t> batA(NLAB, -1), batB(NLAB, -1);  // stamps: label is a batch label inside child A / B
+        const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
+        for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
+            const int t = *it, A = lch[t], B = rch[t];
+            const int sN = ++stamp;  // stamp of this node (stA, stB, batA, batB)
+            const int32_t* lc = P.lay_data.data() + P.lay_off[t];
+            const int rc = P.lay_n[t];
+            for (int i = 0; i < rc; ++i) posC[lc[i]] = i;
+            for (int q = 0; q < lab_n[A]; ++q) stA[labp(A)[q]] = sN;
+            for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = sN;
+            // batch labels of the children (labels shared by a child's own operands)
+            for (int side = 0; side < 2; ++side) {
+                const int ch = side ? B : A;
+                if (leaf[ch]) continue;
+                auto& bat = side ? batB : batA;
+                const int c1 = lch[ch], c2 = rch[ch];
+                const int sS = ++stamp;
+                for (int q = 0; q < lab_n[c1]; ++q) stC[labp(c1)[q]] = sS;
+                for (int q = 0; q < lab_n[c2]; ++q)
+                    if (stC[labp(c2)[q]] == sS) bat[labp(c2)[q]] = sN;
             }
-            for (int32_t l : lab[B]) {
-                if (contains_sorted(lab[A], l)) continue;
-                (posC[l] >= 0 ? c.N : c.KB).push_back(l);
+            int32_t M[40], N[40], Bt[40], K[40], KA[40], KB[40];
+            int nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0;
+            for (int q = 0; q < lab_n[A]; ++q) {
+                int32_t l = labp(A)[q];
+                bool inB = stB[l] == sN, inC = posC[l] >= 0;
+                if (inB) (inC ? Bt[nb++] : K[nk++]) = l;
+                else (inC ? M[nm++] : KA[nka++]) = l;
             }
-            auto key_sort = [&](std::vector<int32_t>& v, int child) {
-                std::sort(v.begin(), v.end(), [&](int32_t x, int32_t y) {
-                    int bx = child >= 0 ? batch_in(child, x) : 0, by = child >= 0 ? batch_in(child, y) : 0;
-                    if (bx != by) return bx < by;
-                    return posC[x] < posC[y];
-                });
-            };
-            key_sort(c.M, A);
-            key_sort(c.N, B);
-            key_sort(c.Bt, -1);
-            std::sort(c.K.begin(), c.K.end(), [&](int32_t x, int32_t y) {
-                int bx = batch_in(A, x) + batch_in(B, x), by = batch_in(A, y) + batch_in(B, y);
-                if (bx != by) return bx < by;
-                return x < y;
-            });
-            if (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) {
+            for (int q = 0; q < lab_n[B]; ++q) {
+                int32_t l = labp(B)[q];
+                if (stA[l] == sN) continue;
+                (posC[l] >= 0 ? N[nn++] : KB[nkb++]) = l;
+            }
+            // M / N: labels that are batch labels inside the producing child go last, then by position in C
+            for (int i = 0; i < nm; ++i) key[M[i]] = ((batA[M[i]] == sN) ? 1024 : 0) + posC[M[i]];
+            sort_by_key(M, key.data(), nm);
+            for (int i = 0; i < nn; ++i) key[N[i]] = ((batB[N[i]] == sN) ? 1024 : 0) + posC[N[i]];
+            sort_by_key(N, key.data(), nn);
+            for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
+            sort_by_key(Bt, key.data(), nb);
+            for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
+            sort_by_key(K, key.data(), nk);
+            if (scramble) {
                 Lcg g((uint64_t)t * 977 + 13);
-                g.shuffle(c.M);
-                g.shuffle(c.N);
-                g.shuffle(c.Bt);
-                g.shuffle(c.K);
-                g.shuffle(c.KA);
-                g.shuffle(c.KB);
+                g.shuffle(M, nm);
+                g.shuffle(N, nn);
+                g.shuffle(Bt, nb);
+                g.shuffle(K, nk);
+                g.shuffle(KA, nka);
+                g.shuffle(KB, nkb);
             }
-            c.tm = std::min<int>((int)c.M.size(), GEMM_TILE_MAX);
-            c.tn = std::min<int>((int)c.N.size(), GEMM_TILE_MAX);
-            auto& la = P.layout[A];
-            la.assign(c.M.begin(), c.M.begin() + c.tm);
-            la.insert(la.end(), c.K.begin(), c.K.end());
-            la.insert(la.end(), c.KA.begin(), c.KA.end());
-            la.insert(la.end(), c.M.begin() + c.tm, c.M.end());
-            la.insert(la.end(), c.Bt.begin(), c.Bt.end());
-            auto& lb = P.layout[B];
-            lb.assign(c.N.begin(), c.N.begin() + c.tn);
-            lb.insert(lb.end(), c.K.begin(), c.K.end());
-            lb.insert(lb.end(), c.KB.begin(), c.KB.end());
-            lb.insert(lb.end(), c.N.begin() + c.tn, c.N.end());
-            lb.insert(lb.end(), c.Bt.begin(), c.Bt.end());
-            for (int32_t l : lc) posC[l] = -1;
+            NodeCls& c = cls[t];
+            c.off = (int32_t)cls_data.size();
+            c.nm = (uint8_t)nm;
+            c.nn = (uint8_t)nn;
+            c.nb = (uint8_t)nb;
+            c.nk = (uint8_t)nk;
+            c.nka = (uint8_t)nka;
+            c.nkb = (uint8_t)nkb;
+            c.tm = (uint8_t)std::min(nm, GEMM_TILE_MAX);
+            c.tn = (uint8_t)std::min(nn, GEMM_TILE_MAX);
+            {
+                const size_t o0 = cls_data.size();
+                cls_data.resize(o0 + nm + nn + nb + nk + nka + nkb);
+                int32_t* w = cls_data.data() + o0;
+                std::memcpy(w, M, nm * 4); w += nm;
+                std::memcpy(w, N, nn * 4); w += nn;
+                std::memcpy(w, Bt, nb * 4); w += nb;
+                std::memcpy(w, K, nk * 4); w += nk;
+                std::memcpy(w, KA, nka * 4); w += nka;
+                std::memcpy(w, KB, nkb * 4);
+            }
+            // A = [M_lo | K | KA | M_hi | Bt],  B = [N_lo | K | KB | N_hi | Bt]
+            {
+                const int ra = nm + nk + nka + nb, rb = nn + nk + nkb + nb;
+                const size_t o0 = P.lay_data.size();
+                P.lay_data.resize(o0 + ra + rb);
+                P.lay_off[A] = (int32_t)o0;
+                P.lay_n[A] = (uint8_t)ra;
+                P.lay_off[B] = (int32_t)(o0 + ra);
+                P.lay_n[B] = (uint8_t)rb;
+                int32_t* w = P.lay_data.data() + o0;
+                std::memcpy(w, M, c.tm * 4); w += c.tm;
+                std::memcpy(w, K, nk * 4); w += nk;
+                std::memcpy(w, KA, nka * 4); w += nka;
+                std::memcpy(w, M + c.tm, (nm - c.tm) * 4); w += nm - c.tm;
+                std::memcpy(w, Bt, nb * 4); w += nb;
+                std::memcpy(w, N, c.tn * 4); w += c.tn;
+                std::memcpy(w, K, nk * 4); w += nk;
+                std::memcpy(w, KB, nkb * 4); w += nkb;
+                std::memcpy(w, N + c.tn, (nn - c.tn) * 4); w += nn - c.tn;
+                std::memcpy(w, Bt, nb * 4);
+            }
+            lc = P.lay_data.data() + P.lay_off[t];  // lay_data may have been reallocated
+            for (int i = 0; i < rc; ++i) posC[lc[i]] = -1;
         }
     }
-    auto rank_of = [&](int t) { return (int)P.layout[t].size(); };
-    auto size_of = [&](int t) { return (int64_t)1 << rank_of(t); };
+    auto rank_of = [&](int t) { return (int)P.lay_n[t]; };
+    auto size_of = [&](int t) { return (int64_t)1 << P.lay_n[t]; };
+    auto layp = [&](int t) { return P.lay_data.data() + P.lay_off[t]; };
 
+    PT(5, "layouts")
     // ---- pool (leaf tensors)
-    std::vector<int64_t> leaf_pool_off(nL, 0);
+    std::vector<int32_t> leaf_pool_off(nT, 0);
     {
         auto push_val = [&](double x, bool neg_inf) {
             uint32_t bits;
@@ -312,47 +527,47 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             }
             P.pool.push_back(bits);
         };
+        P.pool.reserve(8 + 2 * (size_t)nL + 4);
         push_val(0, false); push_val(0, false); push_val(0, false); push_val(0, true);  // edge
         push_val(0, false);                                                            // unit
         push_val(0, false); push_val(0, false); push_val(0, false);                    // pad
         double sum_abs = 0;
-        for (int i = 0; i < nL; ++i) {
-            if (synth && i == 1) {
+        for (int i = 0; i < nT; ++i) {
+            if (!leaf[i]) continue;
+            if (lab_n[i] == 0) {
                 leaf_pool_off[i] = POOL_UNIT;
-            } else if (lab[i].size() == 2) {
+            } else if (lab_n[i] == 2) {
                 leaf_pool_off[i] = POOL_EDGE;
             } else {
-                double w = weight_of(lab[i][0]);
+                double w = weight_of(labp(i)[0]);
                 if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
                 if (vt == TB_VALUE_I32) {
                     if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "value type i32 needs integer weights");
                     sum_abs += std::fabs(w);
                     if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
                 }
-                leaf_pool_off[i] = (int64_t)P.pool.size();
+                leaf_pool_off[i] = (int32_t)P.pool.size();
                 push_val(0, false);
                 push_val(w, false);
             }
         }
         while (P.pool.size() % 4) P.pool.push_back(0);
-        if (P.pool.size() > 65535) {
-            // fused steps address the pool with 16 bits; larger pools simply disable fusion
-            P.flags |= TB_PLAN_NO_FUSED_SUBTREES;
-        }
+        if (P.pool.size() > 65535) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;  // fused steps address the pool with 16 bits
     }
 
+    PT(6, "pool")
     // ---- kinds: fused subtrees / generic / gemm
     std::vector<uint8_t> fus(nT, 0);
     std::vector<int64_t> peak(nT, 0);
     const bool allow_fused = !(P.flags & TB_PLAN_NO_FUSED_SUBTREES);
-    for (int t = nL; t < nT; ++t) {
-        const int A = L(t), B = R(t);
-        const Classes& c = cls[t];
-        int tc = rank_of(t) + (int)(c.K.size() + c.KA.size() + c.KB.size());
+    for (int t : topo) {
+        const int A = lch[t], B = rch[t];
+        const NodeCls& c = cls[t];
+        int tc = rank_of(t) + c.nk + c.nka + c.nkb;
         bool ok = allow_fused && rank_of(t) <= FUSED_MAX_RANK && rank_of(A) <= FUSED_MAX_RANK &&
-                  rank_of(B) <= FUSED_MAX_RANK && tc <= FUSED_MAX_TC && (is_leaf(A) || fus[A]) && (is_leaf(B) || fus[B]);
-        int64_t pA = is_leaf(A) ? 0 : peak[A], sA = is_leaf(A) ? 0 : size_of(A);
-        int64_t pB = is_leaf(B) ? 0 : peak[B], sB = is_leaf(B) ? 0 : size_of(B);
+                  rank_of(B) <= FUSED_MAX_RANK && tc <= FUSED_MAX_TC && (leaf[A] || fus[A]) && (leaf[B] || fus[B]);
+        int64_t pA = leaf[A] ? 0 : peak[A], sA = leaf[A] ? 0 : size_of(A);
+        int64_t pB = leaf[B] ? 0 : peak[B], sB = leaf[B] ? 0 : size_of(B);
         int64_t pk = size_of(t) + (pA >= pB ? std::max(pA, sA + pB) : std::max(pB, sB + pA));
         peak[t] = pk;
         fus[t] = ok && pk <= FUSED_SMEM_ELEMS;
@@ -360,35 +575,40 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     P.loc.assign(nT, LOC_ARENA);
     P.off.assign(nT, 0);
     P.level.assign(nT, -1);
-    for (int i = 0; i < nL; ++i) {
-        P.loc[i] = LOC_POOL;
-        P.off[i] = leaf_pool_off[i];
-    }
+    for (int i = 0; i < nT; ++i)
+        if (leaf[i]) {
+            P.loc[i] = LOC_POOL;
+            P.off[i] = leaf_pool_off[i];
+        }
 
     // ---- levels
-    std::vector<int> kind(nT, -1);
-    for (int t = nL; t < nT; ++t) {
+    std::vector<int8_t> kind(nT, -1);
+    int n_fused_roots = 0, n_big = 0;
+    for (int t : topo) {
         if (fus[t]) {
             kind[t] = KIND_FUSED;
             bool is_sub_root = (t == root) || !fus[parent[t]];
             P.level[t] = is_sub_root ? 0 : -1;
+            n_fused_roots += is_sub_root;
         } else {
             int lv = 1;
-            for (int c : {L(t), R(t)})
-                if (!is_leaf(c)) lv = std::max(lv, P.level[c] + 1);
+            for (int c : {lch[t], rch[t]})
+                if (!leaf[c]) lv = std::max(lv, P.level[c] + 1);
             P.level[t] = lv;
-            const Classes& c = cls[t];
-            bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.M.size() >= 3 && c.N.size() >= 3 && c.tm + c.tn >= 9 &&
-                        c.K.size() >= 1 && c.KA.empty() && c.KB.empty() && !is_leaf(L(t)) && !is_leaf(R(t));
+            const NodeCls& c = cls[t];
+            bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= 3 && c.nn >= 3 && c.tm + c.tn >= 9 && c.nk >= 1 && c.nka == 0 &&
+                        c.nkb == 0 && !leaf[lch[t]] && !leaf[rch[t]];
             kind[t] = gemm ? KIND_GEMM : KIND_GENERIC;
             P.n_levels = std::max(P.n_levels, lv);
+            ++n_big;
         }
     }
 
+    PT(7, "kinds")
     // ---- arena allocation by level intervals
     {
         std::vector<std::vector<int>> born(P.n_levels + 1), dies(P.n_levels + 2);
-        for (int t = nL; t < nT; ++t) {
+        for (int t : topo) {
             if (P.level[t] < 0) continue;
             born[P.level[t]].push_back(t);
             if (t != root) dies[P.level[parent[t]]].push_back(t);
@@ -406,76 +626,102 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         P.root_off = P.off[root];
     }
 
+    PT(8, "arena")
     // ---- emit steps
-    auto fill_info = [&](int t, int knd, int lvl) {
-        tb_step_info s{};
-        const Classes& c = cls[t];
-        s.node = t;
-        s.left = L(t);
-        s.right = R(t);
-        s.kind = knd;
-        s.level = lvl;
-        s.rank_a = rank_of(L(t));
-        s.rank_b = rank_of(R(t));
-        s.rank_c = rank_of(t);
-        s.n_m = (int)c.M.size();
-        s.n_n = (int)c.N.size();
-        s.n_b = (int)c.Bt.size();
-        s.n_k = (int)c.K.size();
-        s.n_ka = (int)c.KA.size();
-        s.n_kb = (int)c.KB.size();
-        s.tile_m = c.tm;
-        s.tile_n = c.tn;
-        s.c_offset = P.off[t];
-        for (int i = 0; i < 32; ++i) s.labels_a[i] = s.labels_b[i] = s.labels_c[i] = -1;
-        for (int i = 0; i < s.rank_a; ++i) s.labels_a[i] = P.layout[L(t)][i];
-        for (int i = 0; i < s.rank_b; ++i) s.labels_b[i] = P.layout[R(t)][i];
-        for (int i = 0; i < s.rank_c; ++i) s.labels_c[i] = P.layout[t][i];
-        return s;
+    std::vector<uint8_t> posA(NLAB, NO_BIT), posB(NLAB, NO_BIT), posCc(NLAB, NO_BIT);
+    auto set_pos = [&](std::vector<uint8_t>& pos, int t, bool on) {
+        const int32_t* v = layp(t);
+        for (int i = 0; i < rank_of(t); ++i) pos[v[i]] = on ? (uint8_t)i : NO_BIT;
     };
-    // position of a label in a layout, NO_BIT if absent
-    auto pos_in = [&](int t, int32_t l) -> uint8_t {
-        const auto& v = P.layout[t];
-        for (size_t i = 0; i < v.size(); ++i)
-            if (v[i] == l) return (uint8_t)i;
-        return NO_BIT;
+    auto rec_of = [&](int t, int knd, int lvl) {
+        const NodeCls& c = cls[t];
+        Plan::StepRec r{};
+        r.node = t;
+        r.left = lch[t];
+        r.right = rch[t];
+        r.kind = (int8_t)knd;
+        r.level = lvl;
+        r.nm = c.nm;
+        r.nn = c.nn;
+        r.nb = c.nb;
+        r.nk = c.nk;
+        r.nka = c.nka;
+        r.nkb = c.nkb;
+        r.tm = c.tm;
+        r.tn = c.tn;
+        return r;
     };
     double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, sc = 0;
-    for (int t = 0; t < nT; ++t) sc = std::max(sc, (double)rank_of(t));
+    for (int t = 0; t < nT0; ++t) sc = std::max(sc, (double)lab_n[t]);
     auto account = [&](int t, int knd) {
-        const Classes& c = cls[t];
-        int tc = rank_of(t) + (int)(c.K.size() + c.KA.size() + c.KB.size());
-        double o = std::ldexp(1.0, tc);
-        (knd == KIND_FUSED ? ops_f : knd == KIND_GENERIC ? ops_g : ops_m) += o;
-        bytes += 4.0 * (std::ldexp(1.0, rank_of(L(t))) + std::ldexp(1.0, rank_of(R(t))) + std::ldexp(1.0, rank_of(t)));
+        const NodeCls& c = cls[t];
+        auto p2 = [](int e) { return (double)(1ull << e); };
+        int tc = rank_of(t) + c.nk + c.nka + c.nkb;
+        if (unary[t]) {  // second half of a split node: engine overhead, not algorithmic work
+            bytes += 4.0 * p2(rank_of(t));
+            return;
+        }
+        (knd == KIND_FUSED ? ops_f : knd == KIND_GENERIC ? ops_g : ops_m) += p2(tc);
+        double cb = (t >= nT0) ? 0.0 : p2(rank_of(t));  // a partial node's output is not algorithmic traffic
+        bytes += 4.0 * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + cb);
     };
+    P.recs.reserve(topo.size());
+    P.sub_steps.reserve(topo.size() - n_big);
+    P.subtrees.reserve(n_fused_roots);
+    P.big_steps.reserve(n_big);
 
-    // fused subtrees: post-order with "reserve C, then children above it" shared-memory stack
-    for (int t = nL; t < nT; ++t) {
+    // fused subtrees: post-order with a "reserve C, then children above it" shared-memory stack
+    struct Frame {
+        int x;
+        int64_t base;
+        bool is_root;
+        int stage;
+        int64_t cur;
+    };
+    std::vector<Frame> stack;
+    for (int t : topo) {
         if (kind[t] != KIND_FUSED || P.level[t] != 0) continue;
         SubTree st{};
         st.first_step = (uint32_t)P.sub_steps.size();
         st.out_off = P.off[t];
         int64_t max_top = 0;
-        std::function<void(int, int64_t, bool)> emit = [&](int x, int64_t base, bool is_root) {
-            const int A = L(x), B = R(x);
-            int64_t above = base;
-            if (!is_root) {
-                P.loc[x] = LOC_SMEM;
-                P.off[x] = base;
-                above = base + size_of(x);
+        stack.clear();
+        stack.push_back({t, 0, true, 0, 0});
+        while (!stack.empty()) {
+            Frame& f = stack.back();
+            const int x = f.x, A = lch[x], B = rch[x];
+            int64_t pA = leaf[A] ? 0 : peak[A], pB = leaf[B] ? 0 : peak[B];
+            const int first = pA >= pB ? A : B, second = pA >= pB ? B : A;
+            if (f.stage == 0) {
+                int64_t above = f.base;
+                if (!f.is_root) {
+                    P.loc[x] = LOC_SMEM;
+                    P.off[x] = f.base;
+                    above = f.base + size_of(x);
+                }
+                max_top = std::max(max_top, above);
+                f.cur = above;
+                f.stage = 1;
+                if (!leaf[first]) {
+                    Frame nf{first, f.cur, false, 0, 0};
+                    f.cur += size_of(first);
+                    max_top = std::max(max_top, f.cur);
+                    stack.push_back(nf);
+                    continue;
+                }
             }
-            max_top = std::max(max_top, above);
-            int64_t pA = is_leaf(A) ? 0 : peak[A], pB = is_leaf(B) ? 0 : peak[B];
-            int first = pA >= pB ? A : B, second = pA >= pB ? B : A;
-            int64_t cur = above;
-            for (int ch : {first, second}) {
-                if (is_leaf(ch)) continue;
-                emit(ch, cur, false);
-                cur += size_of(ch);
-                max_top = std::max(max_top, cur);
+            if (f.stage == 1) {
+                f.stage = 2;
+                if (!leaf[second]) {
+                    Frame nf{second, f.cur, false, 0, 0};
+                    f.cur += size_of(second);
+                    max_top = std::max(max_top, f.cur);
+                    stack.push_back(nf);
+                    continue;
+                }
             }
-            const Classes& c = cls[x];
+            const NodeCls& c = cls[x];
+            const bool is_root = f.is_root;
             SubStep s{};
             s.a_off = (uint16_t)P.off[A];
             s.b_off = (uint16_t)P.off[B];
@@ -484,37 +730,49 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             s.b_loc = (uint8_t)P.loc[B];
             s.c_loc = is_root ? LOC_ARENA : LOC_SMEM;
             s.rc = (uint8_t)rank_of(x);
-            s.nk = (uint8_t)c.K.size();
-            s.nka = (uint8_t)c.KA.size();
-            s.nkb = (uint8_t)c.KB.size();
-            s.sa = (uint8_t)c.tm;
-            s.sb = (uint8_t)c.tn;
-            std::memset(s.a_shift, NO_BIT, sizeof s.a_shift);
-            std::memset(s.b_shift, NO_BIT, sizeof s.b_shift);
-            for (int i = 0; i < rank_of(x); ++i) {
-                s.a_shift[i] = pos_in(A, P.layout[x][i]);
-                s.b_shift[i] = pos_in(B, P.layout[x][i]);
+            s.nk = c.nk;
+            s.nka = c.nka;
+            s.nkb = c.nkb;
+            s.sa = c.tm;
+            s.sb = c.tn;
+            std::memset(s.a_shift, NO_BIT, sizeof s.a_shift + sizeof s.b_shift);
+            {
+                // position of each output label in A / B: stamp the (short) output, then walk A and B once
+                const int32_t* lx = layp(x);
+                const int rx = rank_of(x);
+                for (int i = 0; i < rx; ++i) posCc[lx[i]] = (uint8_t)i;
+                const int32_t* la_ = layp(A);
+                for (int i = 0, ra_ = rank_of(A); i < ra_; ++i)
+                    if (posCc[la_[i]] != NO_BIT) s.a_shift[posCc[la_[i]]] = (uint8_t)i;
+                const int32_t* lb_ = layp(B);
+                for (int i = 0, rb_ = rank_of(B); i < rb_; ++i)
+                    if (posCc[lb_[i]] != NO_BIT) s.b_shift[posCc[lb_[i]]] = (uint8_t)i;
+                for (int i = 0; i < rx; ++i) posCc[lx[i]] = NO_BIT;
             }
             P.sub_steps.push_back(s);
-            P.info.push_back(fill_info(x, KIND_FUSED, 0));
+            P.recs.push_back(rec_of(x, KIND_FUSED, 0));
             account(x, KIND_FUSED);
-        };
-        emit(t, 0, true);
+            stack.pop_back();
+        }
         st.n_steps = (uint32_t)P.sub_steps.size() - st.first_step;
         st.smem_elems = (uint32_t)max_top;
         P.subtrees.push_back(st);
     }
 
+    PT(9, "fused_emit")
     // big steps by level
     {
         std::vector<int> order;
-        for (int t = nL; t < nT; ++t)
+        order.reserve(n_big);
+        for (int t : topo)
             if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) order.push_back(t);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.level[x] < P.level[y]; });
         P.big_level_begin.assign(P.n_levels + 2, 0);
         for (int t : order) {
-            const Classes& c = cls[t];
-            const int A = L(t), B = R(t);
+            const NodeCls& c = cls[t];
+            const int32_t* cd = cls_data.data() + c.off;
+            const int32_t *cM = cd, *cN = cd + c.nm, *cBt = cd + c.nm + c.nn;
+            const int A = lch[t], B = rch[t];
             BigStep s{};
             s.a_off = P.off[A];
             s.b_off = P.off[B];
@@ -523,42 +781,46 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             s.b_loc = (uint8_t)P.loc[B];
             s.kind = (uint8_t)kind[t];
             s.rc = (uint8_t)rank_of(t);
-            s.nk = (uint8_t)c.K.size();
-            s.nka = (uint8_t)c.KA.size();
-            s.nkb = (uint8_t)c.KB.size();
-            s.sa = (uint8_t)c.tm;
-            s.sb = (uint8_t)c.tn;
-            s.tm = (uint8_t)c.tm;
-            s.tn = (uint8_t)c.tn;
+            s.nk = c.nk;
+            s.nka = c.nka;
+            s.nkb = c.nkb;
+            s.sa = c.tm;
+            s.sb = c.tn;
+            s.tm = c.tm;
+            s.tn = c.tn;
             std::memset(s.a_shift, NO_BIT, 32);
             std::memset(s.b_shift, NO_BIT, 32);
             std::memset(s.c_shift, NO_BIT, 32);
             if (kind[t] == KIND_GENERIC) {
+                set_pos(posA, A, true);
+                set_pos(posB, B, true);
+                const int32_t* lt = layp(t);
                 for (int i = 0; i < rank_of(t); ++i) {
-                    s.a_shift[i] = pos_in(A, P.layout[t][i]);
-                    s.b_shift[i] = pos_in(B, P.layout[t][i]);
+                    s.a_shift[i] = posA[lt[i]];
+                    s.b_shift[i] = posB[lt[i]];
                     s.c_shift[i] = (uint8_t)i;
                 }
-                int nkt = s.nk + s.nka + s.nkb;
-                if (s.rc >= 8) {
-                    s.ks = 0;
-                    s.n_tiles = 1u << (s.rc - 8);
-                } else {
-                    s.ks = (uint8_t)std::min(8 - s.rc, nkt);
-                    s.n_tiles = 1;
-                }
+                set_pos(posA, A, false);
+                set_pos(posB, B, false);
+                int ks, po;
+                generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
+                s.ks = (uint8_t)ks;
+                s.po = (uint8_t)po;
+                s.n_tiles = 1u << (s.rc - po);
             } else {
+                set_pos(posCc, t, true);
                 int q = 0;
-                for (int i = 0; i < c.tm; ++i) s.c_shift[q++] = pos_in(t, c.M[i]);
-                for (int i = 0; i < c.tn; ++i) s.c_shift[q++] = pos_in(t, c.N[i]);
-                for (size_t i = c.tm; i < c.M.size(); ++i) s.c_shift[q++] = pos_in(t, c.M[i]);
-                for (size_t i = c.tn; i < c.N.size(); ++i) s.c_shift[q++] = pos_in(t, c.N[i]);
-                for (int32_t l : c.Bt) s.c_shift[q++] = pos_in(t, l);
-                s.n_mhi = (uint8_t)(c.M.size() - c.tm);
-                s.n_nhi = (uint8_t)(c.N.size() - c.tn);
+                for (int i = 0; i < c.tm; ++i) s.c_shift[q++] = posCc[cM[i]];
+                for (int i = 0; i < c.tn; ++i) s.c_shift[q++] = posCc[cN[i]];
+                for (int i = c.tm; i < c.nm; ++i) s.c_shift[q++] = posCc[cM[i]];
+                for (int i = c.tn; i < c.nn; ++i) s.c_shift[q++] = posCc[cN[i]];
+                for (int i = 0; i < c.nb; ++i) s.c_shift[q++] = posCc[cBt[i]];
+                set_pos(posCc, t, false);
+                s.n_mhi = (uint8_t)(c.nm - c.tm);
+                s.n_nhi = (uint8_t)(c.nn - c.tn);
                 s.ng = (uint8_t)(s.rc - c.tm - c.tn);
-                int tps_log = (c.tm - 3) + (c.tn - 3);          // threads per sub-tile
-                int s_log = 8 - tps_log;                        // sub-tiles per CTA (256 threads)
+                int tps_log = (c.tm - 3) + (c.tn - 3);  // threads per sub-tile
+                int s_log = 8 - tps_log;                // sub-tiles per CTA (256 threads)
                 int64_t per_k = ((int64_t)1 << s_log) * (((int64_t)1 << c.tm) + ((int64_t)1 << c.tn));
                 int kc = 0;
                 while (kc + 1 <= s.nk && (per_k << (kc + 1)) <= GEMM_STAGE_ELEMS) ++kc;
@@ -571,10 +833,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 else if (s.c_shift[c.tm] == 0 && s.c_shift[c.tm + 1] == 1) s.store_mode = STORE_VEC_N;
             }
             P.big_steps.push_back(s);
-            P.info.push_back(fill_info(t, kind[t], P.level[t]));
+            P.recs.push_back(rec_of(t, kind[t], P.level[t]));
             account(t, kind[t]);
         }
-        // level offsets
         int idx = 0;
         for (int lv = 1; lv <= P.n_levels + 1; ++lv) {
             while (idx < (int)order.size() && P.level[order[idx]] < lv) ++idx;
@@ -583,6 +844,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         P.big_level_begin[0] = 0;
     }
 
+    PT(10, "big_emit")
     tb_plan_stats& S = P.stats;
     S.sc = sc;
     S.ops = ops_f + ops_g + ops_m;
@@ -602,6 +864,33 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     S.fused_ops = ops_f;
     S.generic_ops = ops_g;
     return TB_OK;
+}
+
+tb_step_info Plan::step_info(size_t i) const {
+    const StepRec& r = recs[i];
+    tb_step_info s{};
+    s.node = r.node;
+    s.left = r.left;
+    s.right = r.right;
+    s.kind = r.kind;
+    s.level = r.level;
+    s.rank_a = rank(r.left);
+    s.rank_b = rank(r.right);
+    s.rank_c = rank(r.node);
+    s.n_m = r.nm;
+    s.n_n = r.nn;
+    s.n_b = r.nb;
+    s.n_k = r.nk;
+    s.n_ka = r.nka;
+    s.n_kb = r.nkb;
+    s.tile_m = r.tm;
+    s.tile_n = r.tn;
+    s.c_offset = off[r.node];
+    for (int q = 0; q < 32; ++q) s.labels_a[q] = s.labels_b[q] = s.labels_c[q] = -1;
+    for (int q = 0; q < s.rank_a; ++q) s.labels_a[q] = layout(r.left)[q];
+    for (int q = 0; q < s.rank_b; ++q) s.labels_b[q] = layout(r.right)[q];
+    for (int q = 0; q < s.rank_c; ++q) s.labels_c[q] = layout(r.node)[q];
+    return s;
 }
 
 void build_blob(Plan& P, std::vector<uint8_t>& blob) {

@@ -19,8 +19,12 @@ struct Plan {
     uint32_t flags = 0;
     int value_type = TB_VALUE_I32;
 
-    // per tensor id (leaves, then nodes)
-    std::vector<std::vector<int32_t>> layout;  // labels in address-bit order
+    // per tensor id (leaves, then nodes, then synthetic split-K tensors)
+    std::vector<int32_t> lay_off;              // layout of tensor t = lay_data[lay_off[t] .. +lay_n[t])
+    std::vector<uint8_t> lay_n;                //   labels in address-bit order (bit 0 first)
+    std::vector<int32_t> lay_data;
+    int rank(int t) const { return lay_n[t]; }
+    const int32_t* layout(int t) const { return lay_data.data() + lay_off[t]; }
     std::vector<int8_t> loc;                   // LOC_*
     std::vector<int64_t> off;                  // element offset within loc
     std::vector<int32_t> level;                // -1 for leaves / interior of fused subtrees
@@ -37,7 +41,16 @@ struct Plan {
     int32_t root_id = 0;
 
     tb_plan_stats stats{};
-    std::vector<tb_step_info> info;  // execution order: fused steps first, then big steps by level
+    // execution order (fused steps first, then big steps by level); tb_step_info is built on demand
+    struct StepRec {
+        int32_t node, left, right;
+        int8_t kind;
+        int32_t level;
+        uint8_t nm, nn, nb, nk, nka, nkb, tm, tn;
+    };
+    std::vector<StepRec> recs;
+    int n_tensors = 0;  // leaves + nodes + synthetic (split-K) tensors
+    tb_step_info step_info(size_t i) const;
 
     // device residency (managed by the engine)
     tb_ctx* owner = nullptr;

@@ -9,7 +9,7 @@ from workloads import standin_host as H
 
 pytestmark = pytest.mark.gpu
 
-FLAGS = [0, 2, 4, 8, 2 | 8, 2 | 4]
+FLAGS = [0, 2, 4, 8, 16, 2 | 8, 2 | 4, 4 | 16]
 
 
 @pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
@@ -60,6 +60,8 @@ def test_every_node_bit_exact(tb, engine, flags):
     engine.contract(p)
     kinds = set()
     for s in p.steps():
+        if s.node not in inter:
+            continue  # synthetic split-K partial tensor: no counterpart in the reference's tree
         labels, data = engine.read_tensor(p, s.node)
         dl, darr = device_tensor_as_ndarray(labels, data)
         ol, oarr = inter[s.node]
@@ -79,6 +81,8 @@ def test_every_node_bit_exact_f32(tb, engine):
     p = tb.Plan(to_sliced(root), flags=1, engine=engine)
     engine.contract(p)
     for s in p.steps():
+        if s.node not in inter:
+            continue
         labels, data = engine.read_tensor(p, s.node)
         dl, darr = device_tensor_as_ndarray(labels, data)
         ol, oarr = inter[s.node]
@@ -107,6 +111,56 @@ def test_large_tensors_sc20(tb, engine):
     # and with the GEMM kernel disabled: identical
     q = tb.Plan(to_sliced(root), flags=4, engine=engine)
     assert engine.contract(q) == engine.contract(p)
+
+
+@pytest.mark.parametrize("n,seed", [(130, 5), (150, 1000)])
+def test_split_k_and_every_node_large(tb, engine, n, seed):
+    """sc ~22 branches: long reductions are split into partial + reduce steps; every ORIGINAL node of the
+    tree still holds exactly the oracle's tensor."""
+    from oracle import c_oracle as CO
+    root = regular_root(n, seed)
+    want = CO.contract_slices([root], np.float32)[0]
+    vals = {}
+    for flags in (0, 16, 4, 8):
+        p = tb.Plan(to_sliced(root), flags=flags, engine=engine)
+        vals[flags] = engine.contract(p)
+        p.close()
+    assert all(v == want for v in vals.values()), (vals, want)
+    p = tb.Plan(to_sliced(root), flags=0, engine=engine)
+    assert any(s.node >= 2 * len(root.ixs) - 1 for s in p.steps())  # split-K really happened
+
+
+def test_gemm_v1_kernel_agrees(tb):
+    """the non-persistent cp.async GEMM (TB_GEMM_V1=1) and the persistent TMA GEMM give identical tensors."""
+    import os
+    root = regular_root(120, 9)
+    os.environ["TB_GEMM_V1"] = "1"
+    try:
+        e1 = tb.Engine(0)
+    finally:
+        del os.environ["TB_GEMM_V1"]
+    e2 = tb.Engine(0)
+    for flags in (1, 1 | 8):
+        p1 = tb.Plan(to_sliced(root), flags=flags, engine=e1)
+        p2 = tb.Plan(to_sliced(root), flags=flags, engine=e2)
+        assert e1.contract(p1) == e2.contract(p2) == O.solve_slice(root, np.float64)
+        for s in p1.steps():
+            if s.kind == 2:
+                l1, d1 = e1.read_tensor(p1, s.node)
+                l2, d2 = e2.read_tensor(p2, s.node)
+                assert l1 == l2 and np.array_equal(d1, d2)
+    e1.close()
+    e2.close()
+
+
+def test_many_lanes_and_small_waves(tb):
+    """multi-stream lanes with tiny waves: same per-branch vector as the oracle."""
+    rec = load_golden("rr100_sc10_unit.json")
+    brs = golden_branches(rec)
+    eng = tb.Engine(0, max_wave=4)
+    got = tb.contract_slices([to_sliced(b) for b in brs], np.float32, True, engine=eng)
+    assert np.array_equal(got.astype(np.float64), np.asarray(rec["values"]))
+    eng.close()
 
 
 def test_corner_cases(tb, engine):
