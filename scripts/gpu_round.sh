@@ -9,15 +9,17 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 nproc > $OUT/host_cores.txt; lscpu | grep -E "Model name|Flags" | cut -c1-400 >> $OUT/host_cores.txt
 timeout 300 python -c "import __graft_entry__ as g; g.build()" > $OUT/build.log 2>&1
 echo "== dpx_peak"; timeout 120 ./tensorbranching.jl_b200/dpx_peak | tee $OUT/dpx_peak.json
-echo "== pytest gpu"; timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/pytest_gpu.log
+echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.log
 echo "== bench cfg1"; timeout 600 python bench.py --workload cfg1 --steps 5 --warmup 3 2>&1 | tail -3 | tee $OUT/bench_cfg1.json
 echo "== bench $WL"; timeout 1500 python bench.py --workload $WL --steps 5 --warmup 3 2>&1 | tail -3 | tee $OUT/bench_$WL.json
+echo "== bench $WL gemm v1"; TB_GEMM_V1=1 timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee $OUT/bench_${WL}_gemmv1.json
+echo "== bench $WL 1 lane"; TB_LANES=1 timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee $OUT/bench_${WL}_1lane.json
 echo "== bench reference"; timeout 900 python bench.py --impl reference --workload $WL --steps 2 --warmup 1 2>&1 | tail -2 | tee $OUT/bench_ref_$WL.json
 echo "== ncu launches"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
     python bench.py --workload $WL --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_launches.log 2>&1
 echo "== ncu full (gemm)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gemm -s 20 -c 3 -o $OUT/prof_gemm \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_gemm -s 24 -c 4 -o $OUT/prof_gemm \
     python bench.py --workload $WL --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $OUT/ncu_full.log 2>&1
 ls -la $OUT

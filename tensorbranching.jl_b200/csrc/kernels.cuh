@@ -361,7 +361,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     unsigned done = 0;
-    unsigned long long spins = 0;
+    long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n"
@@ -372,7 +372,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && ++spins > (1ull << 26)) __trap();  // a lost arrival must fail loudly, never hang the GPU
+        if (!done) {  // a lost arrival must fail loudly (~2 s), never hang the GPU
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) __trap();
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
