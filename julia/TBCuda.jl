@@ -1,0 +1,120 @@
+# TBCuda.jl -- reference-side binding of libtbcuda.so (UNTESTED in this repository's image: no Julia
+# toolchain is available there; written against include/tbcuda.h).
+#
+# Drop-in for the hot path of TensorBranching.jl:
+#     TensorBranching.solve_slice(branch, element_type, usecuda)      src/dynamic_ob.jl:30-34
+#     TensorBranching.contract_slices(branches, element_type, usecuda) src/dynamic_ob.jl:36-48
+# With `using TBCuda`, calls with usecuda=true are routed to the B200 engine; usecuda=false keeps the
+# reference's own CPU route (TropicalGEMM).
+module TBCuda
+
+using TensorBranching
+using TensorBranching: SlicedBranch, CompressedEinsum
+using OMEinsum.OMEinsumContractionOrders: ContractionTree
+using Graphs: nv
+
+const LIB = get(ENV, "LIBTBCUDA", "libtbcuda.so")
+
+# mirrors `struct tb_options` / `struct tb_network` of include/tbcuda.h
+struct TbOptions
+    device::Int32; reserved0::Int32; arena_bytes::Int64
+    max_wave::Int32; host_threads::Int32; plan_flags::UInt32; reserved1::Int32
+end
+struct TbNetwork
+    n_labels::Int32; n_leaves::Int32
+    leaf_off::Ptr{Int32}; leaf_labels::Ptr{Int32}
+    n_open::Int32; open_labels::Ptr{Int32}
+    node_left::Ptr{Int32}; node_right::Ptr{Int32}
+    weights::Ptr{Cvoid}; weight_dtype::Int32; value_type::Int32
+    flags::UInt32; reserved::Int32
+end
+
+const CTX = Ref{Ptr{Cvoid}}(C_NULL)
+
+function ctx(device::Integer = 0)
+    if CTX[] == C_NULL
+        opts = Ref(TbOptions(device, 0, 0, 0, 0, 0, 0))
+        rc = ccall((:tb_init, LIB), Cint, (Ref{TbOptions}, Ref{Ptr{Cvoid}}), opts, CTX)
+        rc == 0 || error("tb_init failed ($rc): " * unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        atexit(() -> ccall((:tb_shutdown, LIB), Cint, (Ptr{Cvoid},), CTX[]))
+    end
+    return CTX[]
+end
+
+# ContractionTree (leaves = 1-based tensor ids) -> 0-based post-order child arrays
+function flatten_tree(ct, n_leaves::Int)
+    left = Int32[]; right = Int32[]
+    function walk(t)
+        t isa Integer && return Int32(t - 1)
+        l = walk(t.left); r = walk(t.right)
+        push!(left, l); push!(right, r)
+        return Int32(n_leaves + length(left) - 1)
+    end
+    walk(ct)
+    return left, right
+end
+
+weight_code(::Type{Int32}) = Int32(1); weight_code(::Type{Int64}) = Int32(2)
+weight_code(::Type{Float32}) = Int32(3); weight_code(::Type{Float64}) = Int32(4)
+
+struct FlatBranch   # keeps the arrays alive while the C call runs
+    leaf_off::Vector{Int32}; leaf_labels::Vector{Int32}; left::Vector{Int32}; right::Vector{Int32}
+    open::Vector{Int32}; weights::Any; net::TbNetwork
+end
+
+function FlatBranch(branch::SlicedBranch)
+    code = branch.code::CompressedEinsum
+    ixs = code.ixs
+    leaf_off = Int32[0]; leaf_labels = Int32[]
+    for ix in ixs
+        append!(leaf_labels, Int32.(ix .- 1)); push!(leaf_off, Int32(length(leaf_labels)))
+    end
+    left, right = length(ixs) == 1 ? (Int32[], Int32[]) : flatten_tree(code.ct, length(ixs))
+    open = Int32.(code.iy .- 1)
+    w = branch.p.weights
+    unit = w isa TensorBranching.UnitWeight
+    wv = unit ? nothing : collect(w)
+    net = TbNetwork(nv(branch.p.g), length(ixs), pointer(leaf_off), pointer(leaf_labels), length(open),
+                    isempty(open) ? C_NULL : pointer(open), isempty(left) ? C_NULL : pointer(left),
+                    isempty(right) ? C_NULL : pointer(right), unit ? C_NULL : Ptr{Cvoid}(pointer(wv)),
+                    unit ? Int32(0) : weight_code(eltype(wv)), Int32(0), UInt32(0), Int32(0))
+    return FlatBranch(leaf_off, leaf_labels, left, right, open, wv, net)
+end
+
+"contract_slices on the B200 engine: one C call for the whole branch list."
+function contract_slices_cuda(branches::Vector{SlicedBranch}, element_type::Type)
+    n = length(branches)
+    flats = Vector{Union{FlatBranch, Nothing}}(undef, n)
+    nets = Vector{TbNetwork}(undef, n)
+    empty_net = TbNetwork(0, 0, C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0, 0, 0, 0)
+    for (i, b) in enumerate(branches)
+        if nv(b.p.g) == 0 || isnothing(b.code)
+            flats[i] = nothing; nets[i] = empty_net
+        else
+            flats[i] = FlatBranch(b); nets[i] = flats[i].net
+        end
+    end
+    vals = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); mx = Ref{Float64}(0)
+    GC.@preserve flats begin
+        rc = ccall((:tb_contract_networks, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{TbNetwork}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Int32}, Ref{Float64}),
+                   ctx(), nets, C_NULL, n, vals, status, mx)
+        rc == 0 || error("tb_contract_networks failed ($rc): " *
+                         unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
+    end
+    # same arithmetic as src/dynamic_ob.jl:39-44: empty graph => element_type(r), else t + element_type(r)
+    return element_type[(nv(b.p.g) == 0 || isnothing(b.code)) ? element_type(b.r) : element_type(vals[i]) + element_type(b.r)
+                        for (i, b) in enumerate(branches)]
+end
+
+# method overrides: the usecuda=true switch position
+function TensorBranching.contract_slices(branches::Vector{SlicedBranch}, element_type::Type, usecuda::Bool)
+    usecuda && return contract_slices_cuda(branches, element_type)
+    return invoke(TensorBranching.contract_slices, Tuple{Vector{SlicedBranch}, Type, Bool}, branches, element_type, false)
+end
+function TensorBranching.solve_slice(branch::SlicedBranch, element_type::Type, usecuda::Bool)
+    usecuda || return invoke(TensorBranching.solve_slice, Tuple{SlicedBranch, Type, Bool}, branch, element_type, false)
+    return contract_slices_cuda(SlicedBranch[TensorBranching.SlicedBranch(branch.p, branch.code, zero(branch.r))], element_type)[1]
+end
+
+end # module
