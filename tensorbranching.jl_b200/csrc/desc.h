@@ -19,6 +19,7 @@ namespace tb {
 enum : uint8_t { LOC_ARENA = 0, LOC_POOL = 1, LOC_SMEM = 2 };
 enum : uint8_t { KIND_FUSED = 0, KIND_GENERIC = 1, KIND_GEMM = 2 };
 enum : uint8_t { STORE_SCALAR = 0, STORE_VEC_M = 1, STORE_VEC_N = 2 };
+enum : uint8_t { OPV_GATHER = 0, OPV_VEC = 1, OPV_BCAST = 2 };  // how the 4 outputs of a vec4 thread map into an operand
 
 constexpr uint8_t NO_BIT = 0xFF;
 constexpr int MAX_RANK = 31;        // tensors up to 2^31 elements; shift tables hold 32 entries
@@ -74,7 +75,8 @@ struct BigStep {
     uint8_t c_shift[32];
     uint8_t ks;  // generic: log2 threads of a CTA cooperating on one output (block-level split-k)
     uint8_t po;  // generic: log2 outputs per CTA (po + ks <= 8); n_tiles = 2^(rc - po)
-    uint8_t pad[2];
+    uint8_t lane_n_first;  // gemm: the n tile index varies fastest across the lanes of a warp (else m)
+    uint8_t vec4;          // generic: every thread owns 4 consecutive outputs (128-bit stores); po = 10, ks = 0
 };
 static_assert(sizeof(BigStep) == 144, "BigStep layout");
 

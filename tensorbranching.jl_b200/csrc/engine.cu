@@ -60,6 +60,7 @@ struct tb_ctx {
     int sm_count = 148;
     bool own_stream = true;
     static constexpr int kMaxLanes = 8;
+    int gemm2_ctas_per_sm = 2;
     bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
     int n_lanes = 4;                       // waves in flight: lane 0 = main stream, others = side streams
     cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
@@ -238,7 +239,7 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
             if (ctx->gemm_v1) {
                 k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             } else {
-                const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(2 * ctx->sm_count));
+                const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
                 k_gemm2<T><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
                                                                    L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off));
             }
@@ -643,6 +644,13 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    {
+        int nb = 0;
+        TB_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm2<int32_t>, G2_THREADS, G2_SMEM_BYTES));
+        c->gemm2_ctas_per_sm = nb;
+    }
     *out_ctx = ctx.release();
     return TB_OK;
 }

@@ -134,6 +134,48 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
     T* __restrict__ C = arena + sd.c_off;
     const int rc = sd.rc, nk = sd.nk, nka = sd.nka, ks = sd.ks, po = sd.po;
     const int nkt = nk + nka + sd.nkb;
+    if (sd.vec4) {
+        // streaming mode: this thread owns outputs c4 .. c4+3 (C address bits 0,1), 128-bit store
+        typedef typename Ops<T>::vec4 vec4;
+        const uint32_t c4 = ((tile << 8) | (uint32_t)tid) << 2;
+        const uint32_t offA = scatter_bits(c4, sd.a_shift, rc), offB = scatter_bits(c4, sd.b_shift, rc);
+        const uint32_t a0 = sd.a_shift[0], a1 = sd.a_shift[1], b0 = sd.b_shift[0], b1 = sd.b_shift[1];
+        const int modeA = (a0 == NO_BIT && a1 == NO_BIT) ? OPV_BCAST : ((a0 == 0 && a1 == 1) ? OPV_VEC : OPV_GATHER);
+        const int modeB = (b0 == NO_BIT && b1 == NO_BIT) ? OPV_BCAST : ((b0 == 0 && b1 == 1) ? OPV_VEC : OPV_GATHER);
+        const uint32_t dA1 = a0 == NO_BIT ? 0u : (1u << a0), dA2 = a1 == NO_BIT ? 0u : (1u << a1);
+        const uint32_t dB1 = b0 == NO_BIT ? 0u : (1u << b0), dB2 = b1 == NO_BIT ? 0u : (1u << b1);
+        const uint32_t kmask = (1u << nk) - 1u, amask = (1u << (nk + nka)) - 1u;
+        const uint32_t n_red = 1u << nkt;
+        const int sa = sd.sa, sb = sd.sb;
+        T acc[4] = {Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf()};
+        for (uint32_t r = 0; r < n_red; ++r) {
+            const uint32_t ra = offA + ((r & amask) << sa);
+            const uint32_t rb = offB + (((r & kmask) | ((r >> (nk + nka)) << nk)) << sb);
+            T av[4], bv[4];
+            if (modeA == OPV_VEC) {
+                const vec4 v = *reinterpret_cast<const vec4*>(A + ra);
+                av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
+            } else if (modeA == OPV_BCAST) {
+                av[0] = av[1] = av[2] = av[3] = A[ra];
+            } else {
+                av[0] = A[ra]; av[1] = A[ra + dA1]; av[2] = A[ra + dA2]; av[3] = A[ra + dA1 + dA2];
+            }
+            if (modeB == OPV_VEC) {
+                const vec4 v = *reinterpret_cast<const vec4*>(B + rb);
+                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+            } else if (modeB == OPV_BCAST) {
+                bv[0] = bv[1] = bv[2] = bv[3] = B[rb];
+            } else {
+                bv[0] = B[rb]; bv[1] = B[rb + dB1]; bv[2] = B[rb + dB2]; bv[3] = B[rb + dB1 + dB2];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = Ops<T>::addmax(av[q], bv[q], acc[q]);
+        }
+        vec4 o;
+        o.x = acc[0]; o.y = acc[1]; o.z = acc[2]; o.w = acc[3];
+        *reinterpret_cast<vec4*>(C + c4) = o;
+        return;
+    }
     // thread -> (output, k-part): 2^po outputs per CTA, 2^ks threads share one output
     const uint32_t c = (tile << po) | (tid & ((1u << po) - 1u));
     const uint32_t kp = (uint32_t)tid >> po;
@@ -338,13 +380,14 @@ __global__ void __launch_bounds__(BIG_THREADS, 2) k_gemm(const BigInst* __restri
 // ------------------------------------------------------------------------------------------------
 constexpr int G2_STAGES = 4;
 constexpr int G2_CONSUMERS = 256;
-constexpr int G2_THREADS = G2_CONSUMERS + 32;
+constexpr int G2_PRODUCERS = 128;  // one warpgroup (setmaxnreg is per warpgroup); only its first warp works
+constexpr int G2_THREADS = G2_PRODUCERS + G2_CONSUMERS;
 constexpr int G2_SMEM_BYTES = G2_STAGES * GEMM_STAGE_ELEMS * 4;
 
 struct TileInfo {
     long long cbase[32];  // per sub-tile element offset into C, -1 = inactive
     void* C;
-    int tm, tn, kc, nchunks, store_mode, valid;
+    int tm, tn, kc, nchunks, store_mode, valid, lane_n_first;
     unsigned char c_shift[16];
 };
 
@@ -386,8 +429,10 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                  : "memory");
 }
 
+// Register budget: 2 CTAs/SM x 384 threads start at 80 registers; the producer warpgroup drops to 32 and the two
+// consumer warpgroups grow to 112 (2 x (128*32 + 256*112) = 65536), so two CTAs stay resident.
 template <typename T>
-__global__ void __maxnreg__(112) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
+__global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter) {
     typedef typename Ops<T>::vec4 vec4;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -408,9 +453,11 @@ __global__ void __maxnreg__(112) k_gemm2(const BigInst* __restrict__ insts, cons
     }
     __syncthreads();
 
-    if (tid >= G2_CONSUMERS) {
-        // ------------------------------------------------------------------ producer warp
-        const int lane = tid - G2_CONSUMERS;
+    if (tid < G2_PRODUCERS) {
+        // ------------------------------------------------------------------ producer warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n" ::);
+        if (tid >= 32) return;
+        const int lane = tid;
         unsigned it = 0;  // global chunk counter (ring position)
         for (unsigned tcount = 0;; ++tcount) {
             unsigned tile_g = 0;
@@ -456,6 +503,7 @@ __global__ void __maxnreg__(112) k_gemm2(const BigInst* __restrict__ insts, cons
                 ti.kc = kc;
                 ti.nchunks = 1 << (nk - kc);
                 ti.store_mode = d->store_mode;
+                ti.lane_n_first = d->lane_n_first;
                 ti.valid = 1;
             }
             __syncwarp();
@@ -480,7 +528,9 @@ __global__ void __maxnreg__(112) k_gemm2(const BigInst* __restrict__ insts, cons
         return;
     }
 
-    // ---------------------------------------------------------------------- consumer warps
+    // ---------------------------------------------------------------------- consumer warpgroups
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::);
+    const int ctid = tid - G2_PRODUCERS;
     const int lane = tid & 31;
     unsigned it = 0;
     for (unsigned tcount = 0;; ++tcount) {
@@ -490,8 +540,9 @@ __global__ void __maxnreg__(112) k_gemm2(const BigInst* __restrict__ insts, cons
         if (!ti.valid) break;
         const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
         const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
-        const int sub = tid >> tps_log, lt = tid & ((1 << tps_log) - 1);
-        const int tmh = lt & ((1 << (tm - 3)) - 1), tnh = lt >> (tm - 3);
+        const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
+        const int tmh = ti.lane_n_first ? (lt >> (tn - 3)) : (lt & ((1 << (tm - 3)) - 1));
+        const int tnh = ti.lane_n_first ? (lt & ((1 << (tn - 3)) - 1)) : (lt >> (tm - 3));
         const int m_lo = tmh * 4, m_hi = (1 << (tm - 1)) + tmh * 4;
         const int n_lo = tnh * 4, n_hi = (1 << (tn - 1)) + tnh * 4;
         const int la = kc + tm, lb = kc + tn;

@@ -411,6 +411,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
         std::vector<int32_t> posC(NLAB, -1);
         std::vector<int32_t> batA(NLAB, -1), batB(NLAB, -1);  // stamps: label is a batch label inside child A / B
+        std::vector<int32_t> secA(NLAB, -1), secB(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
         const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
         for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
             const int t = *it, A = lch[t], B = rch[t];
@@ -425,11 +426,15 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 const int ch = side ? B : A;
                 if (leaf[ch]) continue;
                 auto& bat = side ? batB : batA;
+                auto& sec = side ? secB : secA;
                 const int c1 = lch[ch], c2 = rch[ch];
                 const int sS = ++stamp;
                 for (int q = 0; q < lab_n[c1]; ++q) stC[labp(c1)[q]] = sS;
-                for (int q = 0; q < lab_n[c2]; ++q)
-                    if (stC[labp(c2)[q]] == sS) bat[labp(c2)[q]] = sN;
+                for (int q = 0; q < lab_n[c2]; ++q) {
+                    const int32_t l = labp(c2)[q];
+                    if (stC[l] == sS) bat[l] = sN;
+                    else sec[l] = sN;
+                }
             }
             int32_t M[40], N[40], Bt[40], K[40], KA[40], KB[40];
             int nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0;
@@ -444,11 +449,22 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 if (stA[l] == sN) continue;
                 (posC[l] >= 0 ? N[nn++] : KB[nkb++]) = l;
             }
-            // M / N: labels that are batch labels inside the producing child go last, then by position in C
-            for (int i = 0; i < nm; ++i) key[M[i]] = ((batA[M[i]] == sN) ? 1024 : 0) + posC[M[i]];
-            sort_by_key(M, key.data(), nm);
-            for (int i = 0; i < nn; ++i) key[N[i]] = ((batB[N[i]] == sN) ? 1024 : 0) + posC[N[i]];
-            sort_by_key(N, key.data(), nn);
+            // M / N: group the labels by their class inside the producing child so that the low address bits of
+            // the operand form a run of the child's own tile labels (coalesced stores in the child): the child's
+            // larger output-only class first, then its other one, batch labels of the child last; then by position in C
+            auto class_key = [&](int32_t* v, int n, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
+                int n_first = 0, n_sec = 0;
+                for (int i = 0; i < n; ++i) {
+                    if (bat[v[i]] == sN) continue;
+                    (sec[v[i]] == sN ? n_sec : n_first)++;
+                }
+                const int k_first = n_first >= n_sec ? 0 : 1024, k_sec = n_first >= n_sec ? 1024 : 0;
+                for (int i = 0; i < n; ++i)
+                    key[v[i]] = (bat[v[i]] == sN ? 2048 : (sec[v[i]] == sN ? k_sec : k_first)) + posC[v[i]];
+                sort_by_key(v, key.data(), n);
+            };
+            class_key(M, nm, batA, secA);
+            class_key(N, nn, batB, secB);
             for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
             sort_by_key(Bt, key.data(), nb);
             for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
@@ -804,6 +820,10 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 set_pos(posB, B, false);
                 int ks, po;
                 generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
+                if (ks == 0 && s.rc >= 10) {  // streaming node: 4 consecutive outputs per thread, 1024 per CTA
+                    s.vec4 = 1;
+                    po = 10;
+                }
                 s.ks = (uint8_t)ks;
                 s.po = (uint8_t)po;
                 s.n_tiles = 1u << (s.rc - po);
@@ -831,6 +851,15 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 s.store_mode = STORE_SCALAR;
                 if (s.c_shift[0] == 0 && s.c_shift[1] == 1) s.store_mode = STORE_VEC_M;
                 else if (s.c_shift[c.tm] == 0 && s.c_shift[c.tm + 1] == 1) s.store_mode = STORE_VEC_N;
+                // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
+                // (bit 0 if stores are scalar) on the low lane bits
+                {
+                    const int probe = s.store_mode == STORE_SCALAR ? 0 : 2;
+                    bool n_owns = false;
+                    for (int i = 0; i < c.tn; ++i)
+                        if (s.c_shift[c.tm + i] == probe) n_owns = true;
+                    s.lane_n_first = n_owns ? 1 : 0;
+                }
             }
             P.big_steps.push_back(s);
             P.recs.push_back(rec_of(t, kind[t], P.level[t]));

@@ -23,7 +23,7 @@ BIGSTEP = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("c_off", "<i8"), ("a_lo
                     ("kind", "u1"), ("rc", "u1"), ("nk", "u1"), ("nka", "u1"), ("nkb", "u1"), ("sa", "u1"),
                     ("sb", "u1"), ("tm", "u1"), ("tn", "u1"), ("kc", "u1"), ("ng", "u1"), ("n_mhi", "u1"),
                     ("n_nhi", "u1"), ("store_mode", "u1"), ("n_tiles", "<u4"), ("a_shift", "u1", 32),
-                    ("b_shift", "u1", 32), ("c_shift", "u1", 32), ("ks", "u1"), ("po", "u1"), ("pad", "u1", 2)])
+                    ("b_shift", "u1", 32), ("c_shift", "u1", 32), ("ks", "u1"), ("po", "u1"), ("lane_n_first", "u1"), ("vec4", "u1")])
 assert SUBSTEP.itemsize == 48 and SUBTREE.itemsize == 24 and BIGSTEP.itemsize == 144
 
 
@@ -115,7 +115,11 @@ def run_plan(plan):
                 if s["kind"] == KIND_GENERIC:
                     acc = _generic(A, B, rc, nk, int(s["nka"]), int(s["nkb"]), int(s["sa"]), int(s["sb"]),
                                    s["a_shift"], s["b_shift"], neg)
-                    assert int(s["po"]) + int(s["ks"]) <= 8 and int(s["po"]) <= rc and int(s["n_tiles"]) == 1 << (rc - int(s["po"]))
+                    if s["vec4"]:
+                        assert int(s["po"]) == 10 and int(s["ks"]) == 0 and rc >= 10
+                    else:
+                        assert int(s["po"]) + int(s["ks"]) <= 8
+                    assert int(s["po"]) <= rc and int(s["n_tiles"]) == 1 << (rc - int(s["po"]))
                     assert int(s["ks"]) <= nk + int(s["nka"]) + int(s["nkb"])
                     pending.append((int(s["c_off"]), np.arange(1 << rc), acc))
                 else:
