@@ -61,6 +61,7 @@ struct tb_ctx {
     bool own_stream = true;
     static constexpr int kMaxLanes = 8;
     int gemm2_ctas_per_sm = 2;
+    bool staged_epilogue = true;           // TB_EPI_DIRECT=1: scatter stores straight from registers (A/B testing)
     bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
     int n_lanes = 4;                       // waves in flight: lane 0 = main stream, others = side streams
     cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
@@ -241,7 +242,8 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
             } else {
                 const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
                 k_gemm2<T><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
-                                                                   L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off));
+                                                                   L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
+                                                                   ctx->staged_epilogue ? 1 : 0);
             }
             break;
         case 3:
@@ -630,6 +632,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
     {
         const char* e1 = getenv("TB_GEMM_V1");
         c->gemm_v1 = e1 && e1[0] == '1';
+        const char* e3 = getenv("TB_EPI_DIRECT");
+        c->staged_epilogue = !(e3 && e3[0] == '1');
         const char* e2 = getenv("TB_LANES");
         if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
     }

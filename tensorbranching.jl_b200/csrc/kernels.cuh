@@ -382,14 +382,21 @@ constexpr int G2_STAGES = 4;
 constexpr int G2_CONSUMERS = 256;
 constexpr int G2_PRODUCERS = 128;  // one warpgroup (setmaxnreg is per warpgroup); only its first warp works
 constexpr int G2_THREADS = G2_PRODUCERS + G2_CONSUMERS;
-constexpr int G2_SMEM_BYTES = G2_STAGES * GEMM_STAGE_ELEMS * 4;
+constexpr int G2_RING_BYTES = G2_STAGES * GEMM_STAGE_ELEMS * 4;
+constexpr int G2_STG_ELEMS = 4096;                         // one quarter of a CTA tile
+constexpr int G2_SMEM_BYTES = G2_RING_BYTES + 2 * G2_STG_ELEMS * 4;  // ring + double-buffered epilogue staging
 
 struct TileInfo {
     long long cbase[32];  // per sub-tile element offset into C, -1 = inactive
     void* C;
     int tm, tn, kc, nchunks, store_mode, valid, lane_n_first;
     unsigned char c_shift[16];
+    unsigned char e_spos[12], e_cs[12];  // staged epilogue: sorted in-round tile bits -> staging position / C shift
+    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_pad;
 };
+
+// bank swizzle of the epilogue staging index: permutes 16-byte chunks inside a 128-byte row
+__device__ __forceinline__ uint32_t stg_swz(uint32_t x) { return x ^ ((((x >> 5) ^ (x >> 8) ^ (x >> 11)) & 7u) << 2); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -429,14 +436,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
                  : "memory");
 }
 
-// Register budget: 2 CTAs/SM x 384 threads start at 80 registers; the producer warpgroup drops to 32 and the two
-// consumer warpgroups grow to 112 (2 x (128*32 + 256*112) = 65536), so two CTAs stay resident.
+// Register budget: 2 CTAs/SM x 384 threads are launched with 80 registers/thread; setmaxnreg moves registers
+// INSIDE a CTA's own pool (SASS: USETMAXREG...CTAPOOL), so 128*P + 256*C <= 384*80 must hold or the .inc never
+// succeeds (a silent hang).  P = 24 (producer warpgroup), C = 104 (consumer warpgroups): 3072 + 26624 = 29696.
+static_assert(128 * 24 + 256 * 104 <= 384 * 80, "setmaxnreg budget exceeds the CTA pool");
 template <typename T>
 __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
-                                                         int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter) {
+                                                         int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter,
+                                                         int staged_epilogue) {
     typedef typename Ops<T>::vec4 vec4;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);
+    T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);
     __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2];
     __shared__ TileInfo tinfo[2];
     const int tid = threadIdx.x;
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
 
     if (tid < G2_PRODUCERS) {
         // ------------------------------------------------------------------ producer warpgroup
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n" ::);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::);
         if (tid >= 32) return;
         const int lane = tid;
         unsigned it = 0;  // global chunk counter (ring position)
@@ -496,6 +507,10 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
             TileInfo& ti = tinfo[slot];
             ti.cbase[lane] = cb;
             if (lane < 16) ti.c_shift[lane] = (lane < tm + tn) ? d->c_shift[lane] : NO_BIT;
+            if (lane < 12) {
+                ti.e_spos[lane] = d->a_shift[lane];
+                ti.e_cs[lane] = d->b_shift[lane];
+            }
             if (lane == 0) {
                 ti.C = reinterpret_cast<T*>(inst.arena) + d->c_off;
                 ti.tm = tm;
@@ -504,6 +519,9 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 ti.nchunks = 1 << (nk - kc);
                 ti.store_mode = d->store_mode;
                 ti.lane_n_first = d->lane_n_first;
+                ti.e_cs_mtop = d->a_shift[30];
+                ti.e_cs_ntop = d->a_shift[31];
+                ti.e_vec = d->b_shift[31];
                 ti.valid = 1;
             }
             __syncwarp();
@@ -529,7 +547,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
     }
 
     // ---------------------------------------------------------------------- consumer warpgroups
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n" ::);
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n" ::);
     const int ctid = tid - G2_PRODUCERS;
     const int lane = tid & 31;
     unsigned it = 0;
@@ -574,6 +592,74 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[stage]);
+        }
+        if (staged_epilogue) {
+            // ---- staged epilogue: 4 rounds of (registers -> shared memory in tile order -> global in C-address order)
+            const int nbr = tm + tn - 2;
+            const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
+            uint32_t ts = 0, tc = 0;  // contribution of this thread's fixed element bits (2..9) that are tile bits
+#pragma unroll
+            for (int b = 2; b < 10; ++b) {
+                const uint32_t bit = ((uint32_t)ctid >> (b - 2)) & 1u;
+                if (b < nbr) {
+                    ts |= bit << ti.e_spos[b];
+                    tc |= bit << ti.e_cs[b];
+                }
+            }
+            const uint32_t ds1 = 1u << ti.e_spos[0], ds2 = 1u << ti.e_spos[1];
+            const uint32_t dc1 = 1u << ti.e_cs[0], dc2 = 1u << ti.e_cs[1];
+            const bool evec = ti.e_vec != 0;
+            T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ih = r & 1, jh = r >> 1;
+                T* buf = stg_mem + (r & 1) * G2_STG_ELEMS;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    vec4 v;
+                    v.x = acc[ih * 4 + 0][jh * 4 + j];
+                    v.y = acc[ih * 4 + 1][jh * 4 + j];
+                    v.z = acc[ih * 4 + 2][jh * 4 + j];
+                    v.w = acc[ih * 4 + 3][jh * 4 + j];
+                    *reinterpret_cast<vec4*>(buf + stg_swz(qbase | ((uint32_t)j << (tm - 1)))) = v;
+                }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+                    const uint32_t e4 = ((uint32_t)itr << 10) | ((uint32_t)ctid << 2);
+                    const uint32_t sub_e = e4 >> nbr;
+                    uint32_t so = ts, co = tc;
+#pragma unroll
+                    for (int b = 10; b < 12; ++b) {
+                        const uint32_t bit = ((uint32_t)itr >> (b - 10)) & 1u;
+                        if (b < nbr) {
+                            so |= bit << ti.e_spos[b];
+                            co |= bit << ti.e_cs[b];
+                        }
+                    }
+                    const long long cb = ti.cbase[sub_e];
+                    if (cb >= 0) {
+                        so |= sub_e << nbr;
+                        const T v0 = buf[stg_swz(so)], v1 = buf[stg_swz(so | ds1)], v2 = buf[stg_swz(so | ds2)],
+                                v3 = buf[stg_swz(so | ds1 | ds2)];
+                        T* dst = Cb + cb + roff + co;
+                        if (evec) {
+                            vec4 o;
+                            o.x = v0; o.y = v1; o.z = v2; o.w = v3;
+                            *reinterpret_cast<vec4*>(dst) = o;
+                        } else {
+                            dst[0] = v0;
+                            dst[dc1] = v1;
+                            dst[dc2] = v2;
+                            dst[dc1 + dc2] = v3;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+            continue;
         }
         const long long cbase = ti.cbase[sub];
         if (cbase >= 0) {

@@ -851,6 +851,26 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 s.store_mode = STORE_SCALAR;
                 if (s.c_shift[0] == 0 && s.c_shift[1] == 1) s.store_mode = STORE_VEC_M;
                 else if (s.c_shift[c.tm] == 0 && s.c_shift[c.tm + 1] == 1) s.store_mode = STORE_VEC_N;
+                // staged epilogue tables (k_gemm2): the tile is written in 4 rounds (the top m tile bit and the top n
+                // tile bit select the round); inside a round the (tm-1)+(tn-1) remaining tile bits are enumerated in
+                // C-address order.  a_shift[i] = position of the i-th such bit in the shared-memory staging index
+                // ([m bits 0..tm-2 | n bits 0..tn-2]), b_shift[i] = its C shift.  a_shift[30/31] = C shift of the top
+                // m / n tile bit, b_shift[31] = 1 if the two lowest bits are C bits 0,1 (128-bit stores).
+                {
+                    const int nbr = c.tm + c.tn - 2;
+                    int ent_cs[16], ent_sp[16], ne = 0;
+                    for (int i = 0; i < c.tm - 1; ++i) { ent_cs[ne] = s.c_shift[i]; ent_sp[ne++] = i; }
+                    for (int i = 0; i < c.tn - 1; ++i) { ent_cs[ne] = s.c_shift[c.tm + i]; ent_sp[ne++] = (c.tm - 1) + i; }
+                    for (int i = 1; i < ne; ++i) {
+                        int cs = ent_cs[i], sp = ent_sp[i], j = i - 1;
+                        while (j >= 0 && ent_cs[j] > cs) { ent_cs[j + 1] = ent_cs[j]; ent_sp[j + 1] = ent_sp[j]; --j; }
+                        ent_cs[j + 1] = cs; ent_sp[j + 1] = sp;
+                    }
+                    for (int i = 0; i < nbr; ++i) { s.a_shift[i] = (uint8_t)ent_sp[i]; s.b_shift[i] = (uint8_t)ent_cs[i]; }
+                    s.a_shift[30] = s.c_shift[c.tm - 1];
+                    s.a_shift[31] = s.c_shift[c.tm + c.tn - 1];
+                    s.b_shift[31] = (ent_cs[0] == 0 && ent_cs[1] == 1) ? 1 : 0;
+                }
                 // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
                 // (bit 0 if stores are scalar) on the low lane bits
                 {

@@ -135,6 +135,14 @@ def run_plan(plan):
                         assert s["c_shift"][0] == 0 and s["c_shift"][1] == 1
                     if s["store_mode"] == 2:
                         assert s["c_shift"][tm] == 0 and s["c_shift"][tm + 1] == 1
+                    # staged-epilogue tables: sorted in-round tile bits
+                    nbr = tm + tn - 2
+                    ent = sorted([(int(s["c_shift"][i]), i) for i in range(tm - 1)] +
+                                 [(int(s["c_shift"][tm + i]), (tm - 1) + i) for i in range(tn - 1)])
+                    assert [int(x) for x in s["b_shift"][:nbr]] == [e[0] for e in ent]
+                    assert [int(x) for x in s["a_shift"][:nbr]] == [e[1] for e in ent]
+                    assert int(s["a_shift"][30]) == int(s["c_shift"][tm - 1]) and int(s["a_shift"][31]) == int(s["c_shift"][tm + tn - 1])
+                    assert int(s["b_shift"][31]) == int(ent[0][0] == 0 and ent[1][0] == 1)
                     idxs, vals = [], []
                     for g in range(1 << ng):
                         gm = g & ((1 << n_mhi) - 1)
