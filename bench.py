@@ -323,6 +323,7 @@ def main():
         if world > 1:
             dist.all_reduce(hb)
         e2e = {"value": total_ops / (ms_e2e * 1e-3) * 1e-9, "unit": "Gop/s", "h2d_bytes_per_step": int(hb[0].item()),
+               "host_breakdown_rank0": eng.last_host_breakdown(),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": ms_e2e,
                "slices_per_s": n_br / (ms_e2e * 1e-3)}
         assert np.array_equal(result_e2e, result)

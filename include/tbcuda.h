@@ -196,6 +196,10 @@ int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
 int tb_profile(tb_ctx* ctx, int enable);
 int tb_last_profile(const tb_ctx* ctx, double* ms_by_kind /*[4]*/, int64_t* launches_by_kind /*[4]*/);
 
+/* host wall-clock breakdown (ms) of the last tb_contract_networks call:
+ * [0] plan compilation, [1] descriptor upload, [2] work-list build, [3] launch + wait, [4] plan teardown, [5] total */
+int tb_last_host_breakdown(const tb_ctx* ctx, double* ms6);
+
 /* host<->device bytes moved by the last contract call (descriptors + work lists up, results down) */
 int tb_last_transfers(const tb_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes);
 

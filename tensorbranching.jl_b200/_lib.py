@@ -61,7 +61,7 @@ class tb_step_info(C.Structure):
 EXPORTS = ["tb_version", "tb_init", "tb_shutdown", "tb_last_error", "tb_plan_create", "tb_plan_destroy",
            "tb_plan_info", "tb_plan_export", "tb_plan_export_raw", "tb_contract", "tb_contract_batch",
            "tb_contract_networks", "tb_plan_read_tensor", "tb_last_timing", "tb_permute_bits", "tb_set_stream", "tb_profile",
-           "tb_last_profile", "tb_last_transfers"]
+           "tb_last_profile", "tb_last_transfers", "tb_last_host_breakdown"]
 
 _lib = None
 
@@ -104,6 +104,7 @@ def load():
     lib.tb_set_stream.argtypes = [vp, vp]
     lib.tb_profile.argtypes = [vp, C.c_int]
     lib.tb_last_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.tb_last_host_breakdown.argtypes = [vp, C.POINTER(C.c_double)]
     lib.tb_last_transfers.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.tb_permute_bits.argtypes = [vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     _lib = lib

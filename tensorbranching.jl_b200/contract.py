@@ -212,6 +212,12 @@ class Engine:
         names = ("fused", "generic", "gemm", "finalize")
         return {k: (ms[i], nl[i]) for i, k in enumerate(names)}
 
+    def last_host_breakdown(self):
+        ms = (C.c_double * 6)()
+        L.check(self._lib.tb_last_host_breakdown(self.handle, ms))
+        names = ("compile_ms", "upload_ms", "worklist_ms", "launch_wait_ms", "teardown_ms", "total_ms")
+        return {k: ms[i] for i, k in enumerate(names)}
+
     def last_transfers(self):
         a = C.c_int64()
         b = C.c_int64()

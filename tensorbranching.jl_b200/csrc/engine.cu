@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -29,6 +30,9 @@ using namespace tb;
 
 namespace {
 thread_local std::string g_tls_error;
+inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct BlobChunk {
     void* d = nullptr;
@@ -60,6 +64,7 @@ struct tb_ctx {
     int sm_count = 148;
     bool own_stream = true;
     static constexpr int kMaxLanes = 8;
+    double host_ms[6] = {0, 0, 0, 0, 0, 0};  // last call: compile, upload, build lists, launch+wait, destroy, total
     int gemm2_ctas_per_sm = 2;
     bool staged_epilogue = true;           // TB_EPI_DIRECT=1: scatter stores straight from registers (A/B testing)
     bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
@@ -361,6 +366,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     if (single_plan_mode && !waves.empty()) ctx->last_plan_arena_base_elems = 0;
 
     // ---- build work lists for every wave into one host buffer
+    const double t_b0 = now_ms();
     std::vector<uint8_t> host;
     std::vector<Launch> launches;
     auto align16 = [&]() { host.resize((host.size() + 15) / 16 * 16); };
@@ -486,6 +492,8 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         }
     }
     if (launches.empty()) return TB_OK;
+    const double t_l0 = now_ms();
+    ctx->host_ms[2] += t_l0 - t_b0;
     rc = ensure_stage(ctx, host.size());
     if (rc) return rc;
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -533,6 +541,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     float ms = 0;
     TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms += ms;
+    ctx->host_ms[3] += now_ms() - t_l0;
     ctx->last_launches += (int64_t)launches.size();
     ctx->h2d_bytes += (int64_t)host.size();
     if (ctx->profile) {
@@ -559,8 +568,12 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
         ctx->prof_ms[q] = 0;
         ctx->prof_launches[q] = 0;
     }
+    double t_u0 = now_ms();
     int rc = ensure_uploaded(ctx, plans, n);
     if (rc) return rc;
+    ctx->host_ms[1] = now_ms() - t_u0;
+    ctx->host_ms[2] = 0;
+    ctx->host_ms[3] = 0;
     rc = ensure_results(ctx, (size_t)std::max<int64_t>(n, 1));
     if (rc) return rc;
     std::vector<int32_t> status((size_t)n, TB_OK);
@@ -772,6 +785,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     nthreads = std::max(1, std::min<int>(nthreads, (int)std::max<int64_t>(1, n / 8)));
     std::atomic<int64_t> next{0};
     const uint32_t flags = ctx->opts.plan_flags;
+    const double t_c0 = now_ms();
     auto worker = [&]() {
         for (;;) {
             int64_t i = next.fetch_add(1);
@@ -789,6 +803,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
         worker();
         for (auto& t : th) t.join();
     }
+    const double t_compile = now_ms() - t_c0;
     int rc = TB_OK;
     for (int64_t i = 0; i < n; ++i)
         if (codes[i]) {
@@ -796,6 +811,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
             break;
         }
     if (rc == TB_OK) rc = contract_impl(ctx, plans.data(), r, n, out_values, out_status, out_max, false);
+    const double t_d0 = now_ms();
     // the temporary plans all live in chunks of this call: release the device side once, free hosts in parallel
     for (tb_plan* p : plans)
         if (p && p->p.d_blob) {
@@ -821,6 +837,9 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
         killer();
         for (auto& t : th) t.join();
     }
+    ctx->host_ms[0] = t_compile;
+    ctx->host_ms[4] = now_ms() - t_d0;
+    ctx->host_ms[5] = now_ms() - t_c0;
     return rc;
 }
 
@@ -881,6 +900,12 @@ int tb_last_profile(const tb_ctx* ctx, double* ms_by_kind, int64_t* launches_by_
         if (ms_by_kind) ms_by_kind[q] = ctx->prof_ms[q];
         if (launches_by_kind) launches_by_kind[q] = ctx->prof_launches[q];
     }
+    return TB_OK;
+}
+
+int tb_last_host_breakdown(const tb_ctx* ctx, double* ms6) {
+    if (!ctx || !ms6) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "NULL argument");
+    for (int q = 0; q < 6; ++q) ms6[q] = ctx->host_ms[q];
     return TB_OK;
 }
 
