@@ -647,6 +647,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
         c->gemm_v1 = e1 && e1[0] == '1';
         const char* e3 = getenv("TB_EPI_DIRECT");
         c->staged_epilogue = !(e3 && e3[0] == '1');
+        const char* e4 = getenv("TB_WAVE");
+        if (e4 && atoi(e4) >= 1 && c->opts.max_wave == 0) c->opts.max_wave = atoi(e4);
         const char* e2 = getenv("TB_LANES");
         if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
     }
