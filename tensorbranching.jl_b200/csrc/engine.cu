@@ -49,11 +49,22 @@ struct tb_ctx {
     void* arena = nullptr;
     size_t arena_bytes = 0;
     std::vector<BlobChunk> chunks;
-    // staging for work lists
-    void* h_stage = nullptr;
-    size_t h_stage_cap = 0;
-    void* d_stage = nullptr;
-    size_t d_stage_cap = 0;
+    // staging ring: pinned host + device buffers for descriptor blobs and work lists.  A slot is reused only
+    // after the event recorded behind its last consumer (copy or kernels) has completed.
+    struct Slot {
+        void* h = nullptr;
+        size_t hcap = 0;
+        void* d = nullptr;
+        size_t dcap = 0;
+        cudaEvent_t ev = nullptr;
+        bool busy = false;
+    };
+    static constexpr int kSlots = 6;
+    Slot slots[kSlots];
+    int slot_cursor = 0;
+    cudaStream_t copy_stream = nullptr;    // H2D of blobs / work lists, never blocked behind compute
+    cudaEvent_t ev_copy = nullptr;
+    int lane_cursor = 0;                   // round-robin position of the next wave's lane (kept across batches)
     double* d_results = nullptr;
     double* h_results = nullptr;
     size_t results_cap = 0;
@@ -94,6 +105,8 @@ int set_err(tb_ctx* ctx, int code, const std::string& msg) {
                            std::string(#call) + ": " + cudaGetErrorString(e__));                             \
     } while (0)
 
+int sync_all_lanes(tb_ctx* ctx);
+
 int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
     if (ctx->arena && ctx->arena_bytes >= need_bytes) return TB_OK;
     size_t want = (size_t)ctx->opts.arena_bytes;
@@ -107,7 +120,8 @@ int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
         return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "a single branch needs " + std::to_string(need_bytes) + " bytes of arena, more than configured");
     if (need_bytes > want) return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "a single branch needs " + std::to_string(need_bytes) + " bytes of arena; arena limit is " + std::to_string(want));
     if (ctx->arena) {
-        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int rcs = sync_all_lanes(ctx);
+        if (rcs) return rcs;
         cudaFree(ctx->arena);
         ctx->arena = nullptr;
         ctx->arena_bytes = 0;
@@ -120,21 +134,36 @@ int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
     return TB_OK;
 }
 
-int ensure_stage(tb_ctx* ctx, size_t bytes) {
-    if (ctx->h_stage_cap < bytes) {
-        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-        ctx->h_stage = nullptr;
-        size_t cap = std::max(bytes * 3 / 2, (size_t)1 << 20);
-        TB_CUDA(ctx, cudaMallocHost(&ctx->h_stage, cap));
-        ctx->h_stage_cap = cap;
+int acquire_slot(tb_ctx* ctx, size_t hbytes, size_t dbytes, tb_ctx::Slot** out) {
+    tb_ctx::Slot& sl = ctx->slots[ctx->slot_cursor];
+    ctx->slot_cursor = (ctx->slot_cursor + 1) % tb_ctx::kSlots;
+    if (!sl.ev) TB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    if (sl.busy) {
+        TB_CUDA(ctx, cudaEventSynchronize(sl.ev));
+        sl.busy = false;
     }
-    if (ctx->d_stage_cap < bytes) {
-        if (ctx->d_stage) cudaFree(ctx->d_stage);
-        ctx->d_stage = nullptr;
-        size_t cap = std::max(bytes * 3 / 2, (size_t)1 << 20);
-        TB_CUDA(ctx, cudaMalloc(&ctx->d_stage, cap));
-        ctx->d_stage_cap = cap;
+    if (sl.hcap < hbytes) {
+        if (sl.h) cudaFreeHost(sl.h);
+        sl.h = nullptr;
+        size_t cap = std::max(hbytes * 5 / 4, (size_t)1 << 20);
+        TB_CUDA(ctx, cudaMallocHost(&sl.h, cap));
+        sl.hcap = cap;
     }
+    if (sl.dcap < dbytes) {
+        if (sl.d) cudaFree(sl.d);
+        sl.d = nullptr;
+        size_t cap = std::max(dbytes * 5 / 4, (size_t)1 << 20);
+        TB_CUDA(ctx, cudaMalloc(&sl.d, cap));
+        sl.dcap = cap;
+    }
+    *out = &sl;
+    return TB_OK;
+}
+
+int sync_all_lanes(tb_ctx* ctx) {
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    for (int l = 1; l < ctx->n_lanes; ++l) TB_CUDA(ctx, cudaStreamSynchronize(ctx->side[l]));
+    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return TB_OK;
 }
 
@@ -192,27 +221,29 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
             size_t rest = 0;
             for (size_t j = pos; j < todo.size(); ++j) rest += bsz[j];
             BlobChunk nc;
-            nc.cap = std::max<size_t>(rest, (size_t)8 << 20);
+            size_t prev = ctx->chunks.empty() ? 0 : ctx->chunks.back().cap;
+            nc.cap = std::max<size_t>(std::max(rest, 2 * prev), (size_t)32 << 20);
             TB_CUDA(ctx, cudaMalloc(&nc.d, nc.cap));
             ctx->chunks.push_back(nc);
             ck = &ctx->chunks.back();
         }
         size_t first = pos, bytes = 0;
         while (pos < todo.size() && ck->used + bytes + bsz[pos] <= ck->cap) bytes += bsz[pos++];
-        int rc = ensure_stage(ctx, bytes);
+        tb_ctx::Slot* sl = nullptr;
+        int rc = acquire_slot(ctx, bytes, 0, &sl);
         if (rc) return rc;
-        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // staging buffer may be in flight
         size_t o = 0;
         for (size_t j = first; j < pos; ++j) {
-            write_blob(todo[j]->p, (uint8_t*)ctx->h_stage + o);
+            write_blob(todo[j]->p, (uint8_t*)sl->h + o);
             todo[j]->p.d_blob = (uint8_t*)ck->d + ck->used + o;
             todo[j]->p.owner = ctx;
             ck->live++;
             o += bsz[j];
         }
-        TB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ck->d + ck->used, ctx->h_stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        TB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ck->d + ck->used, sl->h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        TB_CUDA(ctx, cudaEventRecord(sl->ev, ctx->copy_stream));
+        sl->busy = true;
         ctx->h2d_bytes += (int64_t)bytes;
-        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ck->used += bytes;
     }
     (void)total;
@@ -276,7 +307,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         return rc;
     }
     const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 64;
-    const int NL = (ctx->profile || single_plan_mode) ? 1 : std::max(1, std::min(ctx->n_lanes, (int)((idx.size() + max_wave - 1) / max_wave)));
+    const int NL = (ctx->profile || single_plan_mode) ? 1 : ctx->n_lanes;
     // try to grow the arena so that NL full waves fit (bounded by the configured limit)
     {
         std::vector<size_t> needs;
@@ -298,7 +329,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             }
             target = std::min(target, want);
             if (target > ctx->arena_bytes) {
-                cudaStreamSynchronize(ctx->stream);
+                sync_all_lanes(ctx);
                 void* na = nullptr;
                 cudaFree(ctx->arena);
                 ctx->arena = nullptr;
@@ -328,7 +359,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         const size_t cap = (ctx->arena_bytes / (size_t)NL) / 256 * 256;
         Wave cur;
         size_t used = 0;
-        int lane = 0;
+        int lane = ctx->lane_cursor % NL;
         auto flush = [&]() {
             if (cur.members.empty()) return;
             cur.lane = lane;
@@ -360,6 +391,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             used += need;
         }
         flush();
+        ctx->lane_cursor = lane;
     }
     const size_t n_lane_waves = waves.size();
     for (auto& w : solo) waves.push_back(std::move(w));
@@ -494,12 +526,15 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     if (launches.empty()) return TB_OK;
     const double t_l0 = now_ms();
     ctx->host_ms[2] += t_l0 - t_b0;
-    rc = ensure_stage(ctx, host.size());
+    tb_ctx::Slot* sl = nullptr;
+    rc = acquire_slot(ctx, host.size(), host.size(), &sl);
     if (rc) return rc;
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::memcpy(ctx->h_stage, host.data(), host.size());
-    TB_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage, ctx->h_stage, host.size(), cudaMemcpyHostToDevice, ctx->stream));
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    std::memcpy(sl->h, host.data(), host.size());
+    // work lists go up on the copy stream (behind the descriptor blobs they point to); every lane waits for them
+    TB_CUDA(ctx, cudaMemcpyAsync(sl->d, sl->h, host.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    for (int l = 1; l < NL; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_copy, 0));
     if (ctx->profile) {
         while (ctx->prof_events.size() < launches.size() + 1) {
             cudaEvent_t e;
@@ -507,10 +542,6 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             ctx->prof_events.push_back(e);
         }
         TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[0], ctx->stream));
-    }
-    if (NL > 1) {
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        for (int l = 1; l < NL; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
     }
     auto join_lanes = [&]() -> int {
         for (int l = 1; l < NL; ++l) {
@@ -527,24 +558,24 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             joined = true;
         }
         const Launch& L = launches[li];
-        if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)ctx->d_stage);
-        else launch_one<float>(ctx, L, (uint8_t*)ctx->d_stage);
+        if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)sl->d);
+        else launch_one<float>(ctx, L, (uint8_t*)sl->d);
         if (ctx->profile) TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[li + 1], ctx->stream));
     }
+    // the main stream joins the lanes at the end of every group: the slot event (and the caller's final sync)
+    // then cover every kernel that reads this slot's work lists
     if (!joined) {
         rc = join_lanes();
         if (rc) return rc;
     }
     TB_CUDA(ctx, cudaGetLastError());
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    float ms = 0;
-    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms += ms;
+    TB_CUDA(ctx, cudaEventRecord(sl->ev, ctx->stream));
+    sl->busy = true;
     ctx->host_ms[3] += now_ms() - t_l0;
     ctx->last_launches += (int64_t)launches.size();
     ctx->h2d_bytes += (int64_t)host.size();
     if (ctx->profile) {
+        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         for (size_t li = 0; li < launches.size(); ++li) {
             float pm = 0;
             TB_CUDA(ctx, cudaEventElapsedTime(&pm, ctx->prof_events[li], ctx->prof_events[li + 1]));
@@ -555,10 +586,23 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     return TB_OK;
 }
 
-int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
-                  double* out_max, bool single) {
-    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
-    if (n < 0 || (n > 0 && (!plans || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+// one batch of compiled plans: upload what is not resident, enqueue all launches (asynchronous)
+int enqueue_batch(tb_ctx* ctx, tb_plan* const* plans, int64_t lo, int64_t hi, std::vector<int32_t>& status, bool single) {
+    double t_u0 = now_ms();
+    int rc = ensure_uploaded(ctx, plans + lo, hi - lo);
+    if (rc) return rc;
+    ctx->host_ms[1] += now_ms() - t_u0;
+    std::vector<int64_t> gi, gf;
+    for (int64_t i = lo; i < hi; ++i) {
+        if (!plans[i]) continue;
+        (plans[i]->p.value_type == TB_VALUE_I32 ? gi : gf).push_back(i);
+    }
+    rc = run_group(ctx, plans, gi, TB_VALUE_I32, status, single);
+    if (rc) return rc;
+    return run_group(ctx, plans, gf, TB_VALUE_F32, status, single);
+}
+
+int begin_call(tb_ctx* ctx, int64_t n) {
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->last_ms = 0;
     ctx->last_launches = 0;
@@ -568,29 +612,42 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
         ctx->prof_ms[q] = 0;
         ctx->prof_launches[q] = 0;
     }
-    double t_u0 = now_ms();
-    int rc = ensure_uploaded(ctx, plans, n);
-    if (rc) return rc;
-    ctx->host_ms[1] = now_ms() - t_u0;
-    ctx->host_ms[2] = 0;
-    ctx->host_ms[3] = 0;
-    rc = ensure_results(ctx, (size_t)std::max<int64_t>(n, 1));
-    if (rc) return rc;
-    std::vector<int32_t> status((size_t)n, TB_OK);
-    std::vector<int64_t> gi, gf;
-    for (int64_t i = 0; i < n; ++i) {
-        if (!plans[i]) continue;
-        (plans[i]->p.value_type == TB_VALUE_I32 ? gi : gf).push_back(i);
+    for (int q = 0; q < 6; ++q) ctx->host_ms[q] = 0;
+    ctx->lane_cursor = 0;
+    // descriptor chunks: when nothing is resident keep only the largest chunk (the device is idle between calls)
+    {
+        bool all_free = !ctx->chunks.empty();
+        size_t best = 0;
+        for (size_t q = 0; q < ctx->chunks.size(); ++q) {
+            all_free = all_free && ctx->chunks[q].live == 0;
+            if (ctx->chunks[q].cap > ctx->chunks[best].cap) best = q;
+        }
+        if (all_free && ctx->chunks.size() > 1) {
+            BlobChunk keep = ctx->chunks[best];
+            for (size_t q = 0; q < ctx->chunks.size(); ++q)
+                if (q != best && ctx->chunks[q].d) cudaFree(ctx->chunks[q].d);
+            keep.used = 0;
+            ctx->chunks.assign(1, keep);
+        }
     }
-    rc = run_group(ctx, plans, gi, TB_VALUE_I32, status, single);
+    int rc = ensure_results(ctx, (size_t)std::max<int64_t>(n, 1));
     if (rc) return rc;
-    rc = run_group(ctx, plans, gf, TB_VALUE_F32, status, single);
-    if (rc) return rc;
-    if (!gi.empty() || !gf.empty()) {
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return TB_OK;
+}
+
+int finish_call(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, const std::vector<int32_t>& status,
+                double* out_values, int32_t* out_status, double* out_max, bool any) {
+    if (any) {
         TB_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (int64_t)n * 8;
-        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    int rc = sync_all_lanes(ctx);
+    if (rc) return rc;
+    float ms = 0;
+    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
     double mx = -std::numeric_limits<double>::infinity();
     int worst = TB_OK;
     for (int64_t i = 0; i < n; ++i) {
@@ -608,6 +665,23 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
     if (out_max) *out_max = mx;
     if (worst != TB_OK) return set_err(ctx, worst, "one or more branches failed (see per-branch status): arena too small");
     return TB_OK;
+}
+
+int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
+                  double* out_max, bool single) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!plans || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    int rc = begin_call(ctx, n);
+    if (rc) return rc;
+    std::vector<int32_t> status((size_t)n, TB_OK);
+    bool any = false;
+    for (int64_t i = 0; i < n; ++i) any = any || plans[i];
+    rc = enqueue_batch(ctx, plans, 0, n, status, single);
+    if (rc) {
+        sync_all_lanes(ctx);
+        return rc;
+    }
+    return finish_call(ctx, plans, r, n, status, out_values, out_status, out_max, any);
 }
 
 }  // namespace
@@ -653,6 +727,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
         if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
     }
     TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
     for (int l = 1; l < c->n_lanes; ++l) {
         TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking));
         TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
@@ -677,12 +753,17 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
 int tb_shutdown(tb_ctx* ctx) {
     if (!ctx) return TB_OK;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    sync_all_lanes(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
     for (auto& c : ctx->chunks)
         if (c.d) cudaFree(c.d);
-    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
-    if (ctx->d_stage) cudaFree(ctx->d_stage);
+    for (auto& sl : ctx->slots) {
+        if (sl.h) cudaFreeHost(sl.h);
+        if (sl.d) cudaFree(sl.d);
+        if (sl.ev) cudaEventDestroy(sl.ev);
+    }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->d_results) cudaFree(ctx->d_results);
     if (ctx->h_results) cudaFreeHost(ctx->h_results);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -780,39 +861,75 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
                          int32_t* out_status, double* out_max) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
     if (n < 0 || (n > 0 && (!nets || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    const double t_c0 = now_ms();
+    int rc = begin_call(ctx, n);
+    if (rc) return rc;
     std::vector<tb_plan*> plans((size_t)n, nullptr);
     std::vector<int> codes((size_t)n, TB_OK);
     std::vector<std::string> errs((size_t)n);
+    std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[(size_t)std::max<int64_t>(n, 1)]);
+    for (int64_t i = 0; i < n; ++i) done[i].store(0, std::memory_order_relaxed);
     int nthreads = ctx->opts.host_threads > 0 ? ctx->opts.host_threads : (int)std::thread::hardware_concurrency();
     nthreads = std::max(1, std::min<int>(nthreads, (int)std::max<int64_t>(1, n / 8)));
     std::atomic<int64_t> next{0};
+    std::atomic<bool> abort{false};
     const uint32_t flags = ctx->opts.plan_flags;
-    const double t_c0 = now_ms();
+    // plan compilation runs on worker threads, in index order; the calling thread uploads and launches batch b
+    // while the workers are already compiling batch b+1 (the GPU meanwhile executes batch b-1)
     auto worker = [&]() {
         for (;;) {
             int64_t i = next.fetch_add(1);
             if (i >= n) break;
-            if (nets[i].n_leaves == 0) continue;  // empty graph
-            tb_plan* p = new tb_plan();
-            codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
-            if (codes[i]) delete p;
-            else plans[i] = p;
+            if (!abort.load(std::memory_order_relaxed) && nets[i].n_leaves != 0) {
+                tb_plan* p = new tb_plan();
+                codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
+                if (codes[i]) {
+                    delete p;
+                    abort.store(true);
+                } else plans[i] = p;
+            }
+            done[i].store(1, std::memory_order_release);
         }
     };
-    {
-        std::vector<std::thread> th;
-        for (int t = 1; t < nthreads; ++t) th.emplace_back(worker);
-        worker();
-        for (auto& t : th) t.join();
-    }
-    const double t_compile = now_ms() - t_c0;
-    int rc = TB_OK;
-    for (int64_t i = 0; i < n; ++i)
-        if (codes[i]) {
-            rc = set_err(ctx, codes[i], "branch " + std::to_string(i) + ": " + errs[i]);
-            break;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
+    const int64_t batch = std::max<int64_t>(256, (int64_t)(ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 64) * ctx->n_lanes * 2);
+    std::vector<int32_t> status((size_t)n, TB_OK);
+    bool any = false;
+    double t_wait = 0;
+    for (int64_t lo = 0; lo < n && rc == TB_OK; lo += batch) {
+        const int64_t hi = std::min(n, lo + batch);
+        const double tw0 = now_ms();
+        if (nthreads == 1) {
+            while (next.load() < hi && next.load() < n) {  // single-threaded: compile this batch inline
+                int64_t i = next.fetch_add(1);
+                if (i >= n) break;
+                if (nets[i].n_leaves != 0) {
+                    tb_plan* p = new tb_plan();
+                    codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
+                    if (codes[i]) delete p;
+                    else plans[i] = p;
+                }
+                done[i].store(1, std::memory_order_release);
+            }
         }
-    if (rc == TB_OK) rc = contract_impl(ctx, plans.data(), r, n, out_values, out_status, out_max, false);
+        for (int64_t i = lo; i < hi; ++i)
+            while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+        t_wait += now_ms() - tw0;
+        for (int64_t i = lo; i < hi; ++i) {
+            if (codes[i]) {
+                rc = set_err(ctx, codes[i], "branch " + std::to_string(i) + ": " + errs[i]);
+                break;
+            }
+            any = any || plans[i];
+        }
+        if (rc == TB_OK) rc = enqueue_batch(ctx, plans.data(), lo, hi, status, false);
+    }
+    abort.store(rc != TB_OK);
+    for (auto& t : th) t.join();
+    ctx->host_ms[0] = t_wait;  // time the launching thread spent waiting for the compiler threads
+    if (rc == TB_OK) rc = finish_call(ctx, plans.data(), r, n, status, out_values, out_status, out_max, any);
+    else sync_all_lanes(ctx);
     const double t_d0 = now_ms();
     // the temporary plans all live in chunks of this call: release the device side once, free hosts in parallel
     for (tb_plan* p : plans)
@@ -831,15 +948,14 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
             for (;;) {
                 int64_t i = nx.fetch_add(64);
                 if (i >= n) break;
-                for (int64_t j = i; j < std::min<int64_t>(n, i + 64); ++j) delete plans[j];
+                for (int64_t q = i; q < std::min<int64_t>(n, i + 64); ++q) delete plans[q];
             }
         };
-        std::vector<std::thread> th;
-        for (int t = 1; t < nthreads; ++t) th.emplace_back(killer);
+        std::vector<std::thread> th2;
+        for (int t = 1; t < nthreads; ++t) th2.emplace_back(killer);
         killer();
-        for (auto& t : th) t.join();
+        for (auto& t : th2) t.join();
     }
-    ctx->host_ms[0] = t_compile;
     ctx->host_ms[4] = now_ms() - t_d0;
     ctx->host_ms[5] = now_ms() - t_c0;
     return rc;
