@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--value-type", default="i32", choices=["i32", "i16"], help="i16 = packed int16x2 (plan flag PREFER_I16)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -235,7 +236,7 @@ def main():
     n_br = len(branches)
     sliced = [to_sliced(b) for b in branches]
 
-    eng = tbcuda.Engine(local_rank)
+    eng = tbcuda.Engine(local_rank, plan_flags=(tbcuda.TB_PLAN_PREFER_I16 if args.value_type == "i16" else 0))
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # plans for every branch (host-only compile) to get costs; then keep only this rank's shard
@@ -333,10 +334,11 @@ def main():
         dpx = dpx_peak()
         gemm_ms, gemm_launches = prof["gemm"]
         my_gemm_ops = float(sum(stats[i].gemm_ops for i in mine if stats[i]))
-        peak_gops = dpx.get("viaddmax_s32_Gops")
+        peak_gops = dpx.get("viaddmax_s16x2_Gops" if args.value_type == "i16" else "viaddmax_s32_Gops")
         ach = my_gemm_ops / (gemm_ms * 1e-3) * 1e-9 if gemm_ms > 0 else None
-        roofline = {"bound": "dpx-int32 (VIADDMNMX issue rate; the semiring is (max,+), tensor cores do not apply)",
-                    "kernel": "k_gemm<int32>", "achieved": ach, "peak": peak_gops, "unit": "Gop/s",
+        roofline = {"bound": ("dpx-int16x2 (VIADDMNMX.S16x2" if args.value_type == "i16" else "dpx-int32 (VIADDMNMX") +
+                             " issue rate; the semiring is (max,+), tensor cores do not apply)",
+                    "kernel": "k_gemm2h (packed int16x2)" if args.value_type == "i16" else "k_gemm2<int32>", "achieved": ach, "peak": peak_gops, "unit": "Gop/s",
                     "frac": (ach / peak_gops) if (ach and peak_gops) else None, "traffic": None,
                     "peak_source": "tensorbranching.jl_b200/dpx_peak microbenchmark run inside bench.py (register-resident VIADDMNMX, all SMs)",
                     "avg_launch_ms": gemm_ms / max(1, gemm_launches), "launches": gemm_launches,
@@ -345,8 +347,8 @@ def main():
                             "achieved_whole_step": float(abytes[mine].sum()) / (ms_step * 1e-3) * 1e-9}}
         line = {"metric": "tropical contraction throughput", "value": total_ops / (ms_step * 1e-3) * 1e-9, "unit": "Gop/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
-                "data": "synthetic", "config": config, "slices_per_s": n_br / (ms_step * 1e-3), "branches": n_br,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "int16x2" if args.value_type == "i16" else "int32", "data": "synthetic", "config": config, "slices_per_s": n_br / (ms_step * 1e-3), "branches": n_br,
                 "total_ops": total_ops, "mis": float(np.max(result)), "gpu_launches": int(launches_step * args.steps),
                 "launches_per_step": int(launches_step), "device_ms_last_step": dev_ms_last,
                 "plan_compile_s_all_branches": plan_s, "clocks": clocks, "roofline": roofline, "dpx_peak": dpx}

@@ -51,7 +51,7 @@ typedef enum tb_value_type {
     TB_VALUE_AUTO = 0,   /* i32 for unit / integer weights, f32 otherwise */
     TB_VALUE_I32 = 1,    /* exact; -inf is the sentinel -2^30 */
     TB_VALUE_F32 = 2,    /* Tropical{Float32}; -inf is IEEE -inf */
-    TB_VALUE_I16X2 = 3   /* packed pairs; requires sum of weights < 2^13 (reserved) */
+    TB_VALUE_I16X2 = 3   /* int16 values, packed pairs in the GEMM (VIADDMNMX.S16x2); -inf is -2^14; needs sum |w| < 2^13 */
 } tb_value_type;
 
 typedef enum tb_weight_dtype {
@@ -69,6 +69,8 @@ typedef enum tb_weight_dtype {
 #define TB_PLAN_NO_GEMM 4u            /* testing: never choose the tiled max-plus GEMM kernel */
 #define TB_PLAN_SCRAMBLE_LAYOUT 8u    /* testing: pseudo-random (valid) operand layouts */
 #define TB_PLAN_NO_SPLIT_K 16u        /* testing: never split a long reduction into partial + reduce steps */
+#define TB_PLAN_PREFER_I16 32u        /* value_type AUTO picks packed int16 (TB_VALUE_I16X2) when the weights are
+                                         integers with sum |w| < 8192; results are identical, 2x DPX rate, half the bytes */
 
 typedef struct tb_options {
     int32_t device;          /* CUDA device ordinal */

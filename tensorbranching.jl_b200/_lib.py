@@ -23,6 +23,7 @@ TB_PLAN_NO_FUSED_SUBTREES = 2
 TB_PLAN_NO_GEMM = 4
 TB_PLAN_SCRAMBLE_LAYOUT = 8
 TB_PLAN_NO_SPLIT_K = 16
+TB_PLAN_PREFER_I16 = 32
 
 
 class tb_options(C.Structure):

@@ -43,7 +43,7 @@ def _value_type_for(element_type, weight_code):
     Float32 (the only float width the device kernels implement)."""
     et = np.dtype(element_type) if element_type is not None else None
     if weight_code in (L.TB_WEIGHT_UNIT, L.TB_WEIGHT_I32, L.TB_WEIGHT_I64):
-        return L.TB_VALUE_I32
+        return L.TB_VALUE_AUTO  # int32, or packed int16 when the plan flags prefer it and the weights fit
     if et is not None and et == np.float64:
         raise L.TBError(L.TB_ERR_UNSUPPORTED, "element_type Float64 with real weights is not implemented on the device (use Float32)")
     return L.TB_VALUE_F32

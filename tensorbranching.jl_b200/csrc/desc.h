@@ -26,7 +26,8 @@ constexpr int MAX_RANK = 31;        // tensors up to 2^31 elements; shift tables
 constexpr int FUSED_MAX_RANK = 10;  // every tensor inside a fused subtree has rank <= this
 constexpr int FUSED_MAX_TC = 16;    // log2 ops of one fused step
 constexpr int FUSED_SMEM_ELEMS = 8192;  // 32 KB of 4-byte values per subtree
-constexpr int GEMM_TILE_MAX = 7;    // 128 x 128 output tile
+constexpr int GEMM_TILE_MAX = 7;    // 128 x 128 output tile (4-byte values)
+constexpr int GEMM_TILE_MAX_M16 = 8;  // packed int16: 256 x 128 tile, every thread owns 16 (m) x 8 (n) outputs
 constexpr int GEMM_STAGE_ELEMS = 4096;  // elements per pipeline stage (A + B panels of all sub-tiles)
 
 // pool layout (elements): [0..3] edge tensor (0,0,0,-inf)  [4] unit scalar (0)  [8+2i, 8+2i+1] vertex i
@@ -99,6 +100,9 @@ struct BigInst {           // one non-fused step of one branch
 template <typename T> struct Tropical;
 template <> struct Tropical<int32_t> {
     static constexpr int32_t kNegInf = -(1 << 30);
+};
+template <> struct Tropical<int16_t> {
+    static constexpr int32_t kNegInf = -(1 << 14);  // a + b >= -2^15 never wraps; needs sum |w| < 2^13
 };
 
 }  // namespace tb

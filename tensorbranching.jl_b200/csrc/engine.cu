@@ -21,6 +21,7 @@
 #include <memory>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.cuh"
@@ -135,8 +136,27 @@ int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
 }
 
 int acquire_slot(tb_ctx* ctx, size_t hbytes, size_t dbytes, tb_ctx::Slot** out) {
-    tb_ctx::Slot& sl = ctx->slots[ctx->slot_cursor];
-    ctx->slot_cursor = (ctx->slot_cursor + 1) % tb_ctx::kSlots;
+    // prefer a free slot that is already big enough (pinned allocations cost milliseconds), then any free slot,
+    // and only then wait for the oldest busy one
+    int pick = -1;
+    for (int q = 0; q < tb_ctx::kSlots; ++q) {
+        tb_ctx::Slot& c = ctx->slots[q];
+        if (c.busy && c.ev && cudaEventQuery(c.ev) == cudaSuccess) c.busy = false;
+        if (c.busy) continue;
+        const bool fits = c.hcap >= hbytes && c.dcap >= dbytes;
+        if (pick < 0) pick = q;
+        else {
+            tb_ctx::Slot& p = ctx->slots[pick];
+            const bool pfits = p.hcap >= hbytes && p.dcap >= dbytes;
+            if ((fits && !pfits) || (fits == pfits && (fits ? c.hcap + c.dcap < p.hcap + p.dcap : c.hcap + c.dcap > p.hcap + p.dcap))) pick = q;
+        }
+    }
+    cudaGetLastError();  // cudaEventQuery returns cudaErrorNotReady for pending events
+    if (pick < 0) {
+        pick = ctx->slot_cursor;
+        ctx->slot_cursor = (ctx->slot_cursor + 1) % tb_ctx::kSlots;
+    }
+    tb_ctx::Slot& sl = ctx->slots[pick];
     if (!sl.ev) TB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
     if (sl.busy) {
         TB_CUDA(ctx, cudaEventSynchronize(sl.ev));
@@ -156,6 +176,7 @@ int acquire_slot(tb_ctx* ctx, size_t hbytes, size_t dbytes, tb_ctx::Slot** out) 
         TB_CUDA(ctx, cudaMalloc(&sl.d, cap));
         sl.dcap = cap;
     }
+    sl.busy = true;  // reserved; the caller records sl.ev behind the last consumer
     *out = &sl;
     return TB_OK;
 }
@@ -164,6 +185,7 @@ int sync_all_lanes(tb_ctx* ctx) {
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     for (int l = 1; l < ctx->n_lanes; ++l) TB_CUDA(ctx, cudaStreamSynchronize(ctx->side[l]));
     TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& sl : ctx->slots) sl.busy = false;  // everything that used a slot has completed
     return TB_OK;
 }
 
@@ -198,14 +220,14 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
     // section sizes are known from the plan; blobs are serialised straight into the pinned staging buffer
     auto a16 = [](size_t x) { return (x + 15) / 16 * 16; };
     auto blob_size = [&](const Plan& P) {
-        return a16(P.pool.size() * 4) + a16(P.sub_steps.size() * sizeof(SubStep)) + a16(P.big_steps.size() * sizeof(BigStep));
+        return a16(P.pool_bytes()) + a16(P.sub_steps.size() * sizeof(SubStep)) + a16(P.big_steps.size() * sizeof(BigStep));
     };
     auto write_blob = [&](Plan& P, uint8_t* dst) {
-        size_t pool_b = a16(P.pool.size() * 4), sub_b = a16(P.sub_steps.size() * sizeof(SubStep));
+        size_t pool_b = a16(P.pool_bytes()), sub_b = a16(P.sub_steps.size() * sizeof(SubStep));
         P.sub_blob_off = pool_b;
         P.big_blob_off = pool_b + sub_b;
         P.blob_bytes = blob_size(P);
-        if (!P.pool.empty()) std::memcpy(dst, P.pool.data(), P.pool.size() * 4);
+        P.write_pool(dst);
         if (!P.sub_steps.empty()) std::memcpy(dst + P.sub_blob_off, P.sub_steps.data(), P.sub_steps.size() * sizeof(SubStep));
         if (!P.big_steps.empty()) std::memcpy(dst + P.big_blob_off, P.big_steps.data(), P.big_steps.size() * sizeof(BigStep));
     };
@@ -273,7 +295,11 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
             k_generic<T><<<L.grid, BIG_THREADS, 0, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             break;
         case 2:
-            if (ctx->gemm_v1) {
+            if constexpr (std::is_same<T, int16_t>::value) {
+                const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
+                k_gemm2h<<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
+                                                                 L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off));
+            } else if (ctx->gemm_v1) {
                 k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             } else {
                 const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
@@ -292,7 +318,7 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
 int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& idx, int vt, std::vector<int32_t>& status,
               bool single_plan_mode) {
     if (idx.empty()) return TB_OK;
-    const size_t elem = 4;
+    const size_t elem = vt == TB_VALUE_I16X2 ? 2 : 4;
     // ---- waves
     size_t max_need = 0;
     for (int64_t i : idx) max_need = std::max(max_need, (size_t)plans[i]->p.arena_elems * elem + 256);
@@ -559,6 +585,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         }
         const Launch& L = launches[li];
         if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)sl->d);
+        else if (vt == TB_VALUE_I16X2) launch_one<int16_t>(ctx, L, (uint8_t*)sl->d);
         else launch_one<float>(ctx, L, (uint8_t*)sl->d);
         if (ctx->profile) TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[li + 1], ctx->stream));
     }
@@ -592,12 +619,15 @@ int enqueue_batch(tb_ctx* ctx, tb_plan* const* plans, int64_t lo, int64_t hi, st
     int rc = ensure_uploaded(ctx, plans + lo, hi - lo);
     if (rc) return rc;
     ctx->host_ms[1] += now_ms() - t_u0;
-    std::vector<int64_t> gi, gf;
+    std::vector<int64_t> gi, gf, gh;
     for (int64_t i = lo; i < hi; ++i) {
         if (!plans[i]) continue;
-        (plans[i]->p.value_type == TB_VALUE_I32 ? gi : gf).push_back(i);
+        const int v = plans[i]->p.value_type;
+        (v == TB_VALUE_I32 ? gi : v == TB_VALUE_I16X2 ? gh : gf).push_back(i);
     }
     rc = run_group(ctx, plans, gi, TB_VALUE_I32, status, single);
+    if (rc) return rc;
+    rc = run_group(ctx, plans, gh, TB_VALUE_I16X2, status, single);
     if (rc) return rc;
     return run_group(ctx, plans, gf, TB_VALUE_F32, status, single);
 }
@@ -739,6 +769,9 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2h, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2h, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     {
@@ -833,8 +866,9 @@ int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_
     const void* src = nullptr;
     int64_t bytes = 0;
     int64_t header[4] = {P.arena_elems, P.root_off, P.n_levels, P.value_type};
+    std::vector<uint8_t> pool_dev(P.pool_bytes() + 16);
     switch (which) {
-        case 0: src = P.pool.data(); bytes = (int64_t)P.pool.size() * 4; break;
+        case 0: P.write_pool(pool_dev.data()); src = pool_dev.data(); bytes = (int64_t)P.pool_bytes(); break;
         case 1: src = P.sub_steps.data(); bytes = (int64_t)(P.sub_steps.size() * sizeof(SubStep)); break;
         case 2: src = P.subtrees.data(); bytes = (int64_t)(P.subtrees.size() * sizeof(SubTree)); break;
         case 3: src = P.big_steps.data(); bytes = (int64_t)(P.big_steps.size() * sizeof(BigStep)); break;
@@ -978,9 +1012,10 @@ int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_da
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     double* d_tmp = nullptr;
     TB_CUDA(ctx, cudaMalloc(&d_tmp, (size_t)n * sizeof(double)));
-    const uint8_t* src = (const uint8_t*)ctx->arena + (size_t)(ctx->last_plan_arena_base_elems + P.off[node]) * 4;
+    const uint8_t* src = (const uint8_t*)ctx->arena + (size_t)(ctx->last_plan_arena_base_elems + P.off[node]) * (size_t)P.elem_size();
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (P.value_type == TB_VALUE_I32) k_to_double<int32_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t*)src, d_tmp, n);
+    else if (P.value_type == TB_VALUE_I16X2) k_to_double<int16_t><<<blocks, 256, 0, ctx->stream>>>((const int16_t*)src, d_tmp, n);
     else k_to_double<float><<<blocks, 256, 0, ctx->stream>>>((const float*)src, d_tmp, n);
     cudaError_t e = cudaMemcpyAsync(out_data, d_tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

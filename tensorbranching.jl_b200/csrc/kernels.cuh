@@ -29,6 +29,15 @@ template <> struct Ops<int32_t> {
     static __device__ __forceinline__ int32_t vmax(int32_t a, int32_t b) { return max(a, b); }
     static __device__ __forceinline__ double to_double(int32_t v) { return v <= -(1 << 29) ? -INFINITY : (double)v; }
 };
+template <> struct Ops<int16_t> {
+    typedef short4 vec4;  // 4 elements = 8 bytes
+    static __device__ __forceinline__ int16_t neg_inf() { return (int16_t)(-(1 << 14)); }
+    static __device__ __forceinline__ int16_t addmax(int16_t a, int16_t b, int16_t c) {
+        return (int16_t)__viaddmax_s32((int)a, (int)b, (int)c);  // values stay in [-2^15, 2^13): no wrap
+    }
+    static __device__ __forceinline__ int16_t vmax(int16_t a, int16_t b) { return a > b ? a : b; }
+    static __device__ __forceinline__ double to_double(int16_t v) { return v <= -(1 << 13) ? -INFINITY : (double)v; }
+};
 template <> struct Ops<float> {
     typedef float4 vec4;
     static __device__ __forceinline__ float neg_inf() { return -INFINITY; }
@@ -36,6 +45,11 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ float vmax(float a, float b) { return fmaxf(a, b); }
     static __device__ __forceinline__ double to_double(float v) { return (double)v; }
 };
+
+template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+template <> __device__ __forceinline__ int16_t shfl_xor_t<int16_t>(int16_t v, int m) {
+    return (int16_t)__shfl_xor_sync(0xffffffffu, (int)v, m);
+}
 
 __device__ __forceinline__ uint32_t scatter_bits(uint32_t x, const uint8_t* sh, int n) {
     uint32_t off = 0;
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst*
                     acc = Ops<T>::addmax(A[offA + ra], B[offB + rb], acc);
                 }
             }
-            for (int s = 1; s < (1 << ks); s <<= 1) acc = Ops<T>::vmax(acc, __shfl_xor_sync(0xffffffffu, acc, s));
+            for (int s = 1; s < (1 << ks); s <<= 1) acc = Ops<T>::vmax(acc, shfl_xor_t(acc, s));
             if (active && kp == 0) C[c] = acc;
         }
         __syncthreads();
@@ -702,6 +716,252 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 8; ++j) Ct[moff[i] + noff[j]] = acc[i][j];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: packed int16x2 variant of k_gemm2.  Same producer / mbarrier / TMA structure; every consumer thread owns
+// 16 (m) x 8 (n) outputs as 8 x 8 packed words (two consecutive m per word, the pair is A's address bit 0), fed by
+// 2 x LDS.128 (A: 16 int16) + 2 x LDS.64 (B: 8 int16) per k-step; the B value is duplicated into both halves with
+// one PRMT and 64 VIADDMNMX.S16x2 update 128 outputs.  Tile = 2^tm x 2^tn with tm <= 8, tn <= 7.
+// ------------------------------------------------------------------------------------------------
+constexpr int G2H_STG_ELEMS = 8192;  // int16 elements of one staged quarter (16 KB)
+struct TileInfoH {
+    long long cbase[32];
+    void* C;
+    int tm, tn, kc, nchunks, valid, lane_n_first;
+    unsigned char e_spos[14], e_cs[14];
+    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_pad;
+};
+__device__ __forceinline__ uint32_t stg_swz_h(uint32_t x) { return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7u) << 3); }
+
+__global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
+                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter) {
+    typedef int16_t T;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    T* stage_mem = reinterpret_cast<T*>(dyn_smem);                       // G2_STAGES x 16 KB
+    T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);         // 2 x 16 KB
+    constexpr int STAGE_ELEMS = GEMM_STAGE_ELEMS * 2;                    // int16 elements per stage
+    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ TileInfoH tinfo[2];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < G2_STAGES; ++i) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_empty[i], G2_CONSUMERS / 32);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_tfull[i], 1);
+            mbar_init(&bar_tempty[i], G2_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid < G2_PRODUCERS) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::);
+        if (tid >= 32) return;
+        const int lane = tid;
+        unsigned it = 0;
+        for (unsigned tcount = 0;; ++tcount) {
+            unsigned tile_g = 0;
+            if (lane == 0) tile_g = atomicAdd(counter, 1u);
+            tile_g = __shfl_sync(0xffffffffu, tile_g, 0);
+            const int slot = tcount & 1;
+            mbar_wait(&bar_tempty[slot], ((tcount >> 1) & 1) ^ 1);
+            if (tile_g >= total_tiles) {
+                if (lane == 0) {
+                    tinfo[slot].valid = 0;
+                    mbar_arrive(&bar_tfull[slot]);
+                }
+                break;
+            }
+            const int idx = find_inst(tile_starts, n_insts, tile_g);
+            const BigInst inst = insts[idx];
+            const uint32_t tile = tile_g - __ldg(tile_starts + idx);
+            const BigStep* __restrict__ d = inst.step;
+            const int tm = d->tm, tn = d->tn, nk = d->nk, kc = d->kc, ng = d->ng;
+            const int s_log = 8 - (tm + tn - 7), S = 1 << s_log;
+            const T* Ag = reinterpret_cast<const T*>(inst.arena) + d->a_off;
+            const T* Bg = reinterpret_cast<const T*>(inst.arena) + d->b_off;
+            long long ab = -1, bb = -1, cb = -1;
+            if (lane < S) {
+                const unsigned long long g = (unsigned long long)tile * S + lane;
+                if (g < (1ull << ng)) {
+                    const int n_mhi = d->n_mhi, n_nhi = d->n_nhi;
+                    const unsigned long long gm = g & ((1ull << n_mhi) - 1ull);
+                    const unsigned long long gn = (g >> n_mhi) & ((1ull << n_nhi) - 1ull);
+                    const unsigned long long gb = g >> (n_mhi + n_nhi);
+                    ab = (long long)((gm | (gb << n_mhi)) << (tm + nk));
+                    bb = (long long)((gn | (gb << n_nhi)) << (tn + nk));
+                    cb = (long long)scatter_bits((uint32_t)g, d->c_shift + tm + tn, ng);
+                }
+            }
+            TileInfoH& ti = tinfo[slot];
+            ti.cbase[lane] = cb;
+            if (lane < 14) {
+                ti.e_spos[lane] = d->a_shift[lane];
+                ti.e_cs[lane] = d->b_shift[lane];
+            }
+            if (lane == 0) {
+                ti.C = reinterpret_cast<T*>(inst.arena) + d->c_off;
+                ti.tm = tm;
+                ti.tn = tn;
+                ti.kc = kc;
+                ti.nchunks = 1 << (nk - kc);
+                ti.lane_n_first = d->lane_n_first;
+                ti.e_cs_mtop = d->a_shift[30];
+                ti.e_cs_ntop = d->a_shift[31];
+                ti.e_vec = d->b_shift[31];
+                ti.valid = 1;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tfull[slot]);
+            const int la = kc + tm, lb = kc + tn;
+            const unsigned n_active = __popc(__ballot_sync(0xffffffffu, ab >= 0));
+            const unsigned stage_bytes = n_active * ((1u << la) + (1u << lb)) * 2u;
+            const int nchunks = 1 << (nk - kc);
+            for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                const int stage = it % G2_STAGES;
+                mbar_wait(&bar_empty[stage], ((it / G2_STAGES) & 1) ^ 1);
+                if (lane == 0) mbar_arrive_expect_tx(&bar_full[stage], stage_bytes);
+                __syncwarp();
+                if (ab >= 0) {
+                    T* sA = stage_mem + stage * STAGE_ELEMS + ((size_t)lane << la);
+                    T* sB = stage_mem + stage * STAGE_ELEMS + ((size_t)S << la) + ((size_t)lane << lb);
+                    bulk_g2s(sA, Ag + ab + ((long long)ch << la), (1u << la) * 2u, &bar_full[stage]);
+                    bulk_g2s(sB, Bg + bb + ((long long)ch << lb), (1u << lb) * 2u, &bar_full[stage]);
+                }
+            }
+        }
+        return;
+    }
+
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;\n" ::);
+    const int ctid = tid - G2_PRODUCERS;
+    const int lane = tid & 31;
+    unsigned it = 0;
+    for (unsigned tcount = 0;; ++tcount) {
+        const int slot = tcount & 1;
+        mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
+        const TileInfoH& ti = tinfo[slot];
+        if (!ti.valid) break;
+        const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
+        const int tps_log = tm + tn - 7, S = 1 << (8 - tps_log);
+        const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
+        const int tmh = ti.lane_n_first ? (lt >> (tn - 3)) : (lt & ((1 << (tm - 4)) - 1));
+        const int tnh = ti.lane_n_first ? (lt & ((1 << (tn - 3)) - 1)) : (lt >> (tm - 4));
+        const int m_lo = tmh * 8, m_hi = (1 << (tm - 1)) + tmh * 8;   // int16 element offsets inside a k-row
+        const int n_lo = tnh * 4, n_hi = (1 << (tn - 1)) + tnh * 4;
+        const int la = kc + tm, lb = kc + tn;
+        uint32_t acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0xC000C000u;  // (-2^14, -2^14)
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int stage = it % G2_STAGES;
+            mbar_wait(&bar_full[stage], (it / G2_STAGES) & 1);
+            const T* sA = stage_mem + stage * STAGE_ELEMS + ((size_t)sub << la);
+            const T* sB = stage_mem + stage * STAGE_ELEMS + ((size_t)S << la) + ((size_t)sub << lb);
+            const int KC = 1 << kc;
+#pragma unroll 1
+            for (int kk = 0; kk < KC; ++kk) {
+                const T* ar = sA + (kk << tm);
+                const T* br = sB + (kk << tn);
+                const uint4 a0 = *reinterpret_cast<const uint4*>(ar + m_lo);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(ar + m_hi);
+                const uint2 b0 = *reinterpret_cast<const uint2*>(br + n_lo);
+                const uint2 b1 = *reinterpret_cast<const uint2*>(br + n_hi);
+                const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t bw[4] = {b0.x, b0.y, b1.x, b1.y};
+                uint32_t b[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    b[2 * q] = __byte_perm(bw[q], 0, 0x1010);      // low half in both halves
+                    b[2 * q + 1] = __byte_perm(bw[q], 0, 0x3232);  // high half in both halves
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = __viaddmax_s16x2(a[i], b[j], acc[i][j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_empty[stage]);
+        }
+        // ---- staged epilogue (int16 elements, 8 per 16-byte vector)
+        {
+            const int nbr = tm + tn - 2;
+            const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 3) | ((uint32_t)tnh << (tm + 1));
+            uint32_t ts = 0, tc = 0;
+#pragma unroll
+            for (int b = 3; b < 11; ++b) {
+                const uint32_t bit = ((uint32_t)ctid >> (b - 3)) & 1u;
+                if (b < nbr) {
+                    ts |= bit << ti.e_spos[b];
+                    tc |= bit << ti.e_cs[b];
+                }
+            }
+            const bool evec = ti.e_vec != 0;
+            T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ih = r & 1, jh = r >> 1;
+                T* buf = stg_mem + (r & 1) * G2H_STG_ELEMS;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint4 v;
+                    v.x = acc[ih * 4 + 0][jh * 4 + j];
+                    v.y = acc[ih * 4 + 1][jh * 4 + j];
+                    v.z = acc[ih * 4 + 2][jh * 4 + j];
+                    v.w = acc[ih * 4 + 3][jh * 4 + j];
+                    *reinterpret_cast<uint4*>(buf + stg_swz_h(qbase | ((uint32_t)j << (tm - 1)))) = v;
+                }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
+#pragma unroll
+                for (int itr = 0; itr < 4; ++itr) {
+                    const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
+                    const uint32_t sub_e = e8 >> nbr;
+                    uint32_t so = ts, co = tc;
+#pragma unroll
+                    for (int b = 11; b < 13; ++b) {
+                        const uint32_t bit = ((uint32_t)itr >> (b - 11)) & 1u;
+                        if (b < nbr) {
+                            so |= bit << ti.e_spos[b];
+                            co |= bit << ti.e_cs[b];
+                        }
+                    }
+                    const long long cb = ti.cbase[sub_e];
+                    if (cb >= 0) {
+                        so |= sub_e << nbr;
+                        T v[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
+                            v[q] = buf[stg_swz_h(so | dq)];
+                        }
+                        T* dst = Cb + cb + roff + co;
+                        if (evec) {
+                            uint4 o;
+                            o.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+                            o.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+                            o.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+                            o.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+                            *reinterpret_cast<uint4*>(dst) = o;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const uint32_t dq = ((q & 1) << ti.e_cs[0]) | (((q >> 1) & 1) << ti.e_cs[1]) | (((q >> 2) & 1) << ti.e_cs[2]);
+                                dst[dq] = v[q];
+                            }
+                        }
+                    }
+                }
             }
         }
         __syncwarp();

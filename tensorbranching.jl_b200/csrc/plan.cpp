@@ -212,10 +212,32 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             default: return ((const double*)net.weights)[v];
         }
     };
-    if (vt == TB_VALUE_AUTO) vt = (wd == TB_WEIGHT_F32 || wd == TB_WEIGHT_F64) ? TB_VALUE_F32 : TB_VALUE_I32;
-    if (vt == TB_VALUE_I16X2) return fail(TB_ERR_UNSUPPORTED, "value type i16x2 is reserved (not implemented)");
-    if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32) return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
+    const bool int_weights = !(wd == TB_WEIGHT_F32 || wd == TB_WEIGHT_F64);
+    bool auto_i16 = false;
+    if (vt == TB_VALUE_AUTO) {
+        vt = int_weights ? TB_VALUE_I32 : TB_VALUE_F32;
+        auto_i16 = int_weights && (P.flags & TB_PLAN_PREFER_I16);  // downgraded below if the weights do not fit
+    }
+    if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32 && vt != TB_VALUE_I16X2) return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
+    if (vt == TB_VALUE_I16X2 || auto_i16) {
+        // packed int16 needs every partial sum < 2^13: check sum |w| over the vertex leaves
+        double sum_abs = 0;
+        bool integral = true;
+        for (int i = 0; i < net.n_leaves; ++i)
+            if (lab_n[i] == 1) {
+                double w = weight_of(labp(i)[0]);
+                integral = integral && (w == std::floor(w));
+                sum_abs += std::fabs(w);
+            }
+        const bool fits = integral && sum_abs < 8192.0;
+        if (vt == TB_VALUE_I16X2 && !fits) return fail(TB_ERR_UNSUPPORTED, "value type i16x2 needs integer weights with sum |w| < 8192");
+        if (auto_i16 && fits) vt = TB_VALUE_I16X2;
+    }
     P.value_type = vt;
+    const bool half = (vt == TB_VALUE_I16X2);
+    const int TILE_M_MAX = half ? GEMM_TILE_MAX_M16 : GEMM_TILE_MAX;  // tile bits of the M side
+    const int MT_LOG = half ? 4 : 3;                                   // log2 of a thread's microtile extent in m
+    const int STAGE_ELEMS = GEMM_STAGE_ELEMS * (half ? 2 : 1);
 
     // ---- leaf positions (DFS order) and subtree ranges
     std::vector<int32_t> lo(nT0, 0), hi(nT0, 0);
@@ -321,8 +343,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 if (stA[l] != stamp) (stC[l] == stamp ? nn : nkb)++;
             }
             const int rc = lab_n[t];
-            const bool gemm_like = !(P.flags & TB_PLAN_NO_GEMM) && nm >= 3 && nn >= 3 &&
-                                   std::min(nm, GEMM_TILE_MAX) + std::min(nn, GEMM_TILE_MAX) >= 9 && nk >= 1 && nka == 0 &&
+            const int gm = half ? std::max(nm, nn) : nm, gn = half ? std::min(nm, nn) : nn;  // i16 puts the larger side on M
+            const bool gemm_like = !(P.flags & TB_PLAN_NO_GEMM) && gm >= MT_LOG && gn >= 3 &&
+                                   std::min(gm, TILE_M_MAX) + std::min(gn, GEMM_TILE_MAX) >= MT_LOG + 6 && nk >= 1 && nka == 0 &&
                                    nkb == 0 && !leaf[A] && !leaf[B];
             int serial_log, limit;
             if (gemm_like) {
@@ -414,7 +437,27 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         std::vector<int32_t> secA(NLAB, -1), secB(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
         const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
         for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
-            const int t = *it, A = lch[t], B = rch[t];
+            const int t = *it;
+            if (half && !leaf[lch[t]] && !leaf[rch[t]]) {
+                // packed int16 tiles are 16 (m) x 8 (n) per thread: contract(A, B) == contract(B, A), so make the
+                // operand with more output-only labels the M side
+                const int sQ = ++stamp;
+                const int32_t* lcq = P.lay_data.data() + P.lay_off[t];
+                for (int i = 0; i < P.lay_n[t]; ++i) stC[lcq[i]] = sQ;
+                for (int q = 0; q < lab_n[rch[t]]; ++q) stB[labp(rch[t])[q]] = sQ;
+                int ca = 0, cb = 0;
+                for (int q = 0; q < lab_n[lch[t]]; ++q) {
+                    const int32_t l = labp(lch[t])[q];
+                    stA[l] = sQ;
+                    if (stB[l] != sQ && stC[l] == sQ) ++ca;
+                }
+                for (int q = 0; q < lab_n[rch[t]]; ++q) {
+                    const int32_t l = labp(rch[t])[q];
+                    if (stA[l] != sQ && stC[l] == sQ) ++cb;
+                }
+                if (cb > ca) std::swap(lch[t], rch[t]);
+            }
+            const int A = lch[t], B = rch[t];
             const int sN = ++stamp;  // stamp of this node (stA, stB, batA, batB)
             const int32_t* lc = P.lay_data.data() + P.lay_off[t];
             const int rc = P.lay_n[t];
@@ -486,7 +529,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             c.nk = (uint8_t)nk;
             c.nka = (uint8_t)nka;
             c.nkb = (uint8_t)nkb;
-            c.tm = (uint8_t)std::min(nm, GEMM_TILE_MAX);
+            c.tm = (uint8_t)std::min(nm, TILE_M_MAX);
             c.tn = (uint8_t)std::min(nn, GEMM_TILE_MAX);
             {
                 const size_t o0 = cls_data.size();
@@ -534,8 +577,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     {
         auto push_val = [&](double x, bool neg_inf) {
             uint32_t bits;
-            if (vt == TB_VALUE_I32) {
-                int32_t v = neg_inf ? Tropical<int32_t>::kNegInf : (int32_t)x;
+            if (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2) {
+                int32_t v = neg_inf ? (half ? Tropical<int16_t>::kNegInf : Tropical<int32_t>::kNegInf) : (int32_t)x;
                 std::memcpy(&bits, &v, 4);
             } else {
                 float v = neg_inf ? -std::numeric_limits<float>::infinity() : (float)x;
@@ -557,8 +600,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             } else {
                 double w = weight_of(labp(i)[0]);
                 if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
-                if (vt == TB_VALUE_I32) {
-                    if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "value type i32 needs integer weights");
+                if (vt != TB_VALUE_F32) {
+                    if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
                     sum_abs += std::fabs(w);
                     if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
                 }
@@ -612,8 +655,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 if (!leaf[c]) lv = std::max(lv, P.level[c] + 1);
             P.level[t] = lv;
             const NodeCls& c = cls[t];
-            bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= 3 && c.nn >= 3 && c.tm + c.tn >= 9 && c.nk >= 1 && c.nka == 0 &&
-                        c.nkb == 0 && !leaf[lch[t]] && !leaf[rch[t]];
+            bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= MT_LOG && c.nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && c.nk >= 1 &&
+                        c.nka == 0 && c.nkb == 0 && !leaf[lch[t]] && !leaf[rch[t]];
             kind[t] = gemm ? KIND_GEMM : KIND_GENERIC;
             P.n_levels = std::max(P.n_levels, lv);
             ++n_big;
@@ -673,13 +716,14 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         const NodeCls& c = cls[t];
         auto p2 = [](int e) { return (double)(1ull << e); };
         int tc = rank_of(t) + c.nk + c.nka + c.nkb;
+        const double eb = half ? 2.0 : 4.0;
         if (unary[t]) {  // second half of a split node: engine overhead, not algorithmic work
-            bytes += 4.0 * p2(rank_of(t));
+            bytes += eb * p2(rank_of(t));
             return;
         }
         (knd == KIND_FUSED ? ops_f : knd == KIND_GENERIC ? ops_g : ops_m) += p2(tc);
         double cb = (t >= nT0) ? 0.0 : p2(rank_of(t));  // a partial node's output is not algorithmic traffic
-        bytes += 4.0 * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + cb);
+        bytes += eb * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + cb);
     };
     P.recs.reserve(topo.size());
     P.sub_steps.reserve(topo.size() - n_big);
@@ -839,11 +883,11 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 s.n_mhi = (uint8_t)(c.nm - c.tm);
                 s.n_nhi = (uint8_t)(c.nn - c.tn);
                 s.ng = (uint8_t)(s.rc - c.tm - c.tn);
-                int tps_log = (c.tm - 3) + (c.tn - 3);  // threads per sub-tile
-                int s_log = 8 - tps_log;                // sub-tiles per CTA (256 threads)
+                int tps_log = (c.tm - MT_LOG) + (c.tn - 3);  // threads per sub-tile
+                int s_log = 8 - tps_log;                     // sub-tiles per CTA (256 threads)
                 int64_t per_k = ((int64_t)1 << s_log) * (((int64_t)1 << c.tm) + ((int64_t)1 << c.tn));
                 int kc = 0;
-                while (kc + 1 <= s.nk && (per_k << (kc + 1)) <= GEMM_STAGE_ELEMS) ++kc;
+                while (kc + 1 <= s.nk && (per_k << (kc + 1)) <= STAGE_ELEMS) ++kc;
                 s.kc = (uint8_t)kc;
                 int64_t groups = (int64_t)1 << s.ng;
                 int64_t S = (int64_t)1 << s_log;
@@ -869,7 +913,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                     for (int i = 0; i < nbr; ++i) { s.a_shift[i] = (uint8_t)ent_sp[i]; s.b_shift[i] = (uint8_t)ent_cs[i]; }
                     s.a_shift[30] = s.c_shift[c.tm - 1];
                     s.a_shift[31] = s.c_shift[c.tm + c.tn - 1];
-                    s.b_shift[31] = (ent_cs[0] == 0 && ent_cs[1] == 1) ? 1 : 0;
+                    s.b_shift[31] = half ? ((ent_cs[0] == 0 && ent_cs[1] == 1 && ent_cs[2] == 2) ? 1 : 0)
+                                         : ((ent_cs[0] == 0 && ent_cs[1] == 1) ? 1 : 0);
                 }
                 // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
                 // (bit 0 if stores are scalar) on the low lane bits
@@ -942,16 +987,29 @@ tb_step_info Plan::step_info(size_t i) const {
     return s;
 }
 
+void Plan::write_pool(uint8_t* dst) const {
+    if (elem_size() == 4) {
+        if (!pool.empty()) std::memcpy(dst, pool.data(), pool.size() * 4);
+    } else {
+        int16_t* d = reinterpret_cast<int16_t*>(dst);
+        for (size_t i = 0; i < pool.size(); ++i) {
+            int32_t v;
+            std::memcpy(&v, &pool[i], 4);
+            d[i] = (int16_t)v;
+        }
+    }
+}
+
 void build_blob(Plan& P, std::vector<uint8_t>& blob) {
     auto a16 = [](size_t x) { return (x + 15) / 16 * 16; };
-    size_t pool_b = a16(P.pool.size() * 4);
+    size_t pool_b = a16(P.pool_bytes());
     size_t sub_b = a16(P.sub_steps.size() * sizeof(SubStep));
     size_t big_b = a16(P.big_steps.size() * sizeof(BigStep));
     P.sub_blob_off = pool_b;
     P.big_blob_off = pool_b + sub_b;
     P.blob_bytes = pool_b + sub_b + big_b;
     blob.assign(P.blob_bytes, 0);
-    if (!P.pool.empty()) std::memcpy(blob.data(), P.pool.data(), P.pool.size() * 4);
+    P.write_pool(blob.data());
     if (!P.sub_steps.empty()) std::memcpy(blob.data() + P.sub_blob_off, P.sub_steps.data(), P.sub_steps.size() * sizeof(SubStep));
     if (!P.big_steps.empty()) std::memcpy(blob.data() + P.big_blob_off, P.big_steps.data(), P.big_steps.size() * sizeof(BigStep));
 }

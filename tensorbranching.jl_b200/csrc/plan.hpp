@@ -30,7 +30,10 @@ struct Plan {
     std::vector<int32_t> level;                // -1 for leaves / interior of fused subtrees
 
     // descriptors
-    std::vector<uint32_t> pool;  // raw 32-bit values (int32 or float bits)
+    std::vector<uint32_t> pool;  // one 32-bit slot per pool element (int32 / float bits); narrowed to int16 on upload
+    int elem_size() const { return value_type == TB_VALUE_I16X2 ? 2 : 4; }
+    size_t pool_bytes() const { return pool.size() * (size_t)elem_size(); }
+    void write_pool(uint8_t* dst) const;  // device representation of the pool
     std::vector<SubStep> sub_steps;
     std::vector<SubTree> subtrees;
     std::vector<BigStep> big_steps;        // sorted by level (levels start at 1)

@@ -13,6 +13,7 @@ NO_BIT = 0xFF
 LOC_ARENA, LOC_POOL, LOC_SMEM = 0, 1, 2
 KIND_GENERIC, KIND_GEMM = 1, 2
 NEG_I32 = -(1 << 30)
+NEG_I16 = -(1 << 14)
 
 SUBSTEP = np.dtype([("a_off", "<u2"), ("b_off", "<u2"), ("c_off", "<u2"), ("a_loc", "u1"), ("b_loc", "u1"),
                     ("c_loc", "u1"), ("rc", "u1"), ("nk", "u1"), ("nka", "u1"), ("nkb", "u1"), ("sa", "u1"),
@@ -67,19 +68,23 @@ def run_plan(plan):
     """plan: tbcuda.Plan.  Returns (root value as float, arena array, dict of stats)."""
     hdr = np.frombuffer(plan.raw(5), dtype="<i8")
     arena_elems, root_off, n_levels, vt = (int(x) for x in hdr)
-    dt = np.int64 if vt == 1 else np.float32
-    neg = NEG_I32 if vt == 1 else -np.inf
-    praw = np.frombuffer(plan.raw(0), dtype="<u4")
-    pool = praw.view("<i4").astype(np.int64) if vt == 1 else praw.view("<f4").copy()
+    dt = np.int64 if vt in (1, 3) else np.float32
+    neg = NEG_I32 if vt == 1 else NEG_I16 if vt == 3 else -np.inf
+    if vt == 3:
+        pool = np.frombuffer(plan.raw(0), dtype="<i2").astype(np.int64)
+    else:
+        praw = np.frombuffer(plan.raw(0), dtype="<u4")
+        pool = praw.view("<i4").astype(np.int64) if vt == 1 else praw.view("<f4").copy()
+    mt = 4 if vt == 3 else 3  # log2 of a thread's microtile extent in m
     sub = np.frombuffer(plan.raw(1), dtype=SUBSTEP)
     trees = np.frombuffer(plan.raw(2), dtype=SUBTREE)
     big = np.frombuffer(plan.raw(3), dtype=BIGSTEP)
     lvl = np.frombuffer(plan.raw(4), dtype="<i4")
-    arena = np.full(max(arena_elems, 1), 12345 if vt == 1 else np.nan, dtype=dt)
+    arena = np.full(max(arena_elems, 1), 12345 if vt in (1, 3) else np.nan, dtype=dt)
 
     with np.errstate(invalid="ignore"):
         for t in trees:
-            smem = np.full(max(int(t["smem_elems"]), 1), 777 if vt == 1 else np.nan, dtype=dt)
+            smem = np.full(max(int(t["smem_elems"]), 1), 777 if vt in (1, 3) else np.nan, dtype=dt)
             for s in sub[int(t["first_step"]): int(t["first_step"]) + int(t["n_steps"])]:
                 A = (smem if s["a_loc"] == LOC_SMEM else pool)[int(s["a_off"]):]
                 B = (smem if s["b_loc"] == LOC_SMEM else pool)[int(s["b_off"]):]
@@ -128,9 +133,10 @@ def run_plan(plan):
                     assert int(s["nka"]) == 0 and int(s["nkb"]) == 0 and tm + tn + ng == rc
                     moff = scatter(np.arange(1 << tm, dtype=np.int64), s["c_shift"], tm)
                     noff = scatter(np.arange(1 << tn, dtype=np.int64), s["c_shift"][tm:], tn)
-                    S = 1 << (8 - (tm + tn - 6))
+                    S = 1 << (8 - (tm - mt + tn - 3))
+                    assert 1 <= S <= 32 and tm >= mt and tn >= 3 and tm <= (8 if vt == 3 else 7) and tn <= 7
                     assert int(s["n_tiles"]) == ((1 << ng) + S - 1) // S
-                    assert S * (1 << int(s["kc"])) * ((1 << tm) + (1 << tn)) <= 4096 and int(s["kc"]) <= nk
+                    assert S * (1 << int(s["kc"])) * ((1 << tm) + (1 << tn)) <= 4096 * (2 if vt == 3 else 1) and int(s["kc"]) <= nk
                     if s["store_mode"] == 1:
                         assert s["c_shift"][0] == 0 and s["c_shift"][1] == 1
                     if s["store_mode"] == 2:
@@ -142,7 +148,10 @@ def run_plan(plan):
                     assert [int(x) for x in s["b_shift"][:nbr]] == [e[0] for e in ent]
                     assert [int(x) for x in s["a_shift"][:nbr]] == [e[1] for e in ent]
                     assert int(s["a_shift"][30]) == int(s["c_shift"][tm - 1]) and int(s["a_shift"][31]) == int(s["c_shift"][tm + tn - 1])
-                    assert int(s["b_shift"][31]) == int(ent[0][0] == 0 and ent[1][0] == 1)
+                    if vt == 3:
+                        assert int(s["b_shift"][31]) == int([e[0] for e in ent[:3]] == [0, 1, 2])
+                    else:
+                        assert int(s["b_shift"][31]) == int(ent[0][0] == 0 and ent[1][0] == 1)
                     idxs, vals = [], []
                     for g in range(1 << ng):
                         gm = g & ((1 << n_mhi) - 1)
@@ -165,7 +174,9 @@ def run_plan(plan):
             for off, idx, vals in pending:
                 arena[off + idx] = vals
     root = arena[root_off]
-    if vt == 1:
+    if vt == 3:
+        rootf = -np.inf if root <= -(1 << 13) else float(root)
+    elif vt == 1:
         rootf = -np.inf if root <= -(1 << 29) else float(root)
     else:
         rootf = float(root)
@@ -173,8 +184,8 @@ def run_plan(plan):
 
 
 def to_float(arr, vt):
-    if vt == 1:
+    if vt in (1, 3):
         out = arr.astype(np.float64)
-        out[arr <= -(1 << 29)] = -np.inf
+        out[arr <= (-(1 << 29) if vt == 1 else -(1 << 13))] = -np.inf
         return out
     return arr.astype(np.float64)

@@ -9,7 +9,7 @@ from workloads import standin_host as H
 
 pytestmark = pytest.mark.gpu
 
-FLAGS = [0, 2, 4, 8, 16, 2 | 8, 2 | 4, 4 | 16]
+FLAGS = [0, 2, 4, 8, 16, 2 | 8, 2 | 4, 4 | 16, 32, 32 | 8, 32 | 2, 32 | 4, 32 | 16]
 
 
 @pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
@@ -50,7 +50,7 @@ def test_float64_weights_with_float32_element_type(tb, engine):
     assert got == O.solve_slice(root, np.float32) == O.exact_mis_milp(nv, edges)
 
 
-@pytest.mark.parametrize("flags", [1, 1 | 8, 1 | 4])
+@pytest.mark.parametrize("flags", [1, 1 | 8, 1 | 4, 1 | 32, 1 | 32 | 8])
 def test_every_node_bit_exact(tb, engine, flags):
     """node-by-node: every intermediate tensor equals the oracle's (SURVEY 8c oracle plan (1))."""
     root = regular_root(70, 8)
@@ -128,6 +128,43 @@ def test_split_k_and_every_node_large(tb, engine, n, seed):
     assert all(v == want for v in vals.values()), (vals, want)
     p = tb.Plan(to_sliced(root), flags=0, engine=engine)
     assert any(s.node >= 2 * len(root.ixs) - 1 for s in p.steps())  # split-K really happened
+
+
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr30_disconnected", "ksg8x8_sc6"])
+def test_contract_slices_packed_int16(tb, name):
+    """K2: the packed int16x2 value type (plan flag PREFER_I16) returns the same per-branch vector."""
+    rec = load_golden(name + ".json")
+    brs = golden_branches(rec)
+    eng = tb.Engine(0, plan_flags=tb.TB_PLAN_PREFER_I16)
+    got = tb.contract_slices([to_sliced(b) for b in brs], np.float32, True, engine=eng)
+    assert np.array_equal(got.astype(np.float64), np.asarray(rec["values"]))
+    p = tb.Plan(to_sliced(brs[0]), engine=eng)
+    assert p.info().value_type == 3
+    eng.close()
+
+
+@pytest.mark.parametrize("n,seed", [(130, 5), (150, 1000)])
+def test_packed_int16_large(tb, n, seed):
+    from oracle import c_oracle as CO
+    root = regular_root(n, seed)
+    want = CO.contract_slices([root], np.float32)[0]
+    eng = tb.Engine(0, plan_flags=tb.TB_PLAN_PREFER_I16)
+    for flags in (0, 8, 16):
+        p = tb.Plan(to_sliced(root), flags=flags, engine=eng)
+        st = p.info()
+        assert st.value_type == 3 and st.n_gemm_steps > 0
+        assert eng.contract(p) == want
+        p.close()
+    eng.close()
+
+
+def test_int16_falls_back_when_weights_do_not_fit(tb, engine):
+    nv, edges = H.random_regular_graph(40, 3, 2)
+    w = np.full(nv, 1000, dtype=np.int64)  # sum |w| = 40000 >= 8192 -> int32
+    root = H.make_root(nv, edges, weights=w, seed=2)
+    p = tb.Plan(to_sliced(root), flags=tb.TB_PLAN_PREFER_I16, engine=engine)
+    assert p.info().value_type == 1
+    assert engine.contract(p) == O.exact_mis_milp(nv, edges, w)
 
 
 def test_gemm_v1_kernel_agrees(tb):

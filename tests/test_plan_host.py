@@ -40,7 +40,7 @@ def test_usecuda_false_is_refused(tb):
         tb.contract_slices([to_sliced(root)], np.float32, False)
 
 
-FLAGS = [0, 2, 4, 8, 16, 2 | 8, 4 | 8]
+FLAGS = [0, 2, 4, 8, 16, 2 | 8, 4 | 8, 32, 32 | 8, 32 | 2, 32 | 16]
 
 
 @pytest.mark.parametrize("n,seed", [(12, 1), (30, 3), (60, 5), (100, 7)])
@@ -76,14 +76,16 @@ def test_plan_every_node_matches_oracle(tb):
     root = regular_root(40, 8)
     left, right = O.nested_to_postorder(root.tree, len(root.ixs))
     _, _, inter = O.contract_tree(root.ixs, left, right, None, np.float64, keep_intermediates=True)
-    for flags in (1, 1 | 8):
+    for flags in (1, 1 | 8, 1 | 32):
         p = tb.Plan(to_sliced(root), flags=flags)
+        vt = p.info().value_type
+        assert vt == (3 if flags & 32 else 1)
         _, arena = DI.run_plan(p)
         for s in p.steps():
             if s.node not in inter:
                 continue
             labels = [s.labels_c[i] for i in range(s.rank_c)]
-            data = DI.to_float(arena[s.c_offset:s.c_offset + (1 << s.rank_c)], 1)
+            data = DI.to_float(arena[s.c_offset:s.c_offset + (1 << s.rank_c)], vt)
             dl, darr = device_tensor_as_ndarray(labels, data)
             ol, oarr = inter[s.node]
             assert sorted(dl) == sorted(ol)
