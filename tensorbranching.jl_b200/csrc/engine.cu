@@ -609,6 +609,16 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             ctx->prof_ms[launches[li].kind] += pm;
             ctx->prof_launches[launches[li].kind] += 1;
         }
+        if (const char* dump = getenv("TB_DUMP_LAUNCHES")) {  // per-launch records of the profiling pass (diagnostics)
+            if (FILE* f = fopen(dump, "a")) {
+                for (size_t li = 0; li < launches.size(); ++li) {
+                    float pm = 0;
+                    cudaEventElapsedTime(&pm, ctx->prof_events[li], ctx->prof_events[li + 1]);
+                    fprintf(f, "%d,%d,%d,%u,%.4f\n", vt, launches[li].kind, launches[li].n_insts, launches[li].grid, pm);
+                }
+                fclose(f);
+            }
+        }
     }
     return TB_OK;
 }
