@@ -67,8 +67,8 @@ def test_every_node_bit_exact(tb, engine, flags):
         ol, oarr = inter[s.node]
         assert np.array_equal(align_to(dl, darr, ol), oarr), f"node {s.node} kind {s.kind}"
         kinds.add(s.kind)
-    if not flags & 4:
-        assert 2 in kinds  # the tiled GEMM kernel was exercised
+    if not flags & (4 | 32):
+        assert 2 in kinds  # the tiled GEMM kernel was exercised (the packed-int16 tile needs larger nodes)
 
 
 def test_every_node_bit_exact_f32(tb, engine):
