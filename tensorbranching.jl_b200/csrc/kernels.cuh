@@ -621,8 +621,18 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 }
             }
             const uint32_t ds1 = 1u << ti.e_spos[0], ds2 = 1u << ti.e_spos[1];
-            const uint32_t dc1 = 1u << ti.e_cs[0], dc2 = 1u << ti.e_cs[1];
             const bool evec = ti.e_vec != 0;
+            uint32_t ts1 = 0, tc1 = 0;  // element-granular mapping (fallback): element bits 0..7 come from the thread id
+            if (!evec) {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t bit = ((uint32_t)ctid >> b) & 1u;
+                    if (b < nbr) {
+                        ts1 |= bit << ti.e_spos[b];
+                        tc1 |= bit << ti.e_cs[b];
+                    }
+                }
+            }
             T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -639,35 +649,49 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
+                if (evec) {
 #pragma unroll
-                for (int itr = 0; itr < 4; ++itr) {
-                    const uint32_t e4 = ((uint32_t)itr << 10) | ((uint32_t)ctid << 2);
-                    const uint32_t sub_e = e4 >> nbr;
-                    uint32_t so = ts, co = tc;
+                    for (int itr = 0; itr < 4; ++itr) {
+                        const uint32_t e4 = ((uint32_t)itr << 10) | ((uint32_t)ctid << 2);
+                        const uint32_t sub_e = e4 >> nbr;
+                        uint32_t so = ts, co = tc;
 #pragma unroll
-                    for (int b = 10; b < 12; ++b) {
-                        const uint32_t bit = ((uint32_t)itr >> (b - 10)) & 1u;
-                        if (b < nbr) {
-                            so |= bit << ti.e_spos[b];
-                            co |= bit << ti.e_cs[b];
+                        for (int b = 10; b < 12; ++b) {
+                            const uint32_t bit = ((uint32_t)itr >> (b - 10)) & 1u;
+                            if (b < nbr) {
+                                so |= bit << ti.e_spos[b];
+                                co |= bit << ti.e_cs[b];
+                            }
+                        }
+                        const long long cb = ti.cbase[sub_e];
+                        if (cb >= 0) {
+                            so |= sub_e << nbr;
+                            vec4 o;
+                            o.x = buf[stg_swz(so)];
+                            o.y = buf[stg_swz(so | ds1)];
+                            o.z = buf[stg_swz(so | ds2)];
+                            o.w = buf[stg_swz(so | ds1 | ds2)];
+                            *reinterpret_cast<vec4*>(Cb + cb + roff + co) = o;
                         }
                     }
-                    const long long cb = ti.cbase[sub_e];
-                    if (cb >= 0) {
-                        so |= sub_e << nbr;
-                        const T v0 = buf[stg_swz(so)], v1 = buf[stg_swz(so | ds1)], v2 = buf[stg_swz(so | ds2)],
-                                v3 = buf[stg_swz(so | ds1 | ds2)];
-                        T* dst = Cb + cb + roff + co;
-                        if (evec) {
-                            vec4 o;
-                            o.x = v0; o.y = v1; o.z = v2; o.w = v3;
-                            *reinterpret_cast<vec4*>(dst) = o;
-                        } else {
-                            dst[0] = v0;
-                            dst[dc1] = v1;
-                            dst[dc2] = v2;
-                            dst[dc1 + dc2] = v3;
+                } else {
+                    // C bits 0,1 are not both tile bits: consecutive LANES take consecutive tile elements in C order,
+                    // so a warp still writes the densest address set this layout allows
+#pragma unroll 4
+                    for (int itr = 0; itr < 16; ++itr) {
+                        const uint32_t e1 = ((uint32_t)itr << 8) | (uint32_t)ctid;
+                        const uint32_t sub_e = e1 >> nbr;
+                        uint32_t so = ts1, co = tc1;
+#pragma unroll
+                        for (int b = 8; b < 12; ++b) {
+                            const uint32_t bit = ((uint32_t)itr >> (b - 8)) & 1u;
+                            if (b < nbr) {
+                                so |= bit << ti.e_spos[b];
+                                co |= bit << ti.e_cs[b];
+                            }
                         }
+                        const long long cb = ti.cbase[sub_e];
+                        if (cb >= 0) Cb[cb + roff + co] = buf[stg_swz(so | (sub_e << nbr))];
                     }
                 }
             }
@@ -907,6 +931,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 }
             }
             const bool evec = ti.e_vec != 0;
+            uint32_t ts1 = 0, tc1 = 0;
+            if (!evec) {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const uint32_t bit = ((uint32_t)ctid >> b) & 1u;
+                    if (b < nbr) {
+                        ts1 |= bit << ti.e_spos[b];
+                        tc1 |= bit << ti.e_cs[b];
+                    }
+                }
+            }
             T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
@@ -923,43 +958,53 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
+                if (evec) {
 #pragma unroll
-                for (int itr = 0; itr < 4; ++itr) {
-                    const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
-                    const uint32_t sub_e = e8 >> nbr;
-                    uint32_t so = ts, co = tc;
+                    for (int itr = 0; itr < 4; ++itr) {
+                        const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
+                        const uint32_t sub_e = e8 >> nbr;
+                        uint32_t so = ts, co = tc;
 #pragma unroll
-                    for (int b = 11; b < 13; ++b) {
-                        const uint32_t bit = ((uint32_t)itr >> (b - 11)) & 1u;
-                        if (b < nbr) {
-                            so |= bit << ti.e_spos[b];
-                            co |= bit << ti.e_cs[b];
+                        for (int b = 11; b < 13; ++b) {
+                            const uint32_t bit = ((uint32_t)itr >> (b - 11)) & 1u;
+                            if (b < nbr) {
+                                so |= bit << ti.e_spos[b];
+                                co |= bit << ti.e_cs[b];
+                            }
                         }
-                    }
-                    const long long cb = ti.cbase[sub_e];
-                    if (cb >= 0) {
-                        so |= sub_e << nbr;
-                        T v[8];
+                        const long long cb = ti.cbase[sub_e];
+                        if (cb >= 0) {
+                            so |= sub_e << nbr;
+                            T v[8];
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
-                            v[q] = buf[stg_swz_h(so | dq)];
-                        }
-                        T* dst = Cb + cb + roff + co;
-                        if (evec) {
+                            for (int q = 0; q < 8; ++q) {
+                                const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
+                                v[q] = buf[stg_swz_h(so | dq)];
+                            }
                             uint4 o;
                             o.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
                             o.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
                             o.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
                             o.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
-                            *reinterpret_cast<uint4*>(dst) = o;
-                        } else {
+                            *reinterpret_cast<uint4*>(Cb + cb + roff + co) = o;
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int itr = 0; itr < 32; ++itr) {
+                        const uint32_t e1 = ((uint32_t)itr << 8) | (uint32_t)ctid;
+                        const uint32_t sub_e = e1 >> nbr;
+                        uint32_t so = ts1, co = tc1;
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const uint32_t dq = ((q & 1) << ti.e_cs[0]) | (((q >> 1) & 1) << ti.e_cs[1]) | (((q >> 2) & 1) << ti.e_cs[2]);
-                                dst[dq] = v[q];
+                        for (int b = 8; b < 13; ++b) {
+                            const uint32_t bit = ((uint32_t)itr >> (b - 8)) & 1u;
+                            if (b < nbr) {
+                                so |= bit << ti.e_spos[b];
+                                co |= bit << ti.e_cs[b];
                             }
                         }
+                        const long long cb = ti.cbase[sub_e];
+                        if (cb >= 0) Cb[cb + roff + co] = buf[stg_swz_h(so | (sub_e << nbr))];
                     }
                 }
             }

@@ -506,8 +506,26 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                     key[v[i]] = (bat[v[i]] == sN ? 2048 : (sec[v[i]] == sN ? k_sec : k_first)) + posC[v[i]];
                 sort_by_key(v, key.data(), n);
             };
-            class_key(M, nm, batA, secA);
-            class_key(N, nn, batB, secB);
+            // tile set = the labels with the LOWEST positions in C (this node's own stores are enumerated in C order);
+            // inside the tile set the order follows the child's classes (the child's stores), except that the label
+            // with the highest C position goes last: it selects the epilogue round, so it must not be a low C bit
+            auto order_side = [&](int32_t* v, int n, int tmax, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
+                for (int i = 0; i < n; ++i) key[v[i]] = posC[v[i]];
+                sort_by_key(v, key.data(), n);
+                const int tl = std::min(n, tmax);
+                class_key(v, tl, bat, sec);
+                if (tl >= 2) {
+                    int top = 0;
+                    for (int i = 1; i < tl; ++i)
+                        if (posC[v[i]] > posC[v[top]]) top = i;
+                    const int32_t lt = v[top];
+                    for (int i = top; i + 1 < tl; ++i) v[i] = v[i + 1];
+                    v[tl - 1] = lt;
+                }
+                if (n > tl) class_key(v + tl, n - tl, bat, sec);
+            };
+            order_side(M, nm, TILE_M_MAX, batA, secA);
+            order_side(N, nn, GEMM_TILE_MAX, batB, secB);
             for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
             sort_by_key(Bt, key.data(), nb);
             for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
