@@ -406,7 +406,7 @@ struct TileInfo {
     int tm, tn, kc, nchunks, store_mode, valid, lane_n_first;
     unsigned char c_shift[16];
     unsigned char e_spos[12], e_cs[12];  // staged epilogue: sorted in-round tile bits -> staging position / C shift
-    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_pad;
+    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast;
 };
 
 // bank swizzle of the epilogue staging index: permutes 16-byte chunks inside a 128-byte row
@@ -536,6 +536,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 ti.e_cs_mtop = d->a_shift[30];
                 ti.e_cs_ntop = d->a_shift[31];
                 ti.e_vec = d->b_shift[31];
+                ti.e_fast = d->b_shift[30];
                 ti.valid = 1;
             }
             __syncwarp();
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 }
             }
             const uint32_t ds1 = 1u << ti.e_spos[0], ds2 = 1u << ti.e_spos[1];
-            const bool evec = ti.e_vec != 0;
+            const bool evec = ti.e_vec != 0, efast = ti.e_fast != 0;
             uint32_t ts1 = 0, tc1 = 0;  // element-granular mapping (fallback): element bits 0..7 come from the thread id
             if (!evec) {
 #pragma unroll
@@ -667,10 +668,14 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                         if (cb >= 0) {
                             so |= sub_e << nbr;
                             vec4 o;
-                            o.x = buf[stg_swz(so)];
-                            o.y = buf[stg_swz(so | ds1)];
-                            o.z = buf[stg_swz(so | ds2)];
-                            o.w = buf[stg_swz(so | ds1 | ds2)];
+                            if (efast) {
+                                o = *reinterpret_cast<const vec4*>(buf + stg_swz(so));
+                            } else {
+                                o.x = buf[stg_swz(so)];
+                                o.y = buf[stg_swz(so | ds1)];
+                                o.z = buf[stg_swz(so | ds2)];
+                                o.w = buf[stg_swz(so | ds1 | ds2)];
+                            }
                             *reinterpret_cast<vec4*>(Cb + cb + roff + co) = o;
                         }
                     }
@@ -759,7 +764,7 @@ struct TileInfoH {
     void* C;
     int tm, tn, kc, nchunks, valid, lane_n_first;
     unsigned char e_spos[14], e_cs[14];
-    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_pad;
+    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast;
 };
 __device__ __forceinline__ uint32_t stg_swz_h(uint32_t x) { return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7u) << 3); }
 
@@ -841,6 +846,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 ti.e_cs_mtop = d->a_shift[30];
                 ti.e_cs_ntop = d->a_shift[31];
                 ti.e_vec = d->b_shift[31];
+                ti.e_fast = d->b_shift[30];
                 ti.valid = 1;
             }
             __syncwarp();
@@ -930,7 +936,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     tc |= bit << ti.e_cs[b];
                 }
             }
-            const bool evec = ti.e_vec != 0;
+            const bool evec = ti.e_vec != 0, efast = ti.e_fast != 0;
             uint32_t ts1 = 0, tc1 = 0;
             if (!evec) {
 #pragma unroll
@@ -975,17 +981,21 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                         const long long cb = ti.cbase[sub_e];
                         if (cb >= 0) {
                             so |= sub_e << nbr;
-                            T v[8];
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
-                                v[q] = buf[stg_swz_h(so | dq)];
-                            }
                             uint4 o;
-                            o.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
-                            o.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
-                            o.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
-                            o.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+                            if (efast) {
+                                o = *reinterpret_cast<const uint4*>(buf + stg_swz_h(so));
+                            } else {
+                                T v[8];
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) {
+                                    const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
+                                    v[q] = buf[stg_swz_h(so | dq)];
+                                }
+                                o.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+                                o.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+                                o.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+                                o.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+                            }
                             *reinterpret_cast<uint4*>(Cb + cb + roff + co) = o;
                         }
                     }

@@ -457,6 +457,30 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 }
                 if (cb > ca) std::swap(lch[t], rch[t]);
             }
+            if (P.lay_n[t] > 0 && !leaf[lch[t]] && !leaf[rch[t]]) {
+                // orientation: the operand that owns the label at C bit 0 becomes the M side (contract(A,B) == contract(B,A)),
+                // so that the low output bits are m tile bits 0,1,.. and the epilogue can move whole 16-byte vectors
+                const int32_t l0 = P.lay_data[P.lay_off[t]];
+                bool inL = false, inR = false;
+                for (int q = 0; q < lab_n[lch[t]]; ++q) inL = inL || labp(lch[t])[q] == l0;
+                for (int q = 0; q < lab_n[rch[t]]; ++q) inR = inR || labp(rch[t])[q] == l0;
+                if (inR && !inL) {
+                    bool ok = true;
+                    if (half) {  // keep at least 4 output-only labels on the M side of a packed-int16 tile
+                        const int sQ = ++stamp;
+                        const int32_t* lcq = P.lay_data.data() + P.lay_off[t];
+                        for (int i = 0; i < P.lay_n[t]; ++i) stC[lcq[i]] = sQ;
+                        for (int q = 0; q < lab_n[lch[t]]; ++q) stA[labp(lch[t])[q]] = sQ;
+                        int cb = 0;
+                        for (int q = 0; q < lab_n[rch[t]]; ++q) {
+                            const int32_t l = labp(rch[t])[q];
+                            if (stA[l] != sQ && stC[l] == sQ) ++cb;
+                        }
+                        ok = cb >= 4;
+                    }
+                    if (ok) std::swap(lch[t], rch[t]);
+                }
+            }
             const int A = lch[t], B = rch[t];
             const int sN = ++stamp;  // stamp of this node (stA, stB, batA, batB)
             const int32_t* lc = P.lay_data.data() + P.lay_off[t];
@@ -513,7 +537,15 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 for (int i = 0; i < n; ++i) key[v[i]] = posC[v[i]];
                 sort_by_key(v, key.data(), n);
                 const int tl = std::min(n, tmax);
-                class_key(v, tl, bat, sec);
+                // the lowest `nlow` tile labels stay in C order (then a 16-byte output vector is contiguous in the
+                // staging buffer too); the others follow the producing child's classes
+                // labels that are batch labels of the producing child cannot be low output bits of that child: last
+                for (int i = 0; i < tl; ++i) key[v[i]] = (bat[v[i]] == sN ? 1024 : 0) + posC[v[i]];
+                sort_by_key(v, key.data(), tl);
+                int n_free = 0;
+                while (n_free < tl && bat[v[n_free]] != sN) ++n_free;
+                const int nlow = std::min(n_free, half ? 3 : 2);
+                if (n_free > nlow) class_key(v + nlow, n_free - nlow, bat, sec);
                 if (tl >= 2) {
                     int top = 0;
                     for (int i = 1; i < tl; ++i)
@@ -933,6 +965,10 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                     s.a_shift[31] = s.c_shift[c.tm + c.tn - 1];
                     s.b_shift[31] = half ? ((ent_cs[0] == 0 && ent_cs[1] == 1 && ent_cs[2] == 2) ? 1 : 0)
                                          : ((ent_cs[0] == 0 && ent_cs[1] == 1) ? 1 : 0);
+                    // b_shift[30] = 1: the elements of one 16-byte output vector are also contiguous in the staging
+                    // buffer (one LDS.128 instead of 4 / 8 scalar loads)
+                    s.b_shift[30] = half ? ((ent_sp[0] == 0 && ent_sp[1] == 1 && ent_sp[2] == 2) ? 1 : 0)
+                                         : ((ent_sp[0] == 0 && ent_sp[1] == 1) ? 1 : 0);
                 }
                 // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
                 // (bit 0 if stores are scalar) on the low lane bits

@@ -148,6 +148,8 @@ def run_plan(plan):
                     assert [int(x) for x in s["b_shift"][:nbr]] == [e[0] for e in ent]
                     assert [int(x) for x in s["a_shift"][:nbr]] == [e[1] for e in ent]
                     assert int(s["a_shift"][30]) == int(s["c_shift"][tm - 1]) and int(s["a_shift"][31]) == int(s["c_shift"][tm + tn - 1])
+                    nlow = 3 if vt == 3 else 2
+                    assert int(s["b_shift"][30]) == int([e[1] for e in ent[:nlow]] == list(range(nlow)))
                     if vt == 3:
                         assert int(s["b_shift"][31]) == int([e[0] for e in ent[:3]] == [0, 1, 2])
                     else:
