@@ -177,7 +177,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--value-type", default="i32", choices=["i32", "i16"], help="i16 = packed int16x2 (plan flag PREFER_I16)")
+    ap.add_argument("--value-type", default="i16", choices=["i32", "i16"],
+                    help="i16 (default, what value_type AUTO picks for this workload) = packed int16x2; i32 = plan flag NO_I16")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -236,7 +237,7 @@ def main():
     n_br = len(branches)
     sliced = [to_sliced(b) for b in branches]
 
-    eng = tbcuda.Engine(local_rank, plan_flags=(tbcuda.TB_PLAN_PREFER_I16 if args.value_type == "i16" else 0))
+    eng = tbcuda.Engine(local_rank, plan_flags=(tbcuda.TB_PLAN_NO_I16 if args.value_type == "i32" else 0))
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # plans for every branch (host-only compile) to get costs; then keep only this rank's shard

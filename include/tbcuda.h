@@ -48,7 +48,7 @@ typedef enum tb_status {
 
 /* value types of the tropical numbers (element_type of the reference, src/dynamic_ob.jl:6) */
 typedef enum tb_value_type {
-    TB_VALUE_AUTO = 0,   /* i32 for unit / integer weights, f32 otherwise */
+    TB_VALUE_AUTO = 0,   /* integer weights: packed int16 if sum |w| < 8192 (unless TB_PLAN_NO_I16), else int32; real weights: f32 */
     TB_VALUE_I32 = 1,    /* exact; -inf is the sentinel -2^30 */
     TB_VALUE_F32 = 2,    /* Tropical{Float32}; -inf is IEEE -inf */
     TB_VALUE_I16X2 = 3   /* int16 values, packed pairs in the GEMM (VIADDMNMX.S16x2); -inf is -2^14; needs sum |w| < 2^13 */
@@ -69,8 +69,10 @@ typedef enum tb_weight_dtype {
 #define TB_PLAN_NO_GEMM 4u            /* testing: never choose the tiled max-plus GEMM kernel */
 #define TB_PLAN_SCRAMBLE_LAYOUT 8u    /* testing: pseudo-random (valid) operand layouts */
 #define TB_PLAN_NO_SPLIT_K 16u        /* testing: never split a long reduction into partial + reduce steps */
-#define TB_PLAN_PREFER_I16 32u        /* value_type AUTO picks packed int16 (TB_VALUE_I16X2) when the weights are
-                                         integers with sum |w| < 8192; results are identical, 2x DPX rate, half the bytes */
+#define TB_PLAN_PREFER_I16 32u        /* (default behaviour, kept for explicitness) value_type AUTO picks packed int16
+                                         (TB_VALUE_I16X2) when the weights are integers with sum |w| < 8192: identical
+                                         results, 2x DPX rate, half the bytes */
+#define TB_PLAN_NO_I16 64u            /* value_type AUTO never picks packed int16 (int32 for integer weights) */
 
 typedef struct tb_options {
     int32_t device;          /* CUDA device ordinal */

@@ -17,9 +17,9 @@ echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tai
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/smoke.log
 echo "== bench cfg1"; timeout 600 python bench.py --workload cfg1 --steps 5 --warmup 3 2>&1 | tail -3 | tee $OUT/bench_cfg1.json
 echo "== bench $WL"; timeout 1500 python bench.py --workload $WL --steps 5 --warmup 3 2>&1 | tail -3 | tee $OUT/bench_$WL.json
-echo "== bench $WL packed int16"; timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --value-type i16 2>&1 | tail -1 | tee $OUT/bench_${WL}_i16.json
-echo "== bench $WL direct epilogue"; TB_EPI_DIRECT=1 timeout 600 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee $OUT/bench_${WL}_epidirect.json
-echo "== bench $WL gemm v1"; TB_GEMM_V1=1 timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee $OUT/bench_${WL}_gemmv1.json
+echo "== bench $WL int32 value type"; timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --value-type i32 2>&1 | tail -1 | tee $OUT/bench_${WL}_i32.json
+echo "== bench $WL direct epilogue"; TB_EPI_DIRECT=1 timeout 600 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --value-type i32 2>&1 | tail -1 | tee $OUT/bench_${WL}_epidirect.json
+echo "== bench $WL gemm v1"; TB_GEMM_V1=1 timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --value-type i32 2>&1 | tail -1 | tee $OUT/bench_${WL}_gemmv1.json
 echo "== bench $WL 1 lane"; TB_LANES=1 timeout 900 python bench.py --workload $WL --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee $OUT/bench_${WL}_1lane.json
 echo "== bench reference"; timeout 900 python bench.py --impl reference --workload $WL --steps 2 --warmup 1 2>&1 | tail -2 | tee $OUT/bench_ref_$WL.json
 echo "== ncu launches"

@@ -24,6 +24,7 @@ TB_PLAN_NO_GEMM = 4
 TB_PLAN_SCRAMBLE_LAYOUT = 8
 TB_PLAN_NO_SPLIT_K = 16
 TB_PLAN_PREFER_I16 = 32
+TB_PLAN_NO_I16 = 64
 
 
 class tb_options(C.Structure):

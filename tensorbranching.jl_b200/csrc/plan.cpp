@@ -216,7 +216,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     bool auto_i16 = false;
     if (vt == TB_VALUE_AUTO) {
         vt = int_weights ? TB_VALUE_I32 : TB_VALUE_F32;
-        auto_i16 = int_weights && (P.flags & TB_PLAN_PREFER_I16);  // downgraded below if the weights do not fit
+        auto_i16 = int_weights && !(P.flags & TB_PLAN_NO_I16);  // falls back to int32 below if the weights do not fit
     }
     if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32 && vt != TB_VALUE_I16X2) return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
     if (vt == TB_VALUE_I16X2 || auto_i16) {
@@ -357,8 +357,16 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 serial_log = nk + nka + nkb - ks;
                 limit = 7;
             }
-            if (serial_log <= limit || nk == 0) continue;
-            int sk = std::min(serial_log - limit, gemm_like ? nk - 1 : nk);
+            int sk = (serial_log > limit && nk > 0) ? std::min(serial_log - limit, gemm_like ? nk - 1 : nk) : 0;
+            if (gemm_like) {
+                // parallelism: a node with few output tiles and a long reduction would occupy only a few CTAs of its
+                // level launch for a long time; split k until it has ~32 tiles (keeping >= 32 k-steps per tile).  Its
+                // output is small by construction, so the extra unary max pass is cheap.
+                const int tile_log = half ? 15 : 14;
+                const int t_log = std::max(0, rc - tile_log);
+                const int sk_par = std::min(std::max(0, 5 - t_log), std::max(0, nk - 5));
+                sk = std::max(sk, sk_par);
+            }
             sk = std::min(sk, MAX_RANK - rc);
             if (sk <= 0) continue;
             const int u = nT++, ul = nT++;

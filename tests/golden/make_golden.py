@@ -25,9 +25,9 @@ def lst(t):
     return [lst(x) for x in t] if isinstance(t, tuple) else t
 
 
-def record(name, nv, edges, weights, sc_target, seed, element_type):
+def record(name, nv, edges, weights, sc_target, seed, element_type, reduce=True):
     root = H.make_root(nv, edges, weights=weights, seed=seed)
-    brs = H.slice_bfs(root, sc_target)
+    brs = H.slice_bfs(root, sc_target, reduce=reduce)
     vals = O.contract_slices(brs, element_type)
     exact = O.exact_mis_milp(nv, edges, weights)
     assert abs(float(vals.max()) - exact) <= 1e-4 * max(1.0, abs(exact)), (vals.max(), exact)
@@ -61,3 +61,6 @@ if __name__ == "__main__":
     # small KSG
     nv3, edges3 = H.random_ksg(8, 8, 0.8, 3)
     record("ksg8x8_sc6", nv3, edges3, None, 6, 3, np.float32)
+    # the same kind of instance WITHOUT the stand-in kernelisation (which solves small KSGs outright): dense degree-8 network
+    nv4, edges4 = H.random_ksg(7, 7, 0.8, 4)
+    record("ksg7x7_sc8_nokernel", nv4, edges4, None, 8, 4, np.float32, reduce=False)

@@ -9,10 +9,10 @@ from workloads import standin_host as H
 
 pytestmark = pytest.mark.gpu
 
-FLAGS = [0, 2, 4, 8, 16, 2 | 8, 2 | 4, 4 | 16, 32, 32 | 8, 32 | 2, 32 | 4, 32 | 16]
+FLAGS = [0, 2, 4, 8, 16, 2 | 8, 2 | 4, 4 | 16, 64, 64 | 8, 64 | 2, 64 | 4, 64 | 16]
 
 
-@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6", "ksg7x7_sc8_nokernel"])
 def test_contract_slices_on_golden(tb, engine, name):
     rec = load_golden(name + ".json")
     et = np.dtype(rec["element_type"]).type
@@ -50,7 +50,7 @@ def test_float64_weights_with_float32_element_type(tb, engine):
     assert got == O.solve_slice(root, np.float32) == O.exact_mis_milp(nv, edges)
 
 
-@pytest.mark.parametrize("flags", [1, 1 | 8, 1 | 4, 1 | 32, 1 | 32 | 8])
+@pytest.mark.parametrize("flags", [1, 1 | 8, 1 | 4, 1 | 64, 1 | 64 | 8])
 def test_every_node_bit_exact(tb, engine, flags):
     """node-by-node: every intermediate tensor equals the oracle's (SURVEY 8c oracle plan (1))."""
     root = regular_root(70, 8)
@@ -67,7 +67,7 @@ def test_every_node_bit_exact(tb, engine, flags):
         ol, oarr = inter[s.node]
         assert np.array_equal(align_to(dl, darr, ol), oarr), f"node {s.node} kind {s.kind}"
         kinds.add(s.kind)
-    if not flags & (4 | 32):
+    if (flags & 64) and not (flags & 4):
         assert 2 in kinds  # the tiled GEMM kernel was exercised (the packed-int16 tile needs larger nodes)
 
 
@@ -104,13 +104,15 @@ def test_branching_property_config2_shape(tb, engine):
 def test_large_tensors_sc20(tb, engine):
     """one n=150 branch at sc ~20: big GEMM / generic nodes, checked against the oracle root value."""
     root = regular_root(150, 1000)
-    p = tb.Plan(to_sliced(root), engine=engine)
-    st = p.info()
-    assert st.sc >= 16 and st.n_gemm_steps > 0
-    assert engine.contract(p) == O.solve_slice(root, np.float64)
-    # and with the GEMM kernel disabled: identical
-    q = tb.Plan(to_sliced(root), flags=4, engine=engine)
-    assert engine.contract(q) == engine.contract(p)
+    want = O.solve_slice(root, np.float64)
+    for base in (0, 64):  # packed int16 (default) and int32
+        p = tb.Plan(to_sliced(root), flags=base, engine=engine)
+        st = p.info()
+        assert st.sc >= 16 and st.n_gemm_steps > 0 and st.value_type == (1 if base else 3)
+        assert engine.contract(p) == want
+        # and with the GEMM kernel disabled: identical
+        q = tb.Plan(to_sliced(root), flags=base | 4, engine=engine)
+        assert engine.contract(q) == want
 
 
 @pytest.mark.parametrize("n,seed", [(130, 5), (150, 1000)])
@@ -121,16 +123,16 @@ def test_split_k_and_every_node_large(tb, engine, n, seed):
     root = regular_root(n, seed)
     want = CO.contract_slices([root], np.float32)[0]
     vals = {}
-    for flags in (0, 16, 4, 8):
+    for flags in (0, 16, 4, 8, 64, 64 | 16, 64 | 8):
         p = tb.Plan(to_sliced(root), flags=flags, engine=engine)
         vals[flags] = engine.contract(p)
         p.close()
     assert all(v == want for v in vals.values()), (vals, want)
-    p = tb.Plan(to_sliced(root), flags=0, engine=engine)
+    p = tb.Plan(to_sliced(root), flags=64, engine=engine)
     assert any(s.node >= 2 * len(root.ixs) - 1 for s in p.steps())  # split-K really happened
 
 
-@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr30_disconnected", "ksg8x8_sc6"])
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr30_disconnected", "ksg8x8_sc6", "ksg7x7_sc8_nokernel"])
 def test_contract_slices_packed_int16(tb, name):
     """K2: the packed int16x2 value type (plan flag PREFER_I16) returns the same per-branch vector."""
     rec = load_golden(name + ".json")
@@ -138,9 +140,15 @@ def test_contract_slices_packed_int16(tb, name):
     eng = tb.Engine(0, plan_flags=tb.TB_PLAN_PREFER_I16)
     got = tb.contract_slices([to_sliced(b) for b in brs], np.float32, True, engine=eng)
     assert np.array_equal(got.astype(np.float64), np.asarray(rec["values"]))
-    p = tb.Plan(to_sliced(brs[0]), engine=eng)
-    assert p.info().value_type == 3
+    for b in brs[:3]:
+        if b.nv:
+            assert tb.Plan(to_sliced(b), engine=eng).info().value_type == 3
+    # and the int32 value type on the same branches
+    eng32 = tb.Engine(0, plan_flags=tb.TB_PLAN_NO_I16)
+    got32 = tb.contract_slices([to_sliced(b) for b in brs], np.float32, True, engine=eng32)
+    assert np.array_equal(got32, got)
     eng.close()
+    eng32.close()
 
 
 @pytest.mark.parametrize("n,seed", [(130, 5), (150, 1000)])
@@ -162,8 +170,8 @@ def test_int16_falls_back_when_weights_do_not_fit(tb, engine):
     nv, edges = H.random_regular_graph(40, 3, 2)
     w = np.full(nv, 1000, dtype=np.int64)  # sum |w| = 40000 >= 8192 -> int32
     root = H.make_root(nv, edges, weights=w, seed=2)
-    p = tb.Plan(to_sliced(root), flags=tb.TB_PLAN_PREFER_I16, engine=engine)
-    assert p.info().value_type == 1
+    p = tb.Plan(to_sliced(root), engine=engine)
+    assert p.info().value_type == 1  # AUTO falls back to int32
     assert engine.contract(p) == O.exact_mis_milp(nv, edges, w)
 
 
@@ -177,7 +185,7 @@ def test_gemm_v1_kernel_agrees(tb):
     finally:
         del os.environ["TB_GEMM_V1"]
     e2 = tb.Engine(0)
-    for flags in (1, 1 | 8):
+    for flags in (1 | 64, 1 | 8 | 64):
         p1 = tb.Plan(to_sliced(root), flags=flags, engine=e1)
         p2 = tb.Plan(to_sliced(root), flags=flags, engine=e2)
         assert e1.contract(p1) == e2.contract(p2) == O.solve_slice(root, np.float64)

@@ -38,7 +38,7 @@ def test_oracle_disconnected_and_isolated():
     assert O.solve_slice(root, np.float32) == O.exact_mis_milp(nv, edges)
 
 
-@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6", "ksg7x7_sc8_nokernel"])
 def test_oracle_matches_golden(name):
     rec = load_golden(name + ".json")
     brs = golden_branches(rec)

@@ -40,7 +40,7 @@ def test_usecuda_false_is_refused(tb):
         tb.contract_slices([to_sliced(root)], np.float32, False)
 
 
-FLAGS = [0, 2, 4, 8, 16, 2 | 8, 4 | 8, 32, 32 | 8, 32 | 2, 32 | 16]
+FLAGS = [0, 2, 4, 8, 16, 2 | 8, 4 | 8, 64, 64 | 8, 64 | 2, 64 | 4, 64 | 16]
 
 
 @pytest.mark.parametrize("n,seed", [(12, 1), (30, 3), (60, 5), (100, 7)])
@@ -76,10 +76,10 @@ def test_plan_every_node_matches_oracle(tb):
     root = regular_root(40, 8)
     left, right = O.nested_to_postorder(root.tree, len(root.ixs))
     _, _, inter = O.contract_tree(root.ixs, left, right, None, np.float64, keep_intermediates=True)
-    for flags in (1, 1 | 8, 1 | 32):
+    for flags in (1, 1 | 8, 1 | 64):
         p = tb.Plan(to_sliced(root), flags=flags)
         vt = p.info().value_type
-        assert vt == (3 if flags & 32 else 1)
+        assert vt == (1 if flags & 64 else 3)
         _, arena = DI.run_plan(p)
         for s in p.steps():
             if s.node not in inter:
@@ -92,7 +92,7 @@ def test_plan_every_node_matches_oracle(tb):
             assert np.array_equal(align_to(dl, darr, ol), oarr), f"node {s.node}"
 
 
-@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6"])
+@pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6", "ksg7x7_sc8_nokernel"])
 def test_plan_on_golden(tb, name):
     rec = load_golden(name + ".json")
     et = np.dtype(rec["element_type"]).type
