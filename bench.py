@@ -337,10 +337,17 @@ def main():
         my_gemm_ops = float(sum(stats[i].gemm_ops for i in mine if stats[i]))
         peak_gops = dpx.get("viaddmax_s16x2_Gops" if args.value_type == "i16" else "viaddmax_s32_Gops")
         ach = my_gemm_ops / (gemm_ms * 1e-3) * 1e-9 if gemm_ms > 0 else None
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "latest_ncu_traffic.json")
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = tj.get("dram_bytes_per_launch_mean")
+            traffic_note = f"mean dram__bytes_read+write per launch over {len(tj.get('launches', []))} captured launches of {tj.get('kernel')} ({tj.get('source')})"
         roofline = {"bound": ("dpx-int16x2 (VIADDMNMX.S16x2" if args.value_type == "i16" else "dpx-int32 (VIADDMNMX") +
                              " issue rate; the semiring is (max,+), tensor cores do not apply)",
                     "kernel": "k_gemm2h (packed int16x2)" if args.value_type == "i16" else "k_gemm2<int32>", "achieved": ach, "peak": peak_gops, "unit": "Gop/s",
-                    "frac": (ach / peak_gops) if (ach and peak_gops) else None, "traffic": None,
+                    "frac": (ach / peak_gops) if (ach and peak_gops) else None, "traffic": traffic, "traffic_note": traffic_note,
+                    "algorithmic_bytes_per_launch": (float(sum(stats[i].gemm_bytes for i in mine if stats[i])) / max(1, gemm_launches)),
                     "peak_source": "tensorbranching.jl_b200/dpx_peak microbenchmark run inside bench.py (register-resident VIADDMNMX, all SMs)",
                     "avg_launch_ms": gemm_ms / max(1, gemm_launches), "launches": gemm_launches,
                     "share_of_step": {k: v[0] for k, v in prof.items()},

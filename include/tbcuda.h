@@ -128,6 +128,7 @@ typedef struct tb_plan_stats {
     double gemm_ops;         /* ops carried by the tiled GEMM kernel */
     double fused_ops;
     double generic_ops;
+    double gemm_bytes;       /* algorithmic bytes (operands read once + result written once) of the GEMM steps */
 } tb_plan_stats;
 
 /* one exported step (for inspection / the oracle-side plan checker / estimators) */

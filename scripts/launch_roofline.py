@@ -19,6 +19,11 @@ def main():
     branches = bench.make_workload(wl)
     sliced = [tbcuda.SlicedBranch.from_parts(b.nv, b.edges, b.weights, b.ixs, b.tree, b.r) for b in branches]
     plans = [tbcuda.Plan(s) if s.code is not None else None for s in sliced]
+    half = any(p is not None and p.info().value_type == 3 for p in plans)
+    eb = 2 if half else 4
+    global P_DPX
+    if half:
+        P_DPX = 35.4e12
     steps = [p.steps() if p else [] for p in plans]
     # waves of 256 plans in order (the engine's default), per level per kind
     expected = []
@@ -39,9 +44,9 @@ def main():
                         if s.level == lv and s.kind == kind:
                             tc = s.rank_c + s.n_k + s.n_ka + s.n_kb
                             ops += 2.0 ** tc
-                            byts += 4 * (2.0 ** s.rank_a + 2.0 ** s.rank_b + 2.0 ** s.rank_c)
+                            byts += eb * (2.0 ** s.rank_a + 2.0 ** s.rank_b + 2.0 ** s.rank_c)
                             cnt += 1
-                            key = (s.n_m, s.n_n, s.n_b, s.n_k)
+                            key = (s.n_m, s.n_n, s.n_b, s.n_k, s.n_ka + s.n_kb)
                             desc[key] = desc.get(key, 0) + 2.0 ** tc
                 if cnt:
                     top = sorted(desc.items(), key=lambda kv: -kv[1])[:2]

@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #ifdef TB_PLAN_PROFILE
@@ -364,7 +365,11 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 // output is small by construction, so the extra unary max pass is cheap.
                 const int tile_log = half ? 15 : 14;
                 const int t_log = std::max(0, rc - tile_log);
-                const int sk_par = std::min(std::max(0, 5 - t_log), std::max(0, nk - 5));
+                static const int target_log = [] {
+                    const char* e = getenv("TB_SPLIT_TARGET");  // log2 of the tiles a node should have; 0 disables
+                    return e ? atoi(e) : 5;
+                }();
+                const int sk_par = std::min(std::max(0, target_log - t_log), std::max(0, nk - 5));
                 sk = std::max(sk, sk_par);
             }
             sk = std::min(sk, MAX_RANK - rc);
@@ -768,7 +773,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         r.tn = c.tn;
         return r;
     };
-    double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, sc = 0;
+    double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, bytes_m = 0, sc = 0;
     for (int t = 0; t < nT0; ++t) sc = std::max(sc, (double)lab_n[t]);
     auto account = [&](int t, int knd) {
         const NodeCls& c = cls[t];
@@ -781,7 +786,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         }
         (knd == KIND_FUSED ? ops_f : knd == KIND_GENERIC ? ops_g : ops_m) += p2(tc);
         double cb = (t >= nT0) ? 0.0 : p2(rank_of(t));  // a partial node's output is not algorithmic traffic
+        const double nb_ = eb * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + p2(rank_of(t)));
         bytes += eb * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + cb);
+        if (knd == KIND_GEMM) bytes_m += nb_;  // what the kernel itself moves (a partial output included)
     };
     P.recs.reserve(topo.size());
     P.sub_steps.reserve(topo.size() - n_big);
@@ -1019,6 +1026,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     S.gemm_ops = ops_m;
     S.fused_ops = ops_f;
     S.generic_ops = ops_g;
+    S.gemm_bytes = bytes_m;
     return TB_OK;
 }
 
