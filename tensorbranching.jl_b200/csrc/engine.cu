@@ -958,7 +958,23 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
             }
         }
         for (int64_t i = lo; i < hi; ++i)
-            while (!done[i].load(std::memory_order_acquire)) std::this_thread::yield();
+            while (!done[i].load(std::memory_order_acquire)) {
+                // the launching thread compiles too while it would otherwise wait
+                int64_t j = next.fetch_add(1);
+                if (j < n) {
+                    if (!abort.load(std::memory_order_relaxed) && nets[j].n_leaves != 0) {
+                        tb_plan* p = new tb_plan();
+                        codes[j] = compile_plan(nets[j], flags, p->p, errs[j]);
+                        if (codes[j]) {
+                            delete p;
+                            abort.store(true);
+                        } else plans[j] = p;
+                    }
+                    done[j].store(1, std::memory_order_release);
+                } else {
+                    std::this_thread::yield();
+                }
+            }
         t_wait += now_ms() - tw0;
         for (int64_t i = lo; i < hi; ++i) {
             if (codes[i]) {

@@ -151,8 +151,6 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
     if (sd.vec4) {
         // streaming mode: this thread owns outputs c4 .. c4+3 (C address bits 0,1), 128-bit store
         typedef typename Ops<T>::vec4 vec4;
-        const uint32_t c4 = ((tile << 8) | (uint32_t)tid) << 2;
-        const uint32_t offA = scatter_bits(c4, sd.a_shift, rc), offB = scatter_bits(c4, sd.b_shift, rc);
         const uint32_t a0 = sd.a_shift[0], a1 = sd.a_shift[1], b0 = sd.b_shift[0], b1 = sd.b_shift[1];
         const int modeA = (a0 == NO_BIT && a1 == NO_BIT) ? OPV_BCAST : ((a0 == 0 && a1 == 1) ? OPV_VEC : OPV_GATHER);
         const int modeB = (b0 == NO_BIT && b1 == NO_BIT) ? OPV_BCAST : ((b0 == 0 && b1 == 1) ? OPV_VEC : OPV_GATHER);
@@ -161,6 +159,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
         const uint32_t kmask = (1u << nk) - 1u, amask = (1u << (nk + nka)) - 1u;
         const uint32_t n_red = 1u << nkt;
         const int sa = sd.sa, sb = sd.sb;
+        const int n_it = 1 << (po - 10);  // vectors per thread
+        for (int vi = 0; vi < n_it; ++vi) {
+        const uint32_t c4 = ((((tile << (po - 10)) + (uint32_t)vi) << 8) | (uint32_t)tid) << 2;
+        const uint32_t offA = scatter_bits(c4, sd.a_shift, rc), offB = scatter_bits(c4, sd.b_shift, rc);
         T acc[4] = {Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf()};
         for (uint32_t r = 0; r < n_red; ++r) {
             const uint32_t ra = offA + ((r & amask) << sa);
@@ -188,6 +190,7 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
         vec4 o;
         o.x = acc[0]; o.y = acc[1]; o.z = acc[2]; o.w = acc[3];
         *reinterpret_cast<vec4*>(C + c4) = o;
+        }
         return;
     }
     // thread -> (output, k-part): 2^po outputs per CTA, 2^ks threads share one output

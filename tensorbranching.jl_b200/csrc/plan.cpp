@@ -367,7 +367,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 const int t_log = std::max(0, rc - tile_log);
                 static const int target_log = [] {
                     const char* e = getenv("TB_SPLIT_TARGET");  // log2 of the tiles a node should have; 0 disables
-                    return e ? atoi(e) : 5;
+                    return e ? atoi(e) : 0;  // measured on cfg2 (profiles/s02_split_target_sweep.jsonl): with 4 lanes in flight extra levels cost more than idle CTA slots
                 }();
                 const int sk_par = std::min(std::max(0, target_log - t_log), std::max(0, nk - 5));
                 sk = std::max(sk, sk_par);
@@ -501,8 +501,11 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             for (int i = 0; i < rc; ++i) posC[lc[i]] = i;
             for (int q = 0; q < lab_n[A]; ++q) stA[labp(A)[q]] = sN;
             for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = sN;
+            // nodes whose tensors are all tiny end up inside fused subtrees (shared memory): label order is
+            // irrelevant there, so skip the ordering analysis (90 % of all nodes)
+            const bool tiny = rc <= 6 && lab_n[A] <= 6 && lab_n[B] <= 6;
             // batch labels of the children (labels shared by a child's own operands)
-            for (int side = 0; side < 2; ++side) {
+            for (int side = 0; side < 2 && !tiny; ++side) {
                 const int ch = side ? B : A;
                 if (leaf[ch]) continue;
                 auto& bat = side ? batB : batA;
@@ -569,12 +572,14 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 }
                 if (n > tl) class_key(v + tl, n - tl, bat, sec);
             };
-            order_side(M, nm, TILE_M_MAX, batA, secA);
-            order_side(N, nn, GEMM_TILE_MAX, batB, secB);
-            for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
-            sort_by_key(Bt, key.data(), nb);
-            for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
-            sort_by_key(K, key.data(), nk);
+            if (!tiny) {
+                order_side(M, nm, TILE_M_MAX, batA, secA);
+                order_side(N, nn, GEMM_TILE_MAX, batB, secB);
+                for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
+                sort_by_key(Bt, key.data(), nb);
+                for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
+                sort_by_key(K, key.data(), nk);
+            }
             if (scramble) {
                 Lcg g((uint64_t)t * 977 + 13);
                 g.shuffle(M, nm);
@@ -929,9 +934,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 set_pos(posB, B, false);
                 int ks, po;
                 generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
-                if (ks == 0 && s.rc >= 10) {  // streaming node: 4 consecutive outputs per thread, 1024 per CTA
+                if (ks == 0 && s.rc >= 10) {  // streaming node: 4 consecutive outputs per thread and iteration
                     s.vec4 = 1;
-                    po = 10;
+                    po = s.rc >= 14 ? 12 : 10;  // 4096 outputs per CTA (4 iterations) amortise the per-CTA set-up
                 }
                 s.ks = (uint8_t)ks;
                 s.po = (uint8_t)po;

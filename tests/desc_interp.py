@@ -121,7 +121,7 @@ def run_plan(plan):
                     acc = _generic(A, B, rc, nk, int(s["nka"]), int(s["nkb"]), int(s["sa"]), int(s["sb"]),
                                    s["a_shift"], s["b_shift"], neg)
                     if s["vec4"]:
-                        assert int(s["po"]) == 10 and int(s["ks"]) == 0 and rc >= 10
+                        assert int(s["po"]) in (10, 12) and int(s["ks"]) == 0 and rc >= int(s["po"])
                     else:
                         assert int(s["po"]) + int(s["ks"]) <= 8
                     assert int(s["po"]) <= rc and int(s["n_tiles"]) == 1 << (rc - int(s["po"]))
