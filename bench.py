@@ -237,7 +237,9 @@ def main():
     n_br = len(branches)
     sliced = [to_sliced(b) for b in branches]
 
-    eng = tbcuda.Engine(local_rank, plan_flags=(tbcuda.TB_PLAN_NO_I16 if args.value_type == "i32" else 0))
+    host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    eng = tbcuda.Engine(local_rank, plan_flags=(tbcuda.TB_PLAN_NO_I16 if args.value_type == "i32" else 0),
+                        host_threads=max(1, host_cores // world))  # ranks share the host's cores for plan compilation
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # plans for every branch (host-only compile) to get costs; then keep only this rank's shard

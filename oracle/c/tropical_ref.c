@@ -232,6 +232,14 @@ int tref_contract(int n_labels, int n_leaves, const int* leaf_off, const int* le
 /* the loop of contract_slices, branches distributed over OpenMP threads (the most favourable CPU
  * arrangement: every core runs its own branch end to end).  Network i is described by the i-th
  * entries of the pointer arrays.  Returns the number of threads used. */
+void tref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int tref_contract_batch(int n, const int* n_labels, const int* n_leaves, const int* const* leaf_off,
                         const int* const* leaf_labels, const int* const* left, const int* const* right,
                         const double* const* weights, double* out_values, double* out_ops) {

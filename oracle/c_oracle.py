@@ -19,6 +19,10 @@ def load():
             raise ImportError(f"{LIB_PATH} missing: run __graft_entry__.build()")
         _lib = C.CDLL(LIB_PATH)
         _lib.tref_contract_batch.restype = C.c_int
+        try:  # all host cores, even when a launcher (torchrun) exported OMP_NUM_THREADS=1
+            _lib.tref_set_threads(len(os.sched_getaffinity(0)))
+        except AttributeError:
+            _lib.tref_set_threads(os.cpu_count() or 1)
     return _lib
 
 

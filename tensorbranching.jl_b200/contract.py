@@ -78,6 +78,20 @@ def _network_of(branch: SlicedBranch, element_type, flags=0, keep: Optional[list
     return net, w
 
 
+_EMPTY_NET_BYTES = bytes(C.sizeof(L.tb_network))
+
+
+def _network_bytes(branch: SlicedBranch, element_type, flags=0) -> bytes:
+    key = ("bytes", np.dtype(element_type).name if element_type is not None else None, flags)
+    cache = branch.__dict__.setdefault("_net_cache", {})
+    hit = cache.get(key)
+    if hit is None:
+        net, _ = _network_of(branch, element_type, flags)
+        hit = bytes(net)
+        cache[key] = hit
+    return hit
+
+
 class Plan:
     """Compiled, device-resident form of one branch's contraction (tb_plan)."""
 
@@ -180,12 +194,20 @@ class Engine:
         """The whole of contract_slices through ONE C call (compile + upload + contract):
         returns the contracted values WITHOUT r (float64)."""
         n = len(branches)
-        nets = (L.tb_network * max(n, 1))()
-        for i, br in enumerate(branches):
-            if br.p.nv == 0 or br.code is None:
-                nets[i].n_leaves = 0
-            else:
-                nets[i] = _network_of(br, element_type, flags)[0]
+        # one tb_network record per branch; the records are cached as bytes on the branch objects, so a call only
+        # joins them (the pointers inside stay valid as long as the branches are alive)
+        key = ("bytes", np.dtype(element_type).name if element_type is not None else None, flags)
+        parts = []
+        for br in branches:
+            try:
+                parts.append(br._net_cache[key])  # hot path: one attribute + one dict lookup per branch
+            except (AttributeError, KeyError):
+                if br.p.nv == 0 or br.code is None:
+                    br.__dict__.setdefault("_net_cache", {})[key] = _EMPTY_NET_BYTES
+                    parts.append(_EMPTY_NET_BYTES)
+                else:
+                    parts.append(_network_bytes(br, element_type, flags))
+        nets = (L.tb_network * max(n, 1)).from_buffer_copy(b"".join(parts) if n else _EMPTY_NET_BYTES)
         out = np.empty(n, dtype=np.float64)
         status = np.zeros(n, dtype=np.int32)
         mx = C.c_double()
@@ -268,12 +290,11 @@ def contract_slices(branches: Sequence[SlicedBranch], element_type=np.float32, u
     et = np.dtype(element_type).type
     eng = engine or default_engine()
     vals, status = eng.contract_branches(branches, element_type)
-    res = np.empty(len(branches), dtype=element_type)
-    for i, br in enumerate(branches):
-        if br.p.nv == 0 or br.code is None:
-            res[i] = et(br.r)
-        else:
-            res[i] = et(vals[i]) + et(br.r)
+    n = len(branches)
+    r = np.array([br.r for br in branches], dtype=np.float64).astype(element_type)
+    empty = np.array([br.code is None or br.p.nv == 0 for br in branches], dtype=bool)
+    res = vals.astype(element_type) + r  # element_type arithmetic, as t + element_type(branch.r) in the reference
+    res[empty] = r[empty]
     return res
 
 

@@ -428,11 +428,13 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     // ---- layouts top-down (the consumer dictates the layout of both of its operands)
     P.lay_off.assign(nT, 0);
     P.lay_n.assign(nT, 0);
-    P.lay_data.clear();
-    P.lay_data.reserve(lab_data.size() + 64);
+    size_t lab_total = 0;
+    for (int t = 0; t < nT; ++t) lab_total += lab_n[t];
+    P.lay_data.assign(lab_total + (size_t)net.n_open + 64, 0);
+    size_t lay_top = 0;
     std::vector<NodeCls> cls(nT);
-    std::vector<int32_t> cls_data;
-    cls_data.reserve(lab_data.size() * 2);
+    std::vector<int32_t> cls_data(lab_total + 64, 0);  // every operand label falls in exactly one class of its consumer
+    size_t cls_top = 0;
     {
         if (net.n_open) {
             ++stamp;
@@ -442,7 +444,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 if (stC[net.open_labels[i]] != stamp) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
             P.lay_off[root] = 0;
             P.lay_n[root] = (uint8_t)net.n_open;
-            P.lay_data.insert(P.lay_data.end(), net.open_labels, net.open_labels + net.n_open);
+            for (int i = 0; i < net.n_open; ++i) P.lay_data[lay_top++] = net.open_labels[i];
         }
         std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
         std::vector<int32_t> posC(NLAB, -1);
@@ -590,7 +592,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 g.shuffle(KB, nkb);
             }
             NodeCls& c = cls[t];
-            c.off = (int32_t)cls_data.size();
+            c.off = (int32_t)cls_top;
             c.nm = (uint8_t)nm;
             c.nn = (uint8_t)nn;
             c.nb = (uint8_t)nb;
@@ -600,38 +602,35 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             c.tm = (uint8_t)std::min(nm, TILE_M_MAX);
             c.tn = (uint8_t)std::min(nn, GEMM_TILE_MAX);
             {
-                const size_t o0 = cls_data.size();
-                cls_data.resize(o0 + nm + nn + nb + nk + nka + nkb);
-                int32_t* w = cls_data.data() + o0;
-                std::memcpy(w, M, nm * 4); w += nm;
-                std::memcpy(w, N, nn * 4); w += nn;
-                std::memcpy(w, Bt, nb * 4); w += nb;
-                std::memcpy(w, K, nk * 4); w += nk;
-                std::memcpy(w, KA, nka * 4); w += nka;
-                std::memcpy(w, KB, nkb * 4);
+                int32_t* w = cls_data.data() + cls_top;
+                for (int i = 0; i < nm; ++i) *w++ = M[i];
+                for (int i = 0; i < nn; ++i) *w++ = N[i];
+                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                for (int i = 0; i < nk; ++i) *w++ = K[i];
+                for (int i = 0; i < nka; ++i) *w++ = KA[i];
+                for (int i = 0; i < nkb; ++i) *w++ = KB[i];
+                cls_top = (size_t)(w - cls_data.data());
             }
             // A = [M_lo | K | KA | M_hi | Bt],  B = [N_lo | K | KB | N_hi | Bt]
             {
                 const int ra = nm + nk + nka + nb, rb = nn + nk + nkb + nb;
-                const size_t o0 = P.lay_data.size();
-                P.lay_data.resize(o0 + ra + rb);
-                P.lay_off[A] = (int32_t)o0;
+                P.lay_off[A] = (int32_t)lay_top;
                 P.lay_n[A] = (uint8_t)ra;
-                P.lay_off[B] = (int32_t)(o0 + ra);
+                P.lay_off[B] = (int32_t)(lay_top + ra);
                 P.lay_n[B] = (uint8_t)rb;
-                int32_t* w = P.lay_data.data() + o0;
-                std::memcpy(w, M, c.tm * 4); w += c.tm;
-                std::memcpy(w, K, nk * 4); w += nk;
-                std::memcpy(w, KA, nka * 4); w += nka;
-                std::memcpy(w, M + c.tm, (nm - c.tm) * 4); w += nm - c.tm;
-                std::memcpy(w, Bt, nb * 4); w += nb;
-                std::memcpy(w, N, c.tn * 4); w += c.tn;
-                std::memcpy(w, K, nk * 4); w += nk;
-                std::memcpy(w, KB, nkb * 4); w += nkb;
-                std::memcpy(w, N + c.tn, (nn - c.tn) * 4); w += nn - c.tn;
-                std::memcpy(w, Bt, nb * 4);
+                int32_t* w = P.lay_data.data() + lay_top;
+                for (int i = 0; i < c.tm; ++i) *w++ = M[i];
+                for (int i = 0; i < nk; ++i) *w++ = K[i];
+                for (int i = 0; i < nka; ++i) *w++ = KA[i];
+                for (int i = c.tm; i < nm; ++i) *w++ = M[i];
+                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                for (int i = 0; i < c.tn; ++i) *w++ = N[i];
+                for (int i = 0; i < nk; ++i) *w++ = K[i];
+                for (int i = 0; i < nkb; ++i) *w++ = KB[i];
+                for (int i = c.tn; i < nn; ++i) *w++ = N[i];
+                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                lay_top += (size_t)(ra + rb);
             }
-            lc = P.lay_data.data() + P.lay_off[t];  // lay_data may have been reallocated
             for (int i = 0; i < rc; ++i) posC[lc[i]] = -1;
         }
     }
