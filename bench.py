@@ -45,7 +45,14 @@ def make_workload(name, max_branches=None):
     """-> list of standin Branch objects (cached under /tmp: generation is host-side python)."""
     from workloads import standin_host as H
 
-    cache = f"/tmp/tbcuda_workload_{name}_{max_branches}.pkl"
+    # generation is host-side python (tens of seconds): cache it.  workloads/cache/ is git-ignored but travels with
+    # the working tree; /tmp is the fallback when the tree is read-only
+    cdir = os.path.join(ROOT, "workloads", "cache")
+    try:
+        os.makedirs(cdir, exist_ok=True)
+    except OSError:
+        cdir = "/tmp"
+    cache = os.path.join(cdir, f"tbcuda_workload_{name}_{max_branches}.pkl")
     if os.path.exists(cache):
         with open(cache, "rb") as f:
             return pickle.load(f)

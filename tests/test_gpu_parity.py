@@ -208,6 +208,30 @@ def test_many_lanes_and_small_waves(tb):
     eng.close()
 
 
+def test_large_tensors_sc24_vs_c_oracle(tb, engine):
+    """sc = 24 (16 Mi-element tensors): root value equals the C oracle's, both value types."""
+    from oracle import c_oracle as CO
+    root = regular_root(160, 3)
+    want = CO.contract_slices([root], np.float32)[0]
+    for flags in (0, 64):
+        p = tb.Plan(to_sliced(root), flags=flags, engine=engine)
+        assert p.info().sc >= 24
+        assert engine.contract(p) == want
+        p.close()
+
+
+def test_full_size_sc28_property(tb, engine):
+    """BASELINE config-4 tensor size (sc = 28: 2^28-element intermediates, ~1.5 GB arena).  No CPU restatement
+    finishes in seconds at this size, so the check is the size-independent property the reference's tests use:
+    the contracted value equals the exact MIS (independent HiGHS MILP)."""
+    nv, edges = H.random_regular_graph(180, 3, 21)
+    root = H.make_root(nv, edges, seed=21)
+    p = tb.Plan(to_sliced(root), engine=engine)
+    st = p.info()
+    assert st.sc >= 28 and st.arena_elems * 2 > 1e9
+    assert engine.contract(p) == O.exact_mis_milp(nv, edges)
+
+
 def test_corner_cases(tb, engine):
     b1 = tb.SlicedBranch(tb.MISProblem(1, [], None), tb.CompressedEinsum([(0,)], (), None), 3)
     b2 = tb.SlicedBranch(tb.MISProblem(2, [], None), tb.CompressedEinsum([(0,), (1,)], (), (0, 1)), 0)
