@@ -51,6 +51,33 @@ template <> __device__ __forceinline__ int16_t shfl_xor_t<int16_t>(int16_t v, in
     return (int16_t)__shfl_xor_sync(0xffffffffu, (int)v, m);
 }
 
+// acc = max(acc, max_i(a[i] + b[i])) over the 16 bytes at a and b (both 16-byte aligned)
+template <typename T> __device__ __forceinline__ T dot16(const T* a, const T* b, T acc);
+template <> __device__ __forceinline__ int32_t dot16<int32_t>(const int32_t* a, const int32_t* b, int32_t acc) {
+    const int4 x = *reinterpret_cast<const int4*>(a), y = *reinterpret_cast<const int4*>(b);
+    acc = __viaddmax_s32(x.x, y.x, acc);
+    acc = __viaddmax_s32(x.y, y.y, acc);
+    acc = __viaddmax_s32(x.z, y.z, acc);
+    return __viaddmax_s32(x.w, y.w, acc);
+}
+template <> __device__ __forceinline__ float dot16<float>(const float* a, const float* b, float acc) {
+    const float4 x = *reinterpret_cast<const float4*>(a), y = *reinterpret_cast<const float4*>(b);
+    acc = fmaxf(__fadd_rn(x.x, y.x), acc);
+    acc = fmaxf(__fadd_rn(x.y, y.y), acc);
+    acc = fmaxf(__fadd_rn(x.z, y.z), acc);
+    return fmaxf(__fadd_rn(x.w, y.w), acc);
+}
+template <> __device__ __forceinline__ int16_t dot16<int16_t>(const int16_t* a, const int16_t* b, int16_t acc) {
+    const uint4 x = *reinterpret_cast<const uint4*>(a), y = *reinterpret_cast<const uint4*>(b);
+    unsigned p = ((unsigned)(uint16_t)acc) * 0x10001u;  // packed pair (acc, acc)
+    p = __viaddmax_s16x2(x.x, y.x, p);
+    p = __viaddmax_s16x2(x.y, y.y, p);
+    p = __viaddmax_s16x2(x.z, y.z, p);
+    p = __viaddmax_s16x2(x.w, y.w, p);
+    const int16_t lo = (int16_t)(p & 0xffffu), hi = (int16_t)(p >> 16);
+    return lo > hi ? lo : hi;
+}
+
 __device__ __forceinline__ uint32_t scatter_bits(uint32_t x, const uint8_t* sh, int n) {
     uint32_t off = 0;
     for (int i = 0; i < n; ++i) {
@@ -204,7 +231,13 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
         const uint32_t kmask = (1u << nk) - 1u, amask = (1u << (nk + nka)) - 1u;
         const uint32_t n_red = 1u << nkt;
         const int sa = sd.sa, sb = sd.sb;
-        if (nka == 0 && sd.nkb == 0) {
+        constexpr uint32_t V = 16 / sizeof(T);  // elements per 16-byte vector
+        if (nka == 0 && sd.nkb == 0 && sa == 0 && sb == 0 && (n_red >> ks) >= V) {
+            // both operands carry the reduced labels in their lowest address bits (full reductions, e.g. the root
+            // of every tree): 128-bit loads, consecutive threads take consecutive vectors
+#pragma unroll 2
+            for (uint32_t r = kp * V; r < n_red; r += (V << ks)) acc = dot16<T>(A + offA + r, B + offB + r, acc);
+        } else if (nka == 0 && sd.nkb == 0) {
 #pragma unroll 4
             for (uint32_t r = kp; r < n_red; r += (1u << ks))
                 acc = Ops<T>::addmax(A[offA + (r << sa)], B[offB + (r << sb)], acc);
