@@ -9,6 +9,7 @@
 //   for a node  C[M,N,Bt] = max_{K,KA,KB}  A[M,K,KA,Bt] + B[N,K,KB,Bt]
 //   A is stored as  [ M_lo (tm bits) | K | KA | M_hi | Bt ]      (bit 0 first)
 //   B is stored as  [ N_lo (tn bits) | K | KB | N_hi | Bt ]
+//   (packed int16 GEMM nodes: [ K0 | M_lo | K_rest | M_hi | Bt ] / [ K0 | N_lo | K_rest | N_hi | Bt ], "kfirst")
 //   i.e. each operand is written by its producer in the order its (single) consumer wants to read it:
 //   reads are regular (a GEMM panel is one contiguous block), writes are bit-scattered.
 #pragma once
@@ -43,7 +44,7 @@ struct SubStep {
     uint16_t a_off, b_off, c_off;  // element offsets (smem or pool); c_off unused when c_loc == LOC_ARENA
     uint8_t a_loc, b_loc, c_loc;
     uint8_t rc, nk, nka, nkb, sa, sb;
-    uint8_t pad;
+    uint8_t pad;  // kfirst: 1 = reduction bit 0 is address bit 0 of A and B, remaining K bits start at sa+1 / sb+1
     uint8_t a_shift[16];
     uint8_t b_shift[16];
 };

@@ -139,10 +139,16 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst*
             if (active) {
                 const uint32_t offA = scatter_bits(c, d.a_shift, rc);
                 const uint32_t offB = scatter_bits(c, d.b_shift, rc);
-                for (uint32_t r = kp; r < n_red; r += (1u << ks)) {
-                    const uint32_t ra = (r & amask) << d.sa;
-                    const uint32_t rb = ((r & kmask) | ((r >> (nk + nka)) << nk)) << d.sb;
-                    acc = Ops<T>::addmax(A[offA + ra], B[offB + rb], acc);
+                if (d.pad) {  // K0-first operands (packed int16 GEMM layout executed by the fused path)
+                    for (uint32_t r = kp; r < n_red; r += (1u << ks))
+                        acc = Ops<T>::addmax(A[offA + ((r & 1u) | ((r >> 1) << (d.sa + 1)))],
+                                             B[offB + ((r & 1u) | ((r >> 1) << (d.sb + 1)))], acc);
+                } else {
+                    for (uint32_t r = kp; r < n_red; r += (1u << ks)) {
+                        const uint32_t ra = (r & amask) << d.sa;
+                        const uint32_t rb = ((r & kmask) | ((r >> (nk + nka)) << nk)) << d.sb;
+                        acc = Ops<T>::addmax(A[offA + ra], B[offB + rb], acc);
+                    }
                 }
             }
             for (int s = 1; s < (1 << ks); s <<= 1) acc = Ops<T>::vmax(acc, shfl_xor_t(acc, s));
@@ -191,9 +197,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
         const uint32_t c4 = ((((tile << (po - 10)) + (uint32_t)vi) << 8) | (uint32_t)tid) << 2;
         const uint32_t offA = scatter_bits(c4, sd.a_shift, rc), offB = scatter_bits(c4, sd.b_shift, rc);
         T acc[4] = {Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf()};
+        const bool kfirst = sd.store_mode != 0;  // generic steps: K0-first operand layouts
         for (uint32_t r = 0; r < n_red; ++r) {
-            const uint32_t ra = offA + ((r & amask) << sa);
-            const uint32_t rb = offB + (((r & kmask) | ((r >> (nk + nka)) << nk)) << sb);
+            const uint32_t ra = offA + (kfirst ? ((r & 1u) | ((r >> 1) << (sa + 1))) : ((r & amask) << sa));
+            const uint32_t rb = offB + (kfirst ? ((r & 1u) | ((r >> 1) << (sb + 1))) : (((r & kmask) | ((r >> (nk + nka)) << nk)) << sb));
             T av[4], bv[4];
             if (modeA == OPV_VEC) {
                 const vec4 v = *reinterpret_cast<const vec4*>(A + ra);
@@ -232,7 +239,10 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
         const uint32_t n_red = 1u << nkt;
         const int sa = sd.sa, sb = sd.sb;
         constexpr uint32_t V = 16 / sizeof(T);  // elements per 16-byte vector
-        if (nka == 0 && sd.nkb == 0 && sa == 0 && sb == 0 && (n_red >> ks) >= V) {
+        if (sd.store_mode != 0) {  // K0-first operand layouts
+            for (uint32_t r = kp; r < n_red; r += (1u << ks))
+                acc = Ops<T>::addmax(A[offA + ((r & 1u) | ((r >> 1) << (sa + 1)))], B[offB + ((r & 1u) | ((r >> 1) << (sb + 1)))], acc);
+        } else if (nka == 0 && sd.nkb == 0 && sa == 0 && sb == 0 && (n_red >> ks) >= V) {
             // both operands carry the reduced labels in their lowest address bits (full reductions, e.g. the root
             // of every tree): 128-bit loads, consecutive threads take consecutive vectors
 #pragma unroll 2
@@ -789,12 +799,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: packed int16x2 variant of k_gemm2.  Same producer / mbarrier / TMA structure; every consumer thread owns
-// 16 (m) x 8 (n) outputs as 8 x 8 packed words (two consecutive m per word, the pair is A's address bit 0), fed by
-// 2 x LDS.128 (A: 16 int16) + 2 x LDS.64 (B: 8 int16) per k-step; the B value is duplicated into both halves with
-// one PRMT and 64 VIADDMNMX.S16x2 update 128 outputs.  Tile = 2^tm x 2^tn with tm <= 8, tn <= 7.
+// K2: packed int16x2 variant of k_gemm2.  Same producer / mbarrier / TMA structure.  Operands are stored
+// [K0 | tile labels | K_rest | ...], so one 32-bit word holds the SAME (m) or (n) element for two consecutive k.
+// A consumer thread owns 8 x 8 outputs as 8 x 8 packed accumulators whose halves collect the even-k and the odd-k
+// partial maxima: per k-pair 2 x LDS.128 (A: 8 words) + 2 x LDS.128 (B: 8 words) and 64 VIADDMNMX.S16x2 = 128
+// tropical ops, no operand duplication.  The epilogue takes max(lo, hi) per accumulator and stores int16.
 // ------------------------------------------------------------------------------------------------
-constexpr int G2H_STG_ELEMS = 8192;  // int16 elements of one staged quarter (16 KB)
+constexpr int G2H_STG_ELEMS = 4096;  // int16 elements of one staged quarter of a 128 x 128 tile (8 KB)
 struct TileInfoH {
     long long cbase[32];
     void* C;
@@ -850,7 +861,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             const uint32_t tile = tile_g - __ldg(tile_starts + idx);
             const BigStep* __restrict__ d = inst.step;
             const int tm = d->tm, tn = d->tn, nk = d->nk, kc = d->kc, ng = d->ng;
-            const int s_log = 8 - (tm + tn - 7), S = 1 << s_log;
+            const int s_log = 8 - (tm + tn - 6), S = 1 << s_log;
             const T* Ag = reinterpret_cast<const T*>(inst.arena) + d->a_off;
             const T* Bg = reinterpret_cast<const T*>(inst.arena) + d->b_off;
             long long ab = -1, bb = -1, cb = -1;
@@ -917,12 +928,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         const TileInfoH& ti = tinfo[slot];
         if (!ti.valid) break;
         const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
-        const int tps_log = tm + tn - 7, S = 1 << (8 - tps_log);
+        const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
         const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
-        const int tmh = ti.lane_n_first ? (lt >> (tn - 3)) : (lt & ((1 << (tm - 4)) - 1));
-        const int tnh = ti.lane_n_first ? (lt & ((1 << (tn - 3)) - 1)) : (lt >> (tm - 4));
-        const int m_lo = tmh * 8, m_hi = (1 << (tm - 1)) + tmh * 8;   // int16 element offsets inside a k-row
-        const int n_lo = tnh * 4, n_hi = (1 << (tn - 1)) + tnh * 4;
+        const int tmh = ti.lane_n_first ? (lt >> (tn - 3)) : (lt & ((1 << (tm - 3)) - 1));
+        const int tnh = ti.lane_n_first ? (lt & ((1 << (tn - 3)) - 1)) : (lt >> (tm - 3));
+        // a k-pair row of A is 2^tm words (2^(tm+1) int16): word m holds (A[m, k even], A[m, k odd])
+        const int m_lo = tmh * 8, m_hi = (2 << (tm - 1)) + tmh * 8;  // int16 offsets inside a row (4 words each)
+        const int n_lo = tnh * 8, n_hi = (2 << (tn - 1)) + tnh * 8;
         const int la = kc + tm, lb = kc + tn;
         uint32_t acc[8][8];
 #pragma unroll
@@ -934,23 +946,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             mbar_wait(&bar_full[stage], (it / G2_STAGES) & 1);
             const T* sA = stage_mem + stage * STAGE_ELEMS + ((size_t)sub << la);
             const T* sB = stage_mem + stage * STAGE_ELEMS + ((size_t)S << la) + ((size_t)sub << lb);
-            const int KC = 1 << kc;
+            const int KP = 1 << (kc - 1);  // k-pair rows in this chunk
 #pragma unroll 1
-            for (int kk = 0; kk < KC; ++kk) {
-                const T* ar = sA + (kk << tm);
-                const T* br = sB + (kk << tn);
+            for (int kk = 0; kk < KP; ++kk) {
+                const T* ar = sA + (kk << (tm + 1));
+                const T* br = sB + (kk << (tn + 1));
                 const uint4 a0 = *reinterpret_cast<const uint4*>(ar + m_lo);
                 const uint4 a1 = *reinterpret_cast<const uint4*>(ar + m_hi);
-                const uint2 b0 = *reinterpret_cast<const uint2*>(br + n_lo);
-                const uint2 b1 = *reinterpret_cast<const uint2*>(br + n_hi);
+                const uint4 b0 = *reinterpret_cast<const uint4*>(br + n_lo);
+                const uint4 b1 = *reinterpret_cast<const uint4*>(br + n_hi);
                 const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const uint32_t bw[4] = {b0.x, b0.y, b1.x, b1.y};
-                uint32_t b[8];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    b[2 * q] = __byte_perm(bw[q], 0, 0x1010);      // low half in both halves
-                    b[2 * q + 1] = __byte_perm(bw[q], 0, 0x3232);  // high half in both halves
-                }
+                const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -959,10 +965,10 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[stage]);
         }
-        // ---- staged epilogue (int16 elements, 8 per 16-byte vector)
+        // ---- staged epilogue: out = max(even-k half, odd-k half); int16 elements, 8 per 16-byte global vector
         {
             const int nbr = tm + tn - 2;
-            const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 3) | ((uint32_t)tnh << (tm + 1));
+            const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
             uint32_t ts = 0, tc = 0;
 #pragma unroll
             for (int b = 3; b < 11; ++b) {
@@ -991,28 +997,28 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 T* buf = stg_mem + (r & 1) * G2H_STG_ELEMS;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    uint4 v;
-                    v.x = acc[ih * 4 + 0][jh * 4 + j];
-                    v.y = acc[ih * 4 + 1][jh * 4 + j];
-                    v.z = acc[ih * 4 + 2][jh * 4 + j];
-                    v.w = acc[ih * 4 + 3][jh * 4 + j];
-                    *reinterpret_cast<uint4*>(buf + stg_swz_h(qbase | ((uint32_t)j << (tm - 1)))) = v;
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t w = acc[ih * 4 + i][jh * 4 + j];
+                        o[i] = __vmaxs2(w, __byte_perm(w, 0, 0x1032)) & 0xffffu;  // max of the two halves
+                    }
+                    uint2 v;
+                    v.x = o[0] | (o[1] << 16);
+                    v.y = o[2] | (o[3] << 16);
+                    *reinterpret_cast<uint2*>(buf + stg_swz_h(qbase | ((uint32_t)j << (tm - 1)))) = v;
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
                 if (evec) {
 #pragma unroll
-                    for (int itr = 0; itr < 4; ++itr) {
+                    for (int itr = 0; itr < 2; ++itr) {
                         const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
                         const uint32_t sub_e = e8 >> nbr;
                         uint32_t so = ts, co = tc;
-#pragma unroll
-                        for (int b = 11; b < 13; ++b) {
-                            const uint32_t bit = ((uint32_t)itr >> (b - 11)) & 1u;
-                            if (b < nbr) {
-                                so |= bit << ti.e_spos[b];
-                                co |= bit << ti.e_cs[b];
-                            }
+                        if (11 < nbr) {
+                            so |= (uint32_t)itr << ti.e_spos[11];
+                            co |= (uint32_t)itr << ti.e_cs[11];
                         }
                         const long long cb = ti.cbase[sub_e];
                         if (cb >= 0) {
@@ -1037,12 +1043,12 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     }
                 } else {
 #pragma unroll 4
-                    for (int itr = 0; itr < 32; ++itr) {
+                    for (int itr = 0; itr < 16; ++itr) {
                         const uint32_t e1 = ((uint32_t)itr << 8) | (uint32_t)ctid;
                         const uint32_t sub_e = e1 >> nbr;
                         uint32_t so = ts1, co = tc1;
 #pragma unroll
-                        for (int b = 8; b < 13; ++b) {
+                        for (int b = 8; b < 12; ++b) {
                             const uint32_t bit = ((uint32_t)itr >> (b - 8)) & 1u;
                             if (b < nbr) {
                                 so |= bit << ti.e_spos[b];

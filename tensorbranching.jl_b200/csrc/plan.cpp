@@ -33,6 +33,7 @@ namespace {
 struct NodeCls {  // label classes of one contraction, labels stored in cls_data at off in this order
     int32_t off = 0;
     uint8_t nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0, tm = 0, tn = 0;
+    uint8_t kfirst = 0;  // packed int16 GEMM operands: [K0 | X_lo | K_rest | X_hi | Bt]
 };
 
 struct FreeList {
@@ -236,8 +237,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     }
     P.value_type = vt;
     const bool half = (vt == TB_VALUE_I16X2);
-    const int TILE_M_MAX = half ? GEMM_TILE_MAX_M16 : GEMM_TILE_MAX;  // tile bits of the M side
-    const int MT_LOG = half ? 4 : 3;                                   // log2 of a thread's microtile extent in m
+    const int TILE_M_MAX = GEMM_TILE_MAX;  // tile bits of the M side
+    const int MT_LOG = 3;                  // log2 of a thread's microtile extent (8 x 8 outputs, both value widths)
     const int STAGE_ELEMS = GEMM_STAGE_ELEMS * (half ? 2 : 1);
 
     // ---- leaf positions (DFS order) and subtree ranges
@@ -344,7 +345,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 if (stA[l] != stamp) (stC[l] == stamp ? nn : nkb)++;
             }
             const int rc = lab_n[t];
-            const int gm = half ? std::max(nm, nn) : nm, gn = half ? std::min(nm, nn) : nn;  // i16 puts the larger side on M
+            const int gm = nm, gn = nn;
             const bool gemm_like = !(P.flags & TB_PLAN_NO_GEMM) && gm >= MT_LOG && gn >= 3 &&
                                    std::min(gm, TILE_M_MAX) + std::min(gn, GEMM_TILE_MAX) >= MT_LOG + 6 && nk >= 1 && nka == 0 &&
                                    nkb == 0 && !leaf[A] && !leaf[B];
@@ -363,7 +364,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 // parallelism: a node with few output tiles and a long reduction would occupy only a few CTAs of its
                 // level launch for a long time; split k until it has ~32 tiles (keeping >= 32 k-steps per tile).  Its
                 // output is small by construction, so the extra unary max pass is cheap.
-                const int tile_log = half ? 15 : 14;
+                const int tile_log = 14;
                 const int t_log = std::max(0, rc - tile_log);
                 static const int target_log = [] {
                     const char* e = getenv("TB_SPLIT_TARGET");  // log2 of the tiles a node should have; 0 disables
@@ -453,25 +454,6 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
         for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
             const int t = *it;
-            if (half && !leaf[lch[t]] && !leaf[rch[t]]) {
-                // packed int16 tiles are 16 (m) x 8 (n) per thread: contract(A, B) == contract(B, A), so make the
-                // operand with more output-only labels the M side
-                const int sQ = ++stamp;
-                const int32_t* lcq = P.lay_data.data() + P.lay_off[t];
-                for (int i = 0; i < P.lay_n[t]; ++i) stC[lcq[i]] = sQ;
-                for (int q = 0; q < lab_n[rch[t]]; ++q) stB[labp(rch[t])[q]] = sQ;
-                int ca = 0, cb = 0;
-                for (int q = 0; q < lab_n[lch[t]]; ++q) {
-                    const int32_t l = labp(lch[t])[q];
-                    stA[l] = sQ;
-                    if (stB[l] != sQ && stC[l] == sQ) ++ca;
-                }
-                for (int q = 0; q < lab_n[rch[t]]; ++q) {
-                    const int32_t l = labp(rch[t])[q];
-                    if (stA[l] != sQ && stC[l] == sQ) ++cb;
-                }
-                if (cb > ca) std::swap(lch[t], rch[t]);
-            }
             if (P.lay_n[t] > 0 && !leaf[lch[t]] && !leaf[rch[t]]) {
                 // orientation: the operand that owns the label at C bit 0 becomes the M side (contract(A,B) == contract(B,A)),
                 // so that the low output bits are m tile bits 0,1,.. and the epilogue can move whole 16-byte vectors
@@ -480,19 +462,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 for (int q = 0; q < lab_n[lch[t]]; ++q) inL = inL || labp(lch[t])[q] == l0;
                 for (int q = 0; q < lab_n[rch[t]]; ++q) inR = inR || labp(rch[t])[q] == l0;
                 if (inR && !inL) {
-                    bool ok = true;
-                    if (half) {  // keep at least 4 output-only labels on the M side of a packed-int16 tile
-                        const int sQ = ++stamp;
-                        const int32_t* lcq = P.lay_data.data() + P.lay_off[t];
-                        for (int i = 0; i < P.lay_n[t]; ++i) stC[lcq[i]] = sQ;
-                        for (int q = 0; q < lab_n[lch[t]]; ++q) stA[labp(lch[t])[q]] = sQ;
-                        int cb = 0;
-                        for (int q = 0; q < lab_n[rch[t]]; ++q) {
-                            const int32_t l = labp(rch[t])[q];
-                            if (stA[l] != sQ && stC[l] == sQ) ++cb;
-                        }
-                        ok = cb >= 4;
-                    }
+                    const bool ok = true;
                     if (ok) std::swap(lch[t], rch[t]);
                 }
             }
@@ -611,6 +581,31 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 for (int i = 0; i < nkb; ++i) *w++ = KB[i];
                 cls_top = (size_t)(w - cls_data.data());
             }
+            // packed int16 GEMM: the two halves of a word are two consecutive k, so one shared reduced label becomes
+            // address bit 0 of BOTH operands:  A = [K0 | M_lo | K_rest | M_hi | Bt],  B = [K0 | N_lo | K_rest | N_hi | Bt]
+            c.kfirst = (half && !(P.flags & TB_PLAN_NO_GEMM) && nm >= MT_LOG && nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && nk >= 1 &&
+                        nka == 0 && nkb == 0 && !leaf[A] && !leaf[B])
+                           ? 1
+                           : 0;
+            if (c.kfirst) {
+                const int ra = nm + nk + nb, rb = nn + nk + nb;
+                P.lay_off[A] = (int32_t)lay_top;
+                P.lay_n[A] = (uint8_t)ra;
+                P.lay_off[B] = (int32_t)(lay_top + ra);
+                P.lay_n[B] = (uint8_t)rb;
+                int32_t* w = P.lay_data.data() + lay_top;
+                *w++ = K[0];
+                for (int i = 0; i < c.tm; ++i) *w++ = M[i];
+                for (int i = 1; i < nk; ++i) *w++ = K[i];
+                for (int i = c.tm; i < nm; ++i) *w++ = M[i];
+                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                *w++ = K[0];
+                for (int i = 0; i < c.tn; ++i) *w++ = N[i];
+                for (int i = 1; i < nk; ++i) *w++ = K[i];
+                for (int i = c.tn; i < nn; ++i) *w++ = N[i];
+                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                lay_top += (size_t)(ra + rb);
+            } else
             // A = [M_lo | K | KA | M_hi | Bt],  B = [N_lo | K | KB | N_hi | Bt]
             {
                 const int ra = nm + nk + nka + nb, rb = nn + nk + nkb + nb;
@@ -864,6 +859,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             s.nkb = c.nkb;
             s.sa = c.tm;
             s.sb = c.tn;
+            s.pad = c.kfirst;  // reduction bit 0 is address bit 0 of both operands, the other K bits start at sa+1 / sb+1
             std::memset(s.a_shift, NO_BIT, sizeof s.a_shift + sizeof s.b_shift);
             {
                 // position of each output label in A / B: stamp the (short) output, then walk A and B once
@@ -931,6 +927,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 }
                 set_pos(posA, A, false);
                 set_pos(posB, B, false);
+                s.store_mode = c.kfirst;  // generic steps reuse this byte: K0-first operand layouts
                 int ks, po;
                 generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
                 if (ks == 0 && s.rc >= 10) {  // streaming node: 4 consecutive outputs per thread and iteration

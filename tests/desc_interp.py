@@ -37,7 +37,7 @@ def scatter(x: np.ndarray, shifts, n: int) -> np.ndarray:
     return off
 
 
-def _generic(A, B, rc, nk, nka, nkb, sa, sb, a_shift, b_shift, neg):
+def _generic(A, B, rc, nk, nka, nkb, sa, sb, a_shift, b_shift, neg, kfirst=False):
     c = np.arange(1 << rc, dtype=np.int64)
     offA = scatter(c, a_shift, rc)
     offB = scatter(c, b_shift, rc)
@@ -45,6 +45,12 @@ def _generic(A, B, rc, nk, nka, nkb, sa, sb, a_shift, b_shift, neg):
     kmask = (1 << nk) - 1
     amask = (1 << (nk + nka)) - 1
     for r in range(1 << (nk + nka + nkb)):
+        if kfirst:  # K0-first operand layouts: reduction bit 0 = address bit 0, the rest starts at sa+1 / sb+1
+            assert nka == 0 and nkb == 0
+            ra = (r & 1) | ((r >> 1) << (sa + 1))
+            rb = (r & 1) | ((r >> 1) << (sb + 1))
+            acc = np.maximum(acc, A[offA + ra] + B[offB + rb])
+            continue
         ra = (r & amask) << sa
         rb = ((r & kmask) | ((r >> (nk + nka)) << nk)) << sb
         acc = np.maximum(acc, A[offA + ra] + B[offB + rb])
@@ -75,7 +81,7 @@ def run_plan(plan):
     else:
         praw = np.frombuffer(plan.raw(0), dtype="<u4")
         pool = praw.view("<i4").astype(np.int64) if vt == 1 else praw.view("<f4").copy()
-    mt = 4 if vt == 3 else 3  # log2 of a thread's microtile extent in m
+    mt = 3  # log2 of a thread's microtile extent (8 x 8 outputs)
     sub = np.frombuffer(plan.raw(1), dtype=SUBSTEP)
     trees = np.frombuffer(plan.raw(2), dtype=SUBTREE)
     big = np.frombuffer(plan.raw(3), dtype=BIGSTEP)
@@ -90,7 +96,7 @@ def run_plan(plan):
                 B = (smem if s["b_loc"] == LOC_SMEM else pool)[int(s["b_off"]):]
                 rc = int(s["rc"])
                 acc = _generic(A, B, rc, int(s["nk"]), int(s["nka"]), int(s["nkb"]), int(s["sa"]), int(s["sb"]),
-                               s["a_shift"], s["b_shift"], neg)
+                               s["a_shift"], s["b_shift"], neg, kfirst=bool(s["pad"]))
                 if s["c_loc"] == LOC_SMEM:
                     o = int(s["c_off"])
                     assert o + (1 << rc) <= int(t["smem_elems"]), "fused step writes past its subtree's shared memory"
@@ -119,7 +125,7 @@ def run_plan(plan):
                 rc, nk = int(s["rc"]), int(s["nk"])
                 if s["kind"] == KIND_GENERIC:
                     acc = _generic(A, B, rc, nk, int(s["nka"]), int(s["nkb"]), int(s["sa"]), int(s["sb"]),
-                                   s["a_shift"], s["b_shift"], neg)
+                                   s["a_shift"], s["b_shift"], neg, kfirst=bool(s["store_mode"]))
                     if s["vec4"]:
                         assert int(s["po"]) in (10, 12) and int(s["ks"]) == 0 and rc >= int(s["po"])
                     else:
@@ -134,7 +140,7 @@ def run_plan(plan):
                     moff = scatter(np.arange(1 << tm, dtype=np.int64), s["c_shift"], tm)
                     noff = scatter(np.arange(1 << tn, dtype=np.int64), s["c_shift"][tm:], tn)
                     S = 1 << (8 - (tm - mt + tn - 3))
-                    assert 1 <= S <= 32 and tm >= mt and tn >= 3 and tm <= (8 if vt == 3 else 7) and tn <= 7
+                    assert 1 <= S <= 32 and tm >= mt and tn >= 3 and tm <= 7 and tn <= 7
                     assert int(s["n_tiles"]) == ((1 << ng) + S - 1) // S
                     assert S * (1 << int(s["kc"])) * ((1 << tm) + (1 << tn)) <= 4096 * (2 if vt == 3 else 1) and int(s["kc"]) <= nk
                     if s["store_mode"] == 1:
@@ -162,8 +168,13 @@ def run_plan(plan):
                         ab = (gm | (gb << n_mhi)) << (tm + nk)
                         bb = (gn | (gb << n_nhi)) << (tn + nk)
                         cb = int(scatter(np.array([g], dtype=np.int64), s["c_shift"][tm + tn:], ng)[0])
-                        Ap = A[ab:ab + (1 << (tm + nk))].reshape(1 << nk, 1 << tm)
-                        Bp = B[bb:bb + (1 << (tn + nk))].reshape(1 << nk, 1 << tn)
+                        if vt == 3:  # packed int16: panels are [k_rest][tile index][k0]
+                            assert int(s["kc"]) >= 1
+                            Ap = A[ab:ab + (1 << (tm + nk))].reshape(1 << (nk - 1), 1 << tm, 2).transpose(0, 2, 1).reshape(1 << nk, 1 << tm)
+                            Bp = B[bb:bb + (1 << (tn + nk))].reshape(1 << (nk - 1), 1 << tn, 2).transpose(0, 2, 1).reshape(1 << nk, 1 << tn)
+                        else:
+                            Ap = A[ab:ab + (1 << (tm + nk))].reshape(1 << nk, 1 << tm)
+                            Bp = B[bb:bb + (1 << (tn + nk))].reshape(1 << nk, 1 << tn)
                         Ct = np.full((1 << tm, 1 << tn), neg, dtype=dt)
                         for k in range(1 << nk):
                             Ct = np.maximum(Ct, Ap[k][:, None] + Bp[k][None, :])

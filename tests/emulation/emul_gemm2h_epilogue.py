@@ -3,7 +3,7 @@ import random
 def swz(x): return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7) << 3)
 def run(tm, tn, lane_n_first, rng, force_fallback=False):
     nbr = tm + tn - 2
-    tps_log = tm + tn - 7; s_log = 8 - tps_log; S = 1 << s_log
+    tps_log = tm + tn - 6; s_log = 8 - tps_log; S = 1 << s_log
     rc = tm + tn + s_log + 2
     pos = list(range(rc)); rng.shuffle(pos)
     if rng.random() < 0.4:   # make the vector path likely: C bits 0,1,2 are tile bits
@@ -21,11 +21,11 @@ def run(tm, tn, lane_n_first, rng, force_fallback=False):
     cs_mtop = c_shift[tm-1]; cs_ntop = c_shift[tm+tn-1]
     evec = (e_cs[:3] == [0, 1, 2]) and not force_fallback
     out = {}
-    stg = [[-1]*8192, [-1]*8192]
+    stg = [[-1]*4096, [-1]*4096]
     def coords(ctid):
         sub = ctid >> tps_log; lt = ctid & ((1 << tps_log) - 1)
         if lane_n_first: tmh = lt >> (tn-3); tnh = lt & ((1 << (tn-3)) - 1)
-        else: tmh = lt & ((1 << (tm-4)) - 1); tnh = lt >> (tm-4)
+        else: tmh = lt & ((1 << (tm-3)) - 1); tnh = lt >> (tm-3)
         return sub, tmh, tnh
     def val(sub, m, n): return (sub << 20) | (m << 10) | n
     for r in range(4):
@@ -33,14 +33,12 @@ def run(tm, tn, lane_n_first, rng, force_fallback=False):
         buf = stg[r & 1]
         for ctid in range(256):
             sub, tmh, tnh = coords(ctid)
-            qbase = (sub << nbr) | (tmh << 3) | (tnh << (tm+1))
+            qbase = (sub << nbr) | (tmh << 2) | (tnh << (tm+1))
             for j in range(4):
-                for w in range(4):       # 4 packed words = 8 consecutive m
-                    for hb in range(2):
-                        mloc = 2*w + hb
-                        mi = (tmh*8 + mloc) if ih == 0 else ((1 << (tm-1)) + tmh*8 + mloc)
-                        ni = (tnh*4 + j) if jh == 0 else ((1 << (tn-1)) + tnh*4 + j)
-                        buf[swz(qbase | (j << (tm-1))) + mloc] = val(sub, mi, ni)
+                for i in range(4):       # 4 int16 = one 8-byte staging store
+                    mi = (tmh*4 + i) if ih == 0 else ((1 << (tm-1)) + tmh*4 + i)
+                    ni = (tnh*4 + j) if jh == 0 else ((1 << (tn-1)) + tnh*4 + j)
+                    buf[swz(qbase | (j << (tm-1))) + i] = val(sub, mi, ni)
         roff = (ih << cs_mtop) | (jh << cs_ntop)
         for ctid in range(256):
             if evec:
@@ -48,13 +46,11 @@ def run(tm, tn, lane_n_first, rng, force_fallback=False):
                 for b in range(3, 11):
                     bit = (ctid >> (b-3)) & 1
                     if b < nbr: ts |= bit << e_spos[b]; tc |= bit << e_cs[b]
-                for itr in range(4):
+                for itr in range(2):
                     e8 = (itr << 11) | (ctid << 3)
                     sub_e = e8 >> nbr
                     so, co = ts, tc
-                    for b in range(11, 13):
-                        bit = (itr >> (b-11)) & 1
-                        if b < nbr: so |= bit << e_spos[b]; co |= bit << e_cs[b]
+                    if 11 < nbr: so |= itr << e_spos[11]; co |= itr << e_cs[11]
                     cb = cbase[sub_e]
                     if cb >= 0:
                         so |= sub_e << nbr
@@ -68,11 +64,11 @@ def run(tm, tn, lane_n_first, rng, force_fallback=False):
                 for b in range(0, 8):
                     bit = (ctid >> b) & 1
                     if b < nbr: ts1 |= bit << e_spos[b]; tc1 |= bit << e_cs[b]
-                for itr in range(32):
+                for itr in range(16):
                     e1 = (itr << 8) | ctid
                     sub_e = e1 >> nbr
                     so, co = ts1, tc1
-                    for b in range(8, 13):
+                    for b in range(8, 12):
                         bit = (itr >> (b-8)) & 1
                         if b < nbr: so |= bit << e_spos[b]; co |= bit << e_cs[b]
                     cb = cbase[sub_e]
@@ -94,9 +90,9 @@ def run(tm, tn, lane_n_first, rng, force_fallback=False):
                 n_expected += 1
     assert len(out) == n_expected
 rng = random.Random(2)
-for tm in range(4, 9):
+for tm in range(3, 8):
     for tn in range(3, 8):
-        if tm + tn < 10: continue
+        if tm + tn < 9: continue
         for lnf in (0, 1):
             run(tm, tn, lnf, rng)
             run(tm, tn, lnf, rng, True)
