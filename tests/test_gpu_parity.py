@@ -232,6 +232,25 @@ def test_full_size_sc28_property(tb, engine):
     assert engine.contract(p) == O.exact_mis_milp(nv, edges)
 
 
+def test_mixed_value_types_in_one_batch(tb, engine):
+    """one contract_slices call with packed-int16, int32 (weights too large for int16), f32 and empty branches."""
+    rng = np.random.default_rng(11)
+    brs, want = [], []
+    for i, (n, kind) in enumerate([(40, "unit"), (50, "big"), (40, "f32"), (0, "empty"), (60, "unit"), (30, "f32")]):
+        if kind == "empty":
+            brs.append(tb.SlicedBranch(tb.MISProblem(0, [], None), None, 5))
+            want.append(np.float32(5))
+            continue
+        nv, edges = H.random_regular_graph(n, 3, 100 + i)
+        w = None if kind == "unit" else (np.full(nv, 1000, dtype=np.int64) if kind == "big" else (1 + rng.random(nv)).astype(np.float32))
+        root = H.make_root(nv, edges, weights=w, seed=i)
+        root.r = i
+        brs.append(to_sliced(root))
+        want.append(np.float32(O.solve_slice(root, np.float32) + np.float32(i)))
+    got = tb.contract_slices(brs, np.float32, True, engine=engine)
+    assert np.array_equal(got, np.asarray(want, dtype=np.float32))
+
+
 def test_corner_cases(tb, engine):
     b1 = tb.SlicedBranch(tb.MISProblem(1, [], None), tb.CompressedEinsum([(0,)], (), None), 3)
     b2 = tb.SlicedBranch(tb.MISProblem(2, [], None), tb.CompressedEinsum([(0,), (1,)], (), (0, 1)), 0)
