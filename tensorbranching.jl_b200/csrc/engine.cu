@@ -788,6 +788,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
         int nb = 0;
         TB_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm2<int32_t>, G2_THREADS, G2_SMEM_BYTES));
         c->gemm2_ctas_per_sm = nb;
+        const char* eg = getenv("TB_GEMM_CTAS");  // persistent GEMM CTAs per SM and launch (experiments: 1 lets two lanes' GEMMs co-run)
+        if (eg && atoi(eg) >= 1) c->gemm2_ctas_per_sm = std::min(nb, atoi(eg));
     }
     *out_ctx = ctx.release();
     return TB_OK;

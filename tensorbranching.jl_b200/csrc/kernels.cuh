@@ -811,7 +811,7 @@ struct TileInfoH {
     void* C;
     int tm, tn, kc, nchunks, valid, lane_n_first;
     unsigned char e_spos[14], e_cs[14];
-    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast;
+    unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast, mp, mswap;
 };
 __device__ __forceinline__ uint32_t stg_swz_h(uint32_t x) { return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7u) << 3); }
 
@@ -894,6 +894,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 ti.e_cs_ntop = d->a_shift[31];
                 ti.e_vec = d->b_shift[31];
                 ti.e_fast = d->b_shift[30];
+                ti.mp = d->a_shift[29];
+                ti.mswap = d->b_shift[29];
                 ti.valid = 1;
             }
             __syncwarp();
@@ -932,8 +934,11 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
         const int tmh = ti.lane_n_first ? (lt >> (tn - 3)) : (lt & ((1 << (tm - 3)) - 1));
         const int tnh = ti.lane_n_first ? (lt & ((1 << (tn - 3)) - 1)) : (lt >> (tm - 3));
-        // a k-pair row of A is 2^tm words (2^(tm+1) int16): word m holds (A[m, k even], A[m, k odd])
-        const int m_lo = tmh * 8, m_hi = (2 << (tm - 1)) + tmh * 8;  // int16 offsets inside a row (4 words each)
+        // a k-pair row of A is 2^tm words (2^(tm+1) int16): word m holds (A[m, k even], A[m, k odd]).  This thread
+        // owns the m tile bits {0, mp, tm-1}; the bits of tmh fill the other positions in ascending order.
+        const int mp = ti.mp;
+        const int tmw = ((tmh & ((1 << (mp - 1)) - 1)) << 1) | ((tmh >> (mp - 1)) << (mp + 1));  // word offset
+        const int m_lo = tmw * 2, m_p = 2 << mp, m_hi = 2 << (tm - 1);  // int16 offsets inside a row
         const int n_lo = tnh * 8, n_hi = (2 << (tn - 1)) + tnh * 8;
         const int la = kc + tm, lb = kc + tn;
         uint32_t acc[8][8];
@@ -951,11 +956,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             for (int kk = 0; kk < KP; ++kk) {
                 const T* ar = sA + (kk << (tm + 1));
                 const T* br = sB + (kk << (tn + 1));
-                const uint4 a0 = *reinterpret_cast<const uint4*>(ar + m_lo);
-                const uint4 a1 = *reinterpret_cast<const uint4*>(ar + m_hi);
+                const uint2 a0 = *reinterpret_cast<const uint2*>(ar + m_lo);
+                const uint2 a1 = *reinterpret_cast<const uint2*>(ar + m_lo + m_p);
+                const uint2 a2 = *reinterpret_cast<const uint2*>(ar + m_lo + m_hi);
+                const uint2 a3 = *reinterpret_cast<const uint2*>(ar + m_lo + m_hi + m_p);
                 const uint4 b0 = *reinterpret_cast<const uint4*>(br + n_lo);
                 const uint4 b1 = *reinterpret_cast<const uint4*>(br + n_hi);
-                const uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
                 const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
@@ -966,6 +973,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             if (lane == 0) mbar_arrive(&bar_empty[stage]);
         }
         // ---- staged epilogue: out = max(even-k half, odd-k half); int16 elements, 8 per 16-byte global vector
+        if (ti.mswap) {  // the thread pairs its outputs along m_mp instead of m0: exchange the roles of the two bits
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t t = acc[1][j];
+                acc[1][j] = acc[2][j];
+                acc[2][j] = t;
+                t = acc[5][j];
+                acc[5][j] = acc[6][j];
+                acc[6][j] = t;
+            }
+        }
         {
             const int nbr = tm + tn - 2;
             const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
@@ -978,7 +996,10 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     tc |= bit << ti.e_cs[b];
                 }
             }
-            const bool evec = ti.e_vec != 0, efast = ti.e_fast != 0;
+            const bool evec = ti.e_vec != 0;
+            const int ecase = ti.e_fast;  // staging layout (see plan.cpp): 0/1 m-major, 2..4 16-byte vectors per thread
+            const bool efast = ecase != 0;
+            const uint32_t qbase2 = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 4) | ((uint32_t)tnh << (tm + 1));
             uint32_t ts1 = 0, tc1 = 0;
             if (!evec) {
 #pragma unroll
@@ -995,18 +1016,33 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             for (int r = 0; r < 4; ++r) {
                 const int ih = r & 1, jh = r >> 1;
                 T* buf = stg_mem + (r & 1) * G2H_STG_ELEMS;
+                uint32_t W[2][4];  // W[m1][n0 + 2 n1] = outputs (m0 = 0, m0 = 1) as one packed word
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t o[4];
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint32_t w = acc[ih * 4 + i][jh * 4 + j];
-                        o[i] = __vmaxs2(w, __byte_perm(w, 0, 0x1032)) & 0xffffu;  // max of the two halves
+                    for (int i1 = 0; i1 < 2; ++i1) {
+                        const uint32_t w0 = acc[ih * 4 + 2 * i1][jh * 4 + j], w1 = acc[ih * 4 + 2 * i1 + 1][jh * 4 + j];
+                        // max of the two halves (even-k / odd-k partial maxima), then low halves of both
+                        W[i1][j] = __byte_perm(__vmaxs2(w0, __byte_perm(w0, 0, 0x1032)), __vmaxs2(w1, __byte_perm(w1, 0, 0x1032)), 0x5410);
                     }
-                    uint2 v;
-                    v.x = o[0] | (o[1] << 16);
-                    v.y = o[2] | (o[3] << 16);
-                    *reinterpret_cast<uint2*>(buf + stg_swz_h(qbase | ((uint32_t)j << (tm - 1)))) = v;
+                if (ecase <= 1) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint2*>(buf + stg_swz_h(qbase | ((uint32_t)j << (tm - 1)))) = make_uint2(W[0][j], W[1][j]);
+                } else {
+                    uint4 v0, v1;
+                    if (ecase == 2) {  // word order (m1, n0), second vector n1 = 1
+                        v0 = make_uint4(W[0][0], W[1][0], W[0][1], W[1][1]);
+                        v1 = make_uint4(W[0][2], W[1][2], W[0][3], W[1][3]);
+                    } else if (ecase == 3) {  // (n0, m1), second vector n1 = 1
+                        v0 = make_uint4(W[0][0], W[0][1], W[1][0], W[1][1]);
+                        v1 = make_uint4(W[0][2], W[0][3], W[1][2], W[1][3]);
+                    } else {  // (n0, n1), second vector m1 = 1
+                        v0 = make_uint4(W[0][0], W[0][1], W[0][2], W[0][3]);
+                        v1 = make_uint4(W[1][0], W[1][1], W[1][2], W[1][3]);
+                    }
+                    *reinterpret_cast<uint4*>(buf + stg_swz_h(qbase2)) = v0;
+                    *reinterpret_cast<uint4*>(buf + stg_swz_h(qbase2 | 8u)) = v1;
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);

@@ -966,25 +966,86 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 // C-address order.  a_shift[i] = position of the i-th such bit in the shared-memory staging index
                 // ([m bits 0..tm-2 | n bits 0..tn-2]), b_shift[i] = its C shift.  a_shift[30/31] = C shift of the top
                 // m / n tile bit, b_shift[31] = 1 if the two lowest bits are C bits 0,1 (128-bit stores).
+                // packed int16 only: a consumer thread holds the m tile bits {0, mp, tm-1}; mp (a_shift[29], default
+                // 1) is chosen so that the m labels on C bits 0..2 are thread-local, and b_shift[29] = 1 swaps the
+                // roles of m0 and m_mp (the thread pairs outputs along m_mp).  The tables use LOGICAL m positions:
+                // [first local bit, second local bit, the other in-round m bits in ascending order].
                 {
                     const int nbr = c.tm + c.tn - 2;
                     int ent_cs[16], ent_sp[16], ne = 0;
-                    for (int i = 0; i < c.tm - 1; ++i) { ent_cs[ne] = s.c_shift[i]; ent_sp[ne++] = i; }
-                    for (int i = 0; i < c.tn - 1; ++i) { ent_cs[ne] = s.c_shift[c.tm + i]; ent_sp[ne++] = (c.tm - 1) + i; }
-                    for (int i = 1; i < ne; ++i) {
-                        int cs = ent_cs[i], sp = ent_sp[i], j = i - 1;
-                        while (j >= 0 && ent_cs[j] > cs) { ent_cs[j + 1] = ent_cs[j]; ent_sp[j + 1] = ent_sp[j]; --j; }
-                        ent_cs[j + 1] = cs; ent_sp[j + 1] = sp;
+                    auto build = [&](int mp, int mswap) -> int {
+                        int lm[8], nl = 0;  // logical position of the in-round m bit q
+                        lm[mswap ? mp : 0] = nl++;
+                        if (c.tm >= 3) lm[mswap ? 0 : mp] = nl++;
+                        for (int q = 1; q < c.tm - 1; ++q)
+                            if (q != mp) lm[q] = nl++;
+                        ne = 0;
+                        for (int i = 0; i < c.tm - 1; ++i) { ent_cs[ne] = s.c_shift[i]; ent_sp[ne++] = lm[i]; }
+                        for (int i = 0; i < c.tn - 1; ++i) { ent_cs[ne] = s.c_shift[c.tm + i]; ent_sp[ne++] = (c.tm - 1) + i; }
+                        for (int i = 1; i < ne; ++i) {
+                            int cs = ent_cs[i], sp = ent_sp[i], j = i - 1;
+                            while (j >= 0 && ent_cs[j] > cs) { ent_cs[j + 1] = ent_cs[j]; ent_sp[j + 1] = ent_sp[j]; --j; }
+                            ent_cs[j + 1] = cs; ent_sp[j + 1] = sp;
+                        }
+                        const bool evec = half ? (ent_cs[0] == 0 && ent_cs[1] == 1 && ent_cs[2] == 2) : (ent_cs[0] == 0 && ent_cs[1] == 1);
+                        s.b_shift[31] = evec ? 1 : 0;
+                        // ecase != 0: the elements of one 16-byte output vector are also contiguous in the staging
+                        // buffer (one LDS.128 instead of 4 / 8 scalar loads).  int32: 1 = C bits 0,1 are m0,m1.
+                        // packed int16: the thread holds (u, v) x (n0, n1) of a round (u, v = its local m bits), so it
+                        // can write any of the orders C bits (0,1,2) = 1: (u,v,m2)  2: (u,v,n0)  3: (u,n0,v)
+                        // 4: (u,n0,n1) as 16-byte vectors; for 2..4 the staging index is [the three C bits | the fourth
+                        // thread-local bit | m2.. | n2..] and the table holds positions in THAT layout.
+                        int ecase = 0;
+                        if (half) {
+                            const int n0 = c.tm - 1, n1 = c.tm;  // layout-1 staging positions of the n bits 0,1
+                            if (evec && ent_sp[0] == 0) {
+                                if (ent_sp[1] == 1 && ent_sp[2] == 2) ecase = 1;
+                                else if (ent_sp[1] == 1 && ent_sp[2] == n0) ecase = 2;
+                                else if (ent_sp[1] == n0 && ent_sp[2] == 1) ecase = 3;
+                                else if (ent_sp[1] == n0 && ent_sp[2] == n1) ecase = 4;
+                            }
+                            if (ecase >= 2) {
+                                static const int low[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
+                                for (int i = 0; i < ne; ++i) {  // {u, v, n0, n1} -> low[ecase], m q>=2 -> q+2, n unchanged
+                                    const int sp = ent_sp[i];
+                                    if (sp == 0) ent_sp[i] = low[ecase][0];
+                                    else if (sp == 1) ent_sp[i] = low[ecase][1];
+                                    else if (sp == n0) ent_sp[i] = low[ecase][2];
+                                    else if (sp == n1) ent_sp[i] = low[ecase][3];
+                                    else if (sp < n0) ent_sp[i] = sp + 2;
+                                }
+                            }
+                        } else {
+                            ecase = (ent_sp[0] == 0 && ent_sp[1] == 1) ? 1 : 0;
+                        }
+                        return ecase;
+                    };
+                    int mp = 1, mswap = 0;
+                    if (half && c.tm >= 4) {
+                        int q_by_cs[3] = {-1, -1, -1};
+                        for (int q = 0; q < c.tm - 1; ++q)
+                            if (s.c_shift[q] < 3) q_by_cs[s.c_shift[q]] = q;
+                        const int q0 = q_by_cs[0];
+                        if (q0 > 0) {
+                            mp = q0;
+                            mswap = 1;
+                        } else if (q0 == 0) {
+                            const int q1 = q_by_cs[1] > 0 ? q_by_cs[1] : q_by_cs[2];
+                            if (q1 > 1) mp = q1;
+                        }
                     }
-                    for (int i = 0; i < nbr; ++i) { s.a_shift[i] = (uint8_t)ent_sp[i]; s.b_shift[i] = (uint8_t)ent_cs[i]; }
+                    int ecase = build(mp, mswap);
+                    if (ecase == 0 && (mp != 1 || mswap)) {
+                        mp = 1;
+                        mswap = 0;
+                        ecase = build(mp, mswap);
+                    }
+                    s.a_shift[29] = (uint8_t)mp;
+                    s.b_shift[29] = (uint8_t)mswap;
                     s.a_shift[30] = s.c_shift[c.tm - 1];
                     s.a_shift[31] = s.c_shift[c.tm + c.tn - 1];
-                    s.b_shift[31] = half ? ((ent_cs[0] == 0 && ent_cs[1] == 1 && ent_cs[2] == 2) ? 1 : 0)
-                                         : ((ent_cs[0] == 0 && ent_cs[1] == 1) ? 1 : 0);
-                    // b_shift[30] = 1: the elements of one 16-byte output vector are also contiguous in the staging
-                    // buffer (one LDS.128 instead of 4 / 8 scalar loads)
-                    s.b_shift[30] = half ? ((ent_sp[0] == 0 && ent_sp[1] == 1 && ent_sp[2] == 2) ? 1 : 0)
-                                         : ((ent_sp[0] == 0 && ent_sp[1] == 1) ? 1 : 0);
+                    s.b_shift[30] = (uint8_t)ecase;
+                    for (int i = 0; i < nbr; ++i) { s.a_shift[i] = (uint8_t)ent_sp[i]; s.b_shift[i] = (uint8_t)ent_cs[i]; }
                 }
                 // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
                 // (bit 0 if stores are scalar) on the low lane bits

@@ -149,13 +149,47 @@ def run_plan(plan):
                         assert s["c_shift"][tm] == 0 and s["c_shift"][tm + 1] == 1
                     # staged-epilogue tables: sorted in-round tile bits
                     nbr = tm + tn - 2
-                    ent = sorted([(int(s["c_shift"][i]), i) for i in range(tm - 1)] +
-                                 [(int(s["c_shift"][tm + i]), (tm - 1) + i) for i in range(tn - 1)])
+                    cs = [int(x) for x in s["c_shift"]]
+                    n0, n1 = tm - 1, tm
+
+                    def build(mp, mswap):
+                        # logical m positions: [first local bit, second local bit, the others ascending]
+                        order = ([mp, 0] if mswap else [0, mp]) + [q for q in range(1, tm - 1) if q != mp]
+                        lm = {q: k for k, q in enumerate(order)}
+                        ent = sorted([(cs[i], lm[i]) for i in range(tm - 1)] + [(cs[tm + i], (tm - 1) + i) for i in range(tn - 1)])
+                        sp = [e[1] for e in ent]
+                        ecase = 0
+                        if vt == 3:
+                            if [e[0] for e in ent[:3]] == [0, 1, 2] and sp[0] == 0:
+                                ecase = {(1, 2): 1, (1, n0): 2, (n0, 1): 3, (n0, n1): 4}.get((sp[1], sp[2]), 0)
+                            if ecase >= 2:
+                                low = {2: (0, 1, 2, 3), 3: (0, 2, 1, 3), 4: (0, 3, 1, 2)}[ecase]
+                                m = {0: low[0], 1: low[1], n0: low[2], n1: low[3]}
+                                sp = [m[x] if x in m else (x + 2 if x < n0 else x) for x in sp]
+                                assert sorted(sp) == list(range(nbr)) and sp[:3] == [0, 1, 2]
+                        else:
+                            ecase = int(sp[:2] == [0, 1])
+                        return ecase, ent, sp
+
+                    mp, mswap = 1, 0
+                    if vt == 3 and tm >= 4:
+                        q_by_cs = {cs[q]: q for q in range(tm - 1) if cs[q] < 3}
+                        q0 = q_by_cs.get(0, -1)
+                        if q0 > 0:
+                            mp, mswap = q0, 1
+                        elif q0 == 0:
+                            q1 = q_by_cs[1] if q_by_cs.get(1, -1) > 0 else q_by_cs.get(2, -1)
+                            if q1 > 1:
+                                mp = q1
+                    ecase, ent, sp = build(mp, mswap)
+                    if ecase == 0 and (mp != 1 or mswap):
+                        mp, mswap = 1, 0
+                        ecase, ent, sp = build(mp, mswap)
+                    assert (int(s["a_shift"][29]), int(s["b_shift"][29])) == (mp, mswap)
                     assert [int(x) for x in s["b_shift"][:nbr]] == [e[0] for e in ent]
-                    assert [int(x) for x in s["a_shift"][:nbr]] == [e[1] for e in ent]
-                    assert int(s["a_shift"][30]) == int(s["c_shift"][tm - 1]) and int(s["a_shift"][31]) == int(s["c_shift"][tm + tn - 1])
-                    nlow = 3 if vt == 3 else 2
-                    assert int(s["b_shift"][30]) == int([e[1] for e in ent[:nlow]] == list(range(nlow)))
+                    assert int(s["a_shift"][30]) == cs[tm - 1] and int(s["a_shift"][31]) == cs[tm + tn - 1]
+                    assert int(s["b_shift"][30]) == ecase
+                    assert [int(x) for x in s["a_shift"][:nbr]] == sp
                     if vt == 3:
                         assert int(s["b_shift"][31]) == int([e[0] for e in ent[:3]] == [0, 1, 2])
                     else:
