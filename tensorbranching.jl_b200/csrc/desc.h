@@ -88,7 +88,7 @@ struct SubInst {           // one fused subtree of one branch
     const void* pool;
     void* out;             // arena address of the result
     uint32_t n_steps;
-    uint32_t pad;
+    uint32_t n_pool;       // pool slots to stage in shared memory (0: read the pool from global memory)
 };
 struct BigInst {           // one non-fused step of one branch
     const BigStep* step;

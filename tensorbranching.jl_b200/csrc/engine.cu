@@ -272,6 +272,7 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
     return TB_OK;
 }
 
+constexpr uint32_t kFusedSmemMax = 96 * 1024;  // dynamic shared memory limit of k_fused_subtrees (descriptors + pool + data)
 struct Launch {
     int lane;        // stream lane the launch goes to
     int kind;        // 0 fused, 1 generic, 2 gemm, 3 finalize
@@ -440,7 +441,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             L.kind = 0;
             L.vt = vt;
             L.inst_off = host.size();
-            uint32_t smem_elems = 0;
+            uint32_t smem_elems = 0;  // largest shared-memory footprint of a subtree (bytes)
             std::vector<SubInst> insts;
             for (size_t m = 0; m < w.members.size(); ++m) {
                 const Plan& P = plans[w.members[m]]->p;
@@ -452,14 +453,21 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                     si.pool = blob;
                     si.out = ab + st.out_off * elem;
                     si.n_steps = st.n_steps;
+                    si.n_pool = P.pool.size() <= 4096 ? (uint32_t)P.pool.size() : 0u;
+                    uint32_t need = fused_desc_bytes(si.n_steps) + fused_pool_bytes(si.n_pool, (uint32_t)elem) + st.smem_elems * (uint32_t)elem;
+                    if (need > kFusedSmemMax) {  // drop the pool copy first
+                        si.n_pool = 0;
+                        need = fused_desc_bytes(si.n_steps) + st.smem_elems * (uint32_t)elem;
+                        if (need > kFusedSmemMax) return set_err(ctx, TB_ERR_UNSUPPORTED, "a fused subtree has too many steps for shared memory");
+                    }
                     insts.push_back(si);
-                    smem_elems = std::max(smem_elems, st.smem_elems);
+                    smem_elems = std::max(smem_elems, need);
                 }
             }
             if (!insts.empty()) {
                 L.n_insts = (int)insts.size();
                 L.grid = (uint32_t)insts.size();
-                L.smem = std::max<uint32_t>(smem_elems * (uint32_t)elem, 16);
+                L.smem = std::max<uint32_t>(smem_elems, 16);  // bytes: descriptors + pool copy + data
                 size_t o = host.size();
                 host.resize(o + insts.size() * sizeof(SubInst));
                 std::memcpy(host.data() + o, insts.data(), insts.size() * sizeof(SubInst));
@@ -773,8 +781,9 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
         TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->side[l], cudaStreamNonBlocking));
         TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_join[l], cudaEventDisableTiming));
     }
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));

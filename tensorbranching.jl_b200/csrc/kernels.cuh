@@ -87,13 +87,20 @@ __device__ __forceinline__ uint32_t scatter_bits(uint32_t x, const uint8_t* sh, 
     return off;
 }
 
-// largest idx with starts[idx] <= b
+// largest idx with starts[idx] <= b (starts[0] == 0).  Called by all 32 lanes of a converged warp: a 32-ary search,
+// 2-3 dependent loads instead of the ~12 of a binary search (the search sits at the head of every CTA / tile).
 __device__ __forceinline__ int find_inst(const uint32_t* __restrict__ starts, int n, uint32_t b) {
-    int lo = 0, hi = n - 1;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (__ldg(starts + mid) <= b) lo = mid;
-        else hi = mid - 1;
+    const int lane = threadIdx.x & 31;
+    int lo = 0, len = n;
+    while (len > 1) {
+        const int stride = (len + 31) >> 5;
+        const int pos = lo + lane * stride;
+        const bool le = pos < lo + len && __ldg(starts + pos) <= b;
+        const unsigned m = __ballot_sync(0xffffffffu, le);  // monotone; lane 0 is always set
+        const int j = 31 - __clz((int)m);
+        const int hi = lo + len;
+        lo += j * stride;
+        len = min(stride, hi - lo);
     }
     return lo;
 }
@@ -103,22 +110,38 @@ __device__ __forceinline__ int find_inst(const uint32_t* __restrict__ starts, in
 // ------------------------------------------------------------------------------------------------
 constexpr int FUSED_THREADS = 128;
 
+// Dynamic shared memory of one CTA: [all step descriptors of the subtree | a copy of the branch's leaf pool | data].
+// Descriptors and pool arrive with one round of wide loads, after that a step only touches shared memory (the
+// subtrees are ~25 steps of 4..32 outputs each: latency, not throughput, is what a step costs).
+__host__ __device__ inline uint32_t fused_desc_bytes(uint32_t n_steps) { return n_steps * (uint32_t)sizeof(SubStep); }
+__host__ __device__ inline uint32_t fused_pool_bytes(uint32_t n_pool, uint32_t elem) { return (n_pool * elem + 15u) & ~15u; }
+
 template <typename T>
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst* __restrict__ insts, int n_insts) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
-    T* smem = reinterpret_cast<T*>(dyn_smem);
-    __shared__ uint32_t s_desc[2][12];
     if ((int)blockIdx.x >= n_insts) return;
     const SubInst inst = insts[blockIdx.x];
     const int tid = threadIdx.x;
+    {
+        const uint4* g = reinterpret_cast<const uint4*>(inst.steps);
+        uint4* sdst = reinterpret_cast<uint4*>(dyn_smem);
+        const uint32_t nv = inst.n_steps * (uint32_t)(sizeof(SubStep) / 16);
+        for (uint32_t i = tid; i < nv; i += FUSED_THREADS) sdst[i] = __ldg(g + i);
+    }
+    const uint32_t dbytes = fused_desc_bytes(inst.n_steps);
     const T* pool = reinterpret_cast<const T*>(inst.pool);
+    if (inst.n_pool) {  // pool slots come in multiples of 4: 8-byte granules for every value type
+        const uint2* g = reinterpret_cast<const uint2*>(inst.pool);
+        uint2* sdst = reinterpret_cast<uint2*>(dyn_smem + dbytes);
+        const uint32_t nv = inst.n_pool * (uint32_t)sizeof(T) / 8u;
+        for (uint32_t i = tid; i < nv; i += FUSED_THREADS) sdst[i] = __ldg(g + i);
+        pool = reinterpret_cast<const T*>(dyn_smem + dbytes);
+    }
+    T* smem = reinterpret_cast<T*>(dyn_smem + dbytes + fused_pool_bytes(inst.n_pool, sizeof(T)));
     T* out = reinterpret_cast<T*>(inst.out);
-    const uint32_t* gdesc = reinterpret_cast<const uint32_t*>(inst.steps);
-    if (tid < 12) s_desc[0][tid] = __ldg(gdesc + tid);
     __syncthreads();
     for (uint32_t st = 0; st < inst.n_steps; ++st) {
-        const SubStep& d = *reinterpret_cast<const SubStep*>(s_desc[st & 1]);
-        if (st + 1 < inst.n_steps && tid < 12) s_desc[(st + 1) & 1][tid] = __ldg(gdesc + (st + 1) * 12 + tid);
+        const SubStep& d = reinterpret_cast<const SubStep*>(dyn_smem)[st];
         const T* A = (d.a_loc == LOC_SMEM ? smem : pool) + d.a_off;
         const T* B = (d.b_loc == LOC_SMEM ? smem : pool) + d.b_off;
         T* C = (d.c_loc == LOC_SMEM) ? smem + d.c_off : out;
@@ -812,6 +835,7 @@ struct TileInfoH {
     int tm, tn, kc, nchunks, valid, lane_n_first;
     unsigned char e_spos[14], e_cs[14];
     unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast, mp, mswap;
+    int inst;  // index of the (branch, step) instance in this launch: consumers cache per-step values on it
 };
 __device__ __forceinline__ uint32_t stg_swz_h(uint32_t x) { return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7u) << 3); }
 
@@ -896,6 +920,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 ti.e_fast = d->b_shift[30];
                 ti.mp = d->a_shift[29];
                 ti.mswap = d->b_shift[29];
+                ti.inst = idx;
                 ti.valid = 1;
             }
             __syncwarp();
@@ -924,6 +949,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
     const int ctid = tid - G2_PRODUCERS;
     const int lane = tid & 31;
     unsigned it = 0;
+    int ep_inst = -1;  // the step whose epilogue offsets (ts, tc) this thread holds
+    uint32_t ts = 0, tc = 0;
     for (unsigned tcount = 0;; ++tcount) {
         const int slot = tcount & 1;
         mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
@@ -987,13 +1014,16 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         {
             const int nbr = tm + tn - 2;
             const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
-            uint32_t ts = 0, tc = 0;
+            if (ti.inst != ep_inst) {  // consecutive tiles of a persistent CTA mostly belong to the same step
+                ep_inst = ti.inst;
+                ts = tc = 0;
 #pragma unroll
-            for (int b = 3; b < 11; ++b) {
-                const uint32_t bit = ((uint32_t)ctid >> (b - 3)) & 1u;
-                if (b < nbr) {
-                    ts |= bit << ti.e_spos[b];
-                    tc |= bit << ti.e_cs[b];
+                for (int b = 3; b < 11; ++b) {
+                    const uint32_t bit = ((uint32_t)ctid >> (b - 3)) & 1u;
+                    if (b < nbr) {
+                        ts |= bit << ti.e_spos[b];
+                        tc |= bit << ti.e_cs[b];
+                    }
                 }
             }
             const bool evec = ti.e_vec != 0;
