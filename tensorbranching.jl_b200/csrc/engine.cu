@@ -43,6 +43,7 @@ struct BlobChunk {
 }  // namespace
 
 struct tb_ctx {
+    std::thread reaper;  // frees the host side of the previous tb_contract_networks call's temporary plans
     tb_options opts{};
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -333,7 +334,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     } else if (rc) {
         return rc;
     }
-    const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 64;
+    const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;  // profiles/s03_wave_lane_sweep_cfg2.jsonl
     const int NL = (ctx->profile || single_plan_mode) ? 1 : ctx->n_lanes;
     // try to grow the arena so that NL full waves fit (bounded by the configured limit)
     {
@@ -806,6 +807,7 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
 
 int tb_shutdown(tb_ctx* ctx) {
     if (!ctx) return TB_OK;
+    if (ctx->reaper.joinable()) ctx->reaper.join();
     cudaSetDevice(ctx->device);
     sync_all_lanes(ctx);
     if (ctx->arena) cudaFree(ctx->arena);
@@ -948,12 +950,14 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     };
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
-    const int64_t batch = std::max<int64_t>(256, (int64_t)(ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 64) * ctx->n_lanes * 2);
+    const int64_t batch_max = std::max<int64_t>(256, (int64_t)(ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128) * ctx->n_lanes);
     std::vector<int32_t> status((size_t)n, TB_OK);
     bool any = false;
     double t_wait = 0;
-    for (int64_t lo = 0; lo < n && rc == TB_OK; lo += batch) {
-        const int64_t hi = std::min(n, lo + batch);
+    // small first batches: the GPU starts after ~64 compiled plans instead of a full batch (pipeline fill)
+    int64_t batch = std::min<int64_t>(batch_max, 64);
+    for (int64_t lo = 0, hi = 0; lo < n && rc == TB_OK; lo = hi, batch = std::min(batch_max, batch * 2)) {
+        hi = std::min(n, lo + batch);
         const double tw0 = now_ms();
         if (nthreads == 1) {
             while (next.load() < hi && next.load() < n) {  // single-threaded: compile this batch inline
@@ -1013,20 +1017,11 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
             p->p.d_blob = nullptr;
             p->p.owner = nullptr;
         }
-    {
-        std::atomic<int64_t> nx{0};
-        auto killer = [&]() {
-            for (;;) {
-                int64_t i = nx.fetch_add(64);
-                if (i >= n) break;
-                for (int64_t q = i; q < std::min<int64_t>(n, i + 64); ++q) delete plans[q];
-            }
-        };
-        std::vector<std::thread> th2;
-        for (int t = 1; t < nthreads; ++t) th2.emplace_back(killer);
-        killer();
-        for (auto& t : th2) t.join();
-    }
+    // host side: off the caller's critical path (joined by the next call / tb_shutdown)
+    if (ctx->reaper.joinable()) ctx->reaper.join();
+    ctx->reaper = std::thread([dead = std::move(plans)]() {
+        for (tb_plan* p : dead) delete p;
+    });
     ctx->host_ms[4] = now_ms() - t_d0;
     ctx->host_ms[5] = now_ms() - t_c0;
     return rc;

@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "desc.h"
+#include <type_traits>
 
 namespace tb {
 
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst*
 constexpr int BIG_THREADS = 256;
 
 template <typename T>
-__global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restrict__ insts,
+__global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __restrict__ insts,
                                                          const uint32_t* __restrict__ tile_starts, int n_insts) {
     __shared__ BigStep sd;
     __shared__ T s_red[BIG_THREADS];
@@ -215,39 +216,60 @@ __global__ void __launch_bounds__(BIG_THREADS) k_generic(const BigInst* __restri
         const uint32_t kmask = (1u << nk) - 1u, amask = (1u << (nk + nka)) - 1u;
         const uint32_t n_red = 1u << nkt;
         const int sa = sd.sa, sb = sd.sb;
-        const int n_it = 1 << (po - 10);  // vectors per thread
-        for (int vi = 0; vi < n_it; ++vi) {
-        const uint32_t c4 = ((((tile << (po - 10)) + (uint32_t)vi) << 8) | (uint32_t)tid) << 2;
-        const uint32_t offA = scatter_bits(c4, sd.a_shift, rc), offB = scatter_bits(c4, sd.b_shift, rc);
-        T acc[4] = {Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf(), Ops<T>::neg_inf()};
         const bool kfirst = sd.store_mode != 0;  // generic steps: K0-first operand layouts
-        for (uint32_t r = 0; r < n_red; ++r) {
-            const uint32_t ra = offA + (kfirst ? ((r & 1u) | ((r >> 1) << (sa + 1))) : ((r & amask) << sa));
-            const uint32_t rb = offB + (kfirst ? ((r & 1u) | ((r >> 1) << (sb + 1))) : (((r & kmask) | ((r >> (nk + nka)) << nk)) << sb));
-            T av[4], bv[4];
-            if (modeA == OPV_VEC) {
-                const vec4 v = *reinterpret_cast<const vec4*>(A + ra);
-                av[0] = v.x; av[1] = v.y; av[2] = v.z; av[3] = v.w;
-            } else if (modeA == OPV_BCAST) {
-                av[0] = av[1] = av[2] = av[3] = A[ra];
-            } else {
-                av[0] = A[ra]; av[1] = A[ra + dA1]; av[2] = A[ra + dA2]; av[3] = A[ra + dA1 + dA2];
+        // NV vectors per thread; the reduction loop is outermost so that the loads of all NV vectors are in flight
+        // together (these nodes stream: memory-level parallelism is what bounds them)
+        auto vectors = [&](auto nv_tag) {
+            constexpr int NV = decltype(nv_tag)::value;
+            uint32_t c4[NV], offA[NV], offB[NV];
+            T acc[NV][4];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                c4[v] = ((((tile * NV) + (uint32_t)v) << 8) | (uint32_t)tid) << 2;
+                offA[v] = scatter_bits(c4[v], sd.a_shift, rc);
+                offB[v] = scatter_bits(c4[v], sd.b_shift, rc);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[v][q] = Ops<T>::neg_inf();
             }
-            if (modeB == OPV_VEC) {
-                const vec4 v = *reinterpret_cast<const vec4*>(B + rb);
-                bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
-            } else if (modeB == OPV_BCAST) {
-                bv[0] = bv[1] = bv[2] = bv[3] = B[rb];
-            } else {
-                bv[0] = B[rb]; bv[1] = B[rb + dB1]; bv[2] = B[rb + dB2]; bv[3] = B[rb + dB1 + dB2];
+            for (uint32_t r = 0; r < n_red; ++r) {
+                const uint32_t ra = kfirst ? ((r & 1u) | ((r >> 1) << (sa + 1))) : ((r & amask) << sa);
+                const uint32_t rb = kfirst ? ((r & 1u) | ((r >> 1) << (sb + 1))) : (((r & kmask) | ((r >> (nk + nka)) << nk)) << sb);
+                T av[NV][4], bv[NV][4];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    const T* pa = A + offA[v] + ra;
+                    const T* pb = B + offB[v] + rb;
+                    if (modeA == OPV_VEC) {
+                        const vec4 x = *reinterpret_cast<const vec4*>(pa);
+                        av[v][0] = x.x; av[v][1] = x.y; av[v][2] = x.z; av[v][3] = x.w;
+                    } else if (modeA == OPV_BCAST) {
+                        av[v][0] = av[v][1] = av[v][2] = av[v][3] = pa[0];
+                    } else {
+                        av[v][0] = pa[0]; av[v][1] = pa[dA1]; av[v][2] = pa[dA2]; av[v][3] = pa[dA1 + dA2];
+                    }
+                    if (modeB == OPV_VEC) {
+                        const vec4 x = *reinterpret_cast<const vec4*>(pb);
+                        bv[v][0] = x.x; bv[v][1] = x.y; bv[v][2] = x.z; bv[v][3] = x.w;
+                    } else if (modeB == OPV_BCAST) {
+                        bv[v][0] = bv[v][1] = bv[v][2] = bv[v][3] = pb[0];
+                    } else {
+                        bv[v][0] = pb[0]; bv[v][1] = pb[dB1]; bv[v][2] = pb[dB2]; bv[v][3] = pb[dB1 + dB2];
+                    }
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[v][q] = Ops<T>::addmax(av[v][q], bv[v][q], acc[v][q]);
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) acc[q] = Ops<T>::addmax(av[q], bv[q], acc[q]);
-        }
-        vec4 o;
-        o.x = acc[0]; o.y = acc[1]; o.z = acc[2]; o.w = acc[3];
-        *reinterpret_cast<vec4*>(C + c4) = o;
-        }
+            for (int v = 0; v < NV; ++v) {
+                vec4 o;
+                o.x = acc[v][0]; o.y = acc[v][1]; o.z = acc[v][2]; o.w = acc[v][3];
+                *reinterpret_cast<vec4*>(C + c4[v]) = o;
+            }
+        };
+        if (po == 12) vectors(std::integral_constant<int, 4>{});
+        else vectors(std::integral_constant<int, 1>{});
         return;
     }
     // thread -> (output, k-part): 2^po outputs per CTA, 2^ks threads share one output
