@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtbcuda.so")
+LIB_PATH = os.environ.get("TBCUDA_LIB") or os.path.join(_HERE, "libtbcuda.so")  # TBCUDA_LIB: diagnostics builds (e.g. -DTB_KPROF)
 
 TB_OK = 0
 TB_ERR_BAD_ARGUMENT = -1

@@ -808,6 +808,16 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
 int tb_shutdown(tb_ctx* ctx) {
     if (!ctx) return TB_OK;
     if (ctx->reaper.joinable()) ctx->reaper.join();
+#ifdef TB_KPROF
+    {
+        cudaSetDevice(ctx->device);
+        cudaDeviceSynchronize();
+        unsigned long long h[8] = {0};
+        cudaMemcpyFromSymbol(h, g_kprof, sizeof h);
+        fprintf(stderr, "KPROF k_gemm2h consumer cycles: wait_tile %.3e wait_data %.3e main %.3e epilogue %.3e lifetime %.3e tiles %llu\n",
+                (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4], h[5]);
+    }
+#endif
     cudaSetDevice(ctx->device);
     sync_all_lanes(ctx);
     if (ctx->arena) cudaFree(ctx->arena);

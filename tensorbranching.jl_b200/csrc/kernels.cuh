@@ -545,6 +545,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // INSIDE a CTA's own pool (SASS: USETMAXREG...CTAPOOL), so 128*P + 256*C <= 384*80 must hold or the .inc never
 // succeeds (a silent hang).  P = 24 (producer warpgroup), C = 104 (consumer warpgroups): 3072 + 26624 = 29696.
 static_assert(128 * 24 + 256 * 104 <= 384 * 80, "setmaxnreg budget exceeds the CTA pool");
+static_assert(128 * 32 + 256 * 104 <= 384 * 80, "setmaxnreg budget of k_gemm2h exceeds the CTA pool");
 template <typename T>
 __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter,
@@ -850,6 +851,12 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
 // partial maxima: per k-pair 2 x LDS.128 (A: 8 words) + 2 x LDS.128 (B: 8 words) and 64 VIADDMNMX.S16x2 = 128
 // tropical ops, no operand duplication.  The epilogue takes max(lo, hi) per accumulator and stores int16.
 // ------------------------------------------------------------------------------------------------
+#ifdef TB_KPROF
+// diagnostics build: SM-cycle accounting of k_gemm2h consumers (warp 0 of the consumers of every CTA)
+// [0] waiting for a tile descriptor  [1] waiting for operand stages  [2] main loop  [3] epilogue  [4] CTA lifetime  [5] tiles
+__device__ unsigned long long g_kprof[8];
+#endif
+constexpr int G2H_TSLOTS = 4;  // tile descriptors the producer may publish ahead of the consumers
 constexpr int G2H_STG_ELEMS = 4096;  // int16 elements of one staged quarter of a 128 x 128 tile (8 KB)
 struct TileInfoH {
     long long cbase[32];
@@ -868,15 +875,16 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);                       // G2_STAGES x 16 KB
     T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);         // 2 x 16 KB
     constexpr int STAGE_ELEMS = GEMM_STAGE_ELEMS * 2;                    // int16 elements per stage
-    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2];
-    __shared__ TileInfoH tinfo[2];
+    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[G2H_TSLOTS], bar_tempty[G2H_TSLOTS];
+    __shared__ TileInfoH tinfo[G2H_TSLOTS];
+    __shared__ __align__(16) BigStep s_step;  // the producer's copy of the current step descriptor
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < G2_STAGES; ++i) {
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_empty[i], G2_CONSUMERS / 32);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < G2H_TSLOTS; ++i) {
             mbar_init(&bar_tfull[i], 1);
             mbar_init(&bar_tempty[i], G2_CONSUMERS / 32);
         }
@@ -885,16 +893,23 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
     __syncthreads();
 
     if (tid < G2_PRODUCERS) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n" ::);
         if (tid >= 32) return;
         const int lane = tid;
         unsigned it = 0;
+        // the tile counter is read one tile ahead (the atomic's latency overlaps the current tile's set-up), and the
+        // step descriptor is decoded once per (branch, step) instance into shared memory: consecutive tiles mostly
+        // belong to the same instance
+        unsigned tile_next = 0;
+        if (lane == 0) tile_next = atomicAdd(counter, 1u);
+        uint32_t cur_start = 1, cur_end = 0;  // tile range of the cached instance (empty)
+        int cur_idx = -1;
+        const unsigned char* cur_arena = nullptr;
         for (unsigned tcount = 0;; ++tcount) {
-            unsigned tile_g = 0;
-            if (lane == 0) tile_g = atomicAdd(counter, 1u);
-            tile_g = __shfl_sync(0xffffffffu, tile_g, 0);
-            const int slot = tcount & 1;
-            mbar_wait(&bar_tempty[slot], ((tcount >> 1) & 1) ^ 1);
+            const unsigned tile_g = __shfl_sync(0xffffffffu, tile_next, 0);
+            if (lane == 0 && tile_g < total_tiles) tile_next = atomicAdd(counter, 1u);
+            const int slot = tcount % G2H_TSLOTS;
+            mbar_wait(&bar_tempty[slot], ((tcount / G2H_TSLOTS) & 1) ^ 1);
             if (tile_g >= total_tiles) {
                 if (lane == 0) {
                     tinfo[slot].valid = 0;
@@ -902,14 +917,25 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 }
                 break;
             }
-            const int idx = find_inst(tile_starts, n_insts, tile_g);
-            const BigInst inst = insts[idx];
-            const uint32_t tile = tile_g - __ldg(tile_starts + idx);
-            const BigStep* __restrict__ d = inst.step;
+            if (tile_g < cur_start || tile_g >= cur_end) {
+                cur_idx = find_inst(tile_starts, n_insts, tile_g);
+                const BigInst inst = insts[cur_idx];
+                cur_start = __ldg(tile_starts + cur_idx);
+                cur_arena = reinterpret_cast<const unsigned char*>(inst.arena);
+                const uint32_t* gs = reinterpret_cast<const uint32_t*>(inst.step);
+                uint32_t* ss = reinterpret_cast<uint32_t*>(&s_step);
+                for (int w = lane; w < (int)(sizeof(BigStep) / 4); w += 32) ss[w] = __ldg(gs + w);
+                __syncwarp();
+                cur_end = cur_start + s_step.n_tiles;
+            }
+            const int idx = cur_idx;
+            const uint32_t tile = tile_g - cur_start;
+            const BigStep* d = &s_step;
+            const unsigned char* arena = cur_arena;
             const int tm = d->tm, tn = d->tn, nk = d->nk, kc = d->kc, ng = d->ng;
             const int s_log = 8 - (tm + tn - 6), S = 1 << s_log;
-            const T* Ag = reinterpret_cast<const T*>(inst.arena) + d->a_off;
-            const T* Bg = reinterpret_cast<const T*>(inst.arena) + d->b_off;
+            const T* Ag = reinterpret_cast<const T*>(arena) + d->a_off;
+            const T* Bg = reinterpret_cast<const T*>(arena) + d->b_off;
             long long ab = -1, bb = -1, cb = -1;
             if (lane < S) {
                 const unsigned long long g = (unsigned long long)tile * S + lane;
@@ -930,7 +956,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 ti.e_cs[lane] = d->b_shift[lane];
             }
             if (lane == 0) {
-                ti.C = reinterpret_cast<T*>(inst.arena) + d->c_off;
+                ti.C = const_cast<T*>(reinterpret_cast<const T*>(arena)) + d->c_off;
                 ti.tm = tm;
                 ti.tn = tn;
                 ti.kc = kc;
@@ -973,9 +999,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
     unsigned it = 0;
     int ep_inst = -1;  // the step whose epilogue offsets (ts, tc) this thread holds
     uint32_t ts = 0, tc = 0;
+#ifdef TB_KPROF
+    long long kp_t0 = clock64(), kp_last = kp_t0, kp_acc[4] = {0, 0, 0, 0};
+    unsigned kp_tiles = 0;
+#define KP(i) { const long long n_ = clock64(); kp_acc[i] += n_ - kp_last; kp_last = n_; }
+#else
+#define KP(i)
+#endif
     for (unsigned tcount = 0;; ++tcount) {
-        const int slot = tcount & 1;
-        mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
+        const int slot = tcount % G2H_TSLOTS;
+        mbar_wait(&bar_tfull[slot], (tcount / G2H_TSLOTS) & 1);
+        KP(0)
         const TileInfoH& ti = tinfo[slot];
         if (!ti.valid) break;
         const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
@@ -988,29 +1022,36 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         const int mp = ti.mp;
         const int tmw = ((tmh & ((1 << (mp - 1)) - 1)) << 1) | ((tmh >> (mp - 1)) << (mp + 1));  // word offset
         const int m_lo = tmw * 2, m_p = 2 << mp, m_hi = 2 << (tm - 1);  // int16 offsets inside a row
-        const int n_lo = tnh * 8, n_hi = (2 << (tn - 1)) + tnh * 8;
+        const int n_lo = tnh * 8;
         const int la = kc + tm, lb = kc + tn;
         uint32_t acc[8][8];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0xC000C000u;  // (-2^14, -2^14)
+        // per-thread shared-memory byte addresses of its A / B words in stage 0, k-pair row 0; everything added inside
+        // the loops is warp-uniform
+        const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage_mem);
+        const uint32_t a_thr = stage_base + ((((uint32_t)sub << la) + (uint32_t)m_lo) << 1);
+        const uint32_t b_thr = stage_base + ((((uint32_t)S << la) + ((uint32_t)sub << lb) + (uint32_t)n_lo) << 1);
+        const uint32_t a_p = (uint32_t)m_p << 1, a_hi = (uint32_t)m_hi << 1, b_hi = 4u << (tn - 1);
+        const uint32_t rowA = 4u << tm, rowB = 4u << tn;  // bytes per k-pair row
         for (int ch = 0; ch < nchunks; ++ch, ++it) {
             const int stage = it % G2_STAGES;
             mbar_wait(&bar_full[stage], (it / G2_STAGES) & 1);
-            const T* sA = stage_mem + stage * STAGE_ELEMS + ((size_t)sub << la);
-            const T* sB = stage_mem + stage * STAGE_ELEMS + ((size_t)S << la) + ((size_t)sub << lb);
-            const int KP = 1 << (kc - 1);  // k-pair rows in this chunk
+            KP(1)
+            const int KP_ROWS = 1 << (kc - 1);  // k-pair rows in this chunk
+            uint32_t ua = (uint32_t)stage * (uint32_t)(STAGE_ELEMS * 2), ub = ua;
 #pragma unroll 1
-            for (int kk = 0; kk < KP; ++kk) {
-                const T* ar = sA + (kk << (tm + 1));
-                const T* br = sB + (kk << (tn + 1));
-                const uint2 a0 = *reinterpret_cast<const uint2*>(ar + m_lo);
-                const uint2 a1 = *reinterpret_cast<const uint2*>(ar + m_lo + m_p);
-                const uint2 a2 = *reinterpret_cast<const uint2*>(ar + m_lo + m_hi);
-                const uint2 a3 = *reinterpret_cast<const uint2*>(ar + m_lo + m_hi + m_p);
-                const uint4 b0 = *reinterpret_cast<const uint4*>(br + n_lo);
-                const uint4 b1 = *reinterpret_cast<const uint4*>(br + n_hi);
+            for (int kk = 0; kk < KP_ROWS; ++kk, ua += rowA, ub += rowB) {
+                uint2 a0, a1, a2, a3;
+                uint4 b0, b1;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0.x), "=r"(a0.y) : "r"(a_thr + ua));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a1.x), "=r"(a1.y) : "r"(a_thr + ua + a_p));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a2.x), "=r"(a2.y) : "r"(a_thr + ua + a_hi));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a3.x), "=r"(a3.y) : "r"(a_thr + ua + a_hi + a_p));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0.x), "=r"(b0.y), "=r"(b0.z), "=r"(b0.w) : "r"(b_thr + ub));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b1.x), "=r"(b1.y), "=r"(b1.z), "=r"(b1.w) : "r"(b_thr + ub + b_hi));
                 const uint32_t a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
                 const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -1020,19 +1061,11 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[stage]);
+            KP(2)
         }
-        // ---- staged epilogue: out = max(even-k half, odd-k half); int16 elements, 8 per 16-byte global vector
-        if (ti.mswap) {  // the thread pairs its outputs along m_mp instead of m0: exchange the roles of the two bits
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint32_t t = acc[1][j];
-                acc[1][j] = acc[2][j];
-                acc[2][j] = t;
-                t = acc[5][j];
-                acc[5][j] = acc[6][j];
-                acc[6][j] = t;
-            }
-        }
+        // ---- staged epilogue: out = max(even-k half, odd-k half); int16 elements, 8 per 16-byte global vector.
+        // Everything that does not depend on the round is computed once per tile (the ALU pipe that executes these
+        // instructions is the one the main loop's VIADDMNMX need).
         {
             const int nbr = tm + tn - 2;
             const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
@@ -1050,8 +1083,38 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             }
             const bool evec = ti.e_vec != 0;
             const int ecase = ti.e_fast;  // staging layout (see plan.cpp): 0/1 m-major, 2..4 16-byte vectors per thread
-            const bool efast = ecase != 0;
-            const uint32_t qbase2 = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 4) | ((uint32_t)tnh << (tm + 1));
+            const bool mswap = ti.mswap != 0;  // the thread pairs its outputs along m_mp instead of m0
+            T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
+            const uint32_t stg_base = (uint32_t)__cvta_generic_to_shared(stg_mem);
+            // staging write addresses (bytes, buffer 0)
+            uint32_t w_addr[4];
+            if (ecase <= 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w_addr[j] = stg_base + (stg_swz_h(qbase | ((uint32_t)j << (tm - 1))) << 1);
+            } else {
+                const uint32_t qbase2 = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 4) | ((uint32_t)tnh << (tm + 1));
+                w_addr[0] = stg_base + (stg_swz_h(qbase2) << 1);
+                w_addr[1] = w_addr[0] ^ 16u;  // staging index bit 3 (the swizzle never reads it)
+                w_addr[2] = w_addr[3] = 0;
+            }
+            // read side of the 128-bit path: two vectors per thread and round
+            uint32_t r_addr[2] = {0, 0};
+            T* g_ptr[2] = {nullptr, nullptr};
+            if (evec && ecase != 0) {
+#pragma unroll
+                for (int itr = 0; itr < 2; ++itr) {
+                    const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
+                    const uint32_t sub_e = e8 >> nbr;
+                    uint32_t so = ts, co = tc;
+                    if (11 < nbr) {
+                        so |= (uint32_t)itr << ti.e_spos[11];
+                        co |= (uint32_t)itr << ti.e_cs[11];
+                    }
+                    const long long cb = ti.cbase[sub_e];
+                    r_addr[itr] = stg_base + (stg_swz_h(so | (sub_e << nbr)) << 1);
+                    g_ptr[itr] = cb >= 0 ? Cb + cb + co : nullptr;
+                }
+            }
             uint32_t ts1 = 0, tc1 = 0;
             if (!evec) {
 #pragma unroll
@@ -1063,24 +1126,26 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     }
                 }
             }
-            T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int ih = r & 1, jh = r >> 1;
+                const uint32_t boff = (uint32_t)(r & 1) * (uint32_t)(G2H_STG_ELEMS * 2);  // bytes
                 T* buf = stg_mem + (r & 1) * G2H_STG_ELEMS;
-                uint32_t W[2][4];  // W[m1][n0 + 2 n1] = outputs (m0 = 0, m0 = 1) as one packed word
+                uint32_t W[2][4];  // W[second local m bit][n0 + 2 n1] = outputs (first local m bit = 0, 1) as one packed word
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int i1 = 0; i1 < 2; ++i1) {
-                        const uint32_t w0 = acc[ih * 4 + 2 * i1][jh * 4 + j], w1 = acc[ih * 4 + 2 * i1 + 1][jh * 4 + j];
-                        // max of the two halves (even-k / odd-k partial maxima), then low halves of both
-                        W[i1][j] = __byte_perm(__vmaxs2(w0, __byte_perm(w0, 0, 0x1032)), __vmaxs2(w1, __byte_perm(w1, 0, 0x1032)), 0x5410);
+                        // accumulator rows: bit 0 = m0, bit 1 = m_mp, bit 2 = top m bit
+                        const uint32_t w0 = mswap ? acc[ih * 4 + i1][jh * 4 + j] : acc[ih * 4 + 2 * i1][jh * 4 + j];
+                        const uint32_t w1 = mswap ? acc[ih * 4 + i1 + 2][jh * 4 + j] : acc[ih * 4 + 2 * i1 + 1][jh * 4 + j];
+                        // (lo0, lo1) vs (hi0, hi1): max of the even-k and odd-k partial maxima of both outputs at once
+                        W[i1][j] = __vmaxs2(__byte_perm(w0, w1, 0x5410), __byte_perm(w0, w1, 0x7632));
                     }
                 if (ecase <= 1) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint2*>(buf + stg_swz_h(qbase | ((uint32_t)j << (tm - 1)))) = make_uint2(W[0][j], W[1][j]);
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(w_addr[j] + boff), "r"(W[0][j]), "r"(W[1][j]) : "memory");
                 } else {
                     uint4 v0, v1;
                     if (ecase == 2) {  // word order (m1, n0), second vector n1 = 1
@@ -1093,12 +1158,21 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                         v0 = make_uint4(W[0][0], W[0][1], W[0][2], W[0][3]);
                         v1 = make_uint4(W[1][0], W[1][1], W[1][2], W[1][3]);
                     }
-                    *reinterpret_cast<uint4*>(buf + stg_swz_h(qbase2)) = v0;
-                    *reinterpret_cast<uint4*>(buf + stg_swz_h(qbase2 | 8u)) = v1;
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_addr[0] + boff), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_addr[1] + boff), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
                 const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
-                if (evec) {
+                if (evec && ecase != 0) {
+#pragma unroll
+                    for (int itr = 0; itr < 2; ++itr) {
+                        if (g_ptr[itr]) {
+                            uint4 o;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(r_addr[itr] + boff) : "memory");
+                            *reinterpret_cast<uint4*>(g_ptr[itr] + roff) = o;
+                        }
+                    }
+                } else if (evec) {  // C bits 0..2 are tile bits but not contiguous in the staging buffer: gather
 #pragma unroll
                     for (int itr = 0; itr < 2; ++itr) {
                         const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
@@ -1111,21 +1185,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                         const long long cb = ti.cbase[sub_e];
                         if (cb >= 0) {
                             so |= sub_e << nbr;
-                            uint4 o;
-                            if (efast) {
-                                o = *reinterpret_cast<const uint4*>(buf + stg_swz_h(so));
-                            } else {
-                                T v[8];
+                            T v[8];
 #pragma unroll
-                                for (int q = 0; q < 8; ++q) {
-                                    const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
-                                    v[q] = buf[stg_swz_h(so | dq)];
-                                }
-                                o.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
-                                o.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
-                                o.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
-                                o.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
+                            for (int q = 0; q < 8; ++q) {
+                                const uint32_t dq = ((q & 1) << ti.e_spos[0]) | (((q >> 1) & 1) << ti.e_spos[1]) | (((q >> 2) & 1) << ti.e_spos[2]);
+                                v[q] = buf[stg_swz_h(so | dq)];
                             }
+                            uint4 o;
+                            o.x = (uint32_t)(uint16_t)v[0] | ((uint32_t)(uint16_t)v[1] << 16);
+                            o.y = (uint32_t)(uint16_t)v[2] | ((uint32_t)(uint16_t)v[3] << 16);
+                            o.z = (uint32_t)(uint16_t)v[4] | ((uint32_t)(uint16_t)v[5] << 16);
+                            o.w = (uint32_t)(uint16_t)v[6] | ((uint32_t)(uint16_t)v[7] << 16);
                             *reinterpret_cast<uint4*>(Cb + cb + roff + co) = o;
                         }
                     }
@@ -1151,7 +1221,19 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+        KP(3)
+#ifdef TB_KPROF
+        ++kp_tiles;
+#endif
     }
+#ifdef TB_KPROF
+    if (ctid == 0) {
+        for (int q = 0; q < 4; ++q) atomicAdd(&g_kprof[q], (unsigned long long)kp_acc[q]);
+        atomicAdd(&g_kprof[4], (unsigned long long)(clock64() - kp_t0));
+        atomicAdd(&g_kprof[5], (unsigned long long)kp_tiles);
+    }
+#endif
+#undef KP
 }
 
 // ------------------------------------------------------------------------------------------------
