@@ -323,6 +323,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     //      u = contract(A, B) keeping `sk` of the shared reduced labels, t = max over those labels of u
     //      (t = contract(u, unit scalar)).  Balances CTA run times inside a level launch.
     int nT = nT0;
+    std::vector<uint8_t> folded(nTmax, 0);  // split labels a node reduces on behalf of its children (not algorithmic work)
+    std::vector<uint8_t> kept(nTmax, 0);    // split labels a node keeps as extra output labels for its consumer
     if (!(P.flags & TB_PLAN_NO_SPLIT_K)) {
         for (int t = nL; t < nT0; ++t) {
             const int A = lch[t], B = rch[t];
@@ -375,10 +377,39 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             }
             sk = std::min(sk, MAX_RANK - rc);
             if (sk <= 0) continue;
+            // If the consumer of t is itself a reduction over (almost) all of t, it can reduce the split labels too:
+            // t keeps them as output labels and they become labels private to one operand of the consumer.  The
+            // consumer then reads the partial results once - exactly what the separate max pass would have read.
+            if (const int pr = parent[t]; pr >= 0) {
+                const int sib = lch[pr] == t ? rch[pr] : lch[pr];
+                ++stamp;
+                for (int q = 0; q < rc; ++q) stA[labp(t)[q]] = stamp;
+                for (int q = 0; q < lab_n[pr]; ++q) stC[labp(pr)[q]] = stamp;
+                int n_sib_out = 0;  // output labels of the consumer that only the sibling carries
+                for (int q = 0; q < lab_n[sib]; ++q) {
+                    const int32_t l = labp(sib)[q];
+                    if (stA[l] != stamp && stC[l] == stamp) ++n_sib_out;
+                }
+                if (n_sib_out <= 1 && (int)folded[pr] + sk <= 8) {
+                    int32_t tmp[48];
+                    int n = 0;
+                    for (int q = 0; q < rc; ++q) tmp[n++] = labp(t)[q];
+                    for (int q = nk - sk; q < nk; ++q) tmp[n++] = Ksh[q];
+                    std::sort(tmp, tmp + n);
+                    lab_off[t] = (int32_t)lab_data.size();
+                    lab_n[t] = (uint8_t)n;
+                    lab_data.insert(lab_data.end(), tmp, tmp + n);
+                    folded[pr] = (uint8_t)(folded[pr] + sk);
+                    kept[t] = (uint8_t)sk;
+                    continue;
+                }
+            }
             const int u = nT++, ul = nT++;
             lch[u] = A;
             rch[u] = B;
             parent[u] = t;
+            folded[u] = folded[t];
+            folded[t] = 0;
             // lab[u] = lab[t] + the last sk shared reduced labels, sorted
             {
                 int32_t tmp[48];
@@ -773,11 +804,11 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         return r;
     };
     double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, bytes_m = 0, sc = 0;
-    for (int t = 0; t < nT0; ++t) sc = std::max(sc, (double)lab_n[t]);
+    for (int t = 0; t < nT0; ++t) sc = std::max(sc, (double)((int)lab_n[t] - (int)kept[t]));
     auto account = [&](int t, int knd) {
         const NodeCls& c = cls[t];
         auto p2 = [](int e) { return (double)(1ull << e); };
-        int tc = rank_of(t) + c.nk + c.nka + c.nkb;
+        int tc = rank_of(t) + c.nk + c.nka + c.nkb - folded[t];
         const double eb = half ? 2.0 : 4.0;
         if (unary[t]) {  // second half of a split node: engine overhead, not algorithmic work
             bytes += eb * p2(rank_of(t));
