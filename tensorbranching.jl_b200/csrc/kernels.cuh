@@ -292,6 +292,12 @@ __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __res
             // of every tree): 128-bit loads, consecutive threads take consecutive vectors
 #pragma unroll 2
             for (uint32_t r = kp * V; r < n_red; r += (V << ks)) acc = dot16<T>(A + offA + r, B + offB + r, acc);
+        } else if (sa == 0 && sb == 0 && (1u << nk) >= V && (n_red >> ks) >= V) {
+            // the same with labels private to one operand (split-K labels folded into this reduction): a vector of V
+            // consecutive r shares the private index, so both operands still read 16 contiguous bytes
+#pragma unroll 2
+            for (uint32_t r = kp * V; r < n_red; r += (V << ks))
+                acc = dot16<T>(A + offA + (r & amask), B + offB + ((r & kmask) | ((r >> (nk + nka)) << nk)), acc);
         } else if (nka == 0 && sd.nkb == 0) {
 #pragma unroll 4
             for (uint32_t r = kp; r < n_red; r += (1u << ks))
@@ -900,14 +906,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         // the tile counter is read one tile ahead (the atomic's latency overlaps the current tile's set-up), and the
         // step descriptor is decoded once per (branch, step) instance into shared memory: consecutive tiles mostly
         // belong to the same instance
-        unsigned tile_next = 0;
-        if (lane == 0) tile_next = atomicAdd(counter, 1u);
+        unsigned tile_next = blockIdx.x;  // first tile: no atomic on the launch's critical path (the counter hands out gridDim.x + ...)
         uint32_t cur_start = 1, cur_end = 0;  // tile range of the cached instance (empty)
         int cur_idx = -1;
         const unsigned char* cur_arena = nullptr;
         for (unsigned tcount = 0;; ++tcount) {
             const unsigned tile_g = __shfl_sync(0xffffffffu, tile_next, 0);
-            if (lane == 0 && tile_g < total_tiles) tile_next = atomicAdd(counter, 1u);
+            if (lane == 0 && tile_g < total_tiles) tile_next = atomicAdd(counter, 1u) + gridDim.x;
             const int slot = tcount % G2H_TSLOTS;
             mbar_wait(&bar_tempty[slot], ((tcount / G2H_TSLOTS) & 1) ^ 1);
             if (tile_g >= total_tiles) {
@@ -1041,24 +1046,54 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             mbar_wait(&bar_full[stage], (it / G2_STAGES) & 1);
             KP(1)
             const int KP_ROWS = 1 << (kc - 1);  // k-pair rows in this chunk
-            uint32_t ua = (uint32_t)stage * (uint32_t)(STAGE_ELEMS * 2), ub = ua;
+            // Software pipeline over the k-pair rows: B is double-buffered in registers, the first half of A
+            // (rows 0..3 of the microtile) is reloaded in place as soon as its last use has issued, the second half at
+            // the top of the step whose second half needs it: no load is followed directly by its consumers, so the
+            // two warps a lone CTA has per scheduler can keep the VIADDMNMX pipe busy.
+            uint32_t ua = a_thr + (uint32_t)stage * (uint32_t)(STAGE_ELEMS * 2);
+            uint32_t ub = b_thr + (uint32_t)stage * (uint32_t)(STAGE_ELEMS * 2);
+            uint32_t a[8], b0[8], b1[8];
+#define G2H_LDA_LO(addr)                                                                                            \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[0]), "=r"(a[1]) : "r"(addr));                           \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[2]), "=r"(a[3]) : "r"((addr) + a_p));
+#define G2H_LDA_HI(addr)                                                                                            \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[4]), "=r"(a[5]) : "r"((addr) + a_hi));                  \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[6]), "=r"(a[7]) : "r"((addr) + a_hi + a_p));
+#define G2H_LDB(bb, addr)                                                                                           \
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(bb[0]), "=r"(bb[1]), "=r"(bb[2]), "=r"(bb[3]) : "r"(addr)); \
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(bb[4]), "=r"(bb[5]), "=r"(bb[6]), "=r"(bb[7]) : "r"((addr) + b_hi));
+#define G2H_MATH(i0, bb)                                                                                            \
+    _Pragma("unroll") for (int i = i0; i < i0 + 4; ++i)                                                              \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[i][j] = __viaddmax_s16x2(a[i], bb[j], acc[i][j]);
+            G2H_LDA_LO(ua)
+            G2H_LDB(b0, ub)
+            int kk = 0;
 #pragma unroll 1
-            for (int kk = 0; kk < KP_ROWS; ++kk, ua += rowA, ub += rowB) {
-                uint2 a0, a1, a2, a3;
-                uint4 b0, b1;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a0.x), "=r"(a0.y) : "r"(a_thr + ua));
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a1.x), "=r"(a1.y) : "r"(a_thr + ua + a_p));
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a2.x), "=r"(a2.y) : "r"(a_thr + ua + a_hi));
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a3.x), "=r"(a3.y) : "r"(a_thr + ua + a_hi + a_p));
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b0.x), "=r"(b0.y), "=r"(b0.z), "=r"(b0.w) : "r"(b_thr + ub));
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(b1.x), "=r"(b1.y), "=r"(b1.z), "=r"(b1.w) : "r"(b_thr + ub + b_hi));
-                const uint32_t a[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-                const uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = __viaddmax_s16x2(a[i], b[j], acc[i][j]);
+            for (; kk + 2 <= KP_ROWS; kk += 2) {
+                G2H_LDA_HI(ua)
+                G2H_LDB(b1, ub + rowB)
+                G2H_MATH(0, b0)
+                G2H_LDA_LO(ua + rowA)
+                G2H_MATH(4, b0)
+                ua += rowA;
+                ub += rowB;
+                G2H_LDA_HI(ua)
+                G2H_LDB(b0, ub + rowB)  // the last one reads one row past the chunk (still shared memory): discarded
+                G2H_MATH(0, b1)
+                G2H_LDA_LO(ua + rowA)
+                G2H_MATH(4, b1)
+                ua += rowA;
+                ub += rowB;
             }
+            if (kk < KP_ROWS) {  // a single k-pair row (kc == 1)
+                G2H_LDA_HI(ua)
+                G2H_MATH(0, b0)
+                G2H_MATH(4, b0)
+            }
+#undef G2H_LDA_LO
+#undef G2H_LDA_HI
+#undef G2H_LDB
+#undef G2H_MATH
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar_empty[stage]);
             KP(2)

@@ -380,7 +380,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             // If the consumer of t is itself a reduction over (almost) all of t, it can reduce the split labels too:
             // t keeps them as output labels and they become labels private to one operand of the consumer.  The
             // consumer then reads the partial results once - exactly what the separate max pass would have read.
-            if (const int pr = parent[t]; pr >= 0) {
+            static const bool no_fold = getenv("TB_NO_FOLD") != nullptr;  // diagnostics: keep the separate max pass
+            if (const int pr = parent[t]; pr >= 0 && !no_fold) {
                 const int sib = lch[pr] == t ? rch[pr] : lch[pr];
                 ++stamp;
                 for (int q = 0; q < rc; ++q) stA[labp(t)[q]] = stamp;
