@@ -653,6 +653,19 @@ int enqueue_batch(tb_ctx* ctx, tb_plan* const* plans, int64_t lo, int64_t hi, st
 
 int begin_call(tb_ctx* ctx, int64_t n) {
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
+#ifdef TB_KPROF
+    {  // timeline of the most recent call only
+        static TlRec* buf = nullptr;
+        const unsigned cap = 4u << 20, zero = 0;
+        if (!buf) {
+            cudaMalloc(&buf, (size_t)cap * sizeof(TlRec));
+            cudaMemcpyToSymbol(g_tl, &buf, sizeof buf);
+            cudaMemcpyToSymbol(g_tl_cap, &cap, sizeof cap);
+        }
+        cudaDeviceSynchronize();
+        cudaMemcpyToSymbol(g_tl_n, &zero, sizeof zero);
+    }
+#endif
     ctx->last_ms = 0;
     ctx->last_launches = 0;
     ctx->h2d_bytes = 0;
@@ -725,7 +738,15 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
     std::vector<int32_t> status((size_t)n, TB_OK);
     bool any = false;
     for (int64_t i = 0; i < n; ++i) any = any || plans[i];
-    rc = enqueue_batch(ctx, plans, 0, n, status, single);
+    // batches of growing size: the GPU starts on the first wave while the host still builds the work lists of the rest
+    const int64_t wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;
+    int64_t batch = single ? n : wave;
+    for (int64_t lo = 0; lo < n && rc == TB_OK;) {
+        const int64_t hi = std::min(n, lo + std::max<int64_t>(batch, 1));
+        rc = enqueue_batch(ctx, plans, lo, hi, status, single);
+        lo = hi;
+        batch = std::min<int64_t>(batch * 2, wave * ctx->n_lanes * 2);
+    }
     if (rc) {
         sync_all_lanes(ctx);
         return rc;
@@ -814,6 +835,21 @@ int tb_shutdown(tb_ctx* ctx) {
         cudaDeviceSynchronize();
         unsigned long long h[8] = {0};
         cudaMemcpyFromSymbol(h, g_kprof, sizeof h);
+        if (const char* path = getenv("TB_TL_DUMP")) {
+            unsigned n = 0, cap = 0;
+            TlRec* buf = nullptr;
+            cudaMemcpyFromSymbol(&n, g_tl_n, sizeof n);
+            cudaMemcpyFromSymbol(&cap, g_tl_cap, sizeof cap);
+            cudaMemcpyFromSymbol(&buf, g_tl, sizeof buf);
+            n = std::min(n, cap);
+            std::vector<TlRec> hrec(n);
+            if (n) cudaMemcpy(hrec.data(), buf, (size_t)n * sizeof(TlRec), cudaMemcpyDeviceToHost);
+            if (FILE* f = fopen(path, "wb")) {
+                fwrite(hrec.data(), sizeof(TlRec), n, f);
+                fclose(f);
+            }
+            fprintf(stderr, "KPROF timeline: %u CTA records -> %s\n", n, path);
+        }
         fprintf(stderr, "KPROF k_gemm2h consumer cycles: wait_tile %.3e wait_data %.3e main %.3e epilogue %.3e lifetime %.3e tiles %llu\n",
                 (double)h[0], (double)h[1], (double)h[2], (double)h[3], (double)h[4], h[5]);
     }

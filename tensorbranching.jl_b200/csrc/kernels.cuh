@@ -88,6 +88,34 @@ __device__ __forceinline__ uint32_t scatter_bits(uint32_t x, const uint8_t* sh, 
     return off;
 }
 
+#ifdef TB_KPROF
+// diagnostics build: one record per CTA (which launch, which SM, when) for an offline occupancy timeline
+struct TlRec {
+    unsigned long long key, t0, t1;
+    unsigned smid, kind;
+};
+__device__ TlRec* g_tl;
+__device__ unsigned g_tl_n, g_tl_cap;
+__device__ __forceinline__ unsigned long long tl_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_log(const void* key, unsigned kind, unsigned long long t0) {
+    const unsigned i = atomicAdd(&g_tl_n, 1u);
+    if (i < g_tl_cap) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        g_tl[i] = TlRec{(unsigned long long)key, t0, tl_now(), smid, kind};
+    }
+}
+#define TL_BEGIN const unsigned long long tl_t0 = tl_now();
+#define TL_END(key, kind, cond) if (cond) tl_log(key, kind, tl_t0);
+#else
+#define TL_BEGIN
+#define TL_END(key, kind, cond)
+#endif
+
 // largest idx with starts[idx] <= b (starts[0] == 0).  Called by all 32 lanes of a converged warp: a 32-ary search,
 // 2-3 dependent loads instead of the ~12 of a binary search (the search sits at the head of every CTA / tile).
 __device__ __forceinline__ int find_inst(const uint32_t* __restrict__ starts, int n, uint32_t b) {
@@ -121,6 +149,7 @@ template <typename T>
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst* __restrict__ insts, int n_insts) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     if ((int)blockIdx.x >= n_insts) return;
+    TL_BEGIN
     const SubInst inst = insts[blockIdx.x];
     const int tid = threadIdx.x;
     {
@@ -180,6 +209,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst*
         }
         __syncthreads();
     }
+    TL_END(insts, 0u, tid == 0)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -192,6 +222,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __res
                                                          const uint32_t* __restrict__ tile_starts, int n_insts) {
     __shared__ BigStep sd;
     __shared__ T s_red[BIG_THREADS];
+    TL_BEGIN
     const int tid = threadIdx.x;
     const int idx = find_inst(tile_starts, n_insts, blockIdx.x);
     const BigInst inst = insts[idx];
@@ -270,6 +301,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __res
         };
         if (po == 12) vectors(std::integral_constant<int, 4>{});
         else vectors(std::integral_constant<int, 1>{});
+        TL_END(insts, 1u, tid == 0)
         return;
     }
     // thread -> (output, k-part): 2^po outputs per CTA, 2^ks threads share one output
@@ -325,6 +357,7 @@ __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __res
         }
         if (kp == 0) C[c] = acc;
     }
+    TL_END(insts, 1u, tid == 0)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1005,6 +1038,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
     int ep_inst = -1;  // the step whose epilogue offsets (ts, tc) this thread holds
     uint32_t ts = 0, tc = 0;
 #ifdef TB_KPROF
+    const unsigned long long tl_t0 = tl_now();
     long long kp_t0 = clock64(), kp_last = kp_t0, kp_acc[4] = {0, 0, 0, 0};
     unsigned kp_tiles = 0;
 #define KP(i) { const long long n_ = clock64(); kp_acc[i] += n_ - kp_last; kp_last = n_; }
@@ -1263,6 +1297,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
     }
 #ifdef TB_KPROF
     if (ctid == 0) {
+        tl_log(insts, 2u, tl_t0);
         for (int q = 0; q < 4; ++q) atomicAdd(&g_kprof[q], (unsigned long long)kp_acc[q]);
         atomicAdd(&g_kprof[4], (unsigned long long)(clock64() - kp_t0));
         atomicAdd(&g_kprof[5], (unsigned long long)kp_tiles);
