@@ -896,7 +896,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
 __device__ unsigned long long g_kprof[8];
 #endif
 constexpr int G2H_TSLOTS = 4;  // tile descriptors the producer may publish ahead of the consumers
-constexpr int G2H_STG_ELEMS = 8192;  // int16 elements of one staged half of a 128 x 128 tile (16 KB)
+constexpr int G2H_STG_ELEMS = 4096;  // int16 elements of one staged quarter of a 128 x 128 tile (8 KB)
 struct TileInfoH {
     long long cbase[32];
     void* C;
@@ -1133,11 +1133,11 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             KP(2)
         }
         // ---- staged epilogue: out = max(even-k half, odd-k half); int16 elements, 8 per 16-byte global vector.
-        // Two rounds (the top n tile bit), each staging half the tile (16 KB) in C-address order.  Everything that
-        // does not depend on the round is computed once per tile: the ALU pipe that executes these instructions is
-        // the one the main loop's VIADDMNMX need.
+        // Everything that does not depend on the round is computed once per tile (the ALU pipe that executes these
+        // instructions is the one the main loop's VIADDMNMX need).
         {
-            const int nbr = tm + tn - 1;  // in-round tile bits: all m bits and the n bits below the top one
+            const int nbr = tm + tn - 2;
+            const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
             if (ti.inst != ep_inst) {  // consecutive tiles of a persistent CTA mostly belong to the same step
                 ep_inst = ti.inst;
                 ts = tc = 0;
@@ -1155,36 +1155,32 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             const bool mswap = ti.mswap != 0;  // the thread pairs its outputs along m_mp instead of m0
             T* __restrict__ Cb = reinterpret_cast<T*>(ti.C);
             const uint32_t stg_base = (uint32_t)__cvta_generic_to_shared(stg_mem);
-            // staging write offsets (bytes inside a buffer); the swizzle is XOR-linear
-            uint32_t w_off[4], w_top = 0;
+            // staging write addresses (bytes, buffer 0)
+            uint32_t w_addr[4];
             if (ecase <= 1) {
-                const uint32_t qbase = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 2) | ((uint32_t)tnh << (tm + 1));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) w_off[j] = stg_swz_h(qbase | ((uint32_t)j << (tm - 1))) << 1;
-                w_top = stg_swz_h(1u << (nbr - 1)) << 1;  // the top m bit
+                for (int j = 0; j < 4; ++j) w_addr[j] = stg_base + (stg_swz_h(qbase | ((uint32_t)j << (tm - 1))) << 1);
             } else {
-                const uint32_t qbase2 = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 5) | ((uint32_t)tnh << (tm + 2));
-                w_off[0] = stg_swz_h(qbase2) << 1;
-                w_off[1] = w_off[2] = w_off[3] = 0;
+                const uint32_t qbase2 = ((uint32_t)sub << nbr) | ((uint32_t)tmh << 4) | ((uint32_t)tnh << (tm + 1));
+                w_addr[0] = stg_base + (stg_swz_h(qbase2) << 1);
+                w_addr[1] = w_addr[0] ^ 16u;  // staging index bit 3 (the swizzle never reads it)
+                w_addr[2] = w_addr[3] = 0;
             }
-            // read side of the 128-bit path: four vectors per thread and round
-            uint32_t r_off[4] = {0, 0, 0, 0};
-            T* g_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+            // read side of the 128-bit path: two vectors per thread and round
+            uint32_t r_addr[2] = {0, 0};
+            T* g_ptr[2] = {nullptr, nullptr};
             if (evec && ecase != 0) {
 #pragma unroll
-                for (int itr = 0; itr < 4; ++itr) {
+                for (int itr = 0; itr < 2; ++itr) {
                     const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
                     const uint32_t sub_e = e8 >> nbr;
                     uint32_t so = ts, co = tc;
-#pragma unroll
-                    for (int b = 11; b < 13; ++b)
-                        if (b < nbr) {
-                            const uint32_t bit = ((uint32_t)itr >> (b - 11)) & 1u;
-                            so |= bit << ti.e_spos[b];
-                            co |= bit << ti.e_cs[b];
-                        }
+                    if (11 < nbr) {
+                        so |= (uint32_t)itr << ti.e_spos[11];
+                        co |= (uint32_t)itr << ti.e_cs[11];
+                    }
                     const long long cb = ti.cbase[sub_e];
-                    r_off[itr] = stg_swz_h(so | (sub_e << nbr)) << 1;
+                    r_addr[itr] = stg_base + (stg_swz_h(so | (sub_e << nbr)) << 1);
                     g_ptr[itr] = cb >= 0 ? Cb + cb + co : nullptr;
                 }
             }
@@ -1200,74 +1196,61 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 }
             }
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int jh = r;
-                const uint32_t bbase = stg_base + (uint32_t)r * (uint32_t)(G2H_STG_ELEMS * 2);  // byte address of this round's buffer
-                T* buf = stg_mem + r * G2H_STG_ELEMS;
-                // W[top m bit][second local m bit][n0 + 2 n1] = outputs (first local m bit = 0, 1) as one packed word
-                uint32_t W[2][2][4];
+            for (int r = 0; r < 4; ++r) {
+                const int ih = r & 1, jh = r >> 1;
+                const uint32_t boff = (uint32_t)(r & 1) * (uint32_t)(G2H_STG_ELEMS * 2);  // bytes
+                T* buf = stg_mem + (r & 1) * G2H_STG_ELEMS;
+                uint32_t W[2][4];  // W[second local m bit][n0 + 2 n1] = outputs (first local m bit = 0, 1) as one packed word
 #pragma unroll
-                for (int ih = 0; ih < 2; ++ih)
+                for (int j = 0; j < 4; ++j)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-#pragma unroll
-                        for (int i1 = 0; i1 < 2; ++i1) {
-                            // accumulator rows: bit 0 = m0, bit 1 = m_mp, bit 2 = top m bit
-                            const uint32_t w0 = mswap ? acc[ih * 4 + i1][jh * 4 + j] : acc[ih * 4 + 2 * i1][jh * 4 + j];
-                            const uint32_t w1 = mswap ? acc[ih * 4 + i1 + 2][jh * 4 + j] : acc[ih * 4 + 2 * i1 + 1][jh * 4 + j];
-                            // (lo0, lo1) vs (hi0, hi1): max of the even-k and odd-k partial maxima of both outputs at once
-                            W[ih][i1][j] = __vmaxs2(__byte_perm(w0, w1, 0x5410), __byte_perm(w0, w1, 0x7632));
-                        }
+                    for (int i1 = 0; i1 < 2; ++i1) {
+                        // accumulator rows: bit 0 = m0, bit 1 = m_mp, bit 2 = top m bit
+                        const uint32_t w0 = mswap ? acc[ih * 4 + i1][jh * 4 + j] : acc[ih * 4 + 2 * i1][jh * 4 + j];
+                        const uint32_t w1 = mswap ? acc[ih * 4 + i1 + 2][jh * 4 + j] : acc[ih * 4 + 2 * i1 + 1][jh * 4 + j];
+                        // (lo0, lo1) vs (hi0, hi1): max of the even-k and odd-k partial maxima of both outputs at once
+                        W[i1][j] = __vmaxs2(__byte_perm(w0, w1, 0x5410), __byte_perm(w0, w1, 0x7632));
+                    }
                 if (ecase <= 1) {
 #pragma unroll
-                    for (int ih = 0; ih < 2; ++ih)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(bbase + (w_off[j] ^ (ih ? w_top : 0u))), "r"(W[ih][0][j]), "r"(W[ih][1][j]) : "memory");
+                    for (int j = 0; j < 4; ++j)
+                        asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(w_addr[j] + boff), "r"(W[0][j]), "r"(W[1][j]) : "memory");
                 } else {
-#pragma unroll
-                    for (int ih = 0; ih < 2; ++ih) {
-                        uint4 v0, v1;
-                        if (ecase == 2) {  // word order (m1, n0), second vector n1 = 1
-                            v0 = make_uint4(W[ih][0][0], W[ih][1][0], W[ih][0][1], W[ih][1][1]);
-                            v1 = make_uint4(W[ih][0][2], W[ih][1][2], W[ih][0][3], W[ih][1][3]);
-                        } else if (ecase == 3) {  // (n0, m1), second vector n1 = 1
-                            v0 = make_uint4(W[ih][0][0], W[ih][0][1], W[ih][1][0], W[ih][1][1]);
-                            v1 = make_uint4(W[ih][0][2], W[ih][0][3], W[ih][1][2], W[ih][1][3]);
-                        } else {  // (n0, n1), second vector m1 = 1
-                            v0 = make_uint4(W[ih][0][0], W[ih][0][1], W[ih][0][2], W[ih][0][3]);
-                            v1 = make_uint4(W[ih][1][0], W[ih][1][1], W[ih][1][2], W[ih][1][3]);
-                        }
-                        // staging index bits 3 (second vector) and 4 (top m bit): the swizzle never reads them
-                        const uint32_t wa = bbase + (w_off[0] ^ (ih ? 32u : 0u));
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(wa), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(wa ^ 16u), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
+                    uint4 v0, v1;
+                    if (ecase == 2) {  // word order (m1, n0), second vector n1 = 1
+                        v0 = make_uint4(W[0][0], W[1][0], W[0][1], W[1][1]);
+                        v1 = make_uint4(W[0][2], W[1][2], W[0][3], W[1][3]);
+                    } else if (ecase == 3) {  // (n0, m1), second vector n1 = 1
+                        v0 = make_uint4(W[0][0], W[0][1], W[1][0], W[1][1]);
+                        v1 = make_uint4(W[0][2], W[0][3], W[1][2], W[1][3]);
+                    } else {  // (n0, n1), second vector m1 = 1
+                        v0 = make_uint4(W[0][0], W[0][1], W[0][2], W[0][3]);
+                        v1 = make_uint4(W[1][0], W[1][1], W[1][2], W[1][3]);
                     }
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_addr[0] + boff), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_addr[1] + boff), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
                 }
                 asm volatile("bar.sync 1, 256;\n" ::: "memory");
-                const uint32_t roff = (uint32_t)jh << ti.e_cs_ntop;
+                const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
                 if (evec && ecase != 0) {
 #pragma unroll
-                    for (int itr = 0; itr < 4; ++itr) {
+                    for (int itr = 0; itr < 2; ++itr) {
                         if (g_ptr[itr]) {
                             uint4 o;
-                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(bbase + r_off[itr]) : "memory");
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w) : "r"(r_addr[itr] + boff) : "memory");
                             *reinterpret_cast<uint4*>(g_ptr[itr] + roff) = o;
                         }
                     }
                 } else if (evec) {  // C bits 0..2 are tile bits but not contiguous in the staging buffer: gather
-#pragma unroll 1
-                    for (int itr = 0; itr < 4; ++itr) {
+#pragma unroll
+                    for (int itr = 0; itr < 2; ++itr) {
                         const uint32_t e8 = ((uint32_t)itr << 11) | ((uint32_t)ctid << 3);
                         const uint32_t sub_e = e8 >> nbr;
                         uint32_t so = ts, co = tc;
-#pragma unroll
-                        for (int b = 11; b < 13; ++b)
-                            if (b < nbr) {
-                                const uint32_t bit = ((uint32_t)itr >> (b - 11)) & 1u;
-                                so |= bit << ti.e_spos[b];
-                                co |= bit << ti.e_cs[b];
-                            }
+                        if (11 < nbr) {
+                            so |= (uint32_t)itr << ti.e_spos[11];
+                            co |= (uint32_t)itr << ti.e_cs[11];
+                        }
                         const long long cb = ti.cbase[sub_e];
                         if (cb >= 0) {
                             so |= sub_e << nbr;
@@ -1287,12 +1270,12 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     }
                 } else {
 #pragma unroll 4
-                    for (int itr = 0; itr < 32; ++itr) {
+                    for (int itr = 0; itr < 16; ++itr) {
                         const uint32_t e1 = ((uint32_t)itr << 8) | (uint32_t)ctid;
                         const uint32_t sub_e = e1 >> nbr;
                         uint32_t so = ts1, co = tc1;
 #pragma unroll
-                        for (int b = 8; b < 13; ++b) {
+                        for (int b = 8; b < 12; ++b) {
                             const uint32_t bit = ((uint32_t)itr >> (b - 8)) & 1u;
                             if (b < nbr) {
                                 so |= bit << ti.e_spos[b];

@@ -1002,10 +1002,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 // 1) is chosen so that the m labels on C bits 0..2 are thread-local, and b_shift[29] = 1 swaps the
                 // roles of m0 and m_mp (the thread pairs outputs along m_mp).  The tables use LOGICAL m positions:
                 // [first local bit, second local bit, the other in-round m bits in ascending order].
-                // packed int16 stages HALF a tile per round (2 rounds, selected by the top n tile bit): the top m tile
-                // bit is one more in-round bit (thread-local; staging position nbr-1, or 4 in the vector layouts).
                 {
-                    const int nbr = c.tm + c.tn - (half ? 1 : 2);
+                    const int nbr = c.tm + c.tn - 2;
                     int ent_cs[16], ent_sp[16], ne = 0;
                     auto build = [&](int mp, int mswap) -> int {
                         int lm[8], nl = 0;  // logical position of the in-round m bit q
@@ -1016,7 +1014,6 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                         ne = 0;
                         for (int i = 0; i < c.tm - 1; ++i) { ent_cs[ne] = s.c_shift[i]; ent_sp[ne++] = lm[i]; }
                         for (int i = 0; i < c.tn - 1; ++i) { ent_cs[ne] = s.c_shift[c.tm + i]; ent_sp[ne++] = (c.tm - 1) + i; }
-                        if (half) { ent_cs[ne] = s.c_shift[c.tm - 1]; ent_sp[ne++] = nbr - 1; }
                         for (int i = 1; i < ne; ++i) {
                             int cs = ent_cs[i], sp = ent_sp[i], j = i - 1;
                             while (j >= 0 && ent_cs[j] > cs) { ent_cs[j + 1] = ent_cs[j]; ent_sp[j + 1] = ent_sp[j]; --j; }
@@ -1029,7 +1026,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                         // packed int16: the thread holds (u, v) x (n0, n1) of a round (u, v = its local m bits), so it
                         // can write any of the orders C bits (0,1,2) = 1: (u,v,m2)  2: (u,v,n0)  3: (u,n0,v)
                         // 4: (u,n0,n1) as 16-byte vectors; for 2..4 the staging index is [the three C bits | the fourth
-                        // thread-local bit | top m bit | m2.. | n2..] and the table holds positions in THAT layout.
+                        // thread-local bit | m2.. | n2..] and the table holds positions in THAT layout.
                         int ecase = 0;
                         if (half) {
                             const int n0 = c.tm - 1, n1 = c.tm;  // layout-1 staging positions of the n bits 0,1
@@ -1041,15 +1038,13 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                             }
                             if (ecase >= 2) {
                                 static const int low[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
-                                for (int i = 0; i < ne; ++i) {  // {u, v, n0, n1} -> low[ecase], top m -> 4, m q>=2 -> q+3, n q>=2 -> +1
+                                for (int i = 0; i < ne; ++i) {  // {u, v, n0, n1} -> low[ecase], m q>=2 -> q+2, n unchanged
                                     const int sp = ent_sp[i];
                                     if (sp == 0) ent_sp[i] = low[ecase][0];
                                     else if (sp == 1) ent_sp[i] = low[ecase][1];
                                     else if (sp == n0) ent_sp[i] = low[ecase][2];
                                     else if (sp == n1) ent_sp[i] = low[ecase][3];
-                                    else if (sp == nbr - 1) ent_sp[i] = 4;
-                                    else if (sp < n0) ent_sp[i] = sp + 3;
-                                    else ent_sp[i] = sp + 1;
+                                    else if (sp < n0) ent_sp[i] = sp + 2;
                                 }
                             }
                         } else {

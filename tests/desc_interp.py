@@ -148,7 +148,7 @@ def run_plan(plan):
                     if s["store_mode"] == 2:
                         assert s["c_shift"][tm] == 0 and s["c_shift"][tm + 1] == 1
                     # staged-epilogue tables: sorted in-round tile bits
-                    nbr = tm + tn - (1 if vt == 3 else 2)   # packed int16: 2 rounds, the top m bit is an in-round bit
+                    nbr = tm + tn - 2
                     cs = [int(x) for x in s["c_shift"]]
                     n0, n1 = tm - 1, tm
 
@@ -156,8 +156,7 @@ def run_plan(plan):
                         # logical m positions: [first local bit, second local bit, the others ascending]
                         order = ([mp, 0] if mswap else [0, mp]) + [q for q in range(1, tm - 1) if q != mp]
                         lm = {q: k for k, q in enumerate(order)}
-                        ent = sorted([(cs[i], lm[i]) for i in range(tm - 1)] + [(cs[tm + i], (tm - 1) + i) for i in range(tn - 1)] +
-                                     ([(cs[tm - 1], nbr - 1)] if vt == 3 else []))
+                        ent = sorted([(cs[i], lm[i]) for i in range(tm - 1)] + [(cs[tm + i], (tm - 1) + i) for i in range(tn - 1)])
                         sp = [e[1] for e in ent]
                         ecase = 0
                         if vt == 3:
@@ -165,8 +164,8 @@ def run_plan(plan):
                                 ecase = {(1, 2): 1, (1, n0): 2, (n0, 1): 3, (n0, n1): 4}.get((sp[1], sp[2]), 0)
                             if ecase >= 2:
                                 low = {2: (0, 1, 2, 3), 3: (0, 2, 1, 3), 4: (0, 3, 1, 2)}[ecase]
-                                m = {0: low[0], 1: low[1], n0: low[2], n1: low[3], nbr - 1: 4}
-                                sp = [m[x] if x in m else (x + 3 if x < n0 else x + 1) for x in sp]
+                                m = {0: low[0], 1: low[1], n0: low[2], n1: low[3]}
+                                sp = [m[x] if x in m else (x + 2 if x < n0 else x) for x in sp]
                                 assert sorted(sp) == list(range(nbr)) and sp[:3] == [0, 1, 2]
                         else:
                             ecase = int(sp[:2] == [0, 1])
