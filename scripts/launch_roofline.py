@@ -27,7 +27,7 @@ def main():
     steps = [p.steps() if p else [] for p in plans]
     # waves of 256 plans in order (the engine's default), per level per kind
     expected = []
-    W = 64
+    W = 128
     live = [i for i, p in enumerate(plans) if p is not None]
     for w0 in range(0, len(live), W):
         mem = live[w0:w0 + W]
