@@ -176,8 +176,8 @@ def cpu_reference_run(branches, budget_s, ops_per_branch):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="tbcuda", choices=["tbcuda", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--max-branches", type=int, default=None)
@@ -300,11 +300,15 @@ def main():
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
         e0.record()
-        for _ in range(steps):
+        for q in range(steps):
             out = fn()
+            marks[q].record()
         e1.record()
         torch.cuda.synchronize()
+        per_step = [(e0 if q == 0 else marks[q - 1]).elapsed_time(marks[q]) for q in range(steps)]
+        timed.last_per_step = per_step
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -317,6 +321,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ms_step, result = timed(step_resident, args.steps, max(args.warmup, 3), sampler)
     clocks = sampler.stop() if sampler else None
+    per_step_ms = sorted(getattr(timed, "last_per_step", []) or [ms_step])
     launches_step = eng.last_timing()[1]
     dev_ms_last = eng.last_timing()[0]
 
@@ -364,6 +369,7 @@ def main():
                             "achieved_whole_step": float(abytes[mine].sum()) / (ms_step * 1e-3) * 1e-9}}
         line = {"metric": "tropical contraction throughput", "value": total_ops / (ms_step * 1e-3) * 1e-9, "unit": "Gop/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+                "ms_per_step_median_rank0": per_step_ms[len(per_step_ms) // 2], "ms_per_step_max_rank0": per_step_ms[-1],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "int16x2" if args.value_type == "i16" else "int32", "data": "synthetic", "config": config, "slices_per_s": n_br / (ms_step * 1e-3), "branches": n_br,
                 "total_ops": total_ops, "mis": float(np.max(result)), "gpu_launches": int(launches_step * args.steps),

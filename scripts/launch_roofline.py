@@ -57,6 +57,8 @@ def main():
     hdr = rows[hi]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     L = [(r[ki], float(r[vi].replace(",", "")) * 1e-9) for r in rows[hi + 1:] if len(r) > vi and "tb::" in r[ki]]
+    if len(sys.argv) > 3:  # launches of earlier (warm-up) calls; the first call grows the arena and has more, smaller waves
+        L = L[int(sys.argv[3]):]
     print(f"{'kernel':10s} {'us':>9s} {'Gop':>9s} {'MB':>8s} {'Gop/s':>8s} {'%dpx':>6s} {'GB/s':>7s} {'%hbm':>6s} {'t_roof_us':>9s} {'eff':>5s}  nodes top(m,n,b,k)")
     tot_t = tot_roof = 0
     for (name, t), e in zip(L, expected):
