@@ -43,6 +43,7 @@ struct BlobChunk {
 }  // namespace
 
 struct tb_ctx {
+    int call_wave = 0;  // wave size of the current call (a small call is cut into more, smaller waves: all lanes busy)
     std::thread reaper;  // frees the host side of the previous tb_contract_networks call's temporary plans
     tb_options opts{};
     int device = 0;
@@ -334,7 +335,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     } else if (rc) {
         return rc;
     }
-    const int max_wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;  // profiles/s03_wave_lane_sweep_cfg2.jsonl
+    const int max_wave = ctx->call_wave > 0 ? ctx->call_wave : (ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128);
     const int NL = (ctx->profile || single_plan_mode) ? 1 : ctx->n_lanes;
     // try to grow the arena so that NL full waves fit (bounded by the configured limit)
     {
@@ -729,6 +730,14 @@ int finish_call(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, 
     return TB_OK;
 }
 
+// waves of up to 128 plans (profiles/s03_wave_lane_sweep_cfg2.jsonl); a call with few plans (one rank's shard of a
+// multi-GPU run) gets ~2 waves per lane instead of a couple of full ones
+int wave_for_call(const tb_ctx* ctx, int64_t n) {
+    const int64_t cfg = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;
+    const int64_t per = (n + 2 * ctx->n_lanes - 1) / (2 * ctx->n_lanes);
+    return (int)std::min<int64_t>(cfg, std::max<int64_t>(16, per));
+}
+
 int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
                   double* out_max, bool single) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
@@ -739,7 +748,8 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
     bool any = false;
     for (int64_t i = 0; i < n; ++i) any = any || plans[i];
     // batches of growing size: the GPU starts on the first wave while the host still builds the work lists of the rest
-    const int64_t wave = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;
+    const int64_t wave = wave_for_call(ctx, n);
+    ctx->call_wave = (int)wave;
     int64_t batch = single ? n : wave;
     for (int64_t lo = 0; lo < n && rc == TB_OK;) {
         const int64_t hi = std::min(n, lo + std::max<int64_t>(batch, 1));
@@ -996,7 +1006,8 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     };
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
-    const int64_t batch_max = std::max<int64_t>(256, (int64_t)(ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128) * ctx->n_lanes);
+    ctx->call_wave = wave_for_call(ctx, n);
+    const int64_t batch_max = std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
     std::vector<int32_t> status((size_t)n, TB_OK);
     bool any = false;
     double t_wait = 0;
