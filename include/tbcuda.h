@@ -93,6 +93,11 @@ typedef struct tb_options {
  *   children always have smaller ids (post-order); the last node is the root.  n_leaves - 1 nodes.
  *   open_labels (iy) is empty on the solve_slice path; if given, the root keeps those labels.
  *   weights[v] is the weight of label/vertex v (n_labels entries) unless weight_dtype == UNIT.
+ *   Index slicing: fixing label v to x restricts every leaf that carries v to its x-th slice (the vertex
+ *   tensor [0, w_v] becomes the scalar 0 or w_v, the edge tensor a row of it) and v disappears from
+ *   the network, so every tensor that carried it halves.  The 2^k assignments of k fixed labels are
+ *   independent contractions of the same tree; the max of their values is the unsliced value.
+ *   tb_contract_sliced enumerates them, tb_suggest_slices picks the labels.
  */
 typedef struct tb_network {
     int32_t n_labels;
@@ -107,7 +112,9 @@ typedef struct tb_network {
     int32_t weight_dtype;    /* tb_weight_dtype */
     int32_t value_type;      /* tb_value_type */
     uint32_t flags;          /* TB_PLAN_* */
-    int32_t reserved;
+    int32_t n_fixed;         /* index slicing: labels fixed to one value in this contraction; 0 = none */
+    const int32_t* fixed_labels; /* n_fixed distinct labels ... */
+    const uint8_t* fixed_values; /* ... and the value (0 or 1) each one is fixed to */
 } tb_network;
 
 /* what complexity(branch) reports in the reference (src/types.jl:115-121) + engine facts */
@@ -182,6 +189,25 @@ int tb_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64
  * nets[i].n_leaves == 0 means "empty graph". */
 int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n,
                          double* out_values, int32_t* out_status, double* out_max);
+
+/* Index slicing of ONE heavy branch (the 2^k slice assignments of BASELINE.json north_star (4)).
+ * The network's own n_fixed must be 0.  Assignment a in [first, first + count) fixes sliced_labels[i] to
+ * bit i of a; every assignment is a contraction of the same tree with n_sliced labels removed, all of
+ * them run as one batch (tb_contract_networks).  out_values[a - first] = value of assignment a + r
+ * (-inf when the assignment selects two adjacent vertices: such slices are not contracted at all);
+ * out_max = max over the range.  Ranks of a multi-GPU job call this with disjoint ranges and combine with
+ * one all-reduce(max).  out_values and out_status may be NULL. */
+int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced,
+                       int64_t first, int64_t count, double r, double* out_values, int32_t* out_status,
+                       double* out_max);
+
+/* Pick up to max_sliced labels to slice, greedily, until the largest tensor has rank <= sc_target
+ * (sc_target < 0: always pick max_sliced labels): each pick is the label whose removal leaves the smallest
+ * (sc, number of tensors of that rank, tc).  Host-only (no device work; ctx may be NULL).  Returns the number
+ * of labels written to out_labels (<= max_sliced) or a negative tb_status; out_sc / out_tc (may be NULL)
+ * receive the per-slice complexity after slicing. */
+int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int32_t max_sliced,
+                      int32_t* out_labels, double* out_sc, double* out_tc);
 
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */

@@ -137,13 +137,18 @@ def contract_pair(A: np.ndarray, la: Sequence[int], B: np.ndarray, lb: Sequence[
 
 
 def contract_tree(ixs, left, right, weights=None, dtype=np.float64, open_labels=(),
-                  keep_intermediates: bool = False):
-    """Evaluate the whole tree.  Returns (root_tensor, root_labels[, {tensor id: (labels, array)}])."""
+                  keep_intermediates: bool = False, fixed: Optional[Dict[int, int]] = None):
+    """Evaluate the whole tree.  Returns (root_tensor, root_labels[, {tensor id: (labels, array)}]).
+    fixed = {label: value}: index slicing -- every leaf carrying a fixed label is restricted to that index
+    and the label leaves the network (the max over all assignments of the fixed labels is the unsliced value)."""
     n_leaves = len(ixs)
+    vals: List[Optional[np.ndarray]] = [leaf_tensor(ix, weights, dtype) for ix in ixs]
+    if fixed:
+        vals = [np.asarray(v[tuple(fixed[l] if l in fixed else slice(None) for l in ix)]) for ix, v in zip(ixs, vals)]
+        ixs = [tuple(l for l in ix if l not in fixed) for ix in ixs]
     labs = node_output_labels(ixs, left, right, open_labels)
     if open_labels:
         labs[-1] = tuple(open_labels) if len(left) else labs[-1]
-    vals: List[Optional[np.ndarray]] = [leaf_tensor(ix, weights, dtype) for ix in ixs]
     inter = {}
     with np.errstate(invalid="ignore"):
         for j in range(len(left)):
@@ -172,11 +177,11 @@ def contract_tree(ixs, left, right, weights=None, dtype=np.float64, open_labels=
 # --------------------------------------------------------------------------------------------
 # the boundary functions
 # --------------------------------------------------------------------------------------------
-def solve_slice(branch, element_type=np.float32):
-    """/root/reference/src/dynamic_ob.jl:30-34."""
+def solve_slice(branch, element_type=np.float32, fixed: Optional[Dict[int, int]] = None):
+    """/root/reference/src/dynamic_ob.jl:30-34 (fixed: one index slice of it, see contract_tree)."""
     left, right = nested_to_postorder(branch.tree, len(branch.ixs))
     w = None if branch.weights is None else np.asarray(branch.weights).astype(element_type)
-    root, _ = contract_tree(branch.ixs, left, right, w, element_type)
+    root, _ = contract_tree(branch.ixs, left, right, w, element_type, fixed=fixed)
     return element_type(np.asarray(root).reshape(-1)[0])
 
 

@@ -95,12 +95,22 @@ def _network_bytes(branch: SlicedBranch, element_type, flags=0) -> bytes:
 class Plan:
     """Compiled, device-resident form of one branch's contraction (tb_plan)."""
 
-    def __init__(self, branch: SlicedBranch, element_type=np.float32, flags=0, engine: "Engine" = None):
+    def __init__(self, branch: SlicedBranch, element_type=np.float32, flags=0, engine: "Engine" = None,
+                 fixed: Optional[dict] = None):
+        """fixed: {label: 0 | 1} -- index slicing, the labels this contraction holds at one value."""
         lib = L.load()
         self._lib = lib
         self.handle = C.c_void_p()
         net, w = _network_of(branch, element_type, flags)
         self._keep = (branch, w)
+        if fixed:
+            net = L.tb_network.from_buffer_copy(bytes(net))
+            fl = np.asarray(list(fixed.keys()), dtype=np.int32)
+            fv = np.asarray([fixed[k] for k in fixed], dtype=np.uint8)
+            net.n_fixed = len(fl)
+            net.fixed_labels = fl.ctypes.data_as(C.POINTER(C.c_int32))
+            net.fixed_values = fv.ctypes.data_as(C.POINTER(C.c_uint8))
+            self._keep = (branch, w, fl, fv)
         L.check(lib.tb_plan_create(engine.handle if engine else None, C.byref(net), C.byref(self.handle)),
                 engine.handle if engine else None)
 
@@ -215,6 +225,23 @@ class Engine:
                                                status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mx)), self.handle)
         return out, status
 
+    def contract_index_sliced(self, branch: SlicedBranch, sliced_labels: Sequence[int], first: int = 0,
+                              count: Optional[int] = None, element_type=np.float32, flags=0):
+        """tb_contract_sliced: the 2^k assignments [first, first+count) of `sliced_labels` of ONE branch, each a
+        contraction of the same tree without those labels.  -> (values WITHOUT r, status, max)."""
+        lab = np.ascontiguousarray(sliced_labels, dtype=np.int32)
+        k = len(lab)
+        if count is None:
+            count = (1 << k) - first
+        net, _ = _network_of(branch, element_type, flags)
+        out = np.empty(max(count, 0), dtype=np.float64)
+        status = np.zeros(max(count, 0), dtype=np.int32)
+        mx = C.c_double()
+        L.check(self._lib.tb_contract_sliced(self.handle, C.byref(net), lab.ctypes.data_as(C.POINTER(C.c_int32)), k,
+                                             first, count, 0.0, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                             status.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(mx)), self.handle)
+        return out, status, mx.value
+
     def last_timing(self):
         ms = C.c_double()
         nl = C.c_int64()
@@ -296,6 +323,27 @@ def contract_slices(branches: Sequence[SlicedBranch], element_type=np.float32, u
     res = vals.astype(element_type) + r  # element_type arithmetic, as t + element_type(branch.r) in the reference
     res[empty] = r[empty]
     return res
+
+
+def suggest_slices(branch: SlicedBranch, sc_target: int = -1, max_sliced: int = 8):
+    """tb_suggest_slices: greedy choice of the labels to index-slice.  -> (labels, sc, tc) per slice afterwards."""
+    lib = L.load()
+    net, _ = _network_of(branch, np.float32, 0)
+    out = (C.c_int32 * max(max_sliced, 1))()
+    sc_ = C.c_double()
+    tc_ = C.c_double()
+    n = L.check(lib.tb_suggest_slices(None, C.byref(net), sc_target, max_sliced, out, C.byref(sc_), C.byref(tc_)))
+    return list(out[:n]), sc_.value, tc_.value
+
+
+def solve_slice_index_sliced(branch: SlicedBranch, sliced_labels: Sequence[int], element_type=np.float32,
+                             usecuda: bool = True, engine: Engine = None):
+    """solve_slice (src/dynamic_ob.jl:30-34) of ONE heavy branch computed as the max over the 2^k index slices of
+    `sliced_labels`: the same value, from 2^k independent contractions that can be sharded."""
+    _require_cuda(usecuda)
+    eng = engine or default_engine()
+    _, status, mx = eng.contract_index_sliced(branch, sliced_labels, element_type=element_type)
+    return np.dtype(element_type).type(mx)
 
 
 def complexity(branch: SlicedBranch):

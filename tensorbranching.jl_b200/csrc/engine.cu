@@ -1084,6 +1084,82 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     return rc;
 }
 
+int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced, int64_t first,
+                       int64_t count, double r, double* out_values, int32_t* out_status, double* out_max) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (!net || net->n_leaves < 1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL or empty");
+    if (net->n_fixed != 0) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "the network of tb_contract_sliced must not carry fixed labels itself");
+    if (n_sliced < 0 || n_sliced > 40 || (n_sliced > 0 && !sliced_labels)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad sliced labels (0 <= n_sliced <= 40)");
+    const int64_t n_assign = (int64_t)1 << n_sliced;
+    if (first < 0 || count < 0 || first + count > n_assign) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "assignment range outside [0, 2^n_sliced)");
+    // position of every sliced label; pairs of sliced labels joined by an edge leaf make an assignment infeasible
+    std::vector<int32_t> pos((size_t)std::max(net->n_labels, 1), -1);
+    for (int i = 0; i < n_sliced; ++i) {
+        int32_t l = sliced_labels[i];
+        if (l < 0 || l >= net->n_labels) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "sliced label out of range");
+        if (pos[l] >= 0) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "sliced label repeated");
+        pos[l] = i;
+    }
+    std::vector<uint64_t> conflicts;
+    if (!net->leaf_off) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "leaf_off is NULL");
+    for (int i = 0; i < net->n_leaves; ++i) {
+        int b = net->leaf_off[i], e = net->leaf_off[i + 1];
+        if (e - b != 2) continue;
+        int32_t u = net->leaf_labels[b], v = net->leaf_labels[b + 1];
+        if (u < 0 || v < 0 || u >= net->n_labels || v >= net->n_labels) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "leaf label out of range");
+        if (u != v && pos[u] >= 0 && pos[v] >= 0) conflicts.push_back((1ull << pos[u]) | (1ull << pos[v]));
+    }
+    const double ninf = -std::numeric_limits<double>::infinity();
+    std::vector<double> vals((size_t)count, ninf);
+    std::vector<int32_t> stat((size_t)count, TB_OK);
+    std::vector<int64_t> live;  // assignments that are contracted
+    for (int64_t a = first; a < first + count; ++a) {
+        bool ok = true;
+        for (uint64_t c : conflicts)
+            if (((uint64_t)a & c) == c) {
+                ok = false;
+                break;
+            }
+        if (ok) live.push_back(a);
+    }
+    int rc = TB_OK;
+    if (!live.empty()) {
+        const size_t nl = live.size();
+        std::vector<uint8_t> fv(nl * (size_t)std::max(n_sliced, 1));
+        std::vector<tb_network> nets(nl, *net);
+        for (size_t q = 0; q < nl; ++q) {
+            uint8_t* f = fv.data() + q * (size_t)std::max(n_sliced, 1);
+            for (int i = 0; i < n_sliced; ++i) f[i] = (uint8_t)((live[q] >> i) & 1);
+            nets[q].n_fixed = n_sliced;
+            nets[q].fixed_labels = sliced_labels;
+            nets[q].fixed_values = f;
+        }
+        std::vector<double> lv(nl), rr(nl, r);
+        std::vector<int32_t> ls(nl, TB_OK);
+        rc = tb_contract_networks(ctx, nets.data(), rr.data(), (int64_t)nl, lv.data(), ls.data(), nullptr);
+        for (size_t q = 0; q < nl; ++q) {
+            vals[(size_t)(live[q] - first)] = lv[q];
+            stat[(size_t)(live[q] - first)] = ls[q];
+        }
+    }
+    double mx = ninf;
+    for (int64_t i = 0; i < count; ++i)
+        if (stat[(size_t)i] == TB_OK && vals[(size_t)i] > mx) mx = vals[(size_t)i];
+    if (out_values) std::memcpy(out_values, vals.data(), (size_t)count * sizeof(double));
+    if (out_status) std::memcpy(out_status, stat.data(), (size_t)count * sizeof(int32_t));
+    if (out_max) *out_max = mx;
+    return rc;
+}
+
+int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int32_t max_sliced, int32_t* out_labels,
+                      double* out_sc, double* out_tc) {
+    if (!net) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL");
+    std::string err;
+    int rc = suggest_slices(*net, sc_target, max_sliced, out_labels, out_sc, out_tc, err);
+    if (rc < 0) return set_err(ctx, rc, err);
+    return rc;
+}
+
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap, int32_t* out_labels,
                         int32_t* out_rank) {
     if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");

@@ -151,7 +151,29 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     lab_data.reserve((size_t)nT0 * 8);
     auto labp = [&](int t) { return lab_data.data() + lab_off[t]; };
 
-    // ---- leaves
+    // ---- index slicing: fixed[l] = -1 (free) or the value label l is fixed to
+    std::vector<int8_t> fixed;
+    if (net.n_fixed < 0 || (net.n_fixed > 0 && (!net.fixed_labels || !net.fixed_values)))
+        return fail(TB_ERR_BAD_ARGUMENT, "bad fixed labels");
+    if (net.n_fixed > 0) {
+        fixed.assign(NLAB, -1);
+        for (int i = 0; i < net.n_fixed; ++i) {
+            int32_t l = net.fixed_labels[i];
+            if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "fixed label out of range");
+            if (fixed[l] >= 0) return fail(TB_ERR_BAD_ARGUMENT, "fixed label repeated");
+            if (net.fixed_values[i] > 1) return fail(TB_ERR_BAD_ARGUMENT, "fixed value must be 0 or 1");
+            fixed[l] = (int8_t)net.fixed_values[i];
+        }
+        for (int i = 0; i < net.n_open; ++i)
+            if (net.open_labels[i] >= 0 && net.open_labels[i] < net.n_labels && fixed[net.open_labels[i]] >= 0)
+                return fail(TB_ERR_BAD_ARGUMENT, "a label cannot be both open and fixed");
+    }
+
+    // ---- leaves.  leaf_vertex[i] = vertex of a vertex leaf (-1: edge / unit leaf).  A leaf that lost labels to
+    //      index slicing reads a slice of its tensor: leaf_src[i] = fixed pool offset (-1: the tensor as a whole),
+    //      leaf_wsel[i] = 1 when a vertex leaf became the scalar w_v (the second element of its pool pair).
+    std::vector<int32_t> leaf_vertex(nL, -1), leaf_src(nL, -1);
+    std::vector<uint8_t> leaf_wsel(nL, 0);
     for (int i = 0; i < nL; ++i) leaf[i] = 1;
     for (int i = 0; i < net.n_leaves; ++i) {
         int b = net.leaf_off[i], e = net.leaf_off[i + 1];
@@ -161,16 +183,34 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             return fail(TB_ERR_UNSUPPORTED, "leaf " + std::to_string(i) + " has " + std::to_string(r) +
                                                 " labels; IndependentSet leaves have 1 (vertex) or 2 (edge)");
         lab_off[i] = (int32_t)lab_data.size();
-        lab_n[i] = (uint8_t)r;
+        int nfix = 0, nset = 0;  // fixed labels of this leaf / how many of them are fixed to 1
         for (int q = b; q < e; ++q) {
             int32_t l = net.leaf_labels[q];
             if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "leaf label out of range");
-            lab_data.push_back(l);
+            if (!fixed.empty() && fixed[l] >= 0) {
+                ++nfix;
+                nset += fixed[l];
+            } else {
+                lab_data.push_back(l);
+            }
         }
-        if (r == 2) {
+        if (r == 2 && net.leaf_labels[b] == net.leaf_labels[b + 1])
+            return fail(TB_ERR_UNSUPPORTED, "edge tensor with a repeated label (self loop)");
+        if (r == 1) leaf_vertex[i] = net.leaf_labels[b];
+        lab_n[i] = (uint8_t)(r - nfix);
+        if (lab_n[i] == 2) {
             int32_t* v = lab_data.data() + lab_off[i];
-            if (v[0] == v[1]) return fail(TB_ERR_UNSUPPORTED, "edge tensor with a repeated label (self loop)");
             if (v[0] > v[1]) std::swap(v[0], v[1]);
+        }
+        if (nfix) {
+            if (r == 1) {  // [0, w][x]
+                if (nset) leaf_wsel[i] = 1;
+                else leaf_src[i] = POOL_UNIT;
+            } else if (nfix == 1) {  // the edge tensor is symmetric: row 0 = (0, 0), row 1 = (0, -inf)
+                leaf_src[i] = POOL_EDGE + 2 * nset;
+            } else {  // both ends fixed: -inf iff both are 1
+                leaf_src[i] = nset == 2 ? POOL_EDGE + 3 : POOL_UNIT;
+            }
         }
     }
     if (synth) lab_off[1] = (int32_t)lab_data.size();
@@ -226,8 +266,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         double sum_abs = 0;
         bool integral = true;
         for (int i = 0; i < net.n_leaves; ++i)
-            if (lab_n[i] == 1) {
-                double w = weight_of(labp(i)[0]);
+            if (leaf_vertex[i] >= 0) {
+                double w = weight_of(leaf_vertex[i]);
                 integral = integral && (w == std::floor(w));
                 sum_abs += std::fabs(w);
             }
@@ -687,19 +727,22 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         double sum_abs = 0;
         for (int i = 0; i < nT; ++i) {
             if (!leaf[i]) continue;
-            if (lab_n[i] == 0) {
+            const int vtx = i < nL ? leaf_vertex[i] : -1;
+            if (i < nL && leaf_src[i] >= 0) {
+                leaf_pool_off[i] = leaf_src[i];
+            } else if (vtx < 0 && lab_n[i] == 0) {
                 leaf_pool_off[i] = POOL_UNIT;
-            } else if (lab_n[i] == 2) {
+            } else if (vtx < 0) {
                 leaf_pool_off[i] = POOL_EDGE;
             } else {
-                double w = weight_of(labp(i)[0]);
+                double w = weight_of(vtx);
                 if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
                 if (vt != TB_VALUE_F32) {
                     if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
                     sum_abs += std::fabs(w);
                     if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
                 }
-                leaf_pool_off[i] = (int32_t)P.pool.size();
+                leaf_pool_off[i] = (int32_t)P.pool.size() + leaf_wsel[i];
                 push_val(0, false);
                 push_val(w, false);
             }
@@ -1122,6 +1165,125 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     S.generic_ops = ops_g;
     S.gemm_bytes = bytes_m;
     return TB_OK;
+}
+
+// Greedy choice of the labels to slice (tb_suggest_slices).  Works on the label sets of the given tree only:
+// for every node the labels involved (union of the operands) and the labels it keeps; removing label l
+// shrinks every set that holds it by one.  Each pick minimises (sc, number of tensors of rank sc, ops).
+int suggest_slices(const tb_network& net, int sc_target, int max_sliced, int32_t* out_labels, double* out_sc,
+                   double* out_tc, std::string& err) {
+    auto fail = [&](int code, const std::string& m) {
+        err = m;
+        return code;
+    };
+    if (net.n_leaves < 1 || !net.leaf_off) return fail(TB_ERR_BAD_ARGUMENT, "network has no leaves");
+    if (net.n_fixed != 0) return fail(TB_ERR_BAD_ARGUMENT, "network already carries fixed labels");
+    if (max_sliced < 0 || (max_sliced > 0 && !out_labels)) return fail(TB_ERR_BAD_ARGUMENT, "bad max_sliced / out_labels");
+    const int nL = net.n_leaves, nN = nL - 1, nT = nL + nN;
+    if (nN > 0 && (!net.node_left || !net.node_right)) return fail(TB_ERR_BAD_ARGUMENT, "node_left / node_right is NULL");
+    const int NLAB = std::max(net.n_labels, 1);
+    // occurrences of each label over the leaves, and per subtree (small-to-large merging would be faster; trees here
+    // have a few thousand nodes and the sets are short, so sorted-vector merges are enough)
+    std::vector<int32_t> total(NLAB, 0);
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> cnt(nT);  // (label, occurrences in the subtree), open labels only
+    std::vector<uint8_t> is_open(NLAB, 0);
+    for (int i = 0; i < net.n_open; ++i) {
+        int32_t l = net.open_labels[i];
+        if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "open label out of range");
+        is_open[l] = 1;
+    }
+    for (int i = 0; i < nL; ++i) {
+        int b = net.leaf_off[i], e = net.leaf_off[i + 1];
+        if (e < b || e - b > 2) return fail(TB_ERR_UNSUPPORTED, "leaf with more than 2 labels");
+        for (int q = b; q < e; ++q) {
+            int32_t l = net.leaf_labels[q];
+            if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "leaf label out of range");
+            ++total[l];
+            cnt[i].push_back({l, 1});
+        }
+        std::sort(cnt[i].begin(), cnt[i].end());
+    }
+    // per node: involved labels (set_in) and kept labels (set_out), flattened
+    std::vector<int32_t> in_off(nN + 1, 0), out_off(nN + 1, 0), in_data, out_data;
+    std::vector<uint8_t> used(nT, 0);
+    for (int j = 0; j < nN; ++j) {
+        const int a = net.node_left[j], b = net.node_right[j], t = nL + j;
+        if (a < 0 || a >= t || b < 0 || b >= t || a == b || used[a] || used[b])
+            return fail(TB_ERR_NOT_BINARY_TREE, "tree arrays do not describe a binary tree over the leaves");
+        used[a] = used[b] = 1;
+        auto &ca = cnt[a], &cb = cnt[b];
+        auto& ct = cnt[t];
+        ct.reserve(ca.size() + cb.size());
+        size_t x = 0, y = 0;
+        while (x < ca.size() || y < cb.size()) {
+            std::pair<int32_t, int32_t> m;
+            if (y >= cb.size() || (x < ca.size() && ca[x].first < cb[y].first)) m = ca[x++];
+            else if (x >= ca.size() || cb[y].first < ca[x].first) m = cb[y++];
+            else {
+                m = {ca[x].first, ca[x].second + cb[y].second};
+                ++x;
+                ++y;
+            }
+            in_data.push_back(m.first);
+            if (m.second < total[m.first] || is_open[m.first]) {
+                ct.push_back(m);
+                out_data.push_back(m.first);
+            }
+        }
+        in_off[j + 1] = (int32_t)in_data.size();
+        out_off[j + 1] = (int32_t)out_data.size();
+        std::vector<std::pair<int32_t, int32_t>>().swap(ca);
+        std::vector<std::pair<int32_t, int32_t>>().swap(cb);
+    }
+    std::vector<uint8_t> removed(NLAB, 0);
+    std::vector<int32_t> rank_out(std::max(nN, 1), 0), rank_in(std::max(nN, 1), 0);
+    std::vector<int32_t> n_top(NLAB, 0);
+    std::vector<double> gain(NLAB, 0.0);
+    int n_picked = 0;
+    double sc = 0, ops = 0;
+    for (;;) {
+        sc = 0;
+        ops = 0;
+        for (int i = 0; i < nL; ++i) {  // leaves count towards sc too (types.jl:121)
+            int r = 0;
+            for (int q = net.leaf_off[i]; q < net.leaf_off[i + 1]; ++q) r += !removed[net.leaf_labels[q]];
+            sc = std::max(sc, (double)r);
+        }
+        for (int j = 0; j < nN; ++j) {
+            int ro = 0, ri = 0;
+            for (int q = out_off[j]; q < out_off[j + 1]; ++q) ro += !removed[out_data[q]];
+            for (int q = in_off[j]; q < in_off[j + 1]; ++q) ri += !removed[in_data[q]];
+            rank_out[j] = ro;
+            rank_in[j] = ri;
+            sc = std::max(sc, (double)ro);
+            ops += std::ldexp(1.0, ri);
+        }
+        if (n_picked >= max_sliced || (sc_target >= 0 && sc <= sc_target)) break;
+        std::fill(n_top.begin(), n_top.end(), 0);
+        std::fill(gain.begin(), gain.end(), 0.0);
+        int tops = 0;
+        for (int j = 0; j < nN; ++j) {
+            if (rank_out[j] == (int)sc) {
+                ++tops;
+                for (int q = out_off[j]; q < out_off[j + 1]; ++q)
+                    if (!removed[out_data[q]]) ++n_top[out_data[q]];
+            }
+            const double half = std::ldexp(1.0, rank_in[j] - 1);
+            for (int q = in_off[j]; q < in_off[j + 1]; ++q)
+                if (!removed[in_data[q]]) gain[in_data[q]] += half;
+        }
+        int best = -1;
+        for (int l = 0; l < net.n_labels; ++l) {
+            if (removed[l] || is_open[l] || total[l] == 0) continue;
+            if (best < 0 || n_top[l] > n_top[best] || (n_top[l] == n_top[best] && gain[l] > gain[best])) best = l;
+        }
+        if (best < 0 || (tops > 0 && n_top[best] == 0 && gain[best] == 0.0)) break;
+        removed[best] = 1;
+        out_labels[n_picked++] = best;
+    }
+    if (out_sc) *out_sc = sc;
+    if (out_tc) *out_tc = ops > 0 ? std::log2(ops) : 0.0;
+    return n_picked;
 }
 
 tb_step_info Plan::step_info(size_t i) const {

@@ -65,6 +65,10 @@ struct Plan {
 // returns a tb_status; on failure `err` holds the message
 int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& plan, std::string& err);
 
+// greedy label choice for index slicing (tb_suggest_slices); returns the number of labels picked or a tb_status
+int suggest_slices(const tb_network& net, int sc_target, int max_sliced, int32_t* out_labels, double* out_sc,
+                   double* out_tc, std::string& err);
+
 // serialise pool | SubStep[] | BigStep[] (16-byte aligned sections) for upload
 void build_blob(Plan& plan, std::vector<uint8_t>& blob);
 

@@ -69,3 +69,36 @@ def contract_slices_distributed(branches, element_type=np.float32, engine=None, 
         vals = local_contract(shard)
     full = allreduce_max_vector(np.asarray(vals, dtype=np.float64), mine, n, device=device, group=group)
     return full.astype(element_type)
+
+
+def slice_range(n_assign: int, world: int, rank: int):
+    """Contiguous share [first, first + count) of the 2^k assignments for `rank` (slices of one branch cost the same)."""
+    base, extra = divmod(n_assign, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def solve_slice_index_sliced_distributed(branch, sliced_labels, element_type=np.float32, engine=None, group=None,
+                                         local_contract: Optional[Callable] = None, device=None):
+    """ONE heavy branch over all ranks: the 2^k assignments of `sliced_labels` are dealt to the ranks in
+    contiguous ranges, every rank contracts its range (tb_contract_sliced), and one all-reduce(max) over the length-2^k
+    vector gives every rank every slice value.  Returns (value_of_the_branch, per-slice values), r not included.
+    `local_contract(first, count) -> values` replaces the engine in CPU tests of the plumbing."""
+    import torch.distributed as dist
+
+    k = len(sliced_labels)
+    n = 1 << k
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    first, count = slice_range(n, world, rank)
+    if count == 0:
+        vals = np.empty(0)
+    elif local_contract is None:
+        from .contract import default_engine
+        eng = engine or default_engine()
+        vals, status, _ = eng.contract_index_sliced(branch, sliced_labels, first, count, element_type)
+    else:
+        vals = local_contract(first, count)
+    full = allreduce_max_vector(np.asarray(vals, dtype=np.float64), np.arange(first, first + count), n, device=device,
+                                group=group)
+    return np.dtype(element_type).type(full.max()), full.astype(element_type)

@@ -61,6 +61,43 @@ def test_two_rank_sharded_contract_slices(tmp_path):
     assert n0 + n1 == len(rec["values"]) and n0 > 0 and n1 > 0  # no unit contracted twice, both ranks worked
 
 
+def _worker_sliced(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+
+    import tbcuda
+    from tbcuda.multi_gpu import solve_slice_index_sliced_distributed
+    from oracle import tropical_oracle as O
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    b = [x for x in golden_branches(load_golden("rr100_sc10_unit.json")) if x.nv >= 12][0]
+    br = to_sliced(b)
+    labels, _, _ = tbcuda.suggest_slices(br, -1, 3)
+    seen = []
+
+    def local(first, count):
+        seen.append((first, count))
+        return [O.solve_slice(b, np.float64, fixed={l: (a >> i) & 1 for i, l in enumerate(labels)})
+                for a in range(first, first + count)]
+
+    val, full = solve_slice_index_sliced_distributed(br, labels, np.float32, local_contract=local)
+    np.save(os.path.join(out_dir, f"s{rank}.npy"), np.concatenate([[val, O.solve_slice(b, np.float32)], full,
+                                                                   np.asarray(seen[0], dtype=np.float64)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_index_sliced_branch(tmp_path):
+    """one branch, 2^3 index slices dealt to 2 ranks, one all-reduce(max): both ranks get the unsliced value."""
+    port = _free_port()
+    mp.spawn(_worker_sliced, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    s0, s1 = np.load(tmp_path / "s0.npy"), np.load(tmp_path / "s1.npy")
+    assert np.array_equal(s0[:-2], s1[:-2])
+    assert s0[0] == s0[1] and s0[2:10].max() == s0[0]
+    assert tuple(s0[-2:]) == (0, 4) and tuple(s1[-2:]) == (4, 4)
+
+
 def test_lpt_balances():
     from tbcuda.multi_gpu import shard_lpt
 
