@@ -37,8 +37,17 @@ WORKLOADS = {
     "cfg2": ("regular", dict(n=200, d=3, seed=2), 20, None),
     "cfg2s": ("regular", dict(n=160, d=3, seed=2), 18, None),
     "cfg3": ("ksg", dict(m=30, n=30, rho=0.8, seed=3), 24, None),
+    # the full branch set of n=500 at sc 28 is far beyond one bench step (the stand-in host's greedy tree starts at
+    # sc 86): a step contracts the first 32 branches the depth-first slicer finishes, 2^45.5 tropical ops
+    "cfg4": ("regular", dict(n=500, d=3, seed=4), 28, 32),
     "cfg5": ("regular_many", dict(n=150, d=3, seed0=1000, count=1024), 16, None),
 }
+# index slicing: every branch is cut into 2^k independent slices (k labels fixed).  cfg3's stand-in
+# branch list is ONE branch (the kernelised KSG already has sc 23 <= 24), so slices are the only units to shard.
+DEFAULT_SLICE_K = {"cfg3": 3}
+# branches too heavy for the CPU legs (one cfg4 branch is minutes of CPU time): the CPU sample is made of index
+# slices of one branch, cut with this many labels
+CPU_SLICE_K = {"cfg4": 10}
 
 
 def make_workload(name, max_branches=None):
@@ -154,6 +163,47 @@ def dpx_peak():
         return {"error": str(e)}
 
 
+def python_slice_labels(branch, k):
+    """k labels to index-slice, chosen on the host without libtbcuda (the reference arm must not touch the engine):
+    the labels carried by most large intermediates (workloads.standin_host.big_label_histogram)."""
+    from workloads import standin_host as H
+
+    sc, _ = H.tree_complexity(branch.ixs, branch.tree)
+    hist = H.big_label_histogram(branch.ixs, branch.tree, max(0, int(sc) - 6))
+    return [l for l, _ in sorted(hist.items(), key=lambda kv: (-kv[1], kv[0]))[:k]]
+
+
+def feasible_assignments(branch, labels):
+    es = set(map(tuple, branch.edges))
+    bad = [(i, j) for i in range(len(labels)) for j in range(i) if (min(labels[i], labels[j]), max(labels[i], labels[j])) in es]
+    return [a for a in range(1 << len(labels)) if not any((a >> i) & 1 and (a >> j) & 1 for i, j in bad)]
+
+
+def cpu_reference_run_sliced(branches, budget_s, k):
+    """CPU sample for workloads whose single branches are minutes of CPU work: index slices (k labels fixed) of the
+    first sc-maximal branch, one slice per core at a time.  -> (Gop/s, cores, sample, seconds, (branch index, labels,
+    assignments, values))"""
+    from oracle import c_oracle as CO
+    from workloads import standin_host as H
+
+    scs = [H.tree_complexity(b.ixs, b.tree)[0] if b.nv else 0 for b in branches[:8]]
+    bi = int(np.argmax(scs))
+    br = branches[bi]
+    labels = python_slice_labels(br, k)
+    assign = feasible_assignments(br, labels)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    t = time.perf_counter()
+    v0, o0, th = CO.contract_index_slices(br, labels, assign[:cores])
+    dt0 = max(time.perf_counter() - t, 1e-6)
+    n = int(min(len(assign), max(cores, cores * int(budget_s / dt0))))
+    t = time.perf_counter()
+    vals, ops, th = CO.contract_index_slices(br, labels, assign[:n])
+    dt = time.perf_counter() - t
+    sample = (f"{n} of the {len(assign)} feasible index slices (k={len(labels)} labels fixed) of branch {bi} of the workload, "
+              f"{dt:.1f} s")
+    return float(ops.sum()) / dt * 1e-9, th, sample, dt, (bi, labels, assign[:n], vals)
+
+
 def cpu_reference_run(branches, budget_s, ops_per_branch):
     """Time the oracle's C/OpenMP port on a bounded sample (heaviest-first prefix would bias; take
     branches in order until the budget).  -> (Gop/s, cores, sample description, seconds)"""
@@ -181,6 +231,8 @@ def main():
     ap.add_argument("--impl", default="tbcuda", choices=["tbcuda", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--max-branches", type=int, default=None)
+    ap.add_argument("--slice-k", type=int, default=None,
+                    help="index-slice every branch into 2^k units (default: per workload, 0 except cfg3)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -191,8 +243,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl_kind, wl_p, sc_target, _ = WORKLOADS[args.workload]
-    config = {"workload": f"{args.workload}: {wl_kind} {wl_p}, sc_target={sc_target}, unit weights, stand-in host branching",
+    wl_kind, wl_p, sc_target, wl_mb = WORKLOADS[args.workload]
+    wl_mb = args.max_branches or wl_mb
+    config = {"workload": f"{args.workload}: {wl_kind} {wl_p}, sc_target={sc_target}, unit weights, stand-in host branching" +
+                          (f", first {wl_mb} finished branches of the depth-first slicer" if wl_mb else ""),
               "l2": "per-step working set (arena + descriptors) exceeds the 126 MB L2; no explicit flush"}
 
     # ---------------------------------------------------------------- reference arm (CPU)
@@ -205,7 +259,10 @@ def main():
         per_step = max(3.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
         gops = []
         for i in range(args.warmup + args.steps):
-            g, cores, sample, dt, _ = cpu_reference_run(branches, per_step, None)
+            if args.workload in CPU_SLICE_K:
+                g, cores, sample, dt, _ = cpu_reference_run_sliced(branches, per_step, CPU_SLICE_K[args.workload])
+            else:
+                g, cores, sample, dt, _ = cpu_reference_run(branches, per_step, None)
             if i >= args.warmup:
                 gops.append((g, dt))
         value = float(np.mean([g for g, _ in gops]))
@@ -249,9 +306,26 @@ def main():
                         host_threads=max(1, host_cores // world))  # ranks share the host's cores for plan compilation
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
-    # plans for every branch (host-only compile) to get costs; then keep only this rank's shard
+    # units of work: one per branch, or (index slicing) one per feasible assignment of the k sliced labels of a branch
+    slice_k = args.slice_k if args.slice_k is not None else DEFAULT_SLICE_K.get(args.workload, 0)
+    units = []  # (branch index, {label: value} or None)
+    slice_labels = {}
+    for i, s in enumerate(sliced):
+        if s.code is None or slice_k <= 0:
+            units.append((i, None))
+            continue
+        slice_labels[i] = tbcuda.suggest_slices(s, -1, slice_k)[0]
+        for a in feasible_assignments(branches[i], slice_labels[i]):
+            units.append((i, {l: (a >> q) & 1 for q, l in enumerate(slice_labels[i])}))
+    n_units = len(units)
+    ub = np.array([u[0] for u in units], dtype=np.int64)
+    if slice_k > 0:
+        config["index_slicing"] = f"every branch cut into 2^{slice_k} index slices (tb_suggest_slices), {n_units} units"
+
+    # plans for every unit (host-only compile) to get costs; then keep only this rank's shard
     t0 = time.perf_counter()
-    all_plans = [tbcuda.Plan(s, np.float32, engine=eng) if s.code is not None else None for s in sliced]
+    all_plans = [tbcuda.Plan(sliced[i], np.float32, engine=eng, fixed=fx) if sliced[i].code is not None else None
+                 for i, fx in units]
     plan_s = time.perf_counter() - t0
     stats = [p.info() if p is not None else None for p in all_plans]
     ops = np.array([s.ops if s else 0.0 for s in stats])
@@ -259,35 +333,54 @@ def main():
     owner = lpt_shards(ops, world)
     mine = np.nonzero(owner == rank)[0]
     my_plans = [all_plans[i] for i in mine]
-    my_sliced = [sliced[i] for i in mine]
+    my_sliced = [sliced[ub[i]] for i in mine]
     for i in np.nonzero(owner != rank)[0]:
         if all_plans[i] is not None:
             all_plans[i].close()
     total_ops = float(ops.sum())
     r_vec = np.array([b.r for b in branches], dtype=np.float64)
+    r_units = r_vec[ub]
 
-    res_dev = torch.full((n_br,), -float("inf"), dtype=torch.float64, device="cuda")
+    res_dev = torch.full((n_units,), -float("inf"), dtype=torch.float64, device="cuda")
+    mine_dev = torch.from_numpy(mine).cuda()
 
-    def step_resident():
-        vals, status, _ = eng.contract_plans(my_plans, r_vec[mine])
-        if world > 1:
-            res_dev.fill_(-float("inf"))
-            res_dev[torch.from_numpy(mine).cuda()] = torch.from_numpy(vals).cuda()
-            dist.all_reduce(res_dev, op=dist.ReduceOp.MAX)
-            return res_dev.cpu().numpy()
+    def per_branch(unit_vals, idx):
         out = np.full(n_br, -np.inf)
-        out[mine] = vals
+        np.maximum.at(out, ub[idx], unit_vals)
         return out
 
-    def step_e2e():
-        vals = tbcuda.contract_slices(my_sliced, np.float32, True, engine=eng).astype(np.float64)
+    def gather_units(vals):
+        """every rank's unit values -> the per-branch vector on every rank: ONE all-reduce(max)"""
         if world > 1:
             res_dev.fill_(-float("inf"))
-            res_dev[torch.from_numpy(mine).cuda()] = torch.from_numpy(vals).cuda()
+            res_dev[mine_dev] = torch.from_numpy(np.ascontiguousarray(vals)).cuda()
             dist.all_reduce(res_dev, op=dist.ReduceOp.MAX)
-            return res_dev.cpu().numpy()
+            return per_branch(res_dev.cpu().numpy(), np.arange(n_units))
+        return per_branch(vals, mine)
+
+    def step_resident():
+        vals, status, _ = eng.contract_plans(my_plans, r_units[mine])
+        return gather_units(vals)
+
+    from tbcuda.multi_gpu import slice_range
+
+    def step_e2e():
+        if slice_k <= 0:
+            vals = tbcuda.contract_slices(my_sliced, np.float32, True, engine=eng).astype(np.float64)
+            return gather_units(vals)
+        # index slicing through the public call: every rank contracts its contiguous range of each branch's 2^k
+        # assignments (tb_contract_sliced), then one all-reduce(max) over the per-branch vector
         out = np.full(n_br, -np.inf)
-        out[mine] = vals
+        first, count = slice_range(1 << slice_k, world, rank)
+        for i, s in enumerate(sliced):
+            if s.code is None:
+                out[i] = r_vec[i]
+            elif count > 0:
+                out[i] = eng.contract_index_sliced(s, slice_labels[i], first, count)[2] + r_vec[i]
+        if world > 1:
+            t = torch.from_numpy(out).cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out = t.cpu().numpy()
         return out
 
     def timed(fn, steps, warmup, sampler=None):
@@ -338,10 +431,12 @@ def main():
         hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(hb)
+        if slice_k > 0:  # tb_last_transfers covers one call; a sliced step makes one call per branch
+            hb *= sum(1 for s in sliced if s.code is not None)
         e2e = {"value": total_ops / (ms_e2e * 1e-3) * 1e-9, "unit": "Gop/s", "h2d_bytes_per_step": int(hb[0].item()),
                "host_breakdown_rank0": eng.last_host_breakdown(),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": ms_e2e,
-               "slices_per_s": n_br / (ms_e2e * 1e-3)}
+               "slices_per_s": n_units / (ms_e2e * 1e-3)}
         assert np.array_equal(result_e2e, result)
 
     if rank == 0:
@@ -371,7 +466,7 @@ def main():
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "ms_per_step_median_rank0": per_step_ms[len(per_step_ms) // 2], "ms_per_step_max_rank0": per_step_ms[-1],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "int16x2" if args.value_type == "i16" else "int32", "data": "synthetic", "config": config, "slices_per_s": n_br / (ms_step * 1e-3), "branches": n_br,
+                "dtype": "int16x2" if args.value_type == "i16" else "int32", "data": "synthetic", "config": config, "slices_per_s": n_units / (ms_step * 1e-3), "branches": n_br, "units": n_units,
                 "total_ops": total_ops, "mis": float(np.max(result)), "gpu_launches": int(launches_step * args.steps),
                 "launches_per_step": int(launches_step), "device_ms_last_step": dev_ms_last,
                 "plan_compile_s_all_branches": plan_s, "clocks": clocks, "roofline": roofline, "dpx_peak": dpx}
@@ -379,11 +474,17 @@ def main():
             line["e2e"] = e2e
         if not args.no_cpu_baseline:
             G.build()
-            g, cores, sample, dt, vals = cpu_reference_run(branches, args.cpu_budget, None)
-            n = len(vals)
-            cpu_vals = vals + r_vec[:n]
+            if args.workload in CPU_SLICE_K:
+                g, cores, sample, dt, (bi, labels, assign, vals) = cpu_reference_run_sliced(branches, args.cpu_budget,
+                                                                                           CPU_SLICE_K[args.workload])
+                gv = eng.contract_index_sliced(sliced[bi], labels, 0, max(assign) + 1)[0]
+                agrees = bool(np.array_equal(gv[np.asarray(assign)], vals))
+            else:
+                g, cores, sample, dt, vals = cpu_reference_run(branches, args.cpu_budget, None)
+                n = len(vals)
+                agrees = bool(np.array_equal(vals + r_vec[:n], result[:n]))
             line["cpu_baseline"] = {"value": g, "unit": "Gop/s", "cores": cores, "kind": "port", "sample": sample,
-                                    "agrees_with_gpu": bool(np.array_equal(cpu_vals, result[:n]))}
+                                    "agrees_with_gpu": agrees}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

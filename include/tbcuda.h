@@ -201,9 +201,10 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
                        int64_t first, int64_t count, double r, double* out_values, int32_t* out_status,
                        double* out_max);
 
-/* Pick up to max_sliced labels to slice, greedily, until the largest tensor has rank <= sc_target
- * (sc_target < 0: always pick max_sliced labels): each pick is the label whose removal leaves the smallest
- * (sc, number of tensors of that rank, tc).  Host-only (no device work; ctx may be NULL).  Returns the number
+/* Pick up to max_sliced labels to slice, greedily.  sc_target >= 0 (memory-driven): until the largest tensor has
+ * rank <= sc_target, each pick is the label held by most tensors of the current top rank (ties: most ops removed).
+ * sc_target < 0 (parallelism-driven): always max_sliced labels, each pick the label whose removal takes away most
+ * ops, i.e. the least total overhead of the 2^k slices.  Host-only (no device work; ctx may be NULL).  Returns the number
  * of labels written to out_labels (<= max_sliced) or a negative tb_status; out_sc / out_tc (may be NULL)
  * receive the per-slice complexity after slicing. */
 int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int32_t max_sliced,

@@ -113,8 +113,11 @@ static int in_list(const int* v, int n, int x) {
 }
 
 /* returns 0 on success */
-int tref_contract(int n_labels, int n_leaves, const int* leaf_off, const int* leaf_labels, const int* left,
-                  const int* right, const double* weights, double* out_value, double* out_ops) {
+/* fixed (may be NULL): per label -1 = free, 0 / 1 = index slicing, the label is held at that value: every leaf
+ * carrying it is restricted to that index and the label leaves the network. */
+int tref_contract_fixed(int n_labels, int n_leaves, const int* leaf_off, const int* leaf_labels, const int* left,
+                        const int* right, const double* weights, const signed char* fixed, double* out_value,
+                        double* out_ops) {
     int n_nodes = n_leaves - 1, n_t = n_leaves + (n_nodes > 0 ? n_nodes : 0);
     tens* T = (tens*)calloc((size_t)n_t, sizeof(tens));
     int* total = (int*)calloc((size_t)(n_labels > 0 ? n_labels : 1), sizeof(int));
@@ -139,6 +142,22 @@ int tref_contract(int n_labels, int n_leaves, const int* leaf_off, const int* le
         } else {
             free(T); free(total); free(cnt);
             return -3;
+        }
+        if (fixed) {
+            for (int q = r - 1; q >= 0; --q) {
+                int l = T[i].labels[q];
+                if (fixed[l] < 0) continue;
+                /* keep index fixed[l] of position q */
+                int rk = T[i].rank;
+                size_t lo = (size_t)1 << q, n_out = (size_t)1 << (rk - 1);
+                for (size_t o = 0; o < n_out; ++o) {
+                    size_t src = (o & (lo - 1)) | ((o & ~(lo - 1)) << 1) | ((size_t)fixed[l] << q);
+                    T[i].data[o] = T[i].data[src];
+                }
+                total[l]--;
+                for (int z = q; z + 1 < rk; ++z) { T[i].labels[z] = T[i].labels[z + 1]; cnt[i][z] = cnt[i][z + 1]; }
+                T[i].rank = rk - 1;
+            }
         }
     }
     for (int j = 0; j < n_nodes; ++j) {
@@ -229,6 +248,11 @@ int tref_contract(int n_labels, int n_leaves, const int* leaf_off, const int* le
     return 0;
 }
 
+int tref_contract(int n_labels, int n_leaves, const int* leaf_off, const int* leaf_labels, const int* left,
+                  const int* right, const double* weights, double* out_value, double* out_ops) {
+    return tref_contract_fixed(n_labels, n_leaves, leaf_off, leaf_labels, left, right, weights, NULL, out_value, out_ops);
+}
+
 /* the loop of contract_slices, branches distributed over OpenMP threads (the most favourable CPU
  * arrangement: every core runs its own branch end to end).  Network i is described by the i-th
  * entries of the pointer arrays.  Returns the number of threads used. */
@@ -238,6 +262,24 @@ void tref_set_threads(int n) {
 #else
     (void)n;
 #endif
+}
+
+/* index slices of ONE network: slice i holds the labels with fixed[i * n_labels + l] >= 0 at that value */
+int tref_contract_slices_of(int n, int n_labels, int n_leaves, const int* leaf_off, const int* leaf_labels,
+                            const int* left, const int* right, const double* weights, const signed char* fixed,
+                            double* out_values, double* out_ops) {
+    int nthreads = 1;
+#ifdef _OPENMP
+    nthreads = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n; ++i) {
+        double ops = 0;
+        tref_contract_fixed(n_labels, n_leaves, leaf_off, leaf_labels, left, right, weights,
+                            fixed + (size_t)i * (size_t)n_labels, &out_values[i], &ops);
+        if (out_ops) out_ops[i] = ops;
+    }
+    return nthreads;
 }
 
 int tref_contract_batch(int n, const int* n_labels, const int* n_leaves, const int* const* leaf_off,

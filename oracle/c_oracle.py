@@ -89,3 +89,30 @@ def contract_slices(branches, element_type=np.float32):
     vals, _, _ = contract_batch(flats)
     et = np.dtype(element_type).type
     return np.asarray([et(b.r) if b.nv == 0 else et(et(v) + et(b.r)) for b, v in zip(branches, vals)], dtype=element_type)
+
+
+def contract_index_slices(branch, sliced_labels, assignments):
+    """Index slices of ONE branch on the C oracle, one slice per OpenMP thread: assignment a holds
+    sliced_labels[i] at bit i of a.  -> (values float64 WITHOUT r, ops float64, threads)."""
+    lib = load()
+    nlab, off, labs, left, right, w = flatten(branch)
+    off = np.ascontiguousarray(off, dtype=np.int32)
+    labs = np.ascontiguousarray(labs, dtype=np.int32)
+    left = np.ascontiguousarray(left, dtype=np.int32)
+    right = np.ascontiguousarray(right, dtype=np.int32)
+    assignments = list(assignments)
+    n = len(assignments)
+    fixed = np.full((max(n, 1), max(nlab, 1)), -1, dtype=np.int8)
+    for q, a in enumerate(assignments):
+        for i, l in enumerate(sliced_labels):
+            fixed[q, l] = (a >> i) & 1
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    vals = np.zeros(n, dtype=np.float64)
+    ops = np.zeros(n, dtype=np.float64)
+    lib.tref_contract_slices_of.restype = C.c_int
+    th = lib.tref_contract_slices_of(n, nlab, len(off) - 1, off.ctypes.data_as(ip), labs.ctypes.data_as(ip),
+                                     left.ctypes.data_as(ip), right.ctypes.data_as(ip),
+                                     w.ctypes.data_as(dp) if w is not None else None,
+                                     fixed.ctypes.data_as(C.POINTER(C.c_int8)), vals.ctypes.data_as(dp),
+                                     ops.ctypes.data_as(dp))
+    return vals, ops, th

@@ -338,7 +338,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 }
             }
         }
-        if (nu > 40) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 40 labels");
+        if (nu > 62) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 62 labels");
         lab_off[t] = (int32_t)lab_data.size();
         int no = 0;
         for (int q = 0; q < nu; ++q) {
@@ -1275,7 +1275,12 @@ int suggest_slices(const tb_network& net, int sc_target, int max_sliced, int32_t
         int best = -1;
         for (int l = 0; l < net.n_labels; ++l) {
             if (removed[l] || is_open[l] || total[l] == 0) continue;
-            if (best < 0 || n_top[l] > n_top[best] || (n_top[l] == n_top[best] && gain[l] > gain[best])) best = l;
+            // memory-driven (sc_target given): the label in most tensors of the top rank, ties by ops removed;
+            // parallelism-driven (sc_target < 0): the label that removes most ops (least total overhead)
+            const bool better = best < 0 || (sc_target >= 0
+                                                 ? (n_top[l] > n_top[best] || (n_top[l] == n_top[best] && gain[l] > gain[best]))
+                                                 : (gain[l] > gain[best] || (gain[l] == gain[best] && n_top[l] > n_top[best])));
+            if (better) best = l;
         }
         if (best < 0 || (tops > 0 && n_top[best] == 0 && gain[best] == 0.0)) break;
         removed[best] = 1;
