@@ -447,7 +447,8 @@ def main():
         peak_gops = dpx.get("viaddmax_s16x2_Gops" if args.value_type == "i16" else "viaddmax_s32_Gops")
         ach = my_gemm_ops / (gemm_ms * 1e-3) * 1e-9 if gemm_ms > 0 else None
         traffic, traffic_note = None, None
-        tp = os.path.join(ROOT, "profiles", "latest_ncu_traffic.json")
+        # the committed ncu --set full capture of THIS workload (cfg2: latest_ncu_traffic.json); none -> null
+        tp = os.path.join(ROOT, "profiles", "latest_ncu_traffic.json" if args.workload == "cfg2" else f"latest_ncu_traffic_{args.workload}.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic = tj.get("dram_bytes_per_launch_mean")

@@ -190,6 +190,18 @@ int tb_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64
 int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n,
                          double* out_values, int32_t* out_status, double* out_max);
 
+/* Streaming hand-off: the host's slicer decides finished vs unfinished per round
+ * (src/slice.jl:79-86) and hands finished branches over while it keeps slicing the rest.  tb_stream_push compiles,
+ * uploads and ENQUEUES the branches and returns while the GPU contracts them; tb_stream_finish waits and returns one
+ * value per pushed branch, in push order (value + r, as tb_contract_networks), and their max.  `capacity` bounds the
+ * total number of branches of the stream.  The context cannot run other contract calls while a stream is open.
+ * tb_stream_finish always closes the stream, also after a failed push. */
+typedef struct tb_stream tb_stream;
+int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream);
+int tb_stream_push(tb_stream* stream, const tb_network* nets, const double* r, int64_t n);
+int tb_stream_finish(tb_stream* stream, double* out_values, int32_t* out_status, int64_t cap, int64_t* out_n,
+                     double* out_max);
+
 /* Index slicing of ONE heavy branch (the 2^k slice assignments of BASELINE.json north_star (4)).
  * The network's own n_fixed must be 0.  Assignment a in [first, first + count) fixes sliced_labels[i] to
  * bit i of a; every assignment is a contraction of the same tree with n_sliced labels removed, all of

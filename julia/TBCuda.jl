@@ -26,7 +26,8 @@ struct TbNetwork
     n_open::Int32; open_labels::Ptr{Int32}
     node_left::Ptr{Int32}; node_right::Ptr{Int32}
     weights::Ptr{Cvoid}; weight_dtype::Int32; value_type::Int32
-    flags::UInt32; reserved::Int32
+    flags::UInt32; n_fixed::Int32
+    fixed_labels::Ptr{Int32}; fixed_values::Ptr{UInt8}   # index slicing (tb_contract_sliced fills these itself)
 end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
@@ -77,7 +78,7 @@ function FlatBranch(branch::SlicedBranch)
     net = TbNetwork(nv(branch.p.g), length(ixs), pointer(leaf_off), pointer(leaf_labels), length(open),
                     isempty(open) ? C_NULL : pointer(open), isempty(left) ? C_NULL : pointer(left),
                     isempty(right) ? C_NULL : pointer(right), unit ? C_NULL : Ptr{Cvoid}(pointer(wv)),
-                    unit ? Int32(0) : weight_code(eltype(wv)), Int32(0), UInt32(0), Int32(0))
+                    unit ? Int32(0) : weight_code(eltype(wv)), Int32(0), UInt32(0), Int32(0), C_NULL, C_NULL)
     return FlatBranch(leaf_off, leaf_labels, left, right, open, wv, net)
 end
 
@@ -86,7 +87,7 @@ function contract_slices_cuda(branches::Vector{SlicedBranch}, element_type::Type
     n = length(branches)
     flats = Vector{Union{FlatBranch, Nothing}}(undef, n)
     nets = Vector{TbNetwork}(undef, n)
-    empty_net = TbNetwork(0, 0, C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0, 0, 0, 0)
+    empty_net = TbNetwork(0, 0, C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0, 0, 0, 0, C_NULL, C_NULL)
     for (i, b) in enumerate(branches)
         if nv(b.p.g) == 0 || isnothing(b.code)
             flats[i] = nothing; nets[i] = empty_net
@@ -105,6 +106,30 @@ function contract_slices_cuda(branches::Vector{SlicedBranch}, element_type::Type
     # same arithmetic as src/dynamic_ob.jl:39-44: empty graph => element_type(r), else t + element_type(r)
     return element_type[(nv(b.p.g) == 0 || isnothing(b.code)) ? element_type(b.r) : element_type(vals[i]) + element_type(b.r)
                         for (i, b) in enumerate(branches)]
+end
+
+"""
+One heavy branch as 2^k index slices (tb_suggest_slices + tb_contract_sliced): the same value as solve_slice, from
+2^k independent contractions of the same tree.  `range` = the assignments this process contracts (a multi-GPU job
+gives every rank a disjoint range and combines the maxima with one all-reduce(max)).
+"""
+function solve_slice_index_sliced(branch::SlicedBranch, element_type::Type, k::Integer; range = nothing)
+    flat = FlatBranch(branch)
+    labels = Vector{Int32}(undef, k); sc = Ref{Float64}(0); tc = Ref{Float64}(0)
+    GC.@preserve flat begin
+        nk = ccall((:tb_suggest_slices, LIB), Cint,
+                   (Ptr{Cvoid}, Ref{TbNetwork}, Int32, Int32, Ptr{Int32}, Ref{Float64}, Ref{Float64}),
+                   C_NULL, Ref(flat.net), -1, k, labels, sc, tc)
+        nk >= 0 || error("tb_suggest_slices failed ($nk)")
+        first, count = isnothing(range) ? (0, 1 << nk) : (first(range), length(range))
+        mx = Ref{Float64}(0)
+        rc = ccall((:tb_contract_sliced, LIB), Cint,
+                   (Ptr{Cvoid}, Ref{TbNetwork}, Ptr{Int32}, Int32, Int64, Int64, Float64, Ptr{Float64}, Ptr{Int32}, Ref{Float64}),
+                   ctx(), Ref(flat.net), labels, nk, first, count, 0.0, C_NULL, C_NULL, mx)
+        rc == 0 || error("tb_contract_sliced failed ($rc): " *
+                         unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
+    end
+    return element_type(mx[])
 end
 
 # method overrides: the usecuda=true switch position

@@ -284,6 +284,69 @@ class Engine:
         return out
 
 
+class BranchStream:
+    """Streaming hand-off (tb_stream_*): push branches as the slicer finishes them
+    (src/slice.jl:79-86), the GPU contracts them while the host keeps slicing; finish() returns what
+    contract_slices would have returned for the concatenation of everything pushed.
+
+        with tbcuda.BranchStream(engine, capacity=100000) as st:
+            for finished in slicer_rounds():
+                st.push(finished)
+        values = st.values            # element_type vector, push order
+    """
+
+    def __init__(self, engine: "Engine" = None, capacity: int = 1 << 20, element_type=np.float32, flags=0):
+        self._eng = engine or default_engine()
+        self._lib = self._eng._lib
+        self._et = element_type
+        self._flags = flags
+        self._branches: List[SlicedBranch] = []
+        self.handle = C.c_void_p()
+        self.values = None
+        L.check(self._lib.tb_stream_begin(self._eng.handle, capacity, C.byref(self.handle)), self._eng.handle)
+
+    def push(self, branches: Sequence[SlicedBranch]):
+        n = len(branches)
+        if n == 0:
+            return
+        parts = [_EMPTY_NET_BYTES if (br.p.nv == 0 or br.code is None) else _network_bytes(br, self._et, self._flags)
+                 for br in branches]
+        nets = (L.tb_network * n).from_buffer_copy(b"".join(parts))
+        self._branches.extend(branches)  # keeps the arrays the records point into alive until finish()
+        L.check(self._lib.tb_stream_push(self.handle, nets, None, n), self._eng.handle)
+
+    def finish(self) -> np.ndarray:
+        if not self.handle:
+            return self.values
+        n = len(self._branches)
+        out = np.empty(max(n, 1), dtype=np.float64)
+        status = np.zeros(max(n, 1), dtype=np.int32)
+        got = C.c_int64()
+        mx = C.c_double()
+        h, self.handle = self.handle, C.c_void_p()
+        L.check(self._lib.tb_stream_finish(h, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                           status.ctypes.data_as(C.POINTER(C.c_int32)), max(n, 1), C.byref(got),
+                                           C.byref(mx)), self._eng.handle)
+        et = self._et
+        r = np.array([br.r for br in self._branches], dtype=np.float64).astype(et)
+        empty = np.array([br.code is None or br.p.nv == 0 for br in self._branches], dtype=bool)
+        res = out[:n].astype(et) + r  # same arithmetic as contract_slices (src/dynamic_ob.jl:39-44)
+        res[empty] = r[empty]
+        self.values = res
+        return res
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.finish()
+        elif self.handle:  # close the stream without masking the original exception
+            h, self.handle = self.handle, C.c_void_p()
+            self._lib.tb_stream_finish(h, None, None, 0, None, None)
+        return False
+
+
 _default_engine: Optional[Engine] = None
 
 

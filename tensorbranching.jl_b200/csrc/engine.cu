@@ -43,6 +43,7 @@ struct BlobChunk {
 }  // namespace
 
 struct tb_ctx {
+    bool stream_open = false;  // a tb_stream owns the context between tb_stream_begin and tb_stream_finish
     int call_wave = 0;  // wave size of the current call (a small call is cut into more, smaller waves: all lanes busy)
     std::thread reaper;  // frees the host side of the previous tb_contract_networks call's temporary plans
     tb_options opts{};
@@ -653,6 +654,7 @@ int enqueue_batch(tb_ctx* ctx, tb_plan* const* plans, int64_t lo, int64_t hi, st
 }
 
 int begin_call(tb_ctx* ctx, int64_t n) {
+    if (ctx->stream_open) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "a tb_stream is open on this context: finish it first");
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
 #ifdef TB_KPROF
     {  // timeline of the most recent call only
@@ -764,7 +766,38 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
     return finish_call(ctx, plans, r, n, status, out_values, out_status, out_max, any);
 }
 
+// the temporary plans of a *_networks / stream call all live in chunks of that call: release the device side once,
+// free the host side off the caller's critical path (joined by the next call / tb_shutdown)
+void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans) {
+    for (tb_plan* p : plans)
+        if (p && p->p.d_blob) {
+            for (auto& c : ctx->chunks)
+                if ((uint8_t*)p->p.d_blob >= (uint8_t*)c.d && (uint8_t*)p->p.d_blob < (uint8_t*)c.d + c.cap) {
+                    if (--c.live == 0) c.used = 0;
+                    break;
+                }
+            p->p.d_blob = nullptr;
+            p->p.owner = nullptr;
+        }
+    if (ctx->reaper.joinable()) ctx->reaper.join();
+    ctx->reaper = std::thread([dead = std::move(plans)]() {
+        for (tb_plan* p : dead) delete p;
+    });
+}
+
 }  // namespace
+
+// streaming hand-off: branches are pushed as the host's slicer finishes them
+struct tb_stream {
+    tb_ctx* ctx = nullptr;
+    int64_t capacity = 0;
+    std::vector<tb_plan*> plans;
+    std::vector<double> r;
+    std::vector<int32_t> status;
+    bool any = false;
+    bool failed = false;
+    double t0 = 0;
+};
 
 // ================================================================================================
 // C ABI
@@ -1063,24 +1096,94 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     if (rc == TB_OK) rc = finish_call(ctx, plans.data(), r, n, status, out_values, out_status, out_max, any);
     else sync_all_lanes(ctx);
     const double t_d0 = now_ms();
-    // the temporary plans all live in chunks of this call: release the device side once, free hosts in parallel
-    for (tb_plan* p : plans)
-        if (p && p->p.d_blob) {
-            for (auto& c : ctx->chunks)
-                if ((uint8_t*)p->p.d_blob >= (uint8_t*)c.d && (uint8_t*)p->p.d_blob < (uint8_t*)c.d + c.cap) {
-                    if (--c.live == 0) c.used = 0;
-                    break;
-                }
-            p->p.d_blob = nullptr;
-            p->p.owner = nullptr;
-        }
-    // host side: off the caller's critical path (joined by the next call / tb_shutdown)
-    if (ctx->reaper.joinable()) ctx->reaper.join();
-    ctx->reaper = std::thread([dead = std::move(plans)]() {
-        for (tb_plan* p : dead) delete p;
-    });
+    release_temporary_plans(ctx, std::move(plans));
     ctx->host_ms[4] = now_ms() - t_d0;
     ctx->host_ms[5] = now_ms() - t_c0;
+    return rc;
+}
+
+int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream) {
+    if (!ctx || !out_stream) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / out_stream is NULL");
+    *out_stream = nullptr;
+    if (capacity < 1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "capacity must be >= 1");
+    int rc = begin_call(ctx, capacity);
+    if (rc) return rc;
+    std::unique_ptr<tb_stream> s(new tb_stream());
+    s->ctx = ctx;
+    s->capacity = capacity;
+    s->t0 = now_ms();
+    ctx->call_wave = wave_for_call(ctx, std::max<int64_t>(capacity, 1024));
+    ctx->stream_open = true;
+    *out_stream = s.release();
+    return TB_OK;
+}
+
+int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_t n) {
+    if (!s) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "stream is NULL");
+    tb_ctx* ctx = s->ctx;
+    if (s->failed) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "the stream already failed: call tb_stream_finish");
+    if (n < 0 || (n > 0 && !nets)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    const int64_t lo = (int64_t)s->plans.size(), hi = lo + n;
+    if (hi > s->capacity) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "more branches pushed than the capacity given to tb_stream_begin");
+    if (n == 0) return TB_OK;
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double t_c0 = now_ms();
+    s->plans.resize((size_t)hi, nullptr);
+    s->status.resize((size_t)hi, TB_OK);
+    for (int64_t i = 0; i < n; ++i) s->r.push_back(r ? r[i] : 0.0);
+    std::vector<int> codes((size_t)n, TB_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::atomic<int64_t> next{0};
+    const uint32_t flags = ctx->opts.plan_flags;
+    auto worker = [&]() {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            if (nets[i].n_leaves == 0) continue;
+            tb_plan* p = new tb_plan();
+            codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
+            if (codes[i]) delete p;
+            else s->plans[(size_t)(lo + i)] = p;
+        }
+    };
+    int nthreads = ctx->opts.host_threads > 0 ? ctx->opts.host_threads : (int)std::thread::hardware_concurrency();
+    nthreads = std::max(1, std::min<int>(nthreads, (int)std::max<int64_t>(1, n / 8)));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    ctx->host_ms[0] += now_ms() - t_c0;
+    int rc = TB_OK;
+    for (int64_t i = 0; i < n && rc == TB_OK; ++i)
+        if (codes[i]) rc = set_err(ctx, codes[i], "branch " + std::to_string(lo + i) + ": " + errs[i]);
+    for (int64_t i = lo; i < hi; ++i) s->any = s->any || s->plans[(size_t)i];
+    // the launches are asynchronous: the call returns while the GPU contracts, the host goes back to slicing
+    if (rc == TB_OK) rc = enqueue_batch(ctx, s->plans.data(), lo, hi, s->status, false);
+    if (rc) s->failed = true;
+    return rc;
+}
+
+int tb_stream_finish(tb_stream* s, double* out_values, int32_t* out_status, int64_t cap, int64_t* out_n, double* out_max) {
+    if (!s) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "stream is NULL");
+    tb_ctx* ctx = s->ctx;
+    const int64_t n = (int64_t)s->plans.size();
+    int rc = TB_OK;
+    if (out_n) *out_n = n;
+    if (s->failed) {
+        sync_all_lanes(ctx);
+        rc = set_err(ctx, TB_ERR_BAD_ARGUMENT, "the stream failed in tb_stream_push: " + ctx->last_error);
+    } else if (n > 0 && (!out_values || cap < n)) {
+        sync_all_lanes(ctx);
+        rc = set_err(ctx, TB_ERR_BAD_ARGUMENT, "output buffer smaller than the number of pushed branches");
+    } else {
+        std::vector<double> vals((size_t)std::max<int64_t>(n, 1));
+        rc = finish_call(ctx, s->plans.data(), s->r.data(), n, s->status, vals.data(), out_status, out_max, s->any);
+        if (n > 0) std::memcpy(out_values, vals.data(), (size_t)n * sizeof(double));
+    }
+    release_temporary_plans(ctx, std::move(s->plans));
+    ctx->host_ms[5] = now_ms() - s->t0;
+    ctx->stream_open = false;
+    delete s;
     return rc;
 }
 
