@@ -222,6 +222,15 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
 int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int32_t max_sliced,
                       int32_t* out_labels, double* out_sc, double* out_tc);
 
+/* Open-boundary contraction (first half): a network created with open_labels (iy non-empty) keeps
+ * those labels at the root -- for a region of the graph with its boundary vertices open this root is the tensor of
+ * best sizes per boundary configuration that the branching tables of TensorNetworkSolver are read from
+ * (src/branch.jl:79, src/types.jl:46; the configuration-enumerating element types of the table itself are NOT
+ * implemented).  Contracts the plan and returns the whole root tensor: 2^rank doubles (-inf = tropical zero),
+ * layout in out_labels, bit 0 first.  out_data == NULL only queries rank / labels. */
+int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels,
+                       int32_t* out_rank);
+
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap,

@@ -185,6 +185,16 @@ class Engine:
                                               labels, C.byref(rank)), self.handle)
         return list(labels[:rank.value]), data
 
+    def contract_tensor(self, plan: Plan):
+        """tb_contract_tensor: the root tensor of a plan with open labels -> (labels bit-0-first, 2^rank float64)."""
+        labels = (C.c_int32 * 32)()
+        rank = C.c_int32()
+        L.check(self._lib.tb_contract_tensor(self.handle, plan.handle, None, 0, labels, C.byref(rank)), self.handle)
+        data = np.empty(1 << rank.value, dtype=np.float64)
+        L.check(self._lib.tb_contract_tensor(self.handle, plan.handle, data.ctypes.data_as(C.POINTER(C.c_double)),
+                                             data.size, labels, C.byref(rank)), self.handle)
+        return list(labels[:rank.value]), data
+
     # -- batches -----------------------------------------------------------------------------
     def contract_plans(self, plans: Sequence[Optional[Plan]], r: Optional[np.ndarray] = None):
         n = len(plans)

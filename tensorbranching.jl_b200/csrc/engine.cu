@@ -785,6 +785,23 @@ void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans) {
     });
 }
 
+// 2^rank elements of the last single-plan contraction (tb_contract) at arena element offset `off` -> host doubles
+int copy_tensor_to_host(tb_ctx* ctx, const Plan& P, int64_t off, int64_t n, double* out_data) {
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d_tmp = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&d_tmp, (size_t)n * sizeof(double)));
+    const uint8_t* src = (const uint8_t*)ctx->arena + (size_t)(ctx->last_plan_arena_base_elems + off) * (size_t)P.elem_size();
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    if (P.value_type == TB_VALUE_I32) k_to_double<int32_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t*)src, d_tmp, n);
+    else if (P.value_type == TB_VALUE_I16X2) k_to_double<int16_t><<<blocks, 256, 0, ctx->stream>>>((const int16_t*)src, d_tmp, n);
+    else k_to_double<float><<<blocks, 256, 0, ctx->stream>>>((const float*)src, d_tmp, n);
+    cudaError_t e = cudaMemcpyAsync(out_data, d_tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_tmp);
+    if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
+    return TB_OK;
+}
+
 }  // namespace
 
 // streaming hand-off: branches are pushed as the host's slicer finishes them
@@ -1277,19 +1294,24 @@ int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_da
     int64_t n = (int64_t)1 << rank;
     if (!out_data) return TB_OK;
     if (cap < n) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "output buffer too small");
-    TB_CUDA(ctx, cudaSetDevice(ctx->device));
-    double* d_tmp = nullptr;
-    TB_CUDA(ctx, cudaMalloc(&d_tmp, (size_t)n * sizeof(double)));
-    const uint8_t* src = (const uint8_t*)ctx->arena + (size_t)(ctx->last_plan_arena_base_elems + P.off[node]) * (size_t)P.elem_size();
-    unsigned blocks = (unsigned)((n + 255) / 256);
-    if (P.value_type == TB_VALUE_I32) k_to_double<int32_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t*)src, d_tmp, n);
-    else if (P.value_type == TB_VALUE_I16X2) k_to_double<int16_t><<<blocks, 256, 0, ctx->stream>>>((const int16_t*)src, d_tmp, n);
-    else k_to_double<float><<<blocks, 256, 0, ctx->stream>>>((const float*)src, d_tmp, n);
-    cudaError_t e = cudaMemcpyAsync(out_data, d_tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_tmp);
-    if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
-    return TB_OK;
+    return copy_tensor_to_host(ctx, P, P.off[node], n, out_data);
+}
+
+int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels, int32_t* out_rank) {
+    if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
+    const Plan& P = plan->p;
+    const int rank = P.rank(P.root_id);
+    if (out_rank) *out_rank = rank;
+    if (out_labels)
+        for (int i = 0; i < rank; ++i) out_labels[i] = P.layout(P.root_id)[i];
+    const int64_t n = (int64_t)1 << rank;
+    if (!out_data) return TB_OK;  // size query
+    if (cap < n) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "output buffer too small");
+    double first = 0;
+    tb_plan* arr[1] = {plan};
+    int rc = contract_impl(ctx, arr, nullptr, 1, &first, nullptr, nullptr, true);
+    if (rc) return rc;
+    return copy_tensor_to_host(ctx, P, P.root_off, n, out_data);
 }
 
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {
