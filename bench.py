@@ -4,8 +4,11 @@
     python bench.py --gpus 1 --steps K --warmup W            this engine (libtbcuda.so)
     python bench.py --impl reference ...                     CPU arm: the oracle's C/OpenMP port of the
                                                              reference's algorithm on the host cores
-    torchrun ... bench.py --gpus N ...                       one rank per GPU, branches sharded (LPT),
-                                                             one all-reduce(max) over the result vector
+    torchrun ... bench.py --gpus N ...                       one rank per GPU, one all-reduce(max) over the result vector;
+                                                             --scaling weak (default): every rank contracts its own copy of
+                                                             the unit list (per-GPU work fixed, value = N x ops / time);
+                                                             --scaling strong: ONE unit list sharded longest-first (LPT)
+    --workload cfg1|cfg2|cfg3|cfg4|cfg5                      BASELINE.json configs[0..4]; cfg3 is index-sliced (--slice-k)
 
 A "step" = one pass of contract_slices over the whole branch list of the workload:
     cfg2 (default) = BASELINE.json configs[1]: random 3-regular n=200 (seed 2), sc_target=20,
@@ -231,6 +234,9 @@ def main():
     ap.add_argument("--impl", default="tbcuda", choices=["tbcuda", "reference"])
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--max-branches", type=int, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every rank contracts its own copy of the workload's unit list (per-GPU work fixed, "
+                         "N x units in the job); strong: ONE unit list sharded over the ranks by cost")
     ap.add_argument("--slice-k", type=int, default=None,
                     help="index-slice every branch into 2^k units (default: per workload, 0 except cfg3)")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
@@ -269,7 +275,7 @@ def main():
         ms = float(np.mean([d for _, d in gops])) * 1e3
         line = {"impl": "reference", "metric": "tropical contraction throughput", "value": value, "unit": "Gop/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": value, "unit": "Gop/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "Gop/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -330,19 +336,25 @@ def main():
     stats = [p.info() if p is not None else None for p in all_plans]
     ops = np.array([s.ops if s else 0.0 for s in stats])
     abytes = np.array([s.algo_bytes if s else 0.0 for s in stats])
-    owner = lpt_shards(ops, world)
+    weak = args.scaling == "weak"
+    copies = world if weak else 1  # weak: the job holds one copy of the unit list per rank
+    owner = np.full(n_units, rank, dtype=np.int64) if weak else lpt_shards(ops, world)
     mine = np.nonzero(owner == rank)[0]
+    config["sharding"] = (f"weak scaling: every rank contracts its own copy of the unit list ({copies} x {n_units} units), "
+                          "no data-path collective, one all-reduce(max) over the result vector" if weak else
+                          f"strong scaling: {n_units} units dealt to {world} rank(s) longest-first by tb_plan_info.ops, "
+                          "no data-path collective, one all-reduce(max) over the result vector")
     my_plans = [all_plans[i] for i in mine]
     my_sliced = [sliced[ub[i]] for i in mine]
     for i in np.nonzero(owner != rank)[0]:
         if all_plans[i] is not None:
             all_plans[i].close()
-    total_ops = float(ops.sum())
+    total_ops = float(ops.sum()) * copies
     r_vec = np.array([b.r for b in branches], dtype=np.float64)
     r_units = r_vec[ub]
 
-    res_dev = torch.full((n_units,), -float("inf"), dtype=torch.float64, device="cuda")
-    mine_dev = torch.from_numpy(mine).cuda()
+    res_dev = torch.full((copies * n_units,), -float("inf"), dtype=torch.float64, device="cuda")
+    mine_dev = torch.from_numpy(mine + (rank * n_units if weak else 0)).cuda()
 
     def per_branch(unit_vals, idx):
         out = np.full(n_br, -np.inf)
@@ -355,7 +367,10 @@ def main():
             res_dev.fill_(-float("inf"))
             res_dev[mine_dev] = torch.from_numpy(np.ascontiguousarray(vals)).cuda()
             dist.all_reduce(res_dev, op=dist.ReduceOp.MAX)
-            return per_branch(res_dev.cpu().numpy(), np.arange(n_units))
+            full = res_dev.cpu().numpy().reshape(copies, n_units)
+            # weak: the copies are the same instance, so every GPU must have produced the same values (bit-exact)
+            assert (full == full[0]).all(), "ranks disagree on the value of a unit"
+            return per_branch(full[0], np.arange(n_units))
         return per_branch(vals, mine)
 
     def step_resident():
@@ -371,7 +386,7 @@ def main():
         # index slicing through the public call: every rank contracts its contiguous range of each branch's 2^k
         # assignments (tb_contract_sliced), then one all-reduce(max) over the per-branch vector
         out = np.full(n_br, -np.inf)
-        first, count = slice_range(1 << slice_k, world, rank)
+        first, count = (0, 1 << slice_k) if weak else slice_range(1 << slice_k, world, rank)
         for i, s in enumerate(sliced):
             if s.code is None:
                 out[i] = r_vec[i]
@@ -436,7 +451,7 @@ def main():
         e2e = {"value": total_ops / (ms_e2e * 1e-3) * 1e-9, "unit": "Gop/s", "h2d_bytes_per_step": int(hb[0].item()),
                "host_breakdown_rank0": eng.last_host_breakdown(),
                "d2h_bytes_per_step": int(hb[1].item()), "ms_per_step": ms_e2e,
-               "slices_per_s": n_units / (ms_e2e * 1e-3)}
+               "slices_per_s": copies * n_units / (ms_e2e * 1e-3)}
         assert np.array_equal(result_e2e, result)
 
     if rank == 0:
@@ -466,9 +481,10 @@ def main():
         line = {"metric": "tropical contraction throughput", "value": total_ops / (ms_step * 1e-3) * 1e-9, "unit": "Gop/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
                 "ms_per_step_median_rank0": per_step_ms[len(per_step_ms) // 2], "ms_per_step_max_rank0": per_step_ms[-1],
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "int16x2" if args.value_type == "i16" else "int32", "data": "synthetic", "config": config, "slices_per_s": n_units / (ms_step * 1e-3), "branches": n_br, "units": n_units,
-                "total_ops": total_ops, "mis": float(np.max(result)), "gpu_launches": int(launches_step * args.steps),
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": "int16x2" if args.value_type == "i16" else "int32", "data": "synthetic", "config": config,
+                "slices_per_s": copies * n_units / (ms_step * 1e-3), "branches": copies * n_br, "units": copies * n_units,
+                "total_ops": total_ops, "mis": float(np.max(result)), "gpu_launches": int(launches_step * args.steps * copies),
                 "launches_per_step": int(launches_step), "device_ms_last_step": dev_ms_last,
                 "plan_compile_s_all_branches": plan_s, "clocks": clocks, "roofline": roofline, "dpx_peak": dpx}
         if e2e:
