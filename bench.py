@@ -506,6 +506,9 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    for p in my_plans:
+        if p is not None:
+            p.close()
     eng.close()
 
 

@@ -322,8 +322,8 @@ class BranchStream:
         parts = [_EMPTY_NET_BYTES if (br.p.nv == 0 or br.code is None) else _network_bytes(br, self._et, self._flags)
                  for br in branches]
         nets = (L.tb_network * n).from_buffer_copy(b"".join(parts))
-        self._branches.extend(branches)  # keeps the arrays the records point into alive until finish()
-        L.check(self._lib.tb_stream_push(self.handle, nets, None, n), self._eng.handle)
+        L.check(self._lib.tb_stream_push(self.handle, nets, None, n), self._eng.handle)  # inputs are copied by the compiler
+        self._branches.extend(branches)
 
     def finish(self) -> np.ndarray:
         if not self.handle:

@@ -43,6 +43,7 @@ struct BlobChunk {
 }  // namespace
 
 struct tb_ctx {
+    Plan* resident = nullptr;  // head of the intrusive list of plans whose descriptors live on this context
     bool stream_open = false;  // a tb_stream owns the context between tb_stream_begin and tb_stream_finish
     int call_wave = 0;  // wave size of the current call (a small call is cut into more, smaller waves: all lanes busy)
     std::thread reaper;  // frees the host side of the previous tb_contract_networks call's temporary plans
@@ -110,6 +111,19 @@ int set_err(tb_ctx* ctx, int code, const std::string& msg) {
     } while (0)
 
 int sync_all_lanes(tb_ctx* ctx);
+
+void link_resident(tb_ctx* ctx, Plan& P) {
+    P.res_prev = nullptr;
+    P.res_next = ctx->resident;
+    if (ctx->resident) ctx->resident->res_prev = &P;
+    ctx->resident = &P;
+}
+void unlink_resident(tb_ctx* ctx, Plan& P) {
+    if (P.res_prev) P.res_prev->res_next = P.res_next;
+    else if (ctx->resident == &P) ctx->resident = P.res_next;
+    if (P.res_next) P.res_next->res_prev = P.res_prev;
+    P.res_prev = P.res_next = nullptr;
+}
 
 int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
     if (ctx->arena && ctx->arena_bytes >= need_bytes) return TB_OK;
@@ -262,6 +276,7 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
             write_blob(todo[j]->p, (uint8_t*)sl->h + o);
             todo[j]->p.d_blob = (uint8_t*)ck->d + ck->used + o;
             todo[j]->p.owner = ctx;
+            link_resident(ctx, todo[j]->p);
             ck->live++;
             o += bsz[j];
         }
@@ -776,6 +791,7 @@ void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans) {
                     if (--c.live == 0) c.used = 0;
                     break;
                 }
+            unlink_resident(ctx, p->p);
             p->p.d_blob = nullptr;
             p->p.owner = nullptr;
         }
@@ -916,6 +932,15 @@ int tb_shutdown(tb_ctx* ctx) {
 #endif
     cudaSetDevice(ctx->device);
     sync_all_lanes(ctx);
+    // plans may outlive the context (a host language's GC decides when they are destroyed): detach them
+    for (Plan* P = ctx->resident; P;) {
+        Plan* nx = P->res_next;
+        P->owner = nullptr;
+        P->d_blob = nullptr;
+        P->res_prev = P->res_next = nullptr;
+        P = nx;
+    }
+    ctx->resident = nullptr;
     if (ctx->arena) cudaFree(ctx->arena);
     for (auto& c : ctx->chunks)
         if (c.d) cudaFree(c.d);
@@ -956,6 +981,7 @@ int tb_plan_destroy(tb_plan* plan) {
     if (!plan) return TB_OK;
     if (plan->p.owner && plan->p.d_blob) {
         tb_ctx* ctx = plan->p.owner;
+        unlink_resident(ctx, plan->p);
         for (auto& c : ctx->chunks) {
             if ((uint8_t*)plan->p.d_blob >= (uint8_t*)c.d && (uint8_t*)plan->p.d_blob < (uint8_t*)c.d + c.cap) {
                 if (--c.live == 0 && &c != &ctx->chunks.back()) {

@@ -57,6 +57,8 @@ struct Plan {
 
     // device residency (managed by the engine)
     tb_ctx* owner = nullptr;
+    Plan* res_prev = nullptr;  // intrusive list of the plans resident on `owner` (tb_shutdown detaches them, so a plan
+    Plan* res_next = nullptr;  // may safely outlive its context)
     void* d_blob = nullptr;
     size_t blob_bytes = 0;
     size_t sub_blob_off = 0, big_blob_off = 0;

@@ -48,3 +48,23 @@ def test_stream_blocks_other_calls_and_capacity(tb, engine):
     assert np.array_equal(vals.astype(np.float64), np.asarray(rec["values"][:2]))
     assert np.array_equal(tb.contract_slices(brs[:3], np.float32, True, engine=engine).astype(np.float64),
                           np.asarray(rec["values"][:3]))
+
+
+@pytest.mark.gpu
+def test_plans_may_outlive_their_context(tb):
+    """tb_shutdown detaches resident plans: destroying them afterwards (a GC's order) is safe, and a detached plan
+    can be contracted again on another context."""
+    rec = load_golden("rr100_sc10_unit.json")
+    brs = [to_sliced(b) for b in golden_branches(rec) if b.nv > 0][:40]
+    eng = tb.Engine(0)
+    plans = [tb.Plan(b, engine=eng) for b in brs]
+    want, _, _ = eng.contract_plans(plans)
+    eng.close()                       # plans still hold device-side descriptors of the dead context
+    for p in plans[:20]:
+        p.close()
+    eng2 = tb.Engine(0)
+    got, _, _ = eng2.contract_plans(plans[20:])
+    assert np.array_equal(got, want[20:])
+    eng2.close()
+    for p in plans[20:]:
+        p.close()
