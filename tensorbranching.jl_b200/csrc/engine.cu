@@ -832,6 +832,21 @@ struct tb_stream {
     double t0 = 0;
 };
 
+// no C++ exception crosses the ABI: every entry point that allocates is a function-try-block ending in TB_CATCH
+int exception_to_status(tb_ctx* ctx) {
+    try {
+        throw;
+    } catch (const std::bad_alloc&) {
+        return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "host memory allocation failed");
+    } catch (const std::exception& e) {
+        return set_err(ctx, TB_ERR_INTERNAL, std::string("C++ exception: ") + e.what());
+    } catch (...) {
+        return set_err(ctx, TB_ERR_INTERNAL, "unknown C++ exception");
+    }
+}
+#define TB_CATCH(ctx_expr) \
+    catch (...) { return exception_to_status(ctx_expr); }
+
 // ================================================================================================
 // C ABI
 // ================================================================================================
@@ -841,7 +856,7 @@ const char* tb_version(void) { return "tbcuda 0.1.0 (sm_100a)"; }
 
 const char* tb_last_error(const tb_ctx* ctx) { return ctx ? ctx->last_error.c_str() : g_tls_error.c_str(); }
 
-int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
+int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
     if (!out_ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "out_ctx is NULL");
     *out_ctx = nullptr;
     int ndev = 0;
@@ -900,7 +915,7 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) {
     }
     *out_ctx = ctx.release();
     return TB_OK;
-}
+} TB_CATCH(nullptr)
 
 int tb_shutdown(tb_ctx* ctx) {
     if (!ctx) return TB_OK;
@@ -966,7 +981,7 @@ int tb_shutdown(tb_ctx* ctx) {
     return TB_OK;
 }
 
-int tb_plan_create(tb_ctx* ctx, const tb_network* net, tb_plan** out_plan) {
+int tb_plan_create(tb_ctx* ctx, const tb_network* net, tb_plan** out_plan) try {
     if (!net || !out_plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net / out_plan is NULL");
     *out_plan = nullptr;
     std::unique_ptr<tb_plan> p(new tb_plan());
@@ -975,7 +990,7 @@ int tb_plan_create(tb_ctx* ctx, const tb_network* net, tb_plan** out_plan) {
     if (rc) return set_err(ctx, rc, err);
     *out_plan = p.release();
     return TB_OK;
-}
+} TB_CATCH(ctx)
 
 int tb_plan_destroy(tb_plan* plan) {
     if (!plan) return TB_OK;
@@ -1007,15 +1022,15 @@ int tb_plan_info(const tb_plan* plan, tb_plan_stats* out) {
     return TB_OK;
 }
 
-int tb_plan_export(const tb_plan* plan, tb_step_info* out, int32_t cap) {
+int tb_plan_export(const tb_plan* plan, tb_step_info* out, int32_t cap) try {
     if (!plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "plan is NULL");
     int n = (int)plan->p.recs.size();
     if (out)
         for (int i = 0; i < n && i < cap; ++i) out[i] = plan->p.step_info((size_t)i);
     return n;
-}
+} TB_CATCH(nullptr)
 
-int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_t cap) {
+int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_t cap) try {
     if (!plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "plan is NULL");
     const Plan& P = plan->p;
     const void* src = nullptr;
@@ -1033,21 +1048,21 @@ int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_
     }
     if (out && cap > 0 && bytes > 0) std::memcpy(out, src, (size_t)std::min(cap, bytes));
     return bytes;
-}
+} TB_CATCH(nullptr)
 
-int tb_contract(tb_ctx* ctx, tb_plan* plan, double* out_value) {
+int tb_contract(tb_ctx* ctx, tb_plan* plan, double* out_value) try {
     if (!plan || !out_value) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan / out_value is NULL");
     tb_plan* arr[1] = {plan};
     return contract_impl(ctx, arr, nullptr, 1, out_value, nullptr, nullptr, true);
-}
+} TB_CATCH(ctx)
 
 int tb_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
-                      double* out_max) {
+                      double* out_max) try {
     return contract_impl(ctx, plans, r, n, out_values, out_status, out_max, false);
-}
+} TB_CATCH(ctx)
 
 int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n, double* out_values,
-                         int32_t* out_status, double* out_max) {
+                         int32_t* out_status, double* out_max) try {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
     if (n < 0 || (n > 0 && (!nets || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
     const double t_c0 = now_ms();
@@ -1143,9 +1158,9 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     ctx->host_ms[4] = now_ms() - t_d0;
     ctx->host_ms[5] = now_ms() - t_c0;
     return rc;
-}
+} TB_CATCH(ctx)
 
-int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream) {
+int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream) try {
     if (!ctx || !out_stream) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / out_stream is NULL");
     *out_stream = nullptr;
     if (capacity < 1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "capacity must be >= 1");
@@ -1159,9 +1174,9 @@ int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream) {
     ctx->stream_open = true;
     *out_stream = s.release();
     return TB_OK;
-}
+} TB_CATCH(ctx)
 
-int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_t n) {
+int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_t n) try {
     if (!s) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "stream is NULL");
     tb_ctx* ctx = s->ctx;
     if (s->failed) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "the stream already failed: call tb_stream_finish");
@@ -1204,9 +1219,9 @@ int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_
     if (rc == TB_OK) rc = enqueue_batch(ctx, s->plans.data(), lo, hi, s->status, false);
     if (rc) s->failed = true;
     return rc;
-}
+} TB_CATCH((s ? s->ctx : nullptr))
 
-int tb_stream_finish(tb_stream* s, double* out_values, int32_t* out_status, int64_t cap, int64_t* out_n, double* out_max) {
+int tb_stream_finish(tb_stream* s, double* out_values, int32_t* out_status, int64_t cap, int64_t* out_n, double* out_max) try {
     if (!s) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "stream is NULL");
     tb_ctx* ctx = s->ctx;
     const int64_t n = (int64_t)s->plans.size();
@@ -1228,16 +1243,17 @@ int tb_stream_finish(tb_stream* s, double* out_values, int32_t* out_status, int6
     ctx->stream_open = false;
     delete s;
     return rc;
-}
+} TB_CATCH((s ? s->ctx : nullptr))
 
 int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced, int64_t first,
-                       int64_t count, double r, double* out_values, int32_t* out_status, double* out_max) {
+                       int64_t count, double r, double* out_values, int32_t* out_status, double* out_max) try {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
     if (!net || net->n_leaves < 1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL or empty");
     if (net->n_fixed != 0) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "the network of tb_contract_sliced must not carry fixed labels itself");
     if (n_sliced < 0 || n_sliced > 40 || (n_sliced > 0 && !sliced_labels)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad sliced labels (0 <= n_sliced <= 40)");
     const int64_t n_assign = (int64_t)1 << n_sliced;
     if (first < 0 || count < 0 || first + count > n_assign) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "assignment range outside [0, 2^n_sliced)");
+    if (count > ((int64_t)1 << 24)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "more than 2^24 assignments in one call: split the range");
     // position of every sliced label; pairs of sliced labels joined by an edge leaf make an assignment infeasible
     std::vector<int32_t> pos((size_t)std::max(net->n_labels, 1), -1);
     for (int i = 0; i < n_sliced; ++i) {
@@ -1295,19 +1311,19 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
     if (out_status) std::memcpy(out_status, stat.data(), (size_t)count * sizeof(int32_t));
     if (out_max) *out_max = mx;
     return rc;
-}
+} TB_CATCH(ctx)
 
 int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int32_t max_sliced, int32_t* out_labels,
-                      double* out_sc, double* out_tc) {
+                      double* out_sc, double* out_tc) try {
     if (!net) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL");
     std::string err;
     int rc = suggest_slices(*net, sc_target, max_sliced, out_labels, out_sc, out_tc, err);
     if (rc < 0) return set_err(ctx, rc, err);
     return rc;
-}
+} TB_CATCH(ctx)
 
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap, int32_t* out_labels,
-                        int32_t* out_rank) {
+                        int32_t* out_rank) try {
     if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
     const Plan& P = plan->p;
     if (!(P.flags & TB_PLAN_KEEP_INTERMEDIATES)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan was not created with TB_PLAN_KEEP_INTERMEDIATES");
@@ -1321,9 +1337,9 @@ int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_da
     if (!out_data) return TB_OK;
     if (cap < n) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "output buffer too small");
     return copy_tensor_to_host(ctx, P, P.off[node], n, out_data);
-}
+} TB_CATCH(ctx)
 
-int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels, int32_t* out_rank) {
+int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels, int32_t* out_rank) try {
     if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
     const Plan& P = plan->p;
     const int rank = P.rank(P.root_id);
@@ -1338,7 +1354,7 @@ int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap
     int rc = contract_impl(ctx, arr, nullptr, 1, &first, nullptr, nullptr, true);
     if (rc) return rc;
     return copy_tensor_to_host(ctx, P, P.root_off, n, out_data);
-}
+} TB_CATCH(ctx)
 
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
@@ -1385,7 +1401,7 @@ int tb_last_transfers(const tb_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes)
     return TB_OK;
 }
 
-int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const int32_t* perm) {
+int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const int32_t* perm) try {
     if (!ctx || !in || !out || !perm) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "NULL argument");
     if (rank < 0 || rank > 31) return set_err(ctx, TB_ERR_UNSUPPORTED, "rank must be in [0, 31]");
     std::vector<int> dst_of_src(rank, -1);
@@ -1446,6 +1462,6 @@ int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const 
     cudaFree(dout);
     if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
     return TB_OK;
-}
+} TB_CATCH(ctx)
 
 }  // extern "C"
