@@ -136,6 +136,8 @@ typedef struct tb_plan_stats {
     double fused_ops;
     double generic_ops;
     double gemm_bytes;       /* algorithmic bytes (operands read once + result written once) of the GEMM steps */
+    double peak_memory_log2; /* contraction_peak_memory(code, size 2) of the reference (src/utils.jl:197-219), in elements */
+    double all_memory_log2;  /* contraction_all_memory (src/utils.jl:222-229): log2 of the sum of all intermediates */
 } tb_plan_stats;
 
 /* one exported step (for inspection / the oracle-side plan checker / estimators) */

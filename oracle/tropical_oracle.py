@@ -246,3 +246,38 @@ def exact_mis_clique(nv: int, edges, weights=None) -> float:
         gc.nodes[v]["weight"] = 1 if weights is None else int(weights[v])
     _, wt = nx.max_weight_clique(gc, weight="weight")
     return float(wt)
+
+
+# --------------------------------------------------------------------------------------------
+# the reference's memory estimators (restated; used to check tb_plan_info)
+# --------------------------------------------------------------------------------------------
+def contraction_all_memory(ixs, tree) -> float:
+    """/root/reference/src/utils.jl:222-229: log2 of the summed sizes of every intermediate (all label sizes 2)."""
+    left, right = nested_to_postorder(tree, len(ixs))
+    labs = node_output_labels(ixs, left, right)
+    return float(np.log2(sum(2.0 ** len(labs[len(ixs) + j]) for j in range(len(left)))))
+
+
+def contraction_peak_memory(ixs, tree) -> float:
+    """/root/reference/src/utils.jl:197-219: depth-first walk (first operand first); the running total starts at the
+    summed leaf sizes, every node adds its result and releases the operands of its child nodes; log2 of the maximum."""
+    n_leaves = len(ixs)
+    left, right = nested_to_postorder(tree, n_leaves)
+    labs = node_output_labels(ixs, left, right)
+    tscs = [sum(2.0 ** len(set(ix)) for ix in ixs)]
+
+    def walk(t):  # t = tensor id; returns the summed size of t's operands (released by t's parent)
+        if t < n_leaves:
+            return 0.0
+        j = t - n_leaves
+        freed = 0.0
+        for c in (left[j], right[j]):
+            freed += walk(c)
+        future = sum(2.0 ** len(labs[c]) for c in (left[j], right[j]))
+        tscs.append(tscs[-1] + 2.0 ** len(labs[t]) - freed)
+        return future
+
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 4 * n_leaves + 100))
+    walk(n_leaves + len(left) - 1)
+    return float(np.log2(max(tscs)))

@@ -49,7 +49,7 @@ class tb_plan_stats(C.Structure):
                 ("n_fused_subtrees", C.c_int32), ("n_fused_steps", C.c_int32), ("n_gemm_steps", C.c_int32),
                 ("n_generic_steps", C.c_int32), ("value_type", C.c_int32), ("root_rank", C.c_int32),
                 ("gemm_ops", C.c_double), ("fused_ops", C.c_double), ("generic_ops", C.c_double),
-                ("gemm_bytes", C.c_double)]
+                ("gemm_bytes", C.c_double), ("peak_memory_log2", C.c_double), ("all_memory_log2", C.c_double)]
 
 
 class tb_step_info(C.Structure):

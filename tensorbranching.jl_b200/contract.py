@@ -429,6 +429,22 @@ def complexity(branch: SlicedBranch):
     return dict(tc=st.tc, sc=st.sc)
 
 
+def contraction_peak_memory(branch: SlicedBranch) -> float:
+    """contraction_peak_memory(code, uniformsize(code, 2)) (src/utils.jl:197-219), log2 elements."""
+    p = Plan(branch)
+    v = p.info().peak_memory_log2
+    p.close()
+    return v
+
+
+def contraction_all_memory(branch: SlicedBranch) -> float:
+    """contraction_all_memory (src/utils.jl:222-229), log2 elements."""
+    p = Plan(branch)
+    v = p.info().all_memory_log2
+    p.close()
+    return v
+
+
 def tc(branch):  # src/types.jl:120
     return complexity(branch)["tc"]
 

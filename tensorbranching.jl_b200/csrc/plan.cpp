@@ -354,6 +354,42 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         lab_n[t] = (uint8_t)no;
     }
 
+    // ---- the reference's memory estimators on the GIVEN tree (before any rewrite), in elements, all label sizes 2:
+    //      contraction_all_memory = log2(sum of the sizes of all intermediates)          (src/utils.jl:222-229)
+    //      contraction_peak_memory = log2(max of the running total)                       (src/utils.jl:197-219):
+    //      the walk is depth-first, left operand first; a node adds its result and releases the operands of its
+    //      CHILD nodes (its own operands are released one step later, by its parent) -- restated as the reference has it
+    double est_all = 0, est_peak = 0;
+    {
+        double cur = 0;
+        for (int i = 0; i < net.n_leaves; ++i) cur += std::ldexp(1.0, lab_n[i]);
+        est_peak = cur;
+        std::vector<double> freed_later(nT0, 0.0);  // sum of a node's operand sizes
+        std::vector<int32_t> stack;
+        std::vector<uint8_t> seen(nT0, 0);
+        stack.push_back(root);
+        while (!stack.empty()) {
+            const int t = stack.back();
+            if (leaf[t]) {
+                stack.pop_back();
+                continue;
+            }
+            if (!seen[t]) {
+                seen[t] = 1;
+                stack.push_back(rch[t]);
+                stack.push_back(lch[t]);
+                continue;
+            }
+            stack.pop_back();
+            const double freed = freed_later[lch[t]] + freed_later[rch[t]];
+            const double alloc = std::ldexp(1.0, lab_n[t]);
+            freed_later[t] = std::ldexp(1.0, lab_n[lch[t]]) + std::ldexp(1.0, lab_n[rch[t]]);
+            cur += alloc - freed;
+            est_peak = std::max(est_peak, cur);
+            est_all += alloc;
+        }
+    }
+
     PT(2, "labelsets")
     // stamp arrays for O(1) membership
     std::vector<int32_t> stA(NLAB, -1), stB(NLAB, -1), stC(NLAB, -1);
@@ -1164,6 +1200,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     S.fused_ops = ops_f;
     S.generic_ops = ops_g;
     S.gemm_bytes = bytes_m;
+    S.peak_memory_log2 = est_peak > 0 ? std::log2(est_peak) : 0;
+    S.all_memory_log2 = est_all > 0 ? std::log2(est_all) : 0;
     return TB_OK;
 }
 

@@ -121,3 +121,28 @@ def test_gpu_contract_sliced_large(tb, engine):
     vals, status, mx = engine.contract_index_sliced(br, labels)
     assert (status == 0).all() and np.float32(mx) == want
     assert sc_after < tb.sc(br)
+
+
+@pytest.mark.gpu
+def test_gpu_full_size_branch_over_40_labels(tb, engine):
+    """BASELINE config-4 size: a branch of the n=500 / sc 28 workload whose heaviest node involves 42 labels
+    (2^42 tropical ops in one contraction).  No CPU restatement reaches the whole branch; the size-independent property
+    is that the max over its 2^10 index slices (nodes of <= 32 labels, a sample of them checked against the C oracle)
+    equals the unsliced contraction."""
+    from oracle import c_oracle as CO
+    nv, edges = H.random_regular_graph(500, 3, 4)
+    brs = H.slice_bfs(H.make_root(nv, edges, seed=4, ntrials=6), 28, max_branches=4)
+    b = brs[3]
+    br = to_sliced(b)
+    p = tb.Plan(br, engine=engine)
+    st = p.info()
+    steps = p.steps()
+    assert st.sc == 28 and max(s.n_m + s.n_n + s.n_b + s.n_k + s.n_ka + s.n_kb for s in steps) > 40
+    whole = engine.contract(p)
+    p.close()
+    labels, sc_after, _ = tb.suggest_slices(br, -1, 10)
+    vals, status, mx = engine.contract_index_sliced(br, labels)
+    assert (status == 0).all() and mx == whole
+    live = [a for a in range(1 << 10) if vals[a] > -np.inf][:16]
+    cpu, _, _ = CO.contract_index_slices(b, labels, live)
+    assert np.array_equal(cpu, vals[live])

@@ -144,3 +144,19 @@ def test_arena_reuse_is_smaller_than_keep(tb):
     a = tb.Plan(to_sliced(root)).info().arena_elems
     b = tb.Plan(to_sliced(root), flags=1).info().arena_elems
     assert a < b
+
+
+@pytest.mark.parametrize("n,seed", [(12, 1), (30, 3), (60, 5), (100, 7), (160, 3)])
+def test_memory_estimators_match_reference_formulas(tb, n, seed):
+    """tb_plan_info.peak_memory_log2 / all_memory_log2 == the reference's contraction_peak_memory /
+    contraction_all_memory (src/utils.jl:197-229) restated in the oracle; independent of plan flags."""
+    root = regular_root(n, seed)
+    want_peak = O.contraction_peak_memory(root.ixs, root.tree)
+    want_all = O.contraction_all_memory(root.ixs, root.tree)
+    for flags in (0, 2, 16, 64):
+        st = tb.Plan(to_sliced(root), flags=flags).info()
+        assert st.peak_memory_log2 == pytest.approx(want_peak, abs=1e-12)
+        assert st.all_memory_log2 == pytest.approx(want_all, abs=1e-12)
+    br = to_sliced(root)
+    assert tb.contraction_peak_memory(br) == pytest.approx(want_peak) and tb.contraction_all_memory(br) == pytest.approx(want_all)
+    assert want_peak <= want_all + 1 and st.sc <= want_peak
