@@ -85,6 +85,7 @@ struct tb_ctx {
     bool staged_epilogue = true;           // TB_EPI_DIRECT=1: scatter stores straight from registers (A/B testing)
     bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
     int n_lanes = 4;                       // waves in flight: lane 0 = main stream, others = side streams
+    int waves_per_lane = 2;                // a small call is cut into about this many waves per lane (TB_WAVES_PER_LANE)
     cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
     bool profile = false;          // per-launch CUDA events, accumulated by kernel kind
@@ -751,7 +752,8 @@ int finish_call(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, 
 // multi-GPU run) gets ~2 waves per lane instead of a couple of full ones
 int wave_for_call(const tb_ctx* ctx, int64_t n) {
     const int64_t cfg = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;
-    const int64_t per = (n + 2 * ctx->n_lanes - 1) / (2 * ctx->n_lanes);
+    const int64_t parts = (int64_t)std::max(1, ctx->waves_per_lane) * ctx->n_lanes;
+    const int64_t per = (n + parts - 1) / parts;
     return (int)std::min<int64_t>(cfg, std::max<int64_t>(16, per));
 }
 
@@ -884,6 +886,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
         c->staged_epilogue = !(e3 && e3[0] == '1');
         const char* e4 = getenv("TB_WAVE");
         if (e4 && atoi(e4) >= 1 && c->opts.max_wave == 0) c->opts.max_wave = atoi(e4);
+        const char* e5 = getenv("TB_WAVES_PER_LANE");
+        if (e5 && atoi(e5) >= 1) c->waves_per_lane = atoi(e5);
         const char* e2 = getenv("TB_LANES");
         if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
     }
