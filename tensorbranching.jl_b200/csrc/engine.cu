@@ -85,7 +85,7 @@ struct tb_ctx {
     bool staged_epilogue = true;           // TB_EPI_DIRECT=1: scatter stores straight from registers (A/B testing)
     bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
     int n_lanes = 4;                       // waves in flight: lane 0 = main stream, others = side streams
-    int waves_per_lane = 2;                // a small call is cut into about this many waves per lane (TB_WAVES_PER_LANE)
+    int waves_per_lane = 0;                // waves per lane a small call is cut into; 0 = by plan weight (TB_WAVES_PER_LANE)
     cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
     bool profile = false;          // per-launch CUDA events, accumulated by kernel kind
@@ -748,13 +748,28 @@ int finish_call(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, 
     return TB_OK;
 }
 
-// waves of up to 128 plans (profiles/s03_wave_lane_sweep_cfg2.jsonl); a call with few plans (one rank's shard of a
-// multi-GPU run) gets ~2 waves per lane instead of a couple of full ones
-int wave_for_call(const tb_ctx* ctx, int64_t n) {
-    const int64_t cfg = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128;
-    const int64_t parts = (int64_t)std::max(1, ctx->waves_per_lane) * ctx->n_lanes;
+// Wave size of a call.  Heavy plans (cfg2: 2^27 ops each): waves of up to 128 plans, and a call with few plans (one
+// rank's shard of a multi-GPU run) is cut into ~2 waves per lane (profiles/s03_wave_lane_sweep_cfg2.jsonl).  Light plans
+// (cfg5: 2^22.5 ops each) are launch-bound: waves of up to 256, one per lane (profiles/s05_wave_sweep_cfg5_cfg2.jsonl:
+// 1.78 ms instead of 2.16 ms for 1 024 plans).  mean_ops <= 0: unknown, treated as heavy.
+int wave_for_call(const tb_ctx* ctx, int64_t n, double mean_ops) {
+    const bool light = mean_ops > 0 && mean_ops < (double)(1 << 24);
+    const int64_t cfg = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : (light ? 256 : 128);
+    const int wpl = ctx->waves_per_lane > 0 ? ctx->waves_per_lane : (light ? 1 : 2);
+    const int64_t parts = (int64_t)wpl * ctx->n_lanes;
     const int64_t per = (n + parts - 1) / parts;
     return (int)std::min<int64_t>(cfg, std::max<int64_t>(16, per));
+}
+
+double mean_plan_ops(tb_plan* const* plans, int64_t lo, int64_t hi) {
+    double sum = 0;
+    int64_t cnt = 0;
+    for (int64_t i = lo; i < hi; ++i)
+        if (plans[i]) {
+            sum += plans[i]->p.stats.ops;
+            ++cnt;
+        }
+    return cnt ? sum / (double)cnt : 0.0;
 }
 
 int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
@@ -767,7 +782,7 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
     bool any = false;
     for (int64_t i = 0; i < n; ++i) any = any || plans[i];
     // batches of growing size: the GPU starts on the first wave while the host still builds the work lists of the rest
-    const int64_t wave = wave_for_call(ctx, n);
+    const int64_t wave = wave_for_call(ctx, n, mean_plan_ops(plans, 0, n));
     ctx->call_wave = (int)wave;
     int64_t batch = single ? n : wave;
     for (int64_t lo = 0; lo < n && rc == TB_OK;) {
@@ -1101,8 +1116,8 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     };
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
-    ctx->call_wave = wave_for_call(ctx, n);
-    const int64_t batch_max = std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
+    ctx->call_wave = wave_for_call(ctx, n, 0.0);  // refined from the first compiled batch below
+    int64_t batch_max = std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
     std::vector<int32_t> status((size_t)n, TB_OK);
     bool any = false;
     double t_wait = 0;
@@ -1150,6 +1165,10 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
             }
             any = any || plans[i];
         }
+        if (rc == TB_OK && lo == 0) {  // the plans' weight is known now: light plans get larger waves
+            ctx->call_wave = wave_for_call(ctx, n, mean_plan_ops(plans.data(), lo, hi));
+            batch_max = std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
+        }
         if (rc == TB_OK) rc = enqueue_batch(ctx, plans.data(), lo, hi, status, false);
     }
     abort.store(rc != TB_OK);
@@ -1174,7 +1193,7 @@ int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream) try {
     s->ctx = ctx;
     s->capacity = capacity;
     s->t0 = now_ms();
-    ctx->call_wave = wave_for_call(ctx, std::max<int64_t>(capacity, 1024));
+    ctx->call_wave = wave_for_call(ctx, std::max<int64_t>(capacity, 1024), 0.0);
     ctx->stream_open = true;
     *out_stream = s.release();
     return TB_OK;
@@ -1219,6 +1238,7 @@ int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_
     for (int64_t i = 0; i < n && rc == TB_OK; ++i)
         if (codes[i]) rc = set_err(ctx, codes[i], "branch " + std::to_string(lo + i) + ": " + errs[i]);
     for (int64_t i = lo; i < hi; ++i) s->any = s->any || s->plans[(size_t)i];
+    if (rc == TB_OK && lo == 0) ctx->call_wave = wave_for_call(ctx, std::max<int64_t>(s->capacity, 1024), mean_plan_ops(s->plans.data(), lo, hi));
     // the launches are asynchronous: the call returns while the GPU contracts, the host goes back to slicing
     if (rc == TB_OK) rc = enqueue_batch(ctx, s->plans.data(), lo, hi, s->status, false);
     if (rc) s->failed = true;
