@@ -58,6 +58,8 @@ static float* permute(const tens* src, const int* order, int n_order) {
             lut[by][v] = s;
         }
     const float* sd = src->data;
+    /* threads only when the caller is not already inside the branch-parallel loop (nested regions are serialised) */
+#pragma omp parallel for schedule(static) if (n >= ((size_t)1 << 20))
     for (size_t hi = 0; hi < n; hi += 256) {
         size_t sb = 0;
         for (int by = 1; by < nbytes; ++by) sb |= lut[by][(hi >> (8 * by)) & 255];
@@ -83,27 +85,98 @@ static void reduce_label(tens* t, int pos) {
     t->rank--;
 }
 
-/* C[n, m, b] = max_k A[k, m, b] + B[n, k, b]   (n fastest everywhere) */
-static void tropical_gemm(const float* A, const float* B, float* C, int lm, int ln, int lk, int lb) {
-    const size_t M = (size_t)1 << lm, N = (size_t)1 << ln, K = (size_t)1 << lk, Bn = (size_t)1 << lb;
-    for (size_t b = 0; b < Bn; ++b) {
-        const float* Ab = A + b * M * K;
-        const float* Bb = B + b * N * K;
-        float* Cb = C + b * M * N;
-        for (size_t m = 0; m < M; ++m) {
-            float* c = Cb + m * N;
-            for (size_t n = 0; n < N; ++n) c[n] = -INFINITY;
-            for (size_t k = 0; k < K; ++k) {
-                const float a = Ab[m * K + k];
-                const float* __restrict brow = Bb + k * N;
+/* C[n, m, b] = max_k A[k, m, b] + B[n, k, b]   (n fastest everywhere).
+ * TropicalGEMM.jl's role [upstream]: a register-tiled SIMD max-plus micro-kernel (it uses LoopVectorization; here
+ * AVX2 / AVX-512 intrinsics, 4 rows x 2 vectors of accumulators, k innermost) so that the CPU baseline is a fair
+ * one; the plain loop below covers the shapes too small for a tile.  Row blocks are spread over OpenMP threads when
+ * the caller is not already inside a parallel region (single heavy branches). */
+#if defined(__AVX512F__)
+#include <immintrin.h>
+typedef __m512 vf;
+#define VL 16
+#define vf_set1(x) _mm512_set1_ps(x)
+#define vf_loadu(p) _mm512_loadu_ps(p)
+#define vf_storeu(p, v) _mm512_storeu_ps(p, v)
+#define vf_add(a, b) _mm512_add_ps(a, b)
+#define vf_max(a, b) _mm512_max_ps(a, b)
+#define TREF_SIMD "avx512"
+#elif defined(__AVX2__)
+#include <immintrin.h>
+typedef __m256 vf;
+#define VL 8
+#define vf_set1(x) _mm256_set1_ps(x)
+#define vf_loadu(p) _mm256_loadu_ps(p)
+#define vf_storeu(p, v) _mm256_storeu_ps(p, v)
+#define vf_add(a, b) _mm256_add_ps(a, b)
+#define vf_max(a, b) _mm256_max_ps(a, b)
+#define TREF_SIMD "avx2"
+#else
+#define TREF_SIMD "scalar"
+#endif
+
+const char* tref_simd(void) { return TREF_SIMD; }
+
+static void tropical_gemm_plain(const float* Ab, const float* Bb, float* Cb, size_t M, size_t N, size_t K) {
+    for (size_t m = 0; m < M; ++m) {
+        float* c = Cb + m * N;
+        for (size_t n = 0; n < N; ++n) c[n] = -INFINITY;
+        for (size_t k = 0; k < K; ++k) {
+            const float a = Ab[m * K + k];
+            const float* __restrict brow = Bb + k * N;
 #pragma omp simd
-                for (size_t n = 0; n < N; ++n) {
-                    float v = a + brow[n];
-                    c[n] = v > c[n] ? v : c[n];
-                }
+            for (size_t n = 0; n < N; ++n) {
+                float v = a + brow[n];
+                c[n] = v > c[n] ? v : c[n];
             }
         }
     }
+}
+
+#ifdef VL
+/* one 4 x (2 VL) tile of C: rows m0..m0+3, columns n0..n0+2VL-1 */
+static inline void tile_4x2(const float* Ab, const float* Bb, float* Cb, size_t m0, size_t n0, size_t N, size_t K) {
+    const vf ninf = vf_set1(-INFINITY);
+    vf c00 = ninf, c01 = ninf, c10 = ninf, c11 = ninf, c20 = ninf, c21 = ninf, c30 = ninf, c31 = ninf;
+    const float *a0 = Ab + (m0 + 0) * K, *a1 = Ab + (m0 + 1) * K, *a2 = Ab + (m0 + 2) * K, *a3 = Ab + (m0 + 3) * K;
+    const float* b = Bb + n0;
+    for (size_t k = 0; k < K; ++k, b += N) {
+        const vf b0 = vf_loadu(b), b1 = vf_loadu(b + VL);
+        vf a = vf_set1(a0[k]);
+        c00 = vf_max(c00, vf_add(a, b0)); c01 = vf_max(c01, vf_add(a, b1));
+        a = vf_set1(a1[k]);
+        c10 = vf_max(c10, vf_add(a, b0)); c11 = vf_max(c11, vf_add(a, b1));
+        a = vf_set1(a2[k]);
+        c20 = vf_max(c20, vf_add(a, b0)); c21 = vf_max(c21, vf_add(a, b1));
+        a = vf_set1(a3[k]);
+        c30 = vf_max(c30, vf_add(a, b0)); c31 = vf_max(c31, vf_add(a, b1));
+    }
+    float* c = Cb + m0 * N + n0;
+    vf_storeu(c, c00); vf_storeu(c + VL, c01);
+    vf_storeu(c + N, c10); vf_storeu(c + N + VL, c11);
+    vf_storeu(c + 2 * N, c20); vf_storeu(c + 2 * N + VL, c21);
+    vf_storeu(c + 3 * N, c30); vf_storeu(c + 3 * N + VL, c31);
+}
+#endif
+
+static void tropical_gemm(const float* A, const float* B, float* C, int lm, int ln, int lk, int lb) {
+    const size_t M = (size_t)1 << lm, N = (size_t)1 << ln, K = (size_t)1 << lk, Bn = (size_t)1 << lb;
+#ifdef VL
+    if (M >= 4 && N >= 2 * VL) {
+        /* work items = (batch, block of 4 rows); a B column panel (K x 2VL) is reused by consecutive row blocks */
+        const size_t mblocks = M / 4, items = Bn * mblocks;
+        const int par = items >= 64 && (double)M * (double)N * (double)K * (double)Bn >= 1e7;
+#pragma omp parallel for schedule(static) if (par)
+        for (size_t it = 0; it < items; ++it) {
+            const size_t b = it / mblocks, m0 = (it % mblocks) * 4;
+            const float* Ab = A + b * M * K;
+            const float* Bb = B + b * N * K;
+            float* Cb = C + b * M * N;
+            for (size_t n0 = 0; n0 < N; n0 += 2 * VL) tile_4x2(Ab, Bb, Cb, m0, n0, N, K);
+        }
+        return;
+    }
+#endif
+    for (size_t b = 0; b < Bn; ++b) tropical_gemm_plain(A + b * M * K, B + b * N * K, C + b * M * N, M, N, K);
 }
 
 static int in_list(const int* v, int n, int x) {
@@ -272,7 +345,7 @@ int tref_contract_slices_of(int n, int n_labels, int n_leaves, const int* leaf_o
 #ifdef _OPENMP
     nthreads = omp_get_max_threads();
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
+#pragma omp parallel for schedule(dynamic, 1) if (n >= nthreads)
     for (int i = 0; i < n; ++i) {
         double ops = 0;
         tref_contract_fixed(n_labels, n_leaves, leaf_off, leaf_labels, left, right, weights,
@@ -289,7 +362,9 @@ int tref_contract_batch(int n, const int* n_labels, const int* n_leaves, const i
 #ifdef _OPENMP
     nthreads = omp_get_max_threads();
 #endif
-#pragma omp parallel for schedule(dynamic, 1)
+    /* many branches: one branch per thread (the most favourable CPU arrangement); fewer branches than threads: the
+     * branches run one after the other and the threads share each GEMM / permute instead */
+#pragma omp parallel for schedule(dynamic, 1) if (n >= nthreads)
     for (int i = 0; i < n; ++i) {
         double ops = 0;
         if (n_leaves[i] == 0) {
