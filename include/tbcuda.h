@@ -17,8 +17,9 @@
  *     by tb_plan_create).  Handles are library-owned and freed only by the matching destroy call.
  *     Outputs go to caller-allocated buffers.  Device memory never crosses the ABI.
  *   - one tb_ctx is used from one host thread at a time; calls block until results are on the host.
- *     Distinct contexts are independent.  The library installs no signal handlers and owns no thread
- *     that outlives the call that spawned it.
+ *     Distinct contexts are independent.  The library installs no signal handlers; its worker threads end with
+ *     the call that spawned them, except one short-lived helper that frees the host side of a call's temporary
+ *     plans, which is joined by the next call or by tb_shutdown (no thread outlives tb_shutdown).
  *   - a tensor "layout" is a list of labels in address-bit order, bit 0 (fastest) first -- i.e.
  *     Julia's column-major dimension order.  Every label has size 2 (uniformsize(code, 2),
  *     /root/reference/src/types.jl:118).
