@@ -213,16 +213,19 @@ def cpu_reference_run(branches, budget_s, ops_per_branch):
     from oracle import c_oracle as CO
 
     flats = [None if b.nv == 0 else CO.flatten(b) for b in branches]
-    # calibrate on a small prefix, then size the sample
-    n0 = min(len(flats), 8)
-    t = time.perf_counter()
-    _, ops0, th = CO.contract_batch(flats[:n0])
-    dt0 = max(time.perf_counter() - t, 1e-6)
-    rate = n0 / dt0
-    n = int(min(len(flats), max(n0, rate * budget_s)))
-    t = time.perf_counter()
-    vals, ops, th = CO.contract_batch(flats[:n])
-    dt = time.perf_counter() - t
+    # calibrate on a prefix that gives every thread several branches, then size the sample to the budget (and grow it
+    # once more if it still finished far too early: a prefix of light branches underestimates the rate)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = min(len(flats), max(8, 4 * cores))
+    vals = ops = th = None
+    dt = 0.0
+    for _ in range(3):
+        t = time.perf_counter()
+        vals, ops, th = CO.contract_batch(flats[:n])
+        dt = max(time.perf_counter() - t, 1e-6)
+        if n >= len(flats) or dt >= 0.4 * budget_s:
+            break
+        n = int(min(len(flats), max(n + 1, 0.8 * n * budget_s / dt)))
     return float(ops.sum()) / dt * 1e-9, th, f"first {n} of {len(flats)} branches of the workload, {dt:.1f} s", dt, vals
 
 
