@@ -216,6 +216,12 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
                        int64_t first, int64_t count, double r, double* out_values, int32_t* out_status,
                        double* out_max);
 
+/* A plan created with fixed labels, re-targeted to another assignment of the SAME labels (fixed_values[i] for
+ * fixed_labels[i] of the network it was created from): the 2^k assignments share every descriptor and layout and
+ * differ only in a few leaf-pool words, so this is a copy plus a patch, ~30x cheaper than tb_plan_create.
+ * tb_contract_sliced uses it internally (one compilation per call). */
+int tb_plan_reassign(const tb_plan* base, const uint8_t* fixed_values, tb_plan** out_plan);
+
 /* Pick up to max_sliced labels to slice, greedily.  sc_target >= 0 (memory-driven): until the largest tensor has
  * rank <= sc_target, each pick is the label held by most tensors of the current top rank (ties: most ops removed).
  * sc_target < 0 (parallelism-driven): always max_sliced labels, each pick the label whose removal takes away most

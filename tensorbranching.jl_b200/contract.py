@@ -114,6 +114,17 @@ class Plan:
         L.check(lib.tb_plan_create(engine.handle if engine else None, C.byref(net), C.byref(self.handle)),
                 engine.handle if engine else None)
 
+    def reassign(self, fixed: dict) -> "Plan":
+        """tb_plan_reassign: this plan (created with fixed labels) for another assignment of the same labels."""
+        fl = self._keep[2] if len(self._keep) > 2 else []
+        fv = np.asarray([fixed[int(l)] for l in fl] + [0], dtype=np.uint8)  # (+1 pad: never an empty buffer)
+        q = Plan.__new__(Plan)
+        q._lib = self._lib
+        q.handle = C.c_void_p()
+        q._keep = self._keep
+        L.check(self._lib.tb_plan_reassign(self.handle, fv.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(q.handle)))
+        return q
+
     def info(self) -> L.tb_plan_stats:
         st = L.tb_plan_stats()
         L.check(self._lib.tb_plan_info(self.handle, C.byref(st)))

@@ -180,17 +180,24 @@ int acquire_slot(tb_ctx* ctx, size_t hbytes, size_t dbytes, tb_ctx::Slot** out) 
         TB_CUDA(ctx, cudaEventSynchronize(sl.ev));
         sl.busy = false;
     }
+    // a slot that has to grow grows to the largest size any slot has reached: the ring converges in at most kSlots
+    // (re)allocations instead of re-pinning memory (tens of ms) whenever a large batch meets a small free slot
+    size_t max_h = 0, max_d = 0;
+    for (const tb_ctx::Slot& c : ctx->slots) {
+        max_h = std::max(max_h, c.hcap);
+        max_d = std::max(max_d, c.dcap);
+    }
     if (sl.hcap < hbytes) {
         if (sl.h) cudaFreeHost(sl.h);
         sl.h = nullptr;
-        size_t cap = std::max(hbytes * 5 / 4, (size_t)1 << 20);
+        size_t cap = std::max(std::max(hbytes * 5 / 4, (size_t)1 << 20), max_h);
         TB_CUDA(ctx, cudaMallocHost(&sl.h, cap));
         sl.hcap = cap;
     }
     if (sl.dcap < dbytes) {
         if (sl.d) cudaFree(sl.d);
         sl.d = nullptr;
-        size_t cap = std::max(dbytes * 5 / 4, (size_t)1 << 20);
+        size_t cap = std::max(std::max(dbytes * 5 / 4, (size_t)1 << 20), max_d);
         TB_CUDA(ctx, cudaMalloc(&sl.d, cap));
         sl.dcap = cap;
     }
@@ -798,6 +805,18 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
     return finish_call(ctx, plans, r, n, status, out_values, out_status, out_max, any);
 }
 
+// a copy of `base` (compiled with fixed labels) for another assignment of the same labels: the descriptors are shared
+// by value, only the leaf-pool words of the sliced leaves change; the copy is not resident anywhere
+tb_plan* clone_for_assignment(const tb_plan* base, const uint8_t* values) {
+    tb_plan* p = new tb_plan(*base);
+    p->p.owner = nullptr;
+    p->p.d_blob = nullptr;
+    p->p.res_prev = p->p.res_next = nullptr;
+    p->p.blob_bytes = 0;
+    p->p.assign(values);
+    return p;
+}
+
 // the temporary plans of a *_networks / stream call all live in chunks of that call: release the device side once,
 // free the host side off the caller's critical path (joined by the next call / tb_shutdown)
 void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans) {
@@ -1309,25 +1328,44 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
         if (ok) live.push_back(a);
     }
     int rc = TB_OK;
-    if (!live.empty()) {
-        const size_t nl = live.size();
-        std::vector<uint8_t> fv(nl * (size_t)std::max(n_sliced, 1));
-        std::vector<tb_network> nets(nl, *net);
-        for (size_t q = 0; q < nl; ++q) {
-            uint8_t* f = fv.data() + q * (size_t)std::max(n_sliced, 1);
-            for (int i = 0; i < n_sliced; ++i) f[i] = (uint8_t)((live[q] >> i) & 1);
-            nets[q].n_fixed = n_sliced;
-            nets[q].fixed_labels = sliced_labels;
-            nets[q].fixed_values = f;
+    // ONE compilation: every assignment is the same plan with other leaf-pool words (clone_for_assignment), contracted
+    // as resident plans in chunks
+    const double t_c0 = now_ms();
+    double t_build = 0;
+    const size_t kChunk = 4096;
+    std::unique_ptr<tb_plan> base;
+    std::vector<uint8_t> fv((size_t)std::max(n_sliced, 1));
+    auto values_of = [&](int64_t a) {
+        for (int i = 0; i < n_sliced; ++i) fv[(size_t)i] = (uint8_t)((a >> i) & 1);
+        return fv.data();
+    };
+    for (size_t c0 = 0; c0 < live.size() && rc == TB_OK; c0 += kChunk) {
+        const size_t c1 = std::min(live.size(), c0 + kChunk), nl = c1 - c0;
+        const double tb0 = now_ms();
+        if (!base) {
+            tb_network n0 = *net;
+            n0.n_fixed = n_sliced;
+            n0.fixed_labels = sliced_labels;
+            n0.fixed_values = values_of(live[0]);
+            base.reset(new tb_plan());
+            std::string err;
+            rc = compile_plan(n0, ctx->opts.plan_flags, base->p, err);
+            if (rc) return set_err(ctx, rc, err);
         }
+        std::vector<tb_plan*> plans(nl, nullptr);
+        for (size_t q = 0; q < nl; ++q) plans[q] = clone_for_assignment(base.get(), values_of(live[c0 + q]));
+        t_build += now_ms() - tb0;
         std::vector<double> lv(nl), rr(nl, r);
         std::vector<int32_t> ls(nl, TB_OK);
-        rc = tb_contract_networks(ctx, nets.data(), rr.data(), (int64_t)nl, lv.data(), ls.data(), nullptr);
+        rc = contract_impl(ctx, plans.data(), rr.data(), (int64_t)nl, lv.data(), ls.data(), nullptr, false);
         for (size_t q = 0; q < nl; ++q) {
-            vals[(size_t)(live[q] - first)] = lv[q];
-            stat[(size_t)(live[q] - first)] = ls[q];
+            vals[(size_t)(live[c0 + q] - first)] = lv[q];
+            stat[(size_t)(live[c0 + q] - first)] = ls[q];
         }
+        release_temporary_plans(ctx, std::move(plans));
     }
+    ctx->host_ms[0] = t_build;
+    ctx->host_ms[5] = now_ms() - t_c0;
     double mx = ninf;
     for (int64_t i = 0; i < count; ++i)
         if (stat[(size_t)i] == TB_OK && vals[(size_t)i] > mx) mx = vals[(size_t)i];
@@ -1336,6 +1374,16 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
     if (out_max) *out_max = mx;
     return rc;
 } TB_CATCH(ctx)
+
+int tb_plan_reassign(const tb_plan* base, const uint8_t* fixed_values, tb_plan** out_plan) try {
+    if (!base || !fixed_values || !out_plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "base / fixed_values / out_plan is NULL");
+    *out_plan = nullptr;
+    if (base->p.n_fixed <= 0) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "the base plan was not created with fixed labels");
+    for (int i = 0; i < base->p.n_fixed; ++i)
+        if (fixed_values[i] > 1) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "fixed value must be 0 or 1");
+    *out_plan = clone_for_assignment(base, fixed_values);
+    return TB_OK;
+} TB_CATCH(nullptr)
 
 int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int32_t max_sliced, int32_t* out_labels,
                       double* out_sc, double* out_tc) try {

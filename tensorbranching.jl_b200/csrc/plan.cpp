@@ -153,16 +153,19 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
 
     // ---- index slicing: fixed[l] = -1 (free) or the value label l is fixed to
     std::vector<int8_t> fixed;
+    std::vector<int32_t> fixed_idx;  // label -> its position in net.fixed_labels
     if (net.n_fixed < 0 || (net.n_fixed > 0 && (!net.fixed_labels || !net.fixed_values)))
         return fail(TB_ERR_BAD_ARGUMENT, "bad fixed labels");
     if (net.n_fixed > 0) {
         fixed.assign(NLAB, -1);
+        fixed_idx.assign(NLAB, -1);
         for (int i = 0; i < net.n_fixed; ++i) {
             int32_t l = net.fixed_labels[i];
             if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "fixed label out of range");
             if (fixed[l] >= 0) return fail(TB_ERR_BAD_ARGUMENT, "fixed label repeated");
             if (net.fixed_values[i] > 1) return fail(TB_ERR_BAD_ARGUMENT, "fixed value must be 0 or 1");
             fixed[l] = (int8_t)net.fixed_values[i];
+            fixed_idx[l] = i;
         }
         for (int i = 0; i < net.n_open; ++i)
             if (net.open_labels[i] >= 0 && net.open_labels[i] < net.n_labels && fixed[net.open_labels[i]] >= 0)
@@ -170,10 +173,10 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     }
 
     // ---- leaves.  leaf_vertex[i] = vertex of a vertex leaf (-1: edge / unit leaf).  A leaf that lost labels to
-    //      index slicing reads a slice of its tensor: leaf_src[i] = fixed pool offset (-1: the tensor as a whole),
-    //      leaf_wsel[i] = 1 when a vertex leaf became the scalar w_v (the second element of its pool pair).
-    std::vector<int32_t> leaf_vertex(nL, -1), leaf_src(nL, -1);
-    std::vector<uint8_t> leaf_wsel(nL, 0);
+    //      index slicing reads a slice of its tensor from a pool slot of its own, filled by Plan::assign from the
+    //      values of its fixed labels (leaf_fa / leaf_fb = their positions in net.fixed_labels): all 2^k assignments
+    //      of the same labels share every descriptor of the plan and differ only in these pool words.
+    std::vector<int32_t> leaf_vertex(nL, -1), leaf_fa(nL, -1), leaf_fb(nL, -1);
     for (int i = 0; i < nL; ++i) leaf[i] = 1;
     for (int i = 0; i < net.n_leaves; ++i) {
         int b = net.leaf_off[i], e = net.leaf_off[i + 1];
@@ -183,13 +186,12 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             return fail(TB_ERR_UNSUPPORTED, "leaf " + std::to_string(i) + " has " + std::to_string(r) +
                                                 " labels; IndependentSet leaves have 1 (vertex) or 2 (edge)");
         lab_off[i] = (int32_t)lab_data.size();
-        int nfix = 0, nset = 0;  // fixed labels of this leaf / how many of them are fixed to 1
+        int nfix = 0;  // fixed labels of this leaf
         for (int q = b; q < e; ++q) {
             int32_t l = net.leaf_labels[q];
             if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "leaf label out of range");
             if (!fixed.empty() && fixed[l] >= 0) {
-                ++nfix;
-                nset += fixed[l];
+                (nfix++ ? leaf_fb[i] : leaf_fa[i]) = fixed_idx[l];
             } else {
                 lab_data.push_back(l);
             }
@@ -201,16 +203,6 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         if (lab_n[i] == 2) {
             int32_t* v = lab_data.data() + lab_off[i];
             if (v[0] > v[1]) std::swap(v[0], v[1]);
-        }
-        if (nfix) {
-            if (r == 1) {  // [0, w][x]
-                if (nset) leaf_wsel[i] = 1;
-                else leaf_src[i] = POOL_UNIT;
-            } else if (nfix == 1) {  // the edge tensor is symmetric: row 0 = (0, 0), row 1 = (0, -inf)
-                leaf_src[i] = POOL_EDGE + 2 * nset;
-            } else {  // both ends fixed: -inf iff both are 1
-                leaf_src[i] = nset == 2 ? POOL_EDGE + 3 : POOL_UNIT;
-            }
         }
     }
     if (synth) lab_off[1] = (int32_t)lab_data.size();
@@ -745,17 +737,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     // ---- pool (leaf tensors)
     std::vector<int32_t> leaf_pool_off(nT, 0);
     {
-        auto push_val = [&](double x, bool neg_inf) {
-            uint32_t bits;
-            if (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2) {
-                int32_t v = neg_inf ? (half ? Tropical<int16_t>::kNegInf : Tropical<int32_t>::kNegInf) : (int32_t)x;
-                std::memcpy(&bits, &v, 4);
-            } else {
-                float v = neg_inf ? -std::numeric_limits<float>::infinity() : (float)x;
-                std::memcpy(&bits, &v, 4);
-            }
-            P.pool.push_back(bits);
-        };
+        auto push_val = [&](double x, bool neg_inf) { P.pool.push_back(Plan::encode_value(vt, x, neg_inf)); };
         P.pool.reserve(8 + 2 * (size_t)nL + 4);
         push_val(0, false); push_val(0, false); push_val(0, false); push_val(0, true);  // edge
         push_val(0, false);                                                            // unit
@@ -764,8 +746,29 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         for (int i = 0; i < nT; ++i) {
             if (!leaf[i]) continue;
             const int vtx = i < nL ? leaf_vertex[i] : -1;
-            if (i < nL && leaf_src[i] >= 0) {
-                leaf_pool_off[i] = leaf_src[i];
+            if (i < nL && leaf_fa[i] >= 0) {
+                // sliced leaf: a 2-element slot of its own.  vertex [0, w][x] -> scalar; edge with one end fixed -> row x of
+                // the (symmetric) edge tensor, (0, 0) or (0, -inf); both ends fixed -> scalar, -inf iff both are 1
+                double w = 0;
+                if (vtx >= 0) {
+                    w = weight_of(vtx);
+                    if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
+                    if (vt != TB_VALUE_F32) {
+                        if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
+                        sum_abs += std::fabs(w);
+                        if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
+                    }
+                }
+                Plan::PoolPatch pp{};
+                pp.off = (int32_t)P.pool.size();
+                pp.kind = (uint8_t)(vtx >= 0 ? 0 : (leaf_fb[i] < 0 ? 1 : 2));
+                pp.fa = leaf_fa[i];
+                pp.fb = leaf_fb[i];
+                pp.w = w;
+                P.patches.push_back(pp);
+                leaf_pool_off[i] = pp.off;
+                push_val(0, false);
+                push_val(0, false);
             } else if (vtx < 0 && lab_n[i] == 0) {
                 leaf_pool_off[i] = POOL_UNIT;
             } else if (vtx < 0) {
@@ -778,12 +781,14 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                     sum_abs += std::fabs(w);
                     if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
                 }
-                leaf_pool_off[i] = (int32_t)P.pool.size() + leaf_wsel[i];
+                leaf_pool_off[i] = (int32_t)P.pool.size();
                 push_val(0, false);
                 push_val(w, false);
             }
         }
         while (P.pool.size() % 4) P.pool.push_back(0);
+        P.n_fixed = net.n_fixed;
+        if (net.n_fixed > 0) P.assign(net.fixed_values);
         if (P.pool.size() > 65535) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;  // fused steps address the pool with 16 bits
     }
 
@@ -1354,6 +1359,32 @@ tb_step_info Plan::step_info(size_t i) const {
     for (int q = 0; q < s.rank_b; ++q) s.labels_b[q] = layout(r.right)[q];
     for (int q = 0; q < s.rank_c; ++q) s.labels_c[q] = layout(r.node)[q];
     return s;
+}
+
+uint32_t Plan::encode_value(int vt, double x, bool neg_inf) {
+    uint32_t bits;
+    if (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2) {
+        int32_t v = neg_inf ? (vt == TB_VALUE_I16X2 ? Tropical<int16_t>::kNegInf : Tropical<int32_t>::kNegInf) : (int32_t)x;
+        std::memcpy(&bits, &v, 4);
+    } else {
+        float v = neg_inf ? -std::numeric_limits<float>::infinity() : (float)x;
+        std::memcpy(&bits, &v, 4);
+    }
+    return bits;
+}
+
+void Plan::assign(const uint8_t* values) {
+    for (const PoolPatch& pp : patches) {
+        const bool a = values[pp.fa] != 0, b = pp.fb >= 0 && values[pp.fb] != 0;
+        switch (pp.kind) {
+            case 0: pool[pp.off] = encode_value(value_type, a ? pp.w : 0.0, false); break;
+            case 1:
+                pool[pp.off] = encode_value(value_type, 0.0, false);
+                pool[pp.off + 1] = encode_value(value_type, 0.0, a);
+                break;
+            default: pool[pp.off] = encode_value(value_type, 0.0, a && b); break;
+        }
+    }
 }
 
 void Plan::write_pool(uint8_t* dst) const {

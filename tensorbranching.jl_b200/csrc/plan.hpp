@@ -31,6 +31,18 @@ struct Plan {
 
     // descriptors
     std::vector<uint32_t> pool;  // one 32-bit slot per pool element (int32 / float bits); narrowed to int16 on upload
+    // index slicing: the pool words that depend on the values of the fixed labels.  A plan compiled for one assignment
+    // becomes the plan of another by assign() alone (same descriptors, same layouts).
+    struct PoolPatch {
+        int32_t off;      // pool slot of the sliced leaf
+        uint8_t kind;     // 0 vertex leaf, 1 edge leaf with one end fixed, 2 edge leaf with both ends fixed
+        int32_t fa, fb;   // positions of the leaf's fixed labels in the fixed-label list (fb = -1: none)
+        double w;         // vertex weight (kind 0)
+    };
+    std::vector<PoolPatch> patches;
+    int n_fixed = 0;
+    void assign(const uint8_t* values);  // values[i] = 0 / 1 for fixed label i
+    static uint32_t encode_value(int value_type, double x, bool neg_inf);
     int elem_size() const { return value_type == TB_VALUE_I16X2 ? 2 : 4; }
     size_t pool_bytes() const { return pool.size() * (size_t)elem_size(); }
     void write_pool(uint8_t* dst) const;  // device representation of the pool

@@ -36,6 +36,25 @@ def test_sliced_plans_equal_oracle_slices(tb, n, seed, k, flags):
     assert best == full
 
 
+@pytest.mark.parametrize("n,seed,k,flags", [(30, 3, 3, 0), (60, 5, 4, 0), (60, 5, 3, 64), (40, 9, 3, 8)])
+def test_reassigned_plan_equals_compiled_plan(tb, n, seed, k, flags):
+    """tb_plan_reassign: one compilation, the other assignments are copies with patched leaf-pool words -- the same
+    descriptors byte for byte, the same pool as a fresh compilation, the oracle's slice value."""
+    root = regular_root(n, seed)
+    br = to_sliced(root)
+    labels, _, _ = tb.suggest_slices(br, -1, k)
+    base = tb.Plan(br, flags=flags, fixed={l: 0 for l in labels})
+    for a, fixed in _assignments(labels):
+        q = base.reassign(fixed)
+        fresh = tb.Plan(br, flags=flags, fixed=fixed)
+        for which in range(6):
+            assert q.raw(which) == fresh.raw(which), (a, which)
+        val, _ = DI.run_plan(q)
+        assert val == O.solve_slice(root, np.float64, fixed=fixed)
+    with pytest.raises(tb.TBError):
+        tb.Plan(br).reassign({})  # not a sliced plan
+
+
 def test_sliced_weighted_f32(tb):
     rng = np.random.default_rng(5)
     nv, edges = H.random_regular_graph(40, 3, 9)
