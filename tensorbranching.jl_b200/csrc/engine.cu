@@ -1136,7 +1136,13 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
     ctx->call_wave = wave_for_call(ctx, n, 0.0);  // refined from the first compiled batch below
-    int64_t batch_max = std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
+    // TB_BATCH_MAX (experiments): upper bound of a pipeline batch; smaller batches keep the GPU closer behind the
+    // compiler threads (shorter tail after the last plan is compiled) at the price of smaller waves
+    static const int64_t batch_cap = [] {
+        const char* e = getenv("TB_BATCH_MAX");
+        return e && atoll(e) >= 16 ? (int64_t)atoll(e) : (int64_t)0;
+    }();
+    int64_t batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
     std::vector<int32_t> status((size_t)n, TB_OK);
     bool any = false;
     double t_wait = 0;
@@ -1186,7 +1192,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
         }
         if (rc == TB_OK && lo == 0) {  // the plans' weight is known now: light plans get larger waves
             ctx->call_wave = wave_for_call(ctx, n, mean_plan_ops(plans.data(), lo, hi));
-            batch_max = std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
+            batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
         }
         if (rc == TB_OK) rc = enqueue_batch(ctx, plans.data(), lo, hi, status, false);
     }
