@@ -1142,7 +1142,8 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
         const char* e = getenv("TB_BATCH_MAX");
         return e && atoll(e) >= 16 ? (int64_t)atoll(e) : (int64_t)0;
     }();
-    int64_t batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
+    // two waves per batch (profiles/s06_e2e_batch_sweep_cfg2.jsonl: 34.6 ms with 256-plan batches, 37.6 ms with 512)
+    int64_t batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes / 2);
     std::vector<int32_t> status((size_t)n, TB_OK);
     bool any = false;
     double t_wait = 0;
@@ -1192,7 +1193,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
         }
         if (rc == TB_OK && lo == 0) {  // the plans' weight is known now: light plans get larger waves
             ctx->call_wave = wave_for_call(ctx, n, mean_plan_ops(plans.data(), lo, hi));
-            batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes);
+            batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes / 2);
         }
         if (rc == TB_OK) rc = enqueue_batch(ctx, plans.data(), lo, hi, status, false);
     }
