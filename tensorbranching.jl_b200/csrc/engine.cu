@@ -1115,7 +1115,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     nthreads = std::max(1, std::min<int>(nthreads, (int)std::max<int64_t>(1, n / 8)));
     std::atomic<int64_t> next{0};
     std::atomic<bool> abort{false};
-    const uint32_t flags = ctx->opts.plan_flags;
+    const uint32_t flags = ctx->opts.plan_flags | TB_PLAN_TEMPORARY;
     // plan compilation runs on worker threads, in index order; the calling thread uploads and launches batch b
     // while the workers are already compiling batch b+1 (the GPU meanwhile executes batch b-1)
     auto worker = [&]() {
@@ -1241,7 +1241,7 @@ int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_
     std::vector<int> codes((size_t)n, TB_OK);
     std::vector<std::string> errs((size_t)n);
     std::atomic<int64_t> next{0};
-    const uint32_t flags = ctx->opts.plan_flags;
+    const uint32_t flags = ctx->opts.plan_flags | TB_PLAN_TEMPORARY;
     auto worker = [&]() {
         for (;;) {
             const int64_t i = next.fetch_add(1);
@@ -1356,7 +1356,7 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
             n0.fixed_values = values_of(live[0]);
             base.reset(new tb_plan());
             std::string err;
-            rc = compile_plan(n0, ctx->opts.plan_flags, base->p, err);
+            rc = compile_plan(n0, ctx->opts.plan_flags | TB_PLAN_TEMPORARY, base->p, err);
             if (rc) return set_err(ctx, rc, err);
         }
         std::vector<tb_plan*> plans(nl, nullptr);

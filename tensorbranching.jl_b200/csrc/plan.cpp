@@ -130,7 +130,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
 #ifdef TB_PLAN_PROFILE
     auto last_ = std::chrono::steady_clock::now();
 #endif
-    P.flags = net.flags | extra_flags;
+    const bool temporary = (extra_flags & TB_PLAN_TEMPORARY) != 0;
+    extra_flags &= ~TB_PLAN_TEMPORARY;
+    P.flags = (net.flags & ~TB_PLAN_TEMPORARY) | extra_flags;
     if (P.flags & TB_PLAN_KEEP_INTERMEDIATES) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;
     P.n_labels = net.n_labels;
     const bool synth = (net.n_leaves == 1);
@@ -352,37 +354,40 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     //      the walk is depth-first, left operand first; a node adds its result and releases the operands of its
     //      CHILD nodes (its own operands are released one step later, by its parent) -- restated as the reference has it
     double est_all = 0, est_peak = 0;
-    {
+    PT(2, "labelsets")
+    if (!temporary) {
+        // the depth-first order (left operand first) is the order in which the leaf positions lo[] were numbered above:
+        // a node is finished when its last leaf has been seen, so sorting is not needed -- walk the nodes by the stack
+        double p2[33];
+        for (int i = 0; i <= 32; ++i) p2[i] = (double)(1ull << i);
         double cur = 0;
-        for (int i = 0; i < net.n_leaves; ++i) cur += std::ldexp(1.0, lab_n[i]);
+        for (int i = 0; i < net.n_leaves; ++i) cur += p2[lab_n[i]];
         est_peak = cur;
         std::vector<double> freed_later(nT0, 0.0);  // sum of a node's operand sizes
         std::vector<int32_t> stack;
-        std::vector<uint8_t> seen(nT0, 0);
+        stack.reserve(128);
         stack.push_back(root);
         while (!stack.empty()) {
             const int t = stack.back();
-            if (leaf[t]) {
+            if (t < 0) {  // second visit of node ~t: both operands are done
                 stack.pop_back();
-                continue;
-            }
-            if (!seen[t]) {
-                seen[t] = 1;
-                stack.push_back(rch[t]);
-                stack.push_back(lch[t]);
+                const int x = ~t, A = lch[x], B = rch[x];
+                const double alloc = p2[lab_n[x]];
+                cur += alloc - (freed_later[A] + freed_later[B]);
+                freed_later[x] = p2[lab_n[A]] + p2[lab_n[B]];
+                if (cur > est_peak) est_peak = cur;
+                est_all += alloc;
                 continue;
             }
             stack.pop_back();
-            const double freed = freed_later[lch[t]] + freed_later[rch[t]];
-            const double alloc = std::ldexp(1.0, lab_n[t]);
-            freed_later[t] = std::ldexp(1.0, lab_n[lch[t]]) + std::ldexp(1.0, lab_n[rch[t]]);
-            cur += alloc - freed;
-            est_peak = std::max(est_peak, cur);
-            est_all += alloc;
+            if (leaf[t]) continue;
+            stack.push_back(~t);
+            stack.push_back(rch[t]);
+            stack.push_back(lch[t]);
         }
     }
 
-    PT(2, "labelsets")
+    PT(11, "estimators")
     // stamp arrays for O(1) membership
     std::vector<int32_t> stA(NLAB, -1), stB(NLAB, -1), stC(NLAB, -1);
     int stamp = 0;
@@ -905,7 +910,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         bytes += eb * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + cb);
         if (knd == KIND_GEMM) bytes_m += nb_;  // what the kernel itself moves (a partial output included)
     };
-    P.recs.reserve(topo.size());
+    if (!temporary) P.recs.reserve(topo.size());
     P.sub_steps.reserve(topo.size() - n_big);
     P.subtrees.reserve(n_fused_roots);
     P.big_steps.reserve(n_big);
@@ -991,7 +996,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 for (int i = 0; i < rx; ++i) posCc[lx[i]] = NO_BIT;
             }
             P.sub_steps.push_back(s);
-            P.recs.push_back(rec_of(x, KIND_FUSED, 0));
+            if (!temporary) P.recs.push_back(rec_of(x, KIND_FUSED, 0));
             account(x, KIND_FUSED);
             stack.pop_back();
         }
@@ -1174,7 +1179,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 }
             }
             P.big_steps.push_back(s);
-            P.recs.push_back(rec_of(t, kind[t], P.level[t]));
+            if (!temporary) P.recs.push_back(rec_of(t, kind[t], P.level[t]));
             account(t, kind[t]);
         }
         int idx = 0;

@@ -76,6 +76,10 @@ struct Plan {
     size_t sub_blob_off = 0, big_blob_off = 0;
 };
 
+// internal flag (never part of the ABI): the plan is a temporary of tb_contract_networks / tb_stream_push -- nobody will
+// ask for its step records or the reference's memory estimators, so they are not computed
+constexpr uint32_t TB_PLAN_TEMPORARY = 1u << 31;
+
 // returns a tb_status; on failure `err` holds the message
 int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& plan, std::string& err);
 
