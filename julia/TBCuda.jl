@@ -121,15 +121,57 @@ function solve_slice_index_sliced(branch::SlicedBranch, element_type::Type, k::I
                    (Ptr{Cvoid}, Ref{TbNetwork}, Int32, Int32, Ptr{Int32}, Ref{Float64}, Ref{Float64}),
                    C_NULL, Ref(flat.net), -1, k, labels, sc, tc)
         nk >= 0 || error("tb_suggest_slices failed ($nk)")
-        first, count = isnothing(range) ? (0, 1 << nk) : (first(range), length(range))
+        a0, cnt = isnothing(range) ? (0, 1 << nk) : (Base.first(range), length(range))
         mx = Ref{Float64}(0)
         rc = ccall((:tb_contract_sliced, LIB), Cint,
                    (Ptr{Cvoid}, Ref{TbNetwork}, Ptr{Int32}, Int32, Int64, Int64, Float64, Ptr{Float64}, Ptr{Int32}, Ref{Float64}),
-                   ctx(), Ref(flat.net), labels, nk, first, count, 0.0, C_NULL, C_NULL, mx)
+                   ctx(), Ref(flat.net), labels, nk, a0, cnt, 0.0, C_NULL, C_NULL, mx)
         rc == 0 || error("tb_contract_sliced failed ($rc): " *
                          unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
     end
     return element_type(mx[])
+end
+
+# ---- streaming hand-off (tb_stream_*): push the finished slices of every round of slice_bfs / slice_dfs
+#      (src/slice.jl:79-86) while the host keeps slicing; finish returns what contract_slices returns for all of them
+mutable struct BranchStream
+    handle::Ptr{Cvoid}
+    branches::Vector{SlicedBranch}
+end
+
+function stream_begin(capacity::Integer = 1 << 20)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:tb_stream_begin, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Ptr{Cvoid}}), ctx(), capacity, h)
+    rc == 0 || error("tb_stream_begin failed ($rc)")
+    return BranchStream(h[], SlicedBranch[])
+end
+
+function stream_push!(st::BranchStream, branches::Vector{SlicedBranch})
+    isempty(branches) && return st
+    empty_net = TbNetwork(0, 0, C_NULL, C_NULL, 0, C_NULL, C_NULL, C_NULL, C_NULL, 0, 0, 0, 0, C_NULL, C_NULL)
+    flats = [(nv(b.p.g) == 0 || isnothing(b.code)) ? nothing : FlatBranch(b) for b in branches]
+    nets = TbNetwork[isnothing(f) ? empty_net : f.net for f in flats]
+    GC.@preserve flats begin   # the library copies what it needs during the call
+        rc = ccall((:tb_stream_push, LIB), Cint, (Ptr{Cvoid}, Ptr{TbNetwork}, Ptr{Float64}, Int64),
+                   st.handle, nets, C_NULL, length(nets))
+        rc == 0 || error("tb_stream_push failed ($rc): " *
+                         unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
+    end
+    append!(st.branches, branches)
+    return st
+end
+
+function stream_finish!(st::BranchStream, element_type::Type)
+    n = length(st.branches)
+    vals = Vector{Float64}(undef, max(n, 1)); status = Vector{Int32}(undef, max(n, 1))
+    got = Ref{Int64}(0); mx = Ref{Float64}(0)
+    rc = ccall((:tb_stream_finish, LIB), Cint,
+               (Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Int64, Ref{Int64}, Ref{Float64}),
+               st.handle, vals, status, max(n, 1), got, mx)
+    st.handle = C_NULL
+    rc == 0 || error("tb_stream_finish failed ($rc)")
+    return element_type[(nv(b.p.g) == 0 || isnothing(b.code)) ? element_type(b.r) : element_type(vals[i]) + element_type(b.r)
+                        for (i, b) in enumerate(st.branches)]
 end
 
 # method overrides: the usecuda=true switch position
