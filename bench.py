@@ -361,7 +361,10 @@ def main():
 
     def per_branch(unit_vals, idx):
         out = np.full(n_br, -np.inf)
-        np.maximum.at(out, ub[idx], unit_vals)
+        if slice_k <= 0:
+            out[ub[idx]] = unit_vals  # one unit per branch
+        else:
+            np.maximum.at(out, ub[idx], unit_vals)
         return out
 
     def gather_units(vals):
@@ -376,8 +379,10 @@ def main():
             return per_branch(full[0], np.arange(n_units))
         return per_branch(vals, mine)
 
+    my_batch = tbcuda.PlanBatch(my_plans, r_units[mine])  # handle array marshalled once, not once per step
+
     def step_resident():
-        vals, status, _ = eng.contract_plans(my_plans, r_units[mine])
+        vals, status, _ = eng.contract_plans(my_batch)
         return gather_units(vals)
 
     from tbcuda.multi_gpu import slice_range

@@ -207,7 +207,15 @@ class Engine:
         return list(labels[:rank.value]), data
 
     # -- batches -----------------------------------------------------------------------------
-    def contract_plans(self, plans: Sequence[Optional[Plan]], r: Optional[np.ndarray] = None):
+    def contract_plans(self, plans, r: Optional[np.ndarray] = None):
+        """tb_contract_batch over resident plans (None = empty graph).  `plans` may be a PlanBatch: the handle array and
+        the output buffers are then marshalled once and reused by every call (the returned arrays are overwritten by
+        the next call on the same batch)."""
+        if isinstance(plans, PlanBatch):
+            b = plans
+            mx = C.c_double()
+            L.check(self._lib.tb_contract_batch(self.handle, b.arr, b.rp, b.n, b.outp, b.statusp, C.byref(mx)), self.handle)
+            return b.out, b.status, mx.value
         n = len(plans)
         arr = (C.c_void_p * max(n, 1))(*[p.handle if p is not None else None for p in plans])
         out = np.empty(n, dtype=np.float64)
@@ -303,6 +311,21 @@ class Engine:
         p = (C.c_int32 * max(rank, 1))(*perm)
         L.check(self._lib.tb_permute_bits(self.handle, x.ctypes.data, out.ctypes.data, rank, p), self.handle)
         return out
+
+
+class PlanBatch:
+    """A fixed list of resident plans (+ r) marshalled once for repeated Engine.contract_plans calls."""
+
+    def __init__(self, plans: Sequence[Optional[Plan]], r: Optional[np.ndarray] = None):
+        self.plans = list(plans)  # keeps the plans alive
+        self.n = len(self.plans)
+        self.arr = (C.c_void_p * max(self.n, 1))(*[p.handle if p is not None else None for p in self.plans])
+        self.r = None if r is None else np.ascontiguousarray(r, dtype=np.float64)
+        self.rp = None if self.r is None else self.r.ctypes.data_as(C.POINTER(C.c_double))
+        self.out = np.empty(self.n, dtype=np.float64)
+        self.status = np.zeros(self.n, dtype=np.int32)
+        self.outp = self.out.ctypes.data_as(C.POINTER(C.c_double))
+        self.statusp = self.status.ctypes.data_as(C.POINTER(C.c_int32))
 
 
 class BranchStream:
