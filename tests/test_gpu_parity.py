@@ -275,6 +275,11 @@ def test_batch_api_and_max(tb, engine):
     assert np.array_equal(vals, vals2)
     ms, launches = engine.last_timing()
     assert launches > 0 and ms > 0
+    # the same list marshalled once (PlanBatch): identical results on every call
+    batch = tb.PlanBatch(plans, r)
+    for _ in range(3):
+        v3, st3, mx3 = engine.contract_plans(batch)
+        assert np.array_equal(v3, vals) and not st3.any() and mx3 == mx
 
 
 @pytest.mark.parametrize("rank", [0, 1, 3, 7, 12, 20])
