@@ -449,7 +449,7 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        ms_e2e, result_e2e = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+        ms_e2e, result_e2e = timed(step_e2e, max(1, min(args.steps, 5)), 2)
         h2d, d2h = eng.last_transfers()
         hb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
         if world > 1:
