@@ -236,16 +236,19 @@ class Engine:
         # one tb_network record per branch; the records are cached as bytes on the branch objects, so a call only
         # joins them (the pointers inside stay valid as long as the branches are alive)
         key = ("bytes", np.dtype(element_type).name if element_type is not None else None, flags)
-        parts = []
-        for br in branches:
-            try:
-                parts.append(br._net_cache[key])  # hot path: one attribute + one dict lookup per branch
-            except (AttributeError, KeyError):
-                if br.p.nv == 0 or br.code is None:
-                    br.__dict__.setdefault("_net_cache", {})[key] = _EMPTY_NET_BYTES
-                    parts.append(_EMPTY_NET_BYTES)
-                else:
-                    parts.append(_network_bytes(br, element_type, flags))
+        try:  # hot path: every branch already carries its record (one attribute + one dict lookup each)
+            parts = [br._net_cache[key] for br in branches]
+        except (AttributeError, KeyError):
+            parts = []
+            for br in branches:
+                try:
+                    parts.append(br._net_cache[key])
+                except (AttributeError, KeyError):
+                    if br.p.nv == 0 or br.code is None:
+                        br.__dict__.setdefault("_net_cache", {})[key] = _EMPTY_NET_BYTES
+                        parts.append(_EMPTY_NET_BYTES)
+                    else:
+                        parts.append(_network_bytes(br, element_type, flags))
         nets = (L.tb_network * max(n, 1)).from_buffer_copy(b"".join(parts) if n else _EMPTY_NET_BYTES)
         out = np.empty(n, dtype=np.float64)
         status = np.zeros(n, dtype=np.int32)
@@ -425,10 +428,10 @@ def contract_slices(branches: Sequence[SlicedBranch], element_type=np.float32, u
     eng = engine or default_engine()
     vals, status = eng.contract_branches(branches, element_type)
     n = len(branches)
-    r = np.array([br.r for br in branches], dtype=np.float64).astype(element_type)
-    empty = np.array([br.code is None or br.p.nv == 0 for br in branches], dtype=bool)
+    r = np.fromiter((br.r for br in branches), dtype=np.float64, count=n).astype(element_type)
     res = vals.astype(element_type) + r  # element_type arithmetic, as t + element_type(branch.r) in the reference
-    res[empty] = r[empty]
+    # empty graph => element_type(r) (src/dynamic_ob.jl:39-40): the engine contracts nothing and returns 0 for those
+    # entries, so 0 + r is already the answer
     return res
 
 
