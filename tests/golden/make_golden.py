@@ -6,6 +6,7 @@ test/dynamic_ob.jl:20, test/utils.jl:34): each record stores the branch list pro
 stand-in host for a seeded instance, the per-branch values (numpy oracle, following the stored
 trees), and the instance's optimum from an independent exact solver (HiGHS MILP; clique search for
 the small ones).  Run from the repo root:  python tests/golden/make_golden.py
+(`python tests/golden/make_golden.py sliced` regenerates only the index-slicing / open-boundary fixtures.)
 """
 import json
 import os
@@ -45,7 +46,44 @@ def record(name, nv, edges, weights, sc_target, seed, element_type, reduce=True)
     print(name, "branches", len(brs), "exact", exact)
 
 
+def record_sliced_open(name, nv, edges, weights, seed, element_type, k, n_open):
+    """One branch (the unsliced root of the instance) with (a) the values of the 2^k index slices of k labels and (b) the
+    open-boundary root tensor over n_open labels -- both from the numpy oracle, the labels picked without libtbcuda."""
+    root = H.make_root(nv, edges, weights=weights, seed=seed)
+    sc, _ = H.tree_complexity(root.ixs, root.tree)
+    hist = H.big_label_histogram(root.ixs, root.tree, max(0, int(sc) - 4))
+    labels = [l for l, _ in sorted(hist.items(), key=lambda kv: (-kv[1], kv[0]))[:k]]
+    slice_values = [float(O.solve_slice(root, element_type, fixed={l: (a >> i) & 1 for i, l in enumerate(labels)}))
+                    for a in range(1 << k)]
+    whole = float(O.solve_slice(root, element_type))
+    assert max(slice_values) == whole
+    rng = np.random.default_rng(seed)
+    open_labels = sorted(int(v) for v in rng.choice(nv, size=n_open, replace=False))
+    left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+    w = None if weights is None else np.asarray(weights).astype(element_type)
+    t, labs = O.contract_tree(root.ixs, left, right, w, element_type, open_labels=tuple(open_labels))
+    assert float(np.max(t)) == whole
+    rec = dict(name=name, element_type=np.dtype(element_type).name, value=whole,
+               sliced_labels=labels, slice_values=[v if np.isfinite(v) else None for v in slice_values],
+               open_labels=open_labels, open_tensor_labels=[int(l) for l in labs],
+               open_tensor=[float(x) for x in np.asarray(t).reshape(-1)],  # C order over open_tensor_labels
+               branch=dict(nv=root.nv, edges=[list(e) for e in root.edges],
+                           weights=None if root.weights is None else [float(x) for x in root.weights],
+                           weight_dtype=None if root.weights is None else str(np.asarray(root.weights).dtype),
+                           ixs=[list(ix) for ix in root.ixs], tree=lst(root.tree), r=float(root.r)))
+    with open(os.path.join(OUT, name + ".json"), "w") as f:
+        json.dump(rec, f, separators=(",", ":"))
+    print(name, "value", whole, "labels", labels, "open", open_labels)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "sliced":  # only the index-slicing / open-boundary fixtures
+        nv, edges = H.random_regular_graph(60, 3, 5)
+        record_sliced_open("rr60_sliced_open_unit", nv, edges, None, 5, np.float32, 4, 5)
+        rng = np.random.default_rng(9)
+        nv, edges = H.random_regular_graph(40, 3, 9)
+        record_sliced_open("rr40_sliced_open_f32", nv, edges, (1.0 + rng.random(nv)).astype(np.float32), 9, np.float32, 3, 4)
+        sys.exit(0)
     # config 1 of BASELINE.json: README example shape (3-regular n=100, sc_target=10)
     nv, edges = H.random_regular_graph(100, 3, 1)
     record("rr100_sc10_unit", nv, edges, None, 10, 1, np.float32)
