@@ -2,6 +2,8 @@
 private to one operand, very unbalanced shapes), unit / integer / float32 weights, optional index slicing and open
 labels.  The compiled plan, run by the numpy descriptor interpreter, must equal the oracle, and the oracle must equal
 the brute-force MIS (the invariant the reference's tests pin: test/utils.jl:34,37,61, test/decompose.jl:57-85)."""
+import os
+
 import numpy as np
 from hypothesis import HealthCheck, given, settings, strategies as st
 
@@ -13,9 +15,10 @@ from workloads import standin_host as H
 
 @st.composite
 def networks(draw):
-    nv = draw(st.integers(2, 11))
+    big = bool(os.environ.get("TB_HYP_BIG"))  # stress runs: larger, denser graphs
+    nv = draw(st.integers(2, 14 if big else 11))
     pairs = [(u, v) for u in range(nv) for v in range(u + 1, nv)]
-    edges = sorted(draw(st.sets(st.sampled_from(pairs), max_size=min(len(pairs), 2 * nv))))
+    edges = sorted(draw(st.sets(st.sampled_from(pairs), max_size=min(len(pairs), (3 if big else 2) * nv))))
     kind = draw(st.sampled_from(["unit", "int", "f32"]))
     if kind == "unit":
         w = None
@@ -42,7 +45,7 @@ def networks(draw):
     return nv, edges, w, ixs, tree, flags
 
 
-SETTINGS = dict(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+SETTINGS = dict(max_examples=int(os.environ.get("TB_HYP_EXAMPLES", "150")), derandomize=not os.environ.get("TB_HYP_RANDOM"), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
 
 
 @settings(**SETTINGS)
