@@ -102,3 +102,51 @@ def test_random_tree_open_labels(tb, net, data):
     t, labs = O.contract_tree(ixs, left, right, wv, et, open_labels=tuple(open_labels))
     assert sorted(dl) == open_labels
     assert np.array_equal(align_to(dl, darr, list(labs)).astype(et), np.asarray(t))
+
+
+def _random_network(rng, nv_max=12):
+    """numpy-seeded twin of the hypothesis strategy above (for the GPU batch test)."""
+    nv = int(rng.integers(2, nv_max + 1))
+    pairs = [(u, v) for u in range(nv) for v in range(u + 1, nv)]
+    m = int(rng.integers(0, min(len(pairs), 2 * nv) + 1))
+    edges = sorted(pairs[i] for i in rng.choice(len(pairs), size=m, replace=False)) if m else []
+    kind = ("unit", "int", "f32")[int(rng.integers(0, 3))]
+    w = None if kind == "unit" else (rng.integers(0, 10, size=nv).astype(np.int64) if kind == "int"
+                                     else (0.5 + 3.5 * rng.random(nv)).astype(np.float32))
+    ixs = H.mis_ixs(nv, edges)
+    pool = [int(i) for i in rng.permutation(len(ixs))]
+    while len(pool) > 1:
+        a = pool.pop(int(rng.integers(0, len(pool))))
+        b = pool.pop(int(rng.integers(0, len(pool))))
+        pool.append((a, b))
+    return H.Branch(nv, edges, w, ixs, pool[0], float(rng.integers(0, 5)))
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_gpu_random_trees_batch(tb, engine, seed):
+    """300 random networks with random (not greedy) trees and mixed weight kinds in ONE contract_slices call per
+    element type: every value equals the oracle's, which equals the brute-force optimum."""
+    rng = np.random.default_rng(seed)
+    nets = [_random_network(rng) for _ in range(300)]
+    for et, sel in ((np.float64, [b for b in nets if b.weights is None or b.weights.dtype != np.float32]),
+                    (np.float32, [b for b in nets if b.weights is not None and b.weights.dtype == np.float32])):
+        got = tb.contract_slices([to_sliced(b) for b in sel], np.float32 if et is np.float32 else np.float64, True, engine=engine)
+        want = np.array([et(O.solve_slice(b, et) + et(b.r)) for b in sel])
+        assert np.array_equal(got.astype(et), want)
+        if et is np.float64:
+            exact = np.array([O.exact_mis_bruteforce(b.nv, b.edges, b.weights) + b.r for b in sel])
+            assert np.array_equal(want, exact)
+    # index slices and open boundaries of a few of them
+    for b in nets[:25]:
+        if b.nv < 4:
+            continue
+        br = to_sliced(b)
+        labels = [int(x) for x in rng.permutation(b.nv)[:2]]
+        et = np.float32 if (b.weights is not None and b.weights.dtype == np.float32) else np.float64
+        vals, status, mx = engine.contract_index_sliced(br, labels, element_type=np.float32)
+        want = np.array([O.solve_slice(b, et, fixed={l: (a >> i) & 1 for i, l in enumerate(labels)}) for a in range(4)])
+        assert np.array_equal(vals.astype(et), want.astype(et))
