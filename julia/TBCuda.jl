@@ -174,12 +174,17 @@ function stream_finish!(st::BranchStream, element_type::Type)
                         for (i, b) in enumerate(st.branches)]
 end
 
-# method overrides: the usecuda=true switch position
-function TensorBranching.contract_slices(branches::Vector{SlicedBranch}, element_type::Type, usecuda::Bool)
+# The usecuda=true switch position.  The reference defines
+#     contract_slices(::Vector{SlicedBranch}, ::Type, ::Bool)   and   solve_slice(::SlicedBranch, ::Type, ::Bool)
+# (src/dynamic_ob.jl:30,36).  Re-defining exactly those signatures from here would OVERWRITE them (and `invoke` would then
+# recurse), so these methods are strictly more specific in the element type -- `Type{T} where T<:AbstractFloat` wins the
+# dispatch for Float32 / Float64 -- and the usecuda=false branch reaches the reference's own method through `invoke` with
+# the original, less specific signature.  (A maintainer would rather add the two-line hook shown in INTEGRATION.md.)
+function TensorBranching.contract_slices(branches::Vector{SlicedBranch}, element_type::Type{T}, usecuda::Bool) where {T <: AbstractFloat}
     usecuda && return contract_slices_cuda(branches, element_type)
     return invoke(TensorBranching.contract_slices, Tuple{Vector{SlicedBranch}, Type, Bool}, branches, element_type, false)
 end
-function TensorBranching.solve_slice(branch::SlicedBranch, element_type::Type, usecuda::Bool)
+function TensorBranching.solve_slice(branch::SlicedBranch, element_type::Type{T}, usecuda::Bool) where {T <: AbstractFloat}
     usecuda || return invoke(TensorBranching.solve_slice, Tuple{SlicedBranch, Type, Bool}, branch, element_type, false)
     return contract_slices_cuda(SlicedBranch[TensorBranching.SlicedBranch(branch.p, branch.code, zero(branch.r))], element_type)[1]
 end
