@@ -165,3 +165,49 @@ def test_gpu_full_size_branch_over_40_labels(tb, engine):
     live = [a for a in range(1 << 10) if vals[a] > -np.inf][:16]
     cpu, _, _ = CO.contract_index_slices(b, labels, live)
     assert np.array_equal(cpu, vals[live])
+
+
+def test_suggest_slices_edge_cases(tb):
+    import ctypes as C
+    from tbcuda import _lib as L
+    from tbcuda.contract import _network_of
+    lib = tb.load()
+    root = regular_root(30, 3)
+    br = to_sliced(root)
+    # zero labels asked for: nothing picked, complexity of the unsliced tree reported
+    labels, sc, tc = tb.suggest_slices(br, -1, 0)
+    assert labels == [] and sc == tb.sc(br) and tc == pytest.approx(tb.tc(br))
+    # open labels are never sliced
+    open_labels = [0, 1, 2, 3]
+    bo = tb.SlicedBranch(tb.MISProblem(root.nv, root.edges, None), tb.CompressedEinsum(root.ixs, open_labels, root.tree), 0)
+    labels, _, _ = tb.suggest_slices(bo, -1, 6)
+    assert not set(labels) & set(open_labels)
+    # a label cannot be both open and fixed
+    with pytest.raises(tb.TBError) as e:
+        tb.Plan(bo, fixed={0: 1})
+    assert e.value.code == -1
+    # a network that already carries fixed labels is refused; a broken tree gets the tree error code
+    net, _ = _network_of(br, np.float32, 0)
+    bad = L.tb_network.from_buffer_copy(bytes(net))
+    fl = np.asarray([0], dtype=np.int32)
+    fv = np.asarray([0], dtype=np.uint8)
+    bad.n_fixed, bad.fixed_labels, bad.fixed_values = 1, fl.ctypes.data_as(C.POINTER(C.c_int32)), fv.ctypes.data_as(C.POINTER(C.c_uint8))
+    out = (C.c_int32 * 4)()
+    assert lib.tb_suggest_slices(None, C.byref(bad), -1, 2, out, None, None) == -1
+    left = br.code.node_left.copy()
+    left[-1] = left[-2]  # a tensor used twice
+    broken = L.tb_network.from_buffer_copy(bytes(net))
+    broken.node_left = left.ctypes.data_as(C.POINTER(C.c_int32))
+    assert lib.tb_suggest_slices(None, C.byref(broken), -1, 2, out, None, None) == -2
+    assert lib.tb_suggest_slices(None, None, -1, 2, out, None, None) == -1
+
+
+def test_sliced_leaves_get_private_pool_slots(tb):
+    """the descriptors of a sliced plan do not depend on the assignment: only the leaf-pool section does"""
+    root = regular_root(40, 9)
+    br = to_sliced(root)
+    labels, _, _ = tb.suggest_slices(br, -1, 3)
+    plans = [tb.Plan(br, fixed={l: (a >> i) & 1 for i, l in enumerate(labels)}) for a in range(8)]
+    for which in (1, 2, 3, 4, 5):
+        assert len({p.raw(which) for p in plans}) == 1
+    assert len({p.raw(0) for p in plans}) > 1
