@@ -257,6 +257,14 @@ def main():
     config = {"workload": f"{args.workload}: {wl_kind} {wl_p}, sc_target={sc_target}, unit weights, stand-in host branching" +
                           (f", first {wl_mb} finished branches of the depth-first slicer" if wl_mb else ""),
               "l2": "per-step working set (arena + descriptors) exceeds the 126 MB L2; no explicit flush"}
+    # the same config on both arms (the reference arm times the same workload on the host cores)
+    slice_k = args.slice_k if args.slice_k is not None else DEFAULT_SLICE_K.get(args.workload, 0)
+    if slice_k > 0:
+        config["index_slicing"] = f"every branch cut into 2^{slice_k} index slices (tb_suggest_slices); infeasible assignments are not units"
+    config["sharding"] = ("weak scaling: every rank contracts its own copy of the unit list, no data-path collective, one "
+                          "all-reduce(max) over the result vector" if args.scaling == "weak" else
+                          "strong scaling: ONE unit list dealt to the ranks longest-first by tb_plan_info.ops, no data-path "
+                          "collective, one all-reduce(max) over the result vector")
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -316,7 +324,6 @@ def main():
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # units of work: one per branch, or (index slicing) one per feasible assignment of the k sliced labels of a branch
-    slice_k = args.slice_k if args.slice_k is not None else DEFAULT_SLICE_K.get(args.workload, 0)
     units = []  # (branch index, {label: value} or None)
     slice_labels = {}
     for i, s in enumerate(sliced):
@@ -328,8 +335,6 @@ def main():
             units.append((i, {l: (a >> q) & 1 for q, l in enumerate(slice_labels[i])}))
     n_units = len(units)
     ub = np.array([u[0] for u in units], dtype=np.int64)
-    if slice_k > 0:
-        config["index_slicing"] = f"every branch cut into 2^{slice_k} index slices (tb_suggest_slices), {n_units} units"
 
     # plans for every unit (host-only compile) to get costs; then keep only this rank's shard
     t0 = time.perf_counter()
@@ -343,10 +348,6 @@ def main():
     copies = world if weak else 1  # weak: the job holds one copy of the unit list per rank
     owner = np.full(n_units, rank, dtype=np.int64) if weak else lpt_shards(ops, world)
     mine = np.nonzero(owner == rank)[0]
-    config["sharding"] = (f"weak scaling: every rank contracts its own copy of the unit list ({copies} x {n_units} units), "
-                          "no data-path collective, one all-reduce(max) over the result vector" if weak else
-                          f"strong scaling: {n_units} units dealt to {world} rank(s) longest-first by tb_plan_info.ops, "
-                          "no data-path collective, one all-reduce(max) over the result vector")
     my_plans = [all_plans[i] for i in mine]
     my_sliced = [sliced[ub[i]] for i in mine]
     for i in np.nonzero(owner != rank)[0]:
