@@ -125,3 +125,58 @@ def test_bench_tbcuda_arm_dry_run(monkeypatch, argv):
     if "--no-cpu-baseline" not in argv:
         assert set(line["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and line["cpu_baseline"]["agrees_with_gpu"]
     assert line["mis"] == 45.0  # cfg1: exact MIS of the seeded n=100 instance, through the oracle stand-in
+
+
+def _world2_worker(rank, world, port, out_dir, scaling):
+    """one rank of a 2-rank dry run: the same stand-ins, the process group on gloo instead of nccl"""
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import bench
+    import tbcuda
+
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device = lambda d: None
+    torch.cuda.synchronize = lambda *a: None
+    torch.cuda.current_stream = lambda *a: type("S", (), {"cuda_stream": 0})()
+    torch.cuda.Event = _FakeEvent
+    real_full, real_tensor = torch.full, torch.tensor
+    torch.full = lambda *a, **k: real_full(*a, **{q: v for q, v in k.items() if q != "device"})
+    torch.tensor = lambda *a, **k: real_tensor(*a, **{q: v for q, v in k.items() if q != "device"})
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    real_init = dist.init_process_group
+    dist.init_process_group = lambda backend, **k: real_init("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    tbcuda.Engine = _FakeEngine
+    bench.dpx_peak = lambda: {"viaddmax_s16x2_Gops": 35000.0, "viaddmax_s32_Gops": 18000.0}
+
+    def fake_contract_slices(branches, element_type=np.float32, usecuda=True, engine=None):
+        eng = _FakeEngine()
+        return np.array([(eng._value(tbcuda.Plan(b)) if b.code is not None else 0.0) + b.r for b in branches]).astype(element_type)
+
+    tbcuda.contract_slices = fake_contract_slices
+    sys.argv = ["bench.py", "--gpus", str(world), "--workload", "cfg1", "--steps", "2", "--warmup", "1", "--scaling", scaling,
+                "--no-cpu-baseline"]
+    buf = io.StringIO()
+    with redirect_stdout(buf):
+        bench.main()
+    if rank == 0:
+        with open(os.path.join(out_dir, "line.json"), "w") as f:
+            f.write(buf.getvalue().strip().splitlines()[-1])
+
+
+@pytest.mark.parametrize("scaling", ["weak", "strong"])
+def test_bench_two_rank_dry_run(tmp_path, scaling):
+    import socket
+
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mp.spawn(_world2_worker, args=(2, port, str(tmp_path), scaling), nprocs=2, join=True)
+    line = json.loads(open(tmp_path / "line.json").read())
+    assert line["n_gpus"] == 2 and line["scaling"] == scaling and line["mis"] == 45.0
+    assert line["units"] == (92 if scaling == "weak" else 46) and line["branches"] == line["units"]
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
