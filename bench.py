@@ -443,10 +443,10 @@ def main():
     dev_ms_last = eng.last_timing()[0]
 
     # per-kernel-kind timing (profiling mode adds events; separate pass, not the bench value)
-    eng.profile(True)
+    eng.profile(2)
     step_resident()
     prof = eng.last_profile()
-    eng.profile(False)
+    eng.profile(0)
 
     e2e = None
     if not args.no_e2e:

@@ -75,14 +75,22 @@ typedef enum tb_weight_dtype {
                                          results, 2x DPX rate, half the bytes */
 #define TB_PLAN_NO_I16 64u            /* value_type AUTO never picks packed int16 (int32 for integer weights) */
 
+/* The hot path's only knobs in the reference are element_type and usecuda (src/dynamic_ob.jl:6,30,36); everything
+ * else an engine needs is here ("Config / flags"): no environment-variable magic is required. */
 typedef struct tb_options {
-    int32_t device;          /* CUDA device ordinal */
-    int32_t reserved0;
-    int64_t arena_bytes;     /* HBM arena for intermediates; 0 = 60 % of free memory at first use */
-    int32_t max_wave;        /* max branches contracted concurrently (0 = default 256) */
-    int32_t host_threads;    /* plan-compiler threads for the *_networks calls (0 = all cores) */
+    int32_t device;          /* CUDA device ordinal (single-device context) */
+    int32_t n_devices;       /* 0 / 1: one device (`device`); > 1: tb_init returns a multi-GPU context over devices[0 .. n_devices)
+                                (exactly tb_init_multi) */
+    int64_t arena_bytes;     /* HBM arena for intermediates, per device; 0 = 60 % of free memory at first use */
+    int32_t max_wave;        /* max branches contracted concurrently in one wave (0 = by plan weight: 128 / 256) */
+    int32_t host_threads;    /* plan-compiler threads for the *_networks calls, all devices together (0 = all cores) */
     uint32_t plan_flags;     /* default flags OR-ed into every plan */
-    int32_t reserved1;
+    int32_t streams_per_device; /* stream lanes = waves in flight per GPU, 1 .. 8 (0 = default 4) */
+    const int32_t* devices;  /* n_devices > 1: the device ordinals (NULL = 0 .. n_devices-1); read during tb_init only */
+    int32_t slice_budget;    /* index-slicing budget of a multi-GPU context: when a call has fewer branches than 2 x devices,
+                                every branch is cut into up to 2^slice_budget index slices (tb_suggest_slices picks the labels)
+                                so that all devices get work; 0 = never slice on the engine's own initiative */
+    int32_t timing;          /* tb_profile mode from the start: 0 off, 1 per-launch events (lanes concurrent), 2 single lane */
 } tb_options;
 
 /*
@@ -161,6 +169,26 @@ const char* tb_version(void);
 /* lifetime of the engine on one device.  Fails with TB_ERR_CUDA when no device is usable. */
 int tb_init(const tb_options* opts, tb_ctx** out_ctx);
 int tb_shutdown(tb_ctx* ctx);
+
+/* Multi-GPU engine in ONE process (no Distributed.jl / MPI needed on the host side): one sub-context per
+ * device, each with its own arena, stream lanes and share of the plan-compiler threads.  On such a context
+ *   tb_contract_networks / tb_contract_batch  deal the branches to the devices longest-first (LPT) by their tropical
+ *       ops (for resident plans: a plan stays on the device it first ran on), every device contracts its share, and ONE
+ *       ncclAllReduce(ncclMax) over the per-branch result vector -- pre-filled with -inf on every device -- replaces
+ *       maximum(res) (src/dynamic_ob.jl:27); no tensor crosses NVLink;
+ *   tb_contract_sliced  deals the 2^k assignments of one heavy branch in contiguous ranges;
+ *   tb_contract / tb_contract_tensor / tb_plan_read_tensor / tb_stream_*  run on the first device.
+ * devices == NULL means 0 .. n_devices-1.  NCCL (libnccl.so.2) is loaded with dlopen here: TB_ERR_NCCL if it is missing
+ * or a NCCL call fails; a single-device context never needs it.  A device may be listed more than once (exercising
+ * the sharding on a single-GPU box): NCCL cannot form such a communicator, so the per-device vectors are then combined
+ * on the host instead -- a testing configuration, not a product path.  opts->device / n_devices / devices are ignored. */
+int tb_init_multi(const int32_t* devices, int32_t n_devices, const tb_options* opts, tb_ctx** out_ctx);
+/* number of devices of a context (1 for tb_init contexts) */
+int tb_device_count(const tb_ctx* ctx);
+
+/* the cost a sharder needs, without compiling: tropical ops (the reference's 2^tc, src/types.jl:120) and sc (:121) from
+ * the label-set pass alone, ~4x cheaper than tb_plan_create.  Host-only.  out_sc may be NULL. */
+int tb_estimate(const tb_network* net, double* out_ops, double* out_sc);
 const char* tb_last_error(const tb_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 
 /* replaces uncompress(branch.code) + GenericTensorNetwork(...) (src/dynamic_ob.jl:31, src/types.jl:75-79):
@@ -253,10 +281,16 @@ int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launch
  * that the caller's events bracket the engine's work.  The stream is not destroyed by tb_shutdown. */
 int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
 
-/* opt-in per-launch CUDA-event timing, accumulated by kernel kind
- * (0 fused subtrees, 1 generic, 2 tiled max-plus GEMM, 3 finalize) over the last contract call. */
-int tb_profile(tb_ctx* ctx, int enable);
+/* opt-in per-launch CUDA-event timing, accumulated by kernel kind over the last contract call:
+ * 0 fused subtrees, 1 generic (level-synchronous launches only), 2 the persistent max-plus GEMM kernel (in the default
+ * dataflow executor this ONE launch per wave also runs the wave's generic steps on its consumer warps), 3 finalize.
+ * mode 0 = off; 1 = events around every launch on its own stream lane, lanes stay concurrent (the timed configuration);
+ * 2 = the same on a single lane (launches serialised: per-launch durations free of overlap).
+ * tb_last_profile: per kind the SUM of the launch durations; tb_last_profile_union: per kind the length of the union
+ * of the launches' [start, end] intervals, i.e. how long that kind was on the device (equal to the sum in mode 2). */
+int tb_profile(tb_ctx* ctx, int mode);
 int tb_last_profile(const tb_ctx* ctx, double* ms_by_kind /*[4]*/, int64_t* launches_by_kind /*[4]*/);
+int tb_last_profile_union(const tb_ctx* ctx, double* ms_by_kind /*[4]*/);
 
 /* host wall-clock breakdown (ms) of the last tb_contract_networks call:
  * [0] plan compilation, [1] descriptor upload, [2] work-list build, [3] launch + wait, [4] plan teardown, [5] total */

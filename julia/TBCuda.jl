@@ -17,8 +17,9 @@ const LIB = get(ENV, "LIBTBCUDA", "libtbcuda.so")
 
 # mirrors `struct tb_options` / `struct tb_network` of include/tbcuda.h
 struct TbOptions
-    device::Int32; reserved0::Int32; arena_bytes::Int64
-    max_wave::Int32; host_threads::Int32; plan_flags::UInt32; reserved1::Int32
+    device::Int32; n_devices::Int32; arena_bytes::Int64
+    max_wave::Int32; host_threads::Int32; plan_flags::UInt32; streams_per_device::Int32
+    devices::Ptr{Int32}; slice_budget::Int32; timing::Int32
 end
 struct TbNetwork
     n_labels::Int32; n_leaves::Int32
@@ -32,11 +33,17 @@ end
 
 const CTX = Ref{Ptr{Cvoid}}(C_NULL)
 
-function ctx(device::Integer = 0)
+# One engine per Julia process.  `devices` = the GPUs to use: with more than one, libtbcuda shards every
+# contract_slices call over them itself (LPT by tropical ops) and combines with ONE ncclAllReduce(max) -- no
+# Distributed.jl needed (tb_init_multi).  `slice_budget` > 0 lets it cut a call with fewer branches than 2 x GPUs into
+# 2^k index slices.  Set TBCUDA_DEVICES="0,1,2,3,4,5,6,7" to pick the devices without touching code.
+function ctx(devices::AbstractVector{<:Integer} = parse.(Int, split(get(ENV, "TBCUDA_DEVICES", "0"), ",")); slice_budget::Integer = 6)
     if CTX[] == C_NULL
-        opts = Ref(TbOptions(device, 0, 0, 0, 0, 0, 0))
-        rc = ccall((:tb_init, LIB), Cint, (Ref{TbOptions}, Ref{Ptr{Cvoid}}), opts, CTX)
-        rc == 0 || error("tb_init failed ($rc): " * unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        devs = Int32.(devices)
+        opts = Ref(TbOptions(devs[1], 0, 0, 0, 0, 0, 0, C_NULL, slice_budget, 0))
+        rc = GC.@preserve devs ccall((:tb_init_multi, LIB), Cint, (Ptr{Int32}, Int32, Ref{TbOptions}, Ref{Ptr{Cvoid}}),
+                                     devs, length(devs), opts, CTX)
+        rc == 0 || error("tb_init_multi failed ($rc): " * unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
         atexit(() -> ccall((:tb_shutdown, LIB), Cint, (Ptr{Cvoid},), CTX[]))
     end
     return CTX[]

@@ -42,8 +42,20 @@ def flatten(branch):
     return (branch.nv, off, labs, np.asarray(left, dtype=np.int32), np.asarray(right, dtype=np.int32), w)
 
 
-def contract_batch(flat_list):
-    """flat_list: list of flatten() tuples (None for an empty graph).  -> (values float64, ops float64, threads)."""
+VALUE_TYPES = {"f32": 0, "i16": 1, "auto": 2}
+
+
+def simd() -> str:
+    """ISA the micro-kernels dispatch to on this host ("avx512" / "avx2" / "scalar")."""
+    lib = load()
+    lib.tref_simd.restype = C.c_char_p
+    return lib.tref_simd().decode()
+
+
+def contract_batch(flat_list, value_type="f32"):
+    """flat_list: list of flatten() tuples (None for an empty graph).  -> (values float64, ops float64, threads).
+    value_type: "f32" = Tropical{Float32} (the reference's default element_type); "i16" = int16 with a -2^14 sentinel
+    (caller guarantees integer weights with sum |w| < 8192); "auto" = i16 where that holds, else f32."""
     lib = load()
     n = len(flat_list)
     ip = C.POINTER(C.c_int32)
@@ -78,20 +90,21 @@ def contract_batch(flat_list):
             a_w[i] = w.ctypes.data_as(dp)
     vals = np.zeros(n, dtype=np.float64)
     ops = np.zeros(n, dtype=np.float64)
-    th = lib.tref_contract_batch(n, nv, nl, a_off, a_lab, a_l, a_r, a_w if any_w else None,
-                                 vals.ctypes.data_as(dp), ops.ctypes.data_as(dp))
+    lib.tref_contract_batch_vt.restype = C.c_int
+    th = lib.tref_contract_batch_vt(n, nv, nl, a_off, a_lab, a_l, a_r, a_w if any_w else None, VALUE_TYPES[value_type],
+                                    vals.ctypes.data_as(dp), ops.ctypes.data_as(dp))
     return vals, ops, th
 
 
-def contract_slices(branches, element_type=np.float32):
+def contract_slices(branches, element_type=np.float32, value_type="f32"):
     """contract_slices (/root/reference/src/dynamic_ob.jl:36-48) on the C oracle."""
     flats = [None if b.nv == 0 else flatten(b) for b in branches]
-    vals, _, _ = contract_batch(flats)
+    vals, _, _ = contract_batch(flats, value_type)
     et = np.dtype(element_type).type
     return np.asarray([et(b.r) if b.nv == 0 else et(et(v) + et(b.r)) for b, v in zip(branches, vals)], dtype=element_type)
 
 
-def contract_index_slices(branch, sliced_labels, assignments):
+def contract_index_slices(branch, sliced_labels, assignments, value_type="f32"):
     """Index slices of ONE branch on the C oracle, one slice per OpenMP thread: assignment a holds
     sliced_labels[i] at bit i of a.  -> (values float64 WITHOUT r, ops float64, threads)."""
     lib = load()
@@ -109,10 +122,10 @@ def contract_index_slices(branch, sliced_labels, assignments):
     ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
     vals = np.zeros(n, dtype=np.float64)
     ops = np.zeros(n, dtype=np.float64)
-    lib.tref_contract_slices_of.restype = C.c_int
-    th = lib.tref_contract_slices_of(n, nlab, len(off) - 1, off.ctypes.data_as(ip), labs.ctypes.data_as(ip),
-                                     left.ctypes.data_as(ip), right.ctypes.data_as(ip),
-                                     w.ctypes.data_as(dp) if w is not None else None,
-                                     fixed.ctypes.data_as(C.POINTER(C.c_int8)), vals.ctypes.data_as(dp),
-                                     ops.ctypes.data_as(dp))
+    lib.tref_contract_slices_of_vt.restype = C.c_int
+    th = lib.tref_contract_slices_of_vt(n, nlab, len(off) - 1, off.ctypes.data_as(ip), labs.ctypes.data_as(ip),
+                                        left.ctypes.data_as(ip), right.ctypes.data_as(ip),
+                                        w.ctypes.data_as(dp) if w is not None else None,
+                                        fixed.ctypes.data_as(C.POINTER(C.c_int8)), VALUE_TYPES[value_type],
+                                        vals.ctypes.data_as(dp), ops.ctypes.data_as(dp))
     return vals, ops, th

@@ -28,9 +28,10 @@ TB_PLAN_NO_I16 = 64
 
 
 class tb_options(C.Structure):
-    _fields_ = [("device", C.c_int32), ("reserved0", C.c_int32), ("arena_bytes", C.c_int64),
+    _fields_ = [("device", C.c_int32), ("n_devices", C.c_int32), ("arena_bytes", C.c_int64),
                 ("max_wave", C.c_int32), ("host_threads", C.c_int32), ("plan_flags", C.c_uint32),
-                ("reserved1", C.c_int32)]
+                ("streams_per_device", C.c_int32), ("devices", C.POINTER(C.c_int32)), ("slice_budget", C.c_int32),
+                ("timing", C.c_int32)]
 
 
 class tb_network(C.Structure):
@@ -62,10 +63,10 @@ class tb_step_info(C.Structure):
 
 
 # every symbol include/tbcuda.h declares
-EXPORTS = ["tb_version", "tb_init", "tb_shutdown", "tb_last_error", "tb_plan_create", "tb_plan_destroy",
+EXPORTS = ["tb_version", "tb_init", "tb_init_multi", "tb_device_count", "tb_estimate", "tb_shutdown", "tb_last_error", "tb_plan_create", "tb_plan_destroy",
            "tb_plan_info", "tb_plan_export", "tb_plan_export_raw", "tb_contract", "tb_contract_batch",
            "tb_contract_networks", "tb_contract_sliced", "tb_suggest_slices", "tb_stream_begin", "tb_stream_push", "tb_stream_finish", "tb_contract_tensor", "tb_plan_reassign", "tb_plan_read_tensor", "tb_last_timing", "tb_permute_bits", "tb_set_stream", "tb_profile",
-           "tb_last_profile", "tb_last_transfers", "tb_last_host_breakdown"]
+           "tb_last_profile", "tb_last_profile_union", "tb_last_transfers", "tb_last_host_breakdown"]
 
 _lib = None
 
@@ -90,6 +91,9 @@ def load():
     lib.tb_last_error.restype = C.c_char_p
     lib.tb_last_error.argtypes = [vp]
     lib.tb_init.argtypes = [C.POINTER(tb_options), C.POINTER(vp)]
+    lib.tb_init_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(tb_options), C.POINTER(vp)]
+    lib.tb_device_count.argtypes = [vp]
+    lib.tb_estimate.argtypes = [C.POINTER(tb_network), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.tb_shutdown.argtypes = [vp]
     lib.tb_plan_create.argtypes = [vp, C.POINTER(tb_network), C.POINTER(vp)]
     lib.tb_plan_destroy.argtypes = [vp]
@@ -118,6 +122,7 @@ def load():
     lib.tb_set_stream.argtypes = [vp, vp]
     lib.tb_profile.argtypes = [vp, C.c_int]
     lib.tb_last_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.tb_last_profile_union.argtypes = [vp, C.POINTER(C.c_double)]
     lib.tb_last_host_breakdown.argtypes = [vp, C.POINTER(C.c_double)]
     lib.tb_last_transfers.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.tb_permute_bits.argtypes = [vp, vp, vp, C.c_int32, C.POINTER(C.c_int32)]

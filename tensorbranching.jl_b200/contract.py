@@ -159,14 +159,24 @@ class Engine:
     """tb_ctx: one engine per CUDA device."""
 
     def __init__(self, device: int = 0, arena_bytes: int = 0, max_wave: int = 0, host_threads: int = 0,
-                 plan_flags: int = 0):
+                 plan_flags: int = 0, devices: Optional[Sequence[int]] = None, streams_per_device: int = 0,
+                 slice_budget: int = 0, timing: int = 0):
+        """devices=[...]: a multi-GPU engine in this process (tb_init_multi): contract_slices / contract_plans shard the
+        branches over the devices and combine with one ncclAllReduce(max) inside the library."""
         lib = L.load()
         self._lib = lib
         opts = L.tb_options(device=device, arena_bytes=arena_bytes, max_wave=max_wave,
-                            host_threads=host_threads, plan_flags=plan_flags)
+                            host_threads=host_threads, plan_flags=plan_flags, streams_per_device=streams_per_device,
+                            slice_budget=slice_budget, timing=timing)
         self.handle = C.c_void_p()
-        L.check(lib.tb_init(C.byref(opts), C.byref(self.handle)))
+        if devices is not None:
+            devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            L.check(lib.tb_init_multi(devs, len(devices), C.byref(opts), C.byref(self.handle)))
+            device = int(devices[0])
+        else:
+            L.check(lib.tb_init(C.byref(opts), C.byref(self.handle)))
         self.device = device
+        self.n_devices = lib.tb_device_count(self.handle)
 
     def close(self):
         if self.handle:
@@ -283,8 +293,15 @@ class Engine:
     def set_stream(self, cuda_stream_handle: int):
         L.check(self._lib.tb_set_stream(self.handle, C.c_void_p(cuda_stream_handle)), self.handle)
 
-    def profile(self, enable: bool = True):
-        L.check(self._lib.tb_profile(self.handle, int(enable)), self.handle)
+    def profile(self, mode=1):
+        """tb_profile: 0 off, 1 per-launch events with the lanes concurrent, 2 single lane (launches serialised)."""
+        L.check(self._lib.tb_profile(self.handle, int(mode)), self.handle)
+
+    def last_profile_union(self):
+        """per kind: how long that kind of kernel was on the device in the last call (union of its launches' intervals)."""
+        ms = (C.c_double * 4)()
+        L.check(self._lib.tb_last_profile_union(self.handle, ms))
+        return dict(zip(("fused", "generic", "gemm", "finalize"), ms))
 
     def last_profile(self):
         ms = (C.c_double * 4)()
@@ -433,6 +450,18 @@ def contract_slices(branches: Sequence[SlicedBranch], element_type=np.float32, u
     # empty graph => element_type(r) (src/dynamic_ob.jl:39-40): the engine contracts nothing and returns 0 for those
     # entries, so 0 + r is already the answer
     return res
+
+
+def estimate(branch: SlicedBranch):
+    """tb_estimate: (tropical ops, sc) of a branch from the label-set pass alone -- the cost a sharder needs."""
+    if branch.code is None or branch.p.nv == 0:
+        return 0.0, 0.0
+    lib = L.load()
+    net, _ = _network_of(branch, np.float32, 0)
+    ops = C.c_double()
+    sc_ = C.c_double()
+    L.check(lib.tb_estimate(C.byref(net), C.byref(ops), C.byref(sc_)))
+    return ops.value, sc_.value
 
 
 def suggest_slices(branch: SlicedBranch, sc_target: int = -1, max_sliced: int = 8):

@@ -95,8 +95,13 @@ struct BigInst {           // one non-fused step of one branch
     const void* pool;
     void* arena;
     uint32_t tile_start;   // exclusive prefix sum of n_tiles over the launch
+    // dataflow launches (all levels of a wave in one persistent kernel): index, in this launch's instance array, of
+    // the instance that produces operand A / B, or -1 when the operand is ready before the launch starts (leaf pool,
+    // fused subtree, earlier launch).  Instance i is complete when the launch's done[i] counter has reached 0.
+    int32_t dep_a, dep_b;
     uint32_t pad;
 };
+static_assert(sizeof(BigInst) == 40, "BigInst layout");
 
 template <typename T> struct Tropical;
 template <> struct Tropical<int32_t> {

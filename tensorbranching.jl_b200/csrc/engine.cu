@@ -9,6 +9,7 @@
 //   * root scalars are gathered by k_finalize into one result vector, copied back once.
 // There is no CPU fallback: without a CUDA device tb_init fails with TB_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <atomic>
@@ -19,6 +20,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -43,6 +45,13 @@ struct BlobChunk {
 }  // namespace
 
 struct tb_ctx {
+    // ---- multi-GPU context (tb_init_multi): one sub-context per device, this object only coordinates
+    std::vector<tb_ctx*> subs;
+    std::vector<void*> comms;          // ncclComm_t per sub-context (empty: single device, or host combine)
+    bool host_combine = false;         // the device list repeats a device (testing on a single-GPU box): no NCCL possible
+    tb_ctx* parent = nullptr;          // sub-context: the multi context that owns it
+    const int64_t* index_map = nullptr;  // sub-context inside a multi call: local branch index -> index in the call's result vector
+    bool prefill_results = false;        // sub-context inside a multi call: the result vector starts as -inf (input of the max-reduce)
     Plan* resident = nullptr;  // head of the intrusive list of plans whose descriptors live on this context
     bool stream_open = false;  // a tb_stream owns the context between tb_stream_begin and tb_stream_finish
     int call_wave = 0;  // wave size of the current call (a small call is cut into more, smaller waves: all lanes busy)
@@ -88,7 +97,16 @@ struct tb_ctx {
     int waves_per_lane = 0;                // waves per lane a small call is cut into; 0 = by plan weight (TB_WAVES_PER_LANE)
     cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
-    bool profile = false;          // per-launch CUDA events, accumulated by kernel kind
+    bool dataflow = true;          // one persistent launch per wave for all non-fused steps (TB_LEVEL_SYNC=1: one launch per level and kind)
+    bool solo_fence = false;       // a solo wave ran on the whole arena: the side lanes must wait for it before their next wave
+    int profile_mode = 0;          // 1: events around every launch on its own lane (lanes stay concurrent); 2: single lane
+    struct ProfRec {
+        int kind;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<ProfRec> prof_recs;  // launches of the current call (profile_mode != 0)
+    size_t prof_used = 0;            // events of prof_events handed out in the current call
+    double prof_union_ms[4] = {0, 0, 0, 0};  // per kind: length of the union of the launches' [start, end] intervals
     double prof_ms[4] = {0, 0, 0, 0};
     int64_t prof_launches[4] = {0, 0, 0, 0};
     int64_t h2d_bytes = 0, d2h_bytes = 0;  // of the last contract call
@@ -112,6 +130,53 @@ int set_err(tb_ctx* ctx, int code, const std::string& msg) {
     } while (0)
 
 int sync_all_lanes(tb_ctx* ctx);
+
+// NCCL, resolved with dlopen on first use (tb_init_multi): single-GPU users need no NCCL at all
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(void** comms, int ndev, const int* devlist) = nullptr;
+    int (*CommDestroy)(void* comm) = nullptr;
+    int (*AllReduce)(const void* send, void* recv, size_t count, int dtype, int op, void* comm, cudaStream_t st) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+constexpr int kNcclFloat64 = 8, kNcclMax = 2;  // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since NCCL 2.0)
+
+NcclApi* nccl_api() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) {
+            api.err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "unknown");
+            return;
+        }
+        auto sym = [&](const char* n) {
+            void* p = dlsym(api.lib, n);
+            if (!p && api.err.empty()) api.err = std::string("libnccl has no symbol ") + n;
+            return p;
+        };
+        api.CommInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
+        api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+        api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+        api.GroupStart = (int (*)())sym("ncclGroupStart");
+        api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+        api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    });
+    return &api;
+}
+
+#define TB_NCCL(ctx, call)                                                                                         \
+    do {                                                                                                           \
+        int e__ = (call);                                                                                          \
+        if (e__ != 0) return set_err(ctx, TB_ERR_NCCL, std::string(#call) + ": " + nccl_api()->GetErrorString(e__)); \
+    } while (0)
+
 
 void link_resident(tb_ctx* ctx, Plan& P) {
     P.res_prev = nullptr;
@@ -298,6 +363,7 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
     return TB_OK;
 }
 
+constexpr size_t kNoDone = (size_t)-1;
 constexpr uint32_t kFusedSmemMax = 96 * 1024;  // dynamic shared memory limit of k_fused_subtrees (descriptors + pool + data)
 struct Launch {
     int lane;        // stream lane the launch goes to
@@ -306,6 +372,7 @@ struct Launch {
     size_t inst_off; // byte offset of the instance array in the staging buffer
     size_t starts_off;
     size_t counter_off;  // gemm v2: a zeroed u32 tile counter inside the staging buffer
+    size_t done_off = kNoDone;  // dataflow launch: per-instance completion counters inside the staging buffer
     int n_insts;
     uint32_t grid;
     uint32_t smem;
@@ -325,14 +392,16 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
             if constexpr (std::is_same<T, int16_t>::value) {
                 const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
                 k_gemm2h<<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
-                                                                 L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off));
+                                                                 L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
+                                                                 L.done_off == kNoDone ? nullptr : (unsigned int*)(dbase + L.done_off));
             } else if (ctx->gemm_v1) {
                 k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             } else {
                 const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
                 k_gemm2<T><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
                                                                    L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
-                                                                   ctx->staged_epilogue ? 1 : 0);
+                                                                   ctx->staged_epilogue ? 1 : 0,
+                                                                   L.done_off == kNoDone ? nullptr : (unsigned int*)(dbase + L.done_off));
             }
             break;
         case 3:
@@ -360,7 +429,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         return rc;
     }
     const int max_wave = ctx->call_wave > 0 ? ctx->call_wave : (ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128);
-    const int NL = (ctx->profile || single_plan_mode) ? 1 : ctx->n_lanes;
+    const int NL = (ctx->profile_mode == 2 || single_plan_mode) ? 1 : ctx->n_lanes;
     // try to grow the arena so that NL full waves fit (bounded by the configured limit)
     {
         std::vector<size_t> needs;
@@ -500,6 +569,75 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 launches.push_back(L);
             }
         }
+        if (ctx->dataflow) {
+            // ---- dataflow: every big step of every member, level-major, in ONE persistent launch.  A tile waits on the
+            // completion counters of the instances that produce its operands (BigInst::dep_a / dep_b) instead of on a
+            // kernel boundary; tiles are handed out in this (topological) order, so the kernel cannot deadlock.
+            std::vector<BigInst> insts;
+            std::vector<uint32_t> starts, done_init;
+            std::vector<std::vector<int32_t>> inst_of(w.members.size());  // member -> big step -> instance index
+            for (size_t m = 0; m < w.members.size(); ++m) inst_of[m].assign(plans[w.members[m]]->p.big_steps.size(), -1);
+            uint64_t tiles = 0;
+            std::vector<std::pair<uint32_t, uint32_t>> lvl;  // (member, step) of one level and kind
+            for (int lv = 1; lv <= w.levels; ++lv) {
+                for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
+                    lvl.clear();
+                    for (size_t m = 0; m < w.members.size(); ++m) {
+                        const Plan& P = plans[w.members[m]]->p;
+                        if (lv > P.n_levels) continue;
+                        for (int s = P.big_level_begin[lv]; s < P.big_level_begin[lv + 1]; ++s)
+                            if (P.big_steps[s].kind == kind) lvl.push_back({(uint32_t)m, (uint32_t)s});
+                    }
+                    if (kind == KIND_GEMM)  // longest reductions first inside a level
+                        std::stable_sort(lvl.begin(), lvl.end(), [&](const std::pair<uint32_t, uint32_t>& x, const std::pair<uint32_t, uint32_t>& y) {
+                            return plans[w.members[x.first]]->p.big_steps[x.second].nk > plans[w.members[y.first]]->p.big_steps[y.second].nk;
+                        });
+                    for (const auto& ms : lvl) {
+                        const Plan& P = plans[w.members[ms.first]]->p;
+                        const BigStep& st = P.big_steps[ms.second];
+                        uint8_t* blob = (uint8_t*)P.d_blob;
+                        BigInst bi{};
+                        bi.step = (const BigStep*)(blob + P.big_blob_off) + ms.second;
+                        bi.pool = blob;
+                        bi.arena = (uint8_t*)ctx->arena + w.base[ms.first];
+                        bi.tile_start = (uint32_t)tiles;
+                        const int32_t da = P.big_dep_a[ms.second], db = P.big_dep_b[ms.second];
+                        bi.dep_a = da >= 0 ? inst_of[ms.first][(size_t)da] : -1;
+                        bi.dep_b = db >= 0 ? inst_of[ms.first][(size_t)db] : -1;
+                        inst_of[ms.first][ms.second] = (int32_t)insts.size();
+                        insts.push_back(bi);
+                        starts.push_back((uint32_t)tiles);
+                        done_init.push_back(st.n_tiles * (uint32_t)(G2_CONSUMERS / 32));
+                        tiles += st.n_tiles;
+                    }
+                }
+            }
+            if (tiles > 0x7fffffffull) return set_err(ctx, TB_ERR_UNSUPPORTED, "a wave needs more than 2^31 tiles");
+            if (!insts.empty()) {
+                align16();
+                Launch L{};
+                L.lane = w.lane;
+                L.kind = KIND_GEMM;
+                L.vt = vt;
+                L.inst_off = host.size();
+                host.resize(host.size() + insts.size() * sizeof(BigInst));
+                std::memcpy(host.data() + L.inst_off, insts.data(), insts.size() * sizeof(BigInst));
+                align16();
+                L.starts_off = host.size();
+                host.resize(host.size() + starts.size() * 4);
+                std::memcpy(host.data() + L.starts_off, starts.data(), starts.size() * 4);
+                align16();
+                L.done_off = host.size();
+                host.resize(host.size() + done_init.size() * 4);
+                std::memcpy(host.data() + L.done_off, done_init.data(), done_init.size() * 4);
+                align16();
+                L.counter_off = host.size();
+                host.resize(host.size() + 16, 0);
+                L.n_insts = (int)insts.size();
+                L.grid = (uint32_t)tiles;
+                launches.push_back(L);
+            }
+        } else
         for (int lv = 1; lv <= w.levels; ++lv) {
             for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
                 std::vector<BigInst> insts;
@@ -574,7 +712,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 const Plan& P = plans[w.members[m]]->p;
                 FinalInst f{};
                 f.src = (uint8_t*)ctx->arena + w.base[m] + P.root_off * elem;
-                f.out_index = w.members[m];
+                f.out_index = ctx->index_map ? ctx->index_map[w.members[m]] : w.members[m];
                 fin.push_back(f);
             }
             L.n_insts = (int)fin.size();
@@ -595,14 +733,21 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     TB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
     TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     for (int l = 1; l < NL; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_copy, 0));
-    if (ctx->profile) {
-        while (ctx->prof_events.size() < launches.size() + 1) {
+    // a solo wave of the previous group used the whole arena on the main stream: no side lane may touch its partition
+    // before that wave has finished (the main stream itself is ordered behind it)
+    if (ctx->solo_fence) {
+        for (int l = 1; l < ctx->n_lanes; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+        ctx->solo_fence = false;
+    }
+    auto prof_event = [&](cudaEvent_t* out) -> int {
+        if (ctx->prof_used == ctx->prof_events.size()) {
             cudaEvent_t e;
             TB_CUDA(ctx, cudaEventCreate(&e));
             ctx->prof_events.push_back(e);
         }
-        TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[0], ctx->stream));
-    }
+        *out = ctx->prof_events[ctx->prof_used++];
+        return TB_OK;
+    };
     auto join_lanes = [&]() -> int {
         for (int l = 1; l < NL; ++l) {
             TB_CUDA(ctx, cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
@@ -618,10 +763,19 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             joined = true;
         }
         const Launch& L = launches[li];
+        cudaStream_t st = L.lane == 0 ? ctx->stream : ctx->side[L.lane];
+        tb_ctx::ProfRec pr{L.kind, nullptr, nullptr};
+        if (ctx->profile_mode) {
+            if ((rc = prof_event(&pr.e0)) || (rc = prof_event(&pr.e1))) return rc;
+            TB_CUDA(ctx, cudaEventRecord(pr.e0, st));
+        }
         if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)sl->d);
         else if (vt == TB_VALUE_I16X2) launch_one<int16_t>(ctx, L, (uint8_t*)sl->d);
         else launch_one<float>(ctx, L, (uint8_t*)sl->d);
-        if (ctx->profile) TB_CUDA(ctx, cudaEventRecord(ctx->prof_events[li + 1], ctx->stream));
+        if (ctx->profile_mode) {
+            TB_CUDA(ctx, cudaEventRecord(pr.e1, st));
+            ctx->prof_recs.push_back(pr);
+        }
     }
     // the main stream joins the lanes at the end of every group: the slot event (and the caller's final sync)
     // then cover every kernel that reads this slot's work lists
@@ -632,28 +786,13 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     TB_CUDA(ctx, cudaGetLastError());
     TB_CUDA(ctx, cudaEventRecord(sl->ev, ctx->stream));
     sl->busy = true;
+    if (first_solo_launch != (size_t)-1) {
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+        ctx->solo_fence = true;
+    }
     ctx->host_ms[3] += now_ms() - t_l0;
     ctx->last_launches += (int64_t)launches.size();
     ctx->h2d_bytes += (int64_t)host.size();
-    if (ctx->profile) {
-        TB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        for (size_t li = 0; li < launches.size(); ++li) {
-            float pm = 0;
-            TB_CUDA(ctx, cudaEventElapsedTime(&pm, ctx->prof_events[li], ctx->prof_events[li + 1]));
-            ctx->prof_ms[launches[li].kind] += pm;
-            ctx->prof_launches[launches[li].kind] += 1;
-        }
-        if (const char* dump = getenv("TB_DUMP_LAUNCHES")) {  // per-launch records of the profiling pass (diagnostics)
-            if (FILE* f = fopen(dump, "a")) {
-                for (size_t li = 0; li < launches.size(); ++li) {
-                    float pm = 0;
-                    cudaEventElapsedTime(&pm, ctx->prof_events[li], ctx->prof_events[li + 1]);
-                    fprintf(f, "%d,%d,%d,%u,%.4f\n", vt, launches[li].kind, launches[li].n_insts, launches[li].grid, pm);
-                }
-                fclose(f);
-            }
-        }
-    }
     return TB_OK;
 }
 
@@ -699,7 +838,10 @@ int begin_call(tb_ctx* ctx, int64_t n) {
     for (int q = 0; q < 4; ++q) {
         ctx->prof_ms[q] = 0;
         ctx->prof_launches[q] = 0;
+        ctx->prof_union_ms[q] = 0;
     }
+    ctx->prof_recs.clear();
+    ctx->prof_used = 0;
     for (int q = 0; q < 6; ++q) ctx->host_ms[q] = 0;
     ctx->lane_cursor = 0;
     // descriptor chunks: when nothing is resident keep only the largest chunk (the device is idle between calls)
@@ -724,18 +866,17 @@ int begin_call(tb_ctx* ctx, int64_t n) {
     return TB_OK;
 }
 
+// wait for everything the call enqueued; device time and the per-launch profile of the call
+int finish_sync(tb_ctx* ctx);
+
 int finish_call(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, const std::vector<int32_t>& status,
                 double* out_values, int32_t* out_status, double* out_max, bool any) {
     if (any) {
         TB_CUDA(ctx, cudaMemcpyAsync(ctx->h_results, ctx->d_results, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->d2h_bytes += (int64_t)n * 8;
     }
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    int rc = sync_all_lanes(ctx);
+    int rc = finish_sync(ctx);
     if (rc) return rc;
-    float ms = 0;
-    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms;
     double mx = -std::numeric_limits<double>::infinity();
     int worst = TB_OK;
     for (int64_t i = 0; i < n; ++i) {
@@ -752,6 +893,49 @@ int finish_call(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, 
     }
     if (out_max) *out_max = mx;
     if (worst != TB_OK) return set_err(ctx, worst, "one or more branches failed (see per-branch status): arena too small");
+    return TB_OK;
+}
+
+int finish_sync(tb_ctx* ctx) {
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    int rc = sync_all_lanes(ctx);
+    if (rc) return rc;
+    float ms = 0;
+    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    if (!ctx->prof_recs.empty()) {
+        // per-launch CUDA events on the launching lanes: per kind the sum of the launch durations and the length of the
+        // union of their [start, end] intervals (lanes overlap: the union is the time the kind was on the device)
+        std::vector<std::pair<float, float>> iv[4];
+        FILE* dump = nullptr;
+        if (const char* path = getenv("TB_DUMP_LAUNCHES")) dump = fopen(path, "a");  // diagnostics: one record per launch
+        for (const tb_ctx::ProfRec& pr : ctx->prof_recs) {
+            float a = 0, b = 0;
+            TB_CUDA(ctx, cudaEventElapsedTime(&a, ctx->ev0, pr.e0));
+            TB_CUDA(ctx, cudaEventElapsedTime(&b, ctx->ev0, pr.e1));
+            ctx->prof_ms[pr.kind] += b - a;
+            ctx->prof_launches[pr.kind] += 1;
+            iv[pr.kind].push_back({a, b});
+            if (dump) fprintf(dump, "%d,%.4f,%.4f\n", pr.kind, a, b);
+        }
+        if (dump) fclose(dump);
+        for (int k = 0; k < 4; ++k) {
+            std::sort(iv[k].begin(), iv[k].end());
+            float end = -1, total = 0;
+            for (const auto& x : iv[k]) {
+                if (x.first > end) {
+                    total += x.second - x.first;
+                    end = x.second;
+                } else if (x.second > end) {
+                    total += x.second - end;
+                    end = x.second;
+                }
+            }
+            ctx->prof_union_ms[k] = total;
+        }
+        ctx->prof_recs.clear();
+        ctx->prof_used = 0;
+    }
     return TB_OK;
 }
 
@@ -779,16 +963,18 @@ double mean_plan_ops(tb_plan* const* plans, int64_t lo, int64_t hi) {
     return cnt ? sum / (double)cnt : 0.0;
 }
 
-int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
-                  double* out_max, bool single) {
-    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
-    if (n < 0 || (n > 0 && (!plans || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
-    int rc = begin_call(ctx, n);
+int multi_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
+                         double* out_max);
+
+// the asynchronous half of tb_contract_batch on ONE device (resident plans): upload what is missing, enqueue every launch
+int batch_enqueue(tb_ctx* ctx, tb_plan* const* plans, int64_t n, int64_t n_results, std::vector<int32_t>& status, bool single) {
+    int rc = begin_call(ctx, n_results);
     if (rc) return rc;
-    std::vector<int32_t> status((size_t)n, TB_OK);
-    bool any = false;
-    for (int64_t i = 0; i < n; ++i) any = any || plans[i];
-    // batches of growing size: the GPU starts on the first wave while the host still builds the work lists of the rest
+    if (ctx->prefill_results) {
+        const unsigned blocks = (unsigned)((n_results + 255) / 256);
+        k_fill_double<<<blocks, 256, 0, ctx->stream>>>(ctx->d_results, n_results, -std::numeric_limits<double>::infinity());
+    }
+    status.assign((size_t)n, TB_OK);
     const int64_t wave = wave_for_call(ctx, n, mean_plan_ops(plans, 0, n));
     ctx->call_wave = (int)wave;
     int64_t batch = single ? n : wave;
@@ -798,6 +984,21 @@ int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n
         lo = hi;
         batch = std::min<int64_t>(batch * 2, wave * ctx->n_lanes * 2);
     }
+    return rc;
+}
+
+int contract_impl(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
+                  double* out_max, bool single) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!plans || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    if (!ctx->subs.empty()) {
+        if (single) return contract_impl(ctx->subs[0], plans, r, n, out_values, out_status, out_max, true);
+        return multi_contract_batch(ctx, plans, r, n, out_values, out_status, out_max);
+    }
+    std::vector<int32_t> status;
+    bool any = false;
+    for (int64_t i = 0; i < n; ++i) any = any || plans[i];
+    int rc = batch_enqueue(ctx, plans, n, n, status, single);
     if (rc) {
         sync_all_lanes(ctx);
         return rc;
@@ -895,12 +1096,14 @@ const char* tb_last_error(const tb_ctx* ctx) { return ctx ? ctx->last_error.c_st
 int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
     if (!out_ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "out_ctx is NULL");
     *out_ctx = nullptr;
+    if (opts && opts->n_devices > 1) return tb_init_multi(opts->devices, opts->n_devices, opts, out_ctx);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
         return set_err(nullptr, TB_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libtbcuda has no CPU fallback");
     std::unique_ptr<tb_ctx> ctx(new tb_ctx());
     if (opts) ctx->opts = *opts;
+    ctx->opts.devices = nullptr;  // read during init only
     ctx->device = ctx->opts.device;
     if (ctx->device < 0 || ctx->device >= ndev) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "device ordinal out of range");
     tb_ctx* c = ctx.get();
@@ -922,8 +1125,12 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
         if (e4 && atoi(e4) >= 1 && c->opts.max_wave == 0) c->opts.max_wave = atoi(e4);
         const char* e5 = getenv("TB_WAVES_PER_LANE");
         if (e5 && atoi(e5) >= 1) c->waves_per_lane = atoi(e5);
+        const char* e6 = getenv("TB_LEVEL_SYNC");  // A/B testing: one launch per dependency level and kernel kind (the round-1 executor)
+        c->dataflow = !(e6 && e6[0] == '1') && !c->gemm_v1;
+        if (c->opts.streams_per_device >= 1) c->n_lanes = std::min(c->opts.streams_per_device, (int)tb_ctx::kMaxLanes);
         const char* e2 = getenv("TB_LANES");
         if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
+        c->profile_mode = std::max(0, std::min(2, c->opts.timing));
     }
     TB_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     TB_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -955,8 +1162,86 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
     return TB_OK;
 } TB_CATCH(nullptr)
 
+int tb_init_multi(const int32_t* devices, int32_t n_devices, const tb_options* opts, tb_ctx** out_ctx) try {
+    if (!out_ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    if (n_devices < 1 || n_devices > 64) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "n_devices must be in [1, 64]");
+    std::unique_ptr<tb_ctx> ctx(new tb_ctx());
+    if (opts) ctx->opts = *opts;
+    ctx->opts.n_devices = n_devices;
+    ctx->opts.devices = nullptr;  // read during init only
+    std::vector<int> devs((size_t)n_devices);
+    for (int d = 0; d < n_devices; ++d) devs[(size_t)d] = devices ? devices[d] : d;
+    for (int d = 0; d < n_devices; ++d)
+        for (int e = 0; e < d; ++e)
+            if (devs[(size_t)d] == devs[(size_t)e]) ctx->host_combine = true;
+    ctx->device = devs[0];
+    const int total_threads = ctx->opts.host_threads > 0 ? ctx->opts.host_threads : std::max(1, (int)std::thread::hardware_concurrency());
+    auto fail = [&](int rc) {
+        for (tb_ctx* sub : ctx->subs) tb_shutdown(sub);
+        ctx->subs.clear();
+        return rc;
+    };
+    for (int d = 0; d < n_devices; ++d) {
+        tb_options o = ctx->opts;
+        o.device = devs[(size_t)d];
+        o.n_devices = 0;
+        o.devices = nullptr;
+        o.host_threads = std::max(1, total_threads / n_devices);
+        tb_ctx* sub = nullptr;
+        int rc = tb_init(&o, &sub);
+        if (rc) return fail(rc);
+        sub->parent = ctx.get();
+        ctx->subs.push_back(sub);
+    }
+    ctx->profile_mode = ctx->subs[0]->profile_mode;
+    if (n_devices > 1 && !ctx->host_combine) {
+        NcclApi* nc = nccl_api();
+        if (!nc->lib || !nc->err.empty()) return fail(set_err(nullptr, TB_ERR_NCCL, nc->err.empty() ? "NCCL is not available" : nc->err));
+        ctx->comms.assign((size_t)n_devices, nullptr);
+        int e = nc->CommInitAll(ctx->comms.data(), n_devices, devs.data());
+        if (e != 0) {
+            ctx->comms.clear();
+            return fail(set_err(nullptr, TB_ERR_NCCL, std::string("ncclCommInitAll: ") + nc->GetErrorString(e)));
+        }
+    }
+    *out_ctx = ctx.release();
+    return TB_OK;
+} TB_CATCH(nullptr)
+
+int tb_device_count(const tb_ctx* ctx) {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    return ctx->subs.empty() ? 1 : (int)ctx->subs.size();
+}
+
+int tb_estimate(const tb_network* net, double* out_ops, double* out_sc) try {
+    if (!net || !out_ops) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "net / out_ops is NULL");
+    if (net->n_leaves == 0) {  // empty graph: nothing to contract
+        *out_ops = 0;
+        if (out_sc) *out_sc = 0;
+        return TB_OK;
+    }
+    Plan P;
+    std::string err;
+    int rc = compile_plan(*net, TB_PLAN_ESTIMATE_ONLY, P, err);
+    if (rc) return set_err(nullptr, rc, err);
+    *out_ops = P.stats.ops;
+    if (out_sc) *out_sc = P.stats.sc;
+    return TB_OK;
+} TB_CATCH(nullptr)
+
 int tb_shutdown(tb_ctx* ctx) {
     if (!ctx) return TB_OK;
+    if (!ctx->subs.empty()) {  // multi-GPU context: communicators first, then every device's own context
+        if (!ctx->comms.empty()) {
+            NcclApi* nc = nccl_api();
+            for (void* c : ctx->comms)
+                if (c) nc->CommDestroy(c);
+        }
+        for (tb_ctx* sub : ctx->subs) tb_shutdown(sub);
+        delete ctx;
+        return TB_OK;
+    }
     if (ctx->reaper.joinable()) ctx->reaper.join();
 #ifdef TB_KPROF
     {
@@ -1099,14 +1384,33 @@ int tb_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64
     return contract_impl(ctx, plans, r, n, out_values, out_status, out_max, false);
 } TB_CATCH(ctx)
 
-int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n, double* out_values,
-                         int32_t* out_status, double* out_max) try {
-    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
-    if (n < 0 || (n > 0 && (!nets || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
-    const double t_c0 = now_ms();
-    int rc = begin_call(ctx, n);
+}  // extern "C"
+
+namespace {
+
+// the asynchronous half of tb_contract_networks on ONE device: compile (worker threads), upload, enqueue every launch.
+// n_results = length of the call's result vector (> n for a sub-context of a multi-GPU call, which scatters through
+// ctx->index_map into a vector pre-filled with -inf).  The caller finishes with finish_call / finish_sync and
+// release_temporary_plans(cs.plans).
+struct NetworksCall {
+    std::vector<tb_plan*> plans;
+    std::vector<int32_t> status;
+    bool any = false;
+    double t_c0 = 0;
+};
+
+int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_results, NetworksCall& cs) {
+    cs.t_c0 = now_ms();
+    const double t_c0 = cs.t_c0;
+    (void)t_c0;
+    int rc = begin_call(ctx, n_results);
     if (rc) return rc;
-    std::vector<tb_plan*> plans((size_t)n, nullptr);
+    if (ctx->prefill_results) {  // multi-GPU call: entries of other devices (and of empty / failed branches) stay -inf for the max-reduce
+        const unsigned blocks = (unsigned)((n_results + 255) / 256);
+        k_fill_double<<<blocks, 256, 0, ctx->stream>>>(ctx->d_results, n_results, -std::numeric_limits<double>::infinity());
+    }
+    std::vector<tb_plan*>& plans = cs.plans;
+    plans.assign((size_t)n, nullptr);
     std::vector<int> codes((size_t)n, TB_OK);
     std::vector<std::string> errs((size_t)n);
     std::unique_ptr<std::atomic<uint8_t>[]> done(new std::atomic<uint8_t>[(size_t)std::max<int64_t>(n, 1)]);
@@ -1144,8 +1448,9 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     }();
     // two waves per batch (profiles/s06_e2e_batch_sweep_cfg2.jsonl: 34.6 ms with 256-plan batches, 37.6 ms with 512)
     int64_t batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes / 2);
-    std::vector<int32_t> status((size_t)n, TB_OK);
-    bool any = false;
+    std::vector<int32_t>& status = cs.status;
+    status.assign((size_t)n, TB_OK);
+    bool& any = cs.any;
     double t_wait = 0;
     // small first batches: the GPU starts after ~64 compiled plans instead of a full batch (pipeline fill)
     int64_t batch = std::min<int64_t>(batch_max, 64);
@@ -1200,17 +1505,391 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     abort.store(rc != TB_OK);
     for (auto& t : th) t.join();
     ctx->host_ms[0] = t_wait;  // time the launching thread spent waiting for the compiler threads
-    if (rc == TB_OK) rc = finish_call(ctx, plans.data(), r, n, status, out_values, out_status, out_max, any);
+    return rc;
+}
+
+int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n, double* out_values,
+                            int32_t* out_status, double* out_max);
+
+
+// ================================================================================================
+// Multi-GPU inside the library (component C1): ONE process, one sub-context per device with its own
+// arena / streams / worker threads, branches dealt longest-first (LPT) by estimated cost, and ONE
+// ncclAllReduce(ncclMax) over the per-branch result vector -- pre-filled with -inf on every device -- in place of
+// maximum(res) (/root/reference/src/dynamic_ob.jl:27) and of any per-branch gather.  No tensor crosses NVLink.
+// NCCL is resolved with dlopen at tb_init_multi time (libnccl.so.2), so single-GPU users need no NCCL at all.
+// ================================================================================================
+// longest-processing-time-first: units sorted by cost (descending, stable), each to the least-loaded device.
+// `load` may carry work that is already pinned to a device.
+void lpt_assign(const std::vector<double>& cost, const std::vector<int64_t>& units, std::vector<double>& load, std::vector<int>& owner) {
+    std::vector<int64_t> ord(units);
+    std::stable_sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) { return cost[(size_t)a] > cost[(size_t)b]; });
+    for (int64_t i : ord) {
+        int best = 0;
+        for (int d = 1; d < (int)load.size(); ++d)
+            if (load[(size_t)d] < load[(size_t)best]) best = d;
+        owner[(size_t)i] = best;
+        load[(size_t)best] += cost[(size_t)i];
+    }
+}
+
+int host_threads_of(const tb_ctx* ctx) {
+    return ctx->opts.host_threads > 0 ? ctx->opts.host_threads : std::max(1, (int)std::thread::hardware_concurrency());
+}
+
+// after every device thread has enqueued its share: combine the devices' result vectors (length n, -inf where a device
+// has no entry) into the host vector of sub-context 0, then wait for all devices
+int multi_combine(tb_ctx* ctx, int64_t n) {
+    const int D = (int)ctx->subs.size();
+    tb_ctx* s0 = ctx->subs[0];
+    if (n > 0 && D > 1 && !ctx->host_combine) {
+        NcclApi* nc = nccl_api();
+        TB_NCCL(ctx, nc->GroupStart());
+        for (int d = 0; d < D; ++d) {
+            tb_ctx* sub = ctx->subs[(size_t)d];
+            int e = nc->AllReduce(sub->d_results, sub->d_results, (size_t)n, kNcclFloat64, kNcclMax, ctx->comms[(size_t)d], sub->stream);
+            if (e != 0) {
+                nc->GroupEnd();
+                return set_err(ctx, TB_ERR_NCCL, std::string("ncclAllReduce: ") + nc->GetErrorString(e));
+            }
+        }
+        TB_NCCL(ctx, nc->GroupEnd());
+    }
+    const int n_read = (D > 1 && ctx->host_combine) ? D : 1;
+    for (int d = 0; d < n_read && n > 0; ++d) {
+        tb_ctx* sub = ctx->subs[(size_t)d];
+        TB_CUDA(ctx, cudaSetDevice(sub->device));
+        TB_CUDA(ctx, cudaMemcpyAsync(sub->h_results, sub->d_results, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, sub->stream));
+        sub->d2h_bytes += n * 8;
+    }
+    int rc = TB_OK;
+    for (int d = 0; d < D; ++d) {
+        tb_ctx* sub = ctx->subs[(size_t)d];
+        cudaSetDevice(sub->device);
+        int r1 = finish_sync(sub);
+        if (r1 && !rc) rc = set_err(ctx, r1, "device " + std::to_string(sub->device) + ": " + sub->last_error);
+    }
+    if (rc) return rc;
+    for (int d = 1; d < n_read; ++d)  // testing configuration (repeated devices): max over the host copies
+        for (int64_t i = 0; i < n; ++i) s0->h_results[i] = std::max(s0->h_results[i], ctx->subs[(size_t)d]->h_results[i]);
+    return TB_OK;
+}
+
+void multi_aggregate(tb_ctx* ctx, double t0) {
+    ctx->last_ms = 0;
+    ctx->last_launches = 0;
+    ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    for (int q = 0; q < 6; ++q) ctx->host_ms[q] = 0;
+    for (int q = 0; q < 4; ++q) ctx->prof_ms[q] = ctx->prof_union_ms[q] = 0, ctx->prof_launches[q] = 0;
+    for (tb_ctx* sub : ctx->subs) {
+        ctx->last_ms = std::max(ctx->last_ms, sub->last_ms);
+        ctx->last_launches += sub->last_launches;
+        ctx->h2d_bytes += sub->h2d_bytes;
+        ctx->d2h_bytes += sub->d2h_bytes;
+        for (int q = 0; q < 5; ++q) ctx->host_ms[q] = std::max(ctx->host_ms[q], sub->host_ms[q]);
+        for (int q = 0; q < 4; ++q) {
+            ctx->prof_ms[q] += sub->prof_ms[q];
+            ctx->prof_launches[q] += sub->prof_launches[q];
+            ctx->prof_union_ms[q] = std::max(ctx->prof_union_ms[q], sub->prof_union_ms[q]);
+        }
+    }
+    ctx->host_ms[5] = now_ms() - t0;
+}
+
+int contract_sliced_single(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced, int64_t first,
+                           int64_t count, double r, double* out_values, int32_t* out_status, double* out_max);
+
+// ONE heavy branch over all devices: the 2^k assignments are dealt in contiguous ranges (slices of one branch cost the same)
+int multi_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced, int64_t first,
+                          int64_t count, double r, double* out_values, int32_t* out_status, double* out_max) {
+    const int D = (int)ctx->subs.size();
+    const double t0 = now_ms();
+    std::vector<double> vals((size_t)std::max<int64_t>(count, 1));
+    std::vector<int32_t> stat((size_t)std::max<int64_t>(count, 1), TB_OK);
+    std::vector<int> rcs((size_t)D, TB_OK);
+    std::vector<double> mxs((size_t)D, -std::numeric_limits<double>::infinity());
+    std::vector<std::thread> th;
+    const int64_t base = count / D, extra = count % D;
+    for (int d = 0; d < D; ++d) {
+        const int64_t off = d * base + std::min<int64_t>(d, extra), cnt = base + (d < extra ? 1 : 0);
+        if (cnt == 0) continue;
+        th.emplace_back([&, d, off, cnt] {
+            tb_ctx* sub = ctx->subs[(size_t)d];
+            try {
+                cudaSetDevice(sub->device);
+                rcs[(size_t)d] = contract_sliced_single(sub, net, sliced_labels, n_sliced, first + off, cnt, r, vals.data() + off,
+                                                        stat.data() + off, &mxs[(size_t)d]);
+            } catch (...) {
+                rcs[(size_t)d] = exception_to_status(sub);
+            }
+        });
+    }
+    for (auto& t : th) t.join();
+    int rc = TB_OK;
+    for (int d = 0; d < D; ++d)
+        if (rcs[(size_t)d] && !rc) rc = set_err(ctx, rcs[(size_t)d], "device " + std::to_string(ctx->subs[(size_t)d]->device) + ": " + ctx->subs[(size_t)d]->last_error);
+    if (out_values) std::memcpy(out_values, vals.data(), (size_t)count * sizeof(double));
+    if (out_status) std::memcpy(out_status, stat.data(), (size_t)count * sizeof(int32_t));
+    if (out_max) *out_max = *std::max_element(mxs.begin(), mxs.end());
+    multi_aggregate(ctx, t0);
+    return rc;
+}
+
+int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n, double* out_values,
+                            int32_t* out_status, double* out_max) {
+    const int D = (int)ctx->subs.size();
+    const double t0 = now_ms();
+    const double ninf = -std::numeric_limits<double>::infinity();
+    // ---- fewer branches than devices can keep busy and an index-slicing budget: every branch becomes 2^k index slices
+    // spread over all devices (BASELINE config 3 is ONE branch)
+    int64_t n_live = 0;
+    for (int64_t i = 0; i < n; ++i) n_live += nets[i].n_leaves != 0;
+    if (ctx->opts.slice_budget > 0 && n_live > 0 && n_live < 2 * (int64_t)D) {
+        int k = 0;
+        while ((n_live << k) < 2 * (int64_t)D && k < ctx->opts.slice_budget) ++k;
+        double mx = ninf;
+        int rc = TB_OK;
+        for (int64_t i = 0; i < n && rc == TB_OK; ++i) {
+            const double ri = r ? r[i] : 0.0;
+            if (out_status) out_status[i] = TB_OK;
+            if (nets[i].n_leaves == 0) {
+                out_values[i] = ri;
+            } else {
+                std::vector<int32_t> labels((size_t)k);
+                std::string err;
+                const int got = nets[i].n_fixed == 0 ? suggest_slices(nets[i], -1, k, labels.data(), nullptr, nullptr, err) : 0;
+                if (got < 0) return set_err(ctx, got, err);
+                double v = ninf;
+                rc = multi_contract_sliced(ctx, &nets[i], labels.data(), got, 0, (int64_t)1 << got, ri, nullptr, nullptr, &v);
+                out_values[i] = v;
+            }
+            mx = std::max(mx, out_values[i]);
+        }
+        if (out_max) *out_max = mx;
+        return rc;
+    }
+    // ---- 1. cost of every branch (label-set pass only), all host threads
+    std::vector<double> cost((size_t)n, 0.0);
+    {
+        std::atomic<int64_t> next{0};
+        std::atomic<int> bad{TB_OK};
+        std::vector<std::string> errs;
+        std::mutex mu;
+        auto worker = [&] {
+            for (;;) {
+                const int64_t i = next.fetch_add(1);
+                if (i >= n) break;
+                if (nets[i].n_leaves == 0) continue;
+                Plan P;
+                std::string err;
+                const int rc = compile_plan(nets[i], ctx->opts.plan_flags | TB_PLAN_ESTIMATE_ONLY, P, err);
+                if (rc) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (bad.load() == TB_OK) {
+                        bad.store(rc);
+                        errs.push_back("branch " + std::to_string(i) + ": " + err);
+                    }
+                } else cost[(size_t)i] = P.stats.ops;
+            }
+        };
+        const int nt = std::max(1, std::min<int>(host_threads_of(ctx), (int)std::max<int64_t>(1, n / 16)));
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt - 1; ++t) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+        if (bad.load() != TB_OK) return set_err(ctx, bad.load(), errs.empty() ? "plan estimation failed" : errs[0]);
+    }
+    // ---- 2. longest-first assignment
+    std::vector<int> owner((size_t)n, 0);
+    {
+        std::vector<int64_t> units;
+        for (int64_t i = 0; i < n; ++i)
+            if (nets[i].n_leaves != 0) units.push_back(i);
+        std::vector<double> load((size_t)D, 0.0);
+        lpt_assign(cost, units, load, owner);
+    }
+    // ---- 3. every device compiles, uploads and enqueues its share on its own thread
+    struct Dev {
+        std::vector<int64_t> idx;
+        std::vector<tb_network> nets;
+        NetworksCall cs;
+        int rc = TB_OK;
+    };
+    std::vector<Dev> dev((size_t)D);
+    for (int64_t i = 0; i < n; ++i)
+        if (nets[i].n_leaves != 0) {
+            dev[(size_t)owner[(size_t)i]].idx.push_back(i);
+            dev[(size_t)owner[(size_t)i]].nets.push_back(nets[i]);
+        }
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < D; ++d)
+            th.emplace_back([&, d] {
+                tb_ctx* sub = ctx->subs[(size_t)d];
+                Dev& dv = dev[(size_t)d];
+                try {
+                    cudaSetDevice(sub->device);
+                    sub->index_map = dv.idx.data();
+                    sub->prefill_results = true;
+                    dv.rc = networks_enqueue(sub, dv.nets.data(), (int64_t)dv.nets.size(), std::max<int64_t>(n, 1), dv.cs);
+                } catch (...) {
+                    dv.rc = exception_to_status(sub);
+                }
+                sub->index_map = nullptr;
+                sub->prefill_results = false;
+            });
+        for (auto& t : th) t.join();
+    }
+    int rc = TB_OK;
+    for (int d = 0; d < D; ++d)
+        if (dev[(size_t)d].rc && !rc) rc = set_err(ctx, dev[(size_t)d].rc, "device " + std::to_string(ctx->subs[(size_t)d]->device) + ": " + ctx->subs[(size_t)d]->last_error);
+    // ---- 4. one all-reduce(max) over the result vector, then wait
+    if (rc == TB_OK) rc = multi_combine(ctx, n);
+    else
+        for (tb_ctx* sub : ctx->subs) {
+            cudaSetDevice(sub->device);
+            sync_all_lanes(sub);
+        }
+    // ---- 5. outputs
+    if (rc == TB_OK) {
+        std::vector<int32_t> status((size_t)n, TB_OK);
+        for (int d = 0; d < D; ++d)
+            for (size_t q = 0; q < dev[(size_t)d].idx.size(); ++q) status[(size_t)dev[(size_t)d].idx[q]] = dev[(size_t)d].cs.status[q];
+        const double* h = ctx->subs[0]->h_results;
+        double mx = ninf;
+        int worst = TB_OK;
+        for (int64_t i = 0; i < n; ++i) {
+            const double ri = r ? r[i] : 0.0;
+            double v;
+            if (nets[i].n_leaves == 0) v = ri;
+            else if (status[(size_t)i] != TB_OK) {
+                v = std::numeric_limits<double>::quiet_NaN();
+                worst = status[(size_t)i];
+            } else v = h[i] + ri;
+            out_values[i] = v;
+            if (out_status) out_status[i] = status[(size_t)i];
+            if (status[(size_t)i] == TB_OK && v > mx) mx = v;
+        }
+        if (out_max) *out_max = mx;
+        if (worst != TB_OK) rc = set_err(ctx, worst, "one or more branches failed (see per-branch status): arena too small");
+    }
+    for (int d = 0; d < D; ++d) {
+        cudaSetDevice(ctx->subs[(size_t)d]->device);
+        release_temporary_plans(ctx->subs[(size_t)d], std::move(dev[(size_t)d].cs.plans));
+    }
+    multi_aggregate(ctx, t0);
+    return rc;
+}
+
+// resident plans on a multi-GPU context: a plan stays on the device it first ran on; new plans are dealt longest-first
+int multi_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, int64_t n, double* out_values, int32_t* out_status,
+                         double* out_max) {
+    const int D = (int)ctx->subs.size();
+    const double t0 = now_ms();
+    std::vector<int> owner((size_t)n, -1);
+    std::vector<double> cost((size_t)n, 0.0), load((size_t)D, 0.0);
+    std::vector<int64_t> fresh;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!plans[i]) continue;
+        cost[(size_t)i] = plans[i]->p.stats.ops;
+        if (plans[i]->p.d_blob && plans[i]->p.owner) {
+            int d = 0;
+            while (d < D && ctx->subs[(size_t)d] != plans[i]->p.owner) ++d;
+            if (d == D) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan is resident on a different context");
+            owner[(size_t)i] = d;
+            load[(size_t)d] += cost[(size_t)i];
+        } else fresh.push_back(i);
+    }
+    lpt_assign(cost, fresh, load, owner);
+    struct Dev {
+        std::vector<int64_t> idx;
+        std::vector<tb_plan*> plans;
+        std::vector<int32_t> status;
+        int rc = TB_OK;
+    };
+    std::vector<Dev> dev((size_t)D);
+    for (int64_t i = 0; i < n; ++i)
+        if (plans[i]) {
+            dev[(size_t)owner[(size_t)i]].idx.push_back(i);
+            dev[(size_t)owner[(size_t)i]].plans.push_back(plans[i]);
+        }
+    {
+        std::vector<std::thread> th;
+        for (int d = 0; d < D; ++d)
+            th.emplace_back([&, d] {
+                tb_ctx* sub = ctx->subs[(size_t)d];
+                Dev& dv = dev[(size_t)d];
+                try {
+                    cudaSetDevice(sub->device);
+                    sub->index_map = dv.idx.data();
+                    sub->prefill_results = true;
+                    dv.rc = batch_enqueue(sub, dv.plans.data(), (int64_t)dv.plans.size(), std::max<int64_t>(n, 1), dv.status, false);
+                } catch (...) {
+                    dv.rc = exception_to_status(sub);
+                }
+                sub->index_map = nullptr;
+                sub->prefill_results = false;
+            });
+        for (auto& t : th) t.join();
+    }
+    int rc = TB_OK;
+    for (int d = 0; d < D; ++d)
+        if (dev[(size_t)d].rc && !rc) rc = set_err(ctx, dev[(size_t)d].rc, "device " + std::to_string(ctx->subs[(size_t)d]->device) + ": " + ctx->subs[(size_t)d]->last_error);
+    if (rc == TB_OK) rc = multi_combine(ctx, n);
+    else
+        for (tb_ctx* sub : ctx->subs) {
+            cudaSetDevice(sub->device);
+            sync_all_lanes(sub);
+        }
+    if (rc == TB_OK) {
+        std::vector<int32_t> status((size_t)n, TB_OK);
+        for (int d = 0; d < D; ++d)
+            for (size_t q = 0; q < dev[(size_t)d].idx.size(); ++q) status[(size_t)dev[(size_t)d].idx[q]] = dev[(size_t)d].status[q];
+        const double* h = ctx->subs[0]->h_results;
+        double mx = -std::numeric_limits<double>::infinity();
+        int worst = TB_OK;
+        for (int64_t i = 0; i < n; ++i) {
+            const double ri = r ? r[i] : 0.0;
+            double v;
+            if (!plans[i]) v = ri;
+            else if (status[(size_t)i] != TB_OK) {
+                v = std::numeric_limits<double>::quiet_NaN();
+                worst = status[(size_t)i];
+            } else v = h[i] + ri;
+            out_values[i] = v;
+            if (out_status) out_status[i] = status[(size_t)i];
+            if (status[(size_t)i] == TB_OK && v > mx) mx = v;
+        }
+        if (out_max) *out_max = mx;
+        if (worst != TB_OK) rc = set_err(ctx, worst, "one or more branches failed (see per-branch status): arena too small");
+    }
+    multi_aggregate(ctx, t0);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, int64_t n, double* out_values,
+                         int32_t* out_status, double* out_max) try {
+    if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (n < 0 || (n > 0 && (!nets || !out_values))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad arguments");
+    if (!ctx->subs.empty()) return multi_contract_networks(ctx, nets, r, n, out_values, out_status, out_max);
+    NetworksCall cs;
+    int rc = networks_enqueue(ctx, nets, n, n, cs);
+    if (rc == TB_OK) rc = finish_call(ctx, cs.plans.data(), r, n, cs.status, out_values, out_status, out_max, cs.any);
     else sync_all_lanes(ctx);
     const double t_d0 = now_ms();
-    release_temporary_plans(ctx, std::move(plans));
+    release_temporary_plans(ctx, std::move(cs.plans));
     ctx->host_ms[4] = now_ms() - t_d0;
-    ctx->host_ms[5] = now_ms() - t_c0;
+    ctx->host_ms[5] = now_ms() - cs.t_c0;
     return rc;
 } TB_CATCH(ctx)
 
 int tb_stream_begin(tb_ctx* ctx, int64_t capacity, tb_stream** out_stream) try {
     if (!ctx || !out_stream) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / out_stream is NULL");
+    if (!ctx->subs.empty()) return tb_stream_begin(ctx->subs[0], capacity, out_stream);  // streams run on the first device
     *out_stream = nullptr;
     if (capacity < 1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "capacity must be >= 1");
     int rc = begin_call(ctx, capacity);
@@ -1298,6 +1977,19 @@ int tb_stream_finish(tb_stream* s, double* out_values, int32_t* out_status, int6
 int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced, int64_t first,
                        int64_t count, double r, double* out_values, int32_t* out_status, double* out_max) try {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (!ctx->subs.empty()) {
+        if (n_sliced < 0 || n_sliced > 40 || first < 0 || count < 0 || first + count > ((int64_t)1 << n_sliced))
+            return set_err(ctx, TB_ERR_BAD_ARGUMENT, "assignment range outside [0, 2^n_sliced)");
+        return multi_contract_sliced(ctx, net, sliced_labels, n_sliced, first, count, r, out_values, out_status, out_max);
+    }
+    return contract_sliced_single(ctx, net, sliced_labels, n_sliced, first, count, r, out_values, out_status, out_max);
+} TB_CATCH(ctx)
+
+}  // extern "C"
+
+namespace {
+int contract_sliced_single(tb_ctx* ctx, const tb_network* net, const int32_t* sliced_labels, int32_t n_sliced, int64_t first,
+                           int64_t count, double r, double* out_values, int32_t* out_status, double* out_max) {
     if (!net || net->n_leaves < 1) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL or empty");
     if (net->n_fixed != 0) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "the network of tb_contract_sliced must not carry fixed labels itself");
     if (n_sliced < 0 || n_sliced > 40 || (n_sliced > 0 && !sliced_labels)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad sliced labels (0 <= n_sliced <= 40)");
@@ -1380,7 +2072,10 @@ int tb_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sliced
     if (out_status) std::memcpy(out_status, stat.data(), (size_t)count * sizeof(int32_t));
     if (out_max) *out_max = mx;
     return rc;
-} TB_CATCH(ctx)
+}
+}  // namespace
+
+extern "C" {
 
 int tb_plan_reassign(const tb_plan* base, const uint8_t* fixed_values, tb_plan** out_plan) try {
     if (!base || !fixed_values || !out_plan) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "base / fixed_values / out_plan is NULL");
@@ -1404,6 +2099,7 @@ int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap, int32_t* out_labels,
                         int32_t* out_rank) try {
     if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
+    if (!ctx->subs.empty()) return tb_plan_read_tensor(ctx->subs[0], plan, node, out_data, cap, out_labels, out_rank);
     const Plan& P = plan->p;
     if (!(P.flags & TB_PLAN_KEEP_INTERMEDIATES)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan was not created with TB_PLAN_KEEP_INTERMEDIATES");
     if (node < 0 || node >= P.n_tensors || P.loc[node] != LOC_ARENA)
@@ -1420,6 +2116,7 @@ int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_da
 
 int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels, int32_t* out_rank) try {
     if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
+    if (!ctx->subs.empty()) return tb_contract_tensor(ctx->subs[0], plan, out_data, cap, out_labels, out_rank);
     const Plan& P = plan->p;
     const int rank = P.rank(P.root_id);
     if (out_rank) *out_rank = rank;
@@ -1444,6 +2141,7 @@ int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launch
 
 int tb_set_stream(tb_ctx* ctx, void* cuda_stream) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
+    if (!ctx->subs.empty()) return set_err(ctx, TB_ERR_UNSUPPORTED, "tb_set_stream needs a single-device context (a stream belongs to one device)");
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1454,7 +2152,14 @@ int tb_set_stream(tb_ctx* ctx, void* cuda_stream) {
 
 int tb_profile(tb_ctx* ctx, int enable) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
-    ctx->profile = enable != 0;
+    ctx->profile_mode = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+    for (tb_ctx* sub : ctx->subs) sub->profile_mode = ctx->profile_mode;
+    return TB_OK;
+}
+
+int tb_last_profile_union(const tb_ctx* ctx, double* ms_by_kind) {
+    if (!ctx || !ms_by_kind) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "NULL argument");
+    for (int q = 0; q < 4; ++q) ms_by_kind[q] = ctx->prof_union_ms[q];
     return TB_OK;
 }
 
@@ -1482,6 +2187,7 @@ int tb_last_transfers(const tb_ctx* ctx, int64_t* h2d_bytes, int64_t* d2h_bytes)
 
 int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const int32_t* perm) try {
     if (!ctx || !in || !out || !perm) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "NULL argument");
+    if (!ctx->subs.empty()) return tb_permute_bits(ctx->subs[0], in, out, rank, perm);
     if (rank < 0 || rank > 31) return set_err(ctx, TB_ERR_UNSUPPORTED, "rank must be in [0, 31]");
     std::vector<int> dst_of_src(rank, -1);
     for (int i = 0; i < rank; ++i) {

@@ -217,23 +217,23 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_subtrees(const SubInst*
 // ------------------------------------------------------------------------------------------------
 constexpr int BIG_THREADS = 256;
 
-template <typename T>
-__global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __restrict__ insts,
-                                                         const uint32_t* __restrict__ tile_starts, int n_insts) {
-    __shared__ BigStep sd;
-    __shared__ T s_red[BIG_THREADS];
-    TL_BEGIN
-    const int tid = threadIdx.x;
-    const int idx = find_inst(tile_starts, n_insts, blockIdx.x);
-    const BigInst inst = insts[idx];
-    const uint32_t tile = blockIdx.x - __ldg(tile_starts + idx);
-    if (tid < (int)(sizeof(BigStep) / 4)) reinterpret_cast<uint32_t*>(&sd)[tid] = __ldg(reinterpret_cast<const uint32_t*>(inst.step) + tid);
-    __syncthreads();
-    const T* pool = reinterpret_cast<const T*>(inst.pool);
-    T* arena = reinterpret_cast<T*>(inst.arena);
-    const T* __restrict__ A = (sd.a_loc == LOC_POOL ? pool : arena) + sd.a_off;
-    const T* __restrict__ B = (sd.b_loc == LOC_POOL ? pool : arena) + sd.b_off;
-    T* __restrict__ C = arena + sd.c_off;
+// One CTA-sized piece ("tile") of a generic step: 256 threads.  Shared by the stand-alone kernel (level-synchronous
+// launches) and by the consumer warps of the persistent GEMM kernels (dataflow launches, PERSIST: the 256 consumer
+// threads synchronise on named barrier 1 instead of __syncthreads).
+template <bool PERSIST> __device__ __forceinline__ void generic_sync() {
+    if (PERSIST) asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    else __syncthreads();
+}
+
+template <typename T, bool PERSIST>
+__device__ __forceinline__ void generic_tile(const BigStep& sd, const void* poolp, void* arenap, uint32_t tile, int tid, T* s_red) {
+    const T* pool = reinterpret_cast<const T*>(poolp);
+    T* arena = reinterpret_cast<T*>(arenap);
+    // no __restrict__ / read-only qualifiers on the operands: inside a dataflow launch they were written by other CTAs of
+    // the SAME kernel, so the non-coherent load path (LDG.CONSTANT) must never be used for them
+    const T* A = (sd.a_loc == LOC_POOL ? pool : arena) + sd.a_off;
+    const T* B = (sd.b_loc == LOC_POOL ? pool : arena) + sd.b_off;
+    T* C = arena + sd.c_off;
     const int rc = sd.rc, nk = sd.nk, nka = sd.nka, ks = sd.ks, po = sd.po;
     const int nkt = nk + nka + sd.nkb;
     if (sd.vec4) {
@@ -301,7 +301,6 @@ __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __res
         };
         if (po == 12) vectors(std::integral_constant<int, 4>{});
         else vectors(std::integral_constant<int, 1>{});
-        TL_END(insts, 1u, tid == 0)
         return;
     }
     // thread -> (output, k-part): 2^po outputs per CTA, 2^ks threads share one output
@@ -347,16 +346,31 @@ __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __res
     } else {
         // tree reduction over the k-parts (uniform trip count: ks is per-CTA)
         s_red[tid] = acc;
-        __syncthreads();
+        generic_sync<PERSIST>();
         for (int s = ks - 1; s >= 0; --s) {
             if (kp < (1u << s)) {
                 acc = Ops<T>::vmax(acc, s_red[tid + ((1u << s) << po)]);
                 s_red[tid] = acc;
             }
-            __syncthreads();
+            generic_sync<PERSIST>();
         }
         if (kp == 0) C[c] = acc;
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __restrict__ insts,
+                                                         const uint32_t* __restrict__ tile_starts, int n_insts) {
+    __shared__ BigStep sd;
+    __shared__ T s_red[BIG_THREADS];
+    TL_BEGIN
+    const int tid = threadIdx.x;
+    const int idx = find_inst(tile_starts, n_insts, blockIdx.x);
+    const BigInst inst = insts[idx];
+    const uint32_t tile = blockIdx.x - __ldg(tile_starts + idx);
+    if (tid < (int)(sizeof(BigStep) / 4)) reinterpret_cast<uint32_t*>(&sd)[tid] = __ldg(reinterpret_cast<const uint32_t*>(inst.step) + tid);
+    __syncthreads();
+    generic_tile<T, false>(sd, inst.pool, inst.arena, tile, tid, s_red);
     TL_END(insts, 1u, tid == 0)
 }
 
@@ -537,6 +551,12 @@ struct TileInfo {
     unsigned char c_shift[16];
     unsigned char e_spos[12], e_cs[12];  // staged epilogue: sorted in-round tile bits -> staging position / C shift
     unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast;
+    // dataflow launches (see TileInfoH)
+    int kind;
+    uint32_t tile;
+    const void* pool;
+    void* arena;
+    unsigned int* done;
 };
 
 // bank swizzle of the epilogue staging index: permutes 16-byte chunks inside a 128-byte row
@@ -552,6 +572,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
                  : "memory");
 }
+// spin limit of every in-kernel wait (~20 s at 1.97 GHz): in a dataflow launch a wait may legitimately last as long as the
+// producing node runs (BASELINE config 4: ~0.1 s); anything beyond the limit is a lost arrival and traps instead of hanging
+constexpr long long kSpinTimeoutClocks = 40000000000ll;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
     unsigned done = 0;
@@ -566,13 +589,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done) {  // a lost arrival must fail loudly (~2 s), never hang the GPU
+        if (!done) {  // a lost arrival must fail loudly, never hang the GPU
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) __trap();
+            else if (now - t0 > kSpinTimeoutClocks) __trap();
         }
     }
 }
+
+// ---- dataflow launches: completion counters in global memory.  done[i] starts at (tiles of instance i) x (consumer warps
+// per CTA) and every consumer warp decrements it once per finished tile (release); the producer warp of a CTA that has
+// been handed a tile of a dependent instance spins until the counters of both operands' producers read 0 (acquire).
+// Tiles are handed out in topological order by ONE atomic counter, so whatever a spinning CTA waits for has already
+// been handed to a CTA that is running (or finished): no co-residency assumption, no deadlock.
+__device__ __forceinline__ void dep_wait(const unsigned int* p) {
+    long long t0 = 0;
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+        if (v == 0) return;
+        __nanosleep(64);
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > kSpinTimeoutClocks) __trap();
+    }
+}
+// Called by the SIGNAL warp of a CTA once all consumer warps have arrived on the tile's bar_sig mbarrier (their global
+// stores of the tile happen-before the arrival, CTA scope): the gpu-scope fence is cumulative over them, then one relaxed
+// decrement by the number of consumer warps publishes the tile.  The consumer warps themselves never wait for their
+// stores to be acknowledged -- they are already in the next tile's main loop.
+__device__ __forceinline__ void dep_signal(unsigned int* p, unsigned n) {
+    asm volatile("fence.acq_rel.gpu;\n" ::: "memory");
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;\n" ::"l"(p), "r"(0u - n) : "memory");
+}
+// the producer warp reads, with TMA (async proxy), global memory that other CTAs of the same kernel wrote with ordinary
+// stores (generic proxy): cross-proxy fence between the acquire above and the bulk copies below
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                      (unsigned)__cvta_generic_to_shared(smem_dst)),
@@ -588,13 +640,14 @@ static_assert(128 * 32 + 256 * 104 <= 384 * 80, "setmaxnreg budget of k_gemm2h e
 template <typename T>
 __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter,
-                                                         int staged_epilogue) {
+                                                         int staged_epilogue, unsigned int* done) {
     typedef typename Ops<T>::vec4 vec4;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);
     T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);
-    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[2], bar_tempty[2], bar_sig[2];
     __shared__ TileInfo tinfo[2];
+    __shared__ __align__(16) BigStep s_gstep[2];  // generic tiles: the descriptor the consumers execute
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < G2_STAGES; ++i) {
@@ -603,7 +656,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], G2_CONSUMERS / 32);
+            mbar_init(&bar_tempty[i], 1);                  // the signal warp hands the slot back
+            mbar_init(&bar_sig[i], G2_CONSUMERS / 32);     // every consumer warp is done with the tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -612,9 +666,24 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
     if (tid < G2_PRODUCERS) {
         // ------------------------------------------------------------------ producer warpgroup
         asm volatile("setmaxnreg.dec.sync.aligned.u32 24;\n" ::);
-        if (tid >= 32) return;
+        if (tid >= 64) return;
+        if (tid >= 32) {
+            // ------------------------------------------------------------------ signal warp: publishes finished tiles
+            if (tid != 32) return;
+            for (unsigned tcount = 0;; ++tcount) {
+                const int slot = tcount & 1;
+                mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
+                if (!tinfo[slot].valid) break;
+                unsigned int* const dp = tinfo[slot].done;
+                mbar_wait(&bar_sig[slot], (tcount >> 1) & 1);
+                if (dp) dep_signal(dp, G2_CONSUMERS / 32);
+                mbar_arrive(&bar_tempty[slot]);
+            }
+            return;
+        }
         const int lane = tid;
         unsigned it = 0;  // global chunk counter (ring position)
+        int waited_idx = -1;  // dataflow: the instance whose operands this warp has already waited for
         for (unsigned tcount = 0;; ++tcount) {
             unsigned tile_g = 0;
             if (lane == 0) tile_g = atomicAdd(counter, 1u);
@@ -632,6 +701,32 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
             const BigInst inst = insts[idx];
             const uint32_t tile = tile_g - __ldg(tile_starts + idx);
             const BigStep* __restrict__ d = inst.step;
+            if (done && idx != waited_idx) {  // dataflow launch: both operands must be complete before anything of this instance is read
+                if (lane < 2) {  // both operands' counters are polled concurrently
+                    const int dep = lane ? inst.dep_b : inst.dep_a;
+                    if (dep >= 0) dep_wait(done + dep);
+                }
+                __syncwarp();
+                fence_proxy_async();
+                waited_idx = idx;
+            }
+            if (d->kind != KIND_GEMM) {  // a generic step's tile: hand the descriptor to the consumer warps
+                TileInfo& tg = tinfo[slot];
+                uint32_t* gd = reinterpret_cast<uint32_t*>(&s_gstep[slot]);
+                const uint32_t* gs = reinterpret_cast<const uint32_t*>(d);
+                for (int w = lane; w < (int)(sizeof(BigStep) / 4); w += 32) gd[w] = __ldg(gs + w);
+                if (lane == 0) {
+                    tg.kind = KIND_GENERIC;
+                    tg.tile = tile;
+                    tg.pool = inst.pool;
+                    tg.arena = inst.arena;
+                    tg.done = done ? done + idx : nullptr;
+                    tg.valid = 1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tfull[slot]);
+                continue;
+            }
             const int tm = d->tm, tn = d->tn, nk = d->nk, kc = d->kc, ng = d->ng;
             const int s_log = 8 - (tm + tn - 6), S = 1 << s_log;
             const T* Ag = reinterpret_cast<const T*>(inst.arena) + d->a_off;
@@ -668,6 +763,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 ti.e_cs_ntop = d->a_shift[31];
                 ti.e_vec = d->b_shift[31];
                 ti.e_fast = d->b_shift[30];
+                ti.kind = KIND_GEMM;
+                ti.done = done ? done + idx : nullptr;
                 ti.valid = 1;
             }
             __syncwarp();
@@ -702,6 +799,12 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
         mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
         const TileInfo& ti = tinfo[slot];
         if (!ti.valid) break;
+        if (ti.kind != KIND_GEMM) {
+            generic_tile<T, true>(s_gstep[slot], ti.pool, ti.arena, ti.tile, ctid, stg_mem);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_sig[slot]);
+            continue;
+        }
         const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
         const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
         const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
@@ -832,7 +935,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+            if (lane == 0) mbar_arrive(&bar_sig[slot]);
             continue;
         }
         const long long cbase = ti.cbase[sub];
@@ -879,7 +982,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+        if (lane == 0) mbar_arrive(&bar_sig[slot]);
     }
 }
 
@@ -904,19 +1007,28 @@ struct TileInfoH {
     unsigned char e_spos[14], e_cs[14];
     unsigned char e_cs_mtop, e_cs_ntop, e_vec, e_fast, mp, mswap;
     int inst;  // index of the (branch, step) instance in this launch: consumers cache per-step values on it
+    // dataflow launches
+    int kind;               // KIND_GEMM, or KIND_GENERIC: the consumer warps run generic_tile on s_gstep[slot]
+    uint32_t tile;          // generic: index of this tile inside its instance
+    const void* pool;       // generic: leaf pool / arena of the branch
+    void* arena;
+    unsigned int* done;     // completion counter of the instance (nullptr: level-synchronous launch)
 };
 __device__ __forceinline__ uint32_t stg_swz_h(uint32_t x) { return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7u) << 3); }
 
 __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
-                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter) {
+                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter,
+                                                          unsigned int* done) {
     typedef int16_t T;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);                       // G2_STAGES x 16 KB
     T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);         // 2 x 16 KB
     constexpr int STAGE_ELEMS = GEMM_STAGE_ELEMS * 2;                    // int16 elements per stage
-    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[G2H_TSLOTS], bar_tempty[G2H_TSLOTS];
+    __shared__ __align__(8) uint64_t bar_full[G2_STAGES], bar_empty[G2_STAGES], bar_tfull[G2H_TSLOTS], bar_tempty[G2H_TSLOTS],
+        bar_sig[G2H_TSLOTS];
     __shared__ TileInfoH tinfo[G2H_TSLOTS];
     __shared__ __align__(16) BigStep s_step;  // the producer's copy of the current step descriptor
+    __shared__ __align__(16) BigStep s_gstep[G2H_TSLOTS];  // generic tiles: the descriptor the consumers execute
     const int tid = threadIdx.x;
     if (tid == 0) {
         for (int i = 0; i < G2_STAGES; ++i) {
@@ -925,7 +1037,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         }
         for (int i = 0; i < G2H_TSLOTS; ++i) {
             mbar_init(&bar_tfull[i], 1);
-            mbar_init(&bar_tempty[i], G2_CONSUMERS / 32);
+            mbar_init(&bar_tempty[i], 1);                  // the signal warp hands the slot back
+            mbar_init(&bar_sig[i], G2_CONSUMERS / 32);     // every consumer warp is done with the tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -933,7 +1046,22 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
 
     if (tid < G2_PRODUCERS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n" ::);
-        if (tid >= 32) return;
+        if (tid >= 64) return;
+        if (tid >= 32) {
+            // ------------------------------------------------------------------ signal warp: publishes finished tiles
+            if (tid != 32) return;
+            for (unsigned tcount = 0;; ++tcount) {
+                const int slot = tcount % G2H_TSLOTS;
+                const unsigned par = (tcount / G2H_TSLOTS) & 1;
+                mbar_wait(&bar_tfull[slot], par);
+                if (!tinfo[slot].valid) break;
+                unsigned int* const dp = tinfo[slot].done;
+                mbar_wait(&bar_sig[slot], par);
+                if (dp) dep_signal(dp, G2_CONSUMERS / 32);
+                mbar_arrive(&bar_tempty[slot]);
+            }
+            return;
+        }
         const int lane = tid;
         unsigned it = 0;
         // the tile counter is read one tile ahead (the atomic's latency overlaps the current tile's set-up), and the
@@ -943,6 +1071,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         uint32_t cur_start = 1, cur_end = 0;  // tile range of the cached instance (empty)
         int cur_idx = -1;
         const unsigned char* cur_arena = nullptr;
+        const void* cur_pool = nullptr;
         for (unsigned tcount = 0;; ++tcount) {
             const unsigned tile_g = __shfl_sync(0xffffffffu, tile_next, 0);
             if (lane == 0 && tile_g < total_tiles) tile_next = atomicAdd(counter, 1u) + gridDim.x;
@@ -960,16 +1089,43 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 const BigInst inst = insts[cur_idx];
                 cur_start = __ldg(tile_starts + cur_idx);
                 cur_arena = reinterpret_cast<const unsigned char*>(inst.arena);
+                cur_pool = inst.pool;
                 const uint32_t* gs = reinterpret_cast<const uint32_t*>(inst.step);
                 uint32_t* ss = reinterpret_cast<uint32_t*>(&s_step);
                 for (int w = lane; w < (int)(sizeof(BigStep) / 4); w += 32) ss[w] = __ldg(gs + w);
                 __syncwarp();
                 cur_end = cur_start + s_step.n_tiles;
+                if (done) {  // dataflow launch: both operands must be complete before anything of this instance is read
+                    if (lane < 2) {  // both operands' counters are polled concurrently
+                        const int dep = lane ? inst.dep_b : inst.dep_a;
+                        if (dep >= 0) dep_wait(done + dep);
+                    }
+                    __syncwarp();
+                    fence_proxy_async();
+                }
             }
             const int idx = cur_idx;
             const uint32_t tile = tile_g - cur_start;
             const BigStep* d = &s_step;
             const unsigned char* arena = cur_arena;
+            if (d->kind != KIND_GEMM) {  // a generic step's tile: hand the descriptor to the consumer warps, nothing to stage
+                TileInfoH& tg = tinfo[slot];
+                uint32_t* gd = reinterpret_cast<uint32_t*>(&s_gstep[slot]);
+                const uint32_t* ss = reinterpret_cast<const uint32_t*>(&s_step);
+                for (int w = lane; w < (int)(sizeof(BigStep) / 4); w += 32) gd[w] = ss[w];
+                if (lane == 0) {
+                    tg.kind = KIND_GENERIC;
+                    tg.tile = tile;
+                    tg.pool = cur_pool;
+                    tg.arena = const_cast<unsigned char*>(arena);
+                    tg.done = done ? done + idx : nullptr;
+                    tg.inst = idx;
+                    tg.valid = 1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_tfull[slot]);
+                continue;
+            }
             const int tm = d->tm, tn = d->tn, nk = d->nk, kc = d->kc, ng = d->ng;
             const int s_log = 8 - (tm + tn - 6), S = 1 << s_log;
             const T* Ag = reinterpret_cast<const T*>(arena) + d->a_off;
@@ -1007,6 +1163,8 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                 ti.mp = d->a_shift[29];
                 ti.mswap = d->b_shift[29];
                 ti.inst = idx;
+                ti.kind = KIND_GEMM;
+                ti.done = done ? done + idx : nullptr;
                 ti.valid = 1;
             }
             __syncwarp();
@@ -1051,6 +1209,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         KP(0)
         const TileInfoH& ti = tinfo[slot];
         if (!ti.valid) break;
+        if (ti.kind != KIND_GEMM) {
+            generic_tile<T, true>(s_gstep[slot], ti.pool, ti.arena, ti.tile, ctid, stg_mem);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_sig[slot]);
+            KP(3)
+            continue;
+        }
         const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
         const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
         const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
@@ -1289,7 +1454,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_tempty[slot]);
+        if (lane == 0) mbar_arrive(&bar_sig[slot]);
         KP(3)
 #ifdef TB_KPROF
         ++kp_tiles;
@@ -1318,6 +1483,12 @@ template <typename T>
 __global__ void k_finalize(const FinalInst* __restrict__ f, int n, double* __restrict__ results) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) results[f[i].out_index] = Ops<T>::to_double(*reinterpret_cast<const T*>(f[i].src));
+}
+
+// multi-GPU calls: every device's result vector starts as -inf so that ONE all-reduce(max) assembles the per-branch vector
+__global__ void k_fill_double(double* __restrict__ dst, int64_t n, double v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
 }
 
 template <typename T>

@@ -131,8 +131,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     auto last_ = std::chrono::steady_clock::now();
 #endif
     const bool temporary = (extra_flags & TB_PLAN_TEMPORARY) != 0;
-    extra_flags &= ~TB_PLAN_TEMPORARY;
-    P.flags = (net.flags & ~TB_PLAN_TEMPORARY) | extra_flags;
+    const bool estimate_only = (extra_flags & TB_PLAN_ESTIMATE_ONLY) != 0;
+    extra_flags &= ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY);
+    P.flags = (net.flags & ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY)) | extra_flags;
     if (P.flags & TB_PLAN_KEEP_INTERMEDIATES) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;
     P.n_labels = net.n_labels;
     const bool synth = (net.n_leaves == 1);
@@ -314,6 +315,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
 
     PT(1, "positions")
     // ---- label sets bottom-up (ids of the given tree are already topological); sets are sorted
+    double est_ops = 0;  // sum over nodes of 2^(labels involved): the reference's 2^tc (src/types.jl:120)
+    int est_sc = 0;
+    for (int i = 0; i < nL; ++i) est_sc = std::max(est_sc, (int)lab_n[i]);
     for (int t = nL; t < nT0; ++t) {
         const int A = lch[t], B = rch[t];
         const int na = lab_n[A], nb = lab_n[B];
@@ -346,6 +350,17 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         if (no > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(no) + " > 31");
         if (nu - no > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
         lab_n[t] = (uint8_t)no;
+        est_ops += std::ldexp(1.0, nu);
+        est_sc = std::max(est_sc, no);
+    }
+    if (estimate_only) {
+        P.stats = tb_plan_stats{};
+        P.stats.ops = est_ops;
+        P.stats.tc = est_ops > 0 ? std::log2(est_ops) : 0;
+        P.stats.sc = est_sc;
+        P.stats.n_nodes = nN;
+        P.stats.value_type = vt;
+        return TB_OK;
     }
 
     // ---- the reference's memory estimators on the GIVEN tree (before any rewrite), in elements, all label sizes 2:
@@ -847,24 +862,61 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     }
 
     PT(7, "kinds")
-    // ---- arena allocation by level intervals
+    // ---- arena allocation, safe for the dataflow executor: the only ordering between steps is operand -> consumer, so a
+    //      node's output may overlap ONLY tensors that are dead once the node's operands are complete: the interior of its
+    //      own subtree (everything below its two operands).  Sibling subtrees run concurrently and never share memory;
+    //      fused-subtree roots (level 0, all produced by one launch) get fresh blocks.  Post-order walk; every tensor hands
+    //      the free blocks of its subtree up to its consumer.
     {
-        std::vector<std::vector<int>> born(P.n_levels + 1), dies(P.n_levels + 2);
-        for (int t : topo) {
-            if (P.level[t] < 0) continue;
-            born[P.level[t]].push_back(t);
-            if (t != root) dies[P.level[parent[t]]].push_back(t);
-        }
-        FreeList fl;
+        typedef std::vector<std::pair<int64_t, int64_t>> Blocks;  // (offset, size), sorted by offset, coalesced
+        std::vector<Blocks> after(nT);  // free blocks inside the subtree of t once t is complete (t's own block excluded)
         const bool keep = (P.flags & TB_PLAN_KEEP_INTERMEDIATES) != 0;
-        for (int lv = 0; lv <= P.n_levels; ++lv) {
-            auto& bs = born[lv];
-            std::sort(bs.begin(), bs.end(), [&](int x, int y) { return size_of(x) != size_of(y) ? size_of(x) > size_of(y) : x < y; });
-            for (int t : bs) P.off[t] = fl.alloc(align_up(size_of(t), 64));
-            if (!keep)
-                for (int t : dies[lv]) fl.release(P.off[t], align_up(size_of(t), 64));
+        int64_t top = 0;
+        auto insert_block = [](Blocks& bl, int64_t o, int64_t sz) {
+            auto it = std::lower_bound(bl.begin(), bl.end(), std::make_pair(o, (int64_t)0));
+            it = bl.insert(it, {o, sz});
+            auto nx = it + 1;
+            if (nx != bl.end() && it->first + it->second == nx->first) {
+                it->second += nx->second;
+                bl.erase(nx);
+            }
+            if (it != bl.begin()) {
+                auto pv = it - 1;
+                if (pv->first + pv->second == it->first) {
+                    pv->second += it->second;
+                    bl.erase(it);
+                }
+            }
+        };
+        for (int t : topo) {
+            if (P.level[t] < 0) continue;  // interior of a fused subtree: shared memory
+            const int64_t need = align_up(size_of(t), 64);
+            Blocks pool;
+            if (!keep && kind[t] != KIND_FUSED)
+                for (int c : {lch[t], rch[t]})
+                    if (!leaf[c] && P.level[c] >= 0) {
+                        for (const auto& bk : after[c]) insert_block(pool, bk.first, bk.second);
+                        Blocks().swap(after[c]);
+                    }
+            // best fit inside the subtree's dead interior, else a fresh block at the top of the arena
+            int best = -1;
+            for (int i = 0; i < (int)pool.size(); ++i)
+                if (pool[(size_t)i].second >= need && (best < 0 || pool[(size_t)i].second < pool[(size_t)best].second)) best = i;
+            if (best >= 0) {
+                P.off[t] = pool[(size_t)best].first;
+                pool[(size_t)best].first += need;
+                pool[(size_t)best].second -= need;
+                if (pool[(size_t)best].second == 0) pool.erase(pool.begin() + best);
+            } else {
+                P.off[t] = top;
+                top += need;
+            }
+            if (!keep && kind[t] != KIND_FUSED)
+                for (int c : {lch[t], rch[t]})
+                    if (!leaf[c] && P.level[c] >= 0) insert_block(pool, P.off[c], align_up(size_of(c), 64));
+            after[t].swap(pool);
         }
-        P.arena_elems = fl.top;
+        P.arena_elems = top;
         P.root_off = P.off[root];
     }
 
@@ -1014,6 +1066,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) order.push_back(t);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.level[x] < P.level[y]; });
         P.big_level_begin.assign(P.n_levels + 2, 0);
+        std::vector<int32_t> big_index(nT, -1);  // node -> its position in big_steps (dependencies of the dataflow executor)
+        P.big_dep_a.reserve(n_big);
+        P.big_dep_b.reserve(n_big);
         for (int t : order) {
             const NodeCls& c = cls[t];
             const int32_t* cd = cls_data.data() + c.off;
@@ -1178,6 +1233,11 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                     s.lane_n_first = n_owns ? 1 : 0;
                 }
             }
+            big_index[t] = (int32_t)P.big_steps.size();
+            P.big_log2_ops.push_back((float)(rank_of(t) + c.nk + c.nka + c.nkb));
+            P.big_bytes.push_back((half ? 2.0 : 4.0) * (std::ldexp(1.0, rank_of(A)) + std::ldexp(1.0, rank_of(B)) + std::ldexp(1.0, rank_of(t))));
+            P.big_dep_a.push_back(big_index[A]);  // -1 for leaves and fused subtrees
+            P.big_dep_b.push_back(big_index[B]);
             P.big_steps.push_back(s);
             if (!temporary) P.recs.push_back(rec_of(t, kind[t], P.level[t]));
             account(t, kind[t]);

@@ -50,6 +50,10 @@ struct Plan {
     std::vector<SubTree> subtrees;
     std::vector<BigStep> big_steps;        // sorted by level (levels start at 1)
     std::vector<int32_t> big_level_begin;  // big_steps index where level L starts, size n_levels + 2
+    std::vector<float> big_log2_ops;  // per big step: log2 of its tropical ops (per-launch roofline records)
+    std::vector<double> big_bytes;    // per big step: bytes it moves (operands read once + result written once)
+    std::vector<int32_t> big_dep_a, big_dep_b;  // per big step: index of the big step producing operand A / B, -1 = leaf pool
+                                                // or fused subtree (complete before any big step starts); always < own index
     int n_levels = 0;                      // number of levels with big steps (levels 1..n_levels)
     int64_t arena_elems = 0;
     int64_t root_off = 0;
@@ -79,6 +83,9 @@ struct Plan {
 // internal flag (never part of the ABI): the plan is a temporary of tb_contract_networks / tb_stream_push -- nobody will
 // ask for its step records or the reference's memory estimators, so they are not computed
 constexpr uint32_t TB_PLAN_TEMPORARY = 1u << 31;
+// internal flag: stop after the label-set pass; only stats.ops / stats.tc / stats.sc are filled (tb_estimate: the cost a
+// sharder needs, at ~1/4 of the price of a full compilation)
+constexpr uint32_t TB_PLAN_ESTIMATE_ONLY = 1u << 30;
 
 // returns a tb_status; on failure `err` holds the message
 int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& plan, std::string& err);

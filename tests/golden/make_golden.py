@@ -76,7 +76,50 @@ def record_sliced_open(name, nv, edges, weights, seed, element_type, k, n_open):
     print(name, "value", whole, "labels", labels, "open", open_labels)
 
 
+def record_baseline(names):
+    """BASELINE.json configs 2-5 as bench.py runs them (bench.WORKLOADS): one value per branch (value + r, what
+    contract_slices returns) from the C oracle, ONCE, so that `pytest -m gpu` can assert bit-equality at full size.
+    Integer-valued workloads run in the oracle's int16 value type (exact, 2-4x faster than f32); a prefix of every
+    workload is cross-checked against the f32 value type (Tropical{Float32}, the reference's element_type).  The record
+    also pins the branch list itself (sha256 over its canonical content, workloads.standin_host.branch_list_hash)."""
+    import time
+
+    import bench
+    from oracle import c_oracle as CO
+
+    for name in names:
+        brs = bench.make_workload(name)
+        t0 = time.time()
+        flats = [None if b.nv == 0 else CO.flatten(b) for b in brs]
+        vals, ops, th = CO.contract_batch(flats, "auto")
+        dt = time.time() - t0
+        r = np.array([float(b.r) for b in brs])
+        n_chk = {"cfg4": 2}.get(name, min(len(brs), 256))
+        v32, _, _ = CO.contract_batch(flats[:n_chk], "f32")
+        assert np.array_equal(v32, vals[:n_chk]), "int16 and f32 value types of the C oracle disagree"
+        rec = dict(workload=name, spec=[bench.WORKLOADS[name][0], bench.WORKLOADS[name][1], bench.WORKLOADS[name][2],
+                                        bench.WORKLOADS[name][3]],
+                   hash=H.branch_list_hash(brs), n=len(brs), values=[float(v) for v in (vals + r)],
+                   total_ops=float(ops.sum()), mis=float((vals + r).max()),
+                   oracle=f"oracle/c/tropical_ref.c value type auto (int16), {CO.simd()}, {th} threads, {dt:.0f} s; first {n_chk} "
+                          "branches also contracted in f32: identical")
+        if name == "cfg3":  # index slices of the single branch: labels chosen without libtbcuda
+            k = bench.DEFAULT_SLICE_K[name]
+            labels = bench.python_slice_labels(brs[0], k)
+            sv, _, _ = CO.contract_index_slices(brs[0], labels, range(1 << k), "auto")
+            feas = set(bench.feasible_assignments(brs[0], labels))
+            rec["sliced_labels"] = [int(l) for l in labels]
+            rec["slice_values"] = [float(v) + float(brs[0].r) if (a in feas and np.isfinite(v)) else None for a, v in enumerate(sv)]
+            assert max(v for v in rec["slice_values"] if v is not None) == rec["values"][0]
+        with open(os.path.join(OUT, f"baseline_{name}.json"), "w") as f:
+            json.dump(rec, f, separators=(",", ":"))
+        print(name, "branches", len(brs), "mis", rec["mis"], f"{dt:.0f}s", flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "baseline":  # full-size values of the BASELINE configs (minutes of CPU)
+        record_baseline(sys.argv[2:] or ["cfg1", "cfg2", "cfg3", "cfg5", "cfg4"])
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "sliced":  # only the index-slicing / open-boundary fixtures
         nv, edges = H.random_regular_graph(60, 3, 5)
         record_sliced_open("rr60_sliced_open_unit", nv, edges, None, 5, np.float32, 4, 5)

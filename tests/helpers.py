@@ -49,3 +49,15 @@ def align_to(labels_src, arr, labels_dst):
     if len(labels_src) == 0:
         return arr
     return np.transpose(arr, [list(labels_src).index(l) for l in labels_dst])
+
+
+def reduce_to(labels_src, arr, labels_dst):
+    """device tensor (axes = labels_src) -> axes labels_dst.  A node whose long reduction was split keeps some of the
+    reduced labels as extra output labels for its consumer to reduce (plan compiler, folded split-K): max over them
+    first -- the reference's node tensor is the fully reduced one."""
+    labels_src = list(labels_src)
+    extra = [i for i, l in enumerate(labels_src) if l not in labels_dst]
+    if extra:
+        arr = arr.max(axis=tuple(extra))
+        labels_src = [l for l in labels_src if l in labels_dst]
+    return align_to(tuple(labels_src), arr, labels_dst)

@@ -160,3 +160,56 @@ def test_memory_estimators_match_reference_formulas(tb, n, seed):
     br = to_sliced(root)
     assert tb.contraction_peak_memory(br) == pytest.approx(want_peak) and tb.contraction_all_memory(br) == pytest.approx(want_all)
     assert want_peak <= want_all + 1 and st.sc <= want_peak
+
+
+def _arena_blocks(plan):
+    """{node: (offset, size, left, right)} of the tensors that live in the HBM arena (non-fused steps + fused-subtree roots)"""
+    steps = plan.steps()
+    parent = {}
+    kind = {}
+    for s in steps:
+        parent[s.left] = s.node
+        parent[s.right] = s.node
+        kind[s.node] = s.kind
+    out = {}
+    for s in steps:
+        in_arena = s.kind != 0 or s.node not in parent or kind[parent[s.node]] != 0
+        if in_arena:
+            out[s.node] = (s.c_offset, (((1 << s.rank_c) + 63) // 64) * 64, s.left, s.right)
+    return out, parent
+
+
+@pytest.mark.parametrize("n,seed,flags", [(100, 7, 0), (130, 5, 0), (150, 1000, 0), (150, 1000, 16), (150, 1000, 8), (120, 9, 64),
+                                          (160, 3, 0), (140, 11, 2)])
+def test_arena_reuse_is_safe_for_the_dataflow_executor(n, seed, flags):
+    """The dataflow executor orders steps ONLY operand -> consumer.  Two arena tensors may therefore share bytes only
+    if one lies in the interior of the other's subtree (strictly below its operands): everything there is dead -- and
+    complete -- once the operands are complete.  Siblings / cousins run concurrently and must be disjoint."""
+    import tbcuda
+    from helpers import regular_root, to_sliced
+    p = tbcuda.Plan(to_sliced(regular_root(n, seed)), flags=flags)
+    blocks, parent = _arena_blocks(p)
+
+    def ancestors(t):
+        out = []
+        while t in parent:
+            t = parent[t]
+            out.append(t)
+        return out
+
+    nodes = sorted(blocks)
+    n_shared = 0
+    for i, x in enumerate(nodes):
+        ox, sx, _, _ = blocks[x]
+        anc = ancestors(x)
+        for y in nodes[i + 1:]:
+            oy, sy, ly, ry = blocks[y]
+            if ox + sx <= oy or oy + sy <= ox:
+                continue
+            n_shared += 1
+            # y was allocated later (children precede parents): x must be strictly below y's operands
+            assert y in anc and x not in (ly, ry), (x, y)
+    assert p.info().arena_elems >= max(o + s for o, s, _, _ in blocks.values())
+    if n >= 130 and not flags:
+        assert n_shared > 0  # reuse does happen
+    p.close()

@@ -420,3 +420,15 @@ def make_root(nv, edges, weights=None, seed=0, ntrials=4) -> Branch:
         if best is None or (sc, tc) < best[0]:
             best = ((sc, tc), tree)
     return Branch(nv=nv, edges=list(edges), weights=weights, ixs=ixs, tree=best[1], r=0)
+
+
+def branch_list_hash(branches: Sequence[Branch]) -> str:
+    """sha256 over the canonical content of a branch list (graph, weights, leaf labels, tree, r): pins the benched /
+    golden workloads to what this (tracked) generator produces, whatever cache file they were loaded from."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for b in branches:
+        h.update(repr((b.nv, [tuple(e) for e in b.edges], None if b.weights is None else [float(x) for x in b.weights],
+                       [tuple(i) for i in b.ixs], b.tree, float(b.r))).encode())
+    return h.hexdigest()
