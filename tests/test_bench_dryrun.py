@@ -60,11 +60,14 @@ class _FakeEngine:
         vals = np.array(vals)
         return vals, np.zeros(len(vals), dtype=np.int32), float(vals.max())
 
-    def profile(self, on=True):
+    def profile(self, mode=1):
         pass
 
     def last_profile(self):
-        return {"fused": (0.1, 1), "generic": (0.1, 1), "gemm": (0.0, 0), "finalize": (0.01, 1)}
+        return {"fused": (0.1, 1), "generic": (0.0, 0), "gemm": (0.2, 1), "finalize": (0.01, 1)}
+
+    def last_profile_union(self):
+        return {"fused": 0.1, "generic": 0.0, "gemm": 0.2, "finalize": 0.01}
 
     def last_timing(self):
         return 0.2, 3
@@ -79,9 +82,10 @@ class _FakeEngine:
         pass
 
 
-@pytest.mark.parametrize("argv", [["--workload", "cfg1", "--steps", "2", "--warmup", "1", "--cpu-budget", "0.2"],
-                                  ["--workload", "cfg1", "--steps", "2", "--slice-k", "1", "--no-cpu-baseline"],
-                                  ["--workload", "cfg1", "--steps", "1", "--scaling", "strong", "--value-type", "i32", "--no-e2e"]])
+@pytest.mark.parametrize("argv", [["--workload", "cfg1", "--steps", "2", "--warmup", "1", "--cpu-budget", "0.2", "--scaling", "weak"],
+                                  ["--workload", "cfg1", "--steps", "2", "--slice-k", "1", "--no-cpu-baseline", "--scaling", "weak",
+                                   "--no-other-configs"],
+                                  ["--workload", "cfg1", "--steps", "1", "--value-type", "i32", "--no-e2e", "--no-other-configs"]])
 def test_bench_tbcuda_arm_dry_run(monkeypatch, argv):
     import torch
 
@@ -107,6 +111,10 @@ def test_bench_tbcuda_arm_dry_run(monkeypatch, argv):
 
     monkeypatch.setattr(tbcuda, "contract_slices", fake_contract_slices)
     monkeypatch.setattr(bench, "dpx_peak", lambda: {"viaddmax_s16x2_Gops": 35000.0, "viaddmax_s32_Gops": 18000.0})
+    monkeypatch.setattr(bench, "_DPX", None)
+    # the runs appended at N=1 (`other_configs`) on a tiny stand-in instead of cfg2 / cfg3 / cfg5
+    monkeypatch.setitem(bench.WORKLOADS, "tiny", ("regular", dict(n=40, d=3, seed=5), 8, None))
+    monkeypatch.setattr(bench, "OTHER_CONFIGS", ("tiny",))
     monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
@@ -117,7 +125,12 @@ def test_bench_tbcuda_arm_dry_run(monkeypatch, argv):
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
                 "dtype", "data", "config", "gpu_launches", "clocks", "roofline", "units", "branches", "mis"):
         assert key in line, key
-    assert line["scaling"] == ("strong" if "strong" in argv else "weak") and line["n_gpus"] == 1
+    assert line["scaling"] == ("weak" if "weak" in argv else "strong") and line["n_gpus"] == 1  # strong is the default
+    if "--no-other-configs" not in argv:
+        oc = line["other_configs"]["tiny"]
+        assert set(oc) >= {"value", "ms_per_step", "kernel_frac_of_dpx_peak", "e2e", "agrees_with_cpu"} and oc["agrees_with_cpu"]
+    assert line["config"]["workload_hash"].startswith("ok")
+    assert line["agrees_with_golden"] is True
     assert set(line["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
     assert "workload" in line["config"] and "sharding" in line["config"]
     if "--no-e2e" not in argv:
@@ -150,6 +163,7 @@ def _world2_worker(rank, world, port, out_dir, scaling):
     dist.init_process_group = lambda backend, **k: real_init("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     tbcuda.Engine = _FakeEngine
     bench.dpx_peak = lambda: {"viaddmax_s16x2_Gops": 35000.0, "viaddmax_s32_Gops": 18000.0}
+    bench._DPX = None
 
     def fake_contract_slices(branches, element_type=np.float32, usecuda=True, engine=None):
         eng = _FakeEngine()
