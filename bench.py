@@ -288,10 +288,26 @@ def cpu_leg(workload, branches, budget_s):
             "isa": CO.simd()}, dt, check
 
 
-def workload_config(name, max_branches, scaling, slice_k):
+def with_f32_weights(branches, seed=15):
+    """the weighted variant the reference tests with (Float32.(1.0 .+ rand(n)), /root/reference/test/dynamic_ob.jl:15,36):
+    every branch gets w = float32(1 + U[0,1)) on its own vertices (seeded); the engine then computes in Tropical{Float32}"""
+    import copy
+    rng = np.random.default_rng(seed)
+    out = []
+    for b in branches:
+        c = copy.copy(b)
+        if b.nv:
+            c.weights = (1.0 + rng.random(b.nv)).astype(np.float32)
+            c.r = float(np.float32(b.r))
+        out.append(c)
+    return out
+
+
+def workload_config(name, max_branches, scaling, slice_k, weights="unit"):
     wl_kind, wl_p, sc_target, wl_mb = WORKLOADS[name]
     wl_mb = max_branches or wl_mb
-    config = {"workload": f"{name}: {wl_kind} {wl_p}, sc_target={sc_target}, unit weights, stand-in host branching" +
+    wdesc = "unit weights" if weights == "unit" else "Float32 weights 1 + U[0,1) (test/dynamic_ob.jl:15), Tropical{Float32} on the device"
+    config = {"workload": f"{name}: {wl_kind} {wl_p}, sc_target={sc_target}, {wdesc}, stand-in host branching" +
                           (f", first {wl_mb} finished branches of the depth-first slicer" if wl_mb else ""),
               "l2": "per-step working set (arena + descriptors) exceeds the 126 MB L2; no explicit flush"}
     if slice_k > 0:
@@ -308,8 +324,9 @@ def workload_config(name, max_branches, scaling, slice_k):
 class Ctx:
     """what a workload measurement needs from the process: rank, world, engine"""
 
-    def __init__(self, rank, world, local_rank, eng, value_type):
+    def __init__(self, rank, world, local_rank, eng, value_type, weights="unit"):
         self.rank, self.world, self.local_rank, self.eng, self.value_type = rank, world, local_rank, eng, value_type
+        self.weights = weights
 
 
 def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=None, e2e_on=True, cpu_budget=15.0,
@@ -323,7 +340,7 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
 
     rank, world, eng = cx.rank, cx.world, cx.eng
     slice_k = slice_k if slice_k is not None else DEFAULT_SLICE_K.get(name, 0)
-    config = workload_config(name, max_branches, scaling, slice_k)
+    config = workload_config(name, max_branches, scaling, slice_k, cx.weights)
 
     def to_sliced(b):
         return tbcuda.SlicedBranch.from_parts(b.nv, b.edges, b.weights, b.ixs, b.tree, b.r)
@@ -336,6 +353,8 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
     if rank != 0:
         branches = make_workload(name, max_branches)
     config["workload_hash"] = workload_hash_status(name, branches, max_branches)
+    if cx.weights == "f32":
+        branches = with_f32_weights(branches)
     n_br = len(branches)
     sliced = [to_sliced(b) for b in branches]
     weak = scaling == "weak"
@@ -475,17 +494,20 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / n_steps, out, sorted(per_step)
 
-    # ---- the timed region: per-launch events stay on (mode 1: every launch on its own lane, lanes concurrent), so the
-    #      kernel times of the roofline come from the timed steps themselves
-    eng.profile(1)
+    # ---- the timed region (no per-launch events inside it: timestamps between the launches of a lane cost ~10 % on the
+    #      launch-rich workloads, measured on cfg2)
     sampler = ClockSampler(cx.local_rank) if (rank == 0 and sample_clocks) else None
     ms_step, result, per_step_ms = timed(step_resident, steps, max(warmup, 3), sampler)
     clocks = sampler.stop() if sampler else None
-    prof = eng.last_profile()              # last timed step: per kind (sum of launch durations, launches)
-    prof_union = eng.last_profile_union()  # per kind: time on the device (union of the lanes' launch intervals)
     launches_step = eng.last_timing()[1]
     dev_ms_last = eng.last_timing()[0]
-    # single-lane pass (launches serialised: per-launch durations free of overlap) -- beside, not instead of, the above
+    # ---- kernel times for the roofline: ONE more step right behind the timed ones, same configuration (all stream lanes
+    #      concurrent), with CUDA events around every launch on its own lane ...
+    eng.profile(1)
+    step_resident()
+    prof = eng.last_profile()              # per kind (sum of launch durations, launches)
+    prof_union = eng.last_profile_union()  # per kind: time on the device (union of the lanes' launch intervals)
+    # ... and a single-lane pass (launches serialised: per-launch durations free of overlap) beside it
     eng.profile(2)
     step_resident()
     prof1 = eng.last_profile()
@@ -510,7 +532,8 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
         peaks, peak_src = measured_peaks()
         dpx = dpx_peak_once()
         i16 = cx.value_type == "i16"
-        peak_gops = dpx.get("viaddmax_s16x2_Gops" if i16 else "viaddmax_s32_Gops")
+        f32 = cx.value_type == "f32"
+        peak_gops = dpx.get("fadd_fmnmx_f32_Gops" if f32 else ("viaddmax_s16x2_Gops" if i16 else "viaddmax_s32_Gops"))
         # the dominant kernel: the persistent max-plus GEMM kernel; in the dataflow executor its ONE launch per wave also
         # runs the wave's generic steps on its consumer warps, so its ops are the GEMM + generic steps' ops
         n_gen_launches = prof["generic"][1]
@@ -526,15 +549,17 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
             traffic = tj.get("dram_bytes_per_launch_mean")
             traffic_algo = tj.get("algorithmic_bytes_per_launch_mean")
             traffic_note = tj.get("note")
-        kname = ("k_gemm2h (packed int16x2)" if i16 else "k_gemm2<int32>") + \
+        kname = ("k_gemm2<float> (FADD + FMNMX)" if f32 else ("k_gemm2h (packed int16x2)" if i16 else "k_gemm2<int32>")) + \
                 (", persistent dataflow kernel: the tiled max-plus GEMM tiles and the generic tiles of a whole wave"
                  if not n_gen_launches else ", one launch per dependency level")
-        roofline = {"bound": ("dpx-int16x2 (VIADDMNMX.S16x2" if i16 else "dpx-int32 (VIADDMNMX") +
+        roofline = {"bound": ("fp32 FADD+FMNMX (two issues per tropical op" if f32 else
+                              ("dpx-int16x2 (VIADDMNMX.S16x2" if i16 else "dpx-int32 (VIADDMNMX")) +
                              " issue rate; the semiring is (max,+), tensor cores do not apply)",
                     "kernel": kname, "achieved": ach, "peak": peak_gops, "unit": "Gop/s",
                     "frac": (ach / peak_gops) if (ach and peak_gops) else None,
-                    "frac_note": "kernel ops / time the kernel was on the device during the LAST TIMED STEP (CUDA events around "
-                                 "every launch on its own stream lane, union of the lanes' intervals), lanes concurrent as timed",
+                    "frac_note": "kernel ops / time the kernel was on the device in one step run right behind the timed steps in the "
+                                 "timed configuration (all stream lanes concurrent; CUDA events around every launch on its own lane, "
+                                 "union of the lanes' intervals).  frac_whole_step uses the timed steps themselves",
                     "frac_single_lane": (ach1 / peak_gops) if (ach1 and peak_gops) else None,
                     "frac_whole_step": (total_ops / world / (ms_step * 1e-3) * 1e-9 / peak_gops) if peak_gops else None,
                     "traffic": traffic, "traffic_algorithmic_bytes_same_launches": traffic_algo, "traffic_note": traffic_note,
@@ -547,14 +572,14 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
                             "achieved_whole_step": my_sum("algo_bytes") / (ms_step * 1e-3) * 1e-9}}
         out = {"value": total_ops / (ms_step * 1e-3) * 1e-9, "unit": "Gop/s", "ms_per_step": ms_step,
                "ms_per_step_median_rank0": per_step_ms[len(per_step_ms) // 2], "ms_per_step_max_rank0": per_step_ms[-1],
-               "dtype": "int16x2" if i16 else "int32", "config": config,
+               "dtype": "f32" if f32 else ("int16x2" if i16 else "int32"), "config": config,
                "slices_per_s": copies * n_units / (ms_step * 1e-3), "branches": copies * n_br, "units": copies * n_units,
                "total_ops": total_ops, "mis": float(np.max(result)),
                "gpu_launches": int(launches_step * steps * world),  # rank 0's launches per step x ranks (LPT shards are alike)
                "launches_per_step": int(launches_step), "device_ms_last_step": dev_ms_last,
                "plan_compile_s_this_rank": plan_s, "clocks": clocks, "roofline": roofline}
         gold = golden_record(name)
-        if gold is not None and max_branches is None:
+        if gold is not None and max_branches is None and cx.weights == "unit":
             out["agrees_with_golden"] = bool(np.array_equal(result, np.asarray(gold["values"])))
         if e2e:
             out["e2e"] = e2e
@@ -568,7 +593,9 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
                 cb["agrees_with_gpu"] = bool(np.array_equal(gv[np.asarray(assign)], vals))
             else:
                 n = len(check)
-                cb["agrees_with_gpu"] = bool(np.array_equal(check + r_vec[:n], result[:n]))
+                # unit weights: integers, exact in any type; f32 weights: the same Float32 arithmetic as contract_slices
+                want = (check + r_vec[:n]) if cx.weights == "unit" else (check.astype(np.float32) + r_vec[:n].astype(np.float32)).astype(np.float64)
+                cb["agrees_with_gpu"] = bool(np.array_equal(want, result[:n]))
             out["cpu_baseline"] = cb
     for p in my_plans:
         if p is not None:
@@ -595,13 +622,15 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short cfg2 / cfg3 / cfg5 runs appended at N=1")
     ap.add_argument("--value-type", default="i16", choices=["i32", "i16"],
                     help="i16 (default, what value_type AUTO picks for this workload) = packed int16x2; i32 = plan flag NO_I16")
+    ap.add_argument("--weights", default="unit", choices=["unit", "f32"],
+                    help="f32: Float32 vertex weights 1 + U[0,1) (the reference's weighted tests): Tropical{Float32} kernels (K3)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     slice_k = args.slice_k if args.slice_k is not None else DEFAULT_SLICE_K.get(args.workload, 0)
-    config = workload_config(args.workload, args.max_branches, args.scaling, slice_k)
+    config = workload_config(args.workload, args.max_branches, args.scaling, slice_k, args.weights)
 
     # ---------------------------------------------------------------- reference arm (CPU)
     if args.impl == "reference":
@@ -611,6 +640,8 @@ def main():
         G.build()
         branches = make_workload(args.workload, args.max_branches)
         config["workload_hash"] = workload_hash_status(args.workload, branches, args.max_branches)
+        if args.weights == "f32":
+            branches = with_f32_weights(branches)
         per_step = max(3.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
         gops = []
         cb = None
@@ -646,7 +677,7 @@ def main():
     eng = tbcuda.Engine(local_rank, plan_flags=(tbcuda.TB_PLAN_NO_I16 if args.value_type == "i32" else 0),
                         host_threads=max(1, host_cores() // world))  # ranks share the host's cores for plan compilation
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
-    cx = Ctx(rank, world, local_rank, eng, args.value_type)
+    cx = Ctx(rank, world, local_rank, eng, "f32" if args.weights == "f32" else args.value_type, args.weights)
 
     main_res = run_workload(cx, args.workload, args.scaling, args.steps, args.warmup, args.max_branches, args.slice_k,
                             e2e_on=not args.no_e2e, cpu_budget=args.cpu_budget,

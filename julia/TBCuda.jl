@@ -187,12 +187,17 @@ end
 # recurse), so these methods are strictly more specific in the element type -- `Type{T} where T<:AbstractFloat` wins the
 # dispatch for Float32 / Float64 -- and the usecuda=false branch reaches the reference's own method through `invoke` with
 # the original, less specific signature.  (A maintainer would rather add the two-line hook shown in INTEGRATION.md.)
+# The device computes exactly in integers (unit / integer-valued weights, any float container) or in Tropical{Float32}.
+# A Float64 element type with real weights would silently lose precision there, so such calls stay with the reference.
+integer_valued(w) = w isa TensorBranching.UnitWeight || all(isinteger, w)
+on_device(branch::SlicedBranch, ::Type{T}) where {T} = T === Float32 || integer_valued(branch.p.weights)
+
 function TensorBranching.contract_slices(branches::Vector{SlicedBranch}, element_type::Type{T}, usecuda::Bool) where {T <: AbstractFloat}
-    usecuda && return contract_slices_cuda(branches, element_type)
+    usecuda && all(b -> on_device(b, T), branches) && return contract_slices_cuda(branches, element_type)
     return invoke(TensorBranching.contract_slices, Tuple{Vector{SlicedBranch}, Type, Bool}, branches, element_type, false)
 end
 function TensorBranching.solve_slice(branch::SlicedBranch, element_type::Type{T}, usecuda::Bool) where {T <: AbstractFloat}
-    usecuda || return invoke(TensorBranching.solve_slice, Tuple{SlicedBranch, Type, Bool}, branch, element_type, false)
+    (usecuda && on_device(branch, T)) || return invoke(TensorBranching.solve_slice, Tuple{SlicedBranch, Type, Bool}, branch, element_type, false)
     return contract_slices_cuda(SlicedBranch[TensorBranching.SlicedBranch(branch.p, branch.code, zero(branch.r))], element_type)[1]
 end
 

@@ -5,7 +5,7 @@
 name=$1; tmo=$2; script=$3; gpus=${4:-1}
 cd /root/repo
 rm -rf frozen_$name
-rsync -a --exclude 'frozen_*' --exclude gpurun_out --exclude .git --exclude ab_r1 --exclude '__pycache__' --exclude .pytest_cache --exclude .hypothesis ./ frozen_$name/
+mkdir -p frozen_$name && tar -cf - --exclude='./frozen_*' --exclude=./gpurun_out --exclude=./.git --exclude=./ab_r1 --exclude='__pycache__' --exclude=.pytest_cache --exclude=.hypothesis . | tar -xf - -C frozen_$name
 [ -d ab_r1 ] && ln -sfn ../ab_r1 frozen_$name/ab_r1
 ln -sfn ../gpurun_out frozen_$name/gpurun_out
 extra=""

@@ -97,12 +97,23 @@ struct tb_ctx {
     int waves_per_lane = 0;                // waves per lane a small call is cut into; 0 = by plan weight (TB_WAVES_PER_LANE)
     cudaStream_t side[kMaxLanes] = {};     // side[1..n_lanes-1]
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxLanes] = {};
-    bool dataflow = true;          // one persistent launch per wave for all non-fused steps (TB_LEVEL_SYNC=1: one launch per level and kind)
+    // Executor of the non-fused steps of a wave.  dataflow: ONE persistent launch runs every level (tiles wait on
+    // completion counters); level-synchronous: one launch per dependency level and kernel kind.  Measured on B200
+    // (profiles/r2e_*): dataflow wins where launches / level tails dominate (few or light plans: BASELINE configs 3 and 5),
+    // the level-synchronous launches win on DPX-bound calls (configs 2 and 4): their GEMM instance carries no generic-tile
+    // code (uniform-datapath main loop) and the HBM-bound generic steps get a kernel of their own with twice the warps.
+    int dataflow_mode = 0;         // 0 = per call by plan count / weight, 1 = always dataflow (TB_DATAFLOW=1), 2 = never (TB_LEVEL_SYNC=1)
+    bool dataflow = true;          // the choice for the current call
+    int call_lanes = 1;            // stream lanes the current call can fill (its waves): the persistent dataflow kernels of
+                                   // different lanes share the SMs, each takes 1 / call_lanes of the CTA slots
     bool solo_fence = false;       // a solo wave ran on the whole arena: the side lanes must wait for it before their next wave
     int profile_mode = 0;          // 1: events around every launch on its own lane (lanes stay concurrent); 2: single lane
     struct ProfRec {
         int kind;
         cudaEvent_t e0, e1;
+        double ops, bytes;
+        int n_insts;
+        uint32_t grid;
     };
     std::vector<ProfRec> prof_recs;  // launches of the current call (profile_mode != 0)
     size_t prof_used = 0;            // events of prof_events handed out in the current call
@@ -376,7 +387,20 @@ struct Launch {
     int n_insts;
     uint32_t grid;
     uint32_t smem;
+    double ops = 0, bytes = 0;  // big steps only: tropical ops / bytes moved by the launch (per-launch roofline records)
 };
+
+// CTAs of one persistent dataflow kernel: the kernels of the call's concurrent lanes co-reside, each on its share of the
+// CTA slots, so that the dependency stalls and the thin last levels of one wave are covered by the other waves' tiles
+uint32_t dataflow_grid_cap(const tb_ctx* ctx) {
+    static const int forced = [] {
+        const char* e = getenv("TB_DF_GRID");  // experiments: CTAs per dataflow kernel
+        return e ? atoi(e) : 0;
+    }();
+    if (forced > 0) return (uint32_t)forced;
+    const int slots = std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count;
+    return (uint32_t)std::max(1, slots / std::max(1, ctx->call_lanes));
+}
 
 template <typename T>
 void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
@@ -390,18 +414,28 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
             break;
         case 2:
             if constexpr (std::is_same<T, int16_t>::value) {
-                const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
-                k_gemm2h<<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
-                                                                 L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
-                                                                 L.done_off == kNoDone ? nullptr : (unsigned int*)(dbase + L.done_off));
+                uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
+                if (L.done_off != kNoDone) grid = std::min<uint32_t>(grid, dataflow_grid_cap(ctx));
+                if (L.done_off == kNoDone)
+                    k_gemm2h<false><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
+                                                                            L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off), nullptr);
+                else
+                    k_gemm2h<true><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
+                                                                           L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
+                                                                           (unsigned int*)(dbase + L.done_off));
             } else if (ctx->gemm_v1) {
                 k_gemm<T><<<L.grid, BIG_THREADS, GEMM_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             } else {
-                const uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
-                k_gemm2<T><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
-                                                                   L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
-                                                                   ctx->staged_epilogue ? 1 : 0,
-                                                                   L.done_off == kNoDone ? nullptr : (unsigned int*)(dbase + L.done_off));
+                uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
+                if (L.done_off != kNoDone) grid = std::min<uint32_t>(grid, dataflow_grid_cap(ctx));
+                if (L.done_off == kNoDone)
+                    k_gemm2<T, false><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
+                                                                              L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
+                                                                              ctx->staged_epilogue ? 1 : 0, nullptr);
+                else
+                    k_gemm2<T, true><<<grid, G2_THREADS, G2_SMEM_BYTES, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off),
+                                                                             L.n_insts, L.grid, (unsigned int*)(dbase + L.counter_off),
+                                                                             ctx->staged_epilogue ? 1 : 0, (unsigned int*)(dbase + L.done_off));
             }
             break;
         case 3:
@@ -578,6 +612,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             std::vector<std::vector<int32_t>> inst_of(w.members.size());  // member -> big step -> instance index
             for (size_t m = 0; m < w.members.size(); ++m) inst_of[m].assign(plans[w.members[m]]->p.big_steps.size(), -1);
             uint64_t tiles = 0;
+            double df_ops = 0, df_bytes = 0;
             std::vector<std::pair<uint32_t, uint32_t>> lvl;  // (member, step) of one level and kind
             for (int lv = 1; lv <= w.levels; ++lv) {
                 for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
@@ -605,6 +640,8 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                         bi.dep_a = da >= 0 ? inst_of[ms.first][(size_t)da] : -1;
                         bi.dep_b = db >= 0 ? inst_of[ms.first][(size_t)db] : -1;
                         inst_of[ms.first][ms.second] = (int32_t)insts.size();
+                        df_ops += std::ldexp(1.0, (int)P.big_log2_ops[ms.second]);
+                        df_bytes += P.big_bytes[ms.second];
                         insts.push_back(bi);
                         starts.push_back((uint32_t)tiles);
                         done_init.push_back(st.n_tiles * (uint32_t)(G2_CONSUMERS / 32));
@@ -635,6 +672,8 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 host.resize(host.size() + 16, 0);
                 L.n_insts = (int)insts.size();
                 L.grid = (uint32_t)tiles;
+                L.ops = df_ops;
+                L.bytes = df_bytes;
                 launches.push_back(L);
             }
         } else
@@ -643,6 +682,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 std::vector<BigInst> insts;
                 std::vector<uint32_t> starts, inst_nk, inst_tiles;
                 uint64_t tiles = 0;
+                double ls_ops = 0, ls_bytes = 0;
                 for (size_t m = 0; m < w.members.size(); ++m) {
                     const Plan& P = plans[w.members[m]]->p;
                     if (lv > P.n_levels) continue;
@@ -660,6 +700,8 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                         inst_nk.push_back(P.big_steps[s].nk);
                         inst_tiles.push_back(P.big_steps[s].n_tiles);
                         tiles += P.big_steps[s].n_tiles;
+                        ls_ops += std::ldexp(1.0, (int)P.big_log2_ops[(size_t)s]);
+                        ls_bytes += P.big_bytes[(size_t)s];
                     }
                 }
                 if (insts.empty()) continue;
@@ -696,6 +738,8 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 host.resize(host.size() + 16, 0);
                 L.n_insts = (int)insts.size();
                 L.grid = (uint32_t)tiles;
+                L.ops = ls_ops;
+                L.bytes = ls_bytes;
                 launches.push_back(L);
             }
         }
@@ -764,7 +808,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         }
         const Launch& L = launches[li];
         cudaStream_t st = L.lane == 0 ? ctx->stream : ctx->side[L.lane];
-        tb_ctx::ProfRec pr{L.kind, nullptr, nullptr};
+        tb_ctx::ProfRec pr{L.kind, nullptr, nullptr, L.ops, L.bytes, L.n_insts, L.grid};
         if (ctx->profile_mode) {
             if ((rc = prof_event(&pr.e0)) || (rc = prof_event(&pr.e1))) return rc;
             TB_CUDA(ctx, cudaEventRecord(pr.e0, st));
@@ -916,7 +960,7 @@ int finish_sync(tb_ctx* ctx) {
             ctx->prof_ms[pr.kind] += b - a;
             ctx->prof_launches[pr.kind] += 1;
             iv[pr.kind].push_back({a, b});
-            if (dump) fprintf(dump, "%d,%.4f,%.4f\n", pr.kind, a, b);
+            if (dump) fprintf(dump, "%d,%.4f,%.4f,%.6g,%.6g,%d,%u\n", pr.kind, a, b, pr.ops, pr.bytes, pr.n_insts, pr.grid);
         }
         if (dump) fclose(dump);
         for (int k = 0; k < 4; ++k) {
@@ -943,13 +987,19 @@ int finish_sync(tb_ctx* ctx) {
 // rank's shard of a multi-GPU run) is cut into ~2 waves per lane (profiles/s03_wave_lane_sweep_cfg2.jsonl).  Light plans
 // (cfg5: 2^22.5 ops each) are launch-bound: waves of up to 256, one per lane (profiles/s05_wave_sweep_cfg5_cfg2.jsonl:
 // 1.78 ms instead of 2.16 ms for 1 024 plans).  mean_ops <= 0: unknown, treated as heavy.
-int wave_for_call(const tb_ctx* ctx, int64_t n, double mean_ops) {
+int wave_for_call(tb_ctx* ctx, int64_t n, double mean_ops) {
     const bool light = mean_ops > 0 && mean_ops < (double)(1 << 24);
+    // dataflow: launch-bound calls -- light plans, or few plans that are not huge (a plan of >= 2^36 ops runs for
+    // milliseconds per level: nothing to gain from dropping launches, and the level-synchronous GEMM instance is faster)
+    ctx->dataflow = ctx->dataflow_mode == 1 ||
+                    (ctx->dataflow_mode == 0 && (light || (n <= 2 * (int64_t)ctx->n_lanes && mean_ops < 68719476736.0)));
     const int64_t cfg = ctx->opts.max_wave > 0 ? ctx->opts.max_wave : (light ? 256 : 128);
     const int wpl = ctx->waves_per_lane > 0 ? ctx->waves_per_lane : (light ? 1 : 2);
     const int64_t parts = (int64_t)wpl * ctx->n_lanes;
     const int64_t per = (n + parts - 1) / parts;
-    return (int)std::min<int64_t>(cfg, std::max<int64_t>(16, per));
+    const int64_t wave = std::min<int64_t>(cfg, std::max<int64_t>(16, per));
+    ctx->call_lanes = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->n_lanes, (n + wave - 1) / wave));
+    return (int)wave;
 }
 
 double mean_plan_ops(tb_plan* const* plans, int64_t lo, int64_t hi) {
@@ -1126,7 +1176,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
         const char* e5 = getenv("TB_WAVES_PER_LANE");
         if (e5 && atoi(e5) >= 1) c->waves_per_lane = atoi(e5);
         const char* e6 = getenv("TB_LEVEL_SYNC");  // A/B testing: one launch per dependency level and kernel kind (the round-1 executor)
-        c->dataflow = !(e6 && e6[0] == '1') && !c->gemm_v1;
+        const char* e7 = getenv("TB_DATAFLOW");
+        c->dataflow_mode = ((e6 && e6[0] == '1') || c->gemm_v1) ? 2 : ((e7 && e7[0] == '1') ? 1 : 0);
         if (c->opts.streams_per_device >= 1) c->n_lanes = std::min(c->opts.streams_per_device, (int)tb_ctx::kMaxLanes);
         const char* e2 = getenv("TB_LANES");
         if (e2 && atoi(e2) >= 1) c->n_lanes = std::min(atoi(e2), (int)tb_ctx::kMaxLanes);
@@ -1144,16 +1195,17 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2h, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2h, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM_ELEMS * 4));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<int32_t>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm2<float>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    {
+        const void* g2[] = {(const void*)k_gemm2<int32_t, false>, (const void*)k_gemm2<int32_t, true>, (const void*)k_gemm2<float, false>,
+                            (const void*)k_gemm2<float, true>, (const void*)k_gemm2h<false>, (const void*)k_gemm2h<true>};
+        for (const void* fn : g2) {
+            TB_CUDA(nullptr, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+            TB_CUDA(nullptr, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        }
+    }
     {
         int nb = 0;
-        TB_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm2<int32_t>, G2_THREADS, G2_SMEM_BYTES));
+        TB_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_gemm2<int32_t, true>, G2_THREADS, G2_SMEM_BYTES));
         c->gemm2_ctas_per_sm = nb;
         const char* eg = getenv("TB_GEMM_CTAS");  // persistent GEMM CTAs per SM and launch (experiments: 1 lets two lanes' GEMMs co-run)
         if (eg && atoi(eg) >= 1) c->gemm2_ctas_per_sm = std::min(nb, atoi(eg));

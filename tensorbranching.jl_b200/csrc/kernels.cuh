@@ -358,6 +358,14 @@ __device__ __forceinline__ void generic_tile(const BigStep& sd, const void* pool
     }
 }
 
+// The persistent kernels call the generic tile through a real function call: inlined, its (divergent, table-driven) body
+// made ptxas drop the warp-uniform address arithmetic of the GEMM main loop in the same kernel (12 % on BASELINE config 4).
+// No accumulator is live between tiles, so the call costs nothing that matters.
+template <typename T>
+__device__ __noinline__ void generic_tile_call(const BigStep* sd, const void* poolp, void* arenap, uint32_t tile, int tid, T* s_red) {
+    generic_tile<T, true>(*sd, poolp, arenap, tile, tid, s_red);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(BIG_THREADS, 4) k_generic(const BigInst* __restrict__ insts,
                                                          const uint32_t* __restrict__ tile_starts, int n_insts) {
@@ -625,6 +633,30 @@ __device__ __forceinline__ void dep_signal(unsigned int* p, unsigned n) {
 // the producer warp reads, with TMA (async proxy), global memory that other CTAs of the same kernel wrote with ordinary
 // stores (generic proxy): cross-proxy fence between the acquire above and the bulk copies below
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+// the same on a precomputed shared-memory address (hot loops: no generic -> shared conversion per wait)
+__device__ __forceinline__ void mbar_wait_addr(unsigned addr, unsigned parity) {
+    unsigned done = 0;
+    long long t0 = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kSpinTimeoutClocks) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void mbar_arrive_addr(unsigned addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(addr) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                      (unsigned)__cvta_generic_to_shared(smem_dst)),
@@ -637,11 +669,12 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsig
 // succeeds (a silent hang).  P = 24 (producer warpgroup), C = 104 (consumer warpgroups): 3072 + 26624 = 29696.
 static_assert(128 * 24 + 256 * 104 <= 384 * 80, "setmaxnreg budget exceeds the CTA pool");
 static_assert(128 * 32 + 256 * 104 <= 384 * 80, "setmaxnreg budget of k_gemm2h exceeds the CTA pool");
-template <typename T>
+template <typename T, bool DF>
 __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
                                                          int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter,
                                                          int staged_epilogue, unsigned int* done) {
     typedef typename Ops<T>::vec4 vec4;
+    if (!DF) done = nullptr;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);
     T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);
@@ -710,7 +743,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
                 fence_proxy_async();
                 waited_idx = idx;
             }
-            if (d->kind != KIND_GEMM) {  // a generic step's tile: hand the descriptor to the consumer warps
+            if (DF && d->kind != KIND_GEMM) {  // a generic step's tile: hand the descriptor to the consumer warps
                 TileInfo& tg = tinfo[slot];
                 uint32_t* gd = reinterpret_cast<uint32_t*>(&s_gstep[slot]);
                 const uint32_t* gs = reinterpret_cast<const uint32_t*>(d);
@@ -799,11 +832,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2(const BigInst* __restri
         mbar_wait(&bar_tfull[slot], (tcount >> 1) & 1);
         const TileInfo& ti = tinfo[slot];
         if (!ti.valid) break;
-        if (ti.kind != KIND_GEMM) {
-            generic_tile<T, true>(s_gstep[slot], ti.pool, ti.arena, ti.tile, ctid, stg_mem);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_sig[slot]);
-            continue;
+        if constexpr (DF) {
+            if (ti.kind != KIND_GEMM) {
+                generic_tile_call<T>(&s_gstep[slot], ti.pool, ti.arena, ti.tile, ctid, stg_mem);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_sig[slot]);
+                continue;
+            }
         }
         const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
         const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
@@ -1016,10 +1051,84 @@ struct TileInfoH {
 };
 __device__ __forceinline__ uint32_t stg_swz_h(uint32_t x) { return x ^ ((((x >> 6) ^ (x >> 9) ^ (x >> 12)) & 7u) << 3); }
 
+// The k loop of one pipeline stage for a tile shape known at compile time: every shared-memory offset (k-pair row pitch,
+// upper half of the m / n microtile) is an immediate of the load instruction, the only address arithmetic left is three
+// adds per two k-pair rows (128 VIADDMNMX).  ua / ua_p = byte addresses of this thread's first A words (tile bit m0 / m_mp),
+// ub = of its first B words, all in the stage being consumed.  Same software pipeline as the generic loop below: B double
+// buffered in registers, the two halves of A reloaded in place right after their last use.
+template <int TM, int TN>
+__device__ __forceinline__ void g2h_stage_loop(uint32_t ua, uint32_t ua_p, uint32_t ub, int kp_rows, uint32_t (&acc)[8][8]) {
+    constexpr int ROWA = 4 << TM, ROWB = 4 << TN, A_HI = 2 << TM, B_HI = 4 << (TN - 1);
+    uint32_t a[8], b0[8], b1[8];
+#define G2T_LDA_LO(OFF)                                                                                                  \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(a[0]), "=r"(a[1]) : "r"(ua), "n"(OFF));                     \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(a[2]), "=r"(a[3]) : "r"(ua_p), "n"(OFF));
+#define G2T_LDA_HI(OFF)                                                                                                  \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(a[4]), "=r"(a[5]) : "r"(ua), "n"((OFF) + A_HI));            \
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(a[6]), "=r"(a[7]) : "r"(ua_p), "n"((OFF) + A_HI));
+#define G2T_LDB(bb, OFF)                                                                                                 \
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(bb[0]), "=r"(bb[1]), "=r"(bb[2]), "=r"(bb[3]) : "r"(ub), "n"(OFF)); \
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(bb[4]), "=r"(bb[5]), "=r"(bb[6]), "=r"(bb[7]) : "r"(ub), "n"((OFF) + B_HI));
+#define G2T_MATH(i0, bb)                                                                                                 \
+    _Pragma("unroll") for (int i = i0; i < i0 + 4; ++i)                                                                   \
+        _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[i][j] = __viaddmax_s16x2(a[i], bb[j], acc[i][j]);
+    G2T_LDA_LO(0)
+    G2T_LDB(b0, 0)
+    int kk = 0;
+#pragma unroll 1
+    for (int n2 = kp_rows >> 1; n2 > 0; --n2) {  // two k-pair rows (128 VIADDMNMX) per trip: 3 address adds + a countdown
+        G2T_LDA_HI(0)
+        G2T_LDB(b1, ROWB)
+        G2T_MATH(0, b0)
+        G2T_LDA_LO(ROWA)
+        G2T_MATH(4, b0)
+        G2T_LDA_HI(ROWA)
+        G2T_LDB(b0, 2 * ROWB)  // the last one reads one row past the chunk (still shared memory): discarded
+        G2T_MATH(0, b1)
+        G2T_LDA_LO(2 * ROWA)
+        G2T_MATH(4, b1)
+        ua += 2 * ROWA;
+        ua_p += 2 * ROWA;
+        ub += 2 * ROWB;
+    }
+    kk = kp_rows & ~1;
+    if (kk < kp_rows) {  // a single k-pair row (kc == 1)
+        G2T_LDA_HI(0)
+        G2T_MATH(0, b0)
+        G2T_MATH(4, b0)
+    }
+#undef G2T_LDA_LO
+#undef G2T_LDA_HI
+#undef G2T_LDB
+#undef G2T_MATH
+}
+
+// All pipeline stages of one tile for a compile-time tile shape: wait for the stage, run its k loop, hand it back.
+// a_thr / b_thr = this thread's A / B byte addresses in stage 0; full0 / empty0 = shared addresses of bar_full[0] / bar_empty[0].
+template <int TM, int TN>
+__device__ __forceinline__ void g2h_tile_mainloop(uint32_t a_thr, uint32_t a_p, uint32_t b_thr, int kp_rows, int nchunks, unsigned& it,
+                                                  uint32_t full0, uint32_t empty0, int lane, uint32_t (&acc)[8][8]) {
+    constexpr uint32_t STAGE_BYTES = (uint32_t)GEMM_STAGE_ELEMS * 4u;  // 2 * GEMM_STAGE_ELEMS int16 elements
+#pragma unroll 1
+    for (int ch = 0; ch < nchunks; ++ch, ++it) {
+        const unsigned stage = it % G2_STAGES;
+        mbar_wait_addr(full0 + stage * 8u, (it / G2_STAGES) & 1u);
+        const uint32_t ua = a_thr + stage * STAGE_BYTES;
+        g2h_stage_loop<TM, TN>(ua, ua + a_p, b_thr + stage * STAGE_BYTES, kp_rows, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_addr(empty0 + stage * 8u);
+    }
+}
+
+// DF = dataflow launch (all levels of a wave, generic tiles included, completion counters).  The level-synchronous
+// instance (DF = false) contains no generic-tile code at all: with it in the same function ptxas no longer proves the
+// main loop's address arithmetic warp-uniform (no uniform-datapath instructions), which costs 7 % on DPX-bound workloads.
+template <bool DF>
 __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restrict__ insts, const uint32_t* __restrict__ tile_starts,
                                                           int n_insts, uint32_t total_tiles, unsigned int* __restrict__ counter,
                                                           unsigned int* done) {
     typedef int16_t T;
+    if (!DF) done = nullptr;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     T* stage_mem = reinterpret_cast<T*>(dyn_smem);                       // G2_STAGES x 16 KB
     T* stg_mem = reinterpret_cast<T*>(dyn_smem + G2_RING_BYTES);         // 2 x 16 KB
@@ -1108,7 +1217,7 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             const uint32_t tile = tile_g - cur_start;
             const BigStep* d = &s_step;
             const unsigned char* arena = cur_arena;
-            if (d->kind != KIND_GEMM) {  // a generic step's tile: hand the descriptor to the consumer warps, nothing to stage
+            if (DF && d->kind != KIND_GEMM) {  // a generic step's tile: hand the descriptor to the consumer warps, nothing to stage
                 TileInfoH& tg = tinfo[slot];
                 uint32_t* gd = reinterpret_cast<uint32_t*>(&s_gstep[slot]);
                 const uint32_t* ss = reinterpret_cast<const uint32_t*>(&s_step);
@@ -1209,14 +1318,17 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         KP(0)
         const TileInfoH& ti = tinfo[slot];
         if (!ti.valid) break;
-        if (ti.kind != KIND_GEMM) {
-            generic_tile<T, true>(s_gstep[slot], ti.pool, ti.arena, ti.tile, ctid, stg_mem);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bar_sig[slot]);
-            KP(3)
-            continue;
+        if constexpr (DF) {
+            if (ti.kind != KIND_GEMM) {
+                generic_tile_call<T>(&s_gstep[slot], ti.pool, ti.arena, ti.tile, ctid, stg_mem);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_sig[slot]);
+                KP(3)
+                continue;
+            }
         }
-        const int tm = ti.tm, tn = ti.tn, kc = ti.kc, nchunks = ti.nchunks;
+        const int tm = ti.tm, tn = ti.tn, kc = ti.kc;
+        int nchunks = ti.nchunks;
         const int tps_log = tm + tn - 6, S = 1 << (8 - tps_log);
         const int sub = ctid >> tps_log, lt = ctid & ((1 << tps_log) - 1);
         const int tmh = ti.lane_n_first ? (lt >> (tn - 3)) : (lt & ((1 << (tm - 3)) - 1));
@@ -1240,6 +1352,21 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
         const uint32_t b_thr = stage_base + ((((uint32_t)S << la) + ((uint32_t)sub << lb) + (uint32_t)n_lo) << 1);
         const uint32_t a_p = (uint32_t)m_p << 1, a_hi = (uint32_t)m_hi << 1, b_hi = 4u << (tn - 1);
         const uint32_t rowA = 4u << tm, rowB = 4u << tn;  // bytes per k-pair row
+        // dataflow instance: the common tile shapes run the whole main loop with compile-time offsets (g2h_tile_mainloop)
+        if constexpr (DF) {
+            const uint32_t full0 = (uint32_t)__cvta_generic_to_shared(&bar_full[0]);
+            const uint32_t empty0 = (uint32_t)__cvta_generic_to_shared(&bar_empty[0]);
+            const int kpr = 1 << (kc - 1);
+            bool fast = true;
+            switch (tm * 8 + tn) {
+                case 7 * 8 + 7: g2h_tile_mainloop<7, 7>(a_thr, a_p, b_thr, kpr, nchunks, it, full0, empty0, lane, acc); break;
+                case 7 * 8 + 6: g2h_tile_mainloop<7, 6>(a_thr, a_p, b_thr, kpr, nchunks, it, full0, empty0, lane, acc); break;
+                case 6 * 8 + 7: g2h_tile_mainloop<6, 7>(a_thr, a_p, b_thr, kpr, nchunks, it, full0, empty0, lane, acc); break;
+                default: fast = false;
+            }
+            if (fast) nchunks = 0;  // nothing left for the generic loop below
+            KP(2)
+        }
         for (int ch = 0; ch < nchunks; ++ch, ++it) {
             const int stage = it % G2_STAGES;
             mbar_wait(&bar_full[stage], (it / G2_STAGES) & 1);

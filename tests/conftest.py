@@ -62,6 +62,18 @@ def engine(tb):
 
 
 @pytest.fixture(scope="session")
+def engine_dataflow(tb):
+    """the dataflow executor forced for every call (TB_DATAFLOW=1); the default engine picks per call"""
+    os.environ["TB_DATAFLOW"] = "1"
+    try:
+        eng = tb.Engine(0)
+    finally:
+        del os.environ["TB_DATAFLOW"]
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
 def engine_levelsync(tb):
     """the round-1 executor (one launch per dependency level and kernel kind), kept for A/B testing: TB_LEVEL_SYNC=1"""
     os.environ["TB_LEVEL_SYNC"] = "1"

@@ -5,7 +5,7 @@
 CPU part (-m "not gpu"): the branch lists bench.py contracts are the ones the goldens were made from (sha256 over their
 canonical content: the tracked generator, not whatever cache file happens to ship), and the oracle reproduces a sample.
 GPU part (-m gpu): bit-equality of the engine on all of cfg1 / cfg2 / cfg3 (+ its 2^3 index slices) / cfg4 / cfg5,
-through both executors (dataflow, level-synchronous)."""
+through both executors (dataflow, level-synchronous) and the engine's own per-call choice."""
 import os
 
 import numpy as np
@@ -43,13 +43,13 @@ def test_c_oracle_reproduces_a_sample_of_the_golden_values(name, count):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CONFIGS)
-def test_gpu_equals_golden_at_full_size(tb, engine, engine_levelsync, name):
+def test_gpu_equals_golden_at_full_size(tb, engine, engine_dataflow, engine_levelsync, name):
     rec, brs = _workload(name)
     sliced = [to_sliced(b) for b in brs]
     want = np.asarray(rec["values"])
-    for eng in (engine, engine_levelsync):
-        if name == "cfg4" and eng is engine_levelsync:
-            continue  # 1.5 s of device time per pass: once is enough at this size
+    for eng in (engine, engine_dataflow, engine_levelsync):  # the engine's own choice, and both executors forced
+        if name == "cfg4" and eng is engine:
+            continue  # 1.5 s of device time per pass: the default engine picks the level-synchronous executor here
         got = tb.contract_slices(sliced, np.float32, True, engine=eng)
         assert np.array_equal(got.astype(np.float64), want)
         assert float(got.max()) == rec["mis"]

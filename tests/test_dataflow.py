@@ -1,7 +1,8 @@
-"""The dataflow executor (default): ONE persistent launch per wave runs every non-fused step of every level; a tile waits on
+"""The dataflow executor: ONE persistent launch per wave runs every non-fused step of every level; a tile waits on
 the completion counters of the instances producing its operands instead of on a kernel boundary.  Replaces the recursive
-executor behind solve (/root/reference/src/dynamic_ob.jl:32).  Checked against the oracle and against the
-level-synchronous executor of round 1 (TB_LEVEL_SYNC=1), which shares no scheduling code with it."""
+executor behind solve (/root/reference/src/dynamic_ob.jl:32).  The engine picks it per call (few or light plans); here
+it is forced (TB_DATAFLOW=1) and checked against the oracle and against the level-synchronous executor (TB_LEVEL_SYNC=1),
+which shares no scheduling code with it."""
 import numpy as np
 import pytest
 
@@ -14,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["rr100_sc10_unit", "rr100_sc10_f32", "rr30_disconnected", "ksg8x8_sc6", "ksg7x7_sc8_nokernel"])
-def test_both_executors_on_golden(tb, engine, engine_levelsync, name):
+def test_both_executors_on_golden(tb, engine_dataflow, engine_levelsync, name):
+    engine = engine_dataflow
     rec = load_golden(name + ".json")
     et = np.dtype(rec["element_type"]).type
     brs = [to_sliced(b) for b in golden_branches(rec)]
@@ -24,7 +26,8 @@ def test_both_executors_on_golden(tb, engine, engine_levelsync, name):
 
 
 @pytest.mark.parametrize("flags", [0, 8, 16, 64, 64 | 8, 4, 2])
-def test_many_level_branches_and_launch_count(tb, engine, engine_levelsync, flags):
+def test_many_level_branches_and_launch_count(tb, engine_dataflow, engine_levelsync, flags):
+    engine = engine_dataflow
     """3-regular n=140 cut to sc 14: branches with 4-8 dependency levels of generic and GEMM steps.  Same vector from both
     executors and the oracle; the dataflow executor needs at most 3 launches per wave (fused, persistent, finalize)."""
     nv, edges = H.random_regular_graph(140, 3, 7)
@@ -48,7 +51,8 @@ def test_many_level_branches_and_launch_count(tb, engine, engine_levelsync, flag
             p.close()
 
 
-def test_dataflow_every_node_weighted_f32_with_gemm_steps(tb, engine):
+def test_dataflow_every_node_weighted_f32_with_gemm_steps(tb, engine_dataflow):
+    engine = engine_dataflow
     """K3 (FADD + FMNMX tiled GEMM) on a Float32-weighted instance (w = 1 + rand, /root/reference/test/dynamic_ob.jl:15)
     large enough (sc >= 18) to have tiled GEMM steps: every node bit-exact against the oracle's intermediates."""
     rng = np.random.default_rng(7)
@@ -89,7 +93,12 @@ def test_solo_waves_do_not_race_with_the_lanes(tb):
     probe = tb.Plan(to_sliced(big))
     need = probe.info().arena_elems * 2 + 4096
     probe.close()
-    eng = tb.Engine(0, arena_bytes=int(need * 1.5), max_wave=4)  # 4 lanes x cap < need: the big plan is always solo
+    import os
+    os.environ["TB_DATAFLOW"] = os.environ.get("TB_SOLO_TEST_EXECUTOR", "1")
+    try:
+        eng = tb.Engine(0, arena_bytes=int(need * 1.5), max_wave=4)  # 4 lanes x cap < need: the big plan is always solo
+    finally:
+        del os.environ["TB_DATAFLOW"]
     brs, want = [], []
     for rep in range(6):
         brs += small[rep * 4:(rep + 1) * 4] + [big]
@@ -101,7 +110,8 @@ def test_solo_waves_do_not_race_with_the_lanes(tb):
     eng.close()
 
 
-def test_profile_modes_agree(tb, engine):
+def test_profile_modes_agree(tb, engine_dataflow):
+    engine = engine_dataflow
     rec = load_golden("rr100_sc10_unit.json")
     brs = [to_sliced(b) for b in golden_branches(rec)]
     for mode in (1, 2):
@@ -114,3 +124,13 @@ def test_profile_modes_agree(tb, engine):
         for k in prof:
             assert uni[k] <= prof[k][0] + 1e-3  # a union is never longer than the sum
     engine.profile(0)
+
+
+def test_default_engine_picks_the_executor_per_call(tb, engine):
+    """few plans or light plans -> dataflow (3 launches per wave); many heavy plans -> one launch per level and kind"""
+    root = regular_root(150, 1000)  # one heavy plan, several levels
+    p = tb.Plan(to_sliced(root), engine=engine)
+    want = CO.contract_slices([root], np.float32)[0]
+    assert engine.contract(p) == want
+    assert engine.last_timing()[1] <= 3 and p.info().n_levels >= 3
+    p.close()

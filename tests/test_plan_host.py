@@ -213,3 +213,19 @@ def test_arena_reuse_is_safe_for_the_dataflow_executor(n, seed, flags):
     if n >= 130 and not flags:
         assert n_shared > 0  # reuse does happen
     p.close()
+
+
+def test_estimate_equals_plan_ops():
+    """tb_estimate (label-set pass only) returns exactly the ops / sc of the compiled plan: what the sharders balance"""
+    import tbcuda
+    from helpers import golden_branches, load_golden, regular_root, to_sliced
+    for n, seed in [(12, 1), (60, 5), (100, 7), (150, 1000)]:
+        s = to_sliced(regular_root(n, seed))
+        p = tbcuda.Plan(s)
+        st = p.info()
+        assert tbcuda.estimate(s) == (st.ops, st.sc)
+        p.close()
+    brs = golden_branches(load_golden("rr100_sc10_unit.json"))
+    assert tbcuda.estimate(to_sliced([b for b in brs if b.nv == 0][0] if any(b.nv == 0 for b in brs) else brs[0]))[0] >= 0
+    from tbcuda.multi_gpu import branch_cost
+    assert branch_cost(to_sliced(regular_root(60, 5))) == tbcuda.Plan(to_sliced(regular_root(60, 5))).info().ops
