@@ -330,7 +330,7 @@ class Ctx:
 
 
 def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=None, e2e_on=True, cpu_budget=15.0,
-                 cpu_on=True, sample_clocks=True):
+                 cpu_on=True, sample_clocks=True, min_timed_s=0.0):
     """measure one workload on the job's GPUs -> dict (the bench line without the process-level keys; None off rank 0)"""
     import torch
     import torch.distributed as dist
@@ -384,8 +384,7 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
         """tropical ops of every branch from tb_estimate (label-set pass only): each rank estimates a strided share,
         one all-reduce(sum) gives every rank the whole vector"""
         c = np.zeros(n_br)
-        for i in range(rank, n_br, world):
-            c[i] = tbcuda.estimate(sliced[i])[0]
+        c[rank::world] = tbcuda.estimate_many(sliced[rank::world], max(1, host_cores() // world))
         return all_sum(c)
 
     t0 = time.perf_counter()
@@ -434,11 +433,13 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
             return per_branch(full[0], np.arange(n_units))
         return per_branch(vals, idx)
 
-    my_batch = tbcuda.PlanBatch(my_plans, r_units[mine])  # handle array marshalled once, not once per step
+    my_batch = tbcuda.PlanBatch(my_plans, None)  # handle array marshalled once, not once per step
+    r_mine32 = r_units[mine].astype(np.float32)
 
     def step_resident():
         vals, status, _ = eng.contract_plans(my_batch)
-        return gather_units(vals)
+        # + r in element_type (Float32) arithmetic, as contract_slices does (src/dynamic_ob.jl:43)
+        return gather_units((vals.astype(np.float32) + r_mine32).astype(np.float64))
 
     def step_e2e():
         """the public call from host objects: (strong) estimate costs + LPT, compile, upload, contract, read back"""
@@ -468,9 +469,19 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
 
     def timed(fn, n_steps, n_warm, sampler=None):
         out = None
+        t_w = time.perf_counter()
         for _ in range(n_warm):
             out = fn()
         torch.cuda.synchronize()
+        if min_timed_s > 0:
+            # short workloads (a step of a millisecond): keep warming up until the clocks have ramped, and time enough
+            # steps that the timed region lasts min_timed_s (the step count is reported)
+            est = max((time.perf_counter() - t_w) / max(1, n_warm), 1e-5)
+            while time.perf_counter() - t_w < 0.4 * min_timed_s:
+                out = fn()
+            torch.cuda.synchronize()
+            n_steps = max(n_steps, int(np.ceil(min_timed_s / est)))
+        timed.steps = n_steps
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -498,6 +509,7 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
     #      launch-rich workloads, measured on cfg2)
     sampler = ClockSampler(cx.local_rank) if (rank == 0 and sample_clocks) else None
     ms_step, result, per_step_ms = timed(step_resident, steps, max(warmup, 3), sampler)
+    steps_timed = timed.steps
     clocks = sampler.stop() if sampler else None
     launches_step = eng.last_timing()[1]
     dev_ms_last = eng.last_timing()[0]
@@ -521,7 +533,7 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
         if slice_k > 0:  # tb_last_transfers covers one call; a sliced step makes one call per branch
             hb = hb * sum(1 for s in sliced if s.code is not None)
         e2e = {"value": total_ops / (ms_e2e * 1e-3) * 1e-9, "unit": "Gop/s", "h2d_bytes_per_step": int(hb[0]),
-               "d2h_bytes_per_step": int(hb[1]), "ms_per_step": ms_e2e, "steps": steps, "warmup": 2,
+               "d2h_bytes_per_step": int(hb[1]), "ms_per_step": ms_e2e, "steps": timed.steps, "warmup": 2,
                "host_breakdown_rank0": eng.last_host_breakdown(),
                "slices_per_s": copies * n_units / (ms_e2e * 1e-3),
                "vs_resident": ms_step / ms_e2e}
@@ -575,7 +587,8 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
                "dtype": "f32" if f32 else ("int16x2" if i16 else "int32"), "config": config,
                "slices_per_s": copies * n_units / (ms_step * 1e-3), "branches": copies * n_br, "units": copies * n_units,
                "total_ops": total_ops, "mis": float(np.max(result)),
-               "gpu_launches": int(launches_step * steps * world),  # rank 0's launches per step x ranks (LPT shards are alike)
+               "gpu_launches": int(launches_step * steps_timed * world),  # rank 0's launches per step x ranks (LPT shards are alike)
+               "steps_timed": steps_timed,
                "launches_per_step": int(launches_step), "device_ms_last_step": dev_ms_last,
                "plan_compile_s_this_rank": plan_s, "clocks": clocks, "roofline": roofline}
         gold = golden_record(name)
@@ -689,16 +702,17 @@ def main():
                 continue
             n_steps = min(args.steps, 10)
             r = run_workload(cx, wl, args.scaling, n_steps, 3, None, None, e2e_on=not args.no_e2e,
-                             cpu_budget=min(args.cpu_budget, 4.0), cpu_on=not args.no_cpu_baseline, sample_clocks=False)
-            others[wl] = {"value": r["value"], "unit": "Gop/s", "ms_per_step": r["ms_per_step"], "steps": n_steps,
+                             cpu_budget=min(args.cpu_budget, 4.0), cpu_on=not args.no_cpu_baseline, sample_clocks=False,
+                             min_timed_s=0.5)
+            others[wl] = {"value": r["value"], "unit": "Gop/s", "ms_per_step": r["ms_per_step"], "steps": r["steps_timed"],
                           "units": r["units"], "slices_per_s": r["slices_per_s"], "launches_per_step": r["launches_per_step"],
                           "mis": r["mis"], "agrees_with_golden": r.get("agrees_with_golden"),
                           "kernel_frac_of_dpx_peak": r["roofline"]["frac"],
                           "kernel_frac_single_lane": r["roofline"]["frac_single_lane"],
                           "whole_step_frac_of_dpx_peak": r["roofline"]["frac_whole_step"],
                           "e2e": ({"value": r["e2e"]["value"], "ms_per_step": r["e2e"]["ms_per_step"],
-                                   "vs_resident": r["e2e"]["vs_resident"],
-                                   "compile_wait_ms": r["e2e"]["host_breakdown_rank0"].get("compile_ms")} if "e2e" in r else None),
+                                   "vs_resident": r["e2e"]["vs_resident"], "steps": r["e2e"]["steps"],
+                                   "host_breakdown": r["e2e"]["host_breakdown_rank0"]} if "e2e" in r else None),
                           "cpu_port_gops": r.get("cpu_baseline", {}).get("value"),
                           "agrees_with_cpu": r.get("cpu_baseline", {}).get("agrees_with_gpu"),
                           "workload": r["config"]["workload"]}

@@ -52,7 +52,12 @@ typedef enum tb_value_type {
     TB_VALUE_AUTO = 0,   /* integer weights: packed int16 if sum |w| < 8192 (unless TB_PLAN_NO_I16), else int32; real weights: f32 */
     TB_VALUE_I32 = 1,    /* exact; -inf is the sentinel -2^30 */
     TB_VALUE_F32 = 2,    /* Tropical{Float32}; -inf is IEEE -inf */
-    TB_VALUE_I16X2 = 3   /* int16 values, packed pairs in the GEMM (VIADDMNMX.S16x2); -inf is -2^14; needs sum |w| < 2^13 */
+    TB_VALUE_I16X2 = 3,  /* int16 values, packed pairs in the GEMM (VIADDMNMX.S16x2); -inf is -2^14; needs sum |w| < 2^13 */
+    TB_VALUE_F64 = 4,    /* Tropical{Float64}: element_type = Float64 with real weights.  Never picked by AUTO; generic +
+                            fused kernels only (no tiled GEMM kernel for 8-byte values) */
+    TB_VALUE_SIZE_CONFIG = 5 /* size + ONE optimal configuration per element (the SingleConfigMax element type of the
+                            branching tables, src/branch.jl:79): int64 = size << 32 | vertex mask.  Needs n_labels <= 32 and
+                            integer weights; read back with tb_contract_table */
 } tb_value_type;
 
 typedef enum tb_weight_dtype {
@@ -189,6 +194,8 @@ int tb_device_count(const tb_ctx* ctx);
 /* the cost a sharder needs, without compiling: tropical ops (the reference's 2^tc, src/types.jl:120) and sc (:121) from
  * the label-set pass alone, ~4x cheaper than tb_plan_create.  Host-only.  out_sc may be NULL. */
 int tb_estimate(const tb_network* net, double* out_ops, double* out_sc);
+/* the same for a whole branch list on `threads` host threads (0 = all cores); out_sc may be NULL; n_leaves == 0 gives 0 */
+int tb_estimate_many(const tb_network* nets, int64_t n, int32_t threads, double* out_ops, double* out_sc);
 const char* tb_last_error(const tb_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
 
 /* replaces uncompress(branch.code) + GenericTensorNetwork(...) (src/dynamic_ob.jl:31, src/types.jl:75-79):
@@ -267,6 +274,16 @@ int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int
  * layout in out_labels, bit 0 first.  out_data == NULL only queries rank / labels. */
 int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels,
                        int32_t* out_rank);
+
+/* The configuration-enumerating half of the branching table (branching_table(p, TensorNetworkSolver(),
+ * region), src/branch.jl:79 [upstream OptimalBranchingMIS]): for a region's network created with value_type
+ * TB_VALUE_SIZE_CONFIG and its boundary vertices as open_labels, contracts the plan and returns, for every one of the
+ * 2^rank boundary configurations (layout in out_labels, bit 0 first): out_sizes = the best size of an independent set of
+ * the region compatible with it (-inf if none) and out_configs = ONE such optimal set as a vertex bit mask (bit v =
+ * vertex / label v, boundary vertices included).  Ties are broken towards the larger mask, so the answer is deterministic.
+ * out_sizes == NULL only queries rank / labels. */
+int tb_contract_table(tb_ctx* ctx, tb_plan* plan, double* out_sizes, uint32_t* out_configs, int64_t cap, int32_t* out_labels,
+                      int32_t* out_rank);
 
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */

@@ -70,7 +70,11 @@ struct FlatBranch   # keeps the arrays alive while the C call runs
     open::Vector{Int32}; weights::Any; net::TbNetwork
 end
 
-function FlatBranch(branch::SlicedBranch)
+# tb_value_type: 0 = AUTO (exact integers for unit / integer weights, Tropical{Float32} for real weights),
+# 4 = Tropical{Float64} (element_type Float64 with real weights; slower: no tiled GEMM kernel for 8-byte values)
+value_type_for(::Type{T}, w) where {T} = (T === Float64 && !integer_valued(w)) ? Int32(4) : Int32(0)
+
+function FlatBranch(branch::SlicedBranch, element_type::Type = Float32)
     code = branch.code::CompressedEinsum
     ixs = code.ixs
     leaf_off = Int32[0]; leaf_labels = Int32[]
@@ -85,7 +89,7 @@ function FlatBranch(branch::SlicedBranch)
     net = TbNetwork(nv(branch.p.g), length(ixs), pointer(leaf_off), pointer(leaf_labels), length(open),
                     isempty(open) ? C_NULL : pointer(open), isempty(left) ? C_NULL : pointer(left),
                     isempty(right) ? C_NULL : pointer(right), unit ? C_NULL : Ptr{Cvoid}(pointer(wv)),
-                    unit ? Int32(0) : weight_code(eltype(wv)), Int32(0), UInt32(0), Int32(0), C_NULL, C_NULL)
+                    unit ? Int32(0) : weight_code(eltype(wv)), value_type_for(element_type, w), UInt32(0), Int32(0), C_NULL, C_NULL)
     return FlatBranch(leaf_off, leaf_labels, left, right, open, wv, net)
 end
 
@@ -99,7 +103,7 @@ function contract_slices_cuda(branches::Vector{SlicedBranch}, element_type::Type
         if nv(b.p.g) == 0 || isnothing(b.code)
             flats[i] = nothing; nets[i] = empty_net
         else
-            flats[i] = FlatBranch(b); nets[i] = flats[i].net
+            flats[i] = FlatBranch(b, element_type); nets[i] = flats[i].net
         end
     end
     vals = Vector{Float64}(undef, n); status = Vector{Int32}(undef, n); mx = Ref{Float64}(0)
@@ -187,10 +191,10 @@ end
 # recurse), so these methods are strictly more specific in the element type -- `Type{T} where T<:AbstractFloat` wins the
 # dispatch for Float32 / Float64 -- and the usecuda=false branch reaches the reference's own method through `invoke` with
 # the original, less specific signature.  (A maintainer would rather add the two-line hook shown in INTEGRATION.md.)
-# The device computes exactly in integers (unit / integer-valued weights, any float container) or in Tropical{Float32}.
-# A Float64 element type with real weights would silently lose precision there, so such calls stay with the reference.
+# The device computes exactly in integers (unit / integer-valued weights, any float container), in Tropical{Float32}, or
+# -- element_type Float64 with real weights -- in Tropical{Float64} (value_type_for).  Other float types stay with the reference.
 integer_valued(w) = w isa TensorBranching.UnitWeight || all(isinteger, w)
-on_device(branch::SlicedBranch, ::Type{T}) where {T} = T === Float32 || integer_valued(branch.p.weights)
+on_device(branch::SlicedBranch, ::Type{T}) where {T} = T === Float32 || T === Float64 || integer_valued(branch.p.weights)
 
 function TensorBranching.contract_slices(branches::Vector{SlicedBranch}, element_type::Type{T}, usecuda::Bool) where {T <: AbstractFloat}
     usecuda && all(b -> on_device(b, T), branches) && return contract_slices_cuda(branches, element_type)

@@ -9,6 +9,7 @@ import subprocess
 import sys
 
 rep, dump, out, note = sys.argv[1:5]
+skip = int(sys.argv[5]) if len(sys.argv) > 5 else 0  # launches of the kernel skipped by ncu (--launch-skip)
 METRICS = ["dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
            "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "sm__inst_executed_pipe_alu.sum", "lts__t_bytes.sum",
@@ -50,6 +51,7 @@ for ln in open(dump):
     f = ln.strip().split(",")
     if len(f) >= 7 and int(f[0]) == 2:
         eng.append(dict(event_ms=float(f[2]) - float(f[1]), ops=float(f[3]), algorithmic_bytes=float(f[4]), instances=int(f[5]), tiles=int(f[6])))
+eng = eng[skip:]
 n = min(len(launches), len(eng))
 joined = []
 for a, b in zip(launches[:n], eng[:n]):

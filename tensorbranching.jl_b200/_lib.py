@@ -16,7 +16,7 @@ TB_ERR_CUDA = -5
 TB_ERR_NCCL = -6
 TB_ERR_INTERNAL = -7
 
-TB_VALUE_AUTO, TB_VALUE_I32, TB_VALUE_F32, TB_VALUE_I16X2 = 0, 1, 2, 3
+TB_VALUE_AUTO, TB_VALUE_I32, TB_VALUE_F32, TB_VALUE_I16X2, TB_VALUE_F64, TB_VALUE_SIZE_CONFIG = 0, 1, 2, 3, 4, 5
 TB_WEIGHT_UNIT, TB_WEIGHT_I32, TB_WEIGHT_I64, TB_WEIGHT_F32, TB_WEIGHT_F64 = 0, 1, 2, 3, 4
 TB_PLAN_KEEP_INTERMEDIATES = 1
 TB_PLAN_NO_FUSED_SUBTREES = 2
@@ -63,9 +63,9 @@ class tb_step_info(C.Structure):
 
 
 # every symbol include/tbcuda.h declares
-EXPORTS = ["tb_version", "tb_init", "tb_init_multi", "tb_device_count", "tb_estimate", "tb_shutdown", "tb_last_error", "tb_plan_create", "tb_plan_destroy",
+EXPORTS = ["tb_version", "tb_init", "tb_init_multi", "tb_device_count", "tb_estimate", "tb_estimate_many", "tb_shutdown", "tb_last_error", "tb_plan_create", "tb_plan_destroy",
            "tb_plan_info", "tb_plan_export", "tb_plan_export_raw", "tb_contract", "tb_contract_batch",
-           "tb_contract_networks", "tb_contract_sliced", "tb_suggest_slices", "tb_stream_begin", "tb_stream_push", "tb_stream_finish", "tb_contract_tensor", "tb_plan_reassign", "tb_plan_read_tensor", "tb_last_timing", "tb_permute_bits", "tb_set_stream", "tb_profile",
+           "tb_contract_networks", "tb_contract_sliced", "tb_suggest_slices", "tb_stream_begin", "tb_stream_push", "tb_stream_finish", "tb_contract_tensor", "tb_contract_table", "tb_plan_reassign", "tb_plan_read_tensor", "tb_last_timing", "tb_permute_bits", "tb_set_stream", "tb_profile",
            "tb_last_profile", "tb_last_profile_union", "tb_last_transfers", "tb_last_host_breakdown"]
 
 _lib = None
@@ -94,6 +94,7 @@ def load():
     lib.tb_init_multi.argtypes = [C.POINTER(C.c_int32), C.c_int32, C.POINTER(tb_options), C.POINTER(vp)]
     lib.tb_device_count.argtypes = [vp]
     lib.tb_estimate.argtypes = [C.POINTER(tb_network), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.tb_estimate_many.argtypes = [C.POINTER(tb_network), C.c_int64, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.tb_shutdown.argtypes = [vp]
     lib.tb_plan_create.argtypes = [vp, C.POINTER(tb_network), C.POINTER(vp)]
     lib.tb_plan_destroy.argtypes = [vp]
@@ -109,6 +110,8 @@ def load():
     lib.tb_contract_sliced.argtypes = [vp, C.POINTER(tb_network), C.POINTER(C.c_int32), C.c_int32, C.c_int64, C.c_int64,
                                        C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     lib.tb_contract_tensor.argtypes = [vp, vp, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.tb_contract_table.argtypes = [vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_uint32), C.c_int64, C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32)]
     lib.tb_plan_reassign.argtypes = [vp, C.POINTER(C.c_uint8), C.POINTER(vp)]
     lib.tb_stream_begin.argtypes = [vp, C.c_int64, C.POINTER(vp)]
     lib.tb_stream_push.argtypes = [vp, C.POINTER(tb_network), C.POINTER(C.c_double), C.c_int64]

@@ -39,13 +39,14 @@ def _weight_desc(weights, n_labels):
 
 def _value_type_for(element_type, weight_code):
     """element_type of the reference -> tb_value_type.  Integer-valued problems (UnitWeight / integer
-    weights) are computed exactly in int32 whatever float container is asked for; real weights need
-    Float32 (the only float width the device kernels implement)."""
+    weights) are computed exactly in integers whatever float container is asked for; real weights are computed in
+    Tropical{Float32}, or in Tropical{Float64} when element_type is Float64 (generic + fused kernels only: there is no
+    tiled GEMM kernel for 8-byte values)."""
     et = np.dtype(element_type) if element_type is not None else None
     if weight_code in (L.TB_WEIGHT_UNIT, L.TB_WEIGHT_I32, L.TB_WEIGHT_I64):
-        return L.TB_VALUE_AUTO  # int32, or packed int16 when the plan flags prefer it and the weights fit
+        return L.TB_VALUE_AUTO  # packed int16 when the weights fit, else int32
     if et is not None and et == np.float64:
-        raise L.TBError(L.TB_ERR_UNSUPPORTED, "element_type Float64 with real weights is not implemented on the device (use Float32)")
+        return L.TB_VALUE_F64
     return L.TB_VALUE_F32
 
 
@@ -96,13 +97,17 @@ class Plan:
     """Compiled, device-resident form of one branch's contraction (tb_plan)."""
 
     def __init__(self, branch: SlicedBranch, element_type=np.float32, flags=0, engine: "Engine" = None,
-                 fixed: Optional[dict] = None):
-        """fixed: {label: 0 | 1} -- index slicing, the labels this contraction holds at one value."""
+                 fixed: Optional[dict] = None, value_type: Optional[int] = None):
+        """fixed: {label: 0 | 1} -- index slicing, the labels this contraction holds at one value.
+        value_type: a tb_value_type overriding what element_type implies (TB_VALUE_SIZE_CONFIG for the branching tables)."""
         lib = L.load()
         self._lib = lib
         self.handle = C.c_void_p()
         net, w = _network_of(branch, element_type, flags)
         self._keep = (branch, w)
+        if value_type is not None:
+            net = L.tb_network.from_buffer_copy(bytes(net))
+            net.value_type = int(value_type)
         if fixed:
             net = L.tb_network.from_buffer_copy(bytes(net))
             fl = np.asarray(list(fixed.keys()), dtype=np.int32)
@@ -215,6 +220,19 @@ class Engine:
         L.check(self._lib.tb_contract_tensor(self.handle, plan.handle, data.ctypes.data_as(C.POINTER(C.c_double)),
                                              data.size, labels, C.byref(rank)), self.handle)
         return list(labels[:rank.value]), data
+
+    def contract_table(self, plan: Plan):
+        """tb_contract_table (plan created with value_type=TB_VALUE_SIZE_CONFIG and open labels): per boundary configuration
+        the best size and one optimal vertex set.  -> (labels bit-0-first, sizes float64[2^rank], configs uint32[2^rank])"""
+        labels = (C.c_int32 * 32)()
+        rank = C.c_int32()
+        L.check(self._lib.tb_contract_table(self.handle, plan.handle, None, None, 0, labels, C.byref(rank)), self.handle)
+        n = 1 << rank.value
+        sizes = np.empty(n, dtype=np.float64)
+        cfgs = np.zeros(n, dtype=np.uint32)
+        L.check(self._lib.tb_contract_table(self.handle, plan.handle, sizes.ctypes.data_as(C.POINTER(C.c_double)),
+                                            cfgs.ctypes.data_as(C.POINTER(C.c_uint32)), n, labels, C.byref(rank)), self.handle)
+        return list(labels[:rank.value]), sizes, cfgs
 
     # -- batches -----------------------------------------------------------------------------
     def contract_plans(self, plans, r: Optional[np.ndarray] = None):
@@ -462,6 +480,19 @@ def estimate(branch: SlicedBranch):
     sc_ = C.c_double()
     L.check(lib.tb_estimate(C.byref(net), C.byref(ops), C.byref(sc_)))
     return ops.value, sc_.value
+
+
+def estimate_many(branches: Sequence[SlicedBranch], threads: int = 0) -> np.ndarray:
+    """tb_estimate_many: tropical ops of every branch (0 for an empty graph) in ONE multi-threaded C call."""
+    n = len(branches)
+    if n == 0:
+        return np.zeros(0)
+    lib = L.load()
+    parts = [_EMPTY_NET_BYTES if (br.p.nv == 0 or br.code is None) else _network_bytes(br, np.float32, 0) for br in branches]
+    nets = (L.tb_network * n).from_buffer_copy(b"".join(parts))
+    ops = np.zeros(n, dtype=np.float64)
+    L.check(lib.tb_estimate_many(nets, n, threads, ops.ctypes.data_as(C.POINTER(C.c_double)), None))
+    return ops
 
 
 def suggest_slices(branch: SlicedBranch, sc_target: int = -1, max_sliced: int = 8):

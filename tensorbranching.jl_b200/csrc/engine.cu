@@ -413,7 +413,9 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
             k_generic<T><<<L.grid, BIG_THREADS, 0, st>>>((const BigInst*)(dbase + L.inst_off), (const uint32_t*)(dbase + L.starts_off), L.n_insts);
             break;
         case 2:
-            if constexpr (std::is_same<T, int16_t>::value) {
+            if constexpr (sizeof(T) == 8) {
+                // 8-byte value types are compiled with TB_PLAN_NO_GEMM: no such launch exists
+            } else if constexpr (std::is_same<T, int16_t>::value) {
                 uint32_t grid = std::min<uint32_t>(L.grid, (uint32_t)(std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count));
                 if (L.done_off != kNoDone) grid = std::min<uint32_t>(grid, dataflow_grid_cap(ctx));
                 if (L.done_off == kNoDone)
@@ -448,7 +450,8 @@ void launch_one(tb_ctx* ctx, const Launch& L, uint8_t* dbase) {
 int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& idx, int vt, std::vector<int32_t>& status,
               bool single_plan_mode) {
     if (idx.empty()) return TB_OK;
-    const size_t elem = vt == TB_VALUE_I16X2 ? 2 : 4;
+    const size_t elem = (size_t)Plan::elem_size_of(vt);
+    const bool wide = elem == 8;  // Tropical{Float64} / size+configuration: no persistent GEMM kernel to host a dataflow launch
     // ---- waves
     size_t max_need = 0;
     for (int64_t i : idx) max_need = std::max(max_need, (size_t)plans[i]->p.arena_elems * elem + 256);
@@ -603,7 +606,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 launches.push_back(L);
             }
         }
-        if (ctx->dataflow) {
+        if (ctx->dataflow && !wide) {
             // ---- dataflow: every big step of every member, level-major, in ONE persistent launch.  A tile waits on the
             // completion counters of the instances that produce its operands (BigInst::dep_a / dep_b) instead of on a
             // kernel boundary; tiles are handed out in this (topological) order, so the kernel cannot deadlock.
@@ -815,6 +818,8 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
         }
         if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)sl->d);
         else if (vt == TB_VALUE_I16X2) launch_one<int16_t>(ctx, L, (uint8_t*)sl->d);
+        else if (vt == TB_VALUE_F64) launch_one<double>(ctx, L, (uint8_t*)sl->d);
+        else if (vt == TB_VALUE_SIZE_CONFIG) launch_one<long long>(ctx, L, (uint8_t*)sl->d);
         else launch_one<float>(ctx, L, (uint8_t*)sl->d);
         if (ctx->profile_mode) {
             TB_CUDA(ctx, cudaEventRecord(pr.e1, st));
@@ -846,17 +851,17 @@ int enqueue_batch(tb_ctx* ctx, tb_plan* const* plans, int64_t lo, int64_t hi, st
     int rc = ensure_uploaded(ctx, plans + lo, hi - lo);
     if (rc) return rc;
     ctx->host_ms[1] += now_ms() - t_u0;
-    std::vector<int64_t> gi, gf, gh;
+    std::vector<int64_t> groups[6];  // by tb_value_type
     for (int64_t i = lo; i < hi; ++i) {
         if (!plans[i]) continue;
         const int v = plans[i]->p.value_type;
-        (v == TB_VALUE_I32 ? gi : v == TB_VALUE_I16X2 ? gh : gf).push_back(i);
+        groups[(v >= 1 && v <= 5) ? v : TB_VALUE_F32].push_back(i);
     }
-    rc = run_group(ctx, plans, gi, TB_VALUE_I32, status, single);
-    if (rc) return rc;
-    rc = run_group(ctx, plans, gh, TB_VALUE_I16X2, status, single);
-    if (rc) return rc;
-    return run_group(ctx, plans, gf, TB_VALUE_F32, status, single);
+    for (int v : {(int)TB_VALUE_I32, (int)TB_VALUE_I16X2, (int)TB_VALUE_F32, (int)TB_VALUE_F64, (int)TB_VALUE_SIZE_CONFIG}) {
+        rc = run_group(ctx, plans, groups[v], v, status, single);
+        if (rc) return rc;
+    }
+    return TB_OK;
 }
 
 int begin_call(tb_ctx* ctx, int64_t n) {
@@ -1096,6 +1101,8 @@ int copy_tensor_to_host(tb_ctx* ctx, const Plan& P, int64_t off, int64_t n, doub
     const uint8_t* src = (const uint8_t*)ctx->arena + (size_t)(ctx->last_plan_arena_base_elems + off) * (size_t)P.elem_size();
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (P.value_type == TB_VALUE_I32) k_to_double<int32_t><<<blocks, 256, 0, ctx->stream>>>((const int32_t*)src, d_tmp, n);
+    else if (P.value_type == TB_VALUE_F64) k_to_double<double><<<blocks, 256, 0, ctx->stream>>>((const double*)src, d_tmp, n);
+    else if (P.value_type == TB_VALUE_SIZE_CONFIG) k_to_double<long long><<<blocks, 256, 0, ctx->stream>>>((const long long*)src, d_tmp, n);
     else if (P.value_type == TB_VALUE_I16X2) k_to_double<int16_t><<<blocks, 256, 0, ctx->stream>>>((const int16_t*)src, d_tmp, n);
     else k_to_double<float><<<blocks, 256, 0, ctx->stream>>>((const float*)src, d_tmp, n);
     cudaError_t e = cudaMemcpyAsync(out_data, d_tmp, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
@@ -1193,6 +1200,8 @@ int tb_init(const tb_options* opts, tb_ctx** out_ctx) try {
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
+    TB_CUDA(nullptr, cudaFuncSetAttribute(k_fused_subtrees<long long>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemMax));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     TB_CUDA(nullptr, cudaFuncSetAttribute(k_gemm<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
     {
@@ -1279,6 +1288,46 @@ int tb_estimate(const tb_network* net, double* out_ops, double* out_sc) try {
     if (rc) return set_err(nullptr, rc, err);
     *out_ops = P.stats.ops;
     if (out_sc) *out_sc = P.stats.sc;
+    return TB_OK;
+} TB_CATCH(nullptr)
+
+int tb_estimate_many(const tb_network* nets, int64_t n, int32_t threads, double* out_ops, double* out_sc) try {
+    if (n < 0 || (n > 0 && (!nets || !out_ops))) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "nets / out_ops is NULL");
+    int nt = threads > 0 ? threads : std::max(1, (int)std::thread::hardware_concurrency());
+    nt = std::max(1, std::min<int>(nt, (int)std::max<int64_t>(1, n / 16)));
+    std::atomic<int64_t> next{0};
+    std::atomic<int> bad{TB_OK};
+    std::mutex mu;
+    std::string first_err;
+    auto worker = [&] {
+        for (;;) {
+            const int64_t i = next.fetch_add(1);
+            if (i >= n) break;
+            double ops = 0, sc = 0;
+            if (nets[i].n_leaves != 0) {
+                Plan P;
+                std::string err;
+                const int rc = compile_plan(nets[i], TB_PLAN_ESTIMATE_ONLY, P, err);
+                if (rc) {
+                    std::lock_guard<std::mutex> g(mu);
+                    if (bad.load() == TB_OK) {
+                        bad.store(rc);
+                        first_err = "branch " + std::to_string(i) + ": " + err;
+                    }
+                    continue;
+                }
+                ops = P.stats.ops;
+                sc = P.stats.sc;
+            }
+            out_ops[i] = ops;
+            if (out_sc) out_sc[i] = sc;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt - 1; ++t) th.emplace_back(worker);
+    worker();
+    for (auto& t : th) t.join();
+    if (bad.load() != TB_OK) return set_err(nullptr, bad.load(), first_err);
     return TB_OK;
 } TB_CATCH(nullptr)
 
@@ -2182,6 +2231,27 @@ int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap
     int rc = contract_impl(ctx, arr, nullptr, 1, &first, nullptr, nullptr, true);
     if (rc) return rc;
     return copy_tensor_to_host(ctx, P, P.root_off, n, out_data);
+} TB_CATCH(ctx)
+
+int tb_contract_table(tb_ctx* ctx, tb_plan* plan, double* out_sizes, uint32_t* out_configs, int64_t cap, int32_t* out_labels,
+                      int32_t* out_rank) try {
+    if (!ctx || !plan) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / plan is NULL");
+    if (!ctx->subs.empty()) return tb_contract_table(ctx->subs[0], plan, out_sizes, out_configs, cap, out_labels, out_rank);
+    const Plan& P = plan->p;
+    if (P.value_type != TB_VALUE_SIZE_CONFIG)
+        return set_err(ctx, TB_ERR_BAD_ARGUMENT, "tb_contract_table needs a plan created with value_type TB_VALUE_SIZE_CONFIG");
+    int rc = tb_contract_tensor(ctx, plan, out_sizes, cap, out_labels, out_rank);  // contracts; sizes of the root tensor
+    if (rc || !out_sizes || !out_configs) return rc;
+    const int64_t n = (int64_t)1 << P.rank(P.root_id);
+    uint32_t* d_cfg = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&d_cfg, (size_t)n * sizeof(uint32_t)));
+    const long long* src = (const long long*)ctx->arena + (ctx->last_plan_arena_base_elems + P.root_off);
+    k_to_config<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, d_cfg, n);
+    cudaError_t e = cudaMemcpyAsync(out_configs, d_cfg, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_cfg);
+    if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
+    return TB_OK;
 } TB_CATCH(ctx)
 
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {

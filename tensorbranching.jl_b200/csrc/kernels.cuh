@@ -47,6 +47,28 @@ template <> struct Ops<float> {
     static __device__ __forceinline__ double to_double(float v) { return (double)v; }
 };
 
+// 8-byte value types (no tiled GEMM kernel: generic + fused kernels only; small problems by construction)
+struct alignas(16) Double4 { double x, y, z, w; };
+struct alignas(16) Long4 { long long x, y, z, w; };
+template <> struct Ops<double> {  // Tropical{Float64}
+    typedef Double4 vec4;
+    static __device__ __forceinline__ double neg_inf() { return -INFINITY; }
+    static __device__ __forceinline__ double addmax(double a, double b, double c) { return fmax(__dadd_rn(a, b), c); }
+    static __device__ __forceinline__ double vmax(double a, double b) { return fmax(a, b); }
+    static __device__ __forceinline__ double to_double(double v) { return v; }
+};
+// "size + one optimal configuration" (the SingleConfigMax element of the branching tables) as ONE int64:
+// high 32 bits = size (int32, -2^30 = tropical zero), low 32 bits = bit mask of the chosen vertices.  Every vertex leaf is
+// used exactly once in a contraction tree, so the masks of two operands of a node are disjoint: a (x) b = a + b (the masks
+// OR, no carry into the size), a (+) b = max(a, b) (size first, ties by mask): plain max-plus on int64.
+template <> struct Ops<long long> {
+    typedef Long4 vec4;
+    static __device__ __forceinline__ long long neg_inf() { return -(1ll << 62); }
+    static __device__ __forceinline__ long long addmax(long long a, long long b, long long c) { return max(a + b, c); }
+    static __device__ __forceinline__ long long vmax(long long a, long long b) { return max(a, b); }
+    static __device__ __forceinline__ double to_double(long long v) { return (v >> 32) <= -(1ll << 29) ? -INFINITY : (double)(v >> 32); }
+};
+
 template <typename T> __device__ __forceinline__ T shfl_xor_t(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 template <> __device__ __forceinline__ int16_t shfl_xor_t<int16_t>(int16_t v, int m) {
     return (int16_t)__shfl_xor_sync(0xffffffffu, (int)v, m);
@@ -67,6 +89,14 @@ template <> __device__ __forceinline__ float dot16<float>(const float* a, const 
     acc = fmaxf(__fadd_rn(x.y, y.y), acc);
     acc = fmaxf(__fadd_rn(x.z, y.z), acc);
     return fmaxf(__fadd_rn(x.w, y.w), acc);
+}
+template <> __device__ __forceinline__ double dot16<double>(const double* a, const double* b, double acc) {
+    acc = fmax(__dadd_rn(a[0], b[0]), acc);
+    return fmax(__dadd_rn(a[1], b[1]), acc);
+}
+template <> __device__ __forceinline__ long long dot16<long long>(const long long* a, const long long* b, long long acc) {
+    acc = max(a[0] + b[0], acc);
+    return max(a[1] + b[1], acc);
 }
 template <> __device__ __forceinline__ int16_t dot16<int16_t>(const int16_t* a, const int16_t* b, int16_t acc) {
     const uint4 x = *reinterpret_cast<const uint4*>(a), y = *reinterpret_cast<const uint4*>(b);
@@ -1616,6 +1646,12 @@ __global__ void k_finalize(const FinalInst* __restrict__ f, int n, double* __res
 __global__ void k_fill_double(double* __restrict__ dst, int64_t n, double v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = v;
+}
+
+// low 32 bits of the size + configuration elements: the chosen vertices (0 where the element is tropical zero)
+__global__ void k_to_config(const long long* __restrict__ src, uint32_t* __restrict__ dst, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (src[i] >> 32) <= -(1ll << 29) ? 0u : (uint32_t)(src[i] & 0xffffffffll);
 }
 
 template <typename T>

@@ -255,7 +255,13 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         vt = int_weights ? TB_VALUE_I32 : TB_VALUE_F32;
         auto_i16 = int_weights && !(P.flags & TB_PLAN_NO_I16);  // falls back to int32 below if the weights do not fit
     }
-    if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32 && vt != TB_VALUE_I16X2) return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
+    if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32 && vt != TB_VALUE_I16X2 && vt != TB_VALUE_F64 && vt != TB_VALUE_SIZE_CONFIG)
+        return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
+    const bool wide = (vt == TB_VALUE_F64 || vt == TB_VALUE_SIZE_CONFIG);  // 8-byte values: generic + fused kernels only
+    if (wide) P.flags |= TB_PLAN_NO_GEMM;
+    if (vt == TB_VALUE_SIZE_CONFIG && net.n_labels > 32)
+        return fail(TB_ERR_UNSUPPORTED, "value type size+configuration keeps the chosen vertices in a 32-bit mask: at most 32 labels "
+                                        "(regions of the branching tables have <= n_max = 20 vertices, src/types.jl:10)");
     if (vt == TB_VALUE_I16X2 || auto_i16) {
         // packed int16 needs every partial sum < 2^13: check sum |w| over the vertex leaves
         double sum_abs = 0;
@@ -757,7 +763,8 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
     // ---- pool (leaf tensors)
     std::vector<int32_t> leaf_pool_off(nT, 0);
     {
-        auto push_val = [&](double x, bool neg_inf) { P.pool.push_back(Plan::encode_value(vt, x, neg_inf)); };
+        auto push_val = [&](double x, bool neg_inf, int cfg_bit = -1) { P.pool.push_back(Plan::encode_value(vt, x, neg_inf, cfg_bit)); };
+        const bool int_values = (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2 || vt == TB_VALUE_SIZE_CONFIG);
         P.pool.reserve(8 + 2 * (size_t)nL + 4);
         push_val(0, false); push_val(0, false); push_val(0, false); push_val(0, true);  // edge
         push_val(0, false);                                                            // unit
@@ -773,13 +780,14 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 if (vtx >= 0) {
                     w = weight_of(vtx);
                     if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
-                    if (vt != TB_VALUE_F32) {
+                    if (int_values) {
                         if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
                         sum_abs += std::fabs(w);
                         if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
                     }
                 }
                 Plan::PoolPatch pp{};
+                pp.vtx = vtx;
                 pp.off = (int32_t)P.pool.size();
                 pp.kind = (uint8_t)(vtx >= 0 ? 0 : (leaf_fb[i] < 0 ? 1 : 2));
                 pp.fa = leaf_fa[i];
@@ -796,14 +804,14 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             } else {
                 double w = weight_of(vtx);
                 if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
-                if (vt != TB_VALUE_F32) {
+                if (int_values) {
                     if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
                     sum_abs += std::fabs(w);
                     if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
                 }
                 leaf_pool_off[i] = (int32_t)P.pool.size();
                 push_val(0, false);
-                push_val(w, false);
+                push_val(w, false, vtx);  // size+configuration: choosing the vertex also sets its bit of the mask
             }
         }
         while (P.pool.size() % 4) P.pool.push_back(0);
@@ -827,7 +835,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         int64_t pB = leaf[B] ? 0 : peak[B], sB = leaf[B] ? 0 : size_of(B);
         int64_t pk = size_of(t) + (pA >= pB ? std::max(pA, sA + pB) : std::max(pB, sB + pA));
         peak[t] = pk;
-        fus[t] = ok && pk <= FUSED_SMEM_ELEMS;
+        fus[t] = ok && pk <= (wide ? FUSED_SMEM_ELEMS / 2 : FUSED_SMEM_ELEMS);  // 32 KB of values either way
     }
     P.loc.assign(nT, LOC_ARENA);
     P.off.assign(nT, 0);
@@ -951,7 +959,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         const NodeCls& c = cls[t];
         auto p2 = [](int e) { return (double)(1ull << e); };
         int tc = rank_of(t) + c.nk + c.nka + c.nkb - folded[t];
-        const double eb = half ? 2.0 : 4.0;
+        const double eb = (double)Plan::elem_size_of(vt);
         if (unary[t]) {  // second half of a split node: engine overhead, not algorithmic work
             bytes += eb * p2(rank_of(t));
             return;
@@ -1106,7 +1114,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
                 s.store_mode = c.kfirst;  // generic steps reuse this byte: K0-first operand layouts
                 int ks, po;
                 generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
-                if (ks == 0 && s.rc >= 10) {  // streaming node: 4 consecutive outputs per thread and iteration
+                if (ks == 0 && s.rc >= 10 && !wide) {  // streaming node: 4 consecutive outputs per thread and iteration
                     s.vec4 = 1;
                     po = s.rc >= 14 ? 12 : 10;  // 4096 outputs per CTA (4 iterations) amortise the per-CTA set-up
                 }
@@ -1235,7 +1243,7 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             }
             big_index[t] = (int32_t)P.big_steps.size();
             P.big_log2_ops.push_back((float)(rank_of(t) + c.nk + c.nka + c.nkb));
-            P.big_bytes.push_back((half ? 2.0 : 4.0) * (std::ldexp(1.0, rank_of(A)) + std::ldexp(1.0, rank_of(B)) + std::ldexp(1.0, rank_of(t))));
+            P.big_bytes.push_back((double)Plan::elem_size_of(vt) * (std::ldexp(1.0, rank_of(A)) + std::ldexp(1.0, rank_of(B)) + std::ldexp(1.0, rank_of(t))));
             P.big_dep_a.push_back(big_index[A]);  // -1 for leaves and fused subtrees
             P.big_dep_b.push_back(big_index[B]);
             P.big_steps.push_back(s);
@@ -1426,14 +1434,25 @@ tb_step_info Plan::step_info(size_t i) const {
     return s;
 }
 
-uint32_t Plan::encode_value(int vt, double x, bool neg_inf) {
-    uint32_t bits;
+uint64_t Plan::encode_value(int vt, double x, bool neg_inf, int config_bit) {
+    uint64_t bits = 0;
     if (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2) {
         int32_t v = neg_inf ? (vt == TB_VALUE_I16X2 ? Tropical<int16_t>::kNegInf : Tropical<int32_t>::kNegInf) : (int32_t)x;
-        std::memcpy(&bits, &v, 4);
-    } else {
+        uint32_t b32;
+        std::memcpy(&b32, &v, 4);
+        bits = b32;
+    } else if (vt == TB_VALUE_F32) {
         float v = neg_inf ? -std::numeric_limits<float>::infinity() : (float)x;
-        std::memcpy(&bits, &v, 4);
+        uint32_t b32;
+        std::memcpy(&b32, &v, 4);
+        bits = b32;
+    } else if (vt == TB_VALUE_F64) {
+        double v = neg_inf ? -std::numeric_limits<double>::infinity() : x;
+        std::memcpy(&bits, &v, 8);
+    } else {  // TB_VALUE_SIZE_CONFIG: size << 32 | vertex mask; tropical zero = -2^62 (size -2^30, empty mask)
+        int64_t v = neg_inf ? -((int64_t)1 << 62) : (int64_t)((uint64_t)(int64_t)x << 32);
+        if (!neg_inf && config_bit >= 0) v |= (int64_t)1 << config_bit;
+        std::memcpy(&bits, &v, 8);
     }
     return bits;
 }
@@ -1442,7 +1461,7 @@ void Plan::assign(const uint8_t* values) {
     for (const PoolPatch& pp : patches) {
         const bool a = values[pp.fa] != 0, b = pp.fb >= 0 && values[pp.fb] != 0;
         switch (pp.kind) {
-            case 0: pool[pp.off] = encode_value(value_type, a ? pp.w : 0.0, false); break;
+            case 0: pool[pp.off] = encode_value(value_type, a ? pp.w : 0.0, false, a ? pp.vtx : -1); break;
             case 1:
                 pool[pp.off] = encode_value(value_type, 0.0, false);
                 pool[pp.off + 1] = encode_value(value_type, 0.0, a);
@@ -1453,15 +1472,15 @@ void Plan::assign(const uint8_t* values) {
 }
 
 void Plan::write_pool(uint8_t* dst) const {
-    if (elem_size() == 4) {
-        if (!pool.empty()) std::memcpy(dst, pool.data(), pool.size() * 4);
+    const int es = elem_size();
+    if (es == 8) {
+        if (!pool.empty()) std::memcpy(dst, pool.data(), pool.size() * 8);
+    } else if (es == 4) {
+        uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+        for (size_t i = 0; i < pool.size(); ++i) d[i] = (uint32_t)pool[i];
     } else {
         int16_t* d = reinterpret_cast<int16_t*>(dst);
-        for (size_t i = 0; i < pool.size(); ++i) {
-            int32_t v;
-            std::memcpy(&v, &pool[i], 4);
-            d[i] = (int16_t)v;
-        }
+        for (size_t i = 0; i < pool.size(); ++i) d[i] = (int16_t)(int32_t)(uint32_t)pool[i];
     }
 }
 

@@ -30,7 +30,8 @@ struct Plan {
     std::vector<int32_t> level;                // -1 for leaves / interior of fused subtrees
 
     // descriptors
-    std::vector<uint32_t> pool;  // one 32-bit slot per pool element (int32 / float bits); narrowed to int16 on upload
+    std::vector<uint64_t> pool;  // one slot per pool element (int32 / float bits in the low half, double / int64 bits in full);
+                                 // narrowed to the value type's width on upload
     // index slicing: the pool words that depend on the values of the fixed labels.  A plan compiled for one assignment
     // becomes the plan of another by assign() alone (same descriptors, same layouts).
     struct PoolPatch {
@@ -38,12 +39,14 @@ struct Plan {
         uint8_t kind;     // 0 vertex leaf, 1 edge leaf with one end fixed, 2 edge leaf with both ends fixed
         int32_t fa, fb;   // positions of the leaf's fixed labels in the fixed-label list (fb = -1: none)
         double w;         // vertex weight (kind 0)
+        int32_t vtx;      // the vertex (kind 0): its bit of the configuration mask (TB_VALUE_SIZE_CONFIG)
     };
     std::vector<PoolPatch> patches;
     int n_fixed = 0;
     void assign(const uint8_t* values);  // values[i] = 0 / 1 for fixed label i
-    static uint32_t encode_value(int value_type, double x, bool neg_inf);
-    int elem_size() const { return value_type == TB_VALUE_I16X2 ? 2 : 4; }
+    static uint64_t encode_value(int value_type, double x, bool neg_inf, int config_bit = -1);
+    static int elem_size_of(int vt) { return vt == TB_VALUE_I16X2 ? 2 : (vt == TB_VALUE_F64 || vt == TB_VALUE_SIZE_CONFIG) ? 8 : 4; }
+    int elem_size() const { return elem_size_of(value_type); }
     size_t pool_bytes() const { return pool.size() * (size_t)elem_size(); }
     void write_pool(uint8_t* dst) const;  // device representation of the pool
     std::vector<SubStep> sub_steps;

@@ -82,7 +82,7 @@ def allreduce_max_vector(local_values: np.ndarray, mine: np.ndarray, n: int, dev
     return full.cpu().numpy()
 
 
-def distributed_costs(branches, cost_fn: Callable = branch_cost, device=None, group=None) -> np.ndarray:
+def distributed_costs(branches, cost_fn: Callable = branch_cost, device=None, group=None, threads: int = 0) -> np.ndarray:
     """cost of every branch, computed ONCE across the job: rank r estimates branches r, r + world, ... and one all-reduce
     (sum over a zero vector) gives every rank the whole vector -- so the sharding decision costs 1/world of a pass."""
     import torch
@@ -92,8 +92,12 @@ def distributed_costs(branches, cost_fn: Callable = branch_cost, device=None, gr
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     costs = np.zeros(n, dtype=np.float64)
-    for i in range(rank, n, world):
-        costs[i] = cost_fn(branches[i])
+    if cost_fn is branch_cost:  # one multi-threaded C call for this rank's share
+        from .contract import estimate_many
+        costs[rank::world] = estimate_many(branches[rank::world], threads)
+    else:
+        for i in range(rank, n, world):
+            costs[i] = cost_fn(branches[i])
     if world > 1:
         t = torch.as_tensor(costs, device=_default_device(device))
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)

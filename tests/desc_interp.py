@@ -14,6 +14,7 @@ LOC_ARENA, LOC_POOL, LOC_SMEM = 0, 1, 2
 KIND_GENERIC, KIND_GEMM = 1, 2
 NEG_I32 = -(1 << 30)
 NEG_I16 = -(1 << 14)
+NEG_CFG = -(1 << 62)
 
 SUBSTEP = np.dtype([("a_off", "<u2"), ("b_off", "<u2"), ("c_off", "<u2"), ("a_loc", "u1"), ("b_loc", "u1"),
                     ("c_loc", "u1"), ("rc", "u1"), ("nk", "u1"), ("nka", "u1"), ("nkb", "u1"), ("sa", "u1"),
@@ -74,10 +75,14 @@ def run_plan(plan):
     """plan: tbcuda.Plan.  Returns (root value as float, arena array, dict of stats)."""
     hdr = np.frombuffer(plan.raw(5), dtype="<i8")
     arena_elems, root_off, n_levels, vt = (int(x) for x in hdr)
-    dt = np.int64 if vt in (1, 3) else np.float32
-    neg = NEG_I32 if vt == 1 else NEG_I16 if vt == 3 else -np.inf
+    dt = np.int64 if vt in (1, 3, 5) else np.float64 if vt == 4 else np.float32
+    neg = NEG_I32 if vt == 1 else NEG_I16 if vt == 3 else NEG_CFG if vt == 5 else -np.inf
     if vt == 3:
         pool = np.frombuffer(plan.raw(0), dtype="<i2").astype(np.int64)
+    elif vt == 4:   # Tropical{Float64}
+        pool = np.frombuffer(plan.raw(0), dtype="<f8").copy()
+    elif vt == 5:   # size << 32 | vertex mask
+        pool = np.frombuffer(plan.raw(0), dtype="<i8").copy()
     else:
         praw = np.frombuffer(plan.raw(0), dtype="<u4")
         pool = praw.view("<i4").astype(np.int64) if vt == 1 else praw.view("<f4").copy()
@@ -86,11 +91,11 @@ def run_plan(plan):
     trees = np.frombuffer(plan.raw(2), dtype=SUBTREE)
     big = np.frombuffer(plan.raw(3), dtype=BIGSTEP)
     lvl = np.frombuffer(plan.raw(4), dtype="<i4")
-    arena = np.full(max(arena_elems, 1), 12345 if vt in (1, 3) else np.nan, dtype=dt)
+    arena = np.full(max(arena_elems, 1), 12345 if vt in (1, 3, 5) else np.nan, dtype=dt)
 
     with np.errstate(invalid="ignore"):
         for t in trees:
-            smem = np.full(max(int(t["smem_elems"]), 1), 777 if vt in (1, 3) else np.nan, dtype=dt)
+            smem = np.full(max(int(t["smem_elems"]), 1), 777 if vt in (1, 3, 5) else np.nan, dtype=dt)
             for s in sub[int(t["first_step"]): int(t["first_step"]) + int(t["n_steps"])]:
                 A = (smem if s["a_loc"] == LOC_SMEM else pool)[int(s["a_off"]):]
                 B = (smem if s["b_loc"] == LOC_SMEM else pool)[int(s["b_off"]):]
@@ -225,14 +230,28 @@ def run_plan(plan):
         rootf = -np.inf if root <= -(1 << 13) else float(root)
     elif vt == 1:
         rootf = -np.inf if root <= -(1 << 29) else float(root)
+    elif vt == 5:
+        rootf = -np.inf if (int(root) >> 32) <= -(1 << 29) else float(int(root) >> 32)
     else:
         rootf = float(root)
     return rootf, arena
 
 
 def to_float(arr, vt):
+    if vt == 5:  # the size half of size + configuration elements
+        size = arr >> 32
+        out = size.astype(np.float64)
+        out[size <= -(1 << 29)] = -np.inf
+        return out
     if vt in (1, 3):
         out = arr.astype(np.float64)
         out[arr <= (-(1 << 29) if vt == 1 else -(1 << 13))] = -np.inf
         return out
     return arr.astype(np.float64)
+
+
+def to_config(arr):
+    """the vertex mask half of size + configuration elements (0 where the element is tropical zero)"""
+    cfg = (arr & 0xFFFFFFFF).astype(np.uint32)
+    cfg[(arr >> 32) <= -(1 << 29)] = 0
+    return cfg

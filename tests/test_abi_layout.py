@@ -109,6 +109,8 @@ def test_c_client_builds_against_the_header(c_client):
 
 def _run_client(c_client, path, devices):
     out = subprocess.check_output([c_client, str(path), devices], text=True, timeout=600).strip().splitlines()
+    while out and not out[0].startswith("devices "):  # NCCL may print a version banner first
+        out.pop(0)
     head = out[0].split()
     vals = np.array([float(ln.split()[0]) for ln in out[1:]])
     stat = np.array([int(ln.split()[1]) for ln in out[1:]])

@@ -48,6 +48,7 @@ class _FakeEngine:
 
     def contract_plans(self, batch, r=None):
         vals = np.array([(self._value(p) if p is not None else 0.0) for p in batch.plans]) + (batch.r if batch.r is not None else 0.0)
+        vals = np.asarray(vals, dtype=np.float64).reshape(len(batch.plans))
         return vals, np.zeros(len(vals), dtype=np.int32), float(vals.max()) if len(vals) else -np.inf
 
     def contract_index_sliced(self, branch, labels, first=0, count=None, element_type=np.float32, flags=0):
