@@ -55,6 +55,12 @@ def _network_of(branch: SlicedBranch, element_type, flags=0, keep: Optional[list
     (built once by CompressedEinsum, the analogue of `compress`), so it is cached on the branch."""
     key = (np.dtype(element_type).name if element_type is not None else None, flags)
     cache = branch.__dict__.setdefault("_net_cache", {})
+    # the cached struct holds raw pointers into branch.code's arrays and the weight vector: replacing either on the branch
+    # must not reuse them
+    ident = (id(branch.code), id(branch.p.weights))
+    if cache.get("ident") != ident:
+        cache.clear()
+        cache["ident"] = ident
     hit = cache.get(key)
     if hit is not None:
         return hit
@@ -85,6 +91,8 @@ _EMPTY_NET_BYTES = bytes(C.sizeof(L.tb_network))
 def _network_bytes(branch: SlicedBranch, element_type, flags=0) -> bytes:
     key = ("bytes", np.dtype(element_type).name if element_type is not None else None, flags)
     cache = branch.__dict__.setdefault("_net_cache", {})
+    if cache.get("ident") != (id(branch.code), id(branch.p.weights)):
+        cache.clear()  # _network_of below re-keys the cache on the current code / weights objects
     hit = cache.get(key)
     if hit is None:
         net, _ = _network_of(branch, element_type, flags)
@@ -264,19 +272,23 @@ class Engine:
         # one tb_network record per branch; the records are cached as bytes on the branch objects, so a call only
         # joins them (the pointers inside stay valid as long as the branches are alive)
         key = ("bytes", np.dtype(element_type).name if element_type is not None else None, flags)
-        try:  # hot path: every branch already carries its record (one attribute + one dict lookup each)
-            parts = [br._net_cache[key] for br in branches]
-        except (AttributeError, KeyError):
-            parts = []
-            for br in branches:
-                try:
-                    parts.append(br._net_cache[key])
-                except (AttributeError, KeyError):
-                    if br.p.nv == 0 or br.code is None:
-                        br.__dict__.setdefault("_net_cache", {})[key] = _EMPTY_NET_BYTES
-                        parts.append(_EMPTY_NET_BYTES)
-                    else:
-                        parts.append(_network_bytes(br, element_type, flags))
+        parts = []
+        for br in branches:
+            c = br.__dict__.get("_net_cache")
+            ident = (id(br.code), id(br.p.weights))
+            if c is not None and c.get("ident") == ident:  # hot path: the branch already carries its record
+                hit = c.get(key)
+                if hit is not None:
+                    parts.append(hit)
+                    continue
+            if br.p.nv == 0 or br.code is None:
+                c = br.__dict__.setdefault("_net_cache", {})
+                c.clear()
+                c["ident"] = ident
+                c[key] = _EMPTY_NET_BYTES
+                parts.append(_EMPTY_NET_BYTES)
+            else:
+                parts.append(_network_bytes(br, element_type, flags))
         nets = (L.tb_network * max(n, 1)).from_buffer_copy(b"".join(parts) if n else _EMPTY_NET_BYTES)
         out = np.empty(n, dtype=np.float64)
         status = np.zeros(n, dtype=np.int32)

@@ -142,6 +142,51 @@ int set_err(tb_ctx* ctx, int code, const std::string& msg) {
 
 int sync_all_lanes(tb_ctx* ctx);
 
+// worker threads of one call: always joined, also when the launching thread unwinds (an exception then still reaches the
+// function-try-block of the ABI entry point instead of std::terminate on a joinable std::thread)
+struct ThreadGroup {
+    std::vector<std::thread> th;
+    template <class F> void spawn(F&& f) { th.emplace_back(std::forward<F>(f)); }
+    void join() {
+        for (auto& t : th)
+            if (t.joinable()) t.join();
+        th.clear();
+    }
+    ~ThreadGroup() { join(); }
+};
+
+// compile_plan for worker threads: never throws (an exception escaping a std::thread is std::terminate)
+int compile_guarded(const tb_network& net, uint32_t flags, Plan& P, std::string& err) noexcept {
+    try {
+        return compile_plan(net, flags, P, err);
+    } catch (const std::bad_alloc&) {
+        err = "host memory allocation failed";
+        return TB_ERR_OUT_OF_MEMORY;
+    } catch (const std::exception& e) {
+        err = std::string("C++ exception: ") + e.what();
+        return TB_ERR_INTERNAL;
+    } catch (...) {
+        err = "unknown C++ exception";
+        return TB_ERR_INTERNAL;
+    }
+}
+tb_plan* compile_new(const tb_network& net, uint32_t flags, int& code, std::string& err) noexcept {
+    tb_plan* p = nullptr;
+    try {
+        p = new tb_plan();
+    } catch (...) {
+        code = TB_ERR_OUT_OF_MEMORY;
+        err = "host memory allocation failed";
+        return nullptr;
+    }
+    code = compile_guarded(net, flags, p->p, err);
+    if (code) {
+        delete p;
+        return nullptr;
+    }
+    return p;
+}
+
 // NCCL, resolved with dlopen on first use (tb_init_multi): single-GPU users need no NCCL at all
 struct NcclApi {
     void* lib = nullptr;
@@ -1307,7 +1352,7 @@ int tb_estimate_many(const tb_network* nets, int64_t n, int32_t threads, double*
             if (nets[i].n_leaves != 0) {
                 Plan P;
                 std::string err;
-                const int rc = compile_plan(nets[i], TB_PLAN_ESTIMATE_ONLY, P, err);
+                const int rc = compile_guarded(nets[i], TB_PLAN_ESTIMATE_ONLY, P, err);
                 if (rc) {
                     std::lock_guard<std::mutex> g(mu);
                     if (bad.load() == TB_OK) {
@@ -1323,10 +1368,10 @@ int tb_estimate_many(const tb_network* nets, int64_t n, int32_t threads, double*
             if (out_sc) out_sc[i] = sc;
         }
     };
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt - 1; ++t) th.emplace_back(worker);
+    ThreadGroup th;
+    for (int t = 0; t < nt - 1; ++t) th.spawn(worker);
     worker();
-    for (auto& t : th) t.join();
+    th.join();
     if (bad.load() != TB_OK) return set_err(nullptr, bad.load(), first_err);
     return TB_OK;
 } TB_CATCH(nullptr)
@@ -1528,18 +1573,14 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
             int64_t i = next.fetch_add(1);
             if (i >= n) break;
             if (!abort.load(std::memory_order_relaxed) && nets[i].n_leaves != 0) {
-                tb_plan* p = new tb_plan();
-                codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
-                if (codes[i]) {
-                    delete p;
-                    abort.store(true);
-                } else plans[i] = p;
+                plans[i] = compile_new(nets[i], flags, codes[i], errs[i]);
+                if (codes[i]) abort.store(true);
             }
             done[i].store(1, std::memory_order_release);
         }
     };
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
+    ThreadGroup th;
+    for (int t = 0; t < nthreads - 1; ++t) th.spawn(worker);
     ctx->call_wave = wave_for_call(ctx, n, 0.0);  // refined from the first compiled batch below
     // TB_BATCH_MAX (experiments): upper bound of a pipeline batch; smaller batches keep the GPU closer behind the
     // compiler threads (shorter tail after the last plan is compiled) at the price of smaller waves
@@ -1562,12 +1603,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
             while (next.load() < hi && next.load() < n) {  // single-threaded: compile this batch inline
                 int64_t i = next.fetch_add(1);
                 if (i >= n) break;
-                if (nets[i].n_leaves != 0) {
-                    tb_plan* p = new tb_plan();
-                    codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
-                    if (codes[i]) delete p;
-                    else plans[i] = p;
-                }
+                if (nets[i].n_leaves != 0) plans[i] = compile_new(nets[i], flags, codes[i], errs[i]);
                 done[i].store(1, std::memory_order_release);
             }
         }
@@ -1577,12 +1613,8 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
                 int64_t j = next.fetch_add(1);
                 if (j < n) {
                     if (!abort.load(std::memory_order_relaxed) && nets[j].n_leaves != 0) {
-                        tb_plan* p = new tb_plan();
-                        codes[j] = compile_plan(nets[j], flags, p->p, errs[j]);
-                        if (codes[j]) {
-                            delete p;
-                            abort.store(true);
-                        } else plans[j] = p;
+                        plans[j] = compile_new(nets[j], flags, codes[j], errs[j]);
+                        if (codes[j]) abort.store(true);
                     }
                     done[j].store(1, std::memory_order_release);
                 } else {
@@ -1604,7 +1636,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
         if (rc == TB_OK) rc = enqueue_batch(ctx, plans.data(), lo, hi, status, false);
     }
     abort.store(rc != TB_OK);
-    for (auto& t : th) t.join();
+    th.join();
     ctx->host_ms[0] = t_wait;  // time the launching thread spent waiting for the compiler threads
     return rc;
 }
@@ -1709,12 +1741,12 @@ int multi_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sli
     std::vector<int32_t> stat((size_t)std::max<int64_t>(count, 1), TB_OK);
     std::vector<int> rcs((size_t)D, TB_OK);
     std::vector<double> mxs((size_t)D, -std::numeric_limits<double>::infinity());
-    std::vector<std::thread> th;
+    ThreadGroup th;
     const int64_t base = count / D, extra = count % D;
     for (int d = 0; d < D; ++d) {
         const int64_t off = d * base + std::min<int64_t>(d, extra), cnt = base + (d < extra ? 1 : 0);
         if (cnt == 0) continue;
-        th.emplace_back([&, d, off, cnt] {
+        th.spawn([&, d, off, cnt] {
             tb_ctx* sub = ctx->subs[(size_t)d];
             try {
                 cudaSetDevice(sub->device);
@@ -1725,7 +1757,7 @@ int multi_contract_sliced(tb_ctx* ctx, const tb_network* net, const int32_t* sli
             }
         });
     }
-    for (auto& t : th) t.join();
+    th.join();
     int rc = TB_OK;
     for (int d = 0; d < D; ++d)
         if (rcs[(size_t)d] && !rc) rc = set_err(ctx, rcs[(size_t)d], "device " + std::to_string(ctx->subs[(size_t)d]->device) + ": " + ctx->subs[(size_t)d]->last_error);
@@ -1783,7 +1815,7 @@ int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r
                 if (nets[i].n_leaves == 0) continue;
                 Plan P;
                 std::string err;
-                const int rc = compile_plan(nets[i], ctx->opts.plan_flags | TB_PLAN_ESTIMATE_ONLY, P, err);
+                const int rc = compile_guarded(nets[i], ctx->opts.plan_flags | TB_PLAN_ESTIMATE_ONLY, P, err);
                 if (rc) {
                     std::lock_guard<std::mutex> g(mu);
                     if (bad.load() == TB_OK) {
@@ -1794,10 +1826,10 @@ int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r
             }
         };
         const int nt = std::max(1, std::min<int>(host_threads_of(ctx), (int)std::max<int64_t>(1, n / 16)));
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt - 1; ++t) th.emplace_back(worker);
+        ThreadGroup th;
+        for (int t = 0; t < nt - 1; ++t) th.spawn(worker);
         worker();
-        for (auto& t : th) t.join();
+        th.join();
         if (bad.load() != TB_OK) return set_err(ctx, bad.load(), errs.empty() ? "plan estimation failed" : errs[0]);
     }
     // ---- 2. longest-first assignment
@@ -1823,9 +1855,9 @@ int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r
             dev[(size_t)owner[(size_t)i]].nets.push_back(nets[i]);
         }
     {
-        std::vector<std::thread> th;
+        ThreadGroup th;
         for (int d = 0; d < D; ++d)
-            th.emplace_back([&, d] {
+            th.spawn([&, d] {
                 tb_ctx* sub = ctx->subs[(size_t)d];
                 Dev& dv = dev[(size_t)d];
                 try {
@@ -1839,7 +1871,7 @@ int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r
                 sub->index_map = nullptr;
                 sub->prefill_results = false;
             });
-        for (auto& t : th) t.join();
+        th.join();
     }
     int rc = TB_OK;
     for (int d = 0; d < D; ++d)
@@ -1915,9 +1947,9 @@ int multi_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, in
             dev[(size_t)owner[(size_t)i]].plans.push_back(plans[i]);
         }
     {
-        std::vector<std::thread> th;
+        ThreadGroup th;
         for (int d = 0; d < D; ++d)
-            th.emplace_back([&, d] {
+            th.spawn([&, d] {
                 tb_ctx* sub = ctx->subs[(size_t)d];
                 Dev& dv = dev[(size_t)d];
                 try {
@@ -1931,7 +1963,7 @@ int multi_contract_batch(tb_ctx* ctx, tb_plan* const* plans, const double* r, in
                 sub->index_map = nullptr;
                 sub->prefill_results = false;
             });
-        for (auto& t : th) t.join();
+        th.join();
     }
     int rc = TB_OK;
     for (int d = 0; d < D; ++d)
@@ -2027,18 +2059,15 @@ int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_
             const int64_t i = next.fetch_add(1);
             if (i >= n) break;
             if (nets[i].n_leaves == 0) continue;
-            tb_plan* p = new tb_plan();
-            codes[i] = compile_plan(nets[i], flags, p->p, errs[i]);
-            if (codes[i]) delete p;
-            else s->plans[(size_t)(lo + i)] = p;
+            s->plans[(size_t)(lo + i)] = compile_new(nets[i], flags, codes[i], errs[i]);
         }
     };
     int nthreads = ctx->opts.host_threads > 0 ? ctx->opts.host_threads : (int)std::thread::hardware_concurrency();
     nthreads = std::max(1, std::min<int>(nthreads, (int)std::max<int64_t>(1, n / 8)));
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads - 1; ++t) th.emplace_back(worker);
+    ThreadGroup th;
+    for (int t = 0; t < nthreads - 1; ++t) th.spawn(worker);
     worker();
-    for (auto& t : th) t.join();
+    th.join();
     ctx->host_ms[0] += now_ms() - t_c0;
     int rc = TB_OK;
     for (int64_t i = 0; i < n && rc == TB_OK; ++i)

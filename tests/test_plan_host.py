@@ -229,3 +229,20 @@ def test_estimate_equals_plan_ops():
     assert tbcuda.estimate(to_sliced([b for b in brs if b.nv == 0][0] if any(b.nv == 0 for b in brs) else brs[0]))[0] >= 0
     from tbcuda.multi_gpu import branch_cost
     assert branch_cost(to_sliced(regular_root(60, 5))) == tbcuda.Plan(to_sliced(regular_root(60, 5))).info().ops
+
+
+def test_network_cache_follows_code_and_weights_objects():
+    """the cached tb_network holds raw pointers into branch.code / weights; replacing either must rebuild it"""
+    import numpy as np
+    import tbcuda
+    from tbcuda import contract as Cn
+    from helpers import regular_root, to_sliced
+    a, b = to_sliced(regular_root(30, 3)), to_sliced(regular_root(40, 4))
+    n1 = Cn._network_bytes(a, np.float32)
+    assert Cn._network_bytes(a, np.float32) is n1  # cached
+    a.code = b.code  # the host swaps the tree of a branch
+    a.p = b.p
+    n2 = Cn._network_bytes(a, np.float32)
+    assert n2 != n1 and n2 == Cn._network_bytes(b, np.float32)
+    p = tbcuda.Plan(a)
+    assert p.info().ops == tbcuda.Plan(b).info().ops
