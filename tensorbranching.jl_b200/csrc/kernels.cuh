@@ -375,6 +375,7 @@ __device__ __forceinline__ void generic_tile(const BigStep& sd, const void* pool
         if (active) C[c] = acc;
     } else {
         // tree reduction over the k-parts (uniform trip count: ks is per-CTA)
+        if (PERSIST) generic_sync<true>();  // s_red is epilogue staging memory: the previous GEMM tile's readers must be done
         s_red[tid] = acc;
         generic_sync<PERSIST>();
         for (int s = ks - 1; s >= 0; --s) {
@@ -1517,11 +1518,14 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     }
                 }
             }
+            // The four quarters of the tile (top m bit x top n bit) have a staging buffer each (4 x 8 KB = the whole 128 x 128
+            // int16 tile), so ONE barrier separates all shared-memory writes from all reads; the barrier in front only
+            // orders this tile's writes behind the previous tile's reads (every warp passed those a main loop ago).
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int ih = r & 1, jh = r >> 1;
-                const uint32_t boff = (uint32_t)(r & 1) * (uint32_t)(G2H_STG_ELEMS * 2);  // bytes
-                T* buf = stg_mem + (r & 1) * G2H_STG_ELEMS;
+                const uint32_t boff = (uint32_t)r * (uint32_t)(G2H_STG_ELEMS * 2);  // bytes
                 uint32_t W[2][4];  // W[second local m bit][n0 + 2 n1] = outputs (first local m bit = 0, 1) as one packed word
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -1552,7 +1556,13 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_addr[0] + boff), "r"(v0.x), "r"(v0.y), "r"(v0.z), "r"(v0.w) : "memory");
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(w_addr[1] + boff), "r"(v1.x), "r"(v1.y), "r"(v1.z), "r"(v1.w) : "memory");
                 }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+            }
+            asm volatile("bar.sync 1, 256;\n" ::: "memory");
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int ih = r & 1, jh = r >> 1;
+                const uint32_t boff = (uint32_t)r * (uint32_t)(G2H_STG_ELEMS * 2);  // bytes
+                T* buf = stg_mem + r * G2H_STG_ELEMS;
                 const uint32_t roff = ((uint32_t)ih << ti.e_cs_mtop) | ((uint32_t)jh << ti.e_cs_ntop);
                 if (evec && ecase != 0) {
 #pragma unroll
