@@ -476,10 +476,13 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
         if min_timed_s > 0:
             # short workloads (a step of a millisecond): keep warming up until the clocks have ramped, and time enough
             # steps that the timed region lasts min_timed_s (the step count is reported)
-            est = max((time.perf_counter() - t_w) / max(1, n_warm), 1e-5)
-            while time.perf_counter() - t_w < 0.4 * min_timed_s:
+            t_w = time.perf_counter()
+            n_w = 0
+            while n_w < 2 or time.perf_counter() - t_w < 0.4 * min_timed_s:
                 out = fn()
+                n_w += 1
             torch.cuda.synchronize()
+            est = max((time.perf_counter() - t_w) / n_w, 1e-5)
             n_steps = max(n_steps, int(np.ceil(min_timed_s / est)))
         timed.steps = n_steps
         if world > 1:
