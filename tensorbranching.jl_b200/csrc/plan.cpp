@@ -114,133 +114,55 @@ inline void sort_by_key(int32_t* v, const int32_t* key, int n) {
 
 }  // namespace
 
-int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::string& err) {
-    auto fail = [&](int code, const std::string& m) {
+namespace {
+
+// One compilation: the passes below run in order and share the flat arrays declared first.
+struct PlanCompiler {
+    const tb_network& net;
+    uint32_t extra_flags;
+    Plan& P;
+    std::string& err;
+    PlanCompiler(const tb_network& n, uint32_t f, Plan& p, std::string& e) : net(n), extra_flags(f), P(p), err(e) {}
+
+    // ---- state shared by the passes
+    bool temporary = false, estimate_only = false, synth = false, finished = false;
+    int nL = 0, nN = 0, nT0 = 0, nTmax = 0, nT = 0, NLAB = 1, root = 0;
+    int vt = 0, wd = 0;
+    bool wide = false, half = false;
+    static constexpr int TILE_M_MAX = GEMM_TILE_MAX;  // tile bits of the M side
+    static constexpr int MT_LOG = 3;                  // log2 of a thread's microtile extent (8 x 8 outputs, both value widths)
+    int STAGE_ELEMS = 0;
+    // flat per-tensor storage: tree, sorted label sets
+    std::vector<int32_t> lch, rch, parent, lab_off, lab_data;
+    std::vector<uint8_t> leaf, unary, lab_n;
+    std::vector<int8_t> fixed;        // index slicing: -1 (free) or the value the label is fixed to
+    std::vector<int32_t> fixed_idx;   // label -> its position in net.fixed_labels
+    std::vector<int32_t> leaf_vertex, leaf_fa, leaf_fb;
+    std::vector<int32_t> lo, hi, minpos, maxpos;  // leaf positions (depth-first) covered by a subtree / holding a label
+    std::vector<uint8_t> is_open;
+    double est_ops = 0, est_all = 0, est_peak = 0;
+    int est_sc = 0;
+    std::vector<int32_t> stA, stB, stC;  // stamp arrays for O(1) membership
+    int stamp = 0;
+    std::vector<uint8_t> folded, kept;
+    std::vector<int32_t> topo;
+    size_t lab_total = 0, lay_top = 0, cls_top = 0;
+    std::vector<NodeCls> cls;
+    std::vector<int32_t> cls_data;
+    std::vector<int32_t> leaf_pool_off;
+    std::vector<uint8_t> fus;
+    std::vector<int64_t> peak;
+    std::vector<int8_t> kind;
+    int n_fused_roots = 0, n_big = 0;
+    std::vector<uint8_t> posA, posB, posCc;
+    double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, bytes_m = 0, sc = 0;
+
+    int fail(int code, const std::string& m) {
         err = m;
         return code;
-    };
-    if (net.n_leaves < 1) return fail(TB_ERR_BAD_ARGUMENT, "network has no leaves (pass a NULL plan for an empty graph)");
-    if (net.n_labels < 0) return fail(TB_ERR_BAD_ARGUMENT, "negative n_labels");
-    if (!net.leaf_off || (net.leaf_off[net.n_leaves] > 0 && !net.leaf_labels))
-        return fail(TB_ERR_BAD_ARGUMENT, "leaf_off / leaf_labels is NULL");
-    if (net.n_leaves > 1 && (!net.node_left || !net.node_right))
-        return fail(TB_ERR_BAD_ARGUMENT, "node_left / node_right is NULL");
-    if (net.n_open < 0 || (net.n_open > 0 && !net.open_labels)) return fail(TB_ERR_BAD_ARGUMENT, "bad open labels");
-
-#ifdef TB_PLAN_PROFILE
-    auto last_ = std::chrono::steady_clock::now();
-#endif
-    const bool temporary = (extra_flags & TB_PLAN_TEMPORARY) != 0;
-    const bool estimate_only = (extra_flags & TB_PLAN_ESTIMATE_ONLY) != 0;
-    extra_flags &= ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY);
-    P.flags = (net.flags & ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY)) | extra_flags;
-    if (P.flags & TB_PLAN_KEEP_INTERMEDIATES) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;
-    P.n_labels = net.n_labels;
-    const bool synth = (net.n_leaves == 1);
-    const int nL = net.n_leaves + (synth ? 1 : 0);
-    const int nN = nL - 1;
-    const int nT0 = nL + nN;      // tensors of the given tree
-    const int nTmax = nT0 + 2 * nN;  // + (partial node, unit leaf) per split
-    P.n_leaves = nL;
-    P.n_nodes = nN;
-    const int NLAB = std::max(net.n_labels, 1);
-
-    // ---- flat per-tensor storage
-    std::vector<int32_t> lch(nTmax, -1), rch(nTmax, -1), parent(nTmax, -1);
-    std::vector<uint8_t> leaf(nTmax, 0), unary(nTmax, 0);
-    std::vector<int32_t> lab_off(nTmax, 0);
-    std::vector<uint8_t> lab_n(nTmax, 0);
-    std::vector<int32_t> lab_data;
-    lab_data.reserve((size_t)nT0 * 8);
-    auto labp = [&](int t) { return lab_data.data() + lab_off[t]; };
-
-    // ---- index slicing: fixed[l] = -1 (free) or the value label l is fixed to
-    std::vector<int8_t> fixed;
-    std::vector<int32_t> fixed_idx;  // label -> its position in net.fixed_labels
-    if (net.n_fixed < 0 || (net.n_fixed > 0 && (!net.fixed_labels || !net.fixed_values)))
-        return fail(TB_ERR_BAD_ARGUMENT, "bad fixed labels");
-    if (net.n_fixed > 0) {
-        fixed.assign(NLAB, -1);
-        fixed_idx.assign(NLAB, -1);
-        for (int i = 0; i < net.n_fixed; ++i) {
-            int32_t l = net.fixed_labels[i];
-            if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "fixed label out of range");
-            if (fixed[l] >= 0) return fail(TB_ERR_BAD_ARGUMENT, "fixed label repeated");
-            if (net.fixed_values[i] > 1) return fail(TB_ERR_BAD_ARGUMENT, "fixed value must be 0 or 1");
-            fixed[l] = (int8_t)net.fixed_values[i];
-            fixed_idx[l] = i;
-        }
-        for (int i = 0; i < net.n_open; ++i)
-            if (net.open_labels[i] >= 0 && net.open_labels[i] < net.n_labels && fixed[net.open_labels[i]] >= 0)
-                return fail(TB_ERR_BAD_ARGUMENT, "a label cannot be both open and fixed");
     }
-
-    // ---- leaves.  leaf_vertex[i] = vertex of a vertex leaf (-1: edge / unit leaf).  A leaf that lost labels to
-    //      index slicing reads a slice of its tensor from a pool slot of its own, filled by Plan::assign from the
-    //      values of its fixed labels (leaf_fa / leaf_fb = their positions in net.fixed_labels): all 2^k assignments
-    //      of the same labels share every descriptor of the plan and differ only in these pool words.
-    std::vector<int32_t> leaf_vertex(nL, -1), leaf_fa(nL, -1), leaf_fb(nL, -1);
-    for (int i = 0; i < nL; ++i) leaf[i] = 1;
-    for (int i = 0; i < net.n_leaves; ++i) {
-        int b = net.leaf_off[i], e = net.leaf_off[i + 1];
-        if (e < b) return fail(TB_ERR_BAD_ARGUMENT, "leaf_off not monotone");
-        int r = e - b;
-        if (r < 1 || r > 2)
-            return fail(TB_ERR_UNSUPPORTED, "leaf " + std::to_string(i) + " has " + std::to_string(r) +
-                                                " labels; IndependentSet leaves have 1 (vertex) or 2 (edge)");
-        lab_off[i] = (int32_t)lab_data.size();
-        int nfix = 0;  // fixed labels of this leaf
-        for (int q = b; q < e; ++q) {
-            int32_t l = net.leaf_labels[q];
-            if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "leaf label out of range");
-            if (!fixed.empty() && fixed[l] >= 0) {
-                (nfix++ ? leaf_fb[i] : leaf_fa[i]) = fixed_idx[l];
-            } else {
-                lab_data.push_back(l);
-            }
-        }
-        if (r == 2 && net.leaf_labels[b] == net.leaf_labels[b + 1])
-            return fail(TB_ERR_UNSUPPORTED, "edge tensor with a repeated label (self loop)");
-        if (r == 1) leaf_vertex[i] = net.leaf_labels[b];
-        lab_n[i] = (uint8_t)(r - nfix);
-        if (lab_n[i] == 2) {
-            int32_t* v = lab_data.data() + lab_off[i];
-            if (v[0] > v[1]) std::swap(v[0], v[1]);
-        }
-    }
-    if (synth) lab_off[1] = (int32_t)lab_data.size();
-
-    // ---- tree
-    if (synth) {
-        lch[nL] = 0;
-        rch[nL] = 1;
-    } else {
-        for (int j = 0; j < nN; ++j) {
-            lch[nL + j] = net.node_left[j];
-            rch[nL + j] = net.node_right[j];
-        }
-    }
-    for (int j = 0; j < nN; ++j) {
-        int id = nL + j;
-        for (int c : {lch[id], rch[id]}) {
-            if (c < 0 || c >= id) return fail(TB_ERR_NOT_BINARY_TREE, "node " + std::to_string(j) + ": child id must be in [0, own id)");
-            if (parent[c] != -1) return fail(TB_ERR_NOT_BINARY_TREE, "tensor " + std::to_string(c) + " is used twice");
-            parent[c] = id;
-        }
-        if (lch[id] == rch[id]) return fail(TB_ERR_NOT_BINARY_TREE, "node contracts a tensor with itself");
-    }
-    for (int t = 0; t < nT0 - 1; ++t)
-        if (parent[t] == -1) return fail(TB_ERR_NOT_BINARY_TREE, "tensor " + std::to_string(t) + " is never contracted (forest, not a tree)");
-    const int root = nT0 - 1;
-    P.root_id = root;
-
-    PT(0, "validate")
-    // ---- weights / value type
-    int vt = net.value_type;
-    const int wd = net.weight_dtype;
-    if (wd < TB_WEIGHT_UNIT || wd > TB_WEIGHT_F64) return fail(TB_ERR_BAD_ARGUMENT, "unknown weight_dtype");
-    if (wd != TB_WEIGHT_UNIT && !net.weights) return fail(TB_ERR_BAD_ARGUMENT, "weights is NULL but weight_dtype is not UNIT");
-    auto weight_of = [&](int v) -> double {
+    int32_t* labp(int t) { return lab_data.data() + lab_off[t]; }
+    double weight_of(int v) const {
         switch (wd) {
             case TB_WEIGHT_UNIT: return 1.0;
             case TB_WEIGHT_I32: return (double)((const int32_t*)net.weights)[v];
@@ -248,694 +170,15 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
             case TB_WEIGHT_F32: return (double)((const float*)net.weights)[v];
             default: return ((const double*)net.weights)[v];
         }
-    };
-    const bool int_weights = !(wd == TB_WEIGHT_F32 || wd == TB_WEIGHT_F64);
-    bool auto_i16 = false;
-    if (vt == TB_VALUE_AUTO) {
-        vt = int_weights ? TB_VALUE_I32 : TB_VALUE_F32;
-        auto_i16 = int_weights && !(P.flags & TB_PLAN_NO_I16);  // falls back to int32 below if the weights do not fit
     }
-    if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32 && vt != TB_VALUE_I16X2 && vt != TB_VALUE_F64 && vt != TB_VALUE_SIZE_CONFIG)
-        return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
-    const bool wide = (vt == TB_VALUE_F64 || vt == TB_VALUE_SIZE_CONFIG);  // 8-byte values: generic + fused kernels only
-    if (wide) P.flags |= TB_PLAN_NO_GEMM;
-    if (vt == TB_VALUE_SIZE_CONFIG && net.n_labels > 32)
-        return fail(TB_ERR_UNSUPPORTED, "value type size+configuration keeps the chosen vertices in a 32-bit mask: at most 32 labels "
-                                        "(regions of the branching tables have <= n_max = 20 vertices, src/types.jl:10)");
-    if (vt == TB_VALUE_I16X2 || auto_i16) {
-        // packed int16 needs every partial sum < 2^13: check sum |w| over the vertex leaves
-        double sum_abs = 0;
-        bool integral = true;
-        for (int i = 0; i < net.n_leaves; ++i)
-            if (leaf_vertex[i] >= 0) {
-                double w = weight_of(leaf_vertex[i]);
-                integral = integral && (w == std::floor(w));
-                sum_abs += std::fabs(w);
-            }
-        const bool fits = integral && sum_abs < 8192.0;
-        if (vt == TB_VALUE_I16X2 && !fits) return fail(TB_ERR_UNSUPPORTED, "value type i16x2 needs integer weights with sum |w| < 8192");
-        if (auto_i16 && fits) vt = TB_VALUE_I16X2;
-    }
-    P.value_type = vt;
-    const bool half = (vt == TB_VALUE_I16X2);
-    const int TILE_M_MAX = GEMM_TILE_MAX;  // tile bits of the M side
-    const int MT_LOG = 3;                  // log2 of a thread's microtile extent (8 x 8 outputs, both value widths)
-    const int STAGE_ELEMS = GEMM_STAGE_ELEMS * (half ? 2 : 1);
-
-    // ---- leaf positions (DFS order) and subtree ranges
-    std::vector<int32_t> lo(nT0, 0), hi(nT0, 0);
-    {
-        std::vector<int32_t> stack;
-        stack.reserve(64);
-        stack.push_back(root);
-        int pos = 0;
-        while (!stack.empty()) {
-            int t = stack.back();
-            stack.pop_back();
-            if (leaf[t]) {
-                lo[t] = hi[t] = pos++;
-            } else {
-                stack.push_back(rch[t]);
-                stack.push_back(lch[t]);
-            }
-        }
-        for (int t = nL; t < nT0; ++t) {
-            lo[t] = std::min(lo[lch[t]], lo[rch[t]]);
-            hi[t] = std::max(hi[lch[t]], hi[rch[t]]);
-        }
-    }
-    std::vector<int32_t> minpos(NLAB, std::numeric_limits<int32_t>::max()), maxpos(NLAB, -1);
-    std::vector<uint8_t> is_open(NLAB, 0);
-    for (int i = 0; i < nL; ++i)
-        for (int q = 0; q < lab_n[i]; ++q) {
-            int32_t l = labp(i)[q];
-            minpos[l] = std::min(minpos[l], lo[i]);
-            maxpos[l] = std::max(maxpos[l], lo[i]);
-        }
-    for (int i = 0; i < net.n_open; ++i) {
-        int32_t l = net.open_labels[i];
-        if (l < 0 || l >= net.n_labels || maxpos[l] < 0) return fail(TB_ERR_BAD_ARGUMENT, "open label does not occur in any leaf");
-        if (is_open[l]) return fail(TB_ERR_BAD_ARGUMENT, "open label repeated");
-        is_open[l] = 1;
-    }
-
-    PT(1, "positions")
-    // ---- label sets bottom-up (ids of the given tree are already topological); sets are sorted
-    double est_ops = 0;  // sum over nodes of 2^(labels involved): the reference's 2^tc (src/types.jl:120)
-    int est_sc = 0;
-    for (int i = 0; i < nL; ++i) est_sc = std::max(est_sc, (int)lab_n[i]);
-    for (int t = nL; t < nT0; ++t) {
-        const int A = lch[t], B = rch[t];
-        const int na = lab_n[A], nb = lab_n[B];
-        int32_t u[80];
-        int nu = 0;
-        {
-            const int32_t *a = labp(A), *b = labp(B);
-            int i = 0, j = 0;
-            while (i < na || j < nb) {
-                if (j >= nb || (i < na && a[i] < b[j])) u[nu++] = a[i++];
-                else if (i >= na || b[j] < a[i]) u[nu++] = b[j++];
-                else {
-                    u[nu++] = a[i];
-                    ++i;
-                    ++j;
-                }
-            }
-        }
-        if (nu > 62) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 62 labels");
-        lab_off[t] = (int32_t)lab_data.size();
-        int no = 0;
-        for (int q = 0; q < nu; ++q) {
-            int32_t l = u[q];
-            bool closed = !is_open[l] && minpos[l] >= lo[t] && maxpos[l] <= hi[t];
-            if (!closed) {
-                lab_data.push_back(l);
-                ++no;
-            }
-        }
-        if (no > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(no) + " > 31");
-        if (nu - no > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
-        lab_n[t] = (uint8_t)no;
-        est_ops += std::ldexp(1.0, nu);
-        est_sc = std::max(est_sc, no);
-    }
-    if (estimate_only) {
-        P.stats = tb_plan_stats{};
-        P.stats.ops = est_ops;
-        P.stats.tc = est_ops > 0 ? std::log2(est_ops) : 0;
-        P.stats.sc = est_sc;
-        P.stats.n_nodes = nN;
-        P.stats.value_type = vt;
-        return TB_OK;
-    }
-
-    // ---- the reference's memory estimators on the GIVEN tree (before any rewrite), in elements, all label sizes 2:
-    //      contraction_all_memory = log2(sum of the sizes of all intermediates)          (src/utils.jl:222-229)
-    //      contraction_peak_memory = log2(max of the running total)                       (src/utils.jl:197-219):
-    //      the walk is depth-first, left operand first; a node adds its result and releases the operands of its
-    //      CHILD nodes (its own operands are released one step later, by its parent) -- restated as the reference has it
-    double est_all = 0, est_peak = 0;
-    PT(2, "labelsets")
-    if (!temporary) {
-        // the depth-first order (left operand first) is the order in which the leaf positions lo[] were numbered above:
-        // a node is finished when its last leaf has been seen, so sorting is not needed -- walk the nodes by the stack
-        double p2[33];
-        for (int i = 0; i <= 32; ++i) p2[i] = (double)(1ull << i);
-        double cur = 0;
-        for (int i = 0; i < net.n_leaves; ++i) cur += p2[lab_n[i]];
-        est_peak = cur;
-        std::vector<double> freed_later(nT0, 0.0);  // sum of a node's operand sizes
-        std::vector<int32_t> stack;
-        stack.reserve(128);
-        stack.push_back(root);
-        while (!stack.empty()) {
-            const int t = stack.back();
-            if (t < 0) {  // second visit of node ~t: both operands are done
-                stack.pop_back();
-                const int x = ~t, A = lch[x], B = rch[x];
-                const double alloc = p2[lab_n[x]];
-                cur += alloc - (freed_later[A] + freed_later[B]);
-                freed_later[x] = p2[lab_n[A]] + p2[lab_n[B]];
-                if (cur > est_peak) est_peak = cur;
-                est_all += alloc;
-                continue;
-            }
-            stack.pop_back();
-            if (leaf[t]) continue;
-            stack.push_back(~t);
-            stack.push_back(rch[t]);
-            stack.push_back(lch[t]);
-        }
-    }
-
-    PT(11, "estimators")
-    // stamp arrays for O(1) membership
-    std::vector<int32_t> stA(NLAB, -1), stB(NLAB, -1), stC(NLAB, -1);
-    int stamp = 0;
-
-    // ---- split-K rewrite: node t = contract(A, B) with a long reduction becomes
-    //      u = contract(A, B) keeping `sk` of the shared reduced labels, t = max over those labels of u
-    //      (t = contract(u, unit scalar)).  Balances CTA run times inside a level launch.
-    int nT = nT0;
-    std::vector<uint8_t> folded(nTmax, 0);  // split labels a node reduces on behalf of its children (not algorithmic work)
-    std::vector<uint8_t> kept(nTmax, 0);    // split labels a node keeps as extra output labels for its consumer
-    if (!(P.flags & TB_PLAN_NO_SPLIT_K)) {
-        for (int t = nL; t < nT0; ++t) {
-            const int A = lch[t], B = rch[t];
-            if ((int)lab_n[A] + (int)lab_n[B] < 16) continue;  // cannot have a long reduction
-            ++stamp;
-            for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = stamp;
-            for (int q = 0; q < lab_n[t]; ++q) stC[labp(t)[q]] = stamp;
-            int nm = 0, nn = 0, nk = 0, nka = 0, nkb = 0;
-            int32_t Ksh[40];
-            for (int q = 0; q < lab_n[A]; ++q) {
-                int32_t l = labp(A)[q];
-                stA[l] = stamp;
-                bool inB = stB[l] == stamp, inC = stC[l] == stamp;
-                if (inB && !inC) Ksh[nk++] = l;
-                else if (!inB && inC) ++nm;
-                else if (!inB && !inC) ++nka;
-            }
-            for (int q = 0; q < lab_n[B]; ++q) {
-                int32_t l = labp(B)[q];
-                if (stA[l] != stamp) (stC[l] == stamp ? nn : nkb)++;
-            }
-            const int rc = lab_n[t];
-            const int gm = nm, gn = nn;
-            const bool gemm_like = !(P.flags & TB_PLAN_NO_GEMM) && gm >= MT_LOG && gn >= 3 &&
-                                   std::min(gm, TILE_M_MAX) + std::min(gn, GEMM_TILE_MAX) >= MT_LOG + 6 && nk >= 1 && nka == 0 &&
-                                   nkb == 0 && !leaf[A] && !leaf[B];
-            int serial_log, limit;
-            if (gemm_like) {
-                serial_log = nk;
-                limit = 8;
-            } else {
-                int ks, po;
-                generic_split(rc, nk + nka + nkb, ks, po);
-                serial_log = nk + nka + nkb - ks;
-                limit = 7;
-            }
-            int sk = (serial_log > limit && nk > 0) ? std::min(serial_log - limit, gemm_like ? nk - 1 : nk) : 0;
-            if (gemm_like) {
-                // parallelism: a node with few output tiles and a long reduction would occupy only a few CTAs of its
-                // level launch for a long time; split k until it has ~32 tiles (keeping >= 32 k-steps per tile).  Its
-                // output is small by construction, so the extra unary max pass is cheap.
-                const int tile_log = 14;
-                const int t_log = std::max(0, rc - tile_log);
-                static const int target_log = [] {
-                    const char* e = getenv("TB_SPLIT_TARGET");  // log2 of the tiles a node should have; 0 disables
-                    return e ? atoi(e) : 0;  // measured on cfg2 (profiles/s02_split_target_sweep.jsonl): with 4 lanes in flight extra levels cost more than idle CTA slots
-                }();
-                const int sk_par = std::min(std::max(0, target_log - t_log), std::max(0, nk - 5));
-                sk = std::max(sk, sk_par);
-            }
-            sk = std::min(sk, MAX_RANK - rc);
-            if (sk <= 0) continue;
-            // If the consumer of t is itself a reduction over (almost) all of t, it can reduce the split labels too:
-            // t keeps them as output labels and they become labels private to one operand of the consumer.  The
-            // consumer then reads the partial results once - exactly what the separate max pass would have read.
-            static const bool no_fold = getenv("TB_NO_FOLD") != nullptr;  // diagnostics: keep the separate max pass
-            if (const int pr = parent[t]; pr >= 0 && !no_fold) {
-                const int sib = lch[pr] == t ? rch[pr] : lch[pr];
-                ++stamp;
-                for (int q = 0; q < rc; ++q) stA[labp(t)[q]] = stamp;
-                for (int q = 0; q < lab_n[pr]; ++q) stC[labp(pr)[q]] = stamp;
-                int n_sib_out = 0;  // output labels of the consumer that only the sibling carries
-                for (int q = 0; q < lab_n[sib]; ++q) {
-                    const int32_t l = labp(sib)[q];
-                    if (stA[l] != stamp && stC[l] == stamp) ++n_sib_out;
-                }
-                if (n_sib_out <= 1 && (int)folded[pr] + sk <= 8) {
-                    int32_t tmp[48];
-                    int n = 0;
-                    for (int q = 0; q < rc; ++q) tmp[n++] = labp(t)[q];
-                    for (int q = nk - sk; q < nk; ++q) tmp[n++] = Ksh[q];
-                    std::sort(tmp, tmp + n);
-                    lab_off[t] = (int32_t)lab_data.size();
-                    lab_n[t] = (uint8_t)n;
-                    lab_data.insert(lab_data.end(), tmp, tmp + n);
-                    folded[pr] = (uint8_t)(folded[pr] + sk);
-                    kept[t] = (uint8_t)sk;
-                    continue;
-                }
-            }
-            const int u = nT++, ul = nT++;
-            lch[u] = A;
-            rch[u] = B;
-            parent[u] = t;
-            folded[u] = folded[t];
-            folded[t] = 0;
-            // lab[u] = lab[t] + the last sk shared reduced labels, sorted
-            {
-                int32_t tmp[48];
-                int n = 0;
-                for (int q = 0; q < rc; ++q) tmp[n++] = labp(t)[q];
-                for (int q = nk - sk; q < nk; ++q) tmp[n++] = Ksh[q];
-                std::sort(tmp, tmp + n);
-                lab_off[u] = (int32_t)lab_data.size();
-                lab_n[u] = (uint8_t)n;
-                lab_data.insert(lab_data.end(), tmp, tmp + n);
-            }
-            leaf[ul] = 1;
-            parent[ul] = t;
-            lab_off[ul] = (int32_t)lab_data.size();
-            lab_n[ul] = 0;
-            parent[A] = parent[B] = u;
-            lch[t] = u;
-            rch[t] = ul;
-            unary[t] = 1;
-        }
-    }
-    P.n_tensors = nT;
-
-    PT(3, "splitk")
-    // ---- topological order of internal nodes (children before parents)
-    std::vector<int32_t> topo;
-    topo.reserve(nT);
-    {
-        std::vector<int32_t> stack;
-        stack.reserve(128);
-        stack.push_back(root);
-        // iterative post-order: negative id = "emit"
-        while (!stack.empty()) {
-            int t = stack.back();
-            stack.pop_back();
-            if (t < 0) {
-                topo.push_back(~t);
-                continue;
-            }
-            if (leaf[t]) continue;
-            stack.push_back(~t);
-            stack.push_back(rch[t]);
-            stack.push_back(lch[t]);
-        }
-    }
-
-    PT(4, "topo")
-    // ---- layouts top-down (the consumer dictates the layout of both of its operands)
-    P.lay_off.assign(nT, 0);
-    P.lay_n.assign(nT, 0);
-    size_t lab_total = 0;
-    for (int t = 0; t < nT; ++t) lab_total += lab_n[t];
-    P.lay_data.assign(lab_total + (size_t)net.n_open + 64, 0);
-    size_t lay_top = 0;
-    std::vector<NodeCls> cls(nT);
-    std::vector<int32_t> cls_data(lab_total + 64, 0);  // every operand label falls in exactly one class of its consumer
-    size_t cls_top = 0;
-    {
-        if (net.n_open) {
-            ++stamp;
-            for (int q = 0; q < lab_n[root]; ++q) stC[labp(root)[q]] = stamp;
-            if (net.n_open != lab_n[root]) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
-            for (int i = 0; i < net.n_open; ++i)
-                if (stC[net.open_labels[i]] != stamp) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
-            P.lay_off[root] = 0;
-            P.lay_n[root] = (uint8_t)net.n_open;
-            for (int i = 0; i < net.n_open; ++i) P.lay_data[lay_top++] = net.open_labels[i];
-        }
-        std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
-        std::vector<int32_t> posC(NLAB, -1);
-        std::vector<int32_t> batA(NLAB, -1), batB(NLAB, -1);  // stamps: label is a batch label inside child A / B
-        std::vector<int32_t> secA(NLAB, -1), secB(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
-        const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
-        for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
-            const int t = *it;
-            if (P.lay_n[t] > 0 && !leaf[lch[t]] && !leaf[rch[t]]) {
-                // orientation: the operand that owns the label at C bit 0 becomes the M side (contract(A,B) == contract(B,A)),
-                // so that the low output bits are m tile bits 0,1,.. and the epilogue can move whole 16-byte vectors
-                const int32_t l0 = P.lay_data[P.lay_off[t]];
-                bool inL = false, inR = false;
-                for (int q = 0; q < lab_n[lch[t]]; ++q) inL = inL || labp(lch[t])[q] == l0;
-                for (int q = 0; q < lab_n[rch[t]]; ++q) inR = inR || labp(rch[t])[q] == l0;
-                if (inR && !inL) {
-                    const bool ok = true;
-                    if (ok) std::swap(lch[t], rch[t]);
-                }
-            }
-            const int A = lch[t], B = rch[t];
-            const int sN = ++stamp;  // stamp of this node (stA, stB, batA, batB)
-            const int32_t* lc = P.lay_data.data() + P.lay_off[t];
-            const int rc = P.lay_n[t];
-            for (int i = 0; i < rc; ++i) posC[lc[i]] = i;
-            for (int q = 0; q < lab_n[A]; ++q) stA[labp(A)[q]] = sN;
-            for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = sN;
-            // nodes whose tensors are all tiny end up inside fused subtrees (shared memory): label order is
-            // irrelevant there, so skip the ordering analysis (90 % of all nodes)
-            const bool tiny = rc <= 6 && lab_n[A] <= 6 && lab_n[B] <= 6;
-            // batch labels of the children (labels shared by a child's own operands)
-            for (int side = 0; side < 2 && !tiny; ++side) {
-                const int ch = side ? B : A;
-                if (leaf[ch]) continue;
-                auto& bat = side ? batB : batA;
-                auto& sec = side ? secB : secA;
-                const int c1 = lch[ch], c2 = rch[ch];
-                const int sS = ++stamp;
-                for (int q = 0; q < lab_n[c1]; ++q) stC[labp(c1)[q]] = sS;
-                for (int q = 0; q < lab_n[c2]; ++q) {
-                    const int32_t l = labp(c2)[q];
-                    if (stC[l] == sS) bat[l] = sN;
-                    else sec[l] = sN;
-                }
-            }
-            int32_t M[40], N[40], Bt[40], K[40], KA[40], KB[40];
-            int nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0;
-            for (int q = 0; q < lab_n[A]; ++q) {
-                int32_t l = labp(A)[q];
-                bool inB = stB[l] == sN, inC = posC[l] >= 0;
-                if (inB) (inC ? Bt[nb++] : K[nk++]) = l;
-                else (inC ? M[nm++] : KA[nka++]) = l;
-            }
-            for (int q = 0; q < lab_n[B]; ++q) {
-                int32_t l = labp(B)[q];
-                if (stA[l] == sN) continue;
-                (posC[l] >= 0 ? N[nn++] : KB[nkb++]) = l;
-            }
-            // M / N: group the labels by their class inside the producing child so that the low address bits of
-            // the operand form a run of the child's own tile labels (coalesced stores in the child): the child's
-            // larger output-only class first, then its other one, batch labels of the child last; then by position in C
-            auto class_key = [&](int32_t* v, int n, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
-                int n_first = 0, n_sec = 0;
-                for (int i = 0; i < n; ++i) {
-                    if (bat[v[i]] == sN) continue;
-                    (sec[v[i]] == sN ? n_sec : n_first)++;
-                }
-                const int k_first = n_first >= n_sec ? 0 : 1024, k_sec = n_first >= n_sec ? 1024 : 0;
-                for (int i = 0; i < n; ++i)
-                    key[v[i]] = (bat[v[i]] == sN ? 2048 : (sec[v[i]] == sN ? k_sec : k_first)) + posC[v[i]];
-                sort_by_key(v, key.data(), n);
-            };
-            // tile set = the labels with the LOWEST positions in C (this node's own stores are enumerated in C order);
-            // inside the tile set the order follows the child's classes (the child's stores), except that the label
-            // with the highest C position goes last: it selects the epilogue round, so it must not be a low C bit
-            auto order_side = [&](int32_t* v, int n, int tmax, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
-                for (int i = 0; i < n; ++i) key[v[i]] = posC[v[i]];
-                sort_by_key(v, key.data(), n);
-                const int tl = std::min(n, tmax);
-                // the lowest `nlow` tile labels stay in C order (then a 16-byte output vector is contiguous in the
-                // staging buffer too); the others follow the producing child's classes
-                // labels that are batch labels of the producing child cannot be low output bits of that child: last
-                for (int i = 0; i < tl; ++i) key[v[i]] = (bat[v[i]] == sN ? 1024 : 0) + posC[v[i]];
-                sort_by_key(v, key.data(), tl);
-                int n_free = 0;
-                while (n_free < tl && bat[v[n_free]] != sN) ++n_free;
-                const int nlow = std::min(n_free, half ? 3 : 2);
-                if (n_free > nlow) class_key(v + nlow, n_free - nlow, bat, sec);
-                if (tl >= 2) {
-                    int top = 0;
-                    for (int i = 1; i < tl; ++i)
-                        if (posC[v[i]] > posC[v[top]]) top = i;
-                    const int32_t lt = v[top];
-                    for (int i = top; i + 1 < tl; ++i) v[i] = v[i + 1];
-                    v[tl - 1] = lt;
-                }
-                if (n > tl) class_key(v + tl, n - tl, bat, sec);
-            };
-            if (!tiny) {
-                order_side(M, nm, TILE_M_MAX, batA, secA);
-                order_side(N, nn, GEMM_TILE_MAX, batB, secB);
-                for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
-                sort_by_key(Bt, key.data(), nb);
-                for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
-                sort_by_key(K, key.data(), nk);
-            }
-            if (scramble) {
-                Lcg g((uint64_t)t * 977 + 13);
-                g.shuffle(M, nm);
-                g.shuffle(N, nn);
-                g.shuffle(Bt, nb);
-                g.shuffle(K, nk);
-                g.shuffle(KA, nka);
-                g.shuffle(KB, nkb);
-            }
-            NodeCls& c = cls[t];
-            c.off = (int32_t)cls_top;
-            c.nm = (uint8_t)nm;
-            c.nn = (uint8_t)nn;
-            c.nb = (uint8_t)nb;
-            c.nk = (uint8_t)nk;
-            c.nka = (uint8_t)nka;
-            c.nkb = (uint8_t)nkb;
-            c.tm = (uint8_t)std::min(nm, TILE_M_MAX);
-            c.tn = (uint8_t)std::min(nn, GEMM_TILE_MAX);
-            {
-                int32_t* w = cls_data.data() + cls_top;
-                for (int i = 0; i < nm; ++i) *w++ = M[i];
-                for (int i = 0; i < nn; ++i) *w++ = N[i];
-                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
-                for (int i = 0; i < nk; ++i) *w++ = K[i];
-                for (int i = 0; i < nka; ++i) *w++ = KA[i];
-                for (int i = 0; i < nkb; ++i) *w++ = KB[i];
-                cls_top = (size_t)(w - cls_data.data());
-            }
-            // packed int16 GEMM: the two halves of a word are two consecutive k, so one shared reduced label becomes
-            // address bit 0 of BOTH operands:  A = [K0 | M_lo | K_rest | M_hi | Bt],  B = [K0 | N_lo | K_rest | N_hi | Bt]
-            c.kfirst = (half && !(P.flags & TB_PLAN_NO_GEMM) && nm >= MT_LOG && nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && nk >= 1 &&
-                        nka == 0 && nkb == 0 && !leaf[A] && !leaf[B])
-                           ? 1
-                           : 0;
-            if (c.kfirst) {
-                const int ra = nm + nk + nb, rb = nn + nk + nb;
-                P.lay_off[A] = (int32_t)lay_top;
-                P.lay_n[A] = (uint8_t)ra;
-                P.lay_off[B] = (int32_t)(lay_top + ra);
-                P.lay_n[B] = (uint8_t)rb;
-                int32_t* w = P.lay_data.data() + lay_top;
-                *w++ = K[0];
-                for (int i = 0; i < c.tm; ++i) *w++ = M[i];
-                for (int i = 1; i < nk; ++i) *w++ = K[i];
-                for (int i = c.tm; i < nm; ++i) *w++ = M[i];
-                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
-                *w++ = K[0];
-                for (int i = 0; i < c.tn; ++i) *w++ = N[i];
-                for (int i = 1; i < nk; ++i) *w++ = K[i];
-                for (int i = c.tn; i < nn; ++i) *w++ = N[i];
-                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
-                lay_top += (size_t)(ra + rb);
-            } else
-            // A = [M_lo | K | KA | M_hi | Bt],  B = [N_lo | K | KB | N_hi | Bt]
-            {
-                const int ra = nm + nk + nka + nb, rb = nn + nk + nkb + nb;
-                P.lay_off[A] = (int32_t)lay_top;
-                P.lay_n[A] = (uint8_t)ra;
-                P.lay_off[B] = (int32_t)(lay_top + ra);
-                P.lay_n[B] = (uint8_t)rb;
-                int32_t* w = P.lay_data.data() + lay_top;
-                for (int i = 0; i < c.tm; ++i) *w++ = M[i];
-                for (int i = 0; i < nk; ++i) *w++ = K[i];
-                for (int i = 0; i < nka; ++i) *w++ = KA[i];
-                for (int i = c.tm; i < nm; ++i) *w++ = M[i];
-                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
-                for (int i = 0; i < c.tn; ++i) *w++ = N[i];
-                for (int i = 0; i < nk; ++i) *w++ = K[i];
-                for (int i = 0; i < nkb; ++i) *w++ = KB[i];
-                for (int i = c.tn; i < nn; ++i) *w++ = N[i];
-                for (int i = 0; i < nb; ++i) *w++ = Bt[i];
-                lay_top += (size_t)(ra + rb);
-            }
-            for (int i = 0; i < rc; ++i) posC[lc[i]] = -1;
-        }
-    }
-    auto rank_of = [&](int t) { return (int)P.lay_n[t]; };
-    auto size_of = [&](int t) { return (int64_t)1 << P.lay_n[t]; };
-    auto layp = [&](int t) { return P.lay_data.data() + P.lay_off[t]; };
-
-    PT(5, "layouts")
-    // ---- pool (leaf tensors)
-    std::vector<int32_t> leaf_pool_off(nT, 0);
-    {
-        auto push_val = [&](double x, bool neg_inf, int cfg_bit = -1) { P.pool.push_back(Plan::encode_value(vt, x, neg_inf, cfg_bit)); };
-        const bool int_values = (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2 || vt == TB_VALUE_SIZE_CONFIG);
-        P.pool.reserve(8 + 2 * (size_t)nL + 4);
-        push_val(0, false); push_val(0, false); push_val(0, false); push_val(0, true);  // edge
-        push_val(0, false);                                                            // unit
-        push_val(0, false); push_val(0, false); push_val(0, false);                    // pad
-        double sum_abs = 0;
-        for (int i = 0; i < nT; ++i) {
-            if (!leaf[i]) continue;
-            const int vtx = i < nL ? leaf_vertex[i] : -1;
-            if (i < nL && leaf_fa[i] >= 0) {
-                // sliced leaf: a 2-element slot of its own.  vertex [0, w][x] -> scalar; edge with one end fixed -> row x of
-                // the (symmetric) edge tensor, (0, 0) or (0, -inf); both ends fixed -> scalar, -inf iff both are 1
-                double w = 0;
-                if (vtx >= 0) {
-                    w = weight_of(vtx);
-                    if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
-                    if (int_values) {
-                        if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
-                        sum_abs += std::fabs(w);
-                        if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
-                    }
-                }
-                Plan::PoolPatch pp{};
-                pp.vtx = vtx;
-                pp.off = (int32_t)P.pool.size();
-                pp.kind = (uint8_t)(vtx >= 0 ? 0 : (leaf_fb[i] < 0 ? 1 : 2));
-                pp.fa = leaf_fa[i];
-                pp.fb = leaf_fb[i];
-                pp.w = w;
-                P.patches.push_back(pp);
-                leaf_pool_off[i] = pp.off;
-                push_val(0, false);
-                push_val(0, false);
-            } else if (vtx < 0 && lab_n[i] == 0) {
-                leaf_pool_off[i] = POOL_UNIT;
-            } else if (vtx < 0) {
-                leaf_pool_off[i] = POOL_EDGE;
-            } else {
-                double w = weight_of(vtx);
-                if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
-                if (int_values) {
-                    if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
-                    sum_abs += std::fabs(w);
-                    if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
-                }
-                leaf_pool_off[i] = (int32_t)P.pool.size();
-                push_val(0, false);
-                push_val(w, false, vtx);  // size+configuration: choosing the vertex also sets its bit of the mask
-            }
-        }
-        while (P.pool.size() % 4) P.pool.push_back(0);
-        P.n_fixed = net.n_fixed;
-        if (net.n_fixed > 0) P.assign(net.fixed_values);
-        if (P.pool.size() > 65535) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;  // fused steps address the pool with 16 bits
-    }
-
-    PT(6, "pool")
-    // ---- kinds: fused subtrees / generic / gemm
-    std::vector<uint8_t> fus(nT, 0);
-    std::vector<int64_t> peak(nT, 0);
-    const bool allow_fused = !(P.flags & TB_PLAN_NO_FUSED_SUBTREES);
-    for (int t : topo) {
-        const int A = lch[t], B = rch[t];
-        const NodeCls& c = cls[t];
-        int tc = rank_of(t) + c.nk + c.nka + c.nkb;
-        bool ok = allow_fused && rank_of(t) <= FUSED_MAX_RANK && rank_of(A) <= FUSED_MAX_RANK &&
-                  rank_of(B) <= FUSED_MAX_RANK && tc <= FUSED_MAX_TC && (leaf[A] || fus[A]) && (leaf[B] || fus[B]);
-        int64_t pA = leaf[A] ? 0 : peak[A], sA = leaf[A] ? 0 : size_of(A);
-        int64_t pB = leaf[B] ? 0 : peak[B], sB = leaf[B] ? 0 : size_of(B);
-        int64_t pk = size_of(t) + (pA >= pB ? std::max(pA, sA + pB) : std::max(pB, sB + pA));
-        peak[t] = pk;
-        fus[t] = ok && pk <= (wide ? FUSED_SMEM_ELEMS / 2 : FUSED_SMEM_ELEMS);  // 32 KB of values either way
-    }
-    P.loc.assign(nT, LOC_ARENA);
-    P.off.assign(nT, 0);
-    P.level.assign(nT, -1);
-    for (int i = 0; i < nT; ++i)
-        if (leaf[i]) {
-            P.loc[i] = LOC_POOL;
-            P.off[i] = leaf_pool_off[i];
-        }
-
-    // ---- levels
-    std::vector<int8_t> kind(nT, -1);
-    int n_fused_roots = 0, n_big = 0;
-    for (int t : topo) {
-        if (fus[t]) {
-            kind[t] = KIND_FUSED;
-            bool is_sub_root = (t == root) || !fus[parent[t]];
-            P.level[t] = is_sub_root ? 0 : -1;
-            n_fused_roots += is_sub_root;
-        } else {
-            int lv = 1;
-            for (int c : {lch[t], rch[t]})
-                if (!leaf[c]) lv = std::max(lv, P.level[c] + 1);
-            P.level[t] = lv;
-            const NodeCls& c = cls[t];
-            bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= MT_LOG && c.nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && c.nk >= 1 &&
-                        c.nka == 0 && c.nkb == 0 && !leaf[lch[t]] && !leaf[rch[t]];
-            kind[t] = gemm ? KIND_GEMM : KIND_GENERIC;
-            P.n_levels = std::max(P.n_levels, lv);
-            ++n_big;
-        }
-    }
-
-    PT(7, "kinds")
-    // ---- arena allocation, safe for the dataflow executor: the only ordering between steps is operand -> consumer, so a
-    //      node's output may overlap ONLY tensors that are dead once the node's operands are complete: the interior of its
-    //      own subtree (everything below its two operands).  Sibling subtrees run concurrently and never share memory;
-    //      fused-subtree roots (level 0, all produced by one launch) get fresh blocks.  Post-order walk; every tensor hands
-    //      the free blocks of its subtree up to its consumer.
-    {
-        typedef std::vector<std::pair<int64_t, int64_t>> Blocks;  // (offset, size), sorted by offset, coalesced
-        std::vector<Blocks> after(nT);  // free blocks inside the subtree of t once t is complete (t's own block excluded)
-        const bool keep = (P.flags & TB_PLAN_KEEP_INTERMEDIATES) != 0;
-        int64_t top = 0;
-        auto insert_block = [](Blocks& bl, int64_t o, int64_t sz) {
-            auto it = std::lower_bound(bl.begin(), bl.end(), std::make_pair(o, (int64_t)0));
-            it = bl.insert(it, {o, sz});
-            auto nx = it + 1;
-            if (nx != bl.end() && it->first + it->second == nx->first) {
-                it->second += nx->second;
-                bl.erase(nx);
-            }
-            if (it != bl.begin()) {
-                auto pv = it - 1;
-                if (pv->first + pv->second == it->first) {
-                    pv->second += it->second;
-                    bl.erase(it);
-                }
-            }
-        };
-        for (int t : topo) {
-            if (P.level[t] < 0) continue;  // interior of a fused subtree: shared memory
-            const int64_t need = align_up(size_of(t), 64);
-            Blocks pool;
-            if (!keep && kind[t] != KIND_FUSED)
-                for (int c : {lch[t], rch[t]})
-                    if (!leaf[c] && P.level[c] >= 0) {
-                        for (const auto& bk : after[c]) insert_block(pool, bk.first, bk.second);
-                        Blocks().swap(after[c]);
-                    }
-            // best fit inside the subtree's dead interior, else a fresh block at the top of the arena
-            int best = -1;
-            for (int i = 0; i < (int)pool.size(); ++i)
-                if (pool[(size_t)i].second >= need && (best < 0 || pool[(size_t)i].second < pool[(size_t)best].second)) best = i;
-            if (best >= 0) {
-                P.off[t] = pool[(size_t)best].first;
-                pool[(size_t)best].first += need;
-                pool[(size_t)best].second -= need;
-                if (pool[(size_t)best].second == 0) pool.erase(pool.begin() + best);
-            } else {
-                P.off[t] = top;
-                top += need;
-            }
-            if (!keep && kind[t] != KIND_FUSED)
-                for (int c : {lch[t], rch[t]})
-                    if (!leaf[c] && P.level[c] >= 0) insert_block(pool, P.off[c], align_up(size_of(c), 64));
-            after[t].swap(pool);
-        }
-        P.arena_elems = top;
-        P.root_off = P.off[root];
-    }
-
-    PT(8, "arena")
-    // ---- emit steps
-    std::vector<uint8_t> posA(NLAB, NO_BIT), posB(NLAB, NO_BIT), posCc(NLAB, NO_BIT);
-    auto set_pos = [&](std::vector<uint8_t>& pos, int t, bool on) {
+    int rank_of(int t) const { return (int)P.lay_n[t]; }
+    int64_t size_of(int t) const { return (int64_t)1 << P.lay_n[t]; }
+    const int32_t* layp(int t) const { return P.lay_data.data() + P.lay_off[t]; }
+    void set_pos(std::vector<uint8_t>& pos, int t, bool on) {
         const int32_t* v = layp(t);
         for (int i = 0; i < rank_of(t); ++i) pos[v[i]] = on ? (uint8_t)i : NO_BIT;
-    };
-    auto rec_of = [&](int t, int knd, int lvl) {
+    }
+    Plan::StepRec rec_of(int t, int knd, int lvl) const {
         const NodeCls& c = cls[t];
         Plan::StepRec r{};
         r.node = t;
@@ -952,10 +195,9 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         r.tm = c.tm;
         r.tn = c.tn;
         return r;
-    };
-    double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, bytes_m = 0, sc = 0;
-    for (int t = 0; t < nT0; ++t) sc = std::max(sc, (double)((int)lab_n[t] - (int)kept[t]));
-    auto account = [&](int t, int knd) {
+    }
+    // algorithmic work of one step (ops by kernel kind, bytes the reference's tensors would move)
+    void account(int t, int knd) {
         const NodeCls& c = cls[t];
         auto p2 = [](int e) { return (double)(1ull << e); };
         int tc = rank_of(t) + c.nk + c.nka + c.nkb - folded[t];
@@ -969,318 +211,1207 @@ int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::stri
         const double nb_ = eb * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + p2(rank_of(t)));
         bytes += eb * (p2(rank_of(lch[t])) + p2(rank_of(rch[t])) + cb);
         if (knd == KIND_GEMM) bytes_m += nb_;  // what the kernel itself moves (a partial output included)
-    };
-    if (!temporary) P.recs.reserve(topo.size());
-    P.sub_steps.reserve(topo.size() - n_big);
-    P.subtrees.reserve(n_fused_roots);
-    P.big_steps.reserve(n_big);
-
-    // fused subtrees: post-order with a "reserve C, then children above it" shared-memory stack
-    struct Frame {
-        int x;
-        int64_t base;
-        bool is_root;
-        int stage;
-        int64_t cur;
-    };
-    std::vector<Frame> stack;
-    for (int t : topo) {
-        if (kind[t] != KIND_FUSED || P.level[t] != 0) continue;
-        SubTree st{};
-        st.first_step = (uint32_t)P.sub_steps.size();
-        st.out_off = P.off[t];
-        int64_t max_top = 0;
-        stack.clear();
-        stack.push_back({t, 0, true, 0, 0});
-        while (!stack.empty()) {
-            Frame& f = stack.back();
-            const int x = f.x, A = lch[x], B = rch[x];
-            int64_t pA = leaf[A] ? 0 : peak[A], pB = leaf[B] ? 0 : peak[B];
-            const int first = pA >= pB ? A : B, second = pA >= pB ? B : A;
-            if (f.stage == 0) {
-                int64_t above = f.base;
-                if (!f.is_root) {
-                    P.loc[x] = LOC_SMEM;
-                    P.off[x] = f.base;
-                    above = f.base + size_of(x);
-                }
-                max_top = std::max(max_top, above);
-                f.cur = above;
-                f.stage = 1;
-                if (!leaf[first]) {
-                    Frame nf{first, f.cur, false, 0, 0};
-                    f.cur += size_of(first);
-                    max_top = std::max(max_top, f.cur);
-                    stack.push_back(nf);
-                    continue;
-                }
-            }
-            if (f.stage == 1) {
-                f.stage = 2;
-                if (!leaf[second]) {
-                    Frame nf{second, f.cur, false, 0, 0};
-                    f.cur += size_of(second);
-                    max_top = std::max(max_top, f.cur);
-                    stack.push_back(nf);
-                    continue;
-                }
-            }
-            const NodeCls& c = cls[x];
-            const bool is_root = f.is_root;
-            SubStep s{};
-            s.a_off = (uint16_t)P.off[A];
-            s.b_off = (uint16_t)P.off[B];
-            s.c_off = is_root ? 0 : (uint16_t)P.off[x];
-            s.a_loc = (uint8_t)P.loc[A];
-            s.b_loc = (uint8_t)P.loc[B];
-            s.c_loc = is_root ? LOC_ARENA : LOC_SMEM;
-            s.rc = (uint8_t)rank_of(x);
-            s.nk = c.nk;
-            s.nka = c.nka;
-            s.nkb = c.nkb;
-            s.sa = c.tm;
-            s.sb = c.tn;
-            s.pad = c.kfirst;  // reduction bit 0 is address bit 0 of both operands, the other K bits start at sa+1 / sb+1
-            std::memset(s.a_shift, NO_BIT, sizeof s.a_shift + sizeof s.b_shift);
-            {
-                // position of each output label in A / B: stamp the (short) output, then walk A and B once
-                const int32_t* lx = layp(x);
-                const int rx = rank_of(x);
-                for (int i = 0; i < rx; ++i) posCc[lx[i]] = (uint8_t)i;
-                const int32_t* la_ = layp(A);
-                for (int i = 0, ra_ = rank_of(A); i < ra_; ++i)
-                    if (posCc[la_[i]] != NO_BIT) s.a_shift[posCc[la_[i]]] = (uint8_t)i;
-                const int32_t* lb_ = layp(B);
-                for (int i = 0, rb_ = rank_of(B); i < rb_; ++i)
-                    if (posCc[lb_[i]] != NO_BIT) s.b_shift[posCc[lb_[i]]] = (uint8_t)i;
-                for (int i = 0; i < rx; ++i) posCc[lx[i]] = NO_BIT;
-            }
-            P.sub_steps.push_back(s);
-            if (!temporary) P.recs.push_back(rec_of(x, KIND_FUSED, 0));
-            account(x, KIND_FUSED);
-            stack.pop_back();
-        }
-        st.n_steps = (uint32_t)P.sub_steps.size() - st.first_step;
-        st.smem_elems = (uint32_t)max_top;
-        P.subtrees.push_back(st);
     }
 
-    PT(9, "fused_emit")
-    // big steps by level
-    {
-        std::vector<int> order;
-        order.reserve(n_big);
-        for (int t : topo)
-            if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) order.push_back(t);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.level[x] < P.level[y]; });
-        P.big_level_begin.assign(P.n_levels + 2, 0);
-        std::vector<int32_t> big_index(nT, -1);  // node -> its position in big_steps (dependencies of the dataflow executor)
-        P.big_dep_a.reserve(n_big);
-        P.big_dep_b.reserve(n_big);
-        for (int t : order) {
-            const NodeCls& c = cls[t];
-            const int32_t* cd = cls_data.data() + c.off;
-            const int32_t *cM = cd, *cN = cd + c.nm, *cBt = cd + c.nm + c.nn;
+    // validate the network, copy the tree into flat per-tensor arrays, apply index slicing to the leaves
+    int load_network() {
+        if (net.n_leaves < 1) return fail(TB_ERR_BAD_ARGUMENT, "network has no leaves (pass a NULL plan for an empty graph)");
+        if (net.n_labels < 0) return fail(TB_ERR_BAD_ARGUMENT, "negative n_labels");
+        if (!net.leaf_off || (net.leaf_off[net.n_leaves] > 0 && !net.leaf_labels))
+            return fail(TB_ERR_BAD_ARGUMENT, "leaf_off / leaf_labels is NULL");
+        if (net.n_leaves > 1 && (!net.node_left || !net.node_right))
+            return fail(TB_ERR_BAD_ARGUMENT, "node_left / node_right is NULL");
+        if (net.n_open < 0 || (net.n_open > 0 && !net.open_labels)) return fail(TB_ERR_BAD_ARGUMENT, "bad open labels");
+
+        temporary = (extra_flags & TB_PLAN_TEMPORARY) != 0;
+        estimate_only = (extra_flags & TB_PLAN_ESTIMATE_ONLY) != 0;
+        extra_flags &= ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY);
+        P.flags = (net.flags & ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY)) | extra_flags;
+        if (P.flags & TB_PLAN_KEEP_INTERMEDIATES) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;
+        P.n_labels = net.n_labels;
+        synth = (net.n_leaves == 1);
+        nL = net.n_leaves + (synth ? 1 : 0);
+        nN = nL - 1;
+        nT0 = nL + nN;      // tensors of the given tree
+        nTmax = nT0 + 2 * nN;  // + (partial node, unit leaf) per split
+        P.n_leaves = nL;
+        P.n_nodes = nN;
+        NLAB = std::max(net.n_labels, 1);
+
+        // ---- flat per-tensor storage
+        lch.assign(nTmax, -1);
+        rch.assign(nTmax, -1);
+        parent.assign(nTmax, -1);
+        leaf.assign(nTmax, 0);
+        unary.assign(nTmax, 0);
+        lab_off.assign(nTmax, 0);
+        lab_n.assign(nTmax, 0);
+        lab_data.clear();
+        lab_data.reserve((size_t)nT0 * 8);
+
+        // ---- index slicing: fixed[l] = -1 (free) or the value label l is fixed to
+        fixed.clear();
+        fixed_idx.clear();
+        if (net.n_fixed < 0 || (net.n_fixed > 0 && (!net.fixed_labels || !net.fixed_values)))
+            return fail(TB_ERR_BAD_ARGUMENT, "bad fixed labels");
+        if (net.n_fixed > 0) {
+            fixed.assign(NLAB, -1);
+            fixed_idx.assign(NLAB, -1);
+            for (int i = 0; i < net.n_fixed; ++i) {
+                int32_t l = net.fixed_labels[i];
+                if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "fixed label out of range");
+                if (fixed[l] >= 0) return fail(TB_ERR_BAD_ARGUMENT, "fixed label repeated");
+                if (net.fixed_values[i] > 1) return fail(TB_ERR_BAD_ARGUMENT, "fixed value must be 0 or 1");
+                fixed[l] = (int8_t)net.fixed_values[i];
+                fixed_idx[l] = i;
+            }
+            for (int i = 0; i < net.n_open; ++i)
+                if (net.open_labels[i] >= 0 && net.open_labels[i] < net.n_labels && fixed[net.open_labels[i]] >= 0)
+                    return fail(TB_ERR_BAD_ARGUMENT, "a label cannot be both open and fixed");
+        }
+
+        // ---- leaves.  leaf_vertex[i] = vertex of a vertex leaf (-1: edge / unit leaf).  A leaf that lost labels to
+        //      index slicing reads a slice of its tensor from a pool slot of its own, filled by Plan::assign from the
+        //      values of its fixed labels (leaf_fa / leaf_fb = their positions in net.fixed_labels): all 2^k assignments
+        //      of the same labels share every descriptor of the plan and differ only in these pool words.
+        leaf_vertex.assign(nL, -1);
+        leaf_fa.assign(nL, -1);
+        leaf_fb.assign(nL, -1);
+        for (int i = 0; i < nL; ++i) leaf[i] = 1;
+        for (int i = 0; i < net.n_leaves; ++i) {
+            int b = net.leaf_off[i], e = net.leaf_off[i + 1];
+            if (e < b) return fail(TB_ERR_BAD_ARGUMENT, "leaf_off not monotone");
+            int r = e - b;
+            if (r < 1 || r > 2)
+                return fail(TB_ERR_UNSUPPORTED, "leaf " + std::to_string(i) + " has " + std::to_string(r) +
+                                                    " labels; IndependentSet leaves have 1 (vertex) or 2 (edge)");
+            lab_off[i] = (int32_t)lab_data.size();
+            int nfix = 0;  // fixed labels of this leaf
+            for (int q = b; q < e; ++q) {
+                int32_t l = net.leaf_labels[q];
+                if (l < 0 || l >= net.n_labels) return fail(TB_ERR_BAD_ARGUMENT, "leaf label out of range");
+                if (!fixed.empty() && fixed[l] >= 0) {
+                    (nfix++ ? leaf_fb[i] : leaf_fa[i]) = fixed_idx[l];
+                } else {
+                    lab_data.push_back(l);
+                }
+            }
+            if (r == 2 && net.leaf_labels[b] == net.leaf_labels[b + 1])
+                return fail(TB_ERR_UNSUPPORTED, "edge tensor with a repeated label (self loop)");
+            if (r == 1) leaf_vertex[i] = net.leaf_labels[b];
+            lab_n[i] = (uint8_t)(r - nfix);
+            if (lab_n[i] == 2) {
+                int32_t* v = lab_data.data() + lab_off[i];
+                if (v[0] > v[1]) std::swap(v[0], v[1]);
+            }
+        }
+        if (synth) lab_off[1] = (int32_t)lab_data.size();
+
+        // ---- tree
+        if (synth) {
+            lch[nL] = 0;
+            rch[nL] = 1;
+        } else {
+            for (int j = 0; j < nN; ++j) {
+                lch[nL + j] = net.node_left[j];
+                rch[nL + j] = net.node_right[j];
+            }
+        }
+        for (int j = 0; j < nN; ++j) {
+            int id = nL + j;
+            for (int c : {lch[id], rch[id]}) {
+                if (c < 0 || c >= id) return fail(TB_ERR_NOT_BINARY_TREE, "node " + std::to_string(j) + ": child id must be in [0, own id)");
+                if (parent[c] != -1) return fail(TB_ERR_NOT_BINARY_TREE, "tensor " + std::to_string(c) + " is used twice");
+                parent[c] = id;
+            }
+            if (lch[id] == rch[id]) return fail(TB_ERR_NOT_BINARY_TREE, "node contracts a tensor with itself");
+        }
+        for (int t = 0; t < nT0 - 1; ++t)
+            if (parent[t] == -1) return fail(TB_ERR_NOT_BINARY_TREE, "tensor " + std::to_string(t) + " is never contracted (forest, not a tree)");
+        root = nT0 - 1;
+        P.root_id = root;
+        return TB_OK;
+    }
+
+    // resolve the value type (auto -> packed int16 when the weights allow), number the leaves depth-first
+    int value_type_and_positions() {
+        // ---- weights / value type
+        vt = net.value_type;
+        wd = net.weight_dtype;
+        if (wd < TB_WEIGHT_UNIT || wd > TB_WEIGHT_F64) return fail(TB_ERR_BAD_ARGUMENT, "unknown weight_dtype");
+        if (wd != TB_WEIGHT_UNIT && !net.weights) return fail(TB_ERR_BAD_ARGUMENT, "weights is NULL but weight_dtype is not UNIT");
+        const bool int_weights = !(wd == TB_WEIGHT_F32 || wd == TB_WEIGHT_F64);
+        bool auto_i16 = false;
+        if (vt == TB_VALUE_AUTO) {
+            vt = int_weights ? TB_VALUE_I32 : TB_VALUE_F32;
+            auto_i16 = int_weights && !(P.flags & TB_PLAN_NO_I16);  // falls back to int32 below if the weights do not fit
+        }
+        if (vt != TB_VALUE_I32 && vt != TB_VALUE_F32 && vt != TB_VALUE_I16X2 && vt != TB_VALUE_F64 && vt != TB_VALUE_SIZE_CONFIG)
+            return fail(TB_ERR_BAD_ARGUMENT, "unknown value_type");
+        wide = (vt == TB_VALUE_F64 || vt == TB_VALUE_SIZE_CONFIG);  // 8-byte values: generic + fused kernels only
+        if (wide) P.flags |= TB_PLAN_NO_GEMM;
+        if (vt == TB_VALUE_SIZE_CONFIG && net.n_labels > 32)
+            return fail(TB_ERR_UNSUPPORTED, "value type size+configuration keeps the chosen vertices in a 32-bit mask: at most 32 labels "
+                                            "(regions of the branching tables have <= n_max = 20 vertices, src/types.jl:10)");
+        if (vt == TB_VALUE_I16X2 || auto_i16) {
+            // packed int16 needs every partial sum < 2^13: check sum |w| over the vertex leaves
+            double sum_abs = 0;
+            bool integral = true;
+            for (int i = 0; i < net.n_leaves; ++i)
+                if (leaf_vertex[i] >= 0) {
+                    double w = weight_of(leaf_vertex[i]);
+                    integral = integral && (w == std::floor(w));
+                    sum_abs += std::fabs(w);
+                }
+            const bool fits = integral && sum_abs < 8192.0;
+            if (vt == TB_VALUE_I16X2 && !fits) return fail(TB_ERR_UNSUPPORTED, "value type i16x2 needs integer weights with sum |w| < 8192");
+            if (auto_i16 && fits) vt = TB_VALUE_I16X2;
+        }
+        P.value_type = vt;
+        half = (vt == TB_VALUE_I16X2);
+        STAGE_ELEMS = GEMM_STAGE_ELEMS * (half ? 2 : 1);
+
+        // ---- leaf positions (DFS order) and subtree ranges
+        lo.assign(nT0, 0);
+        hi.assign(nT0, 0);
+        {
+            std::vector<int32_t> stack;
+            stack.reserve(64);
+            stack.push_back(root);
+            int pos = 0;
+            while (!stack.empty()) {
+                int t = stack.back();
+                stack.pop_back();
+                if (leaf[t]) {
+                    lo[t] = hi[t] = pos++;
+                } else {
+                    stack.push_back(rch[t]);
+                    stack.push_back(lch[t]);
+                }
+            }
+            for (int t = nL; t < nT0; ++t) {
+                lo[t] = std::min(lo[lch[t]], lo[rch[t]]);
+                hi[t] = std::max(hi[lch[t]], hi[rch[t]]);
+            }
+        }
+        minpos.assign(NLAB, std::numeric_limits<int32_t>::max());
+        maxpos.assign(NLAB, -1);
+        is_open.assign(NLAB, 0);
+        for (int i = 0; i < nL; ++i)
+            for (int q = 0; q < lab_n[i]; ++q) {
+                int32_t l = labp(i)[q];
+                minpos[l] = std::min(minpos[l], lo[i]);
+                maxpos[l] = std::max(maxpos[l], lo[i]);
+            }
+        for (int i = 0; i < net.n_open; ++i) {
+            int32_t l = net.open_labels[i];
+            if (l < 0 || l >= net.n_labels || maxpos[l] < 0) return fail(TB_ERR_BAD_ARGUMENT, "open label does not occur in any leaf");
+            if (is_open[l]) return fail(TB_ERR_BAD_ARGUMENT, "open label repeated");
+            is_open[l] = 1;
+        }
+        return TB_OK;
+    }
+
+    // label set of every node, bottom-up; a label is reduced at the lowest node that covers all its leaves
+    int label_sets() {
+        // ---- label sets bottom-up (ids of the given tree are already topological); sets are sorted
+        est_ops = 0;  // sum over nodes of 2^(labels involved): the reference's 2^tc (src/types.jl:120)
+        est_sc = 0;
+        for (int i = 0; i < nL; ++i) est_sc = std::max(est_sc, (int)lab_n[i]);
+        for (int t = nL; t < nT0; ++t) {
             const int A = lch[t], B = rch[t];
-            BigStep s{};
-            s.a_off = P.off[A];
-            s.b_off = P.off[B];
-            s.c_off = P.off[t];
-            s.a_loc = (uint8_t)P.loc[A];
-            s.b_loc = (uint8_t)P.loc[B];
-            s.kind = (uint8_t)kind[t];
-            s.rc = (uint8_t)rank_of(t);
-            s.nk = c.nk;
-            s.nka = c.nka;
-            s.nkb = c.nkb;
-            s.sa = c.tm;
-            s.sb = c.tn;
-            s.tm = c.tm;
-            s.tn = c.tn;
-            std::memset(s.a_shift, NO_BIT, 32);
-            std::memset(s.b_shift, NO_BIT, 32);
-            std::memset(s.c_shift, NO_BIT, 32);
-            if (kind[t] == KIND_GENERIC) {
-                set_pos(posA, A, true);
-                set_pos(posB, B, true);
-                const int32_t* lt = layp(t);
-                for (int i = 0; i < rank_of(t); ++i) {
-                    s.a_shift[i] = posA[lt[i]];
-                    s.b_shift[i] = posB[lt[i]];
-                    s.c_shift[i] = (uint8_t)i;
-                }
-                set_pos(posA, A, false);
-                set_pos(posB, B, false);
-                s.store_mode = c.kfirst;  // generic steps reuse this byte: K0-first operand layouts
-                int ks, po;
-                generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
-                if (ks == 0 && s.rc >= 10 && !wide) {  // streaming node: 4 consecutive outputs per thread and iteration
-                    s.vec4 = 1;
-                    po = s.rc >= 14 ? 12 : 10;  // 4096 outputs per CTA (4 iterations) amortise the per-CTA set-up
-                }
-                s.ks = (uint8_t)ks;
-                s.po = (uint8_t)po;
-                s.n_tiles = 1u << (s.rc - po);
-            } else {
-                set_pos(posCc, t, true);
-                int q = 0;
-                for (int i = 0; i < c.tm; ++i) s.c_shift[q++] = posCc[cM[i]];
-                for (int i = 0; i < c.tn; ++i) s.c_shift[q++] = posCc[cN[i]];
-                for (int i = c.tm; i < c.nm; ++i) s.c_shift[q++] = posCc[cM[i]];
-                for (int i = c.tn; i < c.nn; ++i) s.c_shift[q++] = posCc[cN[i]];
-                for (int i = 0; i < c.nb; ++i) s.c_shift[q++] = posCc[cBt[i]];
-                set_pos(posCc, t, false);
-                s.n_mhi = (uint8_t)(c.nm - c.tm);
-                s.n_nhi = (uint8_t)(c.nn - c.tn);
-                s.ng = (uint8_t)(s.rc - c.tm - c.tn);
-                int tps_log = (c.tm - MT_LOG) + (c.tn - 3);  // threads per sub-tile
-                int s_log = 8 - tps_log;                     // sub-tiles per CTA (256 threads)
-                int64_t per_k = ((int64_t)1 << s_log) * (((int64_t)1 << c.tm) + ((int64_t)1 << c.tn));
-                int kc = 0;
-                while (kc + 1 <= s.nk && (per_k << (kc + 1)) <= STAGE_ELEMS) ++kc;
-                s.kc = (uint8_t)kc;
-                int64_t groups = (int64_t)1 << s.ng;
-                int64_t S = (int64_t)1 << s_log;
-                s.n_tiles = (uint32_t)((groups + S - 1) / S);
-                s.store_mode = STORE_SCALAR;
-                if (s.c_shift[0] == 0 && s.c_shift[1] == 1) s.store_mode = STORE_VEC_M;
-                else if (s.c_shift[c.tm] == 0 && s.c_shift[c.tm + 1] == 1) s.store_mode = STORE_VEC_N;
-                // staged epilogue tables (k_gemm2): the tile is written in 4 rounds (the top m tile bit and the top n
-                // tile bit select the round); inside a round the (tm-1)+(tn-1) remaining tile bits are enumerated in
-                // C-address order.  a_shift[i] = position of the i-th such bit in the shared-memory staging index
-                // ([m bits 0..tm-2 | n bits 0..tn-2]), b_shift[i] = its C shift.  a_shift[30/31] = C shift of the top
-                // m / n tile bit, b_shift[31] = 1 if the two lowest bits are C bits 0,1 (128-bit stores).
-                // packed int16 only: a consumer thread holds the m tile bits {0, mp, tm-1}; mp (a_shift[29], default
-                // 1) is chosen so that the m labels on C bits 0..2 are thread-local, and b_shift[29] = 1 swaps the
-                // roles of m0 and m_mp (the thread pairs outputs along m_mp).  The tables use LOGICAL m positions:
-                // [first local bit, second local bit, the other in-round m bits in ascending order].
-                {
-                    const int nbr = c.tm + c.tn - 2;
-                    int ent_cs[16], ent_sp[16], ne = 0;
-                    auto build = [&](int mp, int mswap) -> int {
-                        int lm[8], nl = 0;  // logical position of the in-round m bit q
-                        lm[mswap ? mp : 0] = nl++;
-                        if (c.tm >= 3) lm[mswap ? 0 : mp] = nl++;
-                        for (int q = 1; q < c.tm - 1; ++q)
-                            if (q != mp) lm[q] = nl++;
-                        ne = 0;
-                        for (int i = 0; i < c.tm - 1; ++i) { ent_cs[ne] = s.c_shift[i]; ent_sp[ne++] = lm[i]; }
-                        for (int i = 0; i < c.tn - 1; ++i) { ent_cs[ne] = s.c_shift[c.tm + i]; ent_sp[ne++] = (c.tm - 1) + i; }
-                        for (int i = 1; i < ne; ++i) {
-                            int cs = ent_cs[i], sp = ent_sp[i], j = i - 1;
-                            while (j >= 0 && ent_cs[j] > cs) { ent_cs[j + 1] = ent_cs[j]; ent_sp[j + 1] = ent_sp[j]; --j; }
-                            ent_cs[j + 1] = cs; ent_sp[j + 1] = sp;
-                        }
-                        const bool evec = half ? (ent_cs[0] == 0 && ent_cs[1] == 1 && ent_cs[2] == 2) : (ent_cs[0] == 0 && ent_cs[1] == 1);
-                        s.b_shift[31] = evec ? 1 : 0;
-                        // ecase != 0: the elements of one 16-byte output vector are also contiguous in the staging
-                        // buffer (one LDS.128 instead of 4 / 8 scalar loads).  int32: 1 = C bits 0,1 are m0,m1.
-                        // packed int16: the thread holds (u, v) x (n0, n1) of a round (u, v = its local m bits), so it
-                        // can write any of the orders C bits (0,1,2) = 1: (u,v,m2)  2: (u,v,n0)  3: (u,n0,v)
-                        // 4: (u,n0,n1) as 16-byte vectors; for 2..4 the staging index is [the three C bits | the fourth
-                        // thread-local bit | m2.. | n2..] and the table holds positions in THAT layout.
-                        int ecase = 0;
-                        if (half) {
-                            const int n0 = c.tm - 1, n1 = c.tm;  // layout-1 staging positions of the n bits 0,1
-                            if (evec && ent_sp[0] == 0) {
-                                if (ent_sp[1] == 1 && ent_sp[2] == 2) ecase = 1;
-                                else if (ent_sp[1] == 1 && ent_sp[2] == n0) ecase = 2;
-                                else if (ent_sp[1] == n0 && ent_sp[2] == 1) ecase = 3;
-                                else if (ent_sp[1] == n0 && ent_sp[2] == n1) ecase = 4;
-                            }
-                            if (ecase >= 2) {
-                                static const int low[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
-                                for (int i = 0; i < ne; ++i) {  // {u, v, n0, n1} -> low[ecase], m q>=2 -> q+2, n unchanged
-                                    const int sp = ent_sp[i];
-                                    if (sp == 0) ent_sp[i] = low[ecase][0];
-                                    else if (sp == 1) ent_sp[i] = low[ecase][1];
-                                    else if (sp == n0) ent_sp[i] = low[ecase][2];
-                                    else if (sp == n1) ent_sp[i] = low[ecase][3];
-                                    else if (sp < n0) ent_sp[i] = sp + 2;
-                                }
-                            }
-                        } else {
-                            ecase = (ent_sp[0] == 0 && ent_sp[1] == 1) ? 1 : 0;
-                        }
-                        return ecase;
-                    };
-                    int mp = 1, mswap = 0;
-                    if (half && c.tm >= 4) {
-                        int q_by_cs[3] = {-1, -1, -1};
-                        for (int q = 0; q < c.tm - 1; ++q)
-                            if (s.c_shift[q] < 3) q_by_cs[s.c_shift[q]] = q;
-                        const int q0 = q_by_cs[0];
-                        if (q0 > 0) {
-                            mp = q0;
-                            mswap = 1;
-                        } else if (q0 == 0) {
-                            const int q1 = q_by_cs[1] > 0 ? q_by_cs[1] : q_by_cs[2];
-                            if (q1 > 1) mp = q1;
-                        }
+            const int na = lab_n[A], nb = lab_n[B];
+            int32_t u[80];
+            int nu = 0;
+            {
+                const int32_t *a = labp(A), *b = labp(B);
+                int i = 0, j = 0;
+                while (i < na || j < nb) {
+                    if (j >= nb || (i < na && a[i] < b[j])) u[nu++] = a[i++];
+                    else if (i >= na || b[j] < a[i]) u[nu++] = b[j++];
+                    else {
+                        u[nu++] = a[i];
+                        ++i;
+                        ++j;
                     }
-                    int ecase = build(mp, mswap);
-                    if (ecase == 0 && (mp != 1 || mswap)) {
-                        mp = 1;
-                        mswap = 0;
-                        ecase = build(mp, mswap);
-                    }
-                    s.a_shift[29] = (uint8_t)mp;
-                    s.b_shift[29] = (uint8_t)mswap;
-                    s.a_shift[30] = s.c_shift[c.tm - 1];
-                    s.a_shift[31] = s.c_shift[c.tm + c.tn - 1];
-                    s.b_shift[30] = (uint8_t)ecase;
-                    for (int i = 0; i < nbr; ++i) { s.a_shift[i] = (uint8_t)ent_sp[i]; s.b_shift[i] = (uint8_t)ent_cs[i]; }
-                }
-                // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
-                // (bit 0 if stores are scalar) on the low lane bits
-                {
-                    const int probe = s.store_mode == STORE_SCALAR ? 0 : 2;
-                    bool n_owns = false;
-                    for (int i = 0; i < c.tn; ++i)
-                        if (s.c_shift[c.tm + i] == probe) n_owns = true;
-                    s.lane_n_first = n_owns ? 1 : 0;
                 }
             }
-            big_index[t] = (int32_t)P.big_steps.size();
-            P.big_log2_ops.push_back((float)(rank_of(t) + c.nk + c.nka + c.nkb));
-            P.big_bytes.push_back((double)Plan::elem_size_of(vt) * (std::ldexp(1.0, rank_of(A)) + std::ldexp(1.0, rank_of(B)) + std::ldexp(1.0, rank_of(t))));
-            P.big_dep_a.push_back(big_index[A]);  // -1 for leaves and fused subtrees
-            P.big_dep_b.push_back(big_index[B]);
-            P.big_steps.push_back(s);
-            if (!temporary) P.recs.push_back(rec_of(t, kind[t], P.level[t]));
-            account(t, kind[t]);
+            if (nu > 62) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 62 labels");
+            lab_off[t] = (int32_t)lab_data.size();
+            int no = 0;
+            for (int q = 0; q < nu; ++q) {
+                int32_t l = u[q];
+                bool closed = !is_open[l] && minpos[l] >= lo[t] && maxpos[l] <= hi[t];
+                if (!closed) {
+                    lab_data.push_back(l);
+                    ++no;
+                }
+            }
+            if (no > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(no) + " > 31");
+            if (nu - no > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
+            lab_n[t] = (uint8_t)no;
+            est_ops += std::ldexp(1.0, nu);
+            est_sc = std::max(est_sc, no);
         }
-        int idx = 0;
-        for (int lv = 1; lv <= P.n_levels + 1; ++lv) {
-            while (idx < (int)order.size() && P.level[order[idx]] < lv) ++idx;
-            P.big_level_begin[lv] = idx;
+        if (estimate_only) {
+            P.stats = tb_plan_stats{};
+            P.stats.ops = est_ops;
+            P.stats.tc = est_ops > 0 ? std::log2(est_ops) : 0;
+            P.stats.sc = est_sc;
+            P.stats.n_nodes = nN;
+            P.stats.value_type = vt;
+            finished = true;
+            return TB_OK;
         }
-        P.big_level_begin[0] = 0;
+
+        // ---- the reference's memory estimators on the GIVEN tree (before any rewrite), in elements, all label sizes 2:
+        //      contraction_all_memory = log2(sum of the sizes of all intermediates)          (src/utils.jl:222-229)
+        //      contraction_peak_memory = log2(max of the running total)                       (src/utils.jl:197-219):
+        //      the walk is depth-first, left operand first; a node adds its result and releases the operands of its
+        //      CHILD nodes (its own operands are released one step later, by its parent) -- restated as the reference has it
+        est_all = 0;
+        est_peak = 0;
+        return TB_OK;
     }
 
-    PT(10, "big_emit")
-    tb_plan_stats& S = P.stats;
-    S.sc = sc;
-    S.ops = ops_f + ops_g + ops_m;
-    S.tc = S.ops > 0 ? std::log2(S.ops) : 0;
-    S.algo_bytes = bytes;
-    S.arena_elems = P.arena_elems;
-    S.n_nodes = nN;
-    S.n_levels = P.n_levels;
-    S.n_fused_subtrees = (int)P.subtrees.size();
-    S.n_fused_steps = (int)P.sub_steps.size();
-    S.n_gemm_steps = 0;
-    S.n_generic_steps = 0;
-    for (auto& b : P.big_steps) (b.kind == KIND_GEMM ? S.n_gemm_steps : S.n_generic_steps)++;
-    S.value_type = vt;
-    S.root_rank = rank_of(root);
-    S.gemm_ops = ops_m;
-    S.fused_ops = ops_f;
-    S.generic_ops = ops_g;
-    S.gemm_bytes = bytes_m;
-    S.peak_memory_log2 = est_peak > 0 ? std::log2(est_peak) : 0;
-    S.all_memory_log2 = est_all > 0 ? std::log2(est_all) : 0;
-    return TB_OK;
+    // the reference's contraction_peak_memory / contraction_all_memory on the given tree
+    int reference_estimators() {
+        if (!temporary) {
+            // the depth-first order (left operand first) is the order in which the leaf positions lo[] were numbered above:
+            // a node is finished when its last leaf has been seen, so sorting is not needed -- walk the nodes by the stack
+            double p2[33];
+            for (int i = 0; i <= 32; ++i) p2[i] = (double)(1ull << i);
+            double cur = 0;
+            for (int i = 0; i < net.n_leaves; ++i) cur += p2[lab_n[i]];
+            est_peak = cur;
+            std::vector<double> freed_later(nT0, 0.0);  // sum of a node's operand sizes
+            std::vector<int32_t> stack;
+            stack.reserve(128);
+            stack.push_back(root);
+            while (!stack.empty()) {
+                const int t = stack.back();
+                if (t < 0) {  // second visit of node ~t: both operands are done
+                    stack.pop_back();
+                    const int x = ~t, A = lch[x], B = rch[x];
+                    const double alloc = p2[lab_n[x]];
+                    cur += alloc - (freed_later[A] + freed_later[B]);
+                    freed_later[x] = p2[lab_n[A]] + p2[lab_n[B]];
+                    if (cur > est_peak) est_peak = cur;
+                    est_all += alloc;
+                    continue;
+                }
+                stack.pop_back();
+                if (leaf[t]) continue;
+                stack.push_back(~t);
+                stack.push_back(rch[t]);
+                stack.push_back(lch[t]);
+            }
+        }
+        return TB_OK;
+    }
+
+    // split long reductions into a partial step + a max over the kept labels (or fold it into the consumer)
+    int split_k() {
+        // stamp arrays for O(1) membership
+        stA.assign(NLAB, -1);
+        stB.assign(NLAB, -1);
+        stC.assign(NLAB, -1);
+        stamp = 0;
+
+        // ---- split-K rewrite: node t = contract(A, B) with a long reduction becomes
+        //      u = contract(A, B) keeping `sk` of the shared reduced labels, t = max over those labels of u
+        //      (t = contract(u, unit scalar)).  Balances CTA run times inside a level launch.
+        nT = nT0;
+        folded.assign(nTmax, 0);  // split labels a node reduces on behalf of its children (not algorithmic work)
+        kept.assign(nTmax, 0);    // split labels a node keeps as extra output labels for its consumer
+        if (!(P.flags & TB_PLAN_NO_SPLIT_K)) {
+            for (int t = nL; t < nT0; ++t) {
+                const int A = lch[t], B = rch[t];
+                if ((int)lab_n[A] + (int)lab_n[B] < 16) continue;  // cannot have a long reduction
+                ++stamp;
+                for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = stamp;
+                for (int q = 0; q < lab_n[t]; ++q) stC[labp(t)[q]] = stamp;
+                int nm = 0, nn = 0, nk = 0, nka = 0, nkb = 0;
+                int32_t Ksh[40];
+                for (int q = 0; q < lab_n[A]; ++q) {
+                    int32_t l = labp(A)[q];
+                    stA[l] = stamp;
+                    bool inB = stB[l] == stamp, inC = stC[l] == stamp;
+                    if (inB && !inC) Ksh[nk++] = l;
+                    else if (!inB && inC) ++nm;
+                    else if (!inB && !inC) ++nka;
+                }
+                for (int q = 0; q < lab_n[B]; ++q) {
+                    int32_t l = labp(B)[q];
+                    if (stA[l] != stamp) (stC[l] == stamp ? nn : nkb)++;
+                }
+                const int rc = lab_n[t];
+                const int gm = nm, gn = nn;
+                const bool gemm_like = !(P.flags & TB_PLAN_NO_GEMM) && gm >= MT_LOG && gn >= 3 &&
+                                       std::min(gm, TILE_M_MAX) + std::min(gn, GEMM_TILE_MAX) >= MT_LOG + 6 && nk >= 1 && nka == 0 &&
+                                       nkb == 0 && !leaf[A] && !leaf[B];
+                int serial_log, limit;
+                if (gemm_like) {
+                    serial_log = nk;
+                    limit = 8;
+                } else {
+                    int ks, po;
+                    generic_split(rc, nk + nka + nkb, ks, po);
+                    serial_log = nk + nka + nkb - ks;
+                    limit = 7;
+                }
+                int sk = (serial_log > limit && nk > 0) ? std::min(serial_log - limit, gemm_like ? nk - 1 : nk) : 0;
+                if (gemm_like) {
+                    // parallelism: a node with few output tiles and a long reduction would occupy only a few CTAs of its
+                    // level launch for a long time; split k until it has ~32 tiles (keeping >= 32 k-steps per tile).  Its
+                    // output is small by construction, so the extra unary max pass is cheap.
+                    const int tile_log = 14;
+                    const int t_log = std::max(0, rc - tile_log);
+                    static const int target_log = [] {
+                        const char* e = getenv("TB_SPLIT_TARGET");  // log2 of the tiles a node should have; 0 disables
+                        return e ? atoi(e) : 0;  // measured on cfg2 (profiles/s02_split_target_sweep.jsonl): with 4 lanes in flight extra levels cost more than idle CTA slots
+                    }();
+                    const int sk_par = std::min(std::max(0, target_log - t_log), std::max(0, nk - 5));
+                    sk = std::max(sk, sk_par);
+                }
+                sk = std::min(sk, MAX_RANK - rc);
+                if (sk <= 0) continue;
+                // If the consumer of t is itself a reduction over (almost) all of t, it can reduce the split labels too:
+                // t keeps them as output labels and they become labels private to one operand of the consumer.  The
+                // consumer then reads the partial results once - exactly what the separate max pass would have read.
+                static const bool no_fold = getenv("TB_NO_FOLD") != nullptr;  // diagnostics: keep the separate max pass
+                if (const int pr = parent[t]; pr >= 0 && !no_fold) {
+                    const int sib = lch[pr] == t ? rch[pr] : lch[pr];
+                    ++stamp;
+                    for (int q = 0; q < rc; ++q) stA[labp(t)[q]] = stamp;
+                    for (int q = 0; q < lab_n[pr]; ++q) stC[labp(pr)[q]] = stamp;
+                    int n_sib_out = 0;  // output labels of the consumer that only the sibling carries
+                    for (int q = 0; q < lab_n[sib]; ++q) {
+                        const int32_t l = labp(sib)[q];
+                        if (stA[l] != stamp && stC[l] == stamp) ++n_sib_out;
+                    }
+                    if (n_sib_out <= 1 && (int)folded[pr] + sk <= 8) {
+                        int32_t tmp[48];
+                        int n = 0;
+                        for (int q = 0; q < rc; ++q) tmp[n++] = labp(t)[q];
+                        for (int q = nk - sk; q < nk; ++q) tmp[n++] = Ksh[q];
+                        std::sort(tmp, tmp + n);
+                        lab_off[t] = (int32_t)lab_data.size();
+                        lab_n[t] = (uint8_t)n;
+                        lab_data.insert(lab_data.end(), tmp, tmp + n);
+                        folded[pr] = (uint8_t)(folded[pr] + sk);
+                        kept[t] = (uint8_t)sk;
+                        continue;
+                    }
+                }
+                const int u = nT++, ul = nT++;
+                lch[u] = A;
+                rch[u] = B;
+                parent[u] = t;
+                folded[u] = folded[t];
+                folded[t] = 0;
+                // lab[u] = lab[t] + the last sk shared reduced labels, sorted
+                {
+                    int32_t tmp[48];
+                    int n = 0;
+                    for (int q = 0; q < rc; ++q) tmp[n++] = labp(t)[q];
+                    for (int q = nk - sk; q < nk; ++q) tmp[n++] = Ksh[q];
+                    std::sort(tmp, tmp + n);
+                    lab_off[u] = (int32_t)lab_data.size();
+                    lab_n[u] = (uint8_t)n;
+                    lab_data.insert(lab_data.end(), tmp, tmp + n);
+                }
+                leaf[ul] = 1;
+                parent[ul] = t;
+                lab_off[ul] = (int32_t)lab_data.size();
+                lab_n[ul] = 0;
+                parent[A] = parent[B] = u;
+                lch[t] = u;
+                rch[t] = ul;
+                unary[t] = 1;
+            }
+        }
+        P.n_tensors = nT;
+        return TB_OK;
+    }
+
+    // children before parents, depth-first (left operand first)
+    int topological_order() {
+        // ---- topological order of internal nodes (children before parents)
+        topo.clear();
+        topo.reserve(nT);
+        {
+            std::vector<int32_t> stack;
+            stack.reserve(128);
+            stack.push_back(root);
+            // iterative post-order: negative id = "emit"
+            while (!stack.empty()) {
+                int t = stack.back();
+                stack.pop_back();
+                if (t < 0) {
+                    topo.push_back(~t);
+                    continue;
+                }
+                if (leaf[t]) continue;
+                stack.push_back(~t);
+                stack.push_back(rch[t]);
+                stack.push_back(lch[t]);
+            }
+        }
+        return TB_OK;
+    }
+
+    // top-down: the consumer dictates the label order of both operands, so no step ever permutes
+    int layouts() {
+        // ---- layouts top-down (the consumer dictates the layout of both of its operands)
+        P.lay_off.assign(nT, 0);
+        P.lay_n.assign(nT, 0);
+        lab_total = 0;
+        for (int t = 0; t < nT; ++t) lab_total += lab_n[t];
+        P.lay_data.assign(lab_total + (size_t)net.n_open + 64, 0);
+        lay_top = 0;
+        cls.assign(nT, NodeCls{});
+        cls_data.assign(lab_total + 64, 0);  // every operand label falls in exactly one class of its consumer
+        cls_top = 0;
+        {
+            if (net.n_open) {
+                ++stamp;
+                for (int q = 0; q < lab_n[root]; ++q) stC[labp(root)[q]] = stamp;
+                if (net.n_open != lab_n[root]) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
+                for (int i = 0; i < net.n_open; ++i)
+                    if (stC[net.open_labels[i]] != stamp) return fail(TB_ERR_INTERNAL, "open labels do not match the root label set");
+                P.lay_off[root] = 0;
+                P.lay_n[root] = (uint8_t)net.n_open;
+                for (int i = 0; i < net.n_open; ++i) P.lay_data[lay_top++] = net.open_labels[i];
+            }
+            std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
+            std::vector<int32_t> posC(NLAB, -1);
+            std::vector<int32_t> batA(NLAB, -1), batB(NLAB, -1);  // stamps: label is a batch label inside child A / B
+            std::vector<int32_t> secA(NLAB, -1), secB(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
+            const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
+            for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
+                const int t = *it;
+                if (P.lay_n[t] > 0 && !leaf[lch[t]] && !leaf[rch[t]]) {
+                    // orientation: the operand that owns the label at C bit 0 becomes the M side (contract(A,B) == contract(B,A)),
+                    // so that the low output bits are m tile bits 0,1,.. and the epilogue can move whole 16-byte vectors
+                    const int32_t l0 = P.lay_data[P.lay_off[t]];
+                    bool inL = false, inR = false;
+                    for (int q = 0; q < lab_n[lch[t]]; ++q) inL = inL || labp(lch[t])[q] == l0;
+                    for (int q = 0; q < lab_n[rch[t]]; ++q) inR = inR || labp(rch[t])[q] == l0;
+                    if (inR && !inL) {
+                        const bool ok = true;
+                        if (ok) std::swap(lch[t], rch[t]);
+                    }
+                }
+                const int A = lch[t], B = rch[t];
+                const int sN = ++stamp;  // stamp of this node (stA, stB, batA, batB)
+                const int32_t* lc = P.lay_data.data() + P.lay_off[t];
+                const int rc = P.lay_n[t];
+                for (int i = 0; i < rc; ++i) posC[lc[i]] = i;
+                for (int q = 0; q < lab_n[A]; ++q) stA[labp(A)[q]] = sN;
+                for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = sN;
+                // nodes whose tensors are all tiny end up inside fused subtrees (shared memory): label order is
+                // irrelevant there, so skip the ordering analysis (90 % of all nodes)
+                const bool tiny = rc <= 6 && lab_n[A] <= 6 && lab_n[B] <= 6;
+                // batch labels of the children (labels shared by a child's own operands)
+                for (int side = 0; side < 2 && !tiny; ++side) {
+                    const int ch = side ? B : A;
+                    if (leaf[ch]) continue;
+                    auto& bat = side ? batB : batA;
+                    auto& sec = side ? secB : secA;
+                    const int c1 = lch[ch], c2 = rch[ch];
+                    const int sS = ++stamp;
+                    for (int q = 0; q < lab_n[c1]; ++q) stC[labp(c1)[q]] = sS;
+                    for (int q = 0; q < lab_n[c2]; ++q) {
+                        const int32_t l = labp(c2)[q];
+                        if (stC[l] == sS) bat[l] = sN;
+                        else sec[l] = sN;
+                    }
+                }
+                int32_t M[40], N[40], Bt[40], K[40], KA[40], KB[40];
+                int nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0;
+                for (int q = 0; q < lab_n[A]; ++q) {
+                    int32_t l = labp(A)[q];
+                    bool inB = stB[l] == sN, inC = posC[l] >= 0;
+                    if (inB) (inC ? Bt[nb++] : K[nk++]) = l;
+                    else (inC ? M[nm++] : KA[nka++]) = l;
+                }
+                for (int q = 0; q < lab_n[B]; ++q) {
+                    int32_t l = labp(B)[q];
+                    if (stA[l] == sN) continue;
+                    (posC[l] >= 0 ? N[nn++] : KB[nkb++]) = l;
+                }
+                // M / N: group the labels by their class inside the producing child so that the low address bits of
+                // the operand form a run of the child's own tile labels (coalesced stores in the child): the child's
+                // larger output-only class first, then its other one, batch labels of the child last; then by position in C
+                auto class_key = [&](int32_t* v, int n, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
+                    int n_first = 0, n_sec = 0;
+                    for (int i = 0; i < n; ++i) {
+                        if (bat[v[i]] == sN) continue;
+                        (sec[v[i]] == sN ? n_sec : n_first)++;
+                    }
+                    const int k_first = n_first >= n_sec ? 0 : 1024, k_sec = n_first >= n_sec ? 1024 : 0;
+                    for (int i = 0; i < n; ++i)
+                        key[v[i]] = (bat[v[i]] == sN ? 2048 : (sec[v[i]] == sN ? k_sec : k_first)) + posC[v[i]];
+                    sort_by_key(v, key.data(), n);
+                };
+                // tile set = the labels with the LOWEST positions in C (this node's own stores are enumerated in C order);
+                // inside the tile set the order follows the child's classes (the child's stores), except that the label
+                // with the highest C position goes last: it selects the epilogue round, so it must not be a low C bit
+                auto order_side = [&](int32_t* v, int n, int tmax, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
+                    for (int i = 0; i < n; ++i) key[v[i]] = posC[v[i]];
+                    sort_by_key(v, key.data(), n);
+                    const int tl = std::min(n, tmax);
+                    // the lowest `nlow` tile labels stay in C order (then a 16-byte output vector is contiguous in the
+                    // staging buffer too); the others follow the producing child's classes
+                    // labels that are batch labels of the producing child cannot be low output bits of that child: last
+                    for (int i = 0; i < tl; ++i) key[v[i]] = (bat[v[i]] == sN ? 1024 : 0) + posC[v[i]];
+                    sort_by_key(v, key.data(), tl);
+                    int n_free = 0;
+                    while (n_free < tl && bat[v[n_free]] != sN) ++n_free;
+                    const int nlow = std::min(n_free, half ? 3 : 2);
+                    if (n_free > nlow) class_key(v + nlow, n_free - nlow, bat, sec);
+                    if (tl >= 2) {
+                        int top = 0;
+                        for (int i = 1; i < tl; ++i)
+                            if (posC[v[i]] > posC[v[top]]) top = i;
+                        const int32_t lt = v[top];
+                        for (int i = top; i + 1 < tl; ++i) v[i] = v[i + 1];
+                        v[tl - 1] = lt;
+                    }
+                    if (n > tl) class_key(v + tl, n - tl, bat, sec);
+                };
+                if (!tiny) {
+                    order_side(M, nm, TILE_M_MAX, batA, secA);
+                    order_side(N, nn, GEMM_TILE_MAX, batB, secB);
+                    for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
+                    sort_by_key(Bt, key.data(), nb);
+                    for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
+                    sort_by_key(K, key.data(), nk);
+                }
+                if (scramble) {
+                    Lcg g((uint64_t)t * 977 + 13);
+                    g.shuffle(M, nm);
+                    g.shuffle(N, nn);
+                    g.shuffle(Bt, nb);
+                    g.shuffle(K, nk);
+                    g.shuffle(KA, nka);
+                    g.shuffle(KB, nkb);
+                }
+                NodeCls& c = cls[t];
+                c.off = (int32_t)cls_top;
+                c.nm = (uint8_t)nm;
+                c.nn = (uint8_t)nn;
+                c.nb = (uint8_t)nb;
+                c.nk = (uint8_t)nk;
+                c.nka = (uint8_t)nka;
+                c.nkb = (uint8_t)nkb;
+                c.tm = (uint8_t)std::min(nm, TILE_M_MAX);
+                c.tn = (uint8_t)std::min(nn, GEMM_TILE_MAX);
+                {
+                    int32_t* w = cls_data.data() + cls_top;
+                    for (int i = 0; i < nm; ++i) *w++ = M[i];
+                    for (int i = 0; i < nn; ++i) *w++ = N[i];
+                    for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                    for (int i = 0; i < nk; ++i) *w++ = K[i];
+                    for (int i = 0; i < nka; ++i) *w++ = KA[i];
+                    for (int i = 0; i < nkb; ++i) *w++ = KB[i];
+                    cls_top = (size_t)(w - cls_data.data());
+                }
+                // packed int16 GEMM: the two halves of a word are two consecutive k, so one shared reduced label becomes
+                // address bit 0 of BOTH operands:  A = [K0 | M_lo | K_rest | M_hi | Bt],  B = [K0 | N_lo | K_rest | N_hi | Bt]
+                c.kfirst = (half && !(P.flags & TB_PLAN_NO_GEMM) && nm >= MT_LOG && nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && nk >= 1 &&
+                            nka == 0 && nkb == 0 && !leaf[A] && !leaf[B])
+                               ? 1
+                               : 0;
+                if (c.kfirst) {
+                    const int ra = nm + nk + nb, rb = nn + nk + nb;
+                    P.lay_off[A] = (int32_t)lay_top;
+                    P.lay_n[A] = (uint8_t)ra;
+                    P.lay_off[B] = (int32_t)(lay_top + ra);
+                    P.lay_n[B] = (uint8_t)rb;
+                    int32_t* w = P.lay_data.data() + lay_top;
+                    *w++ = K[0];
+                    for (int i = 0; i < c.tm; ++i) *w++ = M[i];
+                    for (int i = 1; i < nk; ++i) *w++ = K[i];
+                    for (int i = c.tm; i < nm; ++i) *w++ = M[i];
+                    for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                    *w++ = K[0];
+                    for (int i = 0; i < c.tn; ++i) *w++ = N[i];
+                    for (int i = 1; i < nk; ++i) *w++ = K[i];
+                    for (int i = c.tn; i < nn; ++i) *w++ = N[i];
+                    for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                    lay_top += (size_t)(ra + rb);
+                } else
+                // A = [M_lo | K | KA | M_hi | Bt],  B = [N_lo | K | KB | N_hi | Bt]
+                {
+                    const int ra = nm + nk + nka + nb, rb = nn + nk + nkb + nb;
+                    P.lay_off[A] = (int32_t)lay_top;
+                    P.lay_n[A] = (uint8_t)ra;
+                    P.lay_off[B] = (int32_t)(lay_top + ra);
+                    P.lay_n[B] = (uint8_t)rb;
+                    int32_t* w = P.lay_data.data() + lay_top;
+                    for (int i = 0; i < c.tm; ++i) *w++ = M[i];
+                    for (int i = 0; i < nk; ++i) *w++ = K[i];
+                    for (int i = 0; i < nka; ++i) *w++ = KA[i];
+                    for (int i = c.tm; i < nm; ++i) *w++ = M[i];
+                    for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                    for (int i = 0; i < c.tn; ++i) *w++ = N[i];
+                    for (int i = 0; i < nk; ++i) *w++ = K[i];
+                    for (int i = 0; i < nkb; ++i) *w++ = KB[i];
+                    for (int i = c.tn; i < nn; ++i) *w++ = N[i];
+                    for (int i = 0; i < nb; ++i) *w++ = Bt[i];
+                    lay_top += (size_t)(ra + rb);
+                }
+                for (int i = 0; i < rc; ++i) posC[lc[i]] = -1;
+            }
+        }
+        return TB_OK;
+    }
+
+    // leaf tensors (edge / unit / vertex values, slots of sliced leaves)
+    int leaf_pool() {
+        // ---- pool (leaf tensors)
+        leaf_pool_off.assign(nT, 0);
+        {
+            auto push_val = [&](double x, bool neg_inf, int cfg_bit = -1) { P.pool.push_back(Plan::encode_value(vt, x, neg_inf, cfg_bit)); };
+            const bool int_values = (vt == TB_VALUE_I32 || vt == TB_VALUE_I16X2 || vt == TB_VALUE_SIZE_CONFIG);
+            P.pool.reserve(8 + 2 * (size_t)nL + 4);
+            push_val(0, false); push_val(0, false); push_val(0, false); push_val(0, true);  // edge
+            push_val(0, false);                                                            // unit
+            push_val(0, false); push_val(0, false); push_val(0, false);                    // pad
+            double sum_abs = 0;
+            for (int i = 0; i < nT; ++i) {
+                if (!leaf[i]) continue;
+                const int vtx = i < nL ? leaf_vertex[i] : -1;
+                if (i < nL && leaf_fa[i] >= 0) {
+                    // sliced leaf: a 2-element slot of its own.  vertex [0, w][x] -> scalar; edge with one end fixed -> row x of
+                    // the (symmetric) edge tensor, (0, 0) or (0, -inf); both ends fixed -> scalar, -inf iff both are 1
+                    double w = 0;
+                    if (vtx >= 0) {
+                        w = weight_of(vtx);
+                        if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
+                        if (int_values) {
+                            if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
+                            sum_abs += std::fabs(w);
+                            if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
+                        }
+                    }
+                    Plan::PoolPatch pp{};
+                    pp.vtx = vtx;
+                    pp.off = (int32_t)P.pool.size();
+                    pp.kind = (uint8_t)(vtx >= 0 ? 0 : (leaf_fb[i] < 0 ? 1 : 2));
+                    pp.fa = leaf_fa[i];
+                    pp.fb = leaf_fb[i];
+                    pp.w = w;
+                    P.patches.push_back(pp);
+                    leaf_pool_off[i] = pp.off;
+                    push_val(0, false);
+                    push_val(0, false);
+                } else if (vtx < 0 && lab_n[i] == 0) {
+                    leaf_pool_off[i] = POOL_UNIT;
+                } else if (vtx < 0) {
+                    leaf_pool_off[i] = POOL_EDGE;
+                } else {
+                    double w = weight_of(vtx);
+                    if (std::isnan(w)) return fail(TB_ERR_BAD_ARGUMENT, "NaN weight");
+                    if (int_values) {
+                        if (w != std::floor(w)) return fail(TB_ERR_UNSUPPORTED, "integer value types need integer weights");
+                        sum_abs += std::fabs(w);
+                        if (sum_abs >= (double)(1 << 29)) return fail(TB_ERR_UNSUPPORTED, "sum of |weights| >= 2^29 overflows the i32 sentinel scheme");
+                    }
+                    leaf_pool_off[i] = (int32_t)P.pool.size();
+                    push_val(0, false);
+                    push_val(w, false, vtx);  // size+configuration: choosing the vertex also sets its bit of the mask
+                }
+            }
+            while (P.pool.size() % 4) P.pool.push_back(0);
+            P.n_fixed = net.n_fixed;
+            if (net.n_fixed > 0) P.assign(net.fixed_values);
+            if (P.pool.size() > 65535) P.flags |= TB_PLAN_NO_FUSED_SUBTREES;  // fused steps address the pool with 16 bits
+        }
+        return TB_OK;
+    }
+
+    // fused subtree / generic / tiled GEMM per node, dependency levels of the big steps
+    int kinds_and_levels() {
+        // ---- kinds: fused subtrees / generic / gemm
+        fus.assign(nT, 0);
+        peak.assign(nT, 0);
+        const bool allow_fused = !(P.flags & TB_PLAN_NO_FUSED_SUBTREES);
+        for (int t : topo) {
+            const int A = lch[t], B = rch[t];
+            const NodeCls& c = cls[t];
+            int tc = rank_of(t) + c.nk + c.nka + c.nkb;
+            bool ok = allow_fused && rank_of(t) <= FUSED_MAX_RANK && rank_of(A) <= FUSED_MAX_RANK &&
+                      rank_of(B) <= FUSED_MAX_RANK && tc <= FUSED_MAX_TC && (leaf[A] || fus[A]) && (leaf[B] || fus[B]);
+            int64_t pA = leaf[A] ? 0 : peak[A], sA = leaf[A] ? 0 : size_of(A);
+            int64_t pB = leaf[B] ? 0 : peak[B], sB = leaf[B] ? 0 : size_of(B);
+            int64_t pk = size_of(t) + (pA >= pB ? std::max(pA, sA + pB) : std::max(pB, sB + pA));
+            peak[t] = pk;
+            fus[t] = ok && pk <= (wide ? FUSED_SMEM_ELEMS / 2 : FUSED_SMEM_ELEMS);  // 32 KB of values either way
+        }
+        P.loc.assign(nT, LOC_ARENA);
+        P.off.assign(nT, 0);
+        P.level.assign(nT, -1);
+        for (int i = 0; i < nT; ++i)
+            if (leaf[i]) {
+                P.loc[i] = LOC_POOL;
+                P.off[i] = leaf_pool_off[i];
+            }
+
+        // ---- levels
+        kind.assign(nT, -1);
+        n_fused_roots = 0;
+        n_big = 0;
+        for (int t : topo) {
+            if (fus[t]) {
+                kind[t] = KIND_FUSED;
+                bool is_sub_root = (t == root) || !fus[parent[t]];
+                P.level[t] = is_sub_root ? 0 : -1;
+                n_fused_roots += is_sub_root;
+            } else {
+                int lv = 1;
+                for (int c : {lch[t], rch[t]})
+                    if (!leaf[c]) lv = std::max(lv, P.level[c] + 1);
+                P.level[t] = lv;
+                const NodeCls& c = cls[t];
+                bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= MT_LOG && c.nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && c.nk >= 1 &&
+                            c.nka == 0 && c.nkb == 0 && !leaf[lch[t]] && !leaf[rch[t]];
+                kind[t] = gemm ? KIND_GEMM : KIND_GENERIC;
+                P.n_levels = std::max(P.n_levels, lv);
+                ++n_big;
+            }
+        }
+        return TB_OK;
+    }
+
+    // arena offsets, safe for the dataflow executor (a node reuses only the dead interior of its own subtree)
+    int arena() {
+        // ---- arena allocation, safe for the dataflow executor: the only ordering between steps is operand -> consumer, so a
+        //      node's output may overlap ONLY tensors that are dead once the node's operands are complete: the interior of its
+        //      own subtree (everything below its two operands).  Sibling subtrees run concurrently and never share memory;
+        //      fused-subtree roots (level 0, all produced by one launch) get fresh blocks.  Post-order walk; every tensor hands
+        //      the free blocks of its subtree up to its consumer.
+        {
+            typedef std::vector<std::pair<int64_t, int64_t>> Blocks;  // (offset, size), sorted by offset, coalesced
+            std::vector<Blocks> after(nT);  // free blocks inside the subtree of t once t is complete (t's own block excluded)
+            const bool keep = (P.flags & TB_PLAN_KEEP_INTERMEDIATES) != 0;
+            int64_t top = 0;
+            auto insert_block = [](Blocks& bl, int64_t o, int64_t sz) {
+                auto it = std::lower_bound(bl.begin(), bl.end(), std::make_pair(o, (int64_t)0));
+                it = bl.insert(it, {o, sz});
+                auto nx = it + 1;
+                if (nx != bl.end() && it->first + it->second == nx->first) {
+                    it->second += nx->second;
+                    bl.erase(nx);
+                }
+                if (it != bl.begin()) {
+                    auto pv = it - 1;
+                    if (pv->first + pv->second == it->first) {
+                        pv->second += it->second;
+                        bl.erase(it);
+                    }
+                }
+            };
+            for (int t : topo) {
+                if (P.level[t] < 0) continue;  // interior of a fused subtree: shared memory
+                const int64_t need = align_up(size_of(t), 64);
+                Blocks pool;
+                if (!keep && kind[t] != KIND_FUSED)
+                    for (int c : {lch[t], rch[t]})
+                        if (!leaf[c] && P.level[c] >= 0) {
+                            for (const auto& bk : after[c]) insert_block(pool, bk.first, bk.second);
+                            Blocks().swap(after[c]);
+                        }
+                // best fit inside the subtree's dead interior, else a fresh block at the top of the arena
+                int best = -1;
+                for (int i = 0; i < (int)pool.size(); ++i)
+                    if (pool[(size_t)i].second >= need && (best < 0 || pool[(size_t)i].second < pool[(size_t)best].second)) best = i;
+                if (best >= 0) {
+                    P.off[t] = pool[(size_t)best].first;
+                    pool[(size_t)best].first += need;
+                    pool[(size_t)best].second -= need;
+                    if (pool[(size_t)best].second == 0) pool.erase(pool.begin() + best);
+                } else {
+                    P.off[t] = top;
+                    top += need;
+                }
+                if (!keep && kind[t] != KIND_FUSED)
+                    for (int c : {lch[t], rch[t]})
+                        if (!leaf[c] && P.level[c] >= 0) insert_block(pool, P.off[c], align_up(size_of(c), 64));
+                after[t].swap(pool);
+            }
+            P.arena_elems = top;
+            P.root_off = P.off[root];
+        }
+        return TB_OK;
+    }
+
+    // descriptors of the fused subtrees (shared-memory stack allocation inside a subtree)
+    int emit_fused() {
+        // ---- emit steps
+        posA.assign(NLAB, NO_BIT);
+        posB.assign(NLAB, NO_BIT);
+        posCc.assign(NLAB, NO_BIT);
+        ops_f = ops_g = ops_m = bytes = bytes_m = sc = 0;
+        for (int t = 0; t < nT0; ++t) sc = std::max(sc, (double)((int)lab_n[t] - (int)kept[t]));
+        if (!temporary) P.recs.reserve(topo.size());
+        P.sub_steps.reserve(topo.size() - n_big);
+        P.subtrees.reserve(n_fused_roots);
+        P.big_steps.reserve(n_big);
+
+        // fused subtrees: post-order with a "reserve C, then children above it" shared-memory stack
+        struct Frame {
+            int x;
+            int64_t base;
+            bool is_root;
+            int stage;
+            int64_t cur;
+        };
+        std::vector<Frame> stack;
+        for (int t : topo) {
+            if (kind[t] != KIND_FUSED || P.level[t] != 0) continue;
+            SubTree st{};
+            st.first_step = (uint32_t)P.sub_steps.size();
+            st.out_off = P.off[t];
+            int64_t max_top = 0;
+            stack.clear();
+            stack.push_back({t, 0, true, 0, 0});
+            while (!stack.empty()) {
+                Frame& f = stack.back();
+                const int x = f.x, A = lch[x], B = rch[x];
+                int64_t pA = leaf[A] ? 0 : peak[A], pB = leaf[B] ? 0 : peak[B];
+                const int first = pA >= pB ? A : B, second = pA >= pB ? B : A;
+                if (f.stage == 0) {
+                    int64_t above = f.base;
+                    if (!f.is_root) {
+                        P.loc[x] = LOC_SMEM;
+                        P.off[x] = f.base;
+                        above = f.base + size_of(x);
+                    }
+                    max_top = std::max(max_top, above);
+                    f.cur = above;
+                    f.stage = 1;
+                    if (!leaf[first]) {
+                        Frame nf{first, f.cur, false, 0, 0};
+                        f.cur += size_of(first);
+                        max_top = std::max(max_top, f.cur);
+                        stack.push_back(nf);
+                        continue;
+                    }
+                }
+                if (f.stage == 1) {
+                    f.stage = 2;
+                    if (!leaf[second]) {
+                        Frame nf{second, f.cur, false, 0, 0};
+                        f.cur += size_of(second);
+                        max_top = std::max(max_top, f.cur);
+                        stack.push_back(nf);
+                        continue;
+                    }
+                }
+                const NodeCls& c = cls[x];
+                const bool is_root = f.is_root;
+                SubStep s{};
+                s.a_off = (uint16_t)P.off[A];
+                s.b_off = (uint16_t)P.off[B];
+                s.c_off = is_root ? 0 : (uint16_t)P.off[x];
+                s.a_loc = (uint8_t)P.loc[A];
+                s.b_loc = (uint8_t)P.loc[B];
+                s.c_loc = is_root ? LOC_ARENA : LOC_SMEM;
+                s.rc = (uint8_t)rank_of(x);
+                s.nk = c.nk;
+                s.nka = c.nka;
+                s.nkb = c.nkb;
+                s.sa = c.tm;
+                s.sb = c.tn;
+                s.pad = c.kfirst;  // reduction bit 0 is address bit 0 of both operands, the other K bits start at sa+1 / sb+1
+                std::memset(s.a_shift, NO_BIT, sizeof s.a_shift + sizeof s.b_shift);
+                {
+                    // position of each output label in A / B: stamp the (short) output, then walk A and B once
+                    const int32_t* lx = layp(x);
+                    const int rx = rank_of(x);
+                    for (int i = 0; i < rx; ++i) posCc[lx[i]] = (uint8_t)i;
+                    const int32_t* la_ = layp(A);
+                    for (int i = 0, ra_ = rank_of(A); i < ra_; ++i)
+                        if (posCc[la_[i]] != NO_BIT) s.a_shift[posCc[la_[i]]] = (uint8_t)i;
+                    const int32_t* lb_ = layp(B);
+                    for (int i = 0, rb_ = rank_of(B); i < rb_; ++i)
+                        if (posCc[lb_[i]] != NO_BIT) s.b_shift[posCc[lb_[i]]] = (uint8_t)i;
+                    for (int i = 0; i < rx; ++i) posCc[lx[i]] = NO_BIT;
+                }
+                P.sub_steps.push_back(s);
+                if (!temporary) P.recs.push_back(rec_of(x, KIND_FUSED, 0));
+                account(x, KIND_FUSED);
+                stack.pop_back();
+            }
+            st.n_steps = (uint32_t)P.sub_steps.size() - st.first_step;
+            st.smem_elems = (uint32_t)max_top;
+            P.subtrees.push_back(st);
+        }
+        return TB_OK;
+    }
+
+    // descriptors of the generic and GEMM steps, ordered by level, with their dependencies
+    int emit_big() {
+        // big steps by level
+        {
+            std::vector<int> order;
+            order.reserve(n_big);
+            for (int t : topo)
+                if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) order.push_back(t);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.level[x] < P.level[y]; });
+            P.big_level_begin.assign(P.n_levels + 2, 0);
+            std::vector<int32_t> big_index(nT, -1);  // node -> its position in big_steps (dependencies of the dataflow executor)
+            P.big_dep_a.reserve(n_big);
+            P.big_dep_b.reserve(n_big);
+            for (int t : order) {
+                const NodeCls& c = cls[t];
+                const int32_t* cd = cls_data.data() + c.off;
+                const int32_t *cM = cd, *cN = cd + c.nm, *cBt = cd + c.nm + c.nn;
+                const int A = lch[t], B = rch[t];
+                BigStep s{};
+                s.a_off = P.off[A];
+                s.b_off = P.off[B];
+                s.c_off = P.off[t];
+                s.a_loc = (uint8_t)P.loc[A];
+                s.b_loc = (uint8_t)P.loc[B];
+                s.kind = (uint8_t)kind[t];
+                s.rc = (uint8_t)rank_of(t);
+                s.nk = c.nk;
+                s.nka = c.nka;
+                s.nkb = c.nkb;
+                s.sa = c.tm;
+                s.sb = c.tn;
+                s.tm = c.tm;
+                s.tn = c.tn;
+                std::memset(s.a_shift, NO_BIT, 32);
+                std::memset(s.b_shift, NO_BIT, 32);
+                std::memset(s.c_shift, NO_BIT, 32);
+                if (kind[t] == KIND_GENERIC) {
+                    set_pos(posA, A, true);
+                    set_pos(posB, B, true);
+                    const int32_t* lt = layp(t);
+                    for (int i = 0; i < rank_of(t); ++i) {
+                        s.a_shift[i] = posA[lt[i]];
+                        s.b_shift[i] = posB[lt[i]];
+                        s.c_shift[i] = (uint8_t)i;
+                    }
+                    set_pos(posA, A, false);
+                    set_pos(posB, B, false);
+                    s.store_mode = c.kfirst;  // generic steps reuse this byte: K0-first operand layouts
+                    int ks, po;
+                    generic_split(s.rc, s.nk + s.nka + s.nkb, ks, po);
+                    if (ks == 0 && s.rc >= 10 && !wide) {  // streaming node: 4 consecutive outputs per thread and iteration
+                        s.vec4 = 1;
+                        po = s.rc >= 14 ? 12 : 10;  // 4096 outputs per CTA (4 iterations) amortise the per-CTA set-up
+                    }
+                    s.ks = (uint8_t)ks;
+                    s.po = (uint8_t)po;
+                    s.n_tiles = 1u << (s.rc - po);
+                } else {
+                    set_pos(posCc, t, true);
+                    int q = 0;
+                    for (int i = 0; i < c.tm; ++i) s.c_shift[q++] = posCc[cM[i]];
+                    for (int i = 0; i < c.tn; ++i) s.c_shift[q++] = posCc[cN[i]];
+                    for (int i = c.tm; i < c.nm; ++i) s.c_shift[q++] = posCc[cM[i]];
+                    for (int i = c.tn; i < c.nn; ++i) s.c_shift[q++] = posCc[cN[i]];
+                    for (int i = 0; i < c.nb; ++i) s.c_shift[q++] = posCc[cBt[i]];
+                    set_pos(posCc, t, false);
+                    s.n_mhi = (uint8_t)(c.nm - c.tm);
+                    s.n_nhi = (uint8_t)(c.nn - c.tn);
+                    s.ng = (uint8_t)(s.rc - c.tm - c.tn);
+                    int tps_log = (c.tm - MT_LOG) + (c.tn - 3);  // threads per sub-tile
+                    int s_log = 8 - tps_log;                     // sub-tiles per CTA (256 threads)
+                    int64_t per_k = ((int64_t)1 << s_log) * (((int64_t)1 << c.tm) + ((int64_t)1 << c.tn));
+                    int kc = 0;
+                    while (kc + 1 <= s.nk && (per_k << (kc + 1)) <= STAGE_ELEMS) ++kc;
+                    s.kc = (uint8_t)kc;
+                    int64_t groups = (int64_t)1 << s.ng;
+                    int64_t S = (int64_t)1 << s_log;
+                    s.n_tiles = (uint32_t)((groups + S - 1) / S);
+                    s.store_mode = STORE_SCALAR;
+                    if (s.c_shift[0] == 0 && s.c_shift[1] == 1) s.store_mode = STORE_VEC_M;
+                    else if (s.c_shift[c.tm] == 0 && s.c_shift[c.tm + 1] == 1) s.store_mode = STORE_VEC_N;
+                    // staged epilogue tables (k_gemm2): the tile is written in 4 rounds (the top m tile bit and the top n
+                    // tile bit select the round); inside a round the (tm-1)+(tn-1) remaining tile bits are enumerated in
+                    // C-address order.  a_shift[i] = position of the i-th such bit in the shared-memory staging index
+                    // ([m bits 0..tm-2 | n bits 0..tn-2]), b_shift[i] = its C shift.  a_shift[30/31] = C shift of the top
+                    // m / n tile bit, b_shift[31] = 1 if the two lowest bits are C bits 0,1 (128-bit stores).
+                    // packed int16 only: a consumer thread holds the m tile bits {0, mp, tm-1}; mp (a_shift[29], default
+                    // 1) is chosen so that the m labels on C bits 0..2 are thread-local, and b_shift[29] = 1 swaps the
+                    // roles of m0 and m_mp (the thread pairs outputs along m_mp).  The tables use LOGICAL m positions:
+                    // [first local bit, second local bit, the other in-round m bits in ascending order].
+                    {
+                        const int nbr = c.tm + c.tn - 2;
+                        int ent_cs[16], ent_sp[16], ne = 0;
+                        auto build = [&](int mp, int mswap) -> int {
+                            int lm[8], nl = 0;  // logical position of the in-round m bit q
+                            lm[mswap ? mp : 0] = nl++;
+                            if (c.tm >= 3) lm[mswap ? 0 : mp] = nl++;
+                            for (int q = 1; q < c.tm - 1; ++q)
+                                if (q != mp) lm[q] = nl++;
+                            ne = 0;
+                            for (int i = 0; i < c.tm - 1; ++i) { ent_cs[ne] = s.c_shift[i]; ent_sp[ne++] = lm[i]; }
+                            for (int i = 0; i < c.tn - 1; ++i) { ent_cs[ne] = s.c_shift[c.tm + i]; ent_sp[ne++] = (c.tm - 1) + i; }
+                            for (int i = 1; i < ne; ++i) {
+                                int cs = ent_cs[i], sp = ent_sp[i], j = i - 1;
+                                while (j >= 0 && ent_cs[j] > cs) { ent_cs[j + 1] = ent_cs[j]; ent_sp[j + 1] = ent_sp[j]; --j; }
+                                ent_cs[j + 1] = cs; ent_sp[j + 1] = sp;
+                            }
+                            const bool evec = half ? (ent_cs[0] == 0 && ent_cs[1] == 1 && ent_cs[2] == 2) : (ent_cs[0] == 0 && ent_cs[1] == 1);
+                            s.b_shift[31] = evec ? 1 : 0;
+                            // ecase != 0: the elements of one 16-byte output vector are also contiguous in the staging
+                            // buffer (one LDS.128 instead of 4 / 8 scalar loads).  int32: 1 = C bits 0,1 are m0,m1.
+                            // packed int16: the thread holds (u, v) x (n0, n1) of a round (u, v = its local m bits), so it
+                            // can write any of the orders C bits (0,1,2) = 1: (u,v,m2)  2: (u,v,n0)  3: (u,n0,v)
+                            // 4: (u,n0,n1) as 16-byte vectors; for 2..4 the staging index is [the three C bits | the fourth
+                            // thread-local bit | m2.. | n2..] and the table holds positions in THAT layout.
+                            int ecase = 0;
+                            if (half) {
+                                const int n0 = c.tm - 1, n1 = c.tm;  // layout-1 staging positions of the n bits 0,1
+                                if (evec && ent_sp[0] == 0) {
+                                    if (ent_sp[1] == 1 && ent_sp[2] == 2) ecase = 1;
+                                    else if (ent_sp[1] == 1 && ent_sp[2] == n0) ecase = 2;
+                                    else if (ent_sp[1] == n0 && ent_sp[2] == 1) ecase = 3;
+                                    else if (ent_sp[1] == n0 && ent_sp[2] == n1) ecase = 4;
+                                }
+                                if (ecase >= 2) {
+                                    static const int low[5][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2}};
+                                    for (int i = 0; i < ne; ++i) {  // {u, v, n0, n1} -> low[ecase], m q>=2 -> q+2, n unchanged
+                                        const int sp = ent_sp[i];
+                                        if (sp == 0) ent_sp[i] = low[ecase][0];
+                                        else if (sp == 1) ent_sp[i] = low[ecase][1];
+                                        else if (sp == n0) ent_sp[i] = low[ecase][2];
+                                        else if (sp == n1) ent_sp[i] = low[ecase][3];
+                                        else if (sp < n0) ent_sp[i] = sp + 2;
+                                    }
+                                }
+                            } else {
+                                ecase = (ent_sp[0] == 0 && ent_sp[1] == 1) ? 1 : 0;
+                            }
+                            return ecase;
+                        };
+                        int mp = 1, mswap = 0;
+                        if (half && c.tm >= 4) {
+                            int q_by_cs[3] = {-1, -1, -1};
+                            for (int q = 0; q < c.tm - 1; ++q)
+                                if (s.c_shift[q] < 3) q_by_cs[s.c_shift[q]] = q;
+                            const int q0 = q_by_cs[0];
+                            if (q0 > 0) {
+                                mp = q0;
+                                mswap = 1;
+                            } else if (q0 == 0) {
+                                const int q1 = q_by_cs[1] > 0 ? q_by_cs[1] : q_by_cs[2];
+                                if (q1 > 1) mp = q1;
+                            }
+                        }
+                        int ecase = build(mp, mswap);
+                        if (ecase == 0 && (mp != 1 || mswap)) {
+                            mp = 1;
+                            mswap = 0;
+                            ecase = build(mp, mswap);
+                        }
+                        s.a_shift[29] = (uint8_t)mp;
+                        s.b_shift[29] = (uint8_t)mswap;
+                        s.a_shift[30] = s.c_shift[c.tm - 1];
+                        s.a_shift[31] = s.c_shift[c.tm + c.tn - 1];
+                        s.b_shift[30] = (uint8_t)ecase;
+                        for (int i = 0; i < nbr; ++i) { s.a_shift[i] = (uint8_t)ent_sp[i]; s.b_shift[i] = (uint8_t)ent_cs[i]; }
+                    }
+                    // lanes of a warp should write neighbouring addresses: put the tile dimension that owns C's bit 2
+                    // (bit 0 if stores are scalar) on the low lane bits
+                    {
+                        const int probe = s.store_mode == STORE_SCALAR ? 0 : 2;
+                        bool n_owns = false;
+                        for (int i = 0; i < c.tn; ++i)
+                            if (s.c_shift[c.tm + i] == probe) n_owns = true;
+                        s.lane_n_first = n_owns ? 1 : 0;
+                    }
+                }
+                big_index[t] = (int32_t)P.big_steps.size();
+                P.big_log2_ops.push_back((float)(rank_of(t) + c.nk + c.nka + c.nkb));
+                P.big_bytes.push_back((double)Plan::elem_size_of(vt) * (std::ldexp(1.0, rank_of(A)) + std::ldexp(1.0, rank_of(B)) + std::ldexp(1.0, rank_of(t))));
+                P.big_dep_a.push_back(big_index[A]);  // -1 for leaves and fused subtrees
+                P.big_dep_b.push_back(big_index[B]);
+                P.big_steps.push_back(s);
+                if (!temporary) P.recs.push_back(rec_of(t, kind[t], P.level[t]));
+                account(t, kind[t]);
+            }
+            int idx = 0;
+            for (int lv = 1; lv <= P.n_levels + 1; ++lv) {
+                while (idx < (int)order.size() && P.level[order[idx]] < lv) ++idx;
+                P.big_level_begin[lv] = idx;
+            }
+            P.big_level_begin[0] = 0;
+        }
+        return TB_OK;
+    }
+
+    // statistics of the compiled plan (tb_plan_info)
+    int finish_stats() {
+        tb_plan_stats& S = P.stats;
+        S.sc = sc;
+        S.ops = ops_f + ops_g + ops_m;
+        S.tc = S.ops > 0 ? std::log2(S.ops) : 0;
+        S.algo_bytes = bytes;
+        S.arena_elems = P.arena_elems;
+        S.n_nodes = nN;
+        S.n_levels = P.n_levels;
+        S.n_fused_subtrees = (int)P.subtrees.size();
+        S.n_fused_steps = (int)P.sub_steps.size();
+        S.n_gemm_steps = 0;
+        S.n_generic_steps = 0;
+        for (auto& b : P.big_steps) (b.kind == KIND_GEMM ? S.n_gemm_steps : S.n_generic_steps)++;
+        S.value_type = vt;
+        S.root_rank = rank_of(root);
+        S.gemm_ops = ops_m;
+        S.fused_ops = ops_f;
+        S.generic_ops = ops_g;
+        S.gemm_bytes = bytes_m;
+        S.peak_memory_log2 = est_peak > 0 ? std::log2(est_peak) : 0;
+        S.all_memory_log2 = est_all > 0 ? std::log2(est_all) : 0;
+        return TB_OK;
+    }
+
+    int run() {
+#ifdef TB_PLAN_PROFILE
+        auto last_ = std::chrono::steady_clock::now();
+#endif
+        int rc;
+        if ((rc = load_network()) != TB_OK || finished) return rc;
+        PT(0, "validate")
+        if ((rc = value_type_and_positions()) != TB_OK || finished) return rc;
+        PT(1, "positions")
+        if ((rc = label_sets()) != TB_OK || finished) return rc;
+        PT(2, "labelsets")
+        if ((rc = reference_estimators()) != TB_OK || finished) return rc;
+        PT(11, "estimators")
+        if ((rc = split_k()) != TB_OK || finished) return rc;
+        PT(3, "splitk")
+        if ((rc = topological_order()) != TB_OK || finished) return rc;
+        PT(4, "topo")
+        if ((rc = layouts()) != TB_OK || finished) return rc;
+        PT(5, "layouts")
+        if ((rc = leaf_pool()) != TB_OK || finished) return rc;
+        PT(6, "pool")
+        if ((rc = kinds_and_levels()) != TB_OK || finished) return rc;
+        PT(7, "kinds")
+        if ((rc = arena()) != TB_OK || finished) return rc;
+        PT(8, "arena")
+        if ((rc = emit_fused()) != TB_OK || finished) return rc;
+        PT(9, "fused_emit")
+        if ((rc = emit_big()) != TB_OK || finished) return rc;
+        PT(10, "big_emit")
+        return finish_stats();
+    }
+};
+
+}  // namespace
+
+int compile_plan(const tb_network& net, uint32_t extra_flags, Plan& P, std::string& err) {
+    return PlanCompiler(net, extra_flags, P, err).run();
 }
 
 // Greedy choice of the labels to slice (tb_suggest_slices).  Works on the label sets of the given tree only:
