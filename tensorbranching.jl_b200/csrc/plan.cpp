@@ -145,7 +145,7 @@ struct PlanCompiler {
     std::vector<int32_t> stA, stB, stC;  // stamp arrays for O(1) membership
     int stamp = 0;
     std::vector<uint8_t> folded, kept;
-    std::vector<int32_t> topo;
+    std::vector<int32_t> post0, topo;  // internal nodes, children before parents: the given tree / after the split-K rewrite
     size_t lab_total = 0, lay_top = 0, cls_top = 0;
     std::vector<NodeCls> cls;
     std::vector<int32_t> cls_data;
@@ -374,25 +374,26 @@ struct PlanCompiler {
         // ---- leaf positions (DFS order) and subtree ranges
         lo.assign(nT0, 0);
         hi.assign(nT0, 0);
+        // No traversal: ids are topological (children < parent, checked by load_network), so subtree sizes come from one
+        // ascending sweep and the depth-first numbers (left operand first) from one descending sweep.  post0 = the
+        // internal nodes in depth-first post-order: node t is emitted after the internal nodes of both subtrees.
         {
-            std::vector<int32_t> stack;
-            stack.reserve(64);
-            stack.push_back(root);
-            int pos = 0;
-            while (!stack.empty()) {
-                int t = stack.back();
-                stack.pop_back();
-                if (leaf[t]) {
-                    lo[t] = hi[t] = pos++;
-                } else {
-                    stack.push_back(rch[t]);
-                    stack.push_back(lch[t]);
-                }
-            }
+            std::vector<int32_t> nint(nT0, 0), first(nT0, 0);  // internal nodes in the subtree; post-order index of its first one
+            for (int i = 0; i < nL; ++i) hi[i] = 1;              // hi holds the leaf COUNT of the subtree during the sweeps
             for (int t = nL; t < nT0; ++t) {
-                lo[t] = std::min(lo[lch[t]], lo[rch[t]]);
-                hi[t] = std::max(hi[lch[t]], hi[rch[t]]);
+                hi[t] = hi[lch[t]] + hi[rch[t]];
+                nint[t] = nint[lch[t]] + nint[rch[t]] + 1;
             }
+            post0.assign(nN, 0);
+            for (int t = nT0 - 1; t >= nL; --t) {
+                const int l = lch[t], r = rch[t];
+                lo[l] = lo[t];
+                lo[r] = lo[t] + hi[l];
+                first[l] = first[t];
+                first[r] = first[t] + nint[l];
+                post0[first[t] + nint[t] - 1] = t;
+            }
+            for (int t = 0; t < nT0; ++t) hi[t] = lo[t] + hi[t] - 1;
         }
         minpos.assign(NLAB, std::numeric_limits<int32_t>::max());
         maxpos.assign(NLAB, -1);
@@ -424,33 +425,39 @@ struct PlanCompiler {
             int32_t u[80];
             int nu = 0;
             {
+                // union of two sorted sets; the comparison results feed the cursors, not branches
                 const int32_t *a = labp(A), *b = labp(B);
                 int i = 0, j = 0;
-                while (i < na || j < nb) {
-                    if (j >= nb || (i < na && a[i] < b[j])) u[nu++] = a[i++];
-                    else if (i >= na || b[j] < a[i]) u[nu++] = b[j++];
-                    else {
-                        u[nu++] = a[i];
-                        ++i;
-                        ++j;
-                    }
+                while (i < na && j < nb) {
+                    const int32_t x = a[i], y = b[j];
+                    u[nu++] = x < y ? x : y;
+                    i += x <= y;
+                    j += y <= x;
                 }
+                while (i < na) u[nu++] = a[i++];
+                while (j < nb) u[nu++] = b[j++];
             }
             if (nu > 62) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 62 labels");
-            lab_off[t] = (int32_t)lab_data.size();
+            const size_t at = lab_data.size();
+            lab_off[t] = (int32_t)at;
+            lab_data.resize(at + (size_t)nu);
             int no = 0;
-            for (int q = 0; q < nu; ++q) {
-                int32_t l = u[q];
-                bool closed = !is_open[l] && minpos[l] >= lo[t] && maxpos[l] <= hi[t];
-                if (!closed) {
-                    lab_data.push_back(l);
-                    ++no;
+            {
+                // a label is reduced here iff it is not open and all its leaves lie inside this subtree
+                int32_t* w = lab_data.data() + at;
+                const int32_t lo_t = lo[t], hi_t = hi[t];
+                for (int q = 0; q < nu; ++q) {
+                    const int32_t l = u[q];
+                    const bool closed = !is_open[l] & (minpos[l] >= lo_t) & (maxpos[l] <= hi_t);
+                    w[no] = l;
+                    no += !closed;
                 }
             }
+            lab_data.resize(at + (size_t)no);
             if (no > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(no) + " > 31");
             if (nu - no > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
             lab_n[t] = (uint8_t)no;
-            est_ops += std::ldexp(1.0, nu);
+            est_ops += (double)(1ull << nu);
             est_sc = std::max(est_sc, no);
         }
         if (estimate_only) {
@@ -640,23 +647,10 @@ struct PlanCompiler {
         // ---- topological order of internal nodes (children before parents)
         topo.clear();
         topo.reserve(nT);
-        {
-            std::vector<int32_t> stack;
-            stack.reserve(128);
-            stack.push_back(root);
-            // iterative post-order: negative id = "emit"
-            while (!stack.empty()) {
-                int t = stack.back();
-                stack.pop_back();
-                if (t < 0) {
-                    topo.push_back(~t);
-                    continue;
-                }
-                if (leaf[t]) continue;
-                stack.push_back(~t);
-                stack.push_back(rch[t]);
-                stack.push_back(lch[t]);
-            }
+        // the split-K rewrite turns node t into t = max(u), u = contract(A, B): u directly precedes t
+        for (int t : post0) {
+            if (unary[t]) topo.push_back(lch[t]);
+            topo.push_back(t);
         }
         return TB_OK;
     }
@@ -685,34 +679,97 @@ struct PlanCompiler {
                 for (int i = 0; i < net.n_open; ++i) P.lay_data[lay_top++] = net.open_labels[i];
             }
             std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
+            // posC[l] = (stamp of the node being processed) * 64 + position of l in the node's output layout: a stale
+            // stamp means "not an output label", so nothing has to be reset between nodes
             std::vector<int32_t> posC(NLAB, -1);
             std::vector<int32_t> batA(NLAB, -1), batB(NLAB, -1);  // stamps: label is a batch label inside child A / B
             std::vector<int32_t> secA(NLAB, -1), secB(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
             const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
             for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
                 const int t = *it;
-                if (P.lay_n[t] > 0 && !leaf[lch[t]] && !leaf[rch[t]]) {
-                    // orientation: the operand that owns the label at C bit 0 becomes the M side (contract(A,B) == contract(B,A)),
-                    // so that the low output bits are m tile bits 0,1,.. and the epilogue can move whole 16-byte vectors
-                    const int32_t l0 = P.lay_data[P.lay_off[t]];
-                    bool inL = false, inR = false;
-                    for (int q = 0; q < lab_n[lch[t]]; ++q) inL = inL || labp(lch[t])[q] == l0;
-                    for (int q = 0; q < lab_n[rch[t]]; ++q) inR = inR || labp(rch[t])[q] == l0;
-                    if (inR && !inL) {
-                        const bool ok = true;
-                        if (ok) std::swap(lch[t], rch[t]);
+                const int sN = ++stamp;  // stamp of this node (stA, stB, posC, batA, batB)
+                const int32_t *inA = stA.data(), *inB = stB.data();  // inA[l] == sN: label l belongs to operand A
+                {
+                    const int L = lch[t], R = rch[t];
+                    const int32_t *pl = labp(L), *pr = labp(R);
+                    for (int q = 0, n = lab_n[L]; q < n; ++q) stA[pl[q]] = sN;
+                    for (int q = 0, n = lab_n[R]; q < n; ++q) stB[pr[q]] = sN;
+                    if (P.lay_n[t] > 0 && !leaf[L] && !leaf[R]) {
+                        // orientation: the operand that owns the label at C bit 0 becomes the M side (contract(A,B) == contract(B,A)),
+                        // so that the low output bits are m tile bits 0,1,.. and the epilogue can move whole 16-byte vectors
+                        const int32_t l0 = P.lay_data[P.lay_off[t]];
+                        if (stB[l0] == sN && stA[l0] != sN) {
+                            std::swap(lch[t], rch[t]);
+                            std::swap(inA, inB);
+                        }
                     }
                 }
                 const int A = lch[t], B = rch[t];
-                const int sN = ++stamp;  // stamp of this node (stA, stB, batA, batB)
                 const int32_t* lc = P.lay_data.data() + P.lay_off[t];
                 const int rc = P.lay_n[t];
-                for (int i = 0; i < rc; ++i) posC[lc[i]] = i;
-                for (int q = 0; q < lab_n[A]; ++q) stA[labp(A)[q]] = sN;
-                for (int q = 0; q < lab_n[B]; ++q) stB[labp(B)[q]] = sN;
+                for (int i = 0; i < rc; ++i) posC[lc[i]] = sN * 64 + i;
+                auto in_c = [&](int32_t l) { return (posC[l] >> 6) == sN; };
+                auto pos_c = [&](int32_t l) { return posC[l] & 63; };
                 // nodes whose tensors are all tiny end up inside fused subtrees (shared memory): label order is
                 // irrelevant there, so skip the ordering analysis (90 % of all nodes)
                 const bool tiny = rc <= 6 && lab_n[A] <= 6 && lab_n[B] <= 6;
+                if (tiny && !scramble) {
+                    // Fast path (no sorting, no data-dependent branches).  A tiny node is never a GEMM step and all its
+                    // M / N labels are tile labels:  A = [M | K | KA | Bt],  B = [N | K | KB | Bt],  each class in label
+                    // order.  One pass over B classifies its labels and yields every class size (every output label
+                    // belongs to A or B, so nm = rc - nn - nb); A and B are then written straight into place.
+                    static_assert(GEMM_TILE_MAX >= 6, "tiny nodes keep all M / N labels inside the tile");
+                    const int32_t *pa = labp(A), *pb = labp(B);
+                    const int ra = lab_n[A], rb = lab_n[B];
+                    uint8_t kb[8];               // class of B's q-th label: 0 KB, 1 N, 2 K, 3 Bt
+                    int cnt[4] = {0, 0, 0, 0};
+                    for (int q = 0; q < rb; ++q) {
+                        const int32_t l = pb[q];
+                        const int k = ((inA[l] == sN) << 1) | (int)in_c(l);
+                        kb[q] = (uint8_t)k;
+                        ++cnt[k];
+                    }
+                    const int nkb = cnt[0], nn = cnt[1], nk = cnt[2], nb = cnt[3];
+                    const int nm = rc - nn - nb, nka = ra - nm - nk - nb;
+                    NodeCls& c = cls[t];
+                    c.off = 0;  // the label classes of a tiny node are never read back (only GEMM steps do)
+                    c.nm = (uint8_t)nm;
+                    c.nn = (uint8_t)nn;
+                    c.nb = (uint8_t)nb;
+                    c.nk = (uint8_t)nk;
+                    c.nka = (uint8_t)nka;
+                    c.nkb = (uint8_t)nkb;
+                    c.tm = (uint8_t)nm;
+                    c.tn = (uint8_t)nn;
+                    c.kfirst = 0;
+                    P.lay_off[A] = (int32_t)lay_top;
+                    P.lay_n[A] = (uint8_t)ra;
+                    P.lay_off[B] = (int32_t)(lay_top + ra);
+                    P.lay_n[B] = (uint8_t)rb;
+                    int32_t* wa = P.lay_data.data() + lay_top;
+                    int32_t* wb = wa + ra;
+                    int32_t sink;
+                    // write cursors by class (0 KA, 1 M, 2 K, 3 Bt) inside A, and of the shared classes inside B
+                    int32_t* ca[4] = {wa + nm + nk, wa, wa + nm, wa + nm + nk + nka};
+                    int32_t* cs[4] = {&sink, &sink, wb + nn, wb + nn + nk + nkb};
+                    const int step[4] = {0, 0, 1, 1};
+                    for (int q = 0; q < ra; ++q) {
+                        const int32_t l = pa[q];
+                        const int k = ((inB[l] == sN) << 1) | (int)in_c(l);
+                        *ca[k]++ = l;
+                        *cs[k] = l;
+                        cs[k] += step[k];
+                    }
+                    int32_t* cbw[4] = {wb + nn + nk, wb, &sink, &sink};  // KB, N; shared labels were written from A
+                    const int stepb[4] = {1, 1, 0, 0};
+                    for (int q = 0; q < rb; ++q) {
+                        const int k = kb[q];
+                        *cbw[k] = pb[q];
+                        cbw[k] += stepb[k];
+                    }
+                    lay_top += (size_t)(ra + rb);
+                    continue;
+                }
                 // batch labels of the children (labels shared by a child's own operands)
                 for (int side = 0; side < 2 && !tiny; ++side) {
                     const int ch = side ? B : A;
@@ -730,16 +787,21 @@ struct PlanCompiler {
                 }
                 int32_t M[40], N[40], Bt[40], K[40], KA[40], KB[40];
                 int nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0;
+                // output labels in the order of their positions in C (every output label belongs to A or B) ...
+                for (int i = 0; i < rc; ++i) {
+                    const int32_t l = lc[i];
+                    if (inA[l] != sN) N[nn++] = l;
+                    else if (inB[l] != sN) M[nm++] = l;
+                    else Bt[nb++] = l;
+                }
+                // ... reduced labels in label order
                 for (int q = 0; q < lab_n[A]; ++q) {
-                    int32_t l = labp(A)[q];
-                    bool inB = stB[l] == sN, inC = posC[l] >= 0;
-                    if (inB) (inC ? Bt[nb++] : K[nk++]) = l;
-                    else (inC ? M[nm++] : KA[nka++]) = l;
+                    const int32_t l = labp(A)[q];
+                    if (!in_c(l)) (inB[l] == sN ? K[nk++] : KA[nka++]) = l;
                 }
                 for (int q = 0; q < lab_n[B]; ++q) {
-                    int32_t l = labp(B)[q];
-                    if (stA[l] == sN) continue;
-                    (posC[l] >= 0 ? N[nn++] : KB[nkb++]) = l;
+                    const int32_t l = labp(B)[q];
+                    if (!in_c(l) && inA[l] != sN) KB[nkb++] = l;
                 }
                 // M / N: group the labels by their class inside the producing child so that the low address bits of
                 // the operand form a run of the child's own tile labels (coalesced stores in the child): the child's
@@ -752,20 +814,18 @@ struct PlanCompiler {
                     }
                     const int k_first = n_first >= n_sec ? 0 : 1024, k_sec = n_first >= n_sec ? 1024 : 0;
                     for (int i = 0; i < n; ++i)
-                        key[v[i]] = (bat[v[i]] == sN ? 2048 : (sec[v[i]] == sN ? k_sec : k_first)) + posC[v[i]];
+                        key[v[i]] = (bat[v[i]] == sN ? 2048 : (sec[v[i]] == sN ? k_sec : k_first)) + pos_c(v[i]);
                     sort_by_key(v, key.data(), n);
                 };
                 // tile set = the labels with the LOWEST positions in C (this node's own stores are enumerated in C order);
                 // inside the tile set the order follows the child's classes (the child's stores), except that the label
                 // with the highest C position goes last: it selects the epilogue round, so it must not be a low C bit
                 auto order_side = [&](int32_t* v, int n, int tmax, const std::vector<int32_t>& bat, const std::vector<int32_t>& sec) {
-                    for (int i = 0; i < n; ++i) key[v[i]] = posC[v[i]];
-                    sort_by_key(v, key.data(), n);
-                    const int tl = std::min(n, tmax);
+                    const int tl = std::min(n, tmax);  // v arrives sorted by position in C
                     // the lowest `nlow` tile labels stay in C order (then a 16-byte output vector is contiguous in the
                     // staging buffer too); the others follow the producing child's classes
                     // labels that are batch labels of the producing child cannot be low output bits of that child: last
-                    for (int i = 0; i < tl; ++i) key[v[i]] = (bat[v[i]] == sN ? 1024 : 0) + posC[v[i]];
+                    for (int i = 0; i < tl; ++i) key[v[i]] = (bat[v[i]] == sN ? 1024 : 0) + pos_c(v[i]);
                     sort_by_key(v, key.data(), tl);
                     int n_free = 0;
                     while (n_free < tl && bat[v[n_free]] != sN) ++n_free;
@@ -774,7 +834,7 @@ struct PlanCompiler {
                     if (tl >= 2) {
                         int top = 0;
                         for (int i = 1; i < tl; ++i)
-                            if (posC[v[i]] > posC[v[top]]) top = i;
+                            if (pos_c(v[i]) > pos_c(v[top])) top = i;
                         const int32_t lt = v[top];
                         for (int i = top; i + 1 < tl; ++i) v[i] = v[i + 1];
                         v[tl - 1] = lt;
@@ -784,8 +844,6 @@ struct PlanCompiler {
                 if (!tiny) {
                     order_side(M, nm, TILE_M_MAX, batA, secA);
                     order_side(N, nn, GEMM_TILE_MAX, batB, secB);
-                    for (int i = 0; i < nb; ++i) key[Bt[i]] = posC[Bt[i]];
-                    sort_by_key(Bt, key.data(), nb);
                     for (int i = 0; i < nk; ++i) key[K[i]] = (batA[K[i]] == sN) + (batB[K[i]] == sN);
                     sort_by_key(K, key.data(), nk);
                 }
@@ -863,7 +921,6 @@ struct PlanCompiler {
                     for (int i = 0; i < nb; ++i) *w++ = Bt[i];
                     lay_top += (size_t)(ra + rb);
                 }
-                for (int i = 0; i < rc; ++i) posC[lc[i]] = -1;
             }
         }
         return TB_OK;
@@ -1061,58 +1118,47 @@ struct PlanCompiler {
         P.subtrees.reserve(n_fused_roots);
         P.big_steps.reserve(n_big);
 
-        // fused subtrees: post-order with a "reserve C, then children above it" shared-memory stack
-        struct Frame {
-            int x;
-            int64_t base;
-            bool is_root;
-            int stage;
-            int64_t cur;
-        };
-        std::vector<Frame> stack;
+        // Fused subtrees.  Shared memory is a stack: a node's result sits at the bottom, the operand with the larger peak
+        // is computed first, directly above it, the other operand above that one.  The offsets follow top-down from
+        // that rule; the steps are the post-order (first operand's subtree, second operand's subtree, node), obtained
+        // by reversing a pre-order walk that visits the second operand first.
+        std::vector<int32_t> order, stack;
+        std::vector<int32_t> where(NLAB, -1);  // where[l] = (stamp of the step) * 16 + position of l in the step's output
         for (int t : topo) {
             if (kind[t] != KIND_FUSED || P.level[t] != 0) continue;
             SubTree st{};
             st.first_step = (uint32_t)P.sub_steps.size();
             st.out_off = P.off[t];
             int64_t max_top = 0;
+            order.clear();
             stack.clear();
-            stack.push_back({t, 0, true, 0, 0});
+            stack.push_back(t);
             while (!stack.empty()) {
-                Frame& f = stack.back();
-                const int x = f.x, A = lch[x], B = rch[x];
-                int64_t pA = leaf[A] ? 0 : peak[A], pB = leaf[B] ? 0 : peak[B];
+                const int x = stack.back();
+                stack.pop_back();
+                order.push_back(x);
+                const int A = lch[x], B = rch[x];
+                const int64_t pA = leaf[A] ? 0 : peak[A], pB = leaf[B] ? 0 : peak[B];
                 const int first = pA >= pB ? A : B, second = pA >= pB ? B : A;
-                if (f.stage == 0) {
-                    int64_t above = f.base;
-                    if (!f.is_root) {
-                        P.loc[x] = LOC_SMEM;
-                        P.off[x] = f.base;
-                        above = f.base + size_of(x);
-                    }
-                    max_top = std::max(max_top, above);
-                    f.cur = above;
-                    f.stage = 1;
-                    if (!leaf[first]) {
-                        Frame nf{first, f.cur, false, 0, 0};
-                        f.cur += size_of(first);
-                        max_top = std::max(max_top, f.cur);
-                        stack.push_back(nf);
-                        continue;
-                    }
+                int64_t cur = x == t ? 0 : P.off[x] + size_of(x);  // the subtree's root is written to the arena
+                if (!leaf[first]) {
+                    P.loc[first] = LOC_SMEM;
+                    P.off[first] = cur;
+                    cur += size_of(first);
+                    stack.push_back(first);
                 }
-                if (f.stage == 1) {
-                    f.stage = 2;
-                    if (!leaf[second]) {
-                        Frame nf{second, f.cur, false, 0, 0};
-                        f.cur += size_of(second);
-                        max_top = std::max(max_top, f.cur);
-                        stack.push_back(nf);
-                        continue;
-                    }
+                if (!leaf[second]) {
+                    P.loc[second] = LOC_SMEM;
+                    P.off[second] = cur;
+                    cur += size_of(second);
+                    stack.push_back(second);
                 }
+                max_top = std::max(max_top, cur);
+            }
+            for (size_t h = order.size(); h-- > 0;) {
+                const int x = order[h], A = lch[x], B = rch[x];
                 const NodeCls& c = cls[x];
-                const bool is_root = f.is_root;
+                const bool is_root = x == t;
                 SubStep s{};
                 s.a_off = (uint16_t)P.off[A];
                 s.b_off = (uint16_t)P.off[B];
@@ -1127,24 +1173,30 @@ struct PlanCompiler {
                 s.sa = c.tm;
                 s.sb = c.tn;
                 s.pad = c.kfirst;  // reduction bit 0 is address bit 0 of both operands, the other K bits start at sa+1 / sb+1
-                std::memset(s.a_shift, NO_BIT, sizeof s.a_shift + sizeof s.b_shift);
                 {
-                    // position of each output label in A / B: stamp the (short) output, then walk A and B once
+                    // position of each output label in A / B: stamp the (short) output, then walk A and B once; labels
+                    // that are reduced land in a spare slot instead of taking a branch
+                    uint8_t sh[2][32];
+                    std::memset(sh, NO_BIT, sizeof sh);
+                    const int sx = ++stamp;
                     const int32_t* lx = layp(x);
-                    const int rx = rank_of(x);
-                    for (int i = 0; i < rx; ++i) posCc[lx[i]] = (uint8_t)i;
+                    for (int i = 0, rx = rank_of(x); i < rx; ++i) where[lx[i]] = sx * 16 + i;
                     const int32_t* la_ = layp(A);
-                    for (int i = 0, ra_ = rank_of(A); i < ra_; ++i)
-                        if (posCc[la_[i]] != NO_BIT) s.a_shift[posCc[la_[i]]] = (uint8_t)i;
+                    for (int i = 0, ra_ = rank_of(A); i < ra_; ++i) {
+                        const int32_t wv = where[la_[i]];
+                        sh[0][(wv >> 4) == sx ? (wv & 15) : 31] = (uint8_t)i;
+                    }
                     const int32_t* lb_ = layp(B);
-                    for (int i = 0, rb_ = rank_of(B); i < rb_; ++i)
-                        if (posCc[lb_[i]] != NO_BIT) s.b_shift[posCc[lb_[i]]] = (uint8_t)i;
-                    for (int i = 0; i < rx; ++i) posCc[lx[i]] = NO_BIT;
+                    for (int i = 0, rb_ = rank_of(B); i < rb_; ++i) {
+                        const int32_t wv = where[lb_[i]];
+                        sh[1][(wv >> 4) == sx ? (wv & 15) : 31] = (uint8_t)i;
+                    }
+                    std::memcpy(s.a_shift, sh[0], sizeof s.a_shift);
+                    std::memcpy(s.b_shift, sh[1], sizeof s.b_shift);
                 }
                 P.sub_steps.push_back(s);
                 if (!temporary) P.recs.push_back(rec_of(x, KIND_FUSED, 0));
                 account(x, KIND_FUSED);
-                stack.pop_back();
             }
             st.n_steps = (uint32_t)P.sub_steps.size() - st.first_step;
             st.smem_elems = (uint32_t)max_top;
