@@ -24,6 +24,7 @@
 #include <string>
 #include <thread>
 #include <type_traits>
+#include <unordered_set>
 #include <vector>
 
 #include "kernels.cuh"
@@ -55,7 +56,12 @@ struct tb_ctx {
     Plan* resident = nullptr;  // head of the intrusive list of plans whose descriptors live on this context
     bool stream_open = false;  // a tb_stream owns the context between tb_stream_begin and tb_stream_finish
     int call_wave = 0;  // wave size of the current call (a small call is cut into more, smaller waves: all lanes busy)
-    std::thread reaper;  // frees the host side of the previous tb_contract_networks call's temporary plans
+    std::thread reaper;  // frees the host side of the previous call's temporary plans that do not go back to the pool
+    // temporary plans of tb_contract_networks / tb_stream_push are recycled: the next call compiles into the same objects
+    // (arrays keep their capacity), so a steady stream of calls neither allocates nor frees host memory per branch
+    std::mutex pool_mu;
+    std::vector<tb_plan*> plan_pool;
+    static constexpr size_t kPlanPoolMax = 1u << 15;  // ~30 KB of descriptors each for sc 20 branches
     tb_options opts{};
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -90,6 +96,10 @@ struct tb_ctx {
     bool own_stream = true;
     static constexpr int kMaxLanes = 8;
     double host_ms[6] = {0, 0, 0, 0, 0, 0};  // last call: compile, upload, build lists, launch+wait, destroy, total
+    // TB_TRACE_CALL=1: host-side stalls (allocations, waits for a staging slot) longer than 0.2 ms, with the call's clock
+    bool trace_on = false;
+    double trace_t0 = 0;
+    std::vector<std::string> trace_notes;
     int gemm2_ctas_per_sm = 2;
     bool staged_epilogue = true;           // TB_EPI_DIRECT=1: scatter stores straight from registers (A/B testing)
     bool gemm_v1 = false;                  // TB_GEMM_V1=1: the non-persistent cp.async GEMM kernel (A/B testing)
@@ -187,6 +197,36 @@ tb_plan* compile_new(const tb_network& net, uint32_t flags, int& code, std::stri
     return p;
 }
 
+// A temporary of tb_contract_networks / tb_stream_push: compiled in the worker thread's own scratch plan (memory that
+// stays hot in its cache), then only the descriptors are copied into a plan object from the context's pool.
+tb_plan* compile_temporary(tb_ctx* ctx, const tb_network& net, uint32_t flags, int& code, std::string& err) noexcept {
+    tb_plan* p = nullptr;
+    try {
+        static thread_local Plan scratch;
+        scratch.recycle();
+        code = compile_guarded(net, flags | TB_PLAN_TEMPORARY, scratch, err);
+        if (code) return nullptr;
+        {
+            std::lock_guard<std::mutex> lk(ctx->pool_mu);
+            if (!ctx->plan_pool.empty()) {
+                p = ctx->plan_pool.back();
+                ctx->plan_pool.pop_back();
+            }
+        }
+        if (!p) p = new tb_plan();
+        scratch.copy_descriptors_to(p->p);
+        return p;
+    } catch (const std::bad_alloc&) {
+        code = TB_ERR_OUT_OF_MEMORY;
+        err = "host memory allocation failed";
+    } catch (...) {
+        code = TB_ERR_INTERNAL;
+        err = "unknown C++ exception";
+    }
+    delete p;
+    return nullptr;
+}
+
 // NCCL, resolved with dlopen on first use (tb_init_multi): single-GPU users need no NCCL at all
 struct NcclApi {
     void* lib = nullptr;
@@ -247,6 +287,23 @@ void unlink_resident(tb_ctx* ctx, Plan& P) {
     P.res_prev = P.res_next = nullptr;
 }
 
+// times a host-side operation that may stall the launching thread (TB_TRACE_CALL diagnostics)
+struct StallTimer {
+    tb_ctx* ctx;
+    const char* what;
+    double t0;
+    StallTimer(tb_ctx* c, const char* w) : ctx(c), what(w), t0(c->trace_on ? now_ms() : 0) {}
+    ~StallTimer() {
+        if (!ctx->trace_on) return;
+        const double t1 = now_ms();
+        if (t1 - t0 > 0.2) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "%s: %.3f ms at %.3f", what, t1 - t0, t0 - ctx->trace_t0);
+            ctx->trace_notes.push_back(buf);
+        }
+    }
+};
+
 int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
     if (ctx->arena && ctx->arena_bytes >= need_bytes) return TB_OK;
     size_t want = (size_t)ctx->opts.arena_bytes;
@@ -259,6 +316,7 @@ int ensure_arena(tb_ctx* ctx, size_t need_bytes) {
     if (ctx->arena && ctx->arena_bytes >= want && need_bytes > want)
         return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "a single branch needs " + std::to_string(need_bytes) + " bytes of arena, more than configured");
     if (need_bytes > want) return set_err(ctx, TB_ERR_OUT_OF_MEMORY, "a single branch needs " + std::to_string(need_bytes) + " bytes of arena; arena limit is " + std::to_string(want));
+    StallTimer stall(ctx, "arena (re)allocation");
     if (ctx->arena) {
         int rcs = sync_all_lanes(ctx);
         if (rcs) return rcs;
@@ -298,27 +356,31 @@ int acquire_slot(tb_ctx* ctx, size_t hbytes, size_t dbytes, tb_ctx::Slot** out) 
     tb_ctx::Slot& sl = ctx->slots[pick];
     if (!sl.ev) TB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
     if (sl.busy) {
+        StallTimer stall(ctx, "wait for a staging slot");
         TB_CUDA(ctx, cudaEventSynchronize(sl.ev));
         sl.busy = false;
     }
-    // a slot that has to grow grows to the largest size any slot has reached: the ring converges in at most kSlots
-    // (re)allocations instead of re-pinning memory (tens of ms) whenever a large batch meets a small free slot
+    // (Re)pinning host memory costs ~2 ms per MB (profiles/x3_trace_cfg2_before.txt: 6-15 ms stalls in the middle of a call),
+    // so a slot that has to grow grows generously -- twice the request, at least 16 MB, at least the largest size any
+    // slot has reached: the ring stops growing after the first call instead of creeping up for dozens of calls
     size_t max_h = 0, max_d = 0;
     for (const tb_ctx::Slot& c : ctx->slots) {
         max_h = std::max(max_h, c.hcap);
         max_d = std::max(max_d, c.dcap);
     }
     if (sl.hcap < hbytes) {
+        StallTimer stall(ctx, "staging slot grows (pinned host)");
         if (sl.h) cudaFreeHost(sl.h);
         sl.h = nullptr;
-        size_t cap = std::max(std::max(hbytes * 5 / 4, (size_t)1 << 20), max_h);
+        size_t cap = std::max(std::max(hbytes * 2, (size_t)16 << 20), max_h);
         TB_CUDA(ctx, cudaMallocHost(&sl.h, cap));
         sl.hcap = cap;
     }
     if (sl.dcap < dbytes) {
+        StallTimer stall(ctx, "staging slot grows (device)");
         if (sl.d) cudaFree(sl.d);
         sl.d = nullptr;
-        size_t cap = std::max(std::max(dbytes * 5 / 4, (size_t)1 << 20), max_d);
+        size_t cap = std::max(std::max(dbytes * 2, (size_t)8 << 20), max_d);
         TB_CUDA(ctx, cudaMalloc(&sl.d, cap));
         sl.dcap = cap;
     }
@@ -351,6 +413,8 @@ int ensure_results(tb_ctx* ctx, size_t n) {
 // upload the descriptor blobs of all plans that are not resident yet (one staging copy per chunk)
 int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
     std::vector<tb_plan*> todo;
+    std::unordered_set<tb_plan*> seen;
+    seen.reserve((size_t)n * 2);
     size_t total = 0;
     for (int64_t i = 0; i < n; ++i) {
         tb_plan* p = plans[i];
@@ -359,7 +423,7 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
             if (p->p.owner != ctx) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "plan is resident on a different context");
             continue;
         }
-        if (std::find(todo.begin(), todo.end(), p) != todo.end()) continue;
+        if (!seen.insert(p).second) continue;  // the same plan may appear more than once in a batch
         todo.push_back(p);
     }
     if (todo.empty()) return TB_OK;
@@ -391,7 +455,10 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
             BlobChunk nc;
             size_t prev = ctx->chunks.empty() ? 0 : ctx->chunks.back().cap;
             nc.cap = std::max<size_t>(std::max(rest, 2 * prev), (size_t)32 << 20);
-            TB_CUDA(ctx, cudaMalloc(&nc.d, nc.cap));
+            {
+                StallTimer stall(ctx, "descriptor chunk allocation");
+                TB_CUDA(ctx, cudaMalloc(&nc.d, nc.cap));
+            }
             ctx->chunks.push_back(nc);
             ck = &ctx->chunks.back();
         }
@@ -533,6 +600,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             }
             target = std::min(target, want);
             if (target > ctx->arena_bytes) {
+                StallTimer stall(ctx, "arena grows for the waves of a batch");
                 sync_all_lanes(ctx);
                 void* na = nullptr;
                 cudaFree(ctx->arena);
@@ -1120,7 +1188,7 @@ tb_plan* clone_for_assignment(const tb_plan* base, const uint8_t* values) {
 
 // the temporary plans of a *_networks / stream call all live in chunks of that call: release the device side once,
 // free the host side off the caller's critical path (joined by the next call / tb_shutdown)
-void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans) {
+void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans, bool to_pool = false) {
     for (tb_plan* p : plans)
         if (p && p->p.d_blob) {
             for (auto& c : ctx->chunks)
@@ -1132,6 +1200,17 @@ void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans) {
             p->p.d_blob = nullptr;
             p->p.owner = nullptr;
         }
+    if (to_pool) {  // compact temporaries (compile_temporary): the next call compiles into the same objects
+        std::lock_guard<std::mutex> lk(ctx->pool_mu);
+        size_t kept = 0;
+        for (tb_plan*& p : plans)
+            if (p && ctx->plan_pool.size() < tb_ctx::kPlanPoolMax) {
+                ctx->plan_pool.push_back(p);
+                p = nullptr;
+                ++kept;
+            }
+        if (kept == plans.size()) return;
+    }
     if (ctx->reaper.joinable()) ctx->reaper.join();
     ctx->reaper = std::thread([dead = std::move(plans)]() {
         for (tb_plan* p : dead) delete p;
@@ -1389,6 +1468,8 @@ int tb_shutdown(tb_ctx* ctx) {
         return TB_OK;
     }
     if (ctx->reaper.joinable()) ctx->reaper.join();
+    for (tb_plan* p : ctx->plan_pool) delete p;
+    ctx->plan_pool.clear();
 #ifdef TB_KPROF
     {
         cudaSetDevice(ctx->device);
@@ -1545,6 +1626,66 @@ struct NetworksCall {
     double t_c0 = 0;
 };
 
+// TB_TRACE_CALL=1 (diagnostics): per pipeline batch, when the host had it compiled / enqueued and when the device finished
+// it, printed to stderr after the call (device times from events on every lane, relative to the start of the call)
+struct CallTrace {
+    struct Row {
+        int64_t lo, hi;
+        double t_ready, t_enqueued;
+        double upload_ms, lists_ms, launch_ms;  // cumulative over the call
+        std::vector<cudaEvent_t> ev;
+    };
+    bool on = false;
+    cudaEvent_t ev0 = nullptr;
+    std::vector<Row> rows;
+    static bool enabled() {
+        static const bool e = getenv("TB_TRACE_CALL") != nullptr;
+        return e;
+    }
+    void begin(tb_ctx* ctx) {
+        on = enabled();
+        ctx->trace_on = on;
+        ctx->trace_t0 = now_ms();
+        ctx->trace_notes.clear();
+        if (!on) return;
+        cudaEventCreate(&ev0);
+        cudaEventRecord(ev0, ctx->stream);
+    }
+    void batch(tb_ctx* ctx, int64_t lo, int64_t hi, double t_ready, double t_enq) {
+        if (!on) return;
+        Row r{lo, hi, t_ready, t_enq, ctx->host_ms[1], ctx->host_ms[2], ctx->host_ms[3], {}};
+        for (int l = 0; l < ctx->n_lanes; ++l) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, l == 0 ? ctx->stream : ctx->side[l]);
+            r.ev.push_back(e);
+        }
+        rows.push_back(std::move(r));
+    }
+    void dump(tb_ctx* ctx, double t_host_done) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        fprintf(stderr, "[tb trace] device %d: host done at %.3f ms\n", ctx->device, t_host_done);
+        for (Row& r : rows) {
+            float dev_done = 0;
+            for (cudaEvent_t e : r.ev) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev0, e);
+                dev_done = std::max(dev_done, ms);
+                cudaEventDestroy(e);
+            }
+            fprintf(stderr, "[tb trace] plans %5lld..%5lld  compiled %7.3f  enqueued %7.3f  device done %7.3f ms   (cumulative upload %.2f lists %.2f launch %.2f)\n",
+                    (long long)r.lo, (long long)r.hi, r.t_ready, r.t_enqueued, (double)dev_done, r.upload_ms, r.lists_ms, r.launch_ms);
+        }
+        for (const std::string& note : ctx->trace_notes) fprintf(stderr, "[tb trace] stall: %s\n", note.c_str());
+        ctx->trace_notes.clear();
+        ctx->trace_on = false;
+        cudaEventDestroy(ev0);
+        rows.clear();
+        on = false;
+    }
+};
+
 int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_results, NetworksCall& cs) {
     cs.t_c0 = now_ms();
     const double t_c0 = cs.t_c0;
@@ -1555,6 +1696,8 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
         const unsigned blocks = (unsigned)((n_results + 255) / 256);
         k_fill_double<<<blocks, 256, 0, ctx->stream>>>(ctx->d_results, n_results, -std::numeric_limits<double>::infinity());
     }
+    CallTrace trace;
+    trace.begin(ctx);
     std::vector<tb_plan*>& plans = cs.plans;
     plans.assign((size_t)n, nullptr);
     std::vector<int> codes((size_t)n, TB_OK);
@@ -1573,7 +1716,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
             int64_t i = next.fetch_add(1);
             if (i >= n) break;
             if (!abort.load(std::memory_order_relaxed) && nets[i].n_leaves != 0) {
-                plans[i] = compile_new(nets[i], flags, codes[i], errs[i]);
+                plans[i] = compile_temporary(ctx, nets[i], flags, codes[i], errs[i]);
                 if (codes[i]) abort.store(true);
             }
             done[i].store(1, std::memory_order_release);
@@ -1603,7 +1746,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
             while (next.load() < hi && next.load() < n) {  // single-threaded: compile this batch inline
                 int64_t i = next.fetch_add(1);
                 if (i >= n) break;
-                if (nets[i].n_leaves != 0) plans[i] = compile_new(nets[i], flags, codes[i], errs[i]);
+                if (nets[i].n_leaves != 0) plans[i] = compile_temporary(ctx, nets[i], flags, codes[i], errs[i]);
                 done[i].store(1, std::memory_order_release);
             }
         }
@@ -1613,7 +1756,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
                 int64_t j = next.fetch_add(1);
                 if (j < n) {
                     if (!abort.load(std::memory_order_relaxed) && nets[j].n_leaves != 0) {
-                        plans[j] = compile_new(nets[j], flags, codes[j], errs[j]);
+                        plans[j] = compile_temporary(ctx, nets[j], flags, codes[j], errs[j]);
                         if (codes[j]) abort.store(true);
                     }
                     done[j].store(1, std::memory_order_release);
@@ -1622,6 +1765,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
                 }
             }
         t_wait += now_ms() - tw0;
+        const double t_ready = now_ms() - t_c0;
         for (int64_t i = lo; i < hi; ++i) {
             if (codes[i]) {
                 rc = set_err(ctx, codes[i], "branch " + std::to_string(i) + ": " + errs[i]);
@@ -1634,9 +1778,11 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
             batch_max = batch_cap ? batch_cap : std::max<int64_t>(256, (int64_t)ctx->call_wave * ctx->n_lanes / 2);
         }
         if (rc == TB_OK) rc = enqueue_batch(ctx, plans.data(), lo, hi, status, false);
+        trace.batch(ctx, lo, hi, t_ready, now_ms() - t_c0);
     }
     abort.store(rc != TB_OK);
     th.join();
+    trace.dump(ctx, now_ms() - t_c0);
     ctx->host_ms[0] = t_wait;  // time the launching thread spent waiting for the compiler threads
     return rc;
 }
@@ -1908,7 +2054,7 @@ int multi_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r
     }
     for (int d = 0; d < D; ++d) {
         cudaSetDevice(ctx->subs[(size_t)d]->device);
-        release_temporary_plans(ctx->subs[(size_t)d], std::move(dev[(size_t)d].cs.plans));
+        release_temporary_plans(ctx->subs[(size_t)d], std::move(dev[(size_t)d].cs.plans), true);
     }
     multi_aggregate(ctx, t0);
     return rc;
@@ -2014,7 +2160,7 @@ int tb_contract_networks(tb_ctx* ctx, const tb_network* nets, const double* r, i
     if (rc == TB_OK) rc = finish_call(ctx, cs.plans.data(), r, n, cs.status, out_values, out_status, out_max, cs.any);
     else sync_all_lanes(ctx);
     const double t_d0 = now_ms();
-    release_temporary_plans(ctx, std::move(cs.plans));
+    release_temporary_plans(ctx, std::move(cs.plans), true);
     ctx->host_ms[4] = now_ms() - t_d0;
     ctx->host_ms[5] = now_ms() - cs.t_c0;
     return rc;
@@ -2059,7 +2205,7 @@ int tb_stream_push(tb_stream* s, const tb_network* nets, const double* r, int64_
             const int64_t i = next.fetch_add(1);
             if (i >= n) break;
             if (nets[i].n_leaves == 0) continue;
-            s->plans[(size_t)(lo + i)] = compile_new(nets[i], flags, codes[i], errs[i]);
+            s->plans[(size_t)(lo + i)] = compile_temporary(ctx, nets[i], flags, codes[i], errs[i]);
         }
     };
     int nthreads = ctx->opts.host_threads > 0 ? ctx->opts.host_threads : (int)std::thread::hardware_concurrency();
@@ -2097,7 +2243,7 @@ int tb_stream_finish(tb_stream* s, double* out_values, int32_t* out_status, int6
         rc = finish_call(ctx, s->plans.data(), s->r.data(), n, s->status, vals.data(), out_status, out_max, s->any);
         if (n > 0) std::memcpy(out_values, vals.data(), (size_t)n * sizeof(double));
     }
-    release_temporary_plans(ctx, std::move(s->plans));
+    release_temporary_plans(ctx, std::move(s->plans), true);
     ctx->host_ms[5] = now_ms() - s->t0;
     ctx->stream_open = false;
     delete s;

@@ -116,13 +116,48 @@ inline void sort_by_key(int32_t* v, const int32_t* key, int n) {
 
 namespace {
 
-// One compilation: the passes below run in order and share the flat arrays declared first.
-struct PlanCompiler {
+// The compiler's working arrays.  contract_slices compiles thousands of plans per call on every worker thread, so
+// each thread keeps one set and a compilation borrows it: after the first few plans no pass allocates memory.
+struct CompilerArrays {
+    // flat per-tensor storage: tree, sorted label sets
+    std::vector<int32_t> lch, rch, parent, lab_off, lab_data;
+    std::vector<uint8_t> leaf, unary, lab_n;
+    std::vector<int8_t> fixed;        // index slicing: -1 (free) or the value the label is fixed to
+    std::vector<int32_t> fixed_idx;   // label -> its position in net.fixed_labels
+    std::vector<int32_t> leaf_vertex, leaf_fa, leaf_fb;
+    std::vector<int32_t> lo, hi, minpos, maxpos;  // leaf positions (depth-first) covered by a subtree / holding a label
+    std::vector<uint8_t> is_open;
+    std::vector<int32_t> stA, stB, stC;  // stamp arrays for O(1) membership
+    std::vector<uint8_t> folded, kept;
+    std::vector<int32_t> post0, topo;  // internal nodes, children before parents: the given tree / after the split-K rewrite
+    std::vector<NodeCls> cls;
+    std::vector<int32_t> cls_data;
+    std::vector<int32_t> leaf_pool_off;
+    std::vector<uint8_t> fus;
+    std::vector<int64_t> peak;
+    std::vector<int8_t> kind;
+    std::vector<uint8_t> posA, posB, posCc;
+    // pass-local arrays
+    std::vector<int32_t> nint, first;                      // value_type_and_positions
+    std::vector<int32_t> key, posC, batA, batB, secA, secB;  // layouts
+    std::vector<int32_t> order, stack, where;              // emit_fused
+    std::vector<int32_t> big_order, big_index;             // emit_big
+};
+
+// One compilation: the passes below run in order and share the arrays above.
+struct PlanCompiler : CompilerArrays {
     const tb_network& net;
     uint32_t extra_flags;
     Plan& P;
     std::string& err;
-    PlanCompiler(const tb_network& n, uint32_t f, Plan& p, std::string& e) : net(n), extra_flags(f), P(p), err(e) {}
+    static CompilerArrays& thread_arrays() {
+        static thread_local CompilerArrays a;
+        return a;
+    }
+    PlanCompiler(const tb_network& n, uint32_t f, Plan& p, std::string& e) : CompilerArrays(std::move(thread_arrays())), net(n), extra_flags(f), P(p), err(e) {}
+    ~PlanCompiler() { thread_arrays() = std::move(static_cast<CompilerArrays&>(*this)); }
+    PlanCompiler(const PlanCompiler&) = delete;
+    PlanCompiler& operator=(const PlanCompiler&) = delete;
 
     // ---- state shared by the passes
     bool temporary = false, estimate_only = false, synth = false, finished = false;
@@ -132,29 +167,11 @@ struct PlanCompiler {
     static constexpr int TILE_M_MAX = GEMM_TILE_MAX;  // tile bits of the M side
     static constexpr int MT_LOG = 3;                  // log2 of a thread's microtile extent (8 x 8 outputs, both value widths)
     int STAGE_ELEMS = 0;
-    // flat per-tensor storage: tree, sorted label sets
-    std::vector<int32_t> lch, rch, parent, lab_off, lab_data;
-    std::vector<uint8_t> leaf, unary, lab_n;
-    std::vector<int8_t> fixed;        // index slicing: -1 (free) or the value the label is fixed to
-    std::vector<int32_t> fixed_idx;   // label -> its position in net.fixed_labels
-    std::vector<int32_t> leaf_vertex, leaf_fa, leaf_fb;
-    std::vector<int32_t> lo, hi, minpos, maxpos;  // leaf positions (depth-first) covered by a subtree / holding a label
-    std::vector<uint8_t> is_open;
     double est_ops = 0, est_all = 0, est_peak = 0;
     int est_sc = 0;
-    std::vector<int32_t> stA, stB, stC;  // stamp arrays for O(1) membership
     int stamp = 0;
-    std::vector<uint8_t> folded, kept;
-    std::vector<int32_t> post0, topo;  // internal nodes, children before parents: the given tree / after the split-K rewrite
     size_t lab_total = 0, lay_top = 0, cls_top = 0;
-    std::vector<NodeCls> cls;
-    std::vector<int32_t> cls_data;
-    std::vector<int32_t> leaf_pool_off;
-    std::vector<uint8_t> fus;
-    std::vector<int64_t> peak;
-    std::vector<int8_t> kind;
     int n_fused_roots = 0, n_big = 0;
-    std::vector<uint8_t> posA, posB, posCc;
     double ops_f = 0, ops_g = 0, ops_m = 0, bytes = 0, bytes_m = 0, sc = 0;
 
     int fail(int code, const std::string& m) {
@@ -378,7 +395,8 @@ struct PlanCompiler {
         // ascending sweep and the depth-first numbers (left operand first) from one descending sweep.  post0 = the
         // internal nodes in depth-first post-order: node t is emitted after the internal nodes of both subtrees.
         {
-            std::vector<int32_t> nint(nT0, 0), first(nT0, 0);  // internal nodes in the subtree; post-order index of its first one
+            nint.assign(nT0, 0);   // internal nodes in the subtree
+            first.assign(nT0, 0);  // post-order index of the subtree's first internal node
             for (int i = 0; i < nL; ++i) hi[i] = 1;              // hi holds the leaf COUNT of the subtree during the sweeps
             for (int t = nL; t < nT0; ++t) {
                 hi[t] = hi[lch[t]] + hi[rch[t]];
@@ -419,6 +437,7 @@ struct PlanCompiler {
         est_ops = 0;  // sum over nodes of 2^(labels involved): the reference's 2^tc (src/types.jl:120)
         est_sc = 0;
         for (int i = 0; i < nL; ++i) est_sc = std::max(est_sc, (int)lab_n[i]);
+        size_t lab_top = lab_data.size();  // lab_data is grown in large steps; its size is set to lab_top at the end
         for (int t = nL; t < nT0; ++t) {
             const int A = lch[t], B = rch[t];
             const int na = lab_n[A], nb = lab_n[B];
@@ -438,9 +457,9 @@ struct PlanCompiler {
                 while (j < nb) u[nu++] = b[j++];
             }
             if (nu > 62) return fail(TB_ERR_UNSUPPORTED, "a contraction involves more than 62 labels");
-            const size_t at = lab_data.size();
+            const size_t at = lab_top;
             lab_off[t] = (int32_t)at;
-            lab_data.resize(at + (size_t)nu);
+            if (lab_data.size() < at + 64) lab_data.resize(std::max(2 * lab_data.size(), at + 1024));  // room for one more set
             int no = 0;
             {
                 // a label is reduced here iff it is not open and all its leaves lie inside this subtree
@@ -453,13 +472,14 @@ struct PlanCompiler {
                     no += !closed;
                 }
             }
-            lab_data.resize(at + (size_t)no);
+            lab_top = at + (size_t)no;
             if (no > MAX_RANK) return fail(TB_ERR_UNSUPPORTED, "intermediate tensor of rank " + std::to_string(no) + " > 31");
             if (nu - no > 30) return fail(TB_ERR_UNSUPPORTED, "a contraction reduces more than 30 labels");
             lab_n[t] = (uint8_t)no;
             est_ops += (double)(1ull << nu);
             est_sc = std::max(est_sc, no);
         }
+        lab_data.resize(lab_top);
         if (estimate_only) {
             P.stats = tb_plan_stats{};
             P.stats.ops = est_ops;
@@ -678,12 +698,14 @@ struct PlanCompiler {
                 P.lay_n[root] = (uint8_t)net.n_open;
                 for (int i = 0; i < net.n_open; ++i) P.lay_data[lay_top++] = net.open_labels[i];
             }
-            std::vector<int32_t> key(NLAB, 0);      // sort key per label (valid for the node being processed)
+            key.assign(NLAB, 0);  // sort key per label (valid for the node being processed)
             // posC[l] = (stamp of the node being processed) * 64 + position of l in the node's output layout: a stale
             // stamp means "not an output label", so nothing has to be reset between nodes
-            std::vector<int32_t> posC(NLAB, -1);
-            std::vector<int32_t> batA(NLAB, -1), batB(NLAB, -1);  // stamps: label is a batch label inside child A / B
-            std::vector<int32_t> secA(NLAB, -1), secB(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
+            posC.assign(NLAB, -1);
+            batA.assign(NLAB, -1);  // stamps: label is a batch label inside child A / B
+            batB.assign(NLAB, -1);
+            secA.assign(NLAB, -1);  // stamps: label belongs only to the child's SECOND operand
+            secB.assign(NLAB, -1);
             const bool scramble = (P.flags & TB_PLAN_SCRAMBLE_LAYOUT) != 0;
             for (auto it = topo.rbegin(); it != topo.rend(); ++it) {
                 const int t = *it;
@@ -1000,13 +1022,13 @@ struct PlanCompiler {
             const int A = lch[t], B = rch[t];
             const NodeCls& c = cls[t];
             int tc = rank_of(t) + c.nk + c.nka + c.nkb;
-            bool ok = allow_fused && rank_of(t) <= FUSED_MAX_RANK && rank_of(A) <= FUSED_MAX_RANK &&
-                      rank_of(B) <= FUSED_MAX_RANK && tc <= FUSED_MAX_TC && (leaf[A] || fus[A]) && (leaf[B] || fus[B]);
+            const bool ok = allow_fused & (rank_of(t) <= FUSED_MAX_RANK) & (rank_of(A) <= FUSED_MAX_RANK) &
+                            (rank_of(B) <= FUSED_MAX_RANK) & (tc <= FUSED_MAX_TC) & ((leaf[A] | fus[A]) != 0) & ((leaf[B] | fus[B]) != 0);
             int64_t pA = leaf[A] ? 0 : peak[A], sA = leaf[A] ? 0 : size_of(A);
             int64_t pB = leaf[B] ? 0 : peak[B], sB = leaf[B] ? 0 : size_of(B);
             int64_t pk = size_of(t) + (pA >= pB ? std::max(pA, sA + pB) : std::max(pB, sB + pA));
             peak[t] = pk;
-            fus[t] = ok && pk <= (wide ? FUSED_SMEM_ELEMS / 2 : FUSED_SMEM_ELEMS);  // 32 KB of values either way
+            fus[t] = ok & (pk <= (wide ? FUSED_SMEM_ELEMS / 2 : FUSED_SMEM_ELEMS));  // 32 KB of values either way
         }
         P.loc.assign(nT, LOC_ARENA);
         P.off.assign(nT, 0);
@@ -1122,8 +1144,7 @@ struct PlanCompiler {
         // is computed first, directly above it, the other operand above that one.  The offsets follow top-down from
         // that rule; the steps are the post-order (first operand's subtree, second operand's subtree, node), obtained
         // by reversing a pre-order walk that visits the second operand first.
-        std::vector<int32_t> order, stack;
-        std::vector<int32_t> where(NLAB, -1);  // where[l] = (stamp of the step) * 16 + position of l in the step's output
+        where.assign(NLAB, -1);  // where[l] = (stamp of the step) * 16 + position of l in the step's output
         for (int t : topo) {
             if (kind[t] != KIND_FUSED || P.level[t] != 0) continue;
             SubTree st{};
@@ -1209,13 +1230,18 @@ struct PlanCompiler {
     int emit_big() {
         // big steps by level
         {
-            std::vector<int> order;
-            order.reserve(n_big);
-            for (int t : topo)
-                if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) order.push_back(t);
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return P.level[x] < P.level[y]; });
+            // stable counting sort of the big steps by level: big_level_begin[lv] = first step of level lv (levels from 1)
+            std::vector<int32_t>& order = big_order;
+            std::vector<int32_t>& cursor = stack;
             P.big_level_begin.assign(P.n_levels + 2, 0);
-            std::vector<int32_t> big_index(nT, -1);  // node -> its position in big_steps (dependencies of the dataflow executor)
+            for (int t : topo)
+                if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) ++P.big_level_begin[P.level[t] + 1];
+            for (int lv = 1; lv <= P.n_levels; ++lv) P.big_level_begin[lv + 1] += P.big_level_begin[lv];
+            cursor.assign(P.big_level_begin.begin(), P.big_level_begin.end());
+            order.assign(n_big, 0);
+            for (int t : topo)
+                if (kind[t] == KIND_GENERIC || kind[t] == KIND_GEMM) order[cursor[P.level[t]]++] = t;
+            big_index.assign(nT, -1);  // node -> its position in big_steps (dependencies of the dataflow executor)
             P.big_dep_a.reserve(n_big);
             P.big_dep_b.reserve(n_big);
             for (int t : order) {
@@ -1391,12 +1417,6 @@ struct PlanCompiler {
                 if (!temporary) P.recs.push_back(rec_of(t, kind[t], P.level[t]));
                 account(t, kind[t]);
             }
-            int idx = 0;
-            for (int lv = 1; lv <= P.n_levels + 1; ++lv) {
-                while (idx < (int)order.size() && P.level[order[idx]] < lv) ++idx;
-                P.big_level_begin[lv] = idx;
-            }
-            P.big_level_begin[0] = 0;
         }
         return TB_OK;
     }
@@ -1615,6 +1635,44 @@ tb_step_info Plan::step_info(size_t i) const {
     for (int q = 0; q < s.rank_b; ++q) s.labels_b[q] = layout(r.right)[q];
     for (int q = 0; q < s.rank_c; ++q) s.labels_c[q] = layout(r.node)[q];
     return s;
+}
+
+void Plan::recycle() {
+    Plan fresh;
+    // an array that is not listed here just loses its capacity
+#define TB_KEEP(v) \
+    v.clear();     \
+    fresh.v.swap(v);
+    TB_KEEP(lay_off) TB_KEEP(lay_n) TB_KEEP(lay_data) TB_KEEP(loc) TB_KEEP(off) TB_KEEP(level) TB_KEEP(pool) TB_KEEP(patches)
+    TB_KEEP(sub_steps) TB_KEEP(subtrees) TB_KEEP(big_steps) TB_KEEP(big_level_begin) TB_KEEP(big_log2_ops) TB_KEEP(big_bytes)
+    TB_KEEP(big_dep_a) TB_KEEP(big_dep_b) TB_KEEP(recs)
+#undef TB_KEEP
+    *this = std::move(fresh);
+}
+
+void Plan::copy_descriptors_to(Plan& dst) const {
+    dst.n_labels = n_labels;
+    dst.n_leaves = n_leaves;
+    dst.n_nodes = n_nodes;
+    dst.flags = flags;
+    dst.value_type = value_type;
+    dst.pool = pool;
+    dst.patches = patches;
+    dst.n_fixed = n_fixed;
+    dst.sub_steps = sub_steps;
+    dst.subtrees = subtrees;
+    dst.big_steps = big_steps;
+    dst.big_level_begin = big_level_begin;
+    dst.big_log2_ops = big_log2_ops;
+    dst.big_bytes = big_bytes;
+    dst.big_dep_a = big_dep_a;
+    dst.big_dep_b = big_dep_b;
+    dst.n_levels = n_levels;
+    dst.arena_elems = arena_elems;
+    dst.root_off = root_off;
+    dst.root_id = root_id;
+    dst.stats = stats;
+    dst.n_tensors = 0;  // no tensor table: tb_read_tensor / tb_contract_tensor refuse such a plan
 }
 
 uint64_t Plan::encode_value(int vt, double x, bool neg_inf, int config_bit) {

@@ -74,6 +74,12 @@ struct Plan {
     int n_tensors = 0;  // leaves + nodes + synthetic (split-K) tensors
     tb_step_info step_info(size_t i) const;
 
+    // back to the state of a new plan, keeping the capacity of every array: compiling into a recycled plan allocates nothing
+    void recycle();
+    // the part of a compiled plan the executor needs -- descriptors, launch geometry, statistics -- copied into `dst` with
+    // exact-size arrays; layouts, the tensor table and the step records stay behind (temporaries of contract_slices)
+    void copy_descriptors_to(Plan& dst) const;
+
     // device residency (managed by the engine)
     tb_ctx* owner = nullptr;
     Plan* res_prev = nullptr;  // intrusive list of the plans resident on `owner` (tb_shutdown detaches them, so a plan
