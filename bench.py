@@ -530,13 +530,13 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
 
     e2e = None
     if e2e_on:
-        ms_e2e, result_e2e, e2e_steps_ms = timed(step_e2e, steps, 2)
+        ms_e2e, result_e2e, e2e_steps_ms = timed(step_e2e, steps, 3)
         h2d, d2h = eng.last_transfers()
         hb = all_sum([h2d, d2h])
         if slice_k > 0:  # tb_last_transfers covers one call; a sliced step makes one call per branch
             hb = hb * sum(1 for s in sliced if s.code is not None)
         e2e = {"value": total_ops / (ms_e2e * 1e-3) * 1e-9, "unit": "Gop/s", "h2d_bytes_per_step": int(hb[0]),
-               "d2h_bytes_per_step": int(hb[1]), "ms_per_step": ms_e2e, "steps": timed.steps, "warmup": 2,
+               "d2h_bytes_per_step": int(hb[1]), "ms_per_step": ms_e2e, "steps": timed.steps, "warmup": 3,
                "ms_per_step_min_median_max": [round(e2e_steps_ms[0], 4), round(e2e_steps_ms[len(e2e_steps_ms) // 2], 4),
                                               round(e2e_steps_ms[-1], 4)],
                "host_breakdown_rank0": eng.last_host_breakdown(),

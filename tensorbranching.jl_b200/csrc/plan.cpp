@@ -140,6 +140,8 @@ struct CompilerArrays {
     // pass-local arrays
     std::vector<int32_t> nint, first;                      // value_type_and_positions
     std::vector<int32_t> key, posC, batA, batB, secA, secB;  // layouts
+    std::vector<uint8_t> tiny_shift;                       // layouts -> emit_fused: SubStep::a_shift | b_shift of tiny nodes
+    std::vector<uint8_t> is_tiny;
     std::vector<int32_t> order, stack, where;              // emit_fused
     std::vector<int32_t> big_order, big_index;             // emit_big
 };
@@ -699,6 +701,8 @@ struct PlanCompiler : CompilerArrays {
                 for (int i = 0; i < net.n_open; ++i) P.lay_data[lay_top++] = net.open_labels[i];
             }
             key.assign(NLAB, 0);  // sort key per label (valid for the node being processed)
+            is_tiny.assign(nT, 0);
+            tiny_shift.resize((size_t)nT * 32);
             // posC[l] = (stamp of the node being processed) * 64 + position of l in the node's output layout: a stale
             // stamp means "not an output label", so nothing has to be reset between nodes
             posC.assign(NLAB, -1);
@@ -743,12 +747,21 @@ struct PlanCompiler : CompilerArrays {
                     static_assert(GEMM_TILE_MAX >= 6, "tiny nodes keep all M / N labels inside the tile");
                     const int32_t *pa = labp(A), *pb = labp(B);
                     const int ra = lab_n[A], rb = lab_n[B];
+                    // While the labels are placed, their positions are recorded as the step's shift tables (position in A / B
+                    // of the label at output bit p; SubStep::a_shift / b_shift); slot 63 swallows the labels that are reduced.
                     uint8_t kb[8];               // class of B's q-th label: 0 KB, 1 N, 2 K, 3 Bt
+                    uint8_t pcb[8];              // its output bit (63: none)
+                    uint8_t sa[64], sb[64];
+                    std::memset(sa, NO_BIT, 16);
+                    std::memset(sb, NO_BIT, 16);
                     int cnt[4] = {0, 0, 0, 0};
                     for (int q = 0; q < rb; ++q) {
                         const int32_t l = pb[q];
-                        const int k = ((inA[l] == sN) << 1) | (int)in_c(l);
+                        const int32_t pv = posC[l];
+                        const int inC = (pv >> 6) == sN;
+                        const int k = ((inA[l] == sN) << 1) | inC;
                         kb[q] = (uint8_t)k;
+                        pcb[q] = (uint8_t)(inC ? (pv & 63) : 63);
                         ++cnt[k];
                     }
                     const int nkb = cnt[0], nn = cnt[1], nk = cnt[2], nb = cnt[3];
@@ -777,18 +790,30 @@ struct PlanCompiler : CompilerArrays {
                     const int step[4] = {0, 0, 1, 1};
                     for (int q = 0; q < ra; ++q) {
                         const int32_t l = pa[q];
-                        const int k = ((inB[l] == sN) << 1) | (int)in_c(l);
-                        *ca[k]++ = l;
-                        *cs[k] = l;
+                        const int32_t pv = posC[l];
+                        const int inC = (pv >> 6) == sN;
+                        const int pc = inC ? (pv & 63) : 63;
+                        const int k = ((inB[l] == sN) << 1) | inC;
+                        int32_t* da = ca[k]++;
+                        *da = l;
+                        sa[pc] = (uint8_t)(da - wa);
+                        int32_t* db = cs[k];
+                        *db = l;
                         cs[k] += step[k];
+                        sb[k == 3 ? pc : 63] = (uint8_t)(db - wb);
                     }
                     int32_t* cbw[4] = {wb + nn + nk, wb, &sink, &sink};  // KB, N; shared labels were written from A
                     const int stepb[4] = {1, 1, 0, 0};
                     for (int q = 0; q < rb; ++q) {
                         const int k = kb[q];
-                        *cbw[k] = pb[q];
+                        int32_t* db = cbw[k];
+                        *db = pb[q];
                         cbw[k] += stepb[k];
+                        sb[k == 1 ? pcb[q] : 63] = (uint8_t)(db - wb);
                     }
+                    is_tiny[t] = 1;
+                    std::memcpy(tiny_shift.data() + (size_t)t * 32, sa, 16);
+                    std::memcpy(tiny_shift.data() + (size_t)t * 32 + 16, sb, 16);
                     lay_top += (size_t)(ra + rb);
                     continue;
                 }
@@ -807,24 +832,29 @@ struct PlanCompiler : CompilerArrays {
                         else sec[l] = sN;
                     }
                 }
-                int32_t M[40], N[40], Bt[40], K[40], KA[40], KB[40];
-                int nm = 0, nn = 0, nb = 0, nk = 0, nka = 0, nkb = 0;
+                // label classes; the class index is computed from the membership bits, so no branch depends on the data
+                int32_t cl[8][40];  // 1 M, 2 N, 3 Bt (output labels);  4 KA, 5 K, 6 KB (reduced);  0, 7: dropped
+                int cn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
                 // output labels in the order of their positions in C (every output label belongs to A or B) ...
                 for (int i = 0; i < rc; ++i) {
                     const int32_t l = lc[i];
-                    if (inA[l] != sN) N[nn++] = l;
-                    else if (inB[l] != sN) M[nm++] = l;
-                    else Bt[nb++] = l;
+                    const int k = (int)(inA[l] == sN) | ((int)(inB[l] == sN) << 1);
+                    cl[k][cn[k]++] = l;
                 }
                 // ... reduced labels in label order
-                for (int q = 0; q < lab_n[A]; ++q) {
+                for (int q = 0, n = lab_n[A]; q < n; ++q) {
                     const int32_t l = labp(A)[q];
-                    if (!in_c(l)) (inB[l] == sN ? K[nk++] : KA[nka++]) = l;
+                    const int k = in_c(l) ? 7 : 4 + (int)(inB[l] == sN);
+                    cl[k][cn[k]++] = l;
                 }
-                for (int q = 0; q < lab_n[B]; ++q) {
+                cn[7] = 0;
+                for (int q = 0, n = lab_n[B]; q < n; ++q) {
                     const int32_t l = labp(B)[q];
-                    if (!in_c(l) && inA[l] != sN) KB[nkb++] = l;
+                    const int k = (in_c(l) | (inA[l] == sN)) ? 7 : 6;
+                    cl[k][cn[k]++] = l;
                 }
+                int32_t *M = cl[1], *N = cl[2], *Bt = cl[3], *K = cl[5], *KA = cl[4], *KB = cl[6];
+                const int nm = cn[1], nn = cn[2], nb = cn[3], nk = cn[5], nka = cn[4], nkb = cn[6];
                 // M / N: group the labels by their class inside the producing child so that the low address bits of
                 // the operand form a run of the child's own tile labels (coalesced stores in the child): the child's
                 // larger output-only class first, then its other one, batch labels of the child last; then by position in C
@@ -1194,7 +1224,9 @@ struct PlanCompiler : CompilerArrays {
                 s.sa = c.tm;
                 s.sb = c.tn;
                 s.pad = c.kfirst;  // reduction bit 0 is address bit 0 of both operands, the other K bits start at sa+1 / sb+1
-                {
+                if (is_tiny[x]) {  // recorded while the layouts were written
+                    std::memcpy(s.a_shift, tiny_shift.data() + (size_t)x * 32, 32);
+                } else {
                     // position of each output label in A / B: stamp the (short) output, then walk A and B once; labels
                     // that are reduced land in a spare slot instead of taking a branch
                     uint8_t sh[2][32];
