@@ -20,6 +20,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -45,6 +46,63 @@ struct BlobChunk {
 };
 }  // namespace
 
+// A loop the launching thread shares with the call's compile workers: while a call is being compiled, the workers look
+// here between two plans and take chunks of the loop (serialising descriptor blobs into pinned memory is the launching
+// thread's largest serial cost, profiles/x3_e2e_cfg2_*.json).  Everything is under one mutex: a few dozen chunk
+// hand-outs per batch.
+struct HelperJob {
+    std::mutex mu;
+    std::function<void(int64_t, int64_t)> fn;  // [begin, end)
+    int64_t n = 0, next = 0, grain = 1, pending = 0;  // pending = chunks handed out and not finished yet
+    bool active = false;
+    bool has_helpers = false;  // set by the call that runs worker threads
+    bool help_once() {
+        int64_t b, e;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!active || next >= n) return false;
+            b = next;
+            e = std::min(n, b + grain);
+            next = e;
+            ++pending;
+        }
+        fn(b, e);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            --pending;
+        }
+        return true;
+    }
+    // owner: runs fn over [0, count) with whoever helps, returns when every chunk is finished
+    void run(int64_t count, int64_t chunk, std::function<void(int64_t, int64_t)> f) {
+        if (!has_helpers || count <= chunk) {
+            f(0, count);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = std::move(f);
+            n = count;
+            next = 0;
+            grain = std::max<int64_t>(1, chunk);
+            pending = 0;
+            active = true;
+        }
+        while (help_once()) {
+        }
+        for (;;) {
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (pending == 0) {
+                    active = false;
+                    break;
+                }
+            }
+            std::this_thread::yield();
+        }
+    }
+};
+
 struct tb_ctx {
     // ---- multi-GPU context (tb_init_multi): one sub-context per device, this object only coordinates
     std::vector<tb_ctx*> subs;
@@ -59,6 +117,9 @@ struct tb_ctx {
     std::thread reaper;  // frees the host side of the previous call's temporary plans that do not go back to the pool
     // temporary plans of tb_contract_networks / tb_stream_push are recycled: the next call compiles into the same objects
     // (arrays keep their capacity), so a steady stream of calls neither allocates nor frees host memory per branch
+    void* permute_buf = nullptr;  // tb_permute_bits: source | destination, kept between calls
+    size_t permute_cap = 0;
+    HelperJob helper;
     std::mutex pool_mu;
     std::vector<tb_plan*> plan_pool;
     static constexpr size_t kPlanPoolMax = 1u << 15;  // ~30 KB of descriptors each for sc 20 branches
@@ -468,14 +529,19 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
         int rc = acquire_slot(ctx, bytes, 0, &sl);
         if (rc) return rc;
         size_t o = 0;
+        std::vector<size_t> at(pos - first);
         for (size_t j = first; j < pos; ++j) {
-            write_blob(todo[j]->p, (uint8_t*)sl->h + o);
+            at[j - first] = o;
             todo[j]->p.d_blob = (uint8_t*)ck->d + ck->used + o;
             todo[j]->p.owner = ctx;
             link_resident(ctx, todo[j]->p);
             ck->live++;
             o += bsz[j];
         }
+        // serialise into the pinned staging buffer; the call's compile workers take chunks of this loop
+        ctx->helper.run((int64_t)(pos - first), 8, [&](int64_t b, int64_t e) {
+            for (int64_t q = b; q < e; ++q) write_blob(todo[first + (size_t)q]->p, (uint8_t*)sl->h + at[(size_t)q]);
+        });
         TB_CUDA(ctx, cudaMemcpyAsync((uint8_t*)ck->d + ck->used, sl->h, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
         TB_CUDA(ctx, cudaEventRecord(sl->ev, ctx->copy_stream));
         sl->busy = true;
@@ -1507,6 +1573,7 @@ int tb_shutdown(tb_ctx* ctx) {
     }
     ctx->resident = nullptr;
     if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->permute_buf) cudaFree(ctx->permute_buf);
     for (auto& c : ctx->chunks)
         if (c.d) cudaFree(c.d);
     for (auto& sl : ctx->slots) {
@@ -1711,8 +1778,11 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
     const uint32_t flags = ctx->opts.plan_flags | TB_PLAN_TEMPORARY;
     // plan compilation runs on worker threads, in index order; the calling thread uploads and launches batch b
     // while the workers are already compiling batch b+1 (the GPU meanwhile executes batch b-1)
+    std::atomic<bool> enqueued_all{false};
     auto worker = [&]() {
         for (;;) {
+            while (ctx->helper.help_once()) {
+            }
             int64_t i = next.fetch_add(1);
             if (i >= n) break;
             if (!abort.load(std::memory_order_relaxed) && nets[i].n_leaves != 0) {
@@ -1721,8 +1791,20 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
             }
             done[i].store(1, std::memory_order_release);
         }
+        // nothing left to compile: keep helping the launching thread until the last batch is enqueued
+        while (!enqueued_all.load(std::memory_order_acquire))
+            if (!ctx->helper.help_once()) std::this_thread::yield();
     };
     ThreadGroup th;
+    struct HelpersScope {  // the helper loop is live exactly while the workers run
+        tb_ctx* c;
+        std::atomic<bool>& all;
+        ~HelpersScope() {
+            all.store(true, std::memory_order_release);
+            c->helper.has_helpers = false;
+        }
+    } helpers_scope{ctx, enqueued_all};
+    ctx->helper.has_helpers = nthreads > 1;
     for (int t = 0; t < nthreads - 1; ++t) th.spawn(worker);
     ctx->call_wave = wave_for_call(ctx, n, 0.0);  // refined from the first compiled batch below
     // TB_BATCH_MAX (experiments): upper bound of a pipeline batch; smaller batches keep the GPU closer behind the
@@ -1781,6 +1863,7 @@ int networks_enqueue(tb_ctx* ctx, const tb_network* nets, int64_t n, int64_t n_r
         trace.batch(ctx, lo, hi, t_ready, now_ms() - t_c0);
     }
     abort.store(rc != TB_OK);
+    enqueued_all.store(true, std::memory_order_release);
     th.join();
     trace.dump(ctx, now_ms() - t_c0);
     ctx->host_ms[0] = t_wait;  // time the launching thread spent waiting for the compiler threads
@@ -2494,12 +2577,23 @@ int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const 
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     PermuteDesc d{};
     d.rank = (uint8_t)rank;
-    const int Lb = std::min(rank, 5);
+    // tile = the 6 low source bits (256-byte reads) + the source bits that feed the 6 low destination bits (256-byte
+    // writes), filled up with the lowest remaining bits to 2^12 elements: a permutation that leaves the low bits alone
+    // (the identity at the extreme) still moves 16 KB per CTA instead of 128 bytes
+    const int Lb = std::min(rank, 6);
     std::vector<int> in_tile(rank, 0);
+    int n_tile = 0;
     for (int i = 0; i < Lb; ++i) {
-        in_tile[i] = 1;        // low source bits
+        n_tile += !in_tile[i];
+        in_tile[i] = 1;  // low source bits
+        n_tile += !in_tile[perm[i]];
         in_tile[perm[i]] = 1;  // source bits feeding the low destination bits
     }
+    for (int b = 0; b < rank && n_tile < 12; ++b)
+        if (!in_tile[b]) {
+            in_tile[b] = 1;
+            ++n_tile;
+        }
     std::vector<int> tsrc, gsrc;
     for (int b = 0; b < rank; ++b) (in_tile[b] ? tsrc : gsrc).push_back(b);
     d.u = (uint8_t)tsrc.size();
@@ -2518,14 +2612,20 @@ int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const 
         d.grid_dst_bit[j] = (uint8_t)dst_of_src[gsrc[j]];
     }
     size_t bytes = ((size_t)1 << rank) * 4;
-    void *din = nullptr, *dout = nullptr;
-    TB_CUDA(ctx, cudaMalloc(&din, bytes));
-    cudaError_t e = cudaMalloc(&dout, bytes);
-    if (e != cudaSuccess) {
-        cudaFree(din);
-        return set_err(ctx, TB_ERR_OUT_OF_MEMORY, cudaGetErrorString(e));
+    const size_t half_cap = (bytes + 255) / 256 * 256;
+    if (ctx->permute_cap < 2 * half_cap) {  // the scratch pair is kept: repeated calls do not allocate
+        if (ctx->permute_buf) cudaFree(ctx->permute_buf);
+        ctx->permute_buf = nullptr;
+        ctx->permute_cap = 0;
+        cudaError_t ea = cudaMalloc(&ctx->permute_buf, 2 * half_cap);
+        if (ea != cudaSuccess) {
+            cudaGetLastError();
+            return set_err(ctx, TB_ERR_OUT_OF_MEMORY, cudaGetErrorString(ea));
+        }
+        ctx->permute_cap = 2 * half_cap;
     }
-    e = cudaMemcpyAsync(din, in, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    void *din = ctx->permute_buf, *dout = (uint8_t*)ctx->permute_buf + half_cap;
+    cudaError_t e = cudaMemcpyAsync(din, in, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         cudaEventRecord(ctx->ev0, ctx->stream);
         k_permute_bits<<<(unsigned)(1u << d.ng), 256, 0, ctx->stream>>>((const uint32_t*)din, (uint32_t*)dout, d);
@@ -2540,8 +2640,6 @@ int tb_permute_bits(tb_ctx* ctx, const void* in, void* out, int32_t rank, const 
         ctx->last_ms = ms;
         ctx->last_launches = 1;
     }
-    cudaFree(din);
-    cudaFree(dout);
     if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
     return TB_OK;
 } TB_CATCH(ctx)

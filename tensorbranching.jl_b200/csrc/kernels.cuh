@@ -1687,7 +1687,7 @@ struct PermuteDesc {
 };
 
 __global__ void __launch_bounds__(256) k_permute_bits(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, PermuteDesc d) {
-    __shared__ uint32_t tile[1024 + 32];
+    __shared__ uint32_t tile[4096 + 128];  // 2^u <= 4096 elements, one pad word per 32
     const int tid = threadIdx.x;
     const uint64_t g = blockIdx.x;
     uint64_t sbase = 0, dbase = 0;

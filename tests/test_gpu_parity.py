@@ -282,12 +282,14 @@ def test_batch_api_and_max(tb, engine):
         assert np.array_equal(v3, vals) and not st3.any() and mx3 == mx
 
 
-@pytest.mark.parametrize("rank", [0, 1, 3, 7, 12, 20])
+@pytest.mark.parametrize("rank", [0, 1, 3, 7, 11, 12, 13, 20, 22])
 def test_permute_bits(tb, engine, rank):
     rng = np.random.default_rng(rank)
     x = rng.integers(-1000, 1000, size=1 << rank, dtype=np.int32)
-    for trial in range(3):
-        perm = list(rng.permutation(rank)) if trial else list(range(rank))[::-1]
+    # reversal, identity (no bit moves: the tile is filled up with the low bits), a rotation, random permutations
+    perms = [list(range(rank))[::-1], list(range(rank)), [(i + 5) % max(rank, 1) for i in range(rank)],
+             list(rng.permutation(rank)), list(rng.permutation(rank))]
+    for perm in perms:
         perm = [int(v) for v in perm]
         got = engine.permute_bits(x, perm)
         dst = np.arange(1 << rank, dtype=np.int64)
