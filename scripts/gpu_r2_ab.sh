@@ -1,17 +1,26 @@
 #!/bin/bash
-# A/B on one box: round-1 build (ab_r1/) vs this tree, level-synchronous and dataflow executors, alternating
-mkdir -p gpurun_out/r2ab
+# A/B: A operand of k_gemm2h through LDS.128 when mp == 1 (in-tree build) against the previous build (ab_head/)
+O=gpurun_out/r2ab; mkdir -p $O; rm -f $O/*
 for rep in 1 2; do
-  (cd ab_r1 && timeout 300 python bench.py --workload cfg2 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > ../gpurun_out/r2ab/r1_$rep.json 2> ../gpurun_out/r2ab/r1_$rep.err)
-  TB_LEVEL_SYNC=1 timeout 300 python bench.py --workload cfg2 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r2ab/ls_$rep.json 2> gpurun_out/r2ab/ls_$rep.err
-  timeout 300 python bench.py --workload cfg2 --steps 20 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/r2ab/df_$rep.json 2> gpurun_out/r2ab/df_$rep.err
+for v in new head; do
+  if [ $v = head ]; then export TBCUDA_LIB=$PWD/ab_head/libtbcuda.so; else unset TBCUDA_LIB; fi
+  timeout 300 python bench.py --workload cfg2 --steps 20 --warmup 5 --no-other-configs --no-e2e --cpu-budget 0 > $O/${v}_cfg2_$rep.json 2> $O/${v}_cfg2_$rep.err
+  timeout 300 python bench.py --workload cfg5 --steps 20 --warmup 5 --no-other-configs --no-e2e --cpu-budget 0 > $O/${v}_cfg5_$rep.json 2> $O/${v}_cfg5_$rep.err
+  timeout 300 python bench.py --workload cfg3 --steps 20 --warmup 5 --no-other-configs --no-e2e --cpu-budget 0 > $O/${v}_cfg3_$rep.json 2> $O/${v}_cfg3_$rep.err
 done
-tail -c 300 gpurun_out/r2ab/*.err
+done
+for v in new head; do
+  if [ $v = head ]; then export TBCUDA_LIB=$PWD/ab_head/libtbcuda.so; else unset TBCUDA_LIB; fi
+  timeout 600 python bench.py --workload cfg4 --max-branches 8 --steps 5 --warmup 3 --no-other-configs --no-e2e --cpu-budget 0 > $O/${v}_cfg4.json 2> $O/${v}_cfg4.err
+done
+unset TBCUDA_LIB
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_baseline_configs.py -m gpu -x -q 2>&1 | tail -2
+tail -c 300 $O/*.err | tail -20
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r2ab/*.json')):
     try:
-        d=json.loads(open(f).read().strip().splitlines()[-1])
-        print(f.split('/')[-1], 'ms',round(d['ms_per_step'],3),'median',round(d['ms_per_step_median_rank0'],3),'share',{k:round(v,2) for k,v in d['roofline']['share_of_step'].items()})
+        d=json.loads([l for l in open(f).read().strip().splitlines() if l.startswith('{')][-1])
+        print(f.split('/')[-1], 'ms', round(d['ms_per_step'],4), 'frac', d['roofline'].get('frac'), d.get('agrees_with_golden'))
     except Exception as e: print(f,'ERR',e)
 PY

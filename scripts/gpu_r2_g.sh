@@ -7,6 +7,7 @@ timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_default.js
 timeout 600 python bench.py --workload cfg2 --weights f32 --steps 10 --warmup 3 --no-other-configs > $O/bench_cfg2_f32.json 2> $O/bench_cfg2_f32.err
 timeout 600 python bench.py --workload cfg1 --steps 20 --warmup 3 --no-other-configs > $O/bench_cfg1.json 2> $O/bench_cfg1.err
 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.txt 2>&1; tail -2 $O/smoke.txt
+timeout 300 python scripts/permute_bw.py > $O/permute_bw.txt 2>&1; cat $O/permute_bw.txt
 for f in $O/*.err; do echo "== $f"; tail -c 400 $f; done
 python - <<'PY'
 import json,glob
