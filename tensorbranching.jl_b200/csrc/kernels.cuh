@@ -1410,59 +1410,45 @@ __global__ void __launch_bounds__(G2_THREADS, 2) k_gemm2h(const BigInst* __restr
             uint32_t ua = a_thr + (uint32_t)stage * (uint32_t)(STAGE_ELEMS * 2);
             uint32_t ub = b_thr + (uint32_t)stage * (uint32_t)(STAGE_ELEMS * 2);
             uint32_t a[8], b0[8], b1[8];
-            // A words of a thread: tile bits {0, mp, tm-1} of m.  With mp == 1 (the common case) the four words of each
-            // half are contiguous: one LDS.128 instead of two LDS.64 whose lanes (stride 16 bytes, 8 bytes each) hit
-            // every bank twice.
-#define G2H_LDA_LO_V2(addr)                                                                                         \
+#define G2H_LDA_LO(addr)                                                                                            \
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[0]), "=r"(a[1]) : "r"(addr));                           \
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[2]), "=r"(a[3]) : "r"((addr) + a_p));
-#define G2H_LDA_HI_V2(addr)                                                                                         \
+#define G2H_LDA_HI(addr)                                                                                            \
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[4]), "=r"(a[5]) : "r"((addr) + a_hi));                  \
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(a[6]), "=r"(a[7]) : "r"((addr) + a_hi + a_p));
-#define G2H_LDA_LO_V4(addr) \
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
-#define G2H_LDA_HI_V4(addr) \
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "r"((addr) + a_hi));
 #define G2H_LDB(bb, addr)                                                                                           \
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(bb[0]), "=r"(bb[1]), "=r"(bb[2]), "=r"(bb[3]) : "r"(addr)); \
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(bb[4]), "=r"(bb[5]), "=r"(bb[6]), "=r"(bb[7]) : "r"((addr) + b_hi));
 #define G2H_MATH(i0, bb)                                                                                            \
     _Pragma("unroll") for (int i = i0; i < i0 + 4; ++i)                                                              \
         _Pragma("unroll") for (int j = 0; j < 8; ++j) acc[i][j] = __viaddmax_s16x2(a[i], bb[j], acc[i][j]);
-#define G2H_KLOOP(LDA_LO, LDA_HI)                                                                                   \
-    {                                                                                                               \
-        LDA_LO(ua)                                                                                                  \
-        G2H_LDB(b0, ub)                                                                                             \
-        int kk = 0;                                                                                                 \
-        _Pragma("unroll 1") for (; kk + 2 <= KP_ROWS; kk += 2) {                                                    \
-            LDA_HI(ua)                                                                                              \
-            G2H_LDB(b1, ub + rowB)                                                                                  \
-            G2H_MATH(0, b0)                                                                                         \
-            LDA_LO(ua + rowA)                                                                                       \
-            G2H_MATH(4, b0)                                                                                         \
-            ua += rowA;                                                                                             \
-            ub += rowB;                                                                                             \
-            LDA_HI(ua)                                                                                              \
-            G2H_LDB(b0, ub + rowB) /* the last one reads one row past the chunk (still shared memory): discarded */ \
-            G2H_MATH(0, b1)                                                                                         \
-            LDA_LO(ua + rowA)                                                                                       \
-            G2H_MATH(4, b1)                                                                                         \
-            ua += rowA;                                                                                             \
-            ub += rowB;                                                                                             \
-        }                                                                                                           \
-        if (kk < KP_ROWS) { /* a single k-pair row (kc == 1) */                                                     \
-            LDA_HI(ua)                                                                                              \
-            G2H_MATH(0, b0)                                                                                         \
-            G2H_MATH(4, b0)                                                                                         \
-        }                                                                                                           \
-    }
-            if (a_p == 8u) G2H_KLOOP(G2H_LDA_LO_V4, G2H_LDA_HI_V4)
-            else G2H_KLOOP(G2H_LDA_LO_V2, G2H_LDA_HI_V2)
-#undef G2H_KLOOP
-#undef G2H_LDA_LO_V2
-#undef G2H_LDA_HI_V2
-#undef G2H_LDA_LO_V4
-#undef G2H_LDA_HI_V4
+            G2H_LDA_LO(ua)
+            G2H_LDB(b0, ub)
+            int kk = 0;
+#pragma unroll 1
+            for (; kk + 2 <= KP_ROWS; kk += 2) {
+                G2H_LDA_HI(ua)
+                G2H_LDB(b1, ub + rowB)
+                G2H_MATH(0, b0)
+                G2H_LDA_LO(ua + rowA)
+                G2H_MATH(4, b0)
+                ua += rowA;
+                ub += rowB;
+                G2H_LDA_HI(ua)
+                G2H_LDB(b0, ub + rowB)  // the last one reads one row past the chunk (still shared memory): discarded
+                G2H_MATH(0, b1)
+                G2H_LDA_LO(ua + rowA)
+                G2H_MATH(4, b1)
+                ua += rowA;
+                ub += rowB;
+            }
+            if (kk < KP_ROWS) {  // a single k-pair row (kc == 1)
+                G2H_LDA_HI(ua)
+                G2H_MATH(0, b0)
+                G2H_MATH(4, b0)
+            }
+#undef G2H_LDA_LO
+#undef G2H_LDA_HI
 #undef G2H_LDB
 #undef G2H_MATH
             __syncwarp();
