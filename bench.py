@@ -166,14 +166,18 @@ class ClockSampler:
 
 def lpt_shards(costs, n):
     """longest-processing-time-first assignment of units to n ranks."""
-    order = np.argsort(-np.asarray(costs), kind="stable")
-    load = np.zeros(n)
-    owner = np.zeros(len(costs), dtype=np.int64)
+    import heapq
+
+    cost = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-cost, kind="stable").tolist()
+    cost = cost.tolist()
+    heap = [(0.0, r) for r in range(n)]  # (load, rank): the least-loaded rank, the lowest rank among equals
+    owner = [0] * len(cost)
     for i in order:
-        r = int(np.argmin(load))
+        load, r = heapq.heappop(heap)
         owner[i] = r
-        load[r] += costs[i]
-    return owner
+        heapq.heappush(heap, (load + cost[i], r))
+    return np.asarray(owner, dtype=np.int64)
 
 
 def measured_peaks():

@@ -285,6 +285,15 @@ int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap
 int tb_contract_table(tb_ctx* ctx, tb_plan* plan, double* out_sizes, uint32_t* out_configs, int64_t cap, int32_t* out_labels,
                       int32_t* out_rank);
 
+/* The reduction step of the same table solver ([upstream, recalled] GenericTensorNetworks mis_compactify!, applied by
+ * OptimalBranchingMIS reduced_alpha_configs before the table is built; reached from src/branch.jl:79): boundary
+ * configuration a is dominated -- and its row dropped from the branching table -- when some other configuration b chooses
+ * a subset of a's boundary vertices (b & a == b, b != a) and sizes[b] >= sizes[a].  sizes = the 2^rank sizes returned by
+ * tb_contract_table / tb_contract_tensor (index bit i = boundary vertex out_labels[i]; -inf = infeasible);
+ * out_keep[a] = 1 for the rows that survive, 0 for dominated or infeasible ones.  Runs on the device as a subset-max
+ * transform (rank + 1 launches, O(rank 2^rank)) instead of the reference's all-pairs loop (O(4^rank)). */
+int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t* out_keep);
+
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap,

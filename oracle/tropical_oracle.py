@@ -281,3 +281,18 @@ def contraction_peak_memory(ixs, tree) -> float:
     sys.setrecursionlimit(max(sys.getrecursionlimit(), 4 * n_leaves + 100))
     walk(n_leaves + len(left) - 1)
     return float(np.log2(max(tscs)))
+
+
+def mis_compactify_keep(sizes):
+    """[upstream, recalled] GenericTensorNetworks `mis_compactify!`, as OptimalBranchingMIS `reduced_alpha_configs` applies
+    it to the open-boundary size tensor before `branching_table` builds its rows (reached from
+    /root/reference/src/branch.jl:79): entry a is set to tropical zero iff some entry b != a chooses a subset of a's
+    boundary vertices ((b & a) == b) and sizes[b] >= sizes[a].  Plain all-pairs restatement over the flat table (index bit
+    i = boundary vertex i); returns the boolean mask of the entries that survive (infeasible entries do not)."""
+    sizes = np.asarray(sizes, dtype=np.float64).ravel()
+    keep = np.zeros(sizes.size, dtype=bool)
+    for a in range(sizes.size):
+        if sizes[a] == -np.inf:
+            continue
+        keep[a] = not any(b != a and (b & a) == b and sizes[b] >= sizes[a] for b in range(a))
+    return keep

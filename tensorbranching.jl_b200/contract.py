@@ -242,6 +242,28 @@ class Engine:
                                             cfgs.ctypes.data_as(C.POINTER(C.c_uint32)), n, labels, C.byref(rank)), self.handle)
         return list(labels[:rank.value]), sizes, cfgs
 
+    def compactify_table(self, sizes: np.ndarray) -> np.ndarray:
+        """tb_compactify_table (mis_compactify of the reference's table solver): which of the 2^rank boundary configurations
+        survive -- feasible and not dominated by a configuration that chooses a subset of their boundary vertices and is at
+        least as large.  -> bool[2^rank]"""
+        sizes = np.ascontiguousarray(sizes, dtype=np.float64)
+        rank = int(sizes.size).bit_length() - 1
+        if sizes.size != 1 << rank:
+            raise ValueError("a boundary table has 2^rank entries")
+        keep = np.zeros(sizes.size, dtype=np.uint8)
+        L.check(self._lib.tb_compactify_table(self.handle, rank, sizes.ctypes.data_as(C.POINTER(C.c_double)),
+                                              keep.ctypes.data_as(C.POINTER(C.c_uint8))), self.handle)
+        return keep.astype(bool)
+
+    def branching_table(self, plan: Plan):
+        """The table `branching_table(p, TensorNetworkSolver(), region)` hands to the set-cover solver (src/branch.jl:79),
+        with ONE optimal configuration per row: contract the region's network (size + configuration elements, boundary
+        vertices open), drop the dominated boundary configurations.
+        -> (boundary labels bit-0-first, rows) with rows = [(boundary bits, size, vertex mask of one optimal set), ...]"""
+        labels, sizes, cfgs = self.contract_table(plan)
+        keep = self.compactify_table(sizes)
+        return labels, [(int(a), float(sizes[a]), int(cfgs[a])) for a in np.nonzero(keep)[0]]
+
     # -- batches -----------------------------------------------------------------------------
     def contract_plans(self, plans, r: Optional[np.ndarray] = None):
         """tb_contract_batch over resident plans (None = empty graph).  `plans` may be a PlanBatch: the handle array and

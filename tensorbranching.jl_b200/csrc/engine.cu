@@ -2512,6 +2512,46 @@ int tb_contract_table(tb_ctx* ctx, tb_plan* plan, double* out_sizes, uint32_t* o
     return TB_OK;
 } TB_CATCH(ctx)
 
+int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t* out_keep) try {
+    if (!ctx || !sizes || !out_keep) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "NULL argument");
+    if (!ctx->subs.empty()) return tb_compactify_table(ctx->subs[0], rank, sizes, out_keep);
+    if (rank < 0 || rank > 30) return set_err(ctx, TB_ERR_UNSUPPORTED, "rank must be in [0, 30]");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t n = (int64_t)1 << rank;
+    // device scratch: sizes | subset maxima | keep flags
+    const size_t bytes = (size_t)n * (2 * sizeof(double) + 1);
+    uint8_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_err(ctx, TB_ERR_OUT_OF_MEMORY, cudaGetErrorString(e));
+    }
+    double* d_sizes = (double*)d;
+    double* d_z = d_sizes + n;
+    uint8_t* d_keep = (uint8_t*)(d_z + n);
+    e = cudaMemcpyAsync(d_sizes, sizes, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_z, d_sizes, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        for (int bit = 0; bit < rank; ++bit)
+            k_subset_max_stage<<<(unsigned)((n / 2 + 255) / 256), 256, 0, ctx->stream>>>(d_z, bit, n / 2);
+        k_table_keep<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_sizes, d_z, rank, d_keep, n);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_keep, d_keep, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        ctx->last_ms = ms;
+        ctx->last_launches = rank + 1;
+    }
+    cudaFree(d);
+    if (e != cudaSuccess) return set_err(ctx, TB_ERR_CUDA, cudaGetErrorString(e));
+    return TB_OK;
+} TB_CATCH(ctx)
+
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
     if (out_device_ms) *out_device_ms = ctx->last_ms;

@@ -1664,6 +1664,29 @@ __global__ void k_to_config(const long long* __restrict__ src, uint32_t* __restr
     if (i < n) dst[i] = (src[i] >> 32) <= -(1ll << 29) ? 0u : (uint32_t)(src[i] & 0xffffffffll);
 }
 
+// Branching-table reduction (mis_compactify of the reference's table solver): one stage of the subset-max transform.
+// After the stages of all bits, z[a] = max over b subset-of a of the input.  A thread owns the pair (a, a | 1 << bit).
+__global__ void k_subset_max_stage(double* __restrict__ z, int bit, int64_t n_pairs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pairs) return;
+    const int64_t low = i & (((int64_t)1 << bit) - 1);
+    const int64_t a = ((i >> bit) << (bit + 1)) | low;
+    const int64_t b = a | ((int64_t)1 << bit);
+    z[b] = fmax(z[b], z[a]);
+}
+
+// keep[a] = 1 iff entry a is feasible and no entry b that chooses a STRICT subset of a's boundary vertices is at least as
+// large: the strict subsets of a are the subsets of a without vertex i, for the vertices i of a.
+__global__ void k_table_keep(const double* __restrict__ sizes, const double* __restrict__ z, int rank, uint8_t* __restrict__ keep, int64_t n) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const double v = sizes[a];
+    double best = -INFINITY;
+    for (int i = 0; i < rank; ++i)
+        if ((a >> i) & 1) best = fmax(best, z[a ^ ((int64_t)1 << i)]);
+    keep[a] = (v > -INFINITY && !(best >= v)) ? 1 : 0;
+}
+
 template <typename T>
 __global__ void k_to_double(const T* __restrict__ src, double* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

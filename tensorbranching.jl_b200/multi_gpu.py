@@ -20,15 +20,18 @@ import numpy as np
 def shard_lpt(costs: Sequence[float], world: int) -> np.ndarray:
     """Longest-processing-time-first: sort units by cost, give each to the least-loaded rank.
     Returns owner[i] in [0, world).  Deterministic, identical on every rank."""
-    costs = np.asarray(costs, dtype=np.float64)
-    order = np.argsort(-costs, kind="stable")
-    load = np.zeros(world)
-    owner = np.zeros(len(costs), dtype=np.int64)
+    import heapq
+
+    cost = np.asarray(costs, dtype=np.float64)
+    order = np.argsort(-cost, kind="stable").tolist()
+    cost = cost.tolist()
+    heap = [(0.0, r) for r in range(world)]  # (load, rank): the least-loaded rank, the lowest rank among equals
+    owner = [0] * len(cost)
     for i in order:
-        r = int(np.argmin(load))
+        load, r = heapq.heappop(heap)
         owner[i] = r
-        load[r] += costs[i]
-    return owner
+        heapq.heappush(heap, (load + cost[i], r))
+    return np.asarray(owner, dtype=np.int64)
 
 
 def branch_cost(branch) -> float:

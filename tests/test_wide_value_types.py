@@ -122,3 +122,56 @@ def test_gpu_size_config_table(tb, engine, n, seed, n_open):
     # the closed network: the scalar is the MIS size, through tb_contract as for any plan
     q = tb.Plan(to_sliced(root), value_type=tb.TB_VALUE_SIZE_CONFIG, engine=engine)
     assert engine.contract(q) == O.solve_slice(root, np.float64)
+
+
+def _keep_by_definition(sizes):
+    return O.mis_compactify_keep(sizes)
+
+
+def test_oracle_compactify_small_cases():
+    inf = np.inf
+    # one boundary vertex: choosing it survives only if it gains something
+    assert list(O.mis_compactify_keep([2.0, 2.0])) == [True, False]
+    assert list(O.mis_compactify_keep([2.0, 3.0])) == [True, True]
+    # two boundary vertices (index = b1 b0): 3 is dominated by 1, 2 is infeasible
+    assert list(O.mis_compactify_keep([1.0, 2.0, -inf, 2.0])) == [True, True, False, False]
+    # the empty configuration is infeasible: nothing dominates the singletons
+    assert list(O.mis_compactify_keep([-inf, 1.0, 1.0, 1.0])) == [False, True, True, False]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rank,seed", [(0, 0), (1, 1), (3, 2), (6, 3), (9, 4), (11, 5)])
+def test_gpu_compactify_random_tables(tb, engine, rank, seed):
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(0, 6, size=1 << rank).astype(np.float64)
+    sizes[rng.random(sizes.size) < 0.3] = -np.inf  # infeasible boundary configurations
+    assert np.array_equal(engine.compactify_table(sizes), _keep_by_definition(sizes))
+    # ties count as dominated; an all-equal table keeps only the empty configuration
+    flat = np.full(1 << rank, 2.0)
+    want = np.zeros(1 << rank, dtype=bool)
+    want[0] = True
+    assert np.array_equal(engine.compactify_table(flat), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,n_open", [(10, 1, 3), (20, 3, 5), (24, 4, 6), (32, 6, 8)])
+def test_gpu_branching_table(tb, engine, n, seed, n_open):
+    """the table the set-cover solver receives: surviving boundary configurations, one optimal set each"""
+    root, br, open_labels = _region(tb, n, seed, n_open)
+    p = tb.Plan(br, value_type=tb.TB_VALUE_SIZE_CONFIG, engine=engine)
+    labels, rows = engine.branching_table(p)
+    _, sizes, cfgs = engine.contract_table(p)
+    keep = _keep_by_definition(sizes)
+    assert [a for a, _, _ in rows] == list(np.nonzero(keep)[0])
+    adj = {(min(u, v), max(u, v)) for u, v in root.edges}
+    for a, size, mask in rows:
+        chosen = [v for v in range(root.nv) if (mask >> v) & 1]
+        assert len(chosen) == size == sizes[a]
+        assert all((min(u, v), max(u, v)) not in adj for i, u in enumerate(chosen) for v in chosen[i + 1:])
+        for q, l in enumerate(labels):  # the set agrees with its boundary configuration
+            assert ((mask >> l) & 1) == ((a >> q) & 1)
+    # every boundary configuration is covered by a surviving row that chooses a subset of its boundary vertices and is
+    # at least as large (that is what makes dropping the dominated rows safe)
+    for a in range(sizes.size):
+        if sizes[a] > -np.inf:
+            assert any((b & a) == b and sb >= sizes[a] for b, sb, _ in rows)
