@@ -122,7 +122,9 @@ struct tb_ctx {
     HelperJob helper;
     std::mutex pool_mu;
     std::vector<tb_plan*> plan_pool;
-    static constexpr size_t kPlanPoolMax = 1u << 15;  // ~30 KB of descriptors each for sc 20 branches
+    size_t plan_pool_bytes = 0;                             // host memory the pooled plans hold (array capacities)
+    static constexpr size_t kPlanPoolMax = 1u << 15;        // ~30 KB of descriptors each for sc 20 branches ...
+    static constexpr size_t kPlanPoolMaxBytes = 512u << 20;  // ... and never more than this in total
     tb_options opts{};
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -272,6 +274,7 @@ tb_plan* compile_temporary(tb_ctx* ctx, const tb_network& net, uint32_t flags, i
             if (!ctx->plan_pool.empty()) {
                 p = ctx->plan_pool.back();
                 ctx->plan_pool.pop_back();
+                ctx->plan_pool_bytes -= std::min(ctx->plan_pool_bytes, p->p.descriptor_capacity_bytes());
             }
         }
         if (!p) p = new tb_plan();
@@ -741,6 +744,10 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     std::vector<Launch> launches;
     auto align16 = [&]() { host.resize((host.size() + 15) / 16 * 16); };
     size_t first_solo_launch = (size_t)-1;
+    // scratch of the level-synchronous lists, reused by every level of every wave
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> ls_buckets;  // (level, kind) -> (member, step)
+    std::vector<BigInst> ls_insts, ls_sorted;
+    std::vector<uint32_t> ls_starts, ls_nk, ls_tiles, ls_ord;
     for (size_t wi = 0; wi < waves.size(); ++wi) {
         const Wave& w = waves[wi];
         if (wi == n_lane_waves) first_solo_launch = launches.size();
@@ -785,6 +792,16 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 launches.push_back(L);
             }
         }
+        // one pass over the members sorts their big steps into (level, kind) buckets -- member-major inside a bucket, as the
+        // launches list them -- instead of one scan of all members per level and kind
+        ls_buckets.resize(std::max(ls_buckets.size(), (size_t)(w.levels + 1) * 2));
+        for (auto& bk : ls_buckets) bk.clear();
+        for (size_t m = 0; m < w.members.size(); ++m) {
+            const Plan& P = plans[w.members[m]]->p;
+            for (int lv = 1; lv <= P.n_levels; ++lv)
+                for (int s = P.big_level_begin[lv]; s < P.big_level_begin[lv + 1]; ++s)
+                    ls_buckets[(size_t)lv * 2 + (P.big_steps[s].kind == KIND_GEMM ? 1 : 0)].push_back({(uint32_t)m, (uint32_t)s});
+        }
         if (ctx->dataflow && !wide) {
             // ---- dataflow: every big step of every member, level-major, in ONE persistent launch.  A tile waits on the
             // completion counters of the instances that produce its operands (BigInst::dep_a / dep_b) instead of on a
@@ -798,13 +815,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             std::vector<std::pair<uint32_t, uint32_t>> lvl;  // (member, step) of one level and kind
             for (int lv = 1; lv <= w.levels; ++lv) {
                 for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
-                    lvl.clear();
-                    for (size_t m = 0; m < w.members.size(); ++m) {
-                        const Plan& P = plans[w.members[m]]->p;
-                        if (lv > P.n_levels) continue;
-                        for (int s = P.big_level_begin[lv]; s < P.big_level_begin[lv + 1]; ++s)
-                            if (P.big_steps[s].kind == kind) lvl.push_back({(uint32_t)m, (uint32_t)s});
-                    }
+                    lvl = ls_buckets[(size_t)lv * 2 + (kind == KIND_GEMM ? 1 : 0)];
                     if (kind == KIND_GEMM)  // longest reductions first inside a level
                         std::stable_sort(lvl.begin(), lvl.end(), [&](const std::pair<uint32_t, uint32_t>& x, const std::pair<uint32_t, uint32_t>& y) {
                             return plans[w.members[x.first]]->p.big_steps[x.second].nk > plans[w.members[y.first]]->p.big_steps[y.second].nk;
@@ -822,7 +833,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                         bi.dep_a = da >= 0 ? inst_of[ms.first][(size_t)da] : -1;
                         bi.dep_b = db >= 0 ? inst_of[ms.first][(size_t)db] : -1;
                         inst_of[ms.first][ms.second] = (int32_t)insts.size();
-                        df_ops += std::ldexp(1.0, (int)P.big_log2_ops[ms.second]);
+                        df_ops += (double)(1ull << (int)P.big_log2_ops[ms.second]);  // log2 ops <= 62 (plan compiler)
                         df_bytes += P.big_bytes[ms.second];
                         insts.push_back(bi);
                         starts.push_back((uint32_t)tiles);
@@ -858,42 +869,46 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 L.bytes = df_bytes;
                 launches.push_back(L);
             }
-        } else
+        } else {
         for (int lv = 1; lv <= w.levels; ++lv) {
             for (int kind : {(int)KIND_GENERIC, (int)KIND_GEMM}) {
-                std::vector<BigInst> insts;
-                std::vector<uint32_t> starts, inst_nk, inst_tiles;
+                std::vector<BigInst>& insts = ls_insts;
+                std::vector<uint32_t>&starts = ls_starts, &inst_nk = ls_nk, &inst_tiles = ls_tiles;
+                insts.clear();
+                starts.clear();
+                inst_nk.clear();
+                inst_tiles.clear();
                 uint64_t tiles = 0;
                 double ls_ops = 0, ls_bytes = 0;
-                for (size_t m = 0; m < w.members.size(); ++m) {
+                for (const auto& ms : ls_buckets[(size_t)lv * 2 + (kind == KIND_GEMM ? 1 : 0)]) {
+                    const size_t m = ms.first;
+                    const int s = (int)ms.second;
                     const Plan& P = plans[w.members[m]]->p;
-                    if (lv > P.n_levels) continue;
                     uint8_t* blob = (uint8_t*)P.d_blob;
                     const BigStep* dsteps = (const BigStep*)(blob + P.big_blob_off);
-                    for (int s = P.big_level_begin[lv]; s < P.big_level_begin[lv + 1]; ++s) {
-                        if (P.big_steps[s].kind != kind) continue;
-                        BigInst bi{};
-                        bi.step = dsteps + s;
-                        bi.pool = blob;
-                        bi.arena = (uint8_t*)ctx->arena + w.base[m];
-                        bi.tile_start = (uint32_t)tiles;
-                        insts.push_back(bi);
-                        starts.push_back((uint32_t)tiles);
-                        inst_nk.push_back(P.big_steps[s].nk);
-                        inst_tiles.push_back(P.big_steps[s].n_tiles);
-                        tiles += P.big_steps[s].n_tiles;
-                        ls_ops += std::ldexp(1.0, (int)P.big_log2_ops[(size_t)s]);
-                        ls_bytes += P.big_bytes[(size_t)s];
-                    }
+                    BigInst bi{};
+                    bi.step = dsteps + s;
+                    bi.pool = blob;
+                    bi.arena = (uint8_t*)ctx->arena + w.base[m];
+                    bi.tile_start = (uint32_t)tiles;
+                    insts.push_back(bi);
+                    starts.push_back((uint32_t)tiles);
+                    inst_nk.push_back(P.big_steps[s].nk);
+                    inst_tiles.push_back(P.big_steps[s].n_tiles);
+                    tiles += P.big_steps[s].n_tiles;
+                    ls_ops += (double)(1ull << (int)P.big_log2_ops[(size_t)s]);
+                    ls_bytes += P.big_bytes[(size_t)s];
                 }
                 if (insts.empty()) continue;
                 if (tiles > 0x7fffffffull) return set_err(ctx, TB_ERR_UNSUPPORTED, "a level needs more than 2^31 CTAs");
                 if (kind == KIND_GEMM) {
                     // longest reductions first: the dynamic tile scheduler then fills the tail with short tiles
-                    std::vector<uint32_t> ord(insts.size());
+                    std::vector<uint32_t>& ord = ls_ord;
+                    ord.resize(insts.size());
                     for (size_t q = 0; q < ord.size(); ++q) ord[q] = (uint32_t)q;
                     std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return inst_nk[x] > inst_nk[y]; });
-                    std::vector<BigInst> si(insts.size());
+                    std::vector<BigInst>& si = ls_sorted;
+                    si.resize(insts.size());
                     uint64_t acc_t = 0;
                     for (size_t q = 0; q < ord.size(); ++q) {
                         si[q] = insts[ord[q]];
@@ -924,6 +939,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
                 L.bytes = ls_bytes;
                 launches.push_back(L);
             }
+        }
         }
         // finalize
         {
@@ -1269,12 +1285,19 @@ void release_temporary_plans(tb_ctx* ctx, std::vector<tb_plan*> plans, bool to_p
     if (to_pool) {  // compact temporaries (compile_temporary): the next call compiles into the same objects
         std::lock_guard<std::mutex> lk(ctx->pool_mu);
         size_t kept = 0;
-        for (tb_plan*& p : plans)
-            if (p && ctx->plan_pool.size() < tb_ctx::kPlanPoolMax) {
+        for (tb_plan*& p : plans) {
+            if (!p) {
+                ++kept;
+                continue;
+            }
+            const size_t bytes = p->p.descriptor_capacity_bytes();
+            if (ctx->plan_pool.size() < tb_ctx::kPlanPoolMax && ctx->plan_pool_bytes + bytes <= tb_ctx::kPlanPoolMaxBytes) {
                 ctx->plan_pool.push_back(p);
+                ctx->plan_pool_bytes += bytes;
                 p = nullptr;
                 ++kept;
             }
+        }
         if (kept == plans.size()) return;
     }
     if (ctx->reaper.joinable()) ctx->reaper.join();

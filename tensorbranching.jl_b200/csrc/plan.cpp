@@ -1442,7 +1442,7 @@ struct PlanCompiler : CompilerArrays {
                 }
                 big_index[t] = (int32_t)P.big_steps.size();
                 P.big_log2_ops.push_back((float)(rank_of(t) + c.nk + c.nka + c.nkb));
-                P.big_bytes.push_back((double)Plan::elem_size_of(vt) * (std::ldexp(1.0, rank_of(A)) + std::ldexp(1.0, rank_of(B)) + std::ldexp(1.0, rank_of(t))));
+                P.big_bytes.push_back((double)Plan::elem_size_of(vt) * ((double)(1ull << rank_of(A)) + (double)(1ull << rank_of(B)) + (double)(1ull << rank_of(t))));
                 P.big_dep_a.push_back(big_index[A]);  // -1 for leaves and fused subtrees
                 P.big_dep_b.push_back(big_index[B]);
                 P.big_steps.push_back(s);

@@ -79,6 +79,13 @@ struct Plan {
     // the part of a compiled plan the executor needs -- descriptors, launch geometry, statistics -- copied into `dst` with
     // exact-size arrays; layouts, the tensor table and the step records stay behind (temporaries of contract_slices)
     void copy_descriptors_to(Plan& dst) const;
+    // host memory held by the arrays copy_descriptors_to fills (capacities, so a recycled plan reports what it pins)
+    size_t descriptor_capacity_bytes() const {
+        return pool.capacity() * sizeof(uint64_t) + patches.capacity() * sizeof(PoolPatch) + sub_steps.capacity() * sizeof(SubStep) +
+               subtrees.capacity() * sizeof(SubTree) + big_steps.capacity() * sizeof(BigStep) +
+               big_level_begin.capacity() * sizeof(int32_t) + big_log2_ops.capacity() * sizeof(float) +
+               big_bytes.capacity() * sizeof(double) + (big_dep_a.capacity() + big_dep_b.capacity()) * sizeof(int32_t) + sizeof(Plan);
+    }
 
     // device residency (managed by the engine)
     tb_ctx* owner = nullptr;
