@@ -1085,7 +1085,11 @@ struct PlanCompiler : CompilerArrays {
                     if (!leaf[c]) lv = std::max(lv, P.level[c] + 1);
                 P.level[t] = lv;
                 const NodeCls& c = cls[t];
-                bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= MT_LOG && c.nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && c.nk >= 1 &&
+                static const int min_nk = [] {
+                    const char* e = getenv("TB_GEMM_MIN_NK");  // experiments: shorter reductions run as generic steps
+                    return e ? std::max(1, atoi(e)) : 1;
+                }();
+                bool gemm = !(P.flags & TB_PLAN_NO_GEMM) && c.nm >= MT_LOG && c.nn >= 3 && c.tm + c.tn >= MT_LOG + 6 && c.nk >= min_nk &&
                             c.nka == 0 && c.nkb == 0 && !leaf[lch[t]] && !leaf[rch[t]];
                 kind[t] = gemm ? KIND_GEMM : KIND_GENERIC;
                 P.n_levels = std::max(P.n_levels, lv);
