@@ -579,8 +579,11 @@ uint32_t dataflow_grid_cap(const tb_ctx* ctx) {
         return e ? atoi(e) : 0;
     }();
     if (forced > 0) return (uint32_t)forced;
+    // half of the CTA slots when several waves are in flight: two kernels co-reside, the others queue behind them.  An even
+    // share per lane (slots / 4) leaves each kernel too few CTAs to cover its own dependency stalls
+    // (profiles/x3_df_wave_lane_sweep.txt: cfg5 1.73 ms with 74 CTAs per kernel, 1.59 with 148, 1.58 with 296)
     const int slots = std::max(1, ctx->gemm2_ctas_per_sm) * ctx->sm_count;
-    return (uint32_t)std::max(1, slots / std::max(1, ctx->call_lanes));
+    return (uint32_t)std::max(1, slots / std::min(2, std::max(1, ctx->call_lanes)));
 }
 
 template <typename T>

@@ -297,3 +297,26 @@ def test_permute_bits(tb, engine, rank):
         for i, pbit in enumerate(perm):
             src |= ((dst >> i) & 1) << pbit
         assert np.array_equal(got, x[src])
+
+
+def test_interleaved_calls_reuse_pooled_plans(tb):
+    """tb_contract_networks keeps the plan objects of a call and compiles the next call's branches into them: calls with
+    different branch lists (other sizes, value types, empty graphs) must not see anything of their predecessors"""
+    eng = tb.Engine(0)
+    sets = []
+    for name in ["rr100_sc10_unit", "ksg8x8_sc6", "rr100_sc10_f32", "rr30_disconnected"]:
+        rec = load_golden(name + ".json")
+        sets.append((np.dtype(rec["element_type"]).type, [to_sliced(b) for b in golden_branches(rec)], np.asarray(rec["values"])))
+    for rep in range(3):
+        for et, brs, want in sets + sets[::-1]:
+            half = brs[: max(1, len(brs) // (rep + 1))]  # shrinking lists: some pooled objects stay unused
+            got = tb.contract_slices(half, et, True, engine=eng)
+            assert np.array_equal(got.astype(np.float64), want[: len(half)])
+    # the streaming entry point shares the pool
+    et, brs, want = sets[0]
+    with tb.BranchStream(eng, capacity=len(brs), element_type=et) as st:
+        st.push(brs[: len(brs) // 2])
+        st.push(brs[len(brs) // 2:])
+        vals = st.finish()
+    assert np.array_equal(np.asarray(vals, dtype=np.float64), want)
+    eng.close()
