@@ -89,13 +89,20 @@ __global__ void __launch_bounds__(256) k_f32(float* out, float a0, float b0) {
     float b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) b[j] = b0 + j * threadIdx.x;
+    // every operand changes every iteration through COMPILE-TIME indices: with a run-time index into a register array
+    // (the first version) each update costs a predicated copy per element, and those ISETP / FADD took issue slots from
+    // the measured instructions (it reported 6.9 Top/s, less than k_gemm2<float> achieves); with operands that stay
+    // unchanged the compiler drops the repeated max of an unchanged sum.  12 extra FADD per 32 ops go to the FMA pipe,
+    // the FMNMX of the measured pairs to the ALU pipe that bounds them.
     for (int it = 0; it < ITERS; ++it) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i * 8 + j] = fmaxf(__fadd_rn(a[i], b[j]), acc[i * 8 + j]);
-        a[it & 3] += 1.0f;
-        b[it & 7] += 0.5f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] += 1.0f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] += 0.5f;
     }
     float s = 0;
 #pragma unroll
