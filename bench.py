@@ -573,6 +573,31 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
         kname = ("k_gemm2<float> (FADD + FMNMX)" if f32 else ("k_gemm2h (packed int16x2)" if i16 else "k_gemm2<int32>")) + \
                 (", persistent dataflow kernel: the tiled max-plus GEMM tiles and the generic tiles of a whole wave"
                  if not n_gen_launches else ", one launch per dependency level")
+        # per-node hybrid roofline: every non-fused step needs at least max(ops / op rate, algorithmic bytes / HBM
+        # bandwidth), the fused subtrees their ops at the op rate; the sum over this rank's plans is a lower bound of its step
+        hybrid = None
+        if peak_gops:
+            p_ops, bw = peak_gops * 1e9, peaks["hbm_gbs"] * 1e9
+            t_ops = t_mem = 0.0
+            n_mem = n_nodes = 0
+            for pl in my_plans:
+                if pl is None:
+                    continue
+                ops_n = np.exp2(np.frombuffer(pl.raw(6), dtype=np.float32).astype(np.float64))
+                byt_n = np.frombuffer(pl.raw(7), dtype=np.float64)
+                tc, tm = ops_n / p_ops, byt_n / bw
+                mem = tm > tc
+                t_ops += float(tc[~mem].sum())
+                t_mem += float(tm[mem].sum())
+                n_mem += int(mem.sum())
+                n_nodes += int(mem.size)
+            t_fused = my_sum("fused_ops") / p_ops
+            bound_ms = (t_ops + t_mem + t_fused) * 1e3
+            hybrid = {"bound_ms": bound_ms, "frac_whole_step": bound_ms / ms_step if ms_step > 0 else None,
+                      "compute_bound_ms": t_ops * 1e3, "memory_bound_ms": t_mem * 1e3, "fused_ms": t_fused * 1e3,
+                      "memory_bound_nodes": n_mem, "nodes": n_nodes,
+                      "note": "sum over the non-fused steps of this rank's plans of max(ops / peak op rate, algorithmic bytes / measured "
+                              "HBM copy bandwidth) + fused-subtree ops / peak op rate, divided by the timed step"}
         roofline = {"bound": ("fp32 FADD+FMNMX (two issues per tropical op" if f32 else
                               ("dpx-int16x2 (VIADDMNMX.S16x2" if i16 else "dpx-int32 (VIADDMNMX")) +
                              " issue rate; the semiring is (max,+), tensor cores do not apply)",
@@ -589,6 +614,7 @@ def run_workload(cx, name, scaling, steps, warmup, max_branches=None, slice_k=No
                     "avg_launch_ms": k_ms_sum / max(1, k_launches), "launches": k_launches,
                     "kernel_ms_on_device": k_ms_union, "kernel_ms_sum_of_launches": k_ms_sum, "kernel_ms_single_lane": k_ms_1lane,
                     "share_of_step": {k: v[0] for k, v in prof1.items()},
+                    "hybrid": hybrid,
                     "hbm": {"peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
                             "achieved_whole_step": my_sum("algo_bytes") / (ms_step * 1e-3) * 1e-9}}
         out = {"value": total_ops / (ms_step * 1e-3) * 1e-9, "unit": "Gop/s", "ms_per_step": ms_step,
@@ -719,6 +745,8 @@ def main():
                           "kernel_frac_of_dpx_peak": r["roofline"]["frac"],
                           "kernel_frac_single_lane": r["roofline"]["frac_single_lane"],
                           "whole_step_frac_of_dpx_peak": r["roofline"]["frac_whole_step"],
+                          "whole_step_frac_of_hybrid_roofline": (r["roofline"].get("hybrid") or {}).get("frac_whole_step"),
+                          "hybrid_roofline_memory_bound_ms": (r["roofline"].get("hybrid") or {}).get("memory_bound_ms"),
                           "e2e": ({"value": r["e2e"]["value"], "ms_per_step": r["e2e"]["ms_per_step"],
                                    "vs_resident": r["e2e"]["vs_resident"], "steps": r["e2e"]["steps"],
                                    "host_breakdown": r["e2e"]["host_breakdown_rank0"]} if "e2e" in r else None),

@@ -210,7 +210,9 @@ int tb_plan_export(const tb_plan* plan, tb_step_info* out, int32_t cap);
 /* raw descriptor sections of a compiled plan, for the test-side descriptor interpreter and for
  * debugging: which = 0 leaf pool (u32 words), 1 fused steps (48-byte records), 2 fused subtrees
  * (24-byte records), 3 level steps (144-byte records), 4 level index (i32), 5 header (i64 words:
- * arena_elems, root_off, n_levels, value_type).  Copies min(cap, size) bytes, returns the size. */
+ * arena_elems, root_off, n_levels, value_type), 6 log2 of the tropical ops of every level step (f32), 7 algorithmic bytes
+ * of every level step (f64: operands read once + result written once) -- 6 and 7 are what a per-node roofline
+ * max(ops / op rate, bytes / bandwidth) needs.  Copies min(cap, size) bytes, returns the size. */
 int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_t cap);
 
 /* replaces solve(net, SizeMax(), T, usecuda)[].n (src/dynamic_ob.jl:32): the root scalar of one plan */

@@ -1687,6 +1687,8 @@ int64_t tb_plan_export_raw(const tb_plan* plan, int32_t which, void* out, int64_
         case 3: src = P.big_steps.data(); bytes = (int64_t)(P.big_steps.size() * sizeof(BigStep)); break;
         case 4: src = P.big_level_begin.data(); bytes = (int64_t)P.big_level_begin.size() * 4; break;
         case 5: src = header; bytes = sizeof header; break;
+        case 6: src = P.big_log2_ops.data(); bytes = (int64_t)P.big_log2_ops.size() * 4; break;
+        case 7: src = P.big_bytes.data(); bytes = (int64_t)P.big_bytes.size() * 8; break;
         default: return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "unknown section");
     }
     if (out && cap > 0 && bytes > 0) std::memcpy(out, src, (size_t)std::min(cap, bytes));
