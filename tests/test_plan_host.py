@@ -246,3 +246,20 @@ def test_network_cache_follows_code_and_weights_objects():
     assert n2 != n1 and n2 == Cn._network_bytes(b, np.float32)
     p = tbcuda.Plan(a)
     assert p.info().ops == tbcuda.Plan(b).info().ops
+
+
+def test_per_step_ops_and_bytes_export(tb):
+    """tb_plan_export_raw sections 6 / 7 (what bench.py's per-node hybrid roofline reads): one entry per non-fused step,
+    consistent with the plan's totals"""
+    for n, seed in ((60, 5), (100, 7), (130, 5)):
+        p = tb.Plan(to_sliced(regular_root(n, seed)))
+        st = p.info()
+        log2_ops = np.frombuffer(p.raw(6), dtype=np.float32)
+        nbytes = np.frombuffer(p.raw(7), dtype=np.float64)
+        assert log2_ops.size == nbytes.size == st.n_gemm_steps + st.n_generic_steps
+        if log2_ops.size:
+            assert np.all(log2_ops == np.round(log2_ops)) and np.all(nbytes > 0)
+            # second halves of split reductions are engine overhead: their ops are not in the plan's algorithmic totals
+            assert np.exp2(log2_ops.astype(np.float64)).sum() >= st.gemm_ops + st.generic_ops
+            assert nbytes.sum() >= st.gemm_bytes
+        p.close()
