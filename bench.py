@@ -740,6 +740,7 @@ def main():
                              cpu_budget=min(args.cpu_budget, 4.0), cpu_on=not args.no_cpu_baseline, sample_clocks=False,
                              min_timed_s=0.5)
             others[wl] = {"value": r["value"], "unit": "Gop/s", "ms_per_step": r["ms_per_step"], "steps": r["steps_timed"],
+                          "ms_per_step_median": r["ms_per_step_median_rank0"], "ms_per_step_max": r["ms_per_step_max_rank0"],
                           "units": r["units"], "slices_per_s": r["slices_per_s"], "launches_per_step": r["launches_per_step"],
                           "mis": r["mis"], "agrees_with_golden": r.get("agrees_with_golden"),
                           "kernel_frac_of_dpx_peak": r["roofline"]["frac"],

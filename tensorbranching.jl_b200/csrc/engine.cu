@@ -141,8 +141,10 @@ struct tb_ctx {
         size_t dcap = 0;
         cudaEvent_t ev = nullptr;
         bool busy = false;
+        uint64_t seq = 0;  // when the slot was last handed out (the busy slot with the smallest seq frees first)
     };
     static constexpr int kSlots = 6;
+    uint64_t slot_seq = 0;
     Slot slots[kSlots];
     int slot_cursor = 0;
     cudaStream_t copy_stream = nullptr;    // H2D of blobs / work lists, never blocked behind compute
@@ -413,11 +415,27 @@ int acquire_slot(tb_ctx* ctx, size_t hbytes, size_t dbytes, tb_ctx::Slot** out) 
         }
     }
     cudaGetLastError();  // cudaEventQuery returns cudaErrorNotReady for pending events
+    // Growing a slot re-pins host memory (~2 ms per MB) and frees device memory (a device-wide synchronisation), so once half
+    // of the ring is big enough for this request the others are left alone: rather than growing a small free slot (or
+    // waiting for a small busy one and growing it), wait for the big-enough slot that was handed out first.  Without this
+    // a small slot that the warm-up calls never happened to pick grows in the middle of some later call.
+    {
+        int n_fit = 0, oldest_fit = -1;
+        for (int q = 0; q < tb_ctx::kSlots; ++q) {
+            const tb_ctx::Slot& c = ctx->slots[q];
+            if (c.hcap < hbytes || c.dcap < dbytes) continue;
+            ++n_fit;
+            if (c.busy && (oldest_fit < 0 || c.seq < ctx->slots[oldest_fit].seq)) oldest_fit = q;
+        }
+        const bool pick_fits = pick >= 0 && ctx->slots[pick].hcap >= hbytes && ctx->slots[pick].dcap >= dbytes;
+        if (!pick_fits && n_fit >= tb_ctx::kSlots / 2 && oldest_fit >= 0) pick = oldest_fit;
+    }
     if (pick < 0) {
         pick = ctx->slot_cursor;
         ctx->slot_cursor = (ctx->slot_cursor + 1) % tb_ctx::kSlots;
     }
     tb_ctx::Slot& sl = ctx->slots[pick];
+    sl.seq = ++ctx->slot_seq;
     if (!sl.ev) TB_CUDA(ctx, cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
     if (sl.busy) {
         StallTimer stall(ctx, "wait for a staging slot");
