@@ -296,6 +296,24 @@ int tb_contract_table(tb_ctx* ctx, tb_plan* plan, double* out_sizes, uint32_t* o
  * transform (rank + 1 launches, O(rank 2^rank)) instead of the reference's all-pairs loop (O(4^rank)). */
 int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t* out_keep);
 
+/* ALL optimal configurations of the table ([upstream, recalled] the ConfigsMax element type of GenericTensorNetworks that
+ * OptimalBranchingMIS' table solver contracts with; every row of the BranchingTable built at src/branch.jl:79 lists all
+ * optimal vertex sets of its boundary configuration, and the set-cover solver may satisfy a row with any one of them).
+ * net = the region's network (its leaves give the graph and the weights; the tree is not used, n_labels <= 32),
+ * boundary_labels[0 .. rank) = the open vertices in the bit order of the rows (pass tb_contract_table's out_labels, so that
+ * row a here is entry a of its sizes), keep = tb_compactify_table's flags (NULL = every feasible row).
+ *   out_sizes[a]   (optional) the optimum of row a, computed independently of the contraction -- equal to
+ *                  tb_contract_tensor's sizes (the tests assert it); -inf = infeasible
+ *   out_row_off    2^rank + 1 offsets: row a owns out_configs[out_row_off[a] .. out_row_off[a+1]) (empty if dropped)
+ *   out_configs    the vertex masks (bit v = vertex v, boundary vertices included), rows in order, each row ascending in
+ *                  its interior configuration; NULL (or cap == 0) only counts; cap < total is TB_ERR_BAD_ARGUMENT
+ *   out_total      number of configurations in the table
+ * A region has <= n_max = 20 vertices by default (src/types.jl:10), so instead of carrying configuration SETS through the
+ * contraction the device filters the 2^n vertex sets of the region against the row optima (one CTA per boundary
+ * configuration and chunk of interior configurations; three passes: optimum, count, ordered write). */
+int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
+                     double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total);
+
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap,

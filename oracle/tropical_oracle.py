@@ -296,3 +296,88 @@ def mis_compactify_keep(sizes):
             continue
         keep[a] = not any(b != a and (b & a) == b and sizes[b] >= sizes[a] for b in range(a))
     return keep
+
+
+# --------------------------------------------------------------------------------------------
+# all optimal configurations (the rows of the reference's branching tables)
+# --------------------------------------------------------------------------------------------
+def contract_tree_configs(ixs, left, right, weights=None, open_labels=()):
+    """[upstream, recalled] the contraction `solve(problem, ConfigsMax(; bounded=false))` that OptimalBranchingMIS'
+    `reduced_alpha_configs` runs for `branching_table(p, TensorNetworkSolver(), region)` (/root/reference/src/branch.jl:79):
+    the same tree, the same binary rule, but every element is a pair (size, SET of configurations) -- GenericTensorNetworks'
+    CountingTropical{T, ConfigEnumerator}: (x) adds the sizes and joins every pair of configurations (bitwise or),
+    (+) keeps the larger size and unites the sets on a tie; tropical zero = (-inf, {}).  Leaves: vertex v -> [(0, {0}),
+    (w_v, {1 << v})], edge -> [[one, one], [one, zero]] with one = (0, {0}).
+    Pure Python over dictionaries (small regions only).  Returns (labels, {boundary assignment tuple: (size, frozenset of
+    vertex masks)}) for the open labels in the order given."""
+    zero = (NEG_INF, frozenset())
+    one = (0.0, frozenset([0]))
+
+    def add(x, y):
+        if x[0] > y[0]:
+            return x
+        if y[0] > x[0]:
+            return y
+        return (x[0], x[1] | y[1])
+
+    def mul(x, y):
+        if x[0] == NEG_INF or y[0] == NEG_INF:
+            return zero
+        return (x[0] + y[0], frozenset(a | b for a in x[1] for b in y[1]))
+
+    def leaf(ix):
+        if len(ix) == 1:
+            w = 1.0 if weights is None else float(weights[ix[0]])
+            return {(0,): one, (1,): (w, frozenset([1 << ix[0]]))}
+        return {(0, 0): one, (0, 1): one, (1, 0): one, (1, 1): zero}
+
+    n_leaves = len(ixs)
+    labs = node_output_labels(ixs, left, right, open_labels)
+    vals = [leaf(tuple(ix)) for ix in ixs]
+    for j in range(len(left)):
+        a, b = left[j], right[j]
+        la, lb, lo = labs[a], labs[b], labs[n_leaves + j]
+        allv = list(dict.fromkeys(list(la) + list(lb)))
+        out = {}
+        for bits in itertools.product((0, 1), repeat=len(allv)):
+            asg = dict(zip(allv, bits))
+            v = mul(vals[a][tuple(asg[l] for l in la)], vals[b][tuple(asg[l] for l in lb)])
+            key = tuple(asg[l] for l in lo)
+            out[key] = add(out.get(key, zero), v)
+        vals.append(out)
+        vals[a] = vals[b] = None
+    root, rl = vals[-1], labs[-1]
+    res = {}
+    for key, v in root.items():  # single-leaf networks may carry non-open labels: reduce them; then order as asked
+        asg = dict(zip(rl, key))
+        k2 = tuple(asg[l] for l in open_labels)
+        res[k2] = add(res.get(k2, zero), v)
+    return tuple(open_labels), res
+
+
+def table_configs_bruteforce(nv: int, edges, weights, boundary):
+    """Independent check of the above: for every assignment of the boundary vertices, the best weight of an independent
+    set that agrees with it and ALL vertex masks that attain it, by enumerating the 2^nv vertex sets.
+    -> (sizes float64[2^rank] (index bit i = boundary[i]), [sorted list of masks per entry])"""
+    adj = [0] * nv
+    for u, v in edges:
+        adj[u] |= 1 << v
+        adj[v] |= 1 << u
+    w = [1.0] * nv if weights is None else [float(x) for x in weights]
+    rank = len(boundary)
+    sizes = np.full(1 << rank, NEG_INF)
+    rows: List[List[int]] = [[] for _ in range(1 << rank)]
+    for s in range(1 << nv):
+        if any((s >> v) & 1 and adj[v] & s for v in range(nv)):
+            continue
+        tot = 0.0
+        for v in range(nv):  # ascending vertex order (the device sums in the same order: exact equality for real weights)
+            if (s >> v) & 1:
+                tot += w[v]
+        a = sum(((s >> boundary[i]) & 1) << i for i in range(rank))
+        if tot > sizes[a]:
+            sizes[a] = tot
+            rows[a] = [s]
+        elif tot == sizes[a]:
+            rows[a].append(s)
+    return sizes, rows

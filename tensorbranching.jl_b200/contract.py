@@ -255,14 +255,56 @@ class Engine:
                                               keep.ctypes.data_as(C.POINTER(C.c_uint8))), self.handle)
         return keep.astype(bool)
 
-    def branching_table(self, plan: Plan):
-        """The table `branching_table(p, TensorNetworkSolver(), region)` hands to the set-cover solver (src/branch.jl:79),
-        with ONE optimal configuration per row: contract the region's network (size + configuration elements, boundary
-        vertices open), drop the dominated boundary configurations.
-        -> (boundary labels bit-0-first, rows) with rows = [(boundary bits, size, vertex mask of one optimal set), ...]"""
-        labels, sizes, cfgs = self.contract_table(plan)
+    def table_configs(self, branch, labels, keep: Optional[np.ndarray] = None):
+        """tb_table_configs: ALL optimal vertex sets of every boundary configuration of a region (the ConfigsMax rows of the
+        reference's table solver).  branch = the region's SlicedBranch (or a Plan made from it), labels = the boundary
+        vertices in the bit order of the rows (contract_table's labels), keep = compactify_table's flags.
+        -> (sizes float64[2^rank], row_off int64[2^rank + 1], configs uint32[total])"""
+        if isinstance(branch, Plan):
+            branch = branch._keep[0]
+        net, w = _network_of(branch, None, 0)
+        rank = len(labels)
+        n = 1 << rank
+        lab = np.asarray(list(labels) + [0], dtype=np.int32)  # (+1 pad: never an empty buffer)
+        kp = None
+        if keep is not None:
+            keep = np.ascontiguousarray(keep, dtype=np.uint8)
+            if keep.size != n:
+                raise ValueError("keep has one flag per boundary configuration")
+            kp = keep.ctypes.data_as(C.POINTER(C.c_uint8))
+        sizes = np.empty(n, dtype=np.float64)
+        row_off = np.zeros(n + 1, dtype=np.int64)
+        total = C.c_int64()
+        args = (self.handle, C.byref(net), lab.ctypes.data_as(C.POINTER(C.c_int32)), rank, kp,
+                sizes.ctypes.data_as(C.POINTER(C.c_double)), row_off.ctypes.data_as(C.POINTER(C.c_int64)))
+        L.check(self._lib.tb_table_configs(*args, None, 0, C.byref(total)), self.handle)  # counts only
+        cfgs = np.zeros(max(total.value, 1), dtype=np.uint32)
+        L.check(self._lib.tb_table_configs(*args, cfgs.ctypes.data_as(C.POINTER(C.c_uint32)), cfgs.size, C.byref(total)),
+                self.handle)
+        del w
+        return sizes, row_off, cfgs[:total.value]
+
+    def branching_table(self, plan: Plan, all_configs: bool = False):
+        """The table `branching_table(p, TensorNetworkSolver(), region)` hands to the set-cover solver (src/branch.jl:79):
+        contract the region's network (boundary vertices open), drop the dominated boundary configurations.
+        all_configs=False: ONE optimal configuration per row (size + configuration elements carried through the contraction)
+        -> (boundary labels bit-0-first, rows) with rows = [(boundary bits, size, vertex mask of one optimal set), ...]
+        all_configs=True: every optimal configuration of every surviving row, as the reference's ConfigsMax tables hold them
+        -> (labels, rows) with rows = [(boundary bits, size, [vertex masks, ascending]), ...]"""
+        if plan.info().value_type == L.TB_VALUE_SIZE_CONFIG:
+            labels, sizes, cfgs = self.contract_table(plan)
+        else:
+            labels, sizes = self.contract_tensor(plan)
+            cfgs = None
         keep = self.compactify_table(sizes)
-        return labels, [(int(a), float(sizes[a]), int(cfgs[a])) for a in np.nonzero(keep)[0]]
+        if not all_configs:
+            if cfgs is None:
+                raise ValueError("one configuration per row needs a plan created with value_type=TB_VALUE_SIZE_CONFIG")
+            return labels, [(int(a), float(sizes[a]), int(cfgs[a])) for a in np.nonzero(keep)[0]]
+        own_sizes, row_off, allc = self.table_configs(plan, labels, keep)
+        if not np.array_equal(own_sizes, sizes):
+            raise L.TBError(L.TB_ERR_INTERNAL, "the enumerated row optima differ from the contracted sizes")
+        return labels, [(int(a), float(sizes[a]), [int(c) for c in allc[row_off[a]:row_off[a + 1]]]) for a in np.nonzero(keep)[0]]
 
     # -- batches -----------------------------------------------------------------------------
     def contract_plans(self, plans, r: Optional[np.ndarray] = None):

@@ -2598,6 +2598,112 @@ int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t*
     return TB_OK;
 } TB_CATCH(ctx)
 
+int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
+                     double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total) try {
+    if (!ctx || !net || !out_row_off) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / net / out_row_off is NULL");
+    if (!ctx->subs.empty())
+        return tb_table_configs(ctx->subs[0], net, boundary_labels, rank, keep, out_sizes, out_row_off, out_configs, cap, out_total);
+    const int n = net->n_labels;
+    if (n < 0 || n > 32) return set_err(ctx, TB_ERR_UNSUPPORTED, "a region has at most 32 vertices (configurations are 32-bit vertex masks)");
+    if (rank < 0 || rank > n || rank > 24) return set_err(ctx, TB_ERR_UNSUPPORTED, "boundary rank must be in [0, min(n_labels, 24)]");
+    if (rank > 0 && !boundary_labels) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "boundary_labels is NULL");
+    if (net->n_fixed != 0) return set_err(ctx, TB_ERR_UNSUPPORTED, "tb_table_configs does not take index-sliced networks");
+    if (net->n_leaves < 0 || (net->n_leaves > 0 && (!net->leaf_off || !net->leaf_labels)))
+        return set_err(ctx, TB_ERR_BAD_ARGUMENT, "leaf arrays are NULL");
+    const int wd = net->weight_dtype;
+    if (wd < TB_WEIGHT_UNIT || wd > TB_WEIGHT_F64) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "unknown weight_dtype");
+    if (wd != TB_WEIGHT_UNIT && !net->weights) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "weights is NULL but weight_dtype is not UNIT");
+    auto weight_of = [&](int v) -> double {
+        switch (wd) {
+            case TB_WEIGHT_I32: return (double)((const int32_t*)net->weights)[v];
+            case TB_WEIGHT_I64: return (double)((const int64_t*)net->weights)[v];
+            case TB_WEIGHT_F32: return (double)((const float*)net->weights)[v];
+            case TB_WEIGHT_F64: return ((const double*)net->weights)[v];
+            default: return 1.0;
+        }
+    };
+    // the region's graph, read off the leaves: 1 label = vertex tensor [0, w_v], 2 labels = edge tensor (tbcuda.h, tb_network)
+    RegionDesc R;
+    std::memset(&R, 0, sizeof(R));
+    R.n = n;
+    R.rank = rank;
+    for (int32_t l = 0; l < net->n_leaves; ++l) {
+        const int32_t b = net->leaf_off[l], e = net->leaf_off[l + 1];
+        if (e - b < 1 || e - b > 2) return set_err(ctx, TB_ERR_UNSUPPORTED, "leaf tensors have 1 (vertex) or 2 (edge) labels");
+        const int32_t u = net->leaf_labels[b], v = net->leaf_labels[e - 1];
+        if (u < 0 || u >= n || v < 0 || v >= n) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "leaf label out of range");
+        if (e - b == 1) R.w[u] += weight_of(u);
+        else if (u == v) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "an edge tensor joins a vertex with itself");
+        else {
+            R.adj[u] |= 1u << v;
+            R.adj[v] |= 1u << u;
+        }
+    }
+    uint32_t bset = 0;
+    for (int i = 0; i < rank; ++i) {
+        const int32_t v = boundary_labels[i];
+        if (v < 0 || v >= n || ((bset >> v) & 1)) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "boundary labels must be distinct labels of the network");
+        bset |= 1u << v;
+        R.bpos[i] = (uint8_t)v;
+    }
+    for (int v = 0; v < n; ++v)
+        if (!((bset >> v) & 1)) R.ipos[R.n_int++] = (uint8_t)v;
+    R.chunk_log2 = std::min(R.n_int, 12);
+    const int chunks_log2 = R.n_int - R.chunk_log2;
+    const int64_t n_rows = (int64_t)1 << rank, n_cta = n_rows << chunks_log2;
+    if (n_cta > 0x7fffffffll) return set_err(ctx, TB_ERR_UNSUPPORTED, "region too large");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // device scratch: alpha keys | sizes | row offsets | chunk counts | chunk offsets | keep flags
+    const size_t b_rows = (size_t)n_rows * 8, b_off = (size_t)(n_rows + 1) * 8, b_cnt = (size_t)n_cta * 8, b_coff = (size_t)(n_cta + 1) * 8;
+    uint8_t* d = nullptr;
+    TB_CUDA(ctx, cudaMalloc(&d, 2 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
+    struct Free {
+        void* p;
+        ~Free() { if (p) cudaFree(p); }
+    } free_d{d}, free_out{nullptr};
+    unsigned long long* d_alpha = (unsigned long long*)d;
+    double* d_sizes = (double*)(d + b_rows);
+    int64_t* d_row_off = (int64_t*)(d + 2 * b_rows);
+    int64_t* d_cnt = (int64_t*)(d + 2 * b_rows + b_off);
+    int64_t* d_coff = (int64_t*)(d + 2 * b_rows + b_off + b_cnt);
+    uint8_t* d_keep = nullptr;
+    if (keep) {
+        d_keep = d + 2 * b_rows + b_off + b_cnt + b_coff;
+        TB_CUDA(ctx, cudaMemcpyAsync(d_keep, keep, (size_t)n_rows, cudaMemcpyHostToDevice, st));
+    }
+    const unsigned g_rows = (unsigned)((n_rows + 255) / 256);
+    cudaEventRecord(ctx->ev0, st);
+    k_region_init<<<g_rows, 256, 0, st>>>(d_alpha, n_rows);
+    k_region_configs<0><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, nullptr, nullptr, nullptr, nullptr);
+    k_region_sizes<<<g_rows, 256, 0, st>>>(d_alpha, d_sizes, n_rows);
+    k_region_configs<1><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, d_cnt, nullptr, nullptr);
+    k_region_scan<<<1, 1024, 0, st>>>(d_cnt, d_coff, n_cta, d_row_off, n_rows, chunks_log2);
+    TB_CUDA(ctx, cudaGetLastError());
+    TB_CUDA(ctx, cudaMemcpyAsync(out_row_off, d_row_off, b_off, cudaMemcpyDeviceToHost, st));
+    if (out_sizes) TB_CUDA(ctx, cudaMemcpyAsync(out_sizes, d_sizes, b_rows, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t total = out_row_off[n_rows];
+    if (out_total) *out_total = total;
+    ctx->last_launches = 5;
+    if (out_configs && total > 0) {
+        if (cap < total) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "out_configs holds " + std::to_string(cap) + " configurations, the table has " + std::to_string(total));
+        uint32_t* d_out = nullptr;
+        TB_CUDA(ctx, cudaMalloc(&d_out, (size_t)total * sizeof(uint32_t)));
+        free_out.p = d_out;
+        k_region_configs<2><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, nullptr, d_coff, d_out);
+        TB_CUDA(ctx, cudaGetLastError());
+        TB_CUDA(ctx, cudaMemcpyAsync(out_configs, d_out, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        ctx->last_launches = 6;
+    }
+    cudaEventRecord(ctx->ev1, st);
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms;
+    return TB_OK;
+} TB_CATCH(ctx)
+
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {
     if (!ctx) return set_err(nullptr, TB_ERR_BAD_ARGUMENT, "ctx is NULL");
     if (out_device_ms) *out_device_ms = ctx->last_ms;

@@ -1687,6 +1687,169 @@ __global__ void k_table_keep(const double* __restrict__ sizes, const double* __r
     keep[a] = (v > -INFINITY && !(best >= v)) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// ALL optimal configurations of a branching table (the ConfigsMax element type of the reference's table solver,
+// reached from src/branch.jl:79).  A region has at most 32 vertices (n_max = 20 by default, src/types.jl:10), so the set
+// algebra of the reference (unions and cartesian products of configuration sets carried through the contraction) is
+// replaced by a filter over the 2^n vertex sets of the region: a set belongs to the row of its boundary configuration a
+// iff it is independent and its weight equals the row's optimum.  Index space: (boundary configuration a, chunk of the
+// 2^n_int interior configurations); one CTA per (a, chunk), a thread walks the chunk with stride blockDim.
+//   pass 0: alpha[a] = max weight (atomicMax on an order-preserving integer image of the double)
+//   pass 1: chunk_count[cta] = number of optimal sets in the chunk (rows with keep[a] == 0 count nothing)
+//   pass 2: the sets are written at chunk_off[cta] in ascending interior index (block-wide ordered compaction), so the
+//           output is deterministic: rows in boundary-configuration order, each row sorted.
+// ------------------------------------------------------------------------------------------------
+struct RegionDesc {
+    double w[32];           // weight of vertex v (sum of its vertex tensors' weights)
+    uint32_t adj[32];       // neighbours of vertex v inside the region
+    uint8_t bpos[32];       // boundary bit i of a row index  -> vertex
+    uint8_t ipos[32];       // interior bit i of a chunk index -> vertex
+    int32_t n, rank, n_int; // vertices, boundary vertices, interior vertices
+    int32_t chunk_log2;     // interior configurations per CTA = 2^chunk_log2
+};
+static constexpr int kRegionThreads = 256;
+
+__device__ __forceinline__ unsigned long long region_key(double x) {  // order-preserving: x < y <=> key(x) < key(y)
+    const long long b = __double_as_longlong(x);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+__device__ __forceinline__ double region_unkey(unsigned long long k) {
+    const long long b = (long long)k;
+    return __longlong_as_double(b < 0 ? (b ^ (long long)0x8000000000000000ull) : ~b);
+}
+__device__ __forceinline__ uint32_t region_deposit(uint64_t x, const uint8_t* pos) {
+    uint32_t m = 0;
+    while (x) {
+        m |= 1u << pos[__ffsll((long long)x) - 1];
+        x &= x - 1;
+    }
+    return m;
+}
+// weight of the vertex set `cfg`, -inf when it is not independent (vertices added in ascending order: the same order in
+// every pass, so equality with the row optimum is exact for real weights too)
+__device__ __forceinline__ double region_weight(const RegionDesc& R, uint32_t cfg) {
+    double s = 0;
+    for (uint32_t x = cfg; x; x &= x - 1) {
+        const int v = __ffs((int)x) - 1;
+        if (R.adj[v] & cfg) return -INFINITY;
+        s += R.w[v];
+    }
+    return s;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(kRegionThreads)
+k_region_configs(const __grid_constant__ RegionDesc R, unsigned long long* __restrict__ alpha_key, const uint8_t* __restrict__ keep,
+                 int64_t* __restrict__ chunk_count, const int64_t* __restrict__ chunk_off, uint32_t* __restrict__ out_configs) {
+    __shared__ uint32_t warp_tot[kRegionThreads / 32];
+    __shared__ unsigned long long red[kRegionThreads / 32];
+    const int chunks_log2 = R.n_int - R.chunk_log2;
+    const uint64_t cta = blockIdx.x;
+    const uint64_t a = cta >> chunks_log2, chunk = cta & (((uint64_t)1 << chunks_log2) - 1);
+    const uint32_t bmask = region_deposit(a, R.bpos);
+    const uint64_t i0 = chunk << R.chunk_log2, len = (uint64_t)1 << R.chunk_log2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double row_best = -INFINITY;
+    if (PASS > 0) {
+        row_best = region_unkey(alpha_key[a]);
+        if (row_best == -INFINITY || (keep && !keep[a])) {  // infeasible or dropped row: nothing to count or write
+            if (PASS == 1 && threadIdx.x == 0) chunk_count[cta] = 0;
+            return;
+        }
+    }
+    if (PASS == 0 && region_weight(R, bmask) == -INFINITY) return;  // two adjacent boundary vertices chosen: the row stays -inf
+    double best = -INFINITY;
+    int64_t written = 0;
+    uint32_t mine = 0;
+    for (uint64_t j = 0; j < len; j += kRegionThreads) {  // uniform trip count: the block-wide scan below needs every thread
+        const uint64_t i = j + threadIdx.x;
+        bool hit = false;
+        uint32_t cfg = 0;
+        if (i < len) {
+            cfg = bmask | region_deposit(i0 + i, R.ipos);
+            const double wgt = region_weight(R, cfg);
+            if (PASS == 0) best = fmax(best, wgt);
+            else hit = wgt == row_best;
+        }
+        if (PASS == 1) mine += hit;
+        if (PASS == 2) {
+            const uint32_t ball = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) warp_tot[warp] = __popc(ball);
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+            for (int q = 0; q < kRegionThreads / 32; ++q) {
+                before += q < warp ? warp_tot[q] : 0;
+                total += warp_tot[q];
+            }
+            if (hit) out_configs[chunk_off[cta] + written + before + __popc(ball & ((1u << lane) - 1))] = cfg;
+            written += total;
+            __syncthreads();
+        }
+    }
+    if (PASS == 0) {
+        unsigned long long k = region_key(best);
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+            k = other > k ? other : k;
+        }
+        if (lane == 0) red[warp] = k;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int q = 1; q < kRegionThreads / 32; ++q) k = red[q] > k ? red[q] : k;
+            atomicMax(&alpha_key[a], k);
+        }
+    }
+    if (PASS == 1) {
+        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0) warp_tot[warp] = mine;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int q = 0; q < kRegionThreads / 32; ++q) t += warp_tot[q];
+            chunk_count[cta] = t;
+        }
+    }
+}
+
+// exclusive prefix sum of the chunk counts (one CTA: a contiguous segment per thread, then a scan of the 1024 segment sums);
+// off[n] = total.  row_off[a] = off[a << chunks_log2] for a <= n_rows.
+__global__ void __launch_bounds__(1024) k_region_scan(const int64_t* __restrict__ count, int64_t* __restrict__ off, int64_t n,
+                                                      int64_t* __restrict__ row_off, int64_t n_rows, int chunks_log2) {
+    __shared__ int64_t seg[1024];
+    const int64_t per = (n + 1023) / 1024, lo = min(n, per * threadIdx.x), hi = min(n, lo + per);
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += count[i];
+    seg[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t run = 0;
+        for (int q = 0; q < 1024; ++q) {
+            const int64_t t = seg[q];
+            seg[q] = run;
+            run += t;
+        }
+        off[n] = run;
+    }
+    __syncthreads();
+    s = seg[threadIdx.x];
+    for (int64_t i = lo; i < hi; ++i) {
+        off[i] = s;
+        s += count[i];
+    }
+    __syncthreads();
+    __threadfence_block();
+    for (int64_t a = threadIdx.x; a <= n_rows; a += 1024) row_off[a] = a == n_rows ? off[n] : off[a << chunks_log2];
+}
+
+__global__ void k_region_sizes(const unsigned long long* __restrict__ alpha_key, double* __restrict__ sizes, int64_t n) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) sizes[a] = region_unkey(alpha_key[a]);
+}
+__global__ void k_region_init(unsigned long long* __restrict__ alpha_key, int64_t n) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a < n) alpha_key[a] = region_key(-INFINITY);
+}
+
 template <typename T>
 __global__ void k_to_double(const T* __restrict__ src, double* __restrict__ dst, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,162 @@
+"""ALL optimal configurations of the branching tables: `branching_table(p, TensorNetworkSolver(), region)`
+(/root/reference/src/branch.jl:79, default solver /root/reference/src/types.jl:46, regions of at most n_max = 20 vertices
+src/types.jl:10) contracts the region's network with the ConfigsMax element type [upstream GenericTensorNetworks], so every
+row of the table lists every optimal vertex set of its boundary configuration.
+
+CPU: the oracle's restatement of that set algebra along the tree (`contract_tree_configs`) against plain enumeration
+(`table_configs_bruteforce`).  GPU: tb_table_configs through the C ABI against both, and Engine.branching_table(all_configs)."""
+import numpy as np
+import pytest
+
+from helpers import regular_root
+from oracle import tropical_oracle as O
+
+
+def _region(tb, n, seed, n_open, weights=None):
+    root = regular_root(n, seed)
+    rng = np.random.default_rng(seed + 100)
+    open_labels = sorted(int(v) for v in rng.choice(root.nv, size=n_open, replace=False))
+    w = root.weights if weights is None else weights(root.nv, rng)
+    br = tb.SlicedBranch(tb.MISProblem(root.nv, root.edges, w), tb.CompressedEinsum(root.ixs, open_labels, root.tree), 0)
+    return root, br, open_labels, w
+
+
+def _int_weights(nv, rng):
+    return rng.integers(1, 4, size=nv).astype(np.int32)
+
+
+def _real_weights(nv, rng):
+    return (1.0 + rng.random(nv)).astype(np.float64)
+
+
+def _tied_real_weights(nv, rng):
+    # few distinct real values: plenty of exact ties between different vertex sets
+    return rng.choice(np.array([1.0, 1.5, 2.25]), size=nv)
+
+
+@pytest.mark.parametrize("n,seed,n_open", [(8, 1, 2), (10, 1, 3), (12, 2, 4), (14, 3, 5), (14, 4, 0)])
+@pytest.mark.parametrize("weights", [None, _int_weights])
+def test_oracle_set_algebra_equals_enumeration(tb, n, seed, n_open, weights):
+    root, _, open_labels, w = _region(tb, n, seed, n_open, weights)
+    left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+    labs, res = O.contract_tree_configs(root.ixs, left, right, w, open_labels)
+    sizes, rows = O.table_configs_bruteforce(root.nv, root.edges, w, open_labels)
+    # the sizes are the open-boundary tensor of the tropical contraction
+    t, tl = O.contract_tree(root.ixs, left, right, None if w is None else np.asarray(w, dtype=np.float64), np.float64,
+                            open_labels=tuple(open_labels))
+    assert tuple(tl) == tuple(open_labels)
+    for a in range(1 << n_open):
+        key = tuple((a >> i) & 1 for i in range(n_open))
+        assert res[key][0] == sizes[a] == np.asarray(t)[key]
+        assert sorted(res[key][1]) == rows[a]
+
+
+def test_oracle_known_tables():
+    # a path u - x - v with the end vertices open: the interior vertex is chosen only when both ends are out
+    sizes, rows = O.table_configs_bruteforce(3, [(0, 1), (1, 2)], None, [0, 2])
+    assert list(sizes) == [1.0, 1.0, 1.0, 2.0]
+    assert rows == [[0b010], [0b001], [0b100], [0b101]]
+    # a triangle plus a pendant pair, nothing open: all optimal sets of the whole region in one row
+    sizes, rows = O.table_configs_bruteforce(5, [(0, 1), (1, 2), (0, 2), (3, 4)], None, [])
+    assert list(sizes) == [2.0] and len(rows[0]) == 6
+
+
+def _check_against_oracle(root, w, labels, sizes, row_off, cfgs, keep=None):
+    want_sizes, want_rows = O.table_configs_bruteforce(root.nv, root.edges, w, labels)
+    assert np.array_equal(sizes, want_sizes)
+    assert row_off[0] == 0 and row_off[-1] == len(cfgs)
+    for a in range(len(want_rows)):
+        got = [int(c) for c in cfgs[row_off[a]:row_off[a + 1]]]
+        if keep is not None and not keep[a]:
+            assert got == []
+        else:
+            assert got == want_rows[a], f"row {a}"  # same sets AND the documented order (ascending)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,n_open", [(6, 1, 0), (8, 1, 2), (10, 1, 3), (14, 3, 5), (16, 2, 4), (18, 5, 6), (20, 3, 5)])
+@pytest.mark.parametrize("weights", [None, _int_weights, _real_weights, _tied_real_weights])
+def test_gpu_table_configs(tb, engine, n, seed, n_open, weights):
+    root, br, open_labels, w = _region(tb, n, seed, n_open, weights)
+    labels = list(reversed(open_labels))  # any bit order of the rows
+    sizes, row_off, cfgs = engine.table_configs(br, labels)
+    _check_against_oracle(root, w, labels, sizes, row_off, cfgs)
+    ms, launches = engine.last_timing()
+    assert launches == 6 and ms > 0
+    if n <= 14 and weights is not _real_weights and weights is not _tied_real_weights:
+        # the reference's algebra along the tree gives the same rows
+        left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+        _, res = O.contract_tree_configs(root.ixs, left, right, w, labels)
+        for a in range(1 << n_open):
+            key = tuple((a >> i) & 1 for i in range(n_open))
+            assert sorted(res[key][1]) == [int(c) for c in cfgs[row_off[a]:row_off[a + 1]]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,n_open", [(10, 1, 3), (20, 3, 5), (24, 4, 6), (26, 6, 8)])
+def test_gpu_branching_table_all_configs(tb, engine, n, seed, n_open):
+    """contraction (sizes) -> mis_compactify -> all optimal sets of the surviving rows; the enumerated row optima must equal
+    the contracted sizes (branching_table raises otherwise); the one-configuration table is a member of every row"""
+    root, br, open_labels, w = _region(tb, n, seed, n_open)
+    p = tb.Plan(br, value_type=tb.TB_VALUE_SIZE_CONFIG, engine=engine)
+    labels, rows = engine.branching_table(p, all_configs=True)
+    _, one_rows = engine.branching_table(p)
+    _, sizes, _ = engine.contract_table(p)
+    keep = O.mis_compactify_keep(sizes)
+    assert [a for a, _, _ in rows] == [a for a, _, _ in one_rows] == list(np.nonzero(keep)[0])
+    adj = [0] * root.nv
+    for u, v in root.edges:
+        adj[u] |= 1 << v
+        adj[v] |= 1 << u
+    for (a, size, masks), (_, _, one) in zip(rows, one_rows):
+        assert masks == sorted(set(masks)) and one in masks
+        for m in masks:
+            assert bin(m).count("1") == size == sizes[a]
+            assert not any((m >> v) & 1 and adj[v] & m for v in range(root.nv))
+            assert all(((m >> l) & 1) == ((a >> q) & 1) for q, l in enumerate(labels))
+    if n <= 20:
+        _, want_rows = O.table_configs_bruteforce(root.nv, root.edges, None, labels)
+        assert [masks for _, _, masks in rows] == [want_rows[a] for a, _, _ in rows]
+    # the same table from a sizes-only plan (any tropical value type)
+    q = tb.Plan(br, engine=engine)
+    l2, rows2 = engine.branching_table(q, all_configs=True)
+    order = {l: i for i, l in enumerate(l2)}
+    remap = lambda a: sum(((a >> i) & 1) << order[l] for i, l in enumerate(labels))  # noqa: E731
+    assert sorted((remap(a), s, tuple(m)) for a, s, m in rows) == sorted((a, s, tuple(m)) for a, s, m in rows2)
+
+
+@pytest.mark.gpu
+def test_gpu_table_configs_large_region_and_errors(tb, engine):
+    # 30 vertices, 6 open: 2^24 interior configurations per row, 2^30 vertex sets filtered
+    root, br, open_labels, w = _region(tb, 30, 7, 6)
+    sizes, row_off, cfgs = engine.table_configs(br, open_labels)
+    left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+    t, tl = O.contract_tree(root.ixs, left, right, None, np.float64, open_labels=tuple(open_labels))
+    want = np.asarray(t).transpose(list(range(len(tl)))[::-1]).reshape(-1)  # index bit i = open_labels[i]
+    assert np.array_equal(sizes, want)
+    adj = [0] * root.nv
+    for u, v in root.edges:
+        adj[u] |= 1 << v
+        adj[v] |= 1 << u
+    assert len(cfgs) == row_off[-1] > 0
+    for a in range(1 << 6):
+        row = cfgs[row_off[a]:row_off[a + 1]]
+        assert (len(row) > 0) == np.isfinite(sizes[a])
+        assert np.all(np.diff(row.astype(np.int64)) > 0)
+        for m in map(int, row[:50]):
+            assert bin(m).count("1") == sizes[a] and not any((m >> v) & 1 and adj[v] & m for v in range(root.nv))
+    # keep flags drop rows
+    keep = np.zeros(1 << 6, dtype=np.uint8)
+    keep[5] = 1
+    s2, off2, c2 = engine.table_configs(br, open_labels, keep)
+    assert np.array_equal(s2, sizes) and np.array_equal(c2, cfgs[row_off[5]:row_off[6]])
+    assert off2[5] == 0 and off2[6] == off2[-1] == len(c2)
+    # errors: a region of more than 32 vertices, a repeated boundary label
+    big = regular_root(40, 3)
+    bb = tb.SlicedBranch(tb.MISProblem(big.nv, big.edges, big.weights), tb.CompressedEinsum(big.ixs, [0, 1], big.tree), 0)
+    with pytest.raises(tb.TBError) as e:
+        engine.table_configs(bb, [0, 1])
+    assert e.value.code == -3
+    with pytest.raises(tb.TBError) as e:
+        engine.table_configs(br, [1, 1])
+    assert e.value.code == -1
