@@ -314,6 +314,16 @@ int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t*
 int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
                      double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total);
 
+/* The whole of branching_table(p, TensorNetworkSolver(), region) (src/branch.jl:79; [upstream, recalled] OptimalBranchingMIS
+ * reduced_alpha_configs: SizeMax tensor -> mis_compactify! -> ConfigsMax rows of the surviving entries) in ONE call and one
+ * round trip: row optima of the region, dominated rows dropped on the device (out_keep, optional, 2^rank flags as
+ * tb_compactify_table returns them), all optimal configurations of the surviving rows.  Arguments as tb_table_configs;
+ * boundary_labels = the region's open vertices in any order (they define the bit order of the rows).  When cap < total the
+ * call fails with TB_ERR_BAD_ARGUMENT after writing out_total / out_row_off / out_sizes / out_keep: retry with a larger buffer
+ * (tables have tens of rows, so a first guess of a few thousand entries practically always holds). */
+int tb_branching_table(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, uint8_t* out_keep,
+                       double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total);
+
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap,

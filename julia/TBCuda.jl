@@ -185,6 +185,49 @@ function stream_finish!(st::BranchStream, element_type::Type)
                         for (i, b) in enumerate(st.branches)]
 end
 
+# branching_table(p, TensorNetworkSolver(), region) (src/branch.jl:79; default table solver src/types.jl:46): the table of a
+# region with ALL optimal configurations per surviving row, in one C call (tb_branching_table: row optima, mis_compactify and
+# the configuration rows on the device).  `vs` = the region's vertices, `ovs` = its open vertices (both as vertex ids of
+# p.g); bit i-1 of a returned configuration is vertex vs[i], as in the reference's BranchingTable.  A maintainer hooks it in
+# with `OptimalBranchingCore.branching_table(p::MISProblem, ::TensorNetworkSolver, vs) = BranchingTable(length(vs),
+# TBCuda.branching_table_cuda(p.g, p.weights, vs, open_vertices(p.g, vs)))` (then prune_by_env as before, on the host).
+function branching_table_cuda(g, weights, vs::Vector{Int}, ovs::Vector{Int})
+    n = length(vs)
+    n <= 32 || error("TBCuda.branching_table_cuda: a region has at most 32 vertices")
+    pos = Dict(v => Int32(i - 1) for (i, v) in enumerate(vs))
+    leaf_off = Int32[0]; leaf_labels = Int32[]
+    for v in vs                                   # vertex tensors
+        push!(leaf_labels, pos[v]); push!(leaf_off, Int32(length(leaf_labels)))
+    end
+    for (i, u) in enumerate(vs), v in vs[i+1:end]  # edge tensors of the induced subgraph
+        if TensorBranching.Graphs.has_edge(g, u, v)
+            push!(leaf_labels, pos[u], pos[v]); push!(leaf_off, Int32(length(leaf_labels)))
+        end
+    end
+    unit = weights isa TensorBranching.UnitWeight
+    wv = unit ? nothing : collect(weights[vs])
+    boundary = Int32[pos[v] for v in ovs]
+    rank = length(boundary)
+    net = TbNetwork(n, length(leaf_off) - 1, pointer(leaf_off), pointer(leaf_labels), 0, C_NULL, C_NULL, C_NULL,
+                    unit ? C_NULL : Ptr{Cvoid}(pointer(wv)), unit ? Int32(0) : weight_code(eltype(wv)), Int32(0), UInt32(0),
+                    Int32(0), C_NULL, C_NULL)
+    keep = Vector{UInt8}(undef, 1 << rank); sizes = Vector{Float64}(undef, 1 << rank)
+    row_off = Vector{Int64}(undef, (1 << rank) + 1); total = Ref{Int64}(0)
+    cfgs = Vector{UInt32}(undef, 4096)
+    GC.@preserve leaf_off leaf_labels wv boundary begin
+        for attempt in 1:2
+            rc = ccall((:tb_branching_table, LIB), Cint,
+                       (Ptr{Cvoid}, Ref{TbNetwork}, Ptr{Int32}, Int32, Ptr{UInt8}, Ptr{Float64}, Ptr{Int64}, Ptr{UInt32}, Int64, Ref{Int64}),
+                       ctx(), net, boundary, rank, keep, sizes, row_off, cfgs, length(cfgs), total)
+            rc == 0 && break
+            (attempt == 1 && total[] > length(cfgs)) || error("tb_branching_table failed ($rc): " *
+                unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
+            resize!(cfgs, total[])
+        end
+    end
+    return [cfgs[row_off[a]+1:row_off[a+1]] for a in 1:(1 << rank) if keep[a] != 0]
+end
+
 # The usecuda=true switch position.  The reference defines
 #     contract_slices(::Vector{SlicedBranch}, ::Type, ::Bool)   and   solve_slice(::SlicedBranch, ::Type, ::Bool)
 # (src/dynamic_ob.jl:30,36).  Re-defining exactly those signatures from here would OVERWRITE them (and `invoke` would then

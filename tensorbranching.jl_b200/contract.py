@@ -272,17 +272,44 @@ class Engine:
             if keep.size != n:
                 raise ValueError("keep has one flag per boundary configuration")
             kp = keep.ctypes.data_as(C.POINTER(C.c_uint8))
+        sizes, row_off, cfgs = self._table_call(self._lib.tb_table_configs, net, lab, rank, kp)
+        del w
+        return sizes, row_off, cfgs
+
+    def _table_call(self, fn, net, lab, rank, keep_ptr):
+        """tb_table_configs / tb_branching_table with a first guess for the number of configurations; one retry with the exact
+        size when the table is larger (the failed call has already written the total)."""
+        n = 1 << rank
         sizes = np.empty(n, dtype=np.float64)
         row_off = np.zeros(n + 1, dtype=np.int64)
         total = C.c_int64()
-        args = (self.handle, C.byref(net), lab.ctypes.data_as(C.POINTER(C.c_int32)), rank, kp,
-                sizes.ctypes.data_as(C.POINTER(C.c_double)), row_off.ctypes.data_as(C.POINTER(C.c_int64)))
-        L.check(self._lib.tb_table_configs(*args, None, 0, C.byref(total)), self.handle)  # counts only
-        cfgs = np.zeros(max(total.value, 1), dtype=np.uint32)
-        L.check(self._lib.tb_table_configs(*args, cfgs.ctypes.data_as(C.POINTER(C.c_uint32)), cfgs.size, C.byref(total)),
-                self.handle)
+        cfgs = np.zeros(4096, dtype=np.uint32)
+        for attempt in (0, 1):
+            rc = fn(self.handle, C.byref(net), lab.ctypes.data_as(C.POINTER(C.c_int32)), rank, keep_ptr,
+                    sizes.ctypes.data_as(C.POINTER(C.c_double)), row_off.ctypes.data_as(C.POINTER(C.c_int64)),
+                    cfgs.ctypes.data_as(C.POINTER(C.c_uint32)), cfgs.size, C.byref(total))
+            if rc == L.TB_ERR_BAD_ARGUMENT and attempt == 0 and total.value > cfgs.size:
+                cfgs = np.zeros(total.value, dtype=np.uint32)
+                continue
+            L.check(rc, self.handle)
+            break
+        return sizes, row_off, cfgs[:total.value].copy()
+
+    def region_table(self, branch, boundary):
+        """tb_branching_table: the whole `branching_table(p, TensorNetworkSolver(), region)` of the reference (src/branch.jl:79)
+        in one call -- row optima, mis_compactify and all optimal configurations of the surviving rows, all on the device.
+        branch = the region's SlicedBranch (only its graph and weights are read), boundary = its open vertices (bit order of
+        the rows).  -> (sizes float64[2^rank], keep bool[2^rank], rows = [(boundary bits, size, [vertex masks, ascending])])"""
+        if isinstance(branch, Plan):
+            branch = branch._keep[0]
+        net, w = _network_of(branch, None, 0)
+        rank = len(boundary)
+        lab = np.asarray(list(boundary) + [0], dtype=np.int32)
+        keep = np.zeros(1 << rank, dtype=np.uint8)
+        sizes, row_off, cfgs = self._table_call(self._lib.tb_branching_table, net, lab, rank, keep.ctypes.data_as(C.POINTER(C.c_uint8)))
         del w
-        return sizes, row_off, cfgs[:total.value]
+        keep = keep.astype(bool)
+        return sizes, keep, [(int(a), float(sizes[a]), [int(c) for c in cfgs[row_off[a]:row_off[a + 1]]]) for a in np.nonzero(keep)[0]]
 
     def branching_table(self, plan: Plan, all_configs: bool = False):
         """The table `branching_table(p, TensorNetworkSolver(), region)` hands to the set-cover solver (src/branch.jl:79):

@@ -2598,11 +2598,18 @@ int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t*
     return TB_OK;
 } TB_CATCH(ctx)
 
-int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
-                     double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total) try {
+}  // extern "C"
+
+namespace {
+// tb_table_configs (compactify == false: rows chosen by `keep`, NULL = all) and tb_branching_table (compactify == true: the
+// dominated rows are dropped on the device between the optimum pass and the count pass, flags returned in out_keep)
+int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
+                       bool compactify, uint8_t* out_keep, double* out_sizes, int64_t* out_row_off, uint32_t* out_configs,
+                       int64_t cap, int64_t* out_total) {
     if (!ctx || !net || !out_row_off) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / net / out_row_off is NULL");
     if (!ctx->subs.empty())
-        return tb_table_configs(ctx->subs[0], net, boundary_labels, rank, keep, out_sizes, out_row_off, out_configs, cap, out_total);
+        return table_configs_impl(ctx->subs[0], net, boundary_labels, rank, keep, compactify, out_keep, out_sizes, out_row_off,
+                                  out_configs, cap, out_total);
     const int n = net->n_labels;
     if (n < 0 || n > 32) return set_err(ctx, TB_ERR_UNSUPPORTED, "a region has at most 32 vertices (configurations are 32-bit vertex masks)");
     if (rank < 0 || rank > n || rank > 24) return set_err(ctx, TB_ERR_UNSUPPORTED, "boundary rank must be in [0, min(n_labels, 24)]");
@@ -2654,10 +2661,10 @@ int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary
     if (n_cta > 0x7fffffffll) return set_err(ctx, TB_ERR_UNSUPPORTED, "region too large");
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    // device scratch: alpha keys | sizes | row offsets | chunk counts | chunk offsets | keep flags
+    // device scratch: alpha keys | sizes | row offsets | chunk counts | chunk offsets | subset maxima | keep flags
     const size_t b_rows = (size_t)n_rows * 8, b_off = (size_t)(n_rows + 1) * 8, b_cnt = (size_t)n_cta * 8, b_coff = (size_t)(n_cta + 1) * 8;
     uint8_t* d = nullptr;
-    TB_CUDA(ctx, cudaMalloc(&d, 2 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
+    TB_CUDA(ctx, cudaMalloc(&d, 3 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
     struct Free {
         void* p;
         ~Free() { if (p) cudaFree(p); }
@@ -2667,16 +2674,24 @@ int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary
     int64_t* d_row_off = (int64_t*)(d + 2 * b_rows);
     int64_t* d_cnt = (int64_t*)(d + 2 * b_rows + b_off);
     int64_t* d_coff = (int64_t*)(d + 2 * b_rows + b_off + b_cnt);
+    double* d_z = (double*)(d + 2 * b_rows + b_off + b_cnt + b_coff);
     uint8_t* d_keep = nullptr;
-    if (keep) {
-        d_keep = d + 2 * b_rows + b_off + b_cnt + b_coff;
-        TB_CUDA(ctx, cudaMemcpyAsync(d_keep, keep, (size_t)n_rows, cudaMemcpyHostToDevice, st));
-    }
+    if (keep || compactify) d_keep = d + 3 * b_rows + b_off + b_cnt + b_coff;
+    if (keep && !compactify) TB_CUDA(ctx, cudaMemcpyAsync(d_keep, keep, (size_t)n_rows, cudaMemcpyHostToDevice, st));
     const unsigned g_rows = (unsigned)((n_rows + 255) / 256);
+    int launches = 5;
     cudaEventRecord(ctx->ev0, st);
     k_region_init<<<g_rows, 256, 0, st>>>(d_alpha, n_rows);
     k_region_configs<0><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, nullptr, nullptr, nullptr, nullptr);
     k_region_sizes<<<g_rows, 256, 0, st>>>(d_alpha, d_sizes, n_rows);
+    if (compactify) {  // mis_compactify on the row optima (the kernels of tb_compactify_table)
+        TB_CUDA(ctx, cudaMemcpyAsync(d_z, d_sizes, b_rows, cudaMemcpyDeviceToDevice, st));
+        for (int bit = 0; bit < rank; ++bit)
+            k_subset_max_stage<<<(unsigned)((n_rows / 2 + 255) / 256), 256, 0, st>>>(d_z, bit, n_rows / 2);
+        k_table_keep<<<g_rows, 256, 0, st>>>(d_sizes, d_z, rank, d_keep, n_rows);
+        launches += rank + 1;
+        if (out_keep) TB_CUDA(ctx, cudaMemcpyAsync(out_keep, d_keep, (size_t)n_rows, cudaMemcpyDeviceToHost, st));
+    }
     k_region_configs<1><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, d_cnt, nullptr, nullptr);
     k_region_scan<<<1, 1024, 0, st>>>(d_cnt, d_coff, n_cta, d_row_off, n_rows, chunks_log2);
     TB_CUDA(ctx, cudaGetLastError());
@@ -2685,7 +2700,7 @@ int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary
     TB_CUDA(ctx, cudaStreamSynchronize(st));
     const int64_t total = out_row_off[n_rows];
     if (out_total) *out_total = total;
-    ctx->last_launches = 5;
+    ctx->last_launches = launches;
     if (out_configs && total > 0) {
         if (cap < total) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "out_configs holds " + std::to_string(cap) + " configurations, the table has " + std::to_string(total));
         uint32_t* d_out = nullptr;
@@ -2694,7 +2709,7 @@ int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary
         k_region_configs<2><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, nullptr, d_coff, d_out);
         TB_CUDA(ctx, cudaGetLastError());
         TB_CUDA(ctx, cudaMemcpyAsync(out_configs, d_out, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        ctx->last_launches = 6;
+        ctx->last_launches = launches + 1;
     }
     cudaEventRecord(ctx->ev1, st);
     TB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -2702,6 +2717,19 @@ int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary
     cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms;
     return TB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
+                     double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total) try {
+    return table_configs_impl(ctx, net, boundary_labels, rank, keep, false, nullptr, out_sizes, out_row_off, out_configs, cap, out_total);
+} TB_CATCH(ctx)
+
+int tb_branching_table(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, uint8_t* out_keep,
+                       double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total) try {
+    return table_configs_impl(ctx, net, boundary_labels, rank, nullptr, true, out_keep, out_sizes, out_row_off, out_configs, cap, out_total);
 } TB_CATCH(ctx)
 
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {

@@ -160,3 +160,51 @@ def test_gpu_table_configs_large_region_and_errors(tb, engine):
     with pytest.raises(tb.TBError) as e:
         engine.table_configs(br, [1, 1])
     assert e.value.code == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,seed,n_open", [(8, 1, 0), (10, 1, 3), (16, 2, 4), (20, 3, 5), (20, 8, 8)])
+@pytest.mark.parametrize("weights", [None, _int_weights])
+def test_gpu_region_table_single_call(tb, engine, n, seed, n_open, weights):
+    """tb_branching_table = optimum pass + mis_compactify + all optimal configurations in one call: equal to the oracle's
+    table (enumeration + the all-pairs restatement of mis_compactify) and to the chained calls through the contraction"""
+    root, br, open_labels, w = _region(tb, n, seed, n_open, weights)
+    sizes, keep, rows = engine.region_table(br, open_labels)
+    want_sizes, want_rows = O.table_configs_bruteforce(root.nv, root.edges, w, open_labels)
+    want_keep = O.mis_compactify_keep(want_sizes)
+    assert np.array_equal(sizes, want_sizes) and np.array_equal(keep, want_keep)
+    assert rows == [(a, want_sizes[a], want_rows[a]) for a in np.nonzero(want_keep)[0]]
+    assert engine.last_timing()[1] == 5 + n_open + 1 + 1
+    if weights is None:
+        p = tb.Plan(br, engine=engine)
+        labels, rows2 = engine.branching_table(p, all_configs=True)
+        order = {l: i for i, l in enumerate(open_labels)}
+        remap = lambda a: sum(((a >> i) & 1) << order[l] for i, l in enumerate(labels))  # noqa: E731
+        assert sorted((remap(a), s, tuple(m)) for a, s, m in rows2) == sorted((a, s, tuple(m)) for a, s, m in rows)
+
+
+@pytest.mark.gpu
+def test_gpu_region_table_larger_than_first_guess(tb, engine):
+    """13 disjoint edges, nothing open: 2^13 optimal sets in one row (more than the mirror's first buffer: one retry)"""
+    from workloads import standin_host as H
+    edges = [(2 * i, 2 * i + 1) for i in range(13)]
+    root = H.make_root(26, edges, seed=1)
+    br = tb.SlicedBranch(tb.MISProblem(26, edges, None), tb.CompressedEinsum(root.ixs, [], root.tree), 0)
+    sizes, keep, rows = engine.region_table(br, [])
+    assert list(sizes) == [13.0] and list(keep) == [True]
+    (a, size, masks), = rows
+    assert a == 0 and size == 13 and len(masks) == 1 << 13 and masks == sorted(set(masks))
+    assert all(bin(m).count("1") == 13 and not (m & (m >> 1) & 0x1555555) for m in masks)
+    # the C call itself: a short buffer fails with the total written
+    import ctypes as C
+    from tensorbranching_lib import L
+    from tbcuda.contract import _network_of
+    net, _ = _network_of(br, None, 0)
+    lab = np.zeros(1, dtype=np.int32)
+    off = np.zeros(2, dtype=np.int64)
+    buf = np.zeros(16, dtype=np.uint32)
+    total = C.c_int64()
+    rc = L.load().tb_branching_table(engine.handle, C.byref(net), lab.ctypes.data_as(C.POINTER(C.c_int32)), 0, None, None,
+                                     off.ctypes.data_as(C.POINTER(C.c_int64)), buf.ctypes.data_as(C.POINTER(C.c_uint32)), 16,
+                                     C.byref(total))
+    assert rc == L.TB_ERR_BAD_ARGUMENT and total.value == 1 << 13 and list(off) == [0, 1 << 13]
