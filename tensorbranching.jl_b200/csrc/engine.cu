@@ -119,6 +119,10 @@ struct tb_ctx {
     // (arrays keep their capacity), so a steady stream of calls neither allocates nor frees host memory per branch
     void* permute_buf = nullptr;  // tb_permute_bits: source | destination, kept between calls
     size_t permute_cap = 0;
+    void* table_buf = nullptr;    // tb_table_configs / tb_branching_table: device scratch and output rows, kept between calls
+    size_t table_cap = 0;         // (a host calls them once per branching step: no allocation in steady state)
+    void* table_out = nullptr;
+    size_t table_out_cap = 0;
     HelperJob helper;
     std::mutex pool_mu;
     std::vector<tb_plan*> plan_pool;
@@ -1618,6 +1622,8 @@ int tb_shutdown(tb_ctx* ctx) {
     ctx->resident = nullptr;
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->permute_buf) cudaFree(ctx->permute_buf);
+    if (ctx->table_buf) cudaFree(ctx->table_buf);
+    if (ctx->table_out) cudaFree(ctx->table_out);
     for (auto& c : ctx->chunks)
         if (c.d) cudaFree(c.d);
     for (auto& sl : ctx->slots) {
@@ -2663,12 +2669,19 @@ int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* bounda
     cudaStream_t st = ctx->stream;
     // device scratch: alpha keys | sizes | row offsets | chunk counts | chunk offsets | subset maxima | keep flags
     const size_t b_rows = (size_t)n_rows * 8, b_off = (size_t)(n_rows + 1) * 8, b_cnt = (size_t)n_cta * 8, b_coff = (size_t)(n_cta + 1) * 8;
-    uint8_t* d = nullptr;
-    TB_CUDA(ctx, cudaMalloc(&d, 3 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
-    struct Free {
-        void* p;
-        ~Free() { if (p) cudaFree(p); }
-    } free_d{d}, free_out{nullptr};
+    auto grow = [&](void*& buf, size_t& have, size_t need) -> cudaError_t {
+        if (have >= need) return cudaSuccess;
+        if (buf) cudaFree(buf);
+        buf = nullptr;
+        have = 0;
+        need = std::max<size_t>(need + need / 2, 1u << 20);
+        cudaError_t e = cudaMalloc(&buf, need);
+        if (e == cudaSuccess) have = need;
+        else buf = nullptr;
+        return e;
+    };
+    TB_CUDA(ctx, grow(ctx->table_buf, ctx->table_cap, 3 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
+    uint8_t* d = (uint8_t*)ctx->table_buf;
     unsigned long long* d_alpha = (unsigned long long*)d;
     double* d_sizes = (double*)(d + b_rows);
     int64_t* d_row_off = (int64_t*)(d + 2 * b_rows);
@@ -2703,9 +2716,8 @@ int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* bounda
     ctx->last_launches = launches;
     if (out_configs && total > 0) {
         if (cap < total) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "out_configs holds " + std::to_string(cap) + " configurations, the table has " + std::to_string(total));
-        uint32_t* d_out = nullptr;
-        TB_CUDA(ctx, cudaMalloc(&d_out, (size_t)total * sizeof(uint32_t)));
-        free_out.p = d_out;
+        TB_CUDA(ctx, grow(ctx->table_out, ctx->table_out_cap, (size_t)total * sizeof(uint32_t)));
+        uint32_t* d_out = (uint32_t*)ctx->table_out;
         k_region_configs<2><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, nullptr, d_coff, d_out);
         TB_CUDA(ctx, cudaGetLastError());
         TB_CUDA(ctx, cudaMemcpyAsync(out_configs, d_out, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
