@@ -324,6 +324,16 @@ int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary
 int tb_branching_table(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, uint8_t* out_keep,
                        double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total);
 
+/* The tables of MANY regions in the same launches (the reducer and the slicer of the reference ask for the table of one
+ * small region per vertex / per branching step: TensorNetworkReducer src/dynamic_ob.jl:6, table solver src/types.jl:46 --
+ * independent requests, so a host that has several at hand sends them together and pays the launch latency once).
+ * Region i = nets[i] with the open vertices boundary_labels[boundary_off[i] .. boundary_off[i+1]); its rows are
+ * [R_i, R_i + 2^rank_i) with R_i = the sum of 2^rank_j over j < i; out_keep / out_sizes have R_n entries, out_row_off R_n + 1
+ * (one CSR over the rows of all regions); everything else as tb_branching_table. */
+int tb_branching_tables(tb_ctx* ctx, const tb_network* nets, const int32_t* boundary_off, const int32_t* boundary_labels, int64_t n,
+                        uint8_t* out_keep, double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap,
+                        int64_t* out_total);
+
 /* after tb_contract on a TB_PLAN_KEEP_INTERMEDIATES plan: copy tensor `node` (any internal node id,
  * or the root) to the host as doubles (-inf for tropical zero), 2^rank elements, and its layout. */
 int tb_plan_read_tensor(tb_ctx* ctx, tb_plan* plan, int32_t node, double* out_data, int64_t cap,

@@ -65,7 +65,7 @@ class tb_step_info(C.Structure):
 # every symbol include/tbcuda.h declares
 EXPORTS = ["tb_version", "tb_init", "tb_init_multi", "tb_device_count", "tb_estimate", "tb_estimate_many", "tb_shutdown", "tb_last_error", "tb_plan_create", "tb_plan_destroy",
            "tb_plan_info", "tb_plan_export", "tb_plan_export_raw", "tb_contract", "tb_contract_batch",
-           "tb_contract_networks", "tb_contract_sliced", "tb_suggest_slices", "tb_stream_begin", "tb_stream_push", "tb_stream_finish", "tb_contract_tensor", "tb_contract_table", "tb_compactify_table", "tb_table_configs", "tb_branching_table", "tb_plan_reassign", "tb_plan_read_tensor", "tb_last_timing", "tb_permute_bits", "tb_set_stream", "tb_profile",
+           "tb_contract_networks", "tb_contract_sliced", "tb_suggest_slices", "tb_stream_begin", "tb_stream_push", "tb_stream_finish", "tb_contract_tensor", "tb_contract_table", "tb_compactify_table", "tb_table_configs", "tb_branching_table", "tb_branching_tables", "tb_plan_reassign", "tb_plan_read_tensor", "tb_last_timing", "tb_permute_bits", "tb_set_stream", "tb_profile",
            "tb_last_profile", "tb_last_profile_union", "tb_last_transfers", "tb_last_host_breakdown"]
 
 _lib = None
@@ -117,6 +117,9 @@ def load():
                                      C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint32), C.c_int64,
                                      C.POINTER(C.c_int64)]
     lib.tb_branching_table.argtypes = lib.tb_table_configs.argtypes
+    lib.tb_branching_tables.argtypes = [vp, C.POINTER(tb_network), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int64,
+                                        C.POINTER(C.c_uint8), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint32),
+                                        C.c_int64, C.POINTER(C.c_int64)]
     lib.tb_plan_reassign.argtypes = [vp, C.POINTER(C.c_uint8), C.POINTER(vp)]
     lib.tb_stream_begin.argtypes = [vp, C.c_int64, C.POINTER(vp)]
     lib.tb_stream_push.argtypes = [vp, C.POINTER(tb_network), C.POINTER(C.c_double), C.c_int64]

@@ -311,6 +311,46 @@ class Engine:
         keep = keep.astype(bool)
         return sizes, keep, [(int(a), float(sizes[a]), [int(c) for c in cfgs[row_off[a]:row_off[a + 1]]]) for a in np.nonzero(keep)[0]]
 
+    def region_tables(self, branches, boundaries):
+        """tb_branching_tables: the tables of many regions in the same launches.
+        -> one (sizes, keep, rows) per region, each as region_table returns it"""
+        n = len(branches)
+        if n == 0:
+            return []
+        branches = [b._keep[0] if isinstance(b, Plan) else b for b in branches]
+        pairs = [_network_of(b, None, 0) for b in branches]
+        nets = (L.tb_network * n)(*[p[0] for p in pairs])
+        ranks = [len(b) for b in boundaries]
+        boff = np.zeros(n + 1, dtype=np.int32)
+        boff[1:] = np.cumsum(ranks)
+        lab = np.asarray([v for b in boundaries for v in b] + [0], dtype=np.int32)
+        base = np.zeros(n + 1, dtype=np.int64)
+        base[1:] = np.cumsum([1 << r for r in ranks])
+        n_rows = int(base[-1])
+        keep = np.zeros(n_rows, dtype=np.uint8)
+        sizes = np.empty(n_rows, dtype=np.float64)
+        row_off = np.zeros(n_rows + 1, dtype=np.int64)
+        total = C.c_int64()
+        cfgs = np.zeros(max(4096, 64 * n), dtype=np.uint32)
+        for attempt in (0, 1):
+            rc = self._lib.tb_branching_tables(self.handle, nets, boff.ctypes.data_as(C.POINTER(C.c_int32)),
+                                               lab.ctypes.data_as(C.POINTER(C.c_int32)), n, keep.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                               sizes.ctypes.data_as(C.POINTER(C.c_double)), row_off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                               cfgs.ctypes.data_as(C.POINTER(C.c_uint32)), cfgs.size, C.byref(total))
+            if rc == L.TB_ERR_BAD_ARGUMENT and attempt == 0 and total.value > cfgs.size:
+                cfgs = np.zeros(total.value, dtype=np.uint32)
+                continue
+            L.check(rc, self.handle)
+            break
+        del pairs
+        out = []
+        for i in range(n):
+            lo, hi = int(base[i]), int(base[i + 1])
+            kp = keep[lo:hi].astype(bool)
+            rows = [(int(a), float(sizes[lo + a]), [int(c) for c in cfgs[row_off[lo + a]:row_off[lo + a + 1]]]) for a in np.nonzero(kp)[0]]
+            out.append((sizes[lo:hi].copy(), kp, rows))
+        return out
+
     def branching_table(self, plan: Plan, all_configs: bool = False):
         """The table `branching_table(p, TensorNetworkSolver(), region)` hands to the set-cover solver (src/branch.jl:79):
         contract the region's network (boundary vertices open), drop the dominated boundary configurations.

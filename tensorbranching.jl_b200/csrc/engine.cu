@@ -2607,20 +2607,14 @@ int tb_compactify_table(tb_ctx* ctx, int32_t rank, const double* sizes, uint8_t*
 }  // extern "C"
 
 namespace {
-// tb_table_configs (compactify == false: rows chosen by `keep`, NULL = all) and tb_branching_table (compactify == true: the
-// dominated rows are dropped on the device between the optimum pass and the count pass, flags returned in out_keep)
-int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
-                       bool compactify, uint8_t* out_keep, double* out_sizes, int64_t* out_row_off, uint32_t* out_configs,
-                       int64_t cap, int64_t* out_total) {
-    if (!ctx || !net || !out_row_off) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / net / out_row_off is NULL");
-    if (!ctx->subs.empty())
-        return table_configs_impl(ctx->subs[0], net, boundary_labels, rank, keep, compactify, out_keep, out_sizes, out_row_off,
-                                  out_configs, cap, out_total);
+// One region of a batch: the region's graph read off the network's leaves (1 label = vertex tensor [0, w_v], 2 labels = edge
+// tensor; tbcuda.h, tb_network -- the tree is not used) and its boundary vertices in the bit order of its rows.
+int region_desc_of(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, RegionDesc& R) {
     const int n = net->n_labels;
     if (n < 0 || n > 32) return set_err(ctx, TB_ERR_UNSUPPORTED, "a region has at most 32 vertices (configurations are 32-bit vertex masks)");
     if (rank < 0 || rank > n || rank > 24) return set_err(ctx, TB_ERR_UNSUPPORTED, "boundary rank must be in [0, min(n_labels, 24)]");
     if (rank > 0 && !boundary_labels) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "boundary_labels is NULL");
-    if (net->n_fixed != 0) return set_err(ctx, TB_ERR_UNSUPPORTED, "tb_table_configs does not take index-sliced networks");
+    if (net->n_fixed != 0) return set_err(ctx, TB_ERR_UNSUPPORTED, "the table calls do not take index-sliced networks");
     if (net->n_leaves < 0 || (net->n_leaves > 0 && (!net->leaf_off || !net->leaf_labels)))
         return set_err(ctx, TB_ERR_BAD_ARGUMENT, "leaf arrays are NULL");
     const int wd = net->weight_dtype;
@@ -2635,8 +2629,6 @@ int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* bounda
             default: return 1.0;
         }
     };
-    // the region's graph, read off the leaves: 1 label = vertex tensor [0, w_v], 2 labels = edge tensor (tbcuda.h, tb_network)
-    RegionDesc R;
     std::memset(&R, 0, sizeof(R));
     R.n = n;
     R.rank = rank;
@@ -2662,13 +2654,40 @@ int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* bounda
     for (int v = 0; v < n; ++v)
         if (!((bset >> v) & 1)) R.ipos[R.n_int++] = (uint8_t)v;
     R.chunk_log2 = std::min(R.n_int, 12);
-    const int chunks_log2 = R.n_int - R.chunk_log2;
-    const int64_t n_rows = (int64_t)1 << rank, n_cta = n_rows << chunks_log2;
-    if (n_cta > 0x7fffffffll) return set_err(ctx, TB_ERR_UNSUPPORTED, "region too large");
+    return TB_OK;
+}
+
+// tb_table_configs (compactify == false: rows chosen by `keep`, NULL = all), tb_branching_table(s) (compactify == true: the
+// dominated rows are dropped on the device between the optimum pass and the count pass, flags returned in out_keep), over a
+// batch of n regions in the same launches.  Rows of region i: [row_base_i, row_base_i + 2^rank_i).
+int table_configs_impl(tb_ctx* ctx, const tb_network* nets, const int32_t* boundary_off, const int32_t* boundary_labels, int64_t n,
+                       const uint8_t* keep, bool compactify, uint8_t* out_keep, double* out_sizes, int64_t* out_row_off,
+                       uint32_t* out_configs, int64_t cap, int64_t* out_total) {
+    if (!ctx || !out_row_off) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "ctx / out_row_off is NULL");
+    if (n < 0 || n > 0x7fffffffll || (n > 0 && (!nets || !boundary_off))) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "bad region list");
+    if (!ctx->subs.empty())
+        return table_configs_impl(ctx->subs[0], nets, boundary_off, boundary_labels, n, keep, compactify, out_keep, out_sizes,
+                                  out_row_off, out_configs, cap, out_total);
+    if (out_total) *out_total = 0;
+    out_row_off[0] = 0;
+    if (n == 0) return TB_OK;
+    std::vector<RegionDesc> regs((size_t)n);
+    int64_t n_rows = 0, n_cta = 0;
+    int max_rank = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t rank = boundary_off[i + 1] - boundary_off[i];
+        int rc = region_desc_of(ctx, &nets[i], boundary_labels ? boundary_labels + boundary_off[i] : nullptr, rank, regs[(size_t)i]);
+        if (rc) return rc;
+        RegionDesc& R = regs[(size_t)i];
+        R.row_base = n_rows;
+        R.cta_base = n_cta;
+        n_rows += (int64_t)1 << rank;
+        n_cta += (int64_t)1 << (rank + R.n_int - R.chunk_log2);
+        max_rank = std::max(max_rank, (int)rank);
+        if (n_cta > 0x7fffffffll || n_rows > ((int64_t)1 << 28)) return set_err(ctx, TB_ERR_UNSUPPORTED, "the batch of regions is too large for one call");
+    }
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    // device scratch: alpha keys | sizes | row offsets | chunk counts | chunk offsets | subset maxima | keep flags
-    const size_t b_rows = (size_t)n_rows * 8, b_off = (size_t)(n_rows + 1) * 8, b_cnt = (size_t)n_cta * 8, b_coff = (size_t)(n_cta + 1) * 8;
     auto grow = [&](void*& buf, size_t& have, size_t need) -> cudaError_t {
         if (have >= need) return cudaSuccess;
         if (buf) cudaFree(buf);
@@ -2680,33 +2699,38 @@ int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* bounda
         else buf = nullptr;
         return e;
     };
-    TB_CUDA(ctx, grow(ctx->table_buf, ctx->table_cap, 3 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
+    // device scratch: region descriptors | alpha keys | sizes | subset maxima | row offsets | chunk counts | chunk offsets | keep flags
+    const size_t b_regs = (size_t)n * sizeof(RegionDesc), b_rows = (size_t)n_rows * 8, b_off = (size_t)(n_rows + 1) * 8,
+                 b_cnt = (size_t)n_cta * 8, b_coff = (size_t)(n_cta + 1) * 8;
+    TB_CUDA(ctx, grow(ctx->table_buf, ctx->table_cap, b_regs + 3 * b_rows + b_off + b_cnt + b_coff + (size_t)n_rows));
     uint8_t* d = (uint8_t*)ctx->table_buf;
-    unsigned long long* d_alpha = (unsigned long long*)d;
-    double* d_sizes = (double*)(d + b_rows);
-    int64_t* d_row_off = (int64_t*)(d + 2 * b_rows);
-    int64_t* d_cnt = (int64_t*)(d + 2 * b_rows + b_off);
-    int64_t* d_coff = (int64_t*)(d + 2 * b_rows + b_off + b_cnt);
-    double* d_z = (double*)(d + 2 * b_rows + b_off + b_cnt + b_coff);
+    RegionDesc* d_regs = (RegionDesc*)d;
+    unsigned long long* d_alpha = (unsigned long long*)(d + b_regs);
+    double* d_sizes = (double*)(d + b_regs + b_rows);
+    double* d_z = (double*)(d + b_regs + 2 * b_rows);
+    int64_t* d_row_off = (int64_t*)(d + b_regs + 3 * b_rows);
+    int64_t* d_cnt = (int64_t*)(d + b_regs + 3 * b_rows + b_off);
+    int64_t* d_coff = (int64_t*)(d + b_regs + 3 * b_rows + b_off + b_cnt);
     uint8_t* d_keep = nullptr;
-    if (keep || compactify) d_keep = d + 3 * b_rows + b_off + b_cnt + b_coff;
+    if (keep || compactify) d_keep = d + b_regs + 3 * b_rows + b_off + b_cnt + b_coff;
+    TB_CUDA(ctx, cudaMemcpyAsync(d_regs, regs.data(), b_regs, cudaMemcpyHostToDevice, st));  // (pageable source: staged before the call returns)
     if (keep && !compactify) TB_CUDA(ctx, cudaMemcpyAsync(d_keep, keep, (size_t)n_rows, cudaMemcpyHostToDevice, st));
     const unsigned g_rows = (unsigned)((n_rows + 255) / 256);
-    int launches = 5;
+    const int nr = (int)n;
+    int launches = 6;
     cudaEventRecord(ctx->ev0, st);
     k_region_init<<<g_rows, 256, 0, st>>>(d_alpha, n_rows);
-    k_region_configs<0><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, nullptr, nullptr, nullptr, nullptr);
-    k_region_sizes<<<g_rows, 256, 0, st>>>(d_alpha, d_sizes, n_rows);
-    if (compactify) {  // mis_compactify on the row optima (the kernels of tb_compactify_table)
-        TB_CUDA(ctx, cudaMemcpyAsync(d_z, d_sizes, b_rows, cudaMemcpyDeviceToDevice, st));
-        for (int bit = 0; bit < rank; ++bit)
-            k_subset_max_stage<<<(unsigned)((n_rows / 2 + 255) / 256), 256, 0, st>>>(d_z, bit, n_rows / 2);
-        k_table_keep<<<g_rows, 256, 0, st>>>(d_sizes, d_z, rank, d_keep, n_rows);
-        launches += rank + 1;
+    k_region_configs<0><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(d_regs, nr, d_alpha, nullptr, nullptr, nullptr, nullptr);
+    k_region_sizes<<<g_rows, 256, 0, st>>>(d_alpha, d_sizes, d_z, n_rows);
+    if (compactify) {  // mis_compactify on the row optima of every region
+        for (int bit = 0; bit < max_rank; ++bit) k_region_subset_max<<<g_rows, 256, 0, st>>>(d_regs, nr, d_z, bit, n_rows);
+        k_region_keep<<<g_rows, 256, 0, st>>>(d_regs, nr, d_sizes, d_z, d_keep, n_rows);
+        launches += max_rank + 1;
         if (out_keep) TB_CUDA(ctx, cudaMemcpyAsync(out_keep, d_keep, (size_t)n_rows, cudaMemcpyDeviceToHost, st));
     }
-    k_region_configs<1><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, d_cnt, nullptr, nullptr);
-    k_region_scan<<<1, 1024, 0, st>>>(d_cnt, d_coff, n_cta, d_row_off, n_rows, chunks_log2);
+    k_region_configs<1><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(d_regs, nr, d_alpha, d_keep, d_cnt, nullptr, nullptr);
+    k_region_scan<<<1, 1024, 0, st>>>(d_cnt, d_coff, n_cta);
+    k_region_row_off<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(d_regs, nr, d_coff, n_cta, d_row_off, n_rows);
     TB_CUDA(ctx, cudaGetLastError());
     TB_CUDA(ctx, cudaMemcpyAsync(out_row_off, d_row_off, b_off, cudaMemcpyDeviceToHost, st));
     if (out_sizes) TB_CUDA(ctx, cudaMemcpyAsync(out_sizes, d_sizes, b_rows, cudaMemcpyDeviceToHost, st));
@@ -2718,7 +2742,7 @@ int table_configs_impl(tb_ctx* ctx, const tb_network* net, const int32_t* bounda
         if (cap < total) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "out_configs holds " + std::to_string(cap) + " configurations, the table has " + std::to_string(total));
         TB_CUDA(ctx, grow(ctx->table_out, ctx->table_out_cap, (size_t)total * sizeof(uint32_t)));
         uint32_t* d_out = (uint32_t*)ctx->table_out;
-        k_region_configs<2><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(R, d_alpha, d_keep, nullptr, d_coff, d_out);
+        k_region_configs<2><<<(unsigned)n_cta, kRegionThreads, 0, st>>>(d_regs, nr, d_alpha, d_keep, nullptr, d_coff, d_out);
         TB_CUDA(ctx, cudaGetLastError());
         TB_CUDA(ctx, cudaMemcpyAsync(out_configs, d_out, (size_t)total * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         ctx->last_launches = launches + 1;
@@ -2736,12 +2760,22 @@ extern "C" {
 
 int tb_table_configs(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, const uint8_t* keep,
                      double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total) try {
-    return table_configs_impl(ctx, net, boundary_labels, rank, keep, false, nullptr, out_sizes, out_row_off, out_configs, cap, out_total);
+    if (!net) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL");
+    const int32_t off[2] = {0, rank};
+    return table_configs_impl(ctx, net, off, boundary_labels, 1, keep, false, nullptr, out_sizes, out_row_off, out_configs, cap, out_total);
 } TB_CATCH(ctx)
 
 int tb_branching_table(tb_ctx* ctx, const tb_network* net, const int32_t* boundary_labels, int32_t rank, uint8_t* out_keep,
                        double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap, int64_t* out_total) try {
-    return table_configs_impl(ctx, net, boundary_labels, rank, nullptr, true, out_keep, out_sizes, out_row_off, out_configs, cap, out_total);
+    if (!net) return set_err(ctx, TB_ERR_BAD_ARGUMENT, "net is NULL");
+    const int32_t off[2] = {0, rank};
+    return table_configs_impl(ctx, net, off, boundary_labels, 1, nullptr, true, out_keep, out_sizes, out_row_off, out_configs, cap, out_total);
+} TB_CATCH(ctx)
+
+int tb_branching_tables(tb_ctx* ctx, const tb_network* nets, const int32_t* boundary_off, const int32_t* boundary_labels, int64_t n,
+                        uint8_t* out_keep, double* out_sizes, int64_t* out_row_off, uint32_t* out_configs, int64_t cap,
+                        int64_t* out_total) try {
+    return table_configs_impl(ctx, nets, boundary_off, boundary_labels, n, nullptr, true, out_keep, out_sizes, out_row_off, out_configs, cap, out_total);
 } TB_CATCH(ctx)
 
 int tb_last_timing(const tb_ctx* ctx, double* out_device_ms, int64_t* out_launches) {

@@ -1688,16 +1688,18 @@ __global__ void k_table_keep(const double* __restrict__ sizes, const double* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// ALL optimal configurations of a branching table (the ConfigsMax element type of the reference's table solver,
-// reached from src/branch.jl:79).  A region has at most 32 vertices (n_max = 20 by default, src/types.jl:10), so the set
-// algebra of the reference (unions and cartesian products of configuration sets carried through the contraction) is
-// replaced by a filter over the 2^n vertex sets of the region: a set belongs to the row of its boundary configuration a
-// iff it is independent and its weight equals the row's optimum.  Index space: (boundary configuration a, chunk of the
-// 2^n_int interior configurations); one CTA per (a, chunk), a thread walks the chunk with stride blockDim.
-//   pass 0: alpha[a] = max weight (atomicMax on an order-preserving integer image of the double)
-//   pass 1: chunk_count[cta] = number of optimal sets in the chunk (rows with keep[a] == 0 count nothing)
+// ALL optimal configurations of branching tables (the ConfigsMax element type of the reference's table solver,
+// reached from src/branch.jl:79), for a BATCH of regions in the same launches.  A region has at most 32 vertices
+// (n_max = 20 by default, src/types.jl:10), so the set algebra of the reference (unions and cartesian products of
+// configuration sets carried through the contraction) is replaced by a filter over the 2^n vertex sets of the region: a
+// set belongs to the row of its boundary configuration a iff it is independent and its weight equals the row's optimum.
+// Index space: (region, boundary configuration a, chunk of the 2^n_int interior configurations); one CTA per triple (the
+// region is found by bisection over the regions' first-CTA numbers), a thread walks the chunk with stride blockDim.
+//   pass 0: alpha[row] = max weight (atomicMax on an order-preserving integer image of the double)
+//   (mis_compactify of every region's alpha: subset-max stages + keep flags, batched over all rows)
+//   pass 1: chunk_count[cta] = number of optimal sets in the chunk (rows with keep == 0 count nothing)
 //   pass 2: the sets are written at chunk_off[cta] in ascending interior index (block-wide ordered compaction), so the
-//           output is deterministic: rows in boundary-configuration order, each row sorted.
+//           output is deterministic: regions in order, rows in boundary-configuration order, each row sorted.
 // ------------------------------------------------------------------------------------------------
 struct RegionDesc {
     double w[32];           // weight of vertex v (sum of its vertex tensors' weights)
@@ -1706,7 +1708,10 @@ struct RegionDesc {
     uint8_t ipos[32];       // interior bit i of a chunk index -> vertex
     int32_t n, rank, n_int; // vertices, boundary vertices, interior vertices
     int32_t chunk_log2;     // interior configurations per CTA = 2^chunk_log2
+    int64_t row_base;       // first row of the region in the batch's row arrays (sum of 2^rank of the regions before it)
+    int64_t cta_base;       // first CTA of the region
 };
+static_assert(sizeof(RegionDesc) % 8 == 0, "RegionDesc is copied as 8-byte words");
 static constexpr int kRegionThreads = 256;
 
 __device__ __forceinline__ unsigned long long region_key(double x) {  // order-preserving: x < y <=> key(x) < key(y)
@@ -1736,23 +1741,45 @@ __device__ __forceinline__ double region_weight(const RegionDesc& R, uint32_t cf
     }
     return s;
 }
+// the region that owns element x of an array laid out region by region: largest r with first(r) <= x
+template <typename F>
+__device__ __forceinline__ int region_of(int n_regions, int64_t x, F first) {
+    int lo = 0, hi = n_regions - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (first(mid) <= x) lo = mid;
+        else hi = mid - 1;
+    }
+    return lo;
+}
 
 template <int PASS>
 __global__ void __launch_bounds__(kRegionThreads)
-k_region_configs(const __grid_constant__ RegionDesc R, unsigned long long* __restrict__ alpha_key, const uint8_t* __restrict__ keep,
-                 int64_t* __restrict__ chunk_count, const int64_t* __restrict__ chunk_off, uint32_t* __restrict__ out_configs) {
+k_region_configs(const RegionDesc* __restrict__ regs, int n_regions, unsigned long long* __restrict__ alpha_key,
+                 const uint8_t* __restrict__ keep, int64_t* __restrict__ chunk_count, const int64_t* __restrict__ chunk_off,
+                 uint32_t* __restrict__ out_configs) {
+    __shared__ RegionDesc R;
     __shared__ uint32_t warp_tot[kRegionThreads / 32];
     __shared__ unsigned long long red[kRegionThreads / 32];
+    const int64_t cta = blockIdx.x;
+    {
+        const int r = region_of(n_regions, cta, [&](int q) { return regs[q].cta_base; });
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(regs + r);
+        unsigned long long* dst = reinterpret_cast<unsigned long long*>(&R);
+        for (int i = threadIdx.x; i < (int)(sizeof(RegionDesc) / 8); i += kRegionThreads) dst[i] = src[i];
+    }
+    __syncthreads();
     const int chunks_log2 = R.n_int - R.chunk_log2;
-    const uint64_t cta = blockIdx.x;
-    const uint64_t a = cta >> chunks_log2, chunk = cta & (((uint64_t)1 << chunks_log2) - 1);
+    const uint64_t local = (uint64_t)(cta - R.cta_base);
+    const uint64_t a = local >> chunks_log2, chunk = local & (((uint64_t)1 << chunks_log2) - 1);
+    const int64_t row = R.row_base + (int64_t)a;
     const uint32_t bmask = region_deposit(a, R.bpos);
     const uint64_t i0 = chunk << R.chunk_log2, len = (uint64_t)1 << R.chunk_log2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double row_best = -INFINITY;
     if (PASS > 0) {
-        row_best = region_unkey(alpha_key[a]);
-        if (row_best == -INFINITY || (keep && !keep[a])) {  // infeasible or dropped row: nothing to count or write
+        row_best = region_unkey(alpha_key[row]);
+        if (row_best == -INFINITY || (keep && !keep[row])) {  // infeasible or dropped row: nothing to count or write
             if (PASS == 1 && threadIdx.x == 0) chunk_count[cta] = 0;
             return;
         }
@@ -1796,7 +1823,7 @@ k_region_configs(const __grid_constant__ RegionDesc R, unsigned long long* __res
         __syncthreads();
         if (threadIdx.x == 0) {
             for (int q = 1; q < kRegionThreads / 32; ++q) k = red[q] > k ? red[q] : k;
-            atomicMax(&alpha_key[a], k);
+            atomicMax(&alpha_key[row], k);
         }
     }
     if (PASS == 1) {
@@ -1812,9 +1839,8 @@ k_region_configs(const __grid_constant__ RegionDesc R, unsigned long long* __res
 }
 
 // exclusive prefix sum of the chunk counts (one CTA: a contiguous segment per thread, then a scan of the 1024 segment sums);
-// off[n] = total.  row_off[a] = off[a << chunks_log2] for a <= n_rows.
-__global__ void __launch_bounds__(1024) k_region_scan(const int64_t* __restrict__ count, int64_t* __restrict__ off, int64_t n,
-                                                      int64_t* __restrict__ row_off, int64_t n_rows, int chunks_log2) {
+// off[n] = total
+__global__ void __launch_bounds__(1024) k_region_scan(const int64_t* __restrict__ count, int64_t* __restrict__ off, int64_t n) {
     __shared__ int64_t seg[1024];
     const int64_t per = (n + 1023) / 1024, lo = min(n, per * threadIdx.x), hi = min(n, lo + per);
     int64_t s = 0;
@@ -1836,14 +1862,48 @@ __global__ void __launch_bounds__(1024) k_region_scan(const int64_t* __restrict_
         off[i] = s;
         s += count[i];
     }
-    __syncthreads();
-    __threadfence_block();
-    for (int64_t a = threadIdx.x; a <= n_rows; a += 1024) row_off[a] = a == n_rows ? off[n] : off[a << chunks_log2];
 }
 
-__global__ void k_region_sizes(const unsigned long long* __restrict__ alpha_key, double* __restrict__ sizes, int64_t n) {
+// per row of the batch: its offset into the configuration array = the offset of its first chunk; row_off[n_rows] = total
+__global__ void k_region_row_off(const RegionDesc* __restrict__ regs, int n_regions, const int64_t* __restrict__ chunk_off,
+                                 int64_t n_cta, int64_t* __restrict__ row_off, int64_t n_rows) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_rows) return;
+    if (g == n_rows) {
+        row_off[g] = chunk_off[n_cta];
+        return;
+    }
+    const int r = region_of(n_regions, g, [&](int q) { return regs[q].row_base; });
+    const int chunks_log2 = regs[r].n_int - regs[r].chunk_log2;
+    row_off[g] = chunk_off[regs[r].cta_base + ((g - regs[r].row_base) << chunks_log2)];
+}
+
+// mis_compactify of every region of the batch: one stage of the subset-max transform (rows whose configuration has `bit`
+// set take the max with the row that lacks it; regions of rank <= bit are left alone) ...
+__global__ void k_region_subset_max(const RegionDesc* __restrict__ regs, int n_regions, double* __restrict__ z, int bit, int64_t n_rows) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rows) return;
+    const int r = region_of(n_regions, g, [&](int q) { return regs[q].row_base; });
+    const int64_t a = g - regs[r].row_base;
+    if (bit < regs[r].rank && ((a >> bit) & 1)) z[g] = fmax(z[g], z[g - ((int64_t)1 << bit)]);
+}
+// ... and the keep flags (as k_table_keep, per region)
+__global__ void k_region_keep(const RegionDesc* __restrict__ regs, int n_regions, const double* __restrict__ sizes,
+                              const double* __restrict__ z, uint8_t* __restrict__ keep, int64_t n_rows) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rows) return;
+    const int r = region_of(n_regions, g, [&](int q) { return regs[q].row_base; });
+    const int64_t a = g - regs[r].row_base;
+    const double v = sizes[g];
+    double best = -INFINITY;
+    for (int i = 0; i < regs[r].rank; ++i)
+        if ((a >> i) & 1) best = fmax(best, z[g - ((int64_t)1 << i)]);
+    keep[g] = (v > -INFINITY && !(best >= v)) ? 1 : 0;
+}
+
+__global__ void k_region_sizes(const unsigned long long* __restrict__ alpha_key, double* __restrict__ sizes, double* __restrict__ z, int64_t n) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a < n) sizes[a] = region_unkey(alpha_key[a]);
+    if (a < n) sizes[a] = z[a] = region_unkey(alpha_key[a]);
 }
 __global__ void k_region_init(unsigned long long* __restrict__ alpha_key, int64_t n) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -82,7 +82,7 @@ def test_gpu_table_configs(tb, engine, n, seed, n_open, weights):
     sizes, row_off, cfgs = engine.table_configs(br, labels)
     _check_against_oracle(root, w, labels, sizes, row_off, cfgs)
     ms, launches = engine.last_timing()
-    assert launches == 6 and ms > 0
+    assert launches == 7 and ms > 0  # init, optimum, sizes, count, scan, row offsets, write
     if n <= 14 and weights is not _real_weights and weights is not _tied_real_weights:
         # the reference's algebra along the tree gives the same rows
         left, right = O.nested_to_postorder(root.tree, len(root.ixs))
@@ -174,7 +174,7 @@ def test_gpu_region_table_single_call(tb, engine, n, seed, n_open, weights):
     want_keep = O.mis_compactify_keep(want_sizes)
     assert np.array_equal(sizes, want_sizes) and np.array_equal(keep, want_keep)
     assert rows == [(a, want_sizes[a], want_rows[a]) for a in np.nonzero(want_keep)[0]]
-    assert engine.last_timing()[1] == 5 + n_open + 1 + 1
+    assert engine.last_timing()[1] == 6 + n_open + 1 + 1  # + mis_compactify: one stage per boundary vertex, keep flags
     if weights is None:
         p = tb.Plan(br, engine=engine)
         labels, rows2 = engine.branching_table(p, all_configs=True)
@@ -208,3 +208,27 @@ def test_gpu_region_table_larger_than_first_guess(tb, engine):
                                      off.ctypes.data_as(C.POINTER(C.c_int64)), buf.ctypes.data_as(C.POINTER(C.c_uint32)), 16,
                                      C.byref(total))
     assert rc == L.TB_ERR_BAD_ARGUMENT and total.value == 1 << 13 and list(off) == [0, 1 << 13]
+
+
+@pytest.mark.gpu
+def test_gpu_region_tables_batched(tb, engine):
+    """many regions in the same launches (different sizes, ranks and weight kinds, a region without boundary, one with
+    nothing but boundary): every region's table equals its own single call and the oracle"""
+    specs = [(10, 1, 3, None), (16, 2, 4, _int_weights), (8, 1, 0, None), (20, 3, 5, None), (6, 2, 6, None), (14, 3, 5, _real_weights),
+             (18, 5, 6, _tied_real_weights), (12, 2, 4, None), (20, 8, 8, _int_weights)] + [(10 + 2 * (i % 3), 20 + i, i % 5, None) for i in range(40)]
+    regions = [_region(tb, n, seed, n_open, w) for n, seed, n_open, w in specs]
+    got = engine.region_tables([r[1] for r in regions], [r[2] for r in regions])
+    ms, launches = engine.last_timing()
+    assert launches == 6 + 8 + 1 + 1 and len(got) == len(specs)
+    for (root, br, open_labels, w), (sizes, keep, rows) in zip(regions, got):
+        want_sizes, want_rows = O.table_configs_bruteforce(root.nv, root.edges, w, open_labels)
+        want_keep = O.mis_compactify_keep(want_sizes)
+        assert np.array_equal(sizes, want_sizes) and np.array_equal(keep, want_keep)
+        assert rows == [(a, want_sizes[a], want_rows[a]) for a in np.nonzero(want_keep)[0]]
+    one = engine.region_table(regions[3][1], regions[3][2])
+    assert np.array_equal(one[0], got[3][0]) and np.array_equal(one[1], got[3][1]) and one[2] == got[3][2]
+    assert engine.region_tables([], []) == []
+    # a bad region fails the call with its error code
+    with pytest.raises(tb.TBError) as e:
+        engine.region_tables([regions[0][1], regions[1][1]], [regions[0][2], [1, 1]])
+    assert e.value.code == -1
