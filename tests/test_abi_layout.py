@@ -144,3 +144,14 @@ def test_plain_c_client_cfg2(c_client, tmp_path):
     head, vals, stat = _run_client(c_client, path, ",".join(str(d) for d in range(n)))
     assert head["devices"] == n and not stat.any()
     assert np.array_equal(vals, np.asarray(rec["values"])) and head["max"] == rec["mis"]
+
+
+@pytest.mark.gpu
+def test_plain_c_client_branching_tables(tmp_path):
+    """tb_branching_table / tb_table_configs / tb_branching_tables from plain C on known tables (tests/abi/c_table.c)"""
+    exe = tmp_path / "c_table"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ABI, "c_table.c"), "-o", str(exe),
+                           "-L", os.path.dirname(L.LIB_PATH), "-ltbcuda", "-Wl,-rpath," + os.path.dirname(L.LIB_PATH)])
+    out = subprocess.check_output([str(exe)], text=True, timeout=300)
+    assert out.strip().splitlines()[-1] == "ok"
