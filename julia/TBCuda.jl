@@ -191,9 +191,12 @@ end
 # p.g); bit i-1 of a returned configuration is vertex vs[i], as in the reference's BranchingTable.  A maintainer hooks it in
 # with `OptimalBranchingCore.branching_table(p::MISProblem, ::TensorNetworkSolver, vs) = BranchingTable(length(vs),
 # TBCuda.branching_table_cuda(p.g, p.weights, vs, open_vertices(p.g, vs)))` (then prune_by_env as before, on the host).
-function branching_table_cuda(g, weights, vs::Vector{Int}, ovs::Vector{Int})
+struct FlatRegion   # keeps the arrays alive while the C call runs
+    leaf_off::Vector{Int32}; leaf_labels::Vector{Int32}; weights::Any; boundary::Vector{Int32}; net::TbNetwork
+end
+function FlatRegion(g, weights, vs::Vector{Int}, ovs::Vector{Int})
     n = length(vs)
-    n <= 32 || error("TBCuda.branching_table_cuda: a region has at most 32 vertices")
+    n <= 32 || error("TBCuda: a region has at most 32 vertices")
     pos = Dict(v => Int32(i - 1) for (i, v) in enumerate(vs))
     leaf_off = Int32[0]; leaf_labels = Int32[]
     for v in vs                                   # vertex tensors
@@ -206,27 +209,40 @@ function branching_table_cuda(g, weights, vs::Vector{Int}, ovs::Vector{Int})
     end
     unit = weights isa TensorBranching.UnitWeight
     wv = unit ? nothing : collect(weights[vs])
-    boundary = Int32[pos[v] for v in ovs]
-    rank = length(boundary)
     net = TbNetwork(n, length(leaf_off) - 1, pointer(leaf_off), pointer(leaf_labels), 0, C_NULL, C_NULL, C_NULL,
                     unit ? C_NULL : Ptr{Cvoid}(pointer(wv)), unit ? Int32(0) : weight_code(eltype(wv)), Int32(0), UInt32(0),
                     Int32(0), C_NULL, C_NULL)
-    keep = Vector{UInt8}(undef, 1 << rank); sizes = Vector{Float64}(undef, 1 << rank)
-    row_off = Vector{Int64}(undef, (1 << rank) + 1); total = Ref{Int64}(0)
-    cfgs = Vector{UInt32}(undef, 4096)
-    GC.@preserve leaf_off leaf_labels wv boundary begin
+    return FlatRegion(leaf_off, leaf_labels, wv, Int32[pos[v] for v in ovs], net)
+end
+
+"the tables of several regions [(vs, ovs), ...] of one graph in the same launches (tb_branching_tables); one row list per region"
+function branching_tables_cuda(g, weights, regions::Vector{Tuple{Vector{Int}, Vector{Int}}})
+    flats = [FlatRegion(g, weights, vs, ovs) for (vs, ovs) in regions]
+    nets = [f.net for f in flats]
+    boff = Int32[0]; blab = Int32[]
+    for f in flats
+        append!(blab, f.boundary); push!(boff, Int32(length(blab)))
+    end
+    base = cumsum([0; [1 << length(f.boundary) for f in flats]])
+    nrows = base[end]
+    keep = Vector{UInt8}(undef, nrows); sizes = Vector{Float64}(undef, nrows)
+    row_off = Vector{Int64}(undef, nrows + 1); total = Ref{Int64}(0)
+    cfgs = Vector{UInt32}(undef, max(4096, 64 * length(flats)))
+    GC.@preserve flats begin
         for attempt in 1:2
-            rc = ccall((:tb_branching_table, LIB), Cint,
-                       (Ptr{Cvoid}, Ref{TbNetwork}, Ptr{Int32}, Int32, Ptr{UInt8}, Ptr{Float64}, Ptr{Int64}, Ptr{UInt32}, Int64, Ref{Int64}),
-                       ctx(), net, boundary, rank, keep, sizes, row_off, cfgs, length(cfgs), total)
+            rc = ccall((:tb_branching_tables, LIB), Cint,
+                       (Ptr{Cvoid}, Ptr{TbNetwork}, Ptr{Int32}, Ptr{Int32}, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Int64}, Ptr{UInt32}, Int64, Ref{Int64}),
+                       ctx(), nets, boff, blab, length(flats), keep, sizes, row_off, cfgs, length(cfgs), total)
             rc == 0 && break
-            (attempt == 1 && total[] > length(cfgs)) || error("tb_branching_table failed ($rc): " *
+            (attempt == 1 && total[] > length(cfgs)) || error("tb_branching_tables failed ($rc): " *
                 unsafe_string(ccall((:tb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
             resize!(cfgs, total[])
         end
     end
-    return [cfgs[row_off[a]+1:row_off[a+1]] for a in 1:(1 << rank) if keep[a] != 0]
+    return [[cfgs[row_off[a]+1:row_off[a+1]] for a in base[i]+1:base[i+1] if keep[a] != 0] for i in eachindex(flats)]
 end
+
+branching_table_cuda(g, weights, vs::Vector{Int}, ovs::Vector{Int}) = branching_tables_cuda(g, weights, [(vs, ovs)])[1]
 
 # The usecuda=true switch position.  The reference defines
 #     contract_slices(::Vector{SlicedBranch}, ::Type, ::Bool)   and   solve_slice(::SlicedBranch, ::Type, ::Bool)
