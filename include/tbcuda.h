@@ -271,8 +271,8 @@ int tb_suggest_slices(tb_ctx* ctx, const tb_network* net, int32_t sc_target, int
 /* Open-boundary contraction (first half): a network created with open_labels (iy non-empty) keeps
  * those labels at the root -- for a region of the graph with its boundary vertices open this root is the tensor of
  * best sizes per boundary configuration that the branching tables of TensorNetworkSolver are read from
- * (src/branch.jl:79, src/types.jl:46; the configuration-enumerating element types of the table itself are NOT
- * implemented).  Contracts the plan and returns the whole root tensor: 2^rank doubles (-inf = tropical zero),
+ * (src/branch.jl:79, src/types.jl:46; the configurations themselves: tb_contract_table, tb_table_configs,
+ * tb_branching_table below).  Contracts the plan and returns the whole root tensor: 2^rank doubles (-inf = tropical zero),
  * layout in out_labels, bit 0 first.  out_data == NULL only queries rank / labels. */
 int tb_contract_tensor(tb_ctx* ctx, tb_plan* plan, double* out_data, int64_t cap, int32_t* out_labels,
                        int32_t* out_rank);
