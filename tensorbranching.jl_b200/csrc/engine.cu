@@ -103,6 +103,22 @@ struct HelperJob {
     }
 };
 
+constexpr size_t kNoDone = (size_t)-1;
+constexpr uint32_t kFusedSmemMax = 96 * 1024;  // dynamic shared memory limit of k_fused_subtrees (descriptors + pool + data)
+struct Launch {
+    int lane;        // stream lane the launch goes to
+    int kind;        // 0 fused, 1 generic, 2 gemm, 3 finalize
+    int vt;
+    size_t inst_off; // byte offset of the instance array in the staging buffer
+    size_t starts_off;
+    size_t counter_off;  // gemm v2: a zeroed u32 tile counter inside the staging buffer
+    size_t done_off = kNoDone;  // dataflow launch: per-instance completion counters inside the staging buffer
+    int n_insts;
+    uint32_t grid;
+    uint32_t smem;
+    double ops = 0, bytes = 0;  // big steps only: tropical ops / bytes moved by the launch (per-launch roofline records)
+};
+
 struct tb_ctx {
     // ---- multi-GPU context (tb_init_multi): one sub-context per device, this object only coordinates
     std::vector<tb_ctx*> subs;
@@ -119,6 +135,26 @@ struct tb_ctx {
     // (arrays keep their capacity), so a steady stream of calls neither allocates nor frees host memory per branch
     void* permute_buf = nullptr;  // tb_permute_bits: source | destination, kept between calls
     size_t permute_cap = 0;
+    // Work lists of resident plans (tb_contract_batch / tb_contract): a group of plans contracted again with the same arena
+    // placement needs the same instance arrays, tile offsets and launch geometry, so they are kept on the device -- a pristine
+    // copy and a working copy (the kernels count tiles and completions down inside it) -- and replayed: no host pass over the
+    // plans, no upload.  Keyed on the exact plan sequence (pointer + upload id), value type, arena and lane state.
+    struct ListCacheEntry {
+        std::vector<uint64_t> key;
+        std::vector<Launch> launches;
+        size_t first_solo_launch = (size_t)-1;
+        void* d_pristine = nullptr;
+        void* d_work = nullptr;
+        size_t bytes = 0;
+        int lane_after = 0;
+        uint64_t used = 0;
+    };
+    std::vector<ListCacheEntry> list_cache;
+    size_t list_cache_bytes = 0;
+    uint64_t list_cache_clock = 0;
+    int64_t list_cache_hits = 0, list_cache_misses = 0;
+    static constexpr size_t kListCacheMaxEntries = 64;
+    static constexpr size_t kListCacheMaxBytes = 512u << 20;
     void* table_buf = nullptr;    // tb_table_configs / tb_branching_table: device scratch and output rows, kept between calls
     size_t table_cap = 0;         // (a host calls them once per branching step: no allocation in steady state)
     void* table_out = nullptr;
@@ -497,6 +533,8 @@ int ensure_results(tb_ctx* ctx, size_t n) {
 }
 
 // upload the descriptor blobs of all plans that are not resident yet (one staging copy per chunk)
+std::atomic<uint64_t> g_upload_uid{0};
+
 int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
     std::vector<tb_plan*> todo;
     std::unordered_set<tb_plan*> seen;
@@ -558,6 +596,7 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
         for (size_t j = first; j < pos; ++j) {
             at[j - first] = o;
             todo[j]->p.d_blob = (uint8_t*)ck->d + ck->used + o;
+            todo[j]->p.upload_uid = g_upload_uid.fetch_add(1, std::memory_order_relaxed) + 1;
             todo[j]->p.owner = ctx;
             link_resident(ctx, todo[j]->p);
             ck->live++;
@@ -576,22 +615,6 @@ int ensure_uploaded(tb_ctx* ctx, tb_plan* const* plans, int64_t n) {
     (void)total;
     return TB_OK;
 }
-
-constexpr size_t kNoDone = (size_t)-1;
-constexpr uint32_t kFusedSmemMax = 96 * 1024;  // dynamic shared memory limit of k_fused_subtrees (descriptors + pool + data)
-struct Launch {
-    int lane;        // stream lane the launch goes to
-    int kind;        // 0 fused, 1 generic, 2 gemm, 3 finalize
-    int vt;
-    size_t inst_off; // byte offset of the instance array in the staging buffer
-    size_t starts_off;
-    size_t counter_off;  // gemm v2: a zeroed u32 tile counter inside the staging buffer
-    size_t done_off = kNoDone;  // dataflow launch: per-instance completion counters inside the staging buffer
-    int n_insts;
-    uint32_t grid;
-    uint32_t smem;
-    double ops = 0, bytes = 0;  // big steps only: tropical ops / bytes moved by the launch (per-launch roofline records)
-};
 
 // CTAs of one persistent dataflow kernel: the kernels of the call's concurrent lanes co-reside, each on its share of the
 // CTA slots, so that the dependency stalls and the thin last levels of one wave are covered by the other waves' tiles
@@ -658,6 +681,119 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     if (idx.empty()) return TB_OK;
     const size_t elem = (size_t)Plan::elem_size_of(vt);
     const bool wide = elem == 8;  // Tropical{Float64} / size+configuration: no persistent GEMM kernel to host a dataflow launch
+    const int max_wave = ctx->call_wave > 0 ? ctx->call_wave : (ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128);
+    const int NL = (ctx->profile_mode == 2 || single_plan_mode) ? 1 : ctx->n_lanes;
+    // ---- launches of a group: shared by the first contraction (lists just built, in a staging slot) and by the replays of
+    // a cached group (lists resident on the device)
+    auto issue_launches = [&](const std::vector<Launch>& launches, size_t first_solo_launch, uint8_t* dbase, tb_ctx::Slot* sl) -> int {
+        int rc = TB_OK;
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+        TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+        for (int l = 1; l < NL; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_copy, 0));
+        // a solo wave of the previous group used the whole arena on the main stream: no side lane may touch its partition
+        // before that wave has finished (the main stream itself is ordered behind it)
+        if (ctx->solo_fence) {
+            for (int l = 1; l < ctx->n_lanes; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
+            ctx->solo_fence = false;
+        }
+        auto prof_event = [&](cudaEvent_t* out) -> int {
+            if (ctx->prof_used == ctx->prof_events.size()) {
+                cudaEvent_t e;
+                TB_CUDA(ctx, cudaEventCreate(&e));
+                ctx->prof_events.push_back(e);
+            }
+            *out = ctx->prof_events[ctx->prof_used++];
+            return TB_OK;
+        };
+        auto join_lanes = [&]() -> int {
+            for (int l = 1; l < NL; ++l) {
+                TB_CUDA(ctx, cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
+                TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
+            }
+            return TB_OK;
+        };
+        bool joined = (NL == 1);
+        for (size_t li = 0; li < launches.size(); ++li) {
+            if (li == first_solo_launch && !joined) {
+                rc = join_lanes();
+                if (rc) return rc;
+                joined = true;
+            }
+            const Launch& L = launches[li];
+            cudaStream_t st = L.lane == 0 ? ctx->stream : ctx->side[L.lane];
+            tb_ctx::ProfRec pr{L.kind, nullptr, nullptr, L.ops, L.bytes, L.n_insts, L.grid};
+            if (ctx->profile_mode) {
+                if ((rc = prof_event(&pr.e0)) || (rc = prof_event(&pr.e1))) return rc;
+                TB_CUDA(ctx, cudaEventRecord(pr.e0, st));
+            }
+            if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, dbase);
+            else if (vt == TB_VALUE_I16X2) launch_one<int16_t>(ctx, L, dbase);
+            else if (vt == TB_VALUE_F64) launch_one<double>(ctx, L, dbase);
+            else if (vt == TB_VALUE_SIZE_CONFIG) launch_one<long long>(ctx, L, dbase);
+            else launch_one<float>(ctx, L, dbase);
+            if (ctx->profile_mode) {
+                TB_CUDA(ctx, cudaEventRecord(pr.e1, st));
+                ctx->prof_recs.push_back(pr);
+            }
+        }
+        // the main stream joins the lanes at the end of every group: the slot event (and the caller's final sync)
+        // then cover every kernel that reads this group's work lists
+        if (!joined) {
+            rc = join_lanes();
+            if (rc) return rc;
+        }
+        TB_CUDA(ctx, cudaGetLastError());
+        if (sl) {
+            TB_CUDA(ctx, cudaEventRecord(sl->ev, ctx->stream));
+            sl->busy = true;
+        }
+        if (first_solo_launch != (size_t)-1) {
+            TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+            ctx->solo_fence = true;
+        }
+        ctx->last_launches += (int64_t)launches.size();
+        return TB_OK;
+    };
+    // ---- cached work lists (resident plans only: the temporaries of the *_networks calls are contracted once)
+    static const bool list_cache_on = [] {
+        const char* e = getenv("TB_NO_LIST_CACHE");  // A/B: rebuild and upload the lists on every call
+        return !(e && atoi(e) != 0);
+    }();
+    bool cacheable = list_cache_on && !ctx->trace_on;
+    for (size_t q = 0; q < idx.size() && cacheable; ++q) cacheable = !plans[idx[q]]->p.temporary;
+    std::vector<uint64_t> key;
+    const int lane_at_entry = ctx->lane_cursor;
+    auto make_key = [&]() {
+        key.clear();
+        key.reserve(8 + idx.size() * 3);
+        key.push_back((uint64_t)vt | ((uint64_t)NL << 8) | ((uint64_t)(ctx->dataflow ? 1 : 0) << 16) | ((uint64_t)(single_plan_mode ? 1 : 0) << 17) |
+                      ((uint64_t)(uint32_t)max_wave << 32));
+        key.push_back((uint64_t)(uintptr_t)ctx->arena);
+        key.push_back((uint64_t)ctx->arena_bytes);
+        key.push_back((uint64_t)lane_at_entry);
+        for (int64_t i : idx) {
+            key.push_back((uint64_t)(ctx->index_map ? ctx->index_map[i] : i));
+            key.push_back((uint64_t)(uintptr_t)plans[i]);
+            key.push_back(plans[i]->p.upload_uid);
+        }
+    };
+    if (cacheable) {
+        make_key();
+        for (auto& e : ctx->list_cache) {
+            if (e.key != key) continue;
+            const double t_l0 = now_ms();
+            e.used = ++ctx->list_cache_clock;
+            ++ctx->list_cache_hits;
+            TB_CUDA(ctx, cudaMemcpyAsync(e.d_work, e.d_pristine, e.bytes, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+            int rc = issue_launches(e.launches, e.first_solo_launch, (uint8_t*)e.d_work, nullptr);
+            if (rc) return rc;
+            ctx->lane_cursor = e.lane_after;
+            if (single_plan_mode) ctx->last_plan_arena_base_elems = 0;
+            ctx->host_ms[3] += now_ms() - t_l0;
+            return TB_OK;
+        }
+        ++ctx->list_cache_misses;
+    }
     // ---- waves
     size_t max_need = 0;
     for (int64_t i : idx) max_need = std::max(max_need, (size_t)plans[i]->p.arena_elems * elem + 256);
@@ -671,8 +807,6 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     } else if (rc) {
         return rc;
     }
-    const int max_wave = ctx->call_wave > 0 ? ctx->call_wave : (ctx->opts.max_wave > 0 ? ctx->opts.max_wave : 128);
-    const int NL = (ctx->profile_mode == 2 || single_plan_mode) ? 1 : ctx->n_lanes;
     // try to grow the arena so that NL full waves fit (bounded by the configured limit)
     {
         std::vector<size_t> needs;
@@ -740,6 +874,7 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             size_t need = ((size_t)P.arena_elems * elem + 255) / 256 * 256;
             if (need > ctx->arena_bytes) {
                 status[i] = TB_ERR_OUT_OF_MEMORY;
+                cacheable = false;  // (a per-branch status is not part of a cached group)
                 continue;
             }
             if (need > cap) {
@@ -997,70 +1132,42 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
     std::memcpy(sl->h, host.data(), host.size());
     // work lists go up on the copy stream (behind the descriptor blobs they point to); every lane waits for them
     TB_CUDA(ctx, cudaMemcpyAsync(sl->d, sl->h, host.size(), cudaMemcpyHostToDevice, ctx->copy_stream));
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
-    TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
-    for (int l = 1; l < NL; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_copy, 0));
-    // a solo wave of the previous group used the whole arena on the main stream: no side lane may touch its partition
-    // before that wave has finished (the main stream itself is ordered behind it)
-    if (ctx->solo_fence) {
-        for (int l = 1; l < ctx->n_lanes; ++l) TB_CUDA(ctx, cudaStreamWaitEvent(ctx->side[l], ctx->ev_fork, 0));
-        ctx->solo_fence = false;
-    }
-    auto prof_event = [&](cudaEvent_t* out) -> int {
-        if (ctx->prof_used == ctx->prof_events.size()) {
-            cudaEvent_t e;
-            TB_CUDA(ctx, cudaEventCreate(&e));
-            ctx->prof_events.push_back(e);
+    if (cacheable) {
+        // keep the lists for the next contraction of this group: the pristine copy is taken on the copy stream before any
+        // kernel of the group (they all wait for the event recorded behind it) starts counting inside the staging buffer
+        while (!ctx->list_cache.empty() && (ctx->list_cache.size() >= tb_ctx::kListCacheMaxEntries ||
+                                            ctx->list_cache_bytes + 2 * host.size() > tb_ctx::kListCacheMaxBytes)) {
+            size_t old = 0;
+            for (size_t q = 1; q < ctx->list_cache.size(); ++q)
+                if (ctx->list_cache[q].used < ctx->list_cache[old].used) old = q;
+            cudaFree(ctx->list_cache[old].d_pristine);  // (cudaFree waits for the work that may still read it)
+            cudaFree(ctx->list_cache[old].d_work);
+            ctx->list_cache_bytes -= 2 * ctx->list_cache[old].bytes;
+            ctx->list_cache.erase(ctx->list_cache.begin() + (std::ptrdiff_t)old);
         }
-        *out = ctx->prof_events[ctx->prof_used++];
-        return TB_OK;
-    };
-    auto join_lanes = [&]() -> int {
-        for (int l = 1; l < NL; ++l) {
-            TB_CUDA(ctx, cudaEventRecord(ctx->ev_join[l], ctx->side[l]));
-            TB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
-        }
-        return TB_OK;
-    };
-    bool joined = (NL == 1);
-    for (size_t li = 0; li < launches.size(); ++li) {
-        if (li == first_solo_launch && !joined) {
-            rc = join_lanes();
-            if (rc) return rc;
-            joined = true;
-        }
-        const Launch& L = launches[li];
-        cudaStream_t st = L.lane == 0 ? ctx->stream : ctx->side[L.lane];
-        tb_ctx::ProfRec pr{L.kind, nullptr, nullptr, L.ops, L.bytes, L.n_insts, L.grid};
-        if (ctx->profile_mode) {
-            if ((rc = prof_event(&pr.e0)) || (rc = prof_event(&pr.e1))) return rc;
-            TB_CUDA(ctx, cudaEventRecord(pr.e0, st));
-        }
-        if (vt == TB_VALUE_I32) launch_one<int32_t>(ctx, L, (uint8_t*)sl->d);
-        else if (vt == TB_VALUE_I16X2) launch_one<int16_t>(ctx, L, (uint8_t*)sl->d);
-        else if (vt == TB_VALUE_F64) launch_one<double>(ctx, L, (uint8_t*)sl->d);
-        else if (vt == TB_VALUE_SIZE_CONFIG) launch_one<long long>(ctx, L, (uint8_t*)sl->d);
-        else launch_one<float>(ctx, L, (uint8_t*)sl->d);
-        if (ctx->profile_mode) {
-            TB_CUDA(ctx, cudaEventRecord(pr.e1, st));
-            ctx->prof_recs.push_back(pr);
+        if (2 * host.size() <= tb_ctx::kListCacheMaxBytes) {
+            tb_ctx::ListCacheEntry e;
+            if (cudaMalloc(&e.d_pristine, host.size()) == cudaSuccess && cudaMalloc(&e.d_work, host.size()) == cudaSuccess) {
+                make_key();  // (the arena may have grown since the lookup)
+                e.key = key;
+                e.launches = launches;
+                e.first_solo_launch = first_solo_launch;
+                e.bytes = host.size();
+                e.lane_after = ctx->lane_cursor;
+                e.used = ++ctx->list_cache_clock;
+                TB_CUDA(ctx, cudaMemcpyAsync(e.d_pristine, sl->d, host.size(), cudaMemcpyDeviceToDevice, ctx->copy_stream));
+                ctx->list_cache_bytes += 2 * host.size();
+                ctx->list_cache.push_back(std::move(e));
+            } else {
+                cudaGetLastError();
+                if (e.d_pristine) cudaFree(e.d_pristine);
+                if (e.d_work) cudaFree(e.d_work);
+            }
         }
     }
-    // the main stream joins the lanes at the end of every group: the slot event (and the caller's final sync)
-    // then cover every kernel that reads this slot's work lists
-    if (!joined) {
-        rc = join_lanes();
-        if (rc) return rc;
-    }
-    TB_CUDA(ctx, cudaGetLastError());
-    TB_CUDA(ctx, cudaEventRecord(sl->ev, ctx->stream));
-    sl->busy = true;
-    if (first_solo_launch != (size_t)-1) {
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-        ctx->solo_fence = true;
-    }
+    rc = issue_launches(launches, first_solo_launch, (uint8_t*)sl->d, sl);
+    if (rc) return rc;
     ctx->host_ms[3] += now_ms() - t_l0;
-    ctx->last_launches += (int64_t)launches.size();
     ctx->h2d_bytes += (int64_t)host.size();
     return TB_OK;
 }
@@ -1287,6 +1394,7 @@ tb_plan* clone_for_assignment(const tb_plan* base, const uint8_t* values) {
     tb_plan* p = new tb_plan(*base);
     p->p.owner = nullptr;
     p->p.d_blob = nullptr;
+    p->p.upload_uid = 0;
     p->p.res_prev = p->p.res_next = nullptr;
     p->p.blob_bytes = 0;
     p->p.assign(values);
@@ -1622,6 +1730,10 @@ int tb_shutdown(tb_ctx* ctx) {
     ctx->resident = nullptr;
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->permute_buf) cudaFree(ctx->permute_buf);
+    for (auto& e : ctx->list_cache) {
+        if (e.d_pristine) cudaFree(e.d_pristine);
+        if (e.d_work) cudaFree(e.d_work);
+    }
     if (ctx->table_buf) cudaFree(ctx->table_buf);
     if (ctx->table_out) cudaFree(ctx->table_out);
     for (auto& c : ctx->chunks)

@@ -243,6 +243,7 @@ struct PlanCompiler : CompilerArrays {
         if (net.n_open < 0 || (net.n_open > 0 && !net.open_labels)) return fail(TB_ERR_BAD_ARGUMENT, "bad open labels");
 
         temporary = (extra_flags & TB_PLAN_TEMPORARY) != 0;
+        P.temporary = temporary;
         estimate_only = (extra_flags & TB_PLAN_ESTIMATE_ONLY) != 0;
         extra_flags &= ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY);
         P.flags = (net.flags & ~(TB_PLAN_TEMPORARY | TB_PLAN_ESTIMATE_ONLY)) | extra_flags;
@@ -1691,6 +1692,7 @@ void Plan::copy_descriptors_to(Plan& dst) const {
     dst.n_leaves = n_leaves;
     dst.n_nodes = n_nodes;
     dst.flags = flags;
+    dst.temporary = temporary;
     dst.value_type = value_type;
     dst.pool = pool;
     dst.patches = patches;

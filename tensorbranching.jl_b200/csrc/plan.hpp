@@ -17,6 +17,7 @@ struct Plan {
     int n_leaves = 0;  // including the synthetic unit leaf of a single-leaf network
     int n_nodes = 0;
     uint32_t flags = 0;
+    bool temporary = false;  // compiled with TB_PLAN_TEMPORARY (a temporary of the *_networks / stream / sliced calls: contracted once)
     int value_type = TB_VALUE_I32;
 
     // per tensor id (leaves, then nodes, then synthetic split-K tensors)
@@ -92,6 +93,7 @@ struct Plan {
     Plan* res_prev = nullptr;  // intrusive list of the plans resident on `owner` (tb_shutdown detaches them, so a plan
     Plan* res_next = nullptr;  // may safely outlive its context)
     void* d_blob = nullptr;
+    uint64_t upload_uid = 0;  // unique per upload of the descriptors (0 = not resident): what cached work lists are keyed on
     size_t blob_bytes = 0;
     size_t sub_blob_off = 0, big_blob_off = 0;
 };
