@@ -1319,7 +1319,7 @@ int finish_sync(tb_ctx* ctx) {
 // rank's shard of a multi-GPU run) is cut into ~2 waves per lane (profiles/s03_wave_lane_sweep_cfg2.jsonl).  Light plans
 // (cfg5: 2^22.5 ops each) are launch-bound: waves of up to 256, one per lane (profiles/s05_wave_sweep_cfg5_cfg2.jsonl:
 // 1.78 ms instead of 2.16 ms for 1 024 plans).  mean_ops <= 0: unknown, treated as heavy.
-int wave_for_call(tb_ctx* ctx, int64_t n, double mean_ops) {
+int wave_for_call(tb_ctx* ctx, int64_t n, double mean_ops, bool resident = false) {
     const bool light = mean_ops > 0 && mean_ops < (double)(1 << 24);
     // dataflow: launch-bound calls -- light plans, or few plans that are not huge (a plan of >= 2^36 ops runs for
     // milliseconds per level: nothing to gain from dropping launches, and the level-synchronous GEMM instance is faster)
@@ -1329,7 +1329,12 @@ int wave_for_call(tb_ctx* ctx, int64_t n, double mean_ops) {
     const int wpl = ctx->waves_per_lane > 0 ? ctx->waves_per_lane : (light ? 1 : 2);
     const int64_t parts = (int64_t)wpl * ctx->n_lanes;
     const int64_t per = (n + parts - 1) / parts;
-    const int64_t wave = std::min<int64_t>(cfg, std::max<int64_t>(16, per));
+    int64_t wave = std::min<int64_t>(cfg, std::max<int64_t>(16, per));
+    // Resident light plans under the dataflow executor: their work lists are replayed from the device (no host pass to hide
+    // behind other waves), and one persistent kernel over up to 1 024 plans keeps every CTA slot fed where four kernels
+    // of 256 plans serialise pairwise (profiles/x4_listcache_wave_sweep.txt: cfg5 1.00 ms -> 0.91 ms)
+    static const bool wave_forced = getenv("TB_WAVE") != nullptr || getenv("TB_WAVES_PER_LANE") != nullptr;
+    if (resident && light && ctx->dataflow && ctx->opts.max_wave <= 0 && !wave_forced) wave = std::min<int64_t>(1024, std::max<int64_t>(16, n));
     ctx->call_lanes = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->n_lanes, (n + wave - 1) / wave));
     return (int)wave;
 }
@@ -1357,7 +1362,7 @@ int batch_enqueue(tb_ctx* ctx, tb_plan* const* plans, int64_t n, int64_t n_resul
         k_fill_double<<<blocks, 256, 0, ctx->stream>>>(ctx->d_results, n_results, -std::numeric_limits<double>::infinity());
     }
     status.assign((size_t)n, TB_OK);
-    const int64_t wave = wave_for_call(ctx, n, mean_plan_ops(plans, 0, n));
+    const int64_t wave = wave_for_call(ctx, n, mean_plan_ops(plans, 0, n), true);
     ctx->call_wave = (int)wave;
     int64_t batch = single ? n : wave;
     for (int64_t lo = 0; lo < n && rc == TB_OK;) {
