@@ -150,6 +150,8 @@ struct tb_ctx {
         uint64_t used = 0;
     };
     std::vector<ListCacheEntry> list_cache;
+    std::vector<uint64_t> list_seen;  // hashes of the groups contracted once: an entry is made when a group comes back, so a
+    size_t list_seen_pos = 0;         // caller that never repeats a group (new plans every call) pays for no device copies
     size_t list_cache_bytes = 0;
     uint64_t list_cache_clock = 0;
     int64_t list_cache_hits = 0, list_cache_misses = 0;
@@ -793,6 +795,15 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             return TB_OK;
         }
         ++ctx->list_cache_misses;
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t w : key) h = (h ^ w) * 1099511628211ull;
+        bool seen = false;
+        for (uint64_t x : ctx->list_seen) seen = seen || x == h;
+        if (!seen) {
+            if (ctx->list_seen.size() < 256) ctx->list_seen.push_back(h);
+            else ctx->list_seen[ctx->list_seen_pos++ % 256] = h;
+            cacheable = false;  // first time: remember the group only
+        }
     }
     // ---- waves
     size_t max_need = 0;

@@ -33,6 +33,9 @@ def test_replays_equal_first_contraction_and_upload_nothing(tb, engine, engine_d
     v0, s0, _ = eng.contract_plans(plans, r)
     assert not s0.any() and np.array_equal(v0, want)
     h2d_first = eng.last_transfers()[0]
+    # (the lists are kept when a group comes back: the second contraction still builds and uploads them)
+    v1, s1, _ = eng.contract_plans(plans, r)
+    assert not s1.any() and np.array_equal(v1, want) and 0 < eng.last_transfers()[0] < h2d_first
     for _ in range(3):
         v, s, mx = eng.contract_plans(plans, r)
         assert not s.any() and np.array_equal(v, want) and mx == want.max()
