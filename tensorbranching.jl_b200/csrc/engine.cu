@@ -779,6 +779,12 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             key.push_back(plans[i]->p.upload_uid);
         }
     };
+    bool remember = false;
+    auto key_hash = [&]() {
+        uint64_t h = 1469598103934665603ull;
+        for (uint64_t w : key) h = (h ^ w) * 1099511628211ull;
+        return h;
+    };
     if (cacheable) {
         make_key();
         for (auto& e : ctx->list_cache) {
@@ -795,14 +801,12 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             return TB_OK;
         }
         ++ctx->list_cache_misses;
-        uint64_t h = 1469598103934665603ull;
-        for (uint64_t w : key) h = (h ^ w) * 1099511628211ull;
         bool seen = false;
+        const uint64_t h = key_hash();
         for (uint64_t x : ctx->list_seen) seen = seen || x == h;
         if (!seen) {
-            if (ctx->list_seen.size() < 256) ctx->list_seen.push_back(h);
-            else ctx->list_seen[ctx->list_seen_pos++ % 256] = h;
-            cacheable = false;  // first time: remember the group only
+            remember = true;    // first time: remember the group only (its hash is taken once the arena has its final
+            cacheable = false;  // place for this call, below)
         }
     }
     // ---- waves
@@ -1133,6 +1137,12 @@ int run_group(tb_ctx* ctx, tb_plan* const* plans, const std::vector<int64_t>& id
             std::memcpy(host.data() + L.inst_off, fin.data(), fin.size() * sizeof(FinalInst));
             launches.push_back(L);
         }
+    }
+    if (remember) {
+        make_key();  // (the arena may have grown since the lookup)
+        const uint64_t h = key_hash();
+        if (ctx->list_seen.size() < 256) ctx->list_seen.push_back(h);
+        else ctx->list_seen[ctx->list_seen_pos++ % 256] = h;
     }
     if (launches.empty()) return TB_OK;
     const double t_l0 = now_ms();
