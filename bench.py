@@ -321,6 +321,10 @@ def workload_config(name, max_branches, scaling, slice_k, weights="unit"):
                           "strong scaling: ONE unit list dealt to the ranks longest-first (LPT) by tropical ops (tb_estimate), every "
                           "rank compiles and contracts only its shard, no data-path collective, one all-reduce(max) over the "
                           "result vector")
+    config["resident"] = ("`value`: compiled plans, their descriptors AND their work lists (instance arrays, tile offsets, launch "
+                          "geometry) are resident on the device; a step replays the lists and runs every contraction again "
+                          "(TB_NO_LIST_CACHE=1 rebuilds and uploads the lists per step).  `e2e` starts from host branch objects: "
+                          "cost estimate, plan compilation, uploads, contraction, results back")
     return config
 
 
