@@ -232,3 +232,29 @@ def test_gpu_region_tables_batched(tb, engine):
     with pytest.raises(tb.TBError) as e:
         engine.region_tables([regions[0][1], regions[1][1]], [regions[0][2], [1, 1]])
     assert e.value.code == -1
+
+
+def test_oracle_set_algebra_random_graphs_and_trees():
+    """the restatement of the reference's ConfigsMax algebra follows ANY tree of ANY graph: random sparse graphs (isolated
+    vertices, several components), random boundary sets, trees from the stand-in optimiser with different seeds"""
+    from workloads import standin_host as H
+    rng = np.random.default_rng(11)
+    for trial in range(25):
+        nv = int(rng.integers(3, 12))
+        m = int(rng.integers(0, 2 * nv))
+        edges = sorted({(int(min(u, v)), int(max(u, v))) for u, v in rng.integers(0, nv, size=(m, 2)) if u != v})
+        w = None if trial % 3 == 0 else rng.integers(1, 4, size=nv).astype(np.int32)
+        root = H.make_root(nv, edges, weights=w, seed=trial)
+        n_open = int(rng.integers(0, min(nv, 5) + 1))
+        open_labels = [int(v) for v in rng.choice(nv, size=n_open, replace=False)]
+        left, right = O.nested_to_postorder(root.tree, len(root.ixs))
+        _, res = O.contract_tree_configs(root.ixs, left, right, w, open_labels)
+        sizes, rows = O.table_configs_bruteforce(nv, edges, w, open_labels)
+        for a in range(1 << n_open):
+            key = tuple((a >> i) & 1 for i in range(n_open))
+            assert res[key][0] == sizes[a], (trial, a)
+            assert sorted(res[key][1]) == rows[a], (trial, a)
+        # every vertex set of the region sits in at most one row, and a row is never empty when its size is finite
+        allsets = [s for r in rows for s in r]
+        assert len(allsets) == len(set(allsets))
+        assert all((len(r) > 0) == bool(np.isfinite(sizes[a])) for a, r in enumerate(rows))
